@@ -1,0 +1,505 @@
+"""Restatement of the pygeotools / GDAL semantics the demcoreg hot path relies on.
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  PARITY UNPINNED.
+
+The reference imports ``pygeotools.lib.{warplib,malib,filtlib,geolib,iolib}``
+(reference ``demcoreg/coreglib.py:12``, ``demcoreg/dem_align.py:17``), an
+un-vendored dependency with no version pin (reference ``setup.py:18``) that is
+not installed here; pygeotools in turn calls GDAL C++ (``gdal.ReprojectImage``
+cubic, ``gdal.DEMProcessing`` Horn).  Each rule below restates the published
+behaviour of the upstream function named in its docstring
+so that it can be audited and corrected if a real install ever appears.
+
+All arrays are float32 row-major, rows north->south, ``True`` = masked.
+"""
+import math
+
+import numpy as np
+import scipy.stats
+
+__all__ = [
+    "MemDataset", "get_res", "ds_extent", "ds_getma", "b_getma", "memwarp_multi",
+    "warp_geometry", "cubic_weights", "gdal_cubic_warp", "gdaldem_slope",
+    "gdaldem_aspect", "gdaldem_mem_ds", "exact_percentile", "fast_median", "mad",
+    "calcperc", "iqr", "robust_spread", "common_mask", "bin_stats", "get_stats",
+    "print_stats", "get_stats_dict", "range_fltr", "mad_fltr", "perc_fltr",
+]
+
+
+# ----------------------------------------------------------------------------
+# iolib: the in-memory dataset (stands in for a gdal MEM Dataset)
+# ----------------------------------------------------------------------------
+class MemDataset(object):
+    """Minimal stand-in for ``gdal.Dataset`` (MEM driver), one float32 band.
+
+    ``gt`` is the GDAL geotransform ``(x0, res, 0, y0, 0, -res)`` (north-up);
+    ``ndv`` the band nodata value.
+    """
+
+    def __init__(self, array, gt, ndv=-9999.0, proj="LOCAL_CS[\"synthetic metres\"]"):
+        self.array = np.ascontiguousarray(array, dtype=np.float32)
+        self.gt = tuple(float(g) for g in gt)
+        self.ndv = float(ndv)
+        self.proj = proj
+
+    @property
+    def RasterXSize(self):
+        return self.array.shape[1]
+
+    @property
+    def RasterYSize(self):
+        return self.array.shape[0]
+
+    def GetGeoTransform(self):
+        return self.gt
+
+    def SetGeoTransform(self, gt):
+        self.gt = tuple(float(g) for g in gt)
+
+    def copy(self):
+        """``iolib.mem_drv.CreateCopy('', ds, 0)``"""
+        return MemDataset(self.array.copy(), self.gt, self.ndv, self.proj)
+
+
+def get_res(ds, square=True):
+    """``geolib.get_res``: pixel size from the geotransform (square => mean of |x|,|y|)."""
+    gt = ds.GetGeoTransform()
+    res = [gt[1], abs(gt[5])]
+    if square:
+        res = [float(np.mean(res))] * 2
+    return res
+
+
+def ds_extent(ds):
+    """``geolib.ds_extent``: ``[xmin, ymin, xmax, ymax]`` of the outer pixel edges."""
+    gt = ds.GetGeoTransform()
+    xmin = gt[0]
+    ymax = gt[3]
+    xmax = gt[0] + gt[1] * ds.RasterXSize
+    ymin = gt[3] + gt[5] * ds.RasterYSize
+    return [xmin, ymin, xmax, ymax]
+
+
+def b_getma_array(a, ndv):
+    """``iolib.b_getma``: ``np.ma.masked_values(band.ReadAsArray(), ndv, shrink=False)``.
+
+    numpy's ``masked_values`` masks ``|x - ndv| <= 1e-8 + 1e-5*|ndv|``.
+    """
+    return np.ma.masked_values(a, ndv, shrink=False)
+
+
+def b_getma(ds):
+    return b_getma_array(ds.array, ds.ndv)
+
+
+def ds_getma(ds, bnum=1):
+    """``iolib.ds_getma(ds, bnum)`` -> masked array of band ``bnum``."""
+    return b_getma(ds)
+
+
+# ----------------------------------------------------------------------------
+# warplib: memwarp_multi + the GDAL cubic warp kernel (pure translation case)
+# ----------------------------------------------------------------------------
+def cubic_weights(d):
+    """GDAL ``GWKCubicComputeWeights`` (Catmull-Rom, a=-0.5), SURVEY A.1, in double."""
+    h = 0.5 * d
+    t = 3.0 * d
+    h2 = h * d
+    c0 = h * (-1.0 + d * (2.0 - d))
+    c1 = 1.0 + h2 * (-5.0 + t)
+    c2 = h * (1.0 + d * (4.0 - t))
+    c3 = h2 * (-1.0 + d)
+    return (c0, c1, c2, c3)
+
+
+def intersection_grid(ds_list, res):
+    """Common grid of ``memwarp_multi(extent='intersection')``: SURVEY Appendix D.
+
+    Returns ``(xmin, ymax, W, H)`` with ``W = int(round((xmax-xmin)/res))``
+    (Python ``round``: exact halves go to the even integer).
+    """
+    exts = [ds_extent(ds) for ds in ds_list]
+    xmin = max(e[0] for e in exts)
+    ymin = max(e[1] for e in exts)
+    xmax = min(e[2] for e in exts)
+    ymax = min(e[3] for e in exts)
+    if xmax <= xmin or ymax <= ymin:
+        raise ValueError("no intersection between input extents")
+    W = int(round((xmax - xmin) / res))
+    H = int(round((ymax - ymin) / res))
+    return xmin, ymax, W, H, [xmin, ymin, xmax, ymax]
+
+
+def warp_geometry(ds, xmin, ymax, res):
+    """Per-raster constants of the translation-only warp.
+
+    ``ox = (xmin - X_A)/res``, ``oy = (Y_A - ymax)/res``; the 4-tap window of output
+    pixel ``(i, j)`` starts at source column ``j + floor(ox) - 1`` / row
+    ``i + floor(oy) - 1``, the fractional parts give the Catmull-Rom weights, and the
+    "nearest" source pixel GDAL tests first is ``(i + floor(oy+0.5), j + floor(ox+0.5))``.
+    """
+    gt = ds.GetGeoTransform()
+    ox = (xmin - gt[0]) / res
+    oy = (gt[3] - ymax) / res
+    fox = math.floor(ox)
+    foy = math.floor(oy)
+    return dict(ix0=int(fox), iy0=int(foy), dx=ox - fox, dy=oy - foy,
+                nx0=int(math.floor(ox + 0.5)), ny0=int(math.floor(oy + 0.5)))
+
+
+def _shifted(P, r0, c0, H, W, pad):
+    """View of the padded array P whose element (i, j) is source pixel (i+r0, j+c0)."""
+    return P[pad + r0: pad + r0 + H, pad + c0: pad + c0 + W]
+
+
+def gdal_cubic_warp(src, src_ndv, geom, H, W, dst_ndv=0.0):
+    """GDAL ``GDALWarpKernel`` cubic ("4-sample") resample for a pure translation.
+
+    Follows SURVEY A.1: nearest source pixel out of bounds / nodata -> dst nodata;
+    all 16 taps in bounds and valid -> separable Catmull-Rom, rows first then
+    columns of the 4 row results, double precision, left-to-right sums, stored as
+    float32; otherwise bilinear over the valid in-bounds pixels of the 2x2
+    neighbourhood (order UL, UR, LR, LL), normalised by the weight sum (nodata
+    when that sum < 1e-5).
+    """
+    src = np.asarray(src, dtype=np.float32)
+    Hs, Ws = src.shape
+    ix0, iy0, dx, dy = geom["ix0"], geom["iy0"], geom["dx"], geom["dy"]
+    nx0, ny0 = geom["nx0"], geom["ny0"]
+    pad = 4 + max(abs(ix0), abs(iy0), abs(nx0), abs(ny0)) + max(0, H + iy0 - Hs, W + ix0 - Ws) + 2
+    P = np.zeros((Hs + 2 * pad, Ws + 2 * pad), dtype=np.float64)
+    V = np.zeros((Hs + 2 * pad, Ws + 2 * pad), dtype=bool)
+    P[pad:pad + Hs, pad:pad + Ws] = src
+    valid_src = ~(np.isnan(src))
+    if src_ndv is not None:
+        valid_src &= (src != np.float32(src_ndv))
+    V[pad:pad + Hs, pad:pad + Ws] = valid_src
+
+    cx = cubic_weights(dx)
+    cy = cubic_weights(dy)
+
+    # nearest-pixel test
+    near_ok = _shifted(V, ny0, nx0, H, W, pad)
+
+    # all-16-valid test
+    all16 = np.ones((H, W), dtype=bool)
+    for r in range(4):
+        for c in range(4):
+            all16 &= _shifted(V, iy0 - 1 + r, ix0 - 1 + c, H, W, pad)
+
+    # separable cubic (rows first), double, left to right
+    def rowpass(r):
+        p = [_shifted(P, iy0 - 1 + r, ix0 - 1 + c, H, W, pad) for c in range(4)]
+        return cx[0] * p[0] + cx[1] * p[1] + cx[2] * p[2] + cx[3] * p[3]
+    v = [rowpass(r) for r in range(4)]
+    cubic = cy[0] * v[0] + cy[1] * v[1] + cy[2] * v[2] + cy[3] * v[3]
+
+    # bilinear fallback over valid pixels of the 2x2 (UL, UR, LR, LL)
+    acc = np.zeros((H, W), dtype=np.float64)
+    div = np.zeros((H, W), dtype=np.float64)
+    for (r, c, w) in ((0, 0, (1.0 - dx) * (1.0 - dy)), (0, 1, dx * (1.0 - dy)),
+                      (1, 1, dx * dy), (1, 0, (1.0 - dx) * dy)):
+        ok = _shifted(V, iy0 + r, ix0 + c, H, W, pad)
+        val = _shifted(P, iy0 + r, ix0 + c, H, W, pad)
+        div = div + np.where(ok, w, 0.0)
+        acc = acc + np.where(ok, val * w, 0.0)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        bil = np.where(div == 1.0, acc, acc / div)
+    bil_ok = div >= 0.00001
+
+    out = np.where(all16, cubic, bil)
+    ok = near_ok & (all16 | bil_ok)
+    out32 = out.astype(np.float32)
+    out32[~ok] = np.float32(dst_ndv)
+    return out32
+
+
+def memwarp_multi(ds_list, res="max", extent="intersection", t_srs=None, r="cubic", dst_ndv=0):
+    """``warplib.memwarp_multi`` for same-SRS inputs.
+
+    A dataset whose resolution and extent already equal the target grid (compared
+    at 1e-3 precision) is returned unchanged (same object); every other one is
+    resampled with the GDAL cubic kernel onto ``[xmin, res, 0, ymax, 0, -res]`` with
+    band nodata ``dst_ndv`` (0 by default, as in pygeotools).
+    """
+    if extent != "intersection" or r != "cubic":
+        raise NotImplementedError("oracle restates extent='intersection', r='cubic' only")
+    res_list = [get_res(ds, square=True)[0] for ds in ds_list]
+    if isinstance(res, str):
+        if res == "max":
+            tres = max(res_list)
+        elif res == "min":
+            tres = min(res_list)
+        elif res == "mean":
+            tres = float(np.mean(res_list))
+        else:
+            raise NotImplementedError(res)
+    else:
+        tres = float(res)
+    for rr in res_list:
+        if abs(rr - tres) > 1e-3 * tres:
+            raise NotImplementedError("oracle restates the equal-resolution (no down-sampling) case only")
+    xmin, ymax, W, H, text = intersection_grid(ds_list, tres)
+    out = []
+    for ds in ds_list:
+        e = ds_extent(ds)
+        same = all(abs(a - b) < 1e-3 for a, b in zip(e, text)) and abs(get_res(ds)[0] - tres) < 1e-3
+        if same:
+            out.append(ds)
+            continue
+        geom = warp_geometry(ds, xmin, ymax, tres)
+        a = gdal_cubic_warp(ds.array, ds.ndv, geom, H, W, dst_ndv=dst_ndv)
+        out.append(MemDataset(a, (xmin, tres, 0.0, ymax, 0.0, -tres), dst_ndv, ds.proj))
+    return out
+
+
+# ----------------------------------------------------------------------------
+# geolib.gdaldem_mem_ds: GDAL DEMProcessing Horn slope / aspect
+# ----------------------------------------------------------------------------
+GDALDEM_NDV = -9999.0
+
+
+def _horn_windows(a, ndv):
+    a = np.asarray(a, dtype=np.float32)
+    H, W = a.shape
+    w = [a[r:H - 2 + r, c:W - 2 + c] for r in range(3) for c in range(3)]
+    bad = np.zeros((H - 2, W - 2), dtype=bool)
+    for k in range(9):
+        bad |= np.isnan(w[k])
+        if ndv is not None:
+            bad |= (w[k] == np.float32(ndv))
+    return w, bad
+
+
+def gdaldem_slope(a, ndv, ewres, nsres, scale=1.0):
+    """``GDALSlopeHornAlg`` (degrees), computeEdges=False: border and nodata windows -> -9999.
+
+    3x3 sums in float32 in GDAL's order, promoted to double, ``atan(sqrt(dx^2+dy^2)/(8*scale))*180/pi`` -> f32.
+    """
+    H, W = a.shape
+    out = np.full((H, W), np.float32(GDALDEM_NDV), dtype=np.float32)
+    if H < 3 or W < 3:
+        return out
+    w, bad = _horn_windows(a, ndv)
+    dxf = ((w[0] + w[3] + w[3] + w[6]) - (w[2] + w[5] + w[5] + w[8]))
+    dyf = ((w[6] + w[7] + w[7] + w[8]) - (w[0] + w[1] + w[1] + w[2]))
+    dx = dxf.astype(np.float64) / ewres
+    dy = dyf.astype(np.float64) / nsres
+    key = dx * dx + dy * dy
+    s = (np.arctan(np.sqrt(key) / (8.0 * scale)) * (180.0 / math.pi)).astype(np.float32)
+    s[bad] = np.float32(GDALDEM_NDV)
+    out[1:-1, 1:-1] = s
+    return out
+
+
+def gdaldem_aspect(a, ndv):
+    """``GDALAspectAlg`` (azimuth degrees in [0,360), flat -> -9999), computeEdges=False.
+
+    ``a = (float)(atan2(dy, -dx)/(pi/180))`` then, in float32, ``a > 90 ? 450 - a : 90 - a``; 360 -> 0.
+    """
+    H, W = a.shape
+    out = np.full((H, W), np.float32(GDALDEM_NDV), dtype=np.float32)
+    if H < 3 or W < 3:
+        return out
+    w, bad = _horn_windows(a, ndv)
+    dxf = ((w[2] + w[5] + w[5] + w[8]) - (w[0] + w[3] + w[3] + w[6]))
+    dyf = ((w[6] + w[7] + w[7] + w[8]) - (w[0] + w[1] + w[1] + w[2]))
+    dx = dxf.astype(np.float64)
+    dy = dyf.astype(np.float64)
+    asp = (np.arctan2(dy, -dx) / (math.pi / 180.0)).astype(np.float32)
+    flat = (dx == 0) & (dy == 0)
+    asp = np.where(asp > np.float32(90.0), np.float32(450.0) - asp, np.float32(90.0) - asp).astype(np.float32)
+    asp[asp == np.float32(360.0)] = np.float32(0.0)
+    asp[flat | bad] = np.float32(GDALDEM_NDV)
+    out[1:-1, 1:-1] = asp
+    return out
+
+
+def gdaldem_mem_ds(ds, processing="slope", returnma=True, computeEdges=False):
+    """``geolib.gdaldem_mem_ds``: DEMProcessing to MEM, output nodata -9999, as a masked array."""
+    if computeEdges:
+        raise NotImplementedError
+    gt = ds.GetGeoTransform()
+    if processing == "slope":
+        a = gdaldem_slope(ds.array, ds.ndv, gt[1], gt[5])
+    elif processing == "aspect":
+        a = gdaldem_aspect(ds.array, ds.ndv)
+    else:
+        raise NotImplementedError(processing)
+    out = MemDataset(a, gt, GDALDEM_NDV, ds.proj)
+    if returnma:
+        return ds_getma(out)
+    return out
+
+
+# ----------------------------------------------------------------------------
+# malib
+# ----------------------------------------------------------------------------
+def exact_percentile(x, q):
+    """``np.percentile(x, q)`` (linear method) with an exact integer rank.
+
+    The virtual index ``(n-1)*q/100`` is evaluated in float64 (numpy 1.x behaviour,
+    contemporary with the reference; numpy >= 2 evaluates it in the data dtype,
+    which mis-ranks float32 inputs beyond 2**24 elements).  Interpolation is
+    numpy's ``_lerp`` in the data dtype: ``a + (b-a)*g``, or ``b - (b-a)*(1-g)`` when g >= 0.5.
+    """
+    x = np.asarray(x)
+    n = x.size
+    if n == 0:
+        raise ValueError("empty input")
+    vi = (n - 1) * (float(q) / 100.0)
+    lo = int(math.floor(vi))
+    hi = min(lo + 1, n - 1)
+    g = vi - lo
+    part = np.partition(x.ravel(), (lo, hi))
+    a = part[lo]
+    b = part[hi]
+    dt = x.dtype.type
+    d = dt(b - a)
+    if g >= 0.5:
+        return dt(b - d * dt(1.0 - g))
+    return dt(a + d * dt(g))
+
+
+def fast_median(a):
+    """``malib.fast_median``: ``np.percentile(a.compressed(), 50)``; masked if empty."""
+    a = np.ma.asarray(a)
+    if a.count() > 0:
+        return exact_percentile(a.compressed(), 50)
+    return np.ma.masked
+
+
+def mad(a, c=1.4826, return_med=False):
+    """``malib.mad`` (axis=None): ``c * median(|a - median(a)|)``."""
+    a = np.ma.asarray(a)
+    if a.count() > 0:
+        med = fast_median(a)
+        out = fast_median(np.fabs(a - med)) * c
+    else:
+        out = np.ma.masked
+        med = np.ma.masked
+    if return_med:
+        return out, med
+    return out
+
+
+def calcperc(b, perc=(0.1, 99.9)):
+    """``malib.calcperc``: low/high percentile of the compressed data, (0,0) if empty."""
+    b = np.ma.asarray(b)
+    if b.count() > 0:
+        c = b.compressed()
+        return (exact_percentile(c, perc[0]), exact_percentile(c, perc[1]))
+    return (0, 0)
+
+
+def iqr(b, perc=(25, 75)):
+    """``malib.iqr`` -> (q1, q2, q2-q1)."""
+    lo, hi = calcperc(b, perc)
+    return lo, hi, hi - lo
+
+
+def robust_spread(b, perc=(15.9, 84.1)):
+    """``malib.robust_spread`` -> (p16, p84, |p84 - p16|)."""
+    lo, hi = calcperc(b, perc)
+    return lo, hi, abs(hi - lo)
+
+
+def common_mask(ma_list):
+    """``malib.common_mask``: union of the masks."""
+    a = np.ma.array(ma_list, shrink=False)
+    return np.ma.getmaskarray(a).any(axis=0)
+
+
+def bin_stats(x, y, stat="median", nbins=360, bin_range=None):
+    """``malib.bin_stats`` = ``scipy.stats.binned_statistic`` + masked_invalid + centres."""
+    if bin_range is None:
+        bin_range = (x.min(), x.max())
+    bin_stat, bin_edges, binnumber = scipy.stats.binned_statistic(
+        x, y, statistic=stat, bins=nbins, range=bin_range)
+    bin_width = bin_edges[1] - bin_edges[0]
+    bin_centers = bin_edges[1:] - bin_width / 2.0
+    return np.ma.masked_invalid(bin_stat), bin_edges, bin_centers
+
+
+def _mode_subsample(ac):
+    """``scipy.stats.mstats.mode`` equivalent on a compressed 1-D array: smallest most-frequent value."""
+    if ac.size == 0:
+        return np.nan
+    vals, counts = np.unique(ac, return_counts=True)
+    return vals[np.argmax(counts)]
+
+
+def get_stats(a, full=False, with_mode=True):
+    """``malib.get_stats``.
+
+    Returns ``(count, min, max, mean64, std64, med, nmad, q1, q2, iqr, mode, p16, p84, spread)``.
+    When ``count >= 4e6`` and not ``full`` the order statistics are taken on the
+    strided subsample ``compressed()[::int(around(count/4e6))]``.
+    """
+    a = np.ma.asarray(a)
+    thresh = 4E6
+    count = a.count()
+    if full or count < thresh:
+        q = (iqr(a))
+        p16, p84, spread = robust_spread(a)
+        med = fast_median(a)
+        nmad = mad(a)
+        mode = _mode_subsample(a.compressed()) if with_mode else np.nan
+    else:
+        ac = a.compressed()
+        stride = int(np.around(ac.size / thresh))
+        ac = np.ma.array(ac[::stride])
+        q = (iqr(ac))
+        p16, p84, spread = robust_spread(ac)
+        med = fast_median(ac)
+        nmad = mad(ac)
+        mode = _mode_subsample(ac.compressed()) if with_mode else np.nan
+    stats = (count, a.min(), a.max(), a.mean(dtype="float64"), a.std(dtype="float64"),
+             med, nmad, q[0], q[1], q[2], mode, p16, p84, spread)
+    return stats
+
+
+def print_stats(a, full=False, with_mode=True):
+    """``malib.print_stats``: get_stats + a print; index 5 is the median."""
+    return get_stats(a, full=full, with_mode=with_mode)
+
+
+def get_stats_dict(a, full=True):
+    """``malib.get_stats_dict`` -> dict(count,min,max,ptp,mean,std,nmad,med,median,p16,p84,spread,mode)."""
+    d = {}
+    a = np.ma.asarray(a)
+    if a.count() > 0:
+        s = get_stats(a, full=full)
+        d["count"] = int(s[0])
+        d["min"] = float(s[1])
+        d["max"] = float(s[2])
+        d["ptp"] = float(s[2] - s[1])
+        d["mean"] = float(s[3])
+        d["std"] = float(s[4])
+        d["nmad"] = float(s[6])
+        d["med"] = float(s[5])
+        d["median"] = float(s[5])
+        d["p16"] = float(s[11])
+        d["p84"] = float(s[12])
+        d["spread"] = float(s[13])
+        d["mode"] = float(s[10])
+    return d
+
+
+# ----------------------------------------------------------------------------
+# filtlib
+# ----------------------------------------------------------------------------
+def range_fltr(dem, rangelim):
+    """``filtlib.range_fltr`` = ``np.ma.masked_outside`` (inclusive keep)."""
+    return np.ma.masked_outside(dem, *rangelim)
+
+
+def mad_fltr(dem, n=3):
+    """``filtlib.mad_fltr``: keep ``med - n*nmad <= x <= med + n*nmad``."""
+    m, med = mad(dem, return_med=True)
+    return range_fltr(dem, (med - n * m, med + n * m))
+
+
+def perc_fltr(dem, perc=(1.0, 99.0)):
+    """``filtlib.perc_fltr``."""
+    return range_fltr(dem, calcperc(dem, perc))
