@@ -1,0 +1,124 @@
+"""ctypes binding of ``libdemcoreg_b200.so`` (the C-ABI declared in ``include/demcoreg_b200.h``).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is
+visible when a compute entry point is called, this module raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libdemcoreg_b200.so")
+
+NBINS = 360
+M_BASE, M_MAXDZ, M_MAD, M_SLOPE, M_ASPECT = 0x01, 0x02, 0x04, 0x08, 0x10
+M_DIFF = M_BASE | M_MAXDZ | M_MAD | M_SLOPE
+
+
+class RasterDesc(C.Structure):
+    _fields_ = [("gt", C.c_double * 6), ("width", C.c_int32), ("height", C.c_int32),
+                ("ndv", C.c_double), ("has_ndv", C.c_int32), ("_pad", C.c_int32)]
+
+
+class WarpGeom(C.Structure):
+    _fields_ = [("ix0", C.c_int32), ("iy0", C.c_int32), ("nx0", C.c_int32), ("ny0", C.c_int32),
+                ("fx", C.c_double), ("fy", C.c_double), ("wx", C.c_double * 4), ("wy", C.c_double * 4),
+                ("identity", C.c_int32), ("_pad", C.c_int32)]
+
+
+class Grid(C.Structure):
+    _fields_ = [("gt", C.c_double * 6), ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class FrontArgs(C.Structure):
+    _fields_ = [
+        ("ref", C.c_void_p), ("ref_stride", C.c_int64), ("ref_desc", RasterDesc), ("ref_geom", WarpGeom),
+        ("src", C.c_void_p), ("src_stride", C.c_int64), ("src_desc", RasterDesc), ("src_geom", WarpGeom),
+        ("smask", C.c_void_p), ("smask_stride", C.c_int64), ("smask_h", C.c_int32), ("smask_w", C.c_int32),
+        ("smask_nx0", C.c_int32), ("smask_ny0", C.c_int32),
+        ("h", C.c_int32), ("w", C.c_int32),
+        ("ewres", C.c_double), ("nsres", C.c_double), ("dst_ndv", C.c_double),
+        ("max_dz", C.c_float), ("use_max_dz", C.c_int32), ("slope_lo", C.c_float), ("slope_hi", C.c_float),
+        ("dh", C.c_void_p), ("slope", C.c_void_p), ("aspect", C.c_void_p), ("maskbits", C.c_void_p),
+        ("ref_w", C.c_void_p), ("src_w", C.c_void_p),
+    ]
+
+
+class NuthStats(C.Structure):
+    _fields_ = [("n_common", C.c_int64), ("n_final", C.c_int64), ("mean_y", C.c_float), ("std_y", C.c_float),
+                ("rmin", C.c_float), ("rmax", C.c_float), ("bin_count", C.c_int64 * NBINS),
+                ("bin_med", C.c_float * NBINS)]
+
+
+class IterResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("n_valid_bins", C.c_int32), ("count_base", C.c_int64),
+                ("count_maxdz", C.c_int64), ("count_mad", C.c_int64), ("count_final", C.c_int64),
+                ("count_slope", C.c_int64), ("stats_stride", C.c_int64),
+                ("med1", C.c_float), ("nmad1", C.c_float), ("mad_lo", C.c_float), ("mad_hi", C.c_float),
+                ("dz_med", C.c_float), ("med_dh", C.c_float), ("med_slope", C.c_float), ("c_seed", C.c_float),
+                ("nuth", NuthStats), ("fit", C.c_double * 3), ("dx", C.c_double), ("dy", C.c_double),
+                ("dz", C.c_double)]
+
+
+# every symbol include/demcoreg_b200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "dcr_last_error": (C.c_char_p, []),
+    "dcr_version": (C.c_int, []),
+    "dcr_struct_size": (C.c_int, [C.c_int]),
+    "dcr_plan_intersection": (C.c_int, [C.POINTER(RasterDesc), C.POINTER(RasterDesc), C.c_double, C.POINTER(Grid),
+                                        C.POINTER(WarpGeom), C.POINTER(WarpGeom)]),
+    "dcr_plan_onto_grid": (C.c_int, [C.POINTER(RasterDesc), C.POINTER(Grid), C.POINTER(WarpGeom)]),
+    "dcr_warp_cubic": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_int, C.POINTER(WarpGeom), _P,
+                                 C.c_int, C.c_int, C.c_int64, C.c_float, _P]),
+    "dcr_horn_slope_aspect": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_int, C.c_double, C.c_double,
+                                        _P, _P, _P]),
+    "dcr_warp_diff_horn": (C.c_int, [C.POINTER(FrontArgs), _P]),
+    "dcr_select_workspace_bytes": (C.c_size_t, []),
+    "dcr_select_quantiles": (C.c_int, [_P, _P, C.c_uint32, C.c_int64, C.c_int, C.c_float, C.POINTER(C.c_double),
+                                       C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int64), _P, C.c_size_t, _P]),
+    "dcr_moments": (C.c_int, [_P, _P, C.c_uint32, C.c_int64, C.POINTER(C.c_double), _P, C.c_size_t, _P]),
+    "dcr_compress_strided": (C.c_int, [_P, _P, C.c_uint32, C.c_int64, C.c_int64, _P, C.c_int64,
+                                       C.POINTER(C.c_int64), _P, C.c_size_t, _P]),
+    "dcr_nuth_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "dcr_nuth_bin_stats": (C.c_int, [_P, _P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int64, C.c_int,
+                                     C.POINTER(NuthStats), _P, C.c_size_t, _P]),
+    "dcr_fit_nuth": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]),
+    "dcr_apply_z_shift": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_float, _P, _P]),
+    "dcr_iteration_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "dcr_nuth_iteration": (C.c_int, [C.POINTER(FrontArgs), C.c_int, C.POINTER(IterResult), _P, C.c_size_t, _P]),
+}
+
+_lib = None
+
+
+class DcrError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DcrError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(demcoreg_b200 has no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().dcr_last_error()
+        raise DcrError("demcoreg_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise DcrError("demcoreg_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch

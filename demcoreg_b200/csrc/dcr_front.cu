@@ -1,0 +1,629 @@
+// K1 (cubic warp), K2 (Horn slope/aspect) and the fused K1+K2 front end of one iteration.
+//
+// Replaces, for the translation-only case of the dem_align loop:
+//   warplib.memwarp_multi -> gdal.ReprojectImage(GRA_Cubic)   (reference dem_align.py:66-67)
+//   iolib.ds_getma, diff = src - ref, static mask               (reference dem_align.py:79-86)
+//   np.ma.masked_outside(diff, -max_dz, max_dz)                 (reference dem_align.py:39)
+//   geolib.gdaldem_mem_ds('slope'|'aspect') + range_fltr        (reference dem_align.py:51-60, 100, 107)
+//
+// Arithmetic follows SURVEY.md Appendix A.1/A.2: Catmull-Rom rows-then-columns in FP64 with
+// left-to-right sums and NO fused multiply-add (file compiled with -fmad=false), one rounding to
+// FP32; Horn 3x3 sums in FP32 in GDAL's order, FP64 atan/atan2, one rounding to FP32.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include "dcr_common.cuh"
+#include "dcr_internal.cuh"
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void dcr_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* dcr_last_error(void) { return g_err; }
+extern "C" int dcr_version(void) { return 100; }
+extern "C" int dcr_struct_size(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(dcr_raster_desc);
+        case 1: return (int)sizeof(dcr_warp_geom);
+        case 2: return (int)sizeof(dcr_grid);
+        case 3: return (int)sizeof(dcr_front_args);
+        case 4: return (int)sizeof(dcr_nuth_stats);
+        case 5: return (int)sizeof(dcr_iter_result);
+        default: return -1;
+    }
+}
+
+int dcr_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+            n = v;
+        else
+            n = DCR_NSM_DEFAULT;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// geometry (host): SURVEY Appendix D
+// ------------------------------------------------------------------------------------------
+static void cubic_weights(double d, double c[4]) {
+    // GDAL GWKCubicComputeWeights (Catmull-Rom, a = -0.5)
+    double h = 0.5 * d, t = 3.0 * d, h2 = h * d;
+    c[0] = h * (-1.0 + d * (2.0 - d));
+    c[1] = 1.0 + h2 * (-5.0 + t);
+    c[2] = h * (1.0 + d * (4.0 - t));
+    c[3] = h2 * (-1.0 + d);
+}
+
+static void extent_of(const dcr_raster_desc* r, double e[4]) {
+    e[0] = r->gt[0];
+    e[3] = r->gt[3];
+    e[2] = r->gt[0] + r->gt[1] * r->width;
+    e[1] = r->gt[3] + r->gt[5] * r->height;
+}
+
+static double square_res(const dcr_raster_desc* r) { return (r->gt[1] + fabs(r->gt[5])) / 2.0; }
+
+extern "C" int dcr_plan_onto_grid(const dcr_raster_desc* a, const dcr_grid* grid, dcr_warp_geom* g) {
+    DCR_ARG(a && grid && g, "null pointer");
+    const double res = grid->gt[1];
+    const double xmin = grid->gt[0], ymax = grid->gt[3];
+    double ox = (xmin - a->gt[0]) / res;
+    double oy = (a->gt[3] - ymax) / res;
+    double fox = floor(ox), foy = floor(oy);
+    memset(g, 0, sizeof(*g));
+    g->ix0 = (int32_t)fox;
+    g->iy0 = (int32_t)foy;
+    g->fx = ox - fox;
+    g->fy = oy - foy;
+    g->nx0 = (int32_t)floor(ox + 0.5);
+    g->ny0 = (int32_t)floor(oy + 0.5);
+    cubic_weights(g->fx, g->wx);
+    cubic_weights(g->fy, g->wy);
+    double e[4];
+    extent_of(a, e);
+    const double te[4] = {xmin, ymax - res * grid->height, xmin + res * grid->width, ymax};
+    // pygeotools compares extents/resolution at 1e-3 precision; equal -> dataset returned unchanged
+    bool same = fabs(square_res(a) - res) < 1e-3;
+    // the target extent of memwarp_multi is the un-rounded intersection; the caller passes it through
+    // dcr_plan_intersection, which sets `identity` itself.  Here: exact-lattice test only.
+    for (int k = 0; k < 4; ++k) same = same && fabs(e[k] - te[k]) < 1e-3;
+    g->identity = same ? 1 : 0;
+    if (same) {
+        g->ix0 = g->iy0 = g->nx0 = g->ny0 = 0;
+        g->fx = g->fy = 0.0;
+        cubic_weights(0.0, g->wx);
+        cubic_weights(0.0, g->wy);
+    }
+    return 0;
+}
+
+extern "C" int dcr_plan_intersection(const dcr_raster_desc* a, const dcr_raster_desc* b, double res,
+                                     dcr_grid* grid, dcr_warp_geom* ga, dcr_warp_geom* gb) {
+    DCR_ARG(a && b && grid && ga && gb, "null pointer");
+    double ra = square_res(a), rb = square_res(b);
+    double tres = res > 0 ? res : (ra > rb ? ra : rb);
+    if (fabs(ra - tres) > 1e-3 * tres || fabs(rb - tres) > 1e-3 * tres) {
+        dcr_set_error("input resolutions differ (%.6f, %.6f, target %.6f): the down-sampling warp is out of scope",
+                      ra, rb, tres);
+        return -3;
+    }
+    double ea[4], eb[4];
+    extent_of(a, ea);
+    extent_of(b, eb);
+    double xmin = ea[0] > eb[0] ? ea[0] : eb[0];
+    double ymin = ea[1] > eb[1] ? ea[1] : eb[1];
+    double xmax = ea[2] < eb[2] ? ea[2] : eb[2];
+    double ymax = ea[3] < eb[3] ? ea[3] : eb[3];
+    if (!(xmax > xmin) || !(ymax > ymin)) {
+        dcr_set_error("no intersection between input extents");
+        return -2;
+    }
+    grid->gt[0] = xmin;
+    grid->gt[1] = tres;
+    grid->gt[2] = 0.0;
+    grid->gt[3] = ymax;
+    grid->gt[4] = 0.0;
+    grid->gt[5] = -tres;
+    // Python round(): half to even == nearbyint in the default rounding mode
+    grid->width = (int32_t)nearbyint((xmax - xmin) / tres);
+    grid->height = (int32_t)nearbyint((ymax - ymin) / tres);
+    const double te[4] = {xmin, ymin, xmax, ymax};
+    const dcr_raster_desc* rs[2] = {a, b};
+    dcr_warp_geom* gs[2] = {ga, gb};
+    for (int k = 0; k < 2; ++k) {
+        int rc = dcr_plan_onto_grid(rs[k], grid, gs[k]);
+        if (rc) return rc;
+        double e[4];
+        extent_of(rs[k], e);
+        bool same = fabs(square_res(rs[k]) - tres) < 1e-3;
+        for (int m = 0; m < 4; ++m) same = same && fabs(e[m] - te[m]) < 1e-3;
+        gs[k]->identity = same ? 1 : 0;
+        if (same) {
+            gs[k]->ix0 = gs[k]->iy0 = gs[k]->nx0 = gs[k]->ny0 = 0;
+            gs[k]->fx = gs[k]->fy = 0.0;
+            cubic_weights(0.0, gs[k]->wx);
+            cubic_weights(0.0, gs[k]->wy);
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// device pieces shared by the kernels
+// ------------------------------------------------------------------------------------------
+struct DevGeom {
+    int ix0, iy0, nx0, ny0;
+    double fx, fy;
+    double wx[4], wy[4];
+    int hs, ws;
+    long long stride;
+    float ndv;
+    int has_ndv;
+};
+
+static DevGeom make_devgeom(const dcr_warp_geom& g, int hs, int ws, long long stride, double ndv, int has_ndv) {
+    DevGeom d;
+    d.ix0 = g.ix0; d.iy0 = g.iy0; d.nx0 = g.nx0; d.ny0 = g.ny0;
+    d.fx = g.fx; d.fy = g.fy;
+    for (int k = 0; k < 4; ++k) { d.wx[k] = g.wx[k]; d.wy[k] = g.wy[k]; }
+    d.hs = hs; d.ws = ws; d.stride = stride; d.ndv = (float)ndv; d.has_ndv = has_ndv;
+    return d;
+}
+
+// source pixel -> value, NaN when out of bounds / nodata / NaN
+__device__ __forceinline__ float load_px(const float* __restrict__ p, const DevGeom& g, int r, int c) {
+    if (r < 0 || c < 0 || r >= g.hs || c >= g.ws) return __int_as_float(0x7fc00000);
+    float v = __ldg(p + (long long)r * g.stride + c);
+    if (g.has_ndv && v == g.ndv) return __int_as_float(0x7fc00000);
+    return v;
+}
+
+// x pass of the separable cubic: left-to-right FP64 sum of 4 taps
+__device__ __forceinline__ double xpass(const double w[4], float p0, float p1, float p2, float p3) {
+    return w[0] * (double)p0 + w[1] * (double)p1 + w[2] * (double)p2 + w[3] * (double)p3;
+}
+__device__ __forceinline__ double ypass(const double w[4], double v0, double v1, double v2, double v3) {
+    return w[0] * v0 + w[1] * v1 + w[2] * v2 + w[3] * v3;
+}
+
+// GDAL GWKBilinearResample4Sample over the valid pixels of the 2x2 (UL, UR, LR, LL); NaN = fail.
+// near = the nearest source pixel GDAL tests first (NaN -> dst nodata).
+__device__ __noinline__ float bilinear_fallback(float ul, float ur, float lr, float ll, float nearest,
+                                                double fx, double fy) {
+    if (isnan(nearest)) return nearest;
+    double acc = 0.0, div = 0.0;
+    const double w_ul = (1.0 - fx) * (1.0 - fy), w_ur = fx * (1.0 - fy), w_lr = fx * fy, w_ll = (1.0 - fx) * fy;
+    if (!isnan(ul)) { div = div + w_ul; acc = acc + (double)ul * w_ul; }
+    if (!isnan(ur)) { div = div + w_ur; acc = acc + (double)ur * w_ur; }
+    if (!isnan(lr)) { div = div + w_lr; acc = acc + (double)lr * w_lr; }
+    if (!isnan(ll)) { div = div + w_ll; acc = acc + (double)ll * w_ll; }
+    if (!(div >= 0.00001)) return __int_as_float(0x7fc00000);
+    double r = (div == 1.0) ? acc : acc / div;
+    return (float)r;
+}
+
+// Horn slope + aspect from a 3x3 float32 window (GDAL GDALSlopeHornAlg / GDALAspectAlg), A.2.
+// Returns false when any input is NaN (nodata).  aspect = NaN for flat.
+__device__ __forceinline__ bool horn(float w0, float w1, float w2, float w3, float w4, float w5, float w6,
+                                     float w7, float w8, double ewres, double nsres, bool want_slope,
+                                     bool want_aspect, float* slope, float* aspect) {
+    (void)w4;
+    float s = ((w0 + w1) + (w2 + w3)) + ((w4 + w5) + (w6 + w7)) + w8;  // NaN probe only
+    if (isnan(s)) return false;
+    const float a = (w0 + w3 + w3 + w6);
+    const float b = (w2 + w5 + w5 + w8);
+    const float c = (w6 + w7 + w7 + w8);
+    const float d = (w0 + w1 + w1 + w2);
+    const float dyf = c - d;
+    if (want_slope) {
+        const float dxf = a - b;
+        double dx = (double)dxf / ewres;
+        double dy = (double)dyf / nsres;
+        double key = dx * dx + dy * dy;
+        *slope = (float)(atan(sqrt(key) / 8.0) * (180.0 / M_PI));
+    }
+    if (want_aspect) {
+        const float dxf = b - a;
+        double dx = (double)dxf, dy = (double)dyf;
+        if (dx == 0.0 && dy == 0.0) {
+            *aspect = __int_as_float(0x7fc00000);
+        } else {
+            float asp = (float)(atan2(dy, -dx) / (M_PI / 180.0));
+            asp = (asp > 90.0f) ? __fsub_rn(450.0f, asp) : __fsub_rn(90.0f, asp);
+            if (asp == 360.0f) asp = 0.0f;
+            *aspect = asp;
+        }
+    }
+    return true;
+}
+
+#define DCR_GDALDEM_NDV (-9999.0f)
+
+// ------------------------------------------------------------------------------------------
+// K1 standalone: one thread per output pixel, taps through the read-only L1 path
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_px_global(const float* __restrict__ p, const DevGeom& g, int i, int j) {
+    const int r0 = i + g.iy0 - 1, c0 = j + g.ix0 - 1;
+    double v[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        v[r] = xpass(g.wx, load_px(p, g, r0 + r, c0), load_px(p, g, r0 + r, c0 + 1), load_px(p, g, r0 + r, c0 + 2),
+                     load_px(p, g, r0 + r, c0 + 3));
+    double o = ypass(g.wy, v[0], v[1], v[2], v[3]);
+    if (isnan(o)) {
+        return bilinear_fallback(load_px(p, g, r0 + 1, c0 + 1), load_px(p, g, r0 + 1, c0 + 2),
+                                 load_px(p, g, r0 + 2, c0 + 2), load_px(p, g, r0 + 2, c0 + 1),
+                                 load_px(p, g, i + g.ny0, j + g.nx0), g.fx, g.fy);
+    }
+    // nearest-pixel test precedes everything in GDAL
+    if (isnan(load_px(p, g, i + g.ny0, j + g.nx0))) return __int_as_float(0x7fc00000);
+    return (float)o;
+}
+
+__global__ void __launch_bounds__(256) warp_cubic_kernel(const float* __restrict__ src, DevGeom g, float* __restrict__ dst,
+                                                         int h, int w, long long dstride, float dst_ndv) {
+    const int j = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int i = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (i >= h || j >= w) return;
+    float v = warp_px_global(src, g, i, j);
+    dst[(long long)i * dstride + j] = isnan(v) ? dst_ndv : v;
+}
+
+extern "C" int dcr_warp_cubic(const float* src, int src_h, int src_w, int64_t src_stride, double src_ndv, int has_ndv,
+                              const dcr_warp_geom* geom, float* dst, int h, int w, int64_t dst_stride, float dst_ndv,
+                              void* stream) {
+    DCR_ARG(src && dst && geom, "null pointer");
+    DCR_ARG(h > 0 && w > 0 && src_h > 0 && src_w > 0, "empty raster");
+    DevGeom g = make_devgeom(*geom, src_h, src_w, src_stride, src_ndv, has_ndv);
+    dim3 grid((w + 63) / 64, (h + 3) / 4);
+    warp_cubic_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, g, dst, h, w, dst_stride, dst_ndv);
+    DCR_LAUNCH_OK("warp_cubic_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 standalone: Horn slope/aspect, tile + halo staged in shared memory
+// ------------------------------------------------------------------------------------------
+#define K2_TW 64
+#define K2_TH 16
+__global__ void __launch_bounds__(256) horn_kernel(const float* __restrict__ dem, int h, int w, long long stride, float ndv,
+                                                   int has_ndv, double ewres, double nsres, float* __restrict__ slope,
+                                                   float* __restrict__ aspect) {
+    __shared__ float t[K2_TH + 2][K2_TW + 2];
+    const int tj0 = blockIdx.x * K2_TW, ti0 = blockIdx.y * K2_TH;
+    for (int k = threadIdx.x; k < (K2_TH + 2) * (K2_TW + 2); k += 256) {
+        int r = k / (K2_TW + 2), c = k % (K2_TW + 2);
+        int gi = ti0 - 1 + r, gj = tj0 - 1 + c;
+        float v = __int_as_float(0x7fc00000);
+        if (gi >= 0 && gj >= 0 && gi < h && gj < w) {
+            v = __ldg(dem + (long long)gi * stride + gj);
+            if (has_ndv && v == ndv) v = __int_as_float(0x7fc00000);
+        }
+        t[r][c] = v;
+    }
+    __syncthreads();
+    const int c = threadIdx.x & 63;
+    for (int r = threadIdx.x >> 6; r < K2_TH; r += 4) {
+        const int i = ti0 + r, j = tj0 + c;
+        if (i >= h || j >= w) continue;
+        float s = DCR_GDALDEM_NDV, a = DCR_GDALDEM_NDV;
+        if (i > 0 && j > 0 && i < h - 1 && j < w - 1) {
+            float sv, av;
+            if (horn(t[r][c], t[r][c + 1], t[r][c + 2], t[r + 1][c], t[r + 1][c + 1], t[r + 1][c + 2], t[r + 2][c],
+                     t[r + 2][c + 1], t[r + 2][c + 2], ewres, nsres, slope != nullptr, aspect != nullptr, &sv, &av)) {
+                if (slope) s = sv;
+                if (aspect) a = isnan(av) ? DCR_GDALDEM_NDV : av;
+            }
+        }
+        if (slope) slope[(long long)i * w + j] = s;
+        if (aspect) aspect[(long long)i * w + j] = a;
+    }
+}
+
+extern "C" int dcr_horn_slope_aspect(const float* dem, int h, int w, int64_t stride, double ndv, int has_ndv,
+                                     double ewres, double nsres, float* slope, float* aspect, void* stream) {
+    DCR_ARG(dem && (slope || aspect), "null pointer");
+    DCR_ARG(h > 0 && w > 0, "empty raster");
+    dim3 grid((w + K2_TW - 1) / K2_TW, (h + K2_TH - 1) / K2_TH);
+    horn_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dem, h, w, stride, (float)ndv, has_ndv, ewres, nsres, slope, aspect);
+    DCR_LAUNCH_OK("horn_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused front end: warp(ref), warp(src), dh, masks, Horn(slope, aspect of warped src)
+// ------------------------------------------------------------------------------------------
+#define F_TW 128
+#define F_TH 32
+#define F_SRC_R (F_TH + 5)
+#define F_SRC_C (F_TW + 5)
+#define F_REF_R (F_TH + 3)
+#define F_REF_C (F_TW + 3)
+#define F_SW_R (F_TH + 2)
+#define F_SW_C (F_TW + 2)
+#define F_ROWS_PER_THREAD 16
+
+struct FrontParams {
+    DevGeom rg, sg;
+    const float* ref;
+    const float* src;
+    const unsigned char* smask;
+    long long smask_stride;
+    int smask_h, smask_w, smask_nx0, smask_ny0;
+    int h, w;
+    double ewres, nsres;
+    double ref_gm_ndv, ref_gm_tol, src_gm_ndv, src_gm_tol;  // ds_getma masked_values(|x-ndv| <= tol)
+    float ref_fill, src_fill;                               // value written to ref_w/src_w for invalid pixels
+    float max_dz;
+    int use_max_dz;
+    float slope_lo, slope_hi;
+    float* dh;
+    float* slope;
+    float* aspect;
+    unsigned char* maskbits;
+    float* ref_w;
+    float* src_w;
+    unsigned long long* counters;  // [0]=count_base [1]=count_maxdz [2]=count_slope
+};
+
+// 16-tap warp of one pixel out of a shared-memory footprint tile (taps start at (r0, c0))
+template <int PITCH>
+__device__ __forceinline__ float warp_px_tile(const float* t, int r0, int c0, const DevGeom& g) {
+    double v[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const float* q = t + (r0 + r) * PITCH + c0;
+        v[r] = xpass(g.wx, q[0], q[1], q[2], q[3]);
+    }
+    double o = ypass(g.wy, v[0], v[1], v[2], v[3]);
+    const float nearest = t[(r0 + 1 + (g.ny0 - g.iy0)) * PITCH + (c0 + 1 + (g.nx0 - g.ix0))];
+    if (isnan(o)) {
+        return bilinear_fallback(t[(r0 + 1) * PITCH + c0 + 1], t[(r0 + 1) * PITCH + c0 + 2], t[(r0 + 2) * PITCH + c0 + 2],
+                                 t[(r0 + 2) * PITCH + c0 + 1], nearest, g.fx, g.fy);
+    }
+    if (isnan(nearest)) return nearest;
+    return (float)o;
+}
+
+__global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ FrontParams p) {
+    extern __shared__ float smem[];
+    float* s_src = smem;                                  // F_SRC_R x F_SRC_C
+    float* s_ref = s_src + F_SRC_R * F_SRC_C;             // F_REF_R x F_REF_C
+    float* s_sw = s_ref + F_REF_R * F_REF_C;              // F_SW_R x F_SW_C : warped src (NaN = nodata)
+    __shared__ unsigned long long s_cnt[3];
+
+    const int tj0 = blockIdx.x * F_TW, ti0 = blockIdx.y * F_TH;
+    const int tid = threadIdx.x;
+    if (tid < 3) s_cnt[tid] = 0ull;
+
+    // ---- stage the two source footprints (coalesced rows), nodata / out-of-bounds -> NaN
+    {
+        const int r_base = ti0 - 2 + p.sg.iy0, c_base = tj0 - 2 + p.sg.ix0;
+        for (int k = tid; k < F_SRC_R * F_SRC_C; k += 256) {
+            int r = k / F_SRC_C, c = k - r * F_SRC_C;
+            s_src[k] = load_px(p.src, p.sg, r_base + r, c_base + c);
+        }
+        const int rr_base = ti0 - 1 + p.rg.iy0, rc_base = tj0 - 1 + p.rg.ix0;
+        for (int k = tid; k < F_REF_R * F_REF_C; k += 256) {
+            int r = k / F_REF_C, c = k - r * F_REF_C;
+            s_ref[k] = load_px(p.ref, p.rg, rr_base + r, rc_base + c);
+        }
+    }
+    __syncthreads();
+
+    // ---- halo ring of the warped-src tile (needed by the 3x3 stencil only)
+    for (int k = tid; k < 2 * F_SW_C + 2 * F_TH; k += 256) {
+        int rr, cc;
+        if (k < F_SW_C) { rr = 0; cc = k; }
+        else if (k < 2 * F_SW_C) { rr = F_SW_R - 1; cc = k - F_SW_C; }
+        else if (k < 2 * F_SW_C + F_TH) { rr = 1 + (k - 2 * F_SW_C); cc = 0; }
+        else { rr = 1 + (k - 2 * F_SW_C - F_TH); cc = F_SW_C - 1; }
+        const int gi = ti0 - 1 + rr, gj = tj0 - 1 + cc;
+        float v = __int_as_float(0x7fc00000);
+        if (gi >= 0 && gj >= 0 && gi < p.h && gj < p.w) v = warp_px_tile<F_SRC_C>(s_src, rr, cc, p.sg);
+        s_sw[rr * F_SW_C + cc] = v;
+    }
+
+    // ---- main pass: thread = (column c, half hf), 16 consecutive rows, sliding x-pass window
+    const int c = tid & (F_TW - 1);
+    const int hf = tid >> 7;
+    const int rbeg = hf * F_ROWS_PER_THREAD;
+    const int j = tj0 + c;
+    float dh_reg[F_ROWS_PER_THREAD];
+    unsigned valid_bits = 0;  // bit r: base-valid (ref & src unmasked, static mask clear)
+    {
+        double xs0, xs1, xs2, xr0, xr1, xr2;
+        {
+            const float* q = s_src + (rbeg + 1) * F_SRC_C + (c + 1);
+            xs0 = xpass(p.sg.wx, q[0], q[1], q[2], q[3]);
+            q += F_SRC_C;
+            xs1 = xpass(p.sg.wx, q[0], q[1], q[2], q[3]);
+            q += F_SRC_C;
+            xs2 = xpass(p.sg.wx, q[0], q[1], q[2], q[3]);
+            const float* u = s_ref + rbeg * F_REF_C + c;
+            xr0 = xpass(p.rg.wx, u[0], u[1], u[2], u[3]);
+            u += F_REF_C;
+            xr1 = xpass(p.rg.wx, u[0], u[1], u[2], u[3]);
+            u += F_REF_C;
+            xr2 = xpass(p.rg.wx, u[0], u[1], u[2], u[3]);
+        }
+#pragma unroll
+        for (int rr = 0; rr < F_ROWS_PER_THREAD; ++rr) {
+            const int r = rbeg + rr;
+            const int i = ti0 + r;
+            const float* q = s_src + (r + 4) * F_SRC_C + (c + 1);
+            const double xs3 = xpass(p.sg.wx, q[0], q[1], q[2], q[3]);
+            const float* u = s_ref + (r + 3) * F_REF_C + c;
+            const double xr3 = xpass(p.rg.wx, u[0], u[1], u[2], u[3]);
+            double so = ypass(p.sg.wy, xs0, xs1, xs2, xs3);
+            double ro = ypass(p.rg.wy, xr0, xr1, xr2, xr3);
+            xs0 = xs1; xs1 = xs2; xs2 = xs3;
+            xr0 = xr1; xr1 = xr2; xr2 = xr3;
+            float sv, rv;
+            {
+                const float nearest = s_src[(r + 2 + (p.sg.ny0 - p.sg.iy0)) * F_SRC_C + (c + 2 + (p.sg.nx0 - p.sg.ix0))];
+                if (isnan(so))
+                    sv = bilinear_fallback(s_src[(r + 2) * F_SRC_C + c + 2], s_src[(r + 2) * F_SRC_C + c + 3],
+                                           s_src[(r + 3) * F_SRC_C + c + 3], s_src[(r + 3) * F_SRC_C + c + 2], nearest,
+                                           p.sg.fx, p.sg.fy);
+                else
+                    sv = isnan(nearest) ? nearest : (float)so;
+            }
+            {
+                const float nearest = s_ref[(r + 1 + (p.rg.ny0 - p.rg.iy0)) * F_REF_C + (c + 1 + (p.rg.nx0 - p.rg.ix0))];
+                if (isnan(ro))
+                    rv = bilinear_fallback(s_ref[(r + 1) * F_REF_C + c + 1], s_ref[(r + 1) * F_REF_C + c + 2],
+                                           s_ref[(r + 2) * F_REF_C + c + 2], s_ref[(r + 2) * F_REF_C + c + 1], nearest,
+                                           p.rg.fx, p.rg.fy);
+                else
+                    rv = isnan(nearest) ? nearest : (float)ro;
+            }
+            const bool inside = (i < p.h) && (j < p.w);
+            if (!inside) sv = __int_as_float(0x7fc00000);
+            s_sw[(r + 1) * F_SW_C + (c + 1)] = sv;
+            // ds_getma masks: |x - ndv| <= tol in double (numpy masked_values)
+            bool sm = isnan(sv) || fabs((double)sv - p.src_gm_ndv) <= p.src_gm_tol;
+            bool rm = isnan(rv) || fabs((double)rv - p.ref_gm_ndv) <= p.ref_gm_tol;
+            bool base_ok = inside && !sm && !rm;
+            if (base_ok && p.smask) {
+                const int mi = i + p.smask_ny0, mj = j + p.smask_nx0;
+                if (mi < 0 || mj < 0 || mi >= p.smask_h || mj >= p.smask_w) base_ok = false;
+                else if (__ldg(p.smask + (long long)mi * p.smask_stride + mj)) base_ok = false;
+            }
+            dh_reg[rr] = base_ok ? (sv - rv) : 0.0f;
+            if (base_ok) valid_bits |= (1u << rr);
+            if (inside) {
+                const long long o = (long long)i * p.w + j;
+                if (p.ref_w) p.ref_w[o] = isnan(rv) ? p.ref_fill : rv;
+                if (p.src_w) p.src_w[o] = isnan(sv) ? p.src_fill : sv;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- Horn stencil on the warped src + epilogue (masks, counters, stores)
+    unsigned n_base = 0, n_maxdz = 0, n_slope = 0;
+    {
+        float w0, w1, w2, w3, w4, w5, w6, w7, w8;
+        const float* q = s_sw + rbeg * F_SW_C + c;
+        w0 = q[0]; w1 = q[1]; w2 = q[2];
+        q += F_SW_C;
+        w3 = q[0]; w4 = q[1]; w5 = q[2];
+#pragma unroll
+        for (int rr = 0; rr < F_ROWS_PER_THREAD; ++rr) {
+            const int r = rbeg + rr;
+            const int i = ti0 + r;
+            q = s_sw + (r + 2) * F_SW_C + c;
+            w6 = q[0]; w7 = q[1]; w8 = q[2];
+            if (i < p.h && j < p.w) {
+                float sl = DCR_GDALDEM_NDV, as = DCR_GDALDEM_NDV;
+                unsigned bits = 0;
+                bool s_ok = false, a_ok = false;
+                if (i > 0 && j > 0 && i < p.h - 1 && j < p.w - 1) {
+                    float sv, av;
+                    if (horn(w0, w1, w2, w3, w4, w5, w6, w7, w8, p.ewres, p.nsres, true, true, &sv, &av)) {
+                        sl = sv;
+                        s_ok = true;
+                        if (!isnan(av)) { as = av; a_ok = true; }
+                    }
+                }
+                // range_fltr(slope, slope_lim): masked_outside keeps lo <= s <= hi
+                const bool s_keep = s_ok && !(sl < p.slope_lo) && !(sl > p.slope_hi);
+                if (s_keep) ++n_slope;
+                if (!s_keep) bits |= DCR_M_SLOPE;
+                if (!a_ok) bits |= DCR_M_ASPECT;
+                const float dh = dh_reg[rr];
+                if (!(valid_bits & (1u << rr))) bits |= DCR_M_BASE;
+                else {
+                    ++n_base;
+                    if (p.use_max_dz && (dh < -p.max_dz || dh > p.max_dz)) bits |= DCR_M_MAXDZ;
+                    else ++n_maxdz;
+                }
+                const long long o = (long long)i * p.w + j;
+                p.dh[o] = dh;
+                p.slope[o] = sl;
+                p.aspect[o] = as;
+                p.maskbits[o] = (unsigned char)bits;
+            }
+            w0 = w3; w1 = w4; w2 = w5;
+            w3 = w6; w4 = w7; w5 = w8;
+        }
+    }
+    // block-level counter reduction -> 3 global integer atomics per CTA
+    n_base = __reduce_add_sync(0xffffffffu, n_base);
+    n_maxdz = __reduce_add_sync(0xffffffffu, n_maxdz);
+    n_slope = __reduce_add_sync(0xffffffffu, n_slope);
+    if ((tid & 31) == 0) {
+        atomicAdd(&s_cnt[0], (unsigned long long)n_base);
+        atomicAdd(&s_cnt[1], (unsigned long long)n_maxdz);
+        atomicAdd(&s_cnt[2], (unsigned long long)n_slope);
+    }
+    __syncthreads();
+    if (tid < 3 && p.counters) atomicAdd(&p.counters[tid], s_cnt[tid]);
+}
+
+int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cudaStream_t stream) {
+    DCR_ARG(a, "null args");
+    DCR_ARG(a->ref && a->src && a->dh && a->slope && a->aspect && a->maskbits, "null raster pointer");
+    DCR_ARG(a->h > 0 && a->w > 0, "empty grid");
+    FrontParams p;
+    memset(&p, 0, sizeof(p));
+    p.rg = make_devgeom(a->ref_geom, a->ref_desc.height, a->ref_desc.width, a->ref_stride, a->ref_desc.ndv, a->ref_desc.has_ndv);
+    p.sg = make_devgeom(a->src_geom, a->src_desc.height, a->src_desc.width, a->src_stride, a->src_desc.ndv, a->src_desc.has_ndv);
+    p.ref = a->ref;
+    p.src = a->src;
+    p.smask = a->smask;
+    p.smask_stride = a->smask_stride;
+    p.smask_h = a->smask_h;
+    p.smask_w = a->smask_w;
+    p.smask_nx0 = a->smask_nx0;
+    p.smask_ny0 = a->smask_ny0;
+    p.h = a->h;
+    p.w = a->w;
+    p.ewres = a->ewres;
+    p.nsres = a->nsres;
+    // memwarp_multi: identity -> dataset unchanged (own ndv); resampled -> dst_ndv
+    const double rn = a->ref_geom.identity ? a->ref_desc.ndv : a->dst_ndv;
+    const double sn = a->src_geom.identity ? a->src_desc.ndv : a->dst_ndv;
+    p.ref_gm_ndv = rn;
+    p.ref_gm_tol = 1e-8 + 1e-5 * fabs(rn);
+    p.src_gm_ndv = sn;
+    p.src_gm_tol = 1e-8 + 1e-5 * fabs(sn);
+    p.ref_fill = (float)rn;
+    p.src_fill = (float)sn;
+    p.max_dz = a->max_dz;
+    p.use_max_dz = a->use_max_dz;
+    p.slope_lo = a->slope_lo;
+    p.slope_hi = a->slope_hi;
+    p.dh = a->dh;
+    p.slope = a->slope;
+    p.aspect = a->aspect;
+    p.maskbits = a->maskbits;
+    p.ref_w = a->ref_w;
+    p.src_w = a->src_w;
+    p.counters = counters;
+    const size_t smem = (size_t)(F_SRC_R * F_SRC_C + F_REF_R * F_REF_C + F_SW_R * F_SW_C) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        DCR_CUDA_OK(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    dim3 grid((a->w + F_TW - 1) / F_TW, (a->h + F_TH - 1) / F_TH);
+    front_kernel<<<grid, 256, smem, stream>>>(p);
+    DCR_LAUNCH_OK("front_kernel");
+    return 0;
+}
+
+extern "C" int dcr_warp_diff_horn(const dcr_front_args* args, void* stream) {
+    return dcr_front_launch(args, nullptr, (cudaStream_t)stream);
+}

@@ -1,0 +1,47 @@
+// Internal (non-ABI) interfaces shared between the translation units of libdemcoreg_b200.
+#pragma once
+#include "dcr_common.cuh"
+
+// ---- front end (dcr_front.cu) ----
+// counters (device, 3 x u64, zeroed by the caller): base-valid, after max_dz, slope-valid
+int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cudaStream_t stream);
+
+// ---- exact selection (dcr_select.cu) ----
+// A "view" of the values taking part in a selection; all device pointers.
+struct SelView {
+    const float* x;
+    const unsigned char* m;      // mask bytes or nullptr
+    unsigned reject;             // element valid iff (m[i] & reject) == 0
+    int transform;               // 0: x ; 1: |x - center| in float32
+    const float* center_ptr;     // device scalar (takes precedence) or nullptr
+    float center_imm;
+    long long n;
+    const long long* n_ptr;      // device element count (takes precedence) or nullptr
+};
+
+// Device-resident state/result of one selection.
+struct SelState {
+    unsigned prefix_lo, prefix_hi;   // radix prefixes of the two neighbouring order statistics
+    long long k_lo, k_hi;            // remaining ranks inside the prefixes
+    long long count;                 // participating elements
+    double gamma;                    // interpolation weight
+    int same;                        // prefix_lo == prefix_hi so far
+    int empty;
+    float v_lo, v_hi, result;        // result = numpy _lerp(v_lo, v_hi, gamma); NaN if empty
+};
+
+#define DCR_SEL_HIST_WORDS (2 * 2048)
+// Enqueue an exact quantile selection (q in percent) of `v`; the result lands in *st (device).
+// hist: device scratch of DCR_SEL_HIST_WORDS u32.
+int dcr_sel_enqueue(const SelView& v, double q_percent, SelState* st, unsigned* hist, cudaStream_t stream);
+
+// ---- nuth (dcr_nuth.cu) ----
+struct NuthDev;  // device block
+
+// ---- compression (dcr_select.cu) ----
+long long dcr_nchunks(long long n);
+int dcr_chunk_count_scan_enqueue(const float* x, const unsigned char* m, unsigned reject, long long n, unsigned* chunk_cnt,
+                                 long long* chunk_off, long long* total, cudaStream_t s);
+int dcr_compress_enqueue(const float* x, const unsigned char* m, unsigned reject, long long n, const long long* chunk_off,
+                         long long stride_imm, const long long* stride_ptr, float* dense, long long cap,
+                         cudaStream_t s);

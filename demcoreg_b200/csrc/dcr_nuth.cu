@@ -1,0 +1,573 @@
+// K6 Nuth-Kaab aspect-bin statistics, the host fit, K8 apply_z_shift, and the chained
+// one-iteration driver.
+//
+// Replaces reference coreglib.compute_offset_nuth (coreglib.py:201-315: common mask,
+// y = dh/tan(deg2rad(slope)), 3-sigma trim, malib.bin_stats count + median over 360 one-degree
+// aspect bins, curve_fit of nuth_func), coreglib.apply_z_shift (coreglib.py:42-55) and the
+// Nuth branch of dem_align.compute_offset (dem_align.py:62-172).
+#include <string.h>
+#include <stdio.h>
+#include "dcr_common.cuh"
+#include "dcr_internal.cuh"
+
+#define NB DCR_NBINS
+#define BIN_INVALID 0xFFFFu
+
+struct NuthDev {
+    unsigned long long n_common;
+    unsigned long long n_final;
+    float mean_y, std_y, rmin, rmax;
+    unsigned long long bin_count[NB];
+    unsigned prefix_lo[NB], prefix_hi[NB];
+    long long k_lo[NB], k_hi[NB];
+    int same[NB];
+    float bin_med[NB];
+};
+
+struct NuthPartial {
+    unsigned long long n;
+    double s, ss;
+};
+
+// y = dh / tan(deg2rad(slope)) in float32 (numpy: deg2rad = x * f32(pi/180); tan correctly rounded via FP64)
+__device__ __forceinline__ float nuth_y(float dh, float slope) {
+    const float rad = slope * 0.017453292519943295f;
+    const float t = (float)tan((double)rad);
+    return dh / t;
+}
+
+__global__ void __launch_bounds__(256) nuth_prepare_kernel(const float* __restrict__ dh, const float* __restrict__ slope,
+                                                           const float* __restrict__ aspect,
+                                                           const unsigned char* __restrict__ m, unsigned reject, long long n,
+                                                           float* __restrict__ y, unsigned short* __restrict__ bin,
+                                                           NuthPartial* __restrict__ part) {
+    __shared__ NuthPartial sp[8];
+    unsigned long long cnt = 0;
+    double s = 0.0, ss = 0.0;
+    const long long step = (long long)gridDim.x * 256;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += step) {
+        unsigned short b = BIN_INVALID;
+        float yv = 0.f;
+        if (!(m && (m[i] & reject))) {
+            const float a = aspect[i];
+            yv = nuth_y(dh[i], slope[i]);
+            ++cnt;
+            s += (double)yv;
+            ss += (double)yv * (double)yv;
+            // np.digitize on float32 integer edges 0..360: bin = floor(x); x == 360 joins the last bin
+            if (a >= 0.0f && a <= 360.0f) {
+                int bi = (int)floorf(a);
+                if (bi > NB - 1) bi = NB - 1;
+                b = (unsigned short)bi;
+            } else {
+                b = BIN_INVALID - 1;  // in the common mask (counts for mean/std) but outside the bin range
+            }
+        }
+        y[i] = yv;
+        bin[i] = b;
+    }
+    cnt = dcr_warp_sum_u64(cnt);
+    s = dcr_warp_sum(s);
+    ss = dcr_warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) { NuthPartial q; q.n = cnt; q.s = s; q.ss = ss; sp[threadIdx.x >> 5] = q; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        NuthPartial q = sp[0];
+        for (int k = 1; k < 8; ++k) { q.n += sp[k].n; q.s += sp[k].s; q.ss += sp[k].ss; }
+        part[blockIdx.x] = q;
+    }
+}
+
+// single thread block: fixed-order reduction of the partials -> mean/std (float32) -> rmin/rmax
+__global__ void __launch_bounds__(256) nuth_moments_final_kernel(const NuthPartial* __restrict__ part, int nparts,
+                                                                 int remove_outliers, NuthDev* nd) {
+    __shared__ NuthPartial sp[256];
+    NuthPartial q; q.n = 0; q.s = 0; q.ss = 0;
+    for (int k = threadIdx.x; k < nparts; k += 256) { q.n += part[k].n; q.s += part[k].s; q.ss += part[k].ss; }
+    sp[threadIdx.x] = q;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            sp[threadIdx.x].n += sp[threadIdx.x + o].n;
+            sp[threadIdx.x].s += sp[threadIdx.x + o].s;
+            sp[threadIdx.x].ss += sp[threadIdx.x + o].ss;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const unsigned long long cnt = sp[0].n;
+        nd->n_common = cnt;
+        nd->n_final = 0;
+        float mean = __int_as_float(0x7fc00000), sd = mean;
+        if (cnt) {
+            const double mu = sp[0].s / (double)cnt;
+            double var = sp[0].ss / (double)cnt - mu * mu;
+            if (var < 0) var = 0;
+            mean = (float)mu;
+            sd = (float)sqrt(var);
+        }
+        nd->mean_y = mean;
+        nd->std_y = sd;
+        if (remove_outliers) {
+            // coreglib.py:237-241 in float32 (NEP 50: python int 3 is weak)
+            const float fs = 3.0f * sd;
+            nd->rmin = mean - fs;
+            nd->rmax = mean + fs;
+        } else {
+            nd->rmin = -INFINITY;
+            nd->rmax = INFINITY;
+        }
+    }
+    for (int k = threadIdx.x; k < NB; k += 256) {
+        nd->bin_count[k] = 0ull;
+        nd->prefix_lo[k] = nd->prefix_hi[k] = 0u;
+        nd->same[k] = 1;
+        nd->bin_med[k] = __int_as_float(0x7fc00000);
+    }
+}
+
+// ghist layout: [2][NB][2048] u32 (second plane = the upper-median state when it left the lower one's bucket)
+template <int PASS>
+__global__ void __launch_bounds__(256) bin_hist_kernel(const float* __restrict__ y, const unsigned short* __restrict__ bin,
+                                                       long long n, NuthDev* nd, unsigned* __restrict__ ghist) {
+    __shared__ unsigned s_cnt[NB];
+    __shared__ unsigned s_plo[NB], s_phi[NB];
+    __shared__ unsigned char s_same[NB];
+    for (int k = threadIdx.x; k < NB; k += 256) {
+        s_cnt[k] = 0u;
+        if (PASS > 0) { s_plo[k] = nd->prefix_lo[k]; s_phi[k] = nd->prefix_hi[k]; s_same[k] = (unsigned char)nd->same[k]; }
+    }
+    __syncthreads();
+    const float rmin = nd->rmin, rmax = nd->rmax;
+    constexpr int shift_prev = (PASS == 1) ? 21 : 10;
+    constexpr int dshift = (PASS == 0) ? 21 : (PASS == 1 ? 10 : 0);
+    constexpr unsigned dmask = (PASS == 2) ? 1023u : 2047u;
+    const long long step = (long long)gridDim.x * 256;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += step) {
+        const unsigned b = bin[i];
+        if (b >= NB) continue;
+        const float yv = y[i];
+        if (!(yv >= rmin && yv <= rmax)) continue;
+        const unsigned key = dcr_f2key(yv);
+        if (PASS == 0) {
+            atomicAdd(&s_cnt[b], 1u);
+            atomicAdd(&ghist[b * 2048u + (key >> 21)], 1u);
+        } else {
+            if (((key ^ s_plo[b]) >> shift_prev) == 0u) atomicAdd(&ghist[b * 2048u + ((key >> dshift) & dmask)], 1u);
+            if (!s_same[b] && ((key ^ s_phi[b]) >> shift_prev) == 0u)
+                atomicAdd(&ghist[(NB + b) * 2048u + ((key >> dshift) & dmask)], 1u);
+        }
+    }
+    if (PASS == 0) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < NB; k += 256)
+            if (s_cnt[k]) atomicAdd(&nd->bin_count[k], (unsigned long long)s_cnt[k]);
+    }
+}
+
+// one block (256 threads) per bin
+__device__ void bin_find_bucket(const unsigned* __restrict__ hist, int nb, long long k, unsigned* s_scratch,
+                                int* s_bucket, long long* s_before) {
+    // 8 bins per thread
+    unsigned v[8], sum = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int idx = threadIdx.x * 8 + q;
+        v[q] = idx < nb ? hist[idx] : 0u;
+        sum += v[q];
+    }
+    unsigned total;
+    long long ex = dcr_block_excl_scan(sum, s_scratch, &total);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        if (ex <= k && k < ex + v[q]) { *s_bucket = threadIdx.x * 8 + q; *s_before = ex; }
+        ex += v[q];
+    }
+    __syncthreads();
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(256) bin_find_kernel(NuthDev* nd, unsigned* __restrict__ ghist) {
+    __shared__ unsigned s_scratch[33];
+    __shared__ int s_b[2];
+    __shared__ long long s_before[2];
+    const int b = blockIdx.x;
+    constexpr int nb = (PASS == 2) ? 1024 : 2048;
+    constexpr int dshift = (PASS == 0) ? 21 : (PASS == 1 ? 10 : 0);
+    unsigned* h0 = ghist + (size_t)b * 2048u;
+    unsigned* h1 = ghist + (size_t)(NB + b) * 2048u;
+    const long long cnt = (long long)nd->bin_count[b];
+    if (cnt == 0) return;  // histograms of an empty bin are all zero already
+    long long klo, khi;
+    int same;
+    if (PASS == 0) {
+        // scipy binned_statistic 'median': elements floor/ceil(j + (n-1)/2) of the sorted bin
+        klo = (cnt - 1) >> 1;
+        khi = cnt >> 1;
+        same = 1;
+    } else {
+        klo = nd->k_lo[b]; khi = nd->k_hi[b]; same = nd->same[b];
+    }
+    bin_find_bucket(h0, nb, klo, s_scratch, &s_b[0], &s_before[0]);
+    bin_find_bucket(same ? h0 : h1, nb, khi, s_scratch, &s_b[1], &s_before[1]);
+    if (threadIdx.x == 0) {
+        const unsigned plo = (PASS == 0 ? 0u : nd->prefix_lo[b]) | ((unsigned)s_b[0] << dshift);
+        const unsigned phi = (PASS == 0 ? 0u : nd->prefix_hi[b]) | ((unsigned)s_b[1] << dshift);
+        nd->prefix_lo[b] = plo; nd->prefix_hi[b] = phi;
+        nd->k_lo[b] = klo - s_before[0];
+        nd->k_hi[b] = khi - s_before[1];
+        nd->same[b] = (plo == phi) ? 1 : 0;
+        if (PASS == 2) {
+            const float a = dcr_key2f(plo), c = dcr_key2f(phi);
+            nd->bin_med[b] = (a + c) / 2.0f;  // (mid_a + mid_b) / 2 in the values' dtype (float32)
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 2048; k += 256) { h0[k] = 0u; h1[k] = 0u; }
+}
+
+__global__ void nuth_count_final_kernel(NuthDev* nd) {
+    // n_final = sum of the bin counts + in-range samples outside [0,360] (none for gdaldem aspect)
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int k = 0; k < NB; ++k) t += nd->bin_count[k];
+        nd->n_final = t;
+    }
+}
+
+struct NuthWs {
+    float* y;
+    unsigned short* bin;
+    NuthPartial* part;
+    unsigned* ghist;
+    NuthDev* nd;
+};
+static size_t nuth_ws_bytes(long long n, int grid) {
+    return dcr_al256(n * sizeof(float)) + dcr_al256(n * sizeof(unsigned short)) + dcr_al256(grid * sizeof(NuthPartial)) +
+           dcr_al256((size_t)2 * NB * 2048 * sizeof(unsigned)) + dcr_al256(sizeof(NuthDev));
+}
+static int nuth_ws_carve(DcrBump& ws, long long n, int grid, NuthWs* w) {
+    w->y = ws.take<float>(n);
+    w->bin = ws.take<unsigned short>(n);
+    w->part = ws.take<NuthPartial>(grid);
+    w->ghist = ws.take<unsigned>((size_t)2 * NB * 2048);
+    w->nd = ws.take<NuthDev>(1);
+    if (!w->y || !w->bin || !w->part || !w->ghist || !w->nd) { dcr_set_error("workspace too small"); return -1; }
+    return 0;
+}
+
+static int nuth_enqueue(const float* dh, const float* slope, const float* aspect, const unsigned char* m, unsigned reject,
+                        long long n, int remove_outliers, const NuthWs& w, int grid, cudaStream_t s) {
+    DCR_CUDA_OK(cudaMemsetAsync(w.ghist, 0, (size_t)2 * NB * 2048 * sizeof(unsigned), s));
+    nuth_prepare_kernel<<<grid, 256, 0, s>>>(dh, slope, aspect, m, reject, n, w.y, w.bin, w.part);
+    nuth_moments_final_kernel<<<1, 256, 0, s>>>(w.part, grid, remove_outliers, w.nd);
+    bin_hist_kernel<0><<<grid, 256, 0, s>>>(w.y, w.bin, n, w.nd, w.ghist);
+    bin_find_kernel<0><<<NB, 256, 0, s>>>(w.nd, w.ghist);
+    bin_hist_kernel<1><<<grid, 256, 0, s>>>(w.y, w.bin, n, w.nd, w.ghist);
+    bin_find_kernel<1><<<NB, 256, 0, s>>>(w.nd, w.ghist);
+    bin_hist_kernel<2><<<grid, 256, 0, s>>>(w.y, w.bin, n, w.nd, w.ghist);
+    bin_find_kernel<2><<<NB, 256, 0, s>>>(w.nd, w.ghist);
+    nuth_count_final_kernel<<<1, 32, 0, s>>>(w.nd);
+    DCR_LAUNCH_OK("nuth kernels");
+    return 0;
+}
+
+static void nuth_dev_to_stats(const NuthDev& d, dcr_nuth_stats* o) {
+    o->n_common = (int64_t)d.n_common;
+    o->n_final = (int64_t)d.n_final;
+    o->mean_y = d.mean_y; o->std_y = d.std_y; o->rmin = d.rmin; o->rmax = d.rmax;
+    for (int k = 0; k < NB; ++k) { o->bin_count[k] = (int64_t)d.bin_count[k]; o->bin_med[k] = d.bin_med[k]; }
+}
+
+extern "C" size_t dcr_nuth_workspace_bytes(int64_t n) { return nuth_ws_bytes(n, dcr_num_sms() * 8) + 4096; }
+
+extern "C" int dcr_nuth_bin_stats(const float* dh, const float* slope, const float* aspect, const uint8_t* maskbits,
+                                  uint32_t reject_dh, uint32_t reject_slope, uint32_t reject_aspect, int64_t n,
+                                  int remove_outliers, dcr_nuth_stats* out, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+    DCR_ARG(dh && slope && aspect && out && workspace, "null pointer");
+    DCR_ARG(n > 0, "n > 0");
+    const int grid = dcr_num_sms() * 8;
+    DcrBump ws(workspace, workspace_bytes);
+    NuthWs w;
+    if (nuth_ws_carve(ws, n, grid, &w)) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = nuth_enqueue(dh, slope, aspect, maskbits, reject_dh | reject_slope | reject_aspect, n, remove_outliers, w, grid, s);
+    if (rc) return rc;
+    static thread_local NuthDev host;
+    DCR_CUDA_OK(cudaMemcpyAsync(&host, w.nd, sizeof(NuthDev), cudaMemcpyDeviceToHost, s));
+    DCR_CUDA_OK(cudaStreamSynchronize(s));
+    nuth_dev_to_stats(host, out);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// host fit: least squares of a*cos(deg2rad(b - x)) + c == A cos x + B sin x + c  (Householder QR)
+// ------------------------------------------------------------------------------------------
+extern "C" int dcr_fit_nuth(const double* xc, const double* ym, int n, double fit[3]) {
+    DCR_ARG(xc && ym && fit, "null pointer");
+    DCR_ARG(n >= 3 && n <= 4096, "3 <= n <= 4096");
+    static thread_local double M[4096 * 4];
+    for (int r = 0; r < n; ++r) {
+        const double xr = xc[r] * (M_PI / 180.0);
+        M[r * 4 + 0] = cos(xr);
+        M[r * 4 + 1] = sin(xr);
+        M[r * 4 + 2] = 1.0;
+        M[r * 4 + 3] = ym[r];
+    }
+    for (int k = 0; k < 3; ++k) {
+        double norm = 0;
+        for (int r = k; r < n; ++r) norm += M[r * 4 + k] * M[r * 4 + k];
+        norm = sqrt(norm);
+        if (norm == 0) { dcr_set_error("rank-deficient fit"); return -4; }
+        const double alpha = M[k * 4 + k] > 0 ? -norm : norm;
+        // v = x - alpha e1
+        static thread_local double v[4096];
+        for (int r = k; r < n; ++r) v[r] = M[r * 4 + k];
+        v[k] -= alpha;
+        double vv = 0;
+        for (int r = k; r < n; ++r) vv += v[r] * v[r];
+        if (vv == 0) continue;
+        for (int c = k; c < 4; ++c) {
+            double dot = 0;
+            for (int r = k; r < n; ++r) dot += v[r] * M[r * 4 + c];
+            const double f = 2.0 * dot / vv;
+            for (int r = k; r < n; ++r) M[r * 4 + c] -= f * v[r];
+        }
+    }
+    double sol[3];
+    for (int k = 2; k >= 0; --k) {
+        double s = M[k * 4 + 3];
+        for (int c = k + 1; c < 3; ++c) s -= M[k * 4 + c] * sol[c];
+        if (M[k * 4 + k] == 0) { dcr_set_error("rank-deficient fit"); return -4; }
+        sol[k] = s / M[k * 4 + k];
+    }
+    const double A = sol[0], B = sol[1];
+    fit[0] = hypot(A, B);
+    double b = atan2(B, A) * (180.0 / M_PI);
+    fit[1] = b;
+    fit[2] = sol[2];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K8 apply_z_shift
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) zshift_kernel(float* __restrict__ band, int h, int w, long long stride, double ndv,
+                                                     double tol, float ndv32, float dz, const float* __restrict__ dzg) {
+    const long long n = (long long)h * w;
+    const long long step = (long long)gridDim.x * 256;
+    for (long long k = (long long)blockIdx.x * 256 + threadIdx.x; k < n; k += step) {
+        const int i = (int)(k / w), j = (int)(k - (long long)i * w);
+        float* p = band + (long long)i * stride + j;
+        const float v = *p;
+        // b_getma: masked_values(|x - ndv| <= 1e-8 + 1e-5|ndv|); a + dz; filled() -> masked pixels become ndv
+        if (fabs((double)v - ndv) <= tol) *p = ndv32;
+        else *p = v + (dzg ? dzg[k] : dz);
+    }
+}
+
+extern "C" int dcr_apply_z_shift(float* band, int h, int w, int64_t stride, double ndv, float dz, const float* dz_grid,
+                                 void* stream) {
+    DCR_ARG(band, "null pointer");
+    DCR_ARG(h > 0 && w > 0, "empty raster");
+    const double tol = 1e-8 + 1e-5 * fabs(ndv);
+    zshift_kernel<<<dcr_num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(band, h, w, stride, ndv, tol, (float)ndv, dz, dz_grid);
+    DCR_LAUNCH_OK("zshift_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// one chained iteration
+// ------------------------------------------------------------------------------------------
+struct IterDev {
+    unsigned long long counters[4];  // base, after max_dz, slope-valid, (pad)
+    unsigned long long count_mad, count_final;
+    SelState sel[5];                 // 0 med(dh|A)  1 med|dh-med|  2 med(dh|F)  3 med(subsample)  4 med(slope)
+    float nmad, mad_lo, mad_hi, pad0;
+    long long total_final, stride, dense_n;
+    NuthDev nuth;
+};
+
+__global__ void mad_thresholds_kernel(IterDev* d, int remove_outliers) {
+    if (threadIdx.x) return;
+    if (!remove_outliers || d->sel[0].empty) {
+        d->nmad = 0.f; d->mad_lo = -INFINITY; d->mad_hi = INFINITY;
+        return;
+    }
+    // filtlib.mad_fltr: mad = 1.4826 * median(|x - med|) ; keep med - 3*mad <= x <= med + 3*mad  (float32)
+    const float med = d->sel[0].result;
+    const float nmad = d->sel[1].result * 1.4826f;
+    const float t = 3.0f * nmad;
+    d->nmad = nmad;
+    d->mad_lo = med - t;
+    d->mad_hi = med + t;
+}
+
+#define MU_CHUNK 2048
+__global__ void __launch_bounds__(256) mask_update_kernel(const float* __restrict__ dh, unsigned char* __restrict__ m,
+                                                          long long n, IterDev* d, unsigned* __restrict__ chunk_cnt) {
+    __shared__ unsigned s_a[8], s_b[8];
+    const float lo = d->mad_lo, hi = d->mad_hi;
+    const long long base = (long long)blockIdx.x * MU_CHUNK + threadIdx.x * 8;
+    unsigned n_mad = 0, n_fin = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const long long i = base + k;
+        if (i >= n) break;
+        unsigned bits = m[i];
+        if (!(bits & (DCR_M_BASE | DCR_M_MAXDZ))) {
+            const float v = dh[i];
+            if (v < lo || v > hi) { bits |= DCR_M_MAD; m[i] = (unsigned char)bits; }
+            else ++n_mad;
+        }
+        if (!(bits & DCR_M_DIFF)) ++n_fin;
+    }
+    n_mad = __reduce_add_sync(0xffffffffu, n_mad);
+    n_fin = __reduce_add_sync(0xffffffffu, n_fin);
+    if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = n_mad; s_b[threadIdx.x >> 5] = n_fin; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned a = 0, b = 0;
+        for (int k = 0; k < 8; ++k) { a += s_a[k]; b += s_b[k]; }
+        chunk_cnt[blockIdx.x] = b;
+        if (a) atomicAdd(&d->count_mad, (unsigned long long)a);
+        if (b) atomicAdd(&d->count_final, (unsigned long long)b);
+    }
+}
+
+__global__ void stride_kernel(IterDev* d) {
+    if (threadIdx.x) return;
+    // malib.get_stats: thresh = 4e6; stride = int(np.around(count / thresh)) (round half to even)
+    const long long total = d->total_final;
+    long long stride = 1;
+    if ((double)total >= 4e6) stride = (long long)rint((double)total / 4e6);
+    if (stride < 1) stride = 1;
+    d->stride = stride;
+    d->dense_n = stride > 1 ? (total + stride - 1) / stride : 0;
+}
+
+static size_t iter_ws_bytes(long long n, int grid) {
+    const long long nch = (n + MU_CHUNK - 1) / MU_CHUNK;
+    return nuth_ws_bytes(n, grid) + dcr_al256(sizeof(IterDev)) + dcr_al256(DCR_SEL_HIST_WORDS * sizeof(unsigned)) +
+           dcr_al256(nch * sizeof(unsigned)) + dcr_al256(nch * sizeof(long long)) +
+           dcr_al256((size_t)(n < 6000016 ? n : 6000016) * sizeof(float)) + 4096;
+}
+extern "C" size_t dcr_iteration_workspace_bytes(int64_t n) { return iter_ws_bytes(n, dcr_num_sms() * 8); }
+
+int dcr_chunk_scan_enqueue(const unsigned* cnt, long long nchunks, long long* off, long long* total, cudaStream_t s);
+
+extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int remove_outliers, dcr_iter_result* out, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+    DCR_ARG(front && out && workspace, "null pointer");
+    const long long n = (long long)front->h * front->w;
+    DCR_ARG(n > 0, "empty grid");
+    const int grid = dcr_num_sms() * 8;
+    DCR_ARG(workspace_bytes >= iter_ws_bytes(n, grid), "workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    DcrBump ws(workspace, workspace_bytes);
+    IterDev* d = ws.take<IterDev>(1);
+    unsigned* hist = ws.take<unsigned>(DCR_SEL_HIST_WORDS);
+    const long long nch = (n + MU_CHUNK - 1) / MU_CHUNK;
+    unsigned* chunk_cnt = ws.take<unsigned>(nch);
+    long long* chunk_off = ws.take<long long>(nch);
+    const long long dense_cap = n < 6000016 ? n : 6000016;
+    float* dense = ws.take<float>(dense_cap);
+    NuthWs nw;
+    if (nuth_ws_carve(ws, n, grid, &nw)) return -1;
+    nw.nd = &d->nuth;
+
+    DCR_CUDA_OK(cudaMemsetAsync(d, 0, sizeof(IterDev), s));
+    dcr_front_args fa = *front;
+    if (!remove_outliers) fa.use_max_dz = 0;
+    int rc = dcr_front_launch(&fa, d->counters, s);
+    if (rc) return rc;
+
+    SelView v;
+    memset(&v, 0, sizeof(v));
+    v.x = front->dh; v.m = front->maskbits; v.n = n;
+    if (remove_outliers) {
+        v.reject = DCR_M_BASE | DCR_M_MAXDZ; v.transform = 0;
+        if ((rc = dcr_sel_enqueue(v, 50.0, &d->sel[0], hist, s))) return rc;
+        v.transform = 1; v.center_ptr = &d->sel[0].result;
+        if ((rc = dcr_sel_enqueue(v, 50.0, &d->sel[1], hist, s))) return rc;
+    }
+    mad_thresholds_kernel<<<1, 32, 0, s>>>(d, remove_outliers);
+    mask_update_kernel<<<(unsigned)nch, 256, 0, s>>>(front->dh, front->maskbits, n, d, chunk_cnt);
+    if ((rc = dcr_chunk_scan_enqueue(chunk_cnt, nch, chunk_off, &d->total_final, s))) return rc;
+    stride_kernel<<<1, 32, 0, s>>>(d);
+    if ((rc = dcr_compress_enqueue(front->dh, front->maskbits, DCR_M_DIFF, n, chunk_off, 1, &d->stride, dense, dense_cap, s)))
+        return rc;
+    // med_dh over the final mask (coreglib.py:214) and dz on the (possibly strided) subsample (dem_align.py:114-115)
+    v.reject = DCR_M_DIFF; v.transform = 0; v.center_ptr = nullptr;
+    if ((rc = dcr_sel_enqueue(v, 50.0, &d->sel[2], hist, s))) return rc;
+    {
+        SelView vd;
+        memset(&vd, 0, sizeof(vd));
+        vd.x = dense; vd.m = nullptr; vd.n = 0; vd.n_ptr = &d->dense_n;
+        if ((rc = dcr_sel_enqueue(vd, 50.0, &d->sel[3], hist, s))) return rc;
+    }
+    {
+        SelView vs;
+        memset(&vs, 0, sizeof(vs));
+        vs.x = front->slope; vs.m = front->maskbits; vs.reject = DCR_M_SLOPE; vs.n = n;
+        if ((rc = dcr_sel_enqueue(vs, 50.0, &d->sel[4], hist, s))) return rc;
+    }
+    if ((rc = nuth_enqueue(front->dh, front->slope, front->aspect, front->maskbits, DCR_M_DIFF | DCR_M_ASPECT, n,
+                           remove_outliers, nw, grid, s)))
+        return rc;
+    DCR_LAUNCH_OK("iteration kernels");
+
+    static thread_local IterDev* hd = nullptr;
+    if (!hd) DCR_CUDA_OK(cudaHostAlloc((void**)&hd, sizeof(IterDev), cudaHostAllocDefault));
+    DCR_CUDA_OK(cudaMemcpyAsync(hd, d, sizeof(IterDev), cudaMemcpyDeviceToHost, s));
+    DCR_CUDA_OK(cudaStreamSynchronize(s));
+
+    memset(out, 0, sizeof(*out));
+    out->count_base = (int64_t)hd->counters[0];
+    out->count_maxdz = (int64_t)hd->counters[1];
+    out->count_slope = (int64_t)hd->counters[2];
+    out->count_mad = (int64_t)hd->count_mad;
+    out->count_final = (int64_t)hd->count_final;
+    out->stats_stride = hd->stride;
+    out->med1 = hd->sel[0].result;
+    out->nmad1 = hd->nmad;
+    out->mad_lo = hd->mad_lo;
+    out->mad_hi = hd->mad_hi;
+    out->med_dh = hd->sel[2].result;
+    out->dz_med = hd->stride > 1 ? hd->sel[3].result : hd->sel[2].result;
+    out->med_slope = hd->sel[4].result;
+    nuth_dev_to_stats(hd->nuth, &out->nuth);
+    out->dz = -(double)out->dz_med;
+    if (out->count_base == 0) { out->status = 1; return 0; }
+    if (out->count_final < 100) { out->status = 2; return 0; }
+    if (out->count_slope < 100) { out->status = 3; return 0; }
+    // c_seed (coreglib.py:216), float32
+    out->c_seed = out->med_dh / tanf(out->med_slope * 0.017453292519943295f);
+    // keep bins with >= 9 samples; need >= 90 bins and ptp(cos(centres)) >= 1 (coreglib.py:280-301)
+    double xc[NB], ym[NB];
+    int nb = 0;
+    double cmin = INFINITY, cmax = -INFINITY;
+    for (int k = 0; k < NB; ++k) {
+        if (out->nuth.bin_count[k] >= 9) {
+            xc[nb] = k + 0.5;
+            ym[nb] = (double)out->nuth.bin_med[k];
+            const double c = cos(xc[nb] * (M_PI / 180.0));
+            cmin = fmin(cmin, c); cmax = fmax(cmax, c);
+            ++nb;
+        }
+    }
+    out->n_valid_bins = nb;
+    if (nb >= 90 && (cmax - cmin) >= 1.0) {
+        rc = dcr_fit_nuth(xc, ym, nb, out->fit);
+        if (rc) return rc;
+        const double br = out->fit[1] * (M_PI / 180.0);
+        out->dx = -(out->fit[0] * sin(br));
+        out->dy = -(out->fit[0] * cos(br));
+    } else {
+        out->status = 4;
+        out->fit[0] = out->fit[1] = out->fit[2] = NAN;
+        out->dx = -0.0; out->dy = -0.0;
+    }
+    return 0;
+}

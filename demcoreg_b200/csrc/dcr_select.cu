@@ -1,0 +1,381 @@
+// K3 exact order statistics (radix select, 11+11+10 bits), K4 moments, K5 strided compression.
+//
+// Replaces numpy.percentile / partition as reached through pygeotools malib.fast_median, mad,
+// calcperc (reference coreglib.py:88, 214-215; filtlib.mad_fltr <- dem_align.py:46), the
+// float64 mean/std/min/max of malib.get_stats (reference dem_align.py:114) and the
+// `compressed()[::stride]` subsample of malib.get_stats.
+//
+// Integer histograms only: results are exact and independent of launch geometry.
+#include <string.h>
+#include "dcr_common.cuh"
+#include "dcr_internal.cuh"
+
+#define SEL_THREADS 256
+#define CHUNK 2048  // elements per block in the order-sensitive (compression) kernels
+
+__device__ __forceinline__ bool sel_get(const SelView& v, long long i, float center, float* out) {
+    if (v.m && (v.m[i] & v.reject)) return false;
+    float t = v.x[i];
+    if (v.transform == 1) t = fabsf(t - center);
+    if (isnan(t)) return false;
+    *out = t;
+    return true;
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(SEL_THREADS) sel_hist_kernel(const SelView v, const SelState* __restrict__ st,
+                                                               unsigned* __restrict__ ghist) {
+    __shared__ unsigned h[2][2048];
+    for (int k = threadIdx.x; k < 2 * 2048; k += SEL_THREADS) (&h[0][0])[k] = 0u;
+    unsigned plo = 0, phi = 0;
+    int same = 1;
+    if (PASS > 0) {
+        if (st->empty) return;
+        plo = st->prefix_lo;
+        phi = st->prefix_hi;
+        same = st->same;
+    }
+    __syncthreads();
+    const long long n = v.n_ptr ? *v.n_ptr : v.n;
+    const float center = v.center_ptr ? *v.center_ptr : v.center_imm;
+    constexpr int shift_prev = (PASS == 1) ? 21 : 10;
+    constexpr int dshift = (PASS == 0) ? 21 : (PASS == 1 ? 10 : 0);
+    constexpr unsigned dmask = (PASS == 2) ? 1023u : 2047u;
+    const long long step = (long long)gridDim.x * SEL_THREADS;
+    for (long long i = (long long)blockIdx.x * SEL_THREADS + threadIdx.x; i < n; i += step) {
+        float val;
+        if (!sel_get(v, i, center, &val)) continue;
+        const unsigned key = dcr_f2key(val);
+        if (PASS == 0) {
+            atomicAdd(&h[0][key >> 21], 1u);
+        } else {
+            if (((key ^ plo) >> shift_prev) == 0u) atomicAdd(&h[0][(key >> dshift) & dmask], 1u);
+            if (!same && ((key ^ phi) >> shift_prev) == 0u) atomicAdd(&h[1][(key >> dshift) & dmask], 1u);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 2 * 2048; k += SEL_THREADS) {
+        unsigned c = (&h[0][0])[k];
+        if (c) atomicAdd(&ghist[k], c);
+    }
+}
+
+// whole block: find bucket b with cum_excl(b) <= k < cum_incl(b) in hist[nb]
+__device__ void find_bucket(const unsigned* __restrict__ hist, int nb, long long k, unsigned* s_scratch,
+                            int* s_bucket, long long* s_before) {
+    // 1024 threads, nb <= 2048: two bins per thread
+    const int t = threadIdx.x;
+    unsigned a = (2 * t < nb) ? hist[2 * t] : 0u;
+    unsigned b = (2 * t + 1 < nb) ? hist[2 * t + 1] : 0u;
+    unsigned total;
+    unsigned ex = dcr_block_excl_scan(a + b, s_scratch, &total);
+    if ((long long)ex <= k && k < (long long)ex + a) { *s_bucket = 2 * t; *s_before = ex; }
+    else if ((long long)ex + a <= k && k < (long long)ex + a + b) { *s_bucket = 2 * t + 1; *s_before = (long long)ex + a; }
+    __syncthreads();
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(1024) sel_find_kernel(SelState* st, unsigned* ghist, double q_percent) {
+    __shared__ unsigned s_scratch[33];
+    __shared__ int s_b[2];
+    __shared__ long long s_before[2];
+    constexpr int nb = (PASS == 2) ? 1024 : 2048;
+    constexpr int dshift = (PASS == 0) ? 21 : (PASS == 1 ? 10 : 0);
+    if (PASS > 0 && st->empty) return;
+    long long klo, khi;
+    int same;
+    if (PASS == 0) {
+        // count = sum of the first histogram
+        unsigned a = ghist[2 * threadIdx.x], b = ghist[2 * threadIdx.x + 1];
+        unsigned total;
+        (void)dcr_block_excl_scan(a + b, s_scratch, &total);
+        // total may exceed 2^32 only for n > 4.29e9 elements; rasters here are < 2^31 pixels
+        const long long count = (long long)total;
+        if (count == 0) {
+            if (threadIdx.x == 0) {
+                st->empty = 1; st->count = 0;
+                st->v_lo = st->v_hi = st->result = __int_as_float(0x7fc00000);
+            }
+            for (int k = threadIdx.x; k < DCR_SEL_HIST_WORDS; k += 1024) ghist[k] = 0u;
+            return;
+        }
+        // exact rank: virtual index (n-1)*(q/100) in float64
+        const double vi = (double)(count - 1) * (q_percent / 100.0);
+        klo = (long long)floor(vi);
+        khi = klo + 1 < count ? klo + 1 : count - 1;
+        if (threadIdx.x == 0) {
+            st->empty = 0; st->count = count; st->gamma = vi - (double)klo;
+        }
+        same = 1;
+    } else {
+        klo = st->k_lo; khi = st->k_hi; same = st->same;
+    }
+    __syncthreads();
+    find_bucket(ghist, nb, klo, s_scratch, &s_b[0], &s_before[0]);
+    find_bucket(same ? ghist : ghist + 2048, nb, khi, s_scratch, &s_b[1], &s_before[1]);
+    if (threadIdx.x == 0) {
+        unsigned plo = (PASS == 0 ? 0u : st->prefix_lo) | ((unsigned)s_b[0] << dshift);
+        unsigned phi = (PASS == 0 ? 0u : st->prefix_hi) | ((unsigned)s_b[1] << dshift);
+        st->prefix_lo = plo; st->prefix_hi = phi;
+        st->k_lo = klo - s_before[0];
+        st->k_hi = khi - s_before[1];
+        st->same = (plo == phi) ? 1 : 0;
+        if (PASS == 2) {
+            const float a = dcr_key2f(plo), b = dcr_key2f(phi);
+            st->v_lo = a; st->v_hi = b;
+            st->result = dcr_lerp32(a, b, st->gamma);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < DCR_SEL_HIST_WORDS; k += 1024) ghist[k] = 0u;
+}
+
+int dcr_sel_enqueue(const SelView& v, double q_percent, SelState* st, unsigned* hist, cudaStream_t stream) {
+    const int grid = dcr_num_sms() * 8;
+    DCR_CUDA_OK(cudaMemsetAsync(hist, 0, DCR_SEL_HIST_WORDS * sizeof(unsigned), stream));
+    sel_hist_kernel<0><<<grid, SEL_THREADS, 0, stream>>>(v, st, hist);
+    sel_find_kernel<0><<<1, 1024, 0, stream>>>(st, hist, q_percent);
+    sel_hist_kernel<1><<<grid, SEL_THREADS, 0, stream>>>(v, st, hist);
+    sel_find_kernel<1><<<1, 1024, 0, stream>>>(st, hist, q_percent);
+    sel_hist_kernel<2><<<grid, SEL_THREADS, 0, stream>>>(v, st, hist);
+    sel_find_kernel<2><<<1, 1024, 0, stream>>>(st, hist, q_percent);
+    DCR_LAUNCH_OK("sel kernels");
+    return 0;
+}
+
+extern "C" size_t dcr_select_workspace_bytes(void) {
+    return dcr_al256(DCR_SEL_HIST_WORDS * sizeof(unsigned)) + dcr_al256(16 * sizeof(SelState)) + 1024;
+}
+
+extern "C" int dcr_select_quantiles(const float* x, const uint8_t* mask, uint32_t reject, int64_t n, int transform,
+                                    float center, const double* q_percent, int nq, float* out, int64_t* count,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    DCR_ARG(x && q_percent && out && workspace, "null pointer");
+    DCR_ARG(nq >= 1 && nq <= 16, "1 <= nq <= 16");
+    DCR_ARG(n >= 0, "n >= 0");
+    DCR_ARG(workspace_bytes >= dcr_select_workspace_bytes(), "workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    DcrBump ws(workspace, workspace_bytes);
+    unsigned* hist = ws.take<unsigned>(DCR_SEL_HIST_WORDS);
+    SelState* st = ws.take<SelState>(16);
+    SelView v;
+    v.x = x; v.m = mask; v.reject = reject; v.transform = transform; v.center_ptr = nullptr; v.center_imm = center;
+    v.n = n; v.n_ptr = nullptr;
+    for (int k = 0; k < nq; ++k) {
+        int rc = dcr_sel_enqueue(v, q_percent[k], st + k, hist, s);
+        if (rc) return rc;
+    }
+    SelState hst[16];
+    DCR_CUDA_OK(cudaMemcpyAsync(hst, st, nq * sizeof(SelState), cudaMemcpyDeviceToHost, s));
+    DCR_CUDA_OK(cudaStreamSynchronize(s));
+    for (int k = 0; k < nq; ++k) out[k] = hst[k].result;
+    if (count) *count = hst[0].count;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4 moments: count, min, max, sum, sum of squares (FP64), fixed-order two-level reduction
+// ------------------------------------------------------------------------------------------
+struct MomPartial {
+    unsigned long long n;
+    double s, ss;
+    float mn, mx;
+};
+
+__global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ x, const unsigned char* __restrict__ m,
+                                                      unsigned reject, long long n, MomPartial* __restrict__ part) {
+    __shared__ MomPartial sp[8];
+    unsigned long long cnt = 0;
+    double s = 0.0, ss = 0.0;
+    float mn = INFINITY, mx = -INFINITY;
+    const long long step = (long long)gridDim.x * 256;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += step) {
+        if (m && (m[i] & reject)) continue;
+        const float v = x[i];
+        if (isnan(v)) continue;
+        ++cnt;
+        s += (double)v;
+        ss += (double)v * (double)v;
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+    }
+    cnt = dcr_warp_sum_u64(cnt);
+    s = dcr_warp_sum(s);
+    ss = dcr_warp_sum(ss);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        MomPartial q; q.n = cnt; q.s = s; q.ss = ss; q.mn = mn; q.mx = mx;
+        sp[threadIdx.x >> 5] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        MomPartial q = sp[0];
+        for (int k = 1; k < 8; ++k) {
+            q.n += sp[k].n; q.s += sp[k].s; q.ss += sp[k].ss;
+            q.mn = fminf(q.mn, sp[k].mn); q.mx = fmaxf(q.mx, sp[k].mx);
+        }
+        part[blockIdx.x] = q;
+    }
+}
+
+extern "C" int dcr_moments(const float* x, const uint8_t* mask, uint32_t reject, int64_t n, double out[6],
+                           void* workspace, size_t workspace_bytes, void* stream) {
+    DCR_ARG(x && out && workspace, "null pointer");
+    const int grid = dcr_num_sms() * 8;
+    DCR_ARG(workspace_bytes >= grid * sizeof(MomPartial), "workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    MomPartial* part = (MomPartial*)workspace;
+    moments_kernel<<<grid, 256, 0, s>>>(x, mask, reject, n, part);
+    DCR_LAUNCH_OK("moments_kernel");
+    MomPartial* h = new MomPartial[grid];
+    cudaError_t e = cudaMemcpyAsync(h, part, grid * sizeof(MomPartial), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { delete[] h; dcr_set_error("moments copy failed: %s", cudaGetErrorString(e)); return (int)e; }
+    unsigned long long cnt = 0; double sum = 0, ss = 0; float mn = INFINITY, mx = -INFINITY;
+    for (int k = 0; k < grid; ++k) {
+        cnt += h[k].n; sum += h[k].s; ss += h[k].ss; mn = fminf(mn, h[k].mn); mx = fmaxf(mx, h[k].mx);
+    }
+    delete[] h;
+    out[0] = (double)cnt;
+    out[1] = cnt ? mn : NAN;
+    out[2] = cnt ? mx : NAN;
+    const double mean = cnt ? sum / (double)cnt : NAN;
+    out[3] = mean;
+    double var = cnt ? ss / (double)cnt - mean * mean : NAN;
+    if (var < 0) var = 0;
+    out[4] = sqrt(var);
+    out[5] = ss;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K5 strided subsample of the compressed (row-major, unmasked) array
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) chunk_count_kernel(const unsigned char* __restrict__ m, unsigned reject,
+                                                          const float* __restrict__ x, long long n,
+                                                          unsigned* __restrict__ chunk_cnt) {
+    __shared__ unsigned sw[8];
+    const long long base = (long long)blockIdx.x * CHUNK + threadIdx.x * 8;
+    unsigned c = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const long long i = base + k;
+        if (i < n && !(m && (m[i] & reject)) && !isnan(x[i])) ++c;
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int k = 0; k < 8; ++k) t += sw[k];
+        chunk_cnt[blockIdx.x] = t;
+    }
+}
+
+// single block: exclusive scan of the chunk counts; total -> *total_out
+__global__ void __launch_bounds__(1024) chunk_scan_kernel(const unsigned* __restrict__ cnt, long long nchunks,
+                                                          long long* __restrict__ off, long long* total_out) {
+    __shared__ unsigned s_scratch[33];
+    __shared__ long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (long long b = 0; b < nchunks; b += 1024) {
+        const long long i = b + threadIdx.x;
+        unsigned v = i < nchunks ? cnt[i] : 0u;
+        unsigned total;
+        unsigned ex = dcr_block_excl_scan(v, s_scratch, &total);
+        if (i < nchunks) off[i] = s_carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = s_carry;
+}
+
+// stride from device (stride_ptr) or immediate; writes element with compressed rank r to dense[r/stride] when r % stride == 0
+__global__ void __launch_bounds__(256) compress_strided_kernel(const float* __restrict__ x, const unsigned char* __restrict__ m,
+                                                               unsigned reject, long long n,
+                                                               const long long* __restrict__ off, long long stride_imm,
+                                                               const long long* stride_ptr, float* __restrict__ dense,
+                                                               long long cap) {
+    __shared__ unsigned s_scratch[33];
+    const long long stride = stride_ptr ? *stride_ptr : stride_imm;
+    if (stride_ptr && stride <= 1) return;  // iteration driver: no subsample needed
+    const long long base = (long long)blockIdx.x * CHUNK + threadIdx.x * 8;
+    float vals[8];
+    unsigned flags = 0, c = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const long long i = base + k;
+        vals[k] = 0.f;
+        if (i < n && !(m && (m[i] & reject))) {
+            const float v = x[i];
+            if (!isnan(v)) { vals[k] = v; flags |= 1u << k; ++c; }
+        }
+    }
+    unsigned total;
+    unsigned ex = dcr_block_excl_scan(c, s_scratch, &total);
+    long long rank = off[blockIdx.x] + ex;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (flags & (1u << k)) {
+            if (rank % stride == 0) {
+                const long long d = rank / stride;
+                if (d < cap) dense[d] = vals[k];
+            }
+            ++rank;
+        }
+    }
+}
+
+int dcr_compress_enqueue(const float* x, const unsigned char* m, unsigned reject, long long n, const long long* chunk_off,
+                         long long stride_imm, const long long* stride_ptr, float* dense, long long cap,
+                         cudaStream_t s) {
+    const long long nchunks = (n + CHUNK - 1) / CHUNK;
+    compress_strided_kernel<<<(unsigned)nchunks, 256, 0, s>>>(x, m, reject, n, chunk_off, stride_imm, stride_ptr, dense, cap);
+    DCR_LAUNCH_OK("compress_strided_kernel");
+    return 0;
+}
+int dcr_chunk_count_scan_enqueue(const float* x, const unsigned char* m, unsigned reject, long long n, unsigned* chunk_cnt,
+                                 long long* chunk_off, long long* total, cudaStream_t s) {
+    const long long nchunks = (n + CHUNK - 1) / CHUNK;
+    chunk_count_kernel<<<(unsigned)nchunks, 256, 0, s>>>(m, reject, x, n, chunk_cnt);
+    chunk_scan_kernel<<<1, 1024, 0, s>>>(chunk_cnt, nchunks, chunk_off, total);
+    DCR_LAUNCH_OK("chunk count/scan");
+    return 0;
+}
+int dcr_chunk_scan_enqueue(const unsigned* cnt, long long nchunks, long long* off, long long* total, cudaStream_t s) {
+    chunk_scan_kernel<<<1, 1024, 0, s>>>(cnt, nchunks, off, total);
+    DCR_LAUNCH_OK("chunk_scan_kernel");
+    return 0;
+}
+long long dcr_nchunks(long long n) { return (n + CHUNK - 1) / CHUNK; }
+
+extern "C" int dcr_compress_strided(const float* x, const uint8_t* mask, uint32_t reject, int64_t n, int64_t stride,
+                                    float* dense, int64_t dense_capacity, int64_t* n_out, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+    DCR_ARG(x && dense && workspace && n_out, "null pointer");
+    DCR_ARG(stride >= 1, "stride >= 1");
+    const long long nchunks = dcr_nchunks(n);
+    const size_t need = dcr_al256(nchunks * sizeof(unsigned)) + dcr_al256(nchunks * sizeof(long long)) + 256;
+    DCR_ARG(workspace_bytes >= need, "workspace too small");
+    if (n == 0) { *n_out = 0; return 0; }
+    cudaStream_t s = (cudaStream_t)stream;
+    DcrBump ws(workspace, workspace_bytes);
+    unsigned* cnt = ws.take<unsigned>(nchunks);
+    long long* off = ws.take<long long>(nchunks);
+    long long* total = ws.take<long long>(1);
+    int rc = dcr_chunk_count_scan_enqueue(x, mask, reject, n, cnt, off, total, s);
+    if (rc) return rc;
+    rc = dcr_compress_enqueue(x, mask, reject, n, off, stride, nullptr, dense, dense_capacity, s);
+    if (rc) return rc;
+    long long t = 0;
+    DCR_CUDA_OK(cudaMemcpyAsync(&t, total, sizeof(t), cudaMemcpyDeviceToHost, s));
+    DCR_CUDA_OK(cudaStreamSynchronize(s));
+    *n_out = (t + stride - 1) / stride;
+    return 0;
+}

@@ -1,0 +1,258 @@
+#! /usr/bin/env python
+"""Drop-in for the iteration path of reference ``demcoreg/dem_align.py`` (``:26-172``, ``:203-392``).
+
+``compute_offset`` runs ONE chained sequence of sm_100a kernels per call
+(``dcr_nuth_iteration``); the command line (``getparser``/``main``) keeps the reference's
+options and defaults.  Datasets are ``demcoreg_b200.raster.Raster`` objects (device memory).
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+from . import _lib, coreglib, engine
+from .raster import Raster, MaskSource
+
+mask_choices = ['toa', 'snodas', 'modscag', 'bareground', 'glaciers', 'nlcd', 'none']
+
+
+def get_mask(ds, mask_list, dem_fn=None, mask_source=None):
+    """Reference ``dem_align.py:26-30``.  ``dem_mask.get_mask`` needs external land-cover data and is
+    out of scope: a ``MaskSource`` (world-fixed uint8 raster) takes its place; no mask -> scalar ``False``."""
+    if mask_source is None:
+        if mask_list and mask_list != ['none']:
+            raise NotImplementedError("dem_mask layers %s need external datasets (RGI/NLCD/...); pass a MaskSource" % mask_list)
+        return False
+    return mask_source
+
+
+def outlier_filter(diff, f=3, perc=None, max_dz=100):
+    """Reference ``dem_align.py:32-49`` on a masked array or ``(tensor, mask)`` pair -> same kind of object.
+
+    Absolute ``max_dz`` filter, then ``perc`` percentile filter or (default) median +- ``f`` * NMAD.
+    """
+    torch = _lib.require_cuda()
+    is_ma = not (isinstance(diff, (tuple, list)) and hasattr(diff[0], "is_cuda"))
+    x, m = coreglib._to_device_masked(diff)
+    print("Removing outliers")
+    print("Initial pixel count:")
+    m = (m != 0)
+    print(int((~m).sum()))
+    print("Absolute dz filter: %0.2f" % max_dz)
+    lim = np.float32(max_dz)
+    m = m | (x < -float(lim)) | (x > float(lim))
+    print(int((~m).sum()))
+    bits = m.to(torch.uint8).contiguous()
+    if perc is not None:
+        (lo, hi), _ = engine.select_quantiles(x, [perc[0], perc[1]], bits, 1)
+    else:
+        (med,), _ = engine.select_quantiles(x, [50.0], bits, 1)
+        (madv,), _ = engine.select_quantiles(x, [50.0], bits, 1, transform=1, center=float(med))
+        nmad = np.float32(madv) * np.float32(1.4826)
+        lo = np.float32(med) - np.float32(f) * nmad
+        hi = np.float32(med) + np.float32(f) * nmad
+    m = m | (x < float(lo)) | (x > float(hi))
+    print(int((~m).sum()))
+    if is_ma:
+        return np.ma.array(x.cpu().numpy(), mask=m.cpu().numpy())
+    return x, m
+
+
+def get_filtered_slope(ds, slope_lim=(0.1, 40)):
+    """Reference ``dem_align.py:51-60``: Horn slope (degrees) of ``ds`` masked outside ``slope_lim``."""
+    print("Computing slope")
+    s, _ = engine.horn(ds, True, False)
+    print("Slope filter: %0.2f - %0.2f" % slope_lim)
+    a = s.cpu().numpy()
+    slope = np.ma.masked_values(a, -9999.0, shrink=False)
+    print("Initial count: %i" % slope.count())
+    slope = np.ma.masked_outside(slope, *slope_lim)
+    print(slope.count())
+    return slope
+
+
+_EXIT_MSG = {
+    1: "No overlapping, unmasked pixels shared between input DEMs",
+    2: "Not enough dh samples",
+    3: "Not enough slope/aspect samples",
+}
+
+
+def compute_offset(ref_dem_ds, src_dem_ds, src_dem_fn, mode='nuth', remove_outliers=True, max_offset=100,
+                   max_dz=100, slope_lim=(0.1, 40), mask_list=['glaciers', ], plot=True, mask_source=None,
+                   return_static_mask=True, _details=None):
+    """Reference ``dem_align.py:62-172`` -> ``(dx, dy, dz, static_mask, fig)``.
+
+    ``mask_source`` (extension): a ``MaskSource`` standing in for ``dem_mask.get_mask``; with it
+    ``mask_list`` is ignored.  ``return_static_mask=False`` (extension) skips the device->host copy of
+    the final mask, which the Nuth loop only uses for the closing plot.
+    """
+    if mask_source is None and mask_list and mask_list != ['none']:
+        get_mask(None, mask_list)
+    fig = None
+    if mode == 'nuth':
+        res, grid, bufs = engine.nuth_iteration(ref_dem_ds, src_dem_ds, mask_source, remove_outliers, max_dz, slope_lim)
+        if res.status in _EXIT_MSG:
+            sys.exit(_EXIT_MSG[res.status])
+        if _details is not None:
+            _details['result'] = res
+            _details['grid'] = grid
+            _details['bufs'] = bufs
+        dz = np.float32(res.dz_med)
+        if res.status == 4:
+            print("Failed to calculate horizontal shift")
+            dx, dy = 0, 0
+        else:
+            fit_param = res.fit
+            dx = fit_param[0] * np.sin(np.deg2rad(fit_param[1]))
+            dy = fit_param[0] * np.cos(np.deg2rad(fit_param[1]))
+            nuth_dz = fit_param[2] * np.tan(np.deg2rad(res.med_slope))
+            print('Median dz: %0.2f\nNuth dz: %0.2f' % (dz, nuth_dz))
+        static_mask = None
+        if return_static_mask:
+            static_mask = ((bufs.maskbits & _lib.M_DIFF) != 0).cpu().numpy()
+        return -dx, -dy, -dz, static_mask, fig
+    elif mode in ('ncc', 'sad'):
+        from . import corr
+        return corr.compute_offset_corr(ref_dem_ds, src_dem_ds, mode, remove_outliers, max_offset, max_dz, slope_lim,
+                                        mask_source, plot)
+    elif mode == 'all':
+        print("Not yet implemented")
+        return 0, 0, 0, None, None
+    elif mode == 'none':
+        raise NameError("reference dem_align.py:166-170 uses undefined names (outprefix, src_dem_orig) in mode 'none'")
+    raise ValueError(mode)
+
+
+def getparser():
+    """Reference ``dem_align.py:174-201``: same options, names and defaults."""
+    parser = argparse.ArgumentParser(description="Perform DEM co-registration using multiple algorithms",
+                                     formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    parser.add_argument('ref_fn', type=str, help='Reference DEM filename')
+    parser.add_argument('src_fn', type=str, help='Source DEM filename to be shifted')
+    parser.add_argument('-mode', type=str, default='nuth', choices=['ncc', 'sad', 'nuth', 'none'],
+                        help='Type of co-registration to use')
+    parser.add_argument('-mask_list', nargs='+', type=str, default=[], choices=mask_choices,
+                        help='Define masks to use to limit reference surfaces for co-registration')
+    parser.add_argument('-tiltcorr', action='store_true',
+                        help='After preliminary translation, fit polynomial to residual elevation offsets and remove')
+    parser.add_argument('-polyorder', type=int, default=1, help='Specify order of polynomial fit')
+    parser.add_argument('-tol', type=float, default=0.02,
+                        help='When iterative translation magnitude is below this tolerance (meters), break and write out corrected DEM')
+    parser.add_argument('-max_offset', type=float, default=100,
+                        help='Maximum expected horizontal offset in meters, used to set search range for ncc and sad modes')
+    parser.add_argument('-max_dz', type=float, default=100,
+                        help='Maximum expected vertical offset in meters, used to filter outliers')
+    res_choices = ['min', 'max', 'mean', 'common_scale_factor']
+    parser.add_argument('-res', type=str, default='mean', choices=res_choices, help='Warp intputs to this resolution')
+    parser.add_argument('-slope_lim', type=float, nargs=2, default=(0.1, 40),
+                        help='Minimum and maximum surface slope limits to consider')
+    parser.add_argument('-max_iter', type=int, default=30, help='Maximum number of iterations, if tol is not reached')
+    parser.add_argument('-outdir', default=None, help='Output directory')
+    # extension: a world-fixed uint8 stable-surface mask raster (1 = masked) replacing dem_mask layers
+    parser.add_argument('-mask_fn', default=None, help='(extension) uint8 mask raster, 1 = exclude from co-registration')
+    return parser
+
+
+def align(ref_dem_ds, src_dem_ds, mode='nuth', mask_source=None, tol=0.02, max_offset=100, max_dz=100,
+          slope_lim=(0.1, 40), max_iter=30, verbose=True, records=None):
+    """The iteration loop of reference ``dem_align.py:291-357`` on device-resident rasters.
+
+    ``src_dem_ds`` is copied; the copy is shifted in place each iteration (geotransform + band) exactly
+    as the reference does.  Returns ``dict(dx, dy, dz, n_iter, iters, src_align)``.
+    """
+    import contextlib
+    import io
+    src_dem_ds_align = src_dem_ds.copy()
+    n = 1
+    dx_total = 0
+    dy_total = 0
+    dz_total = 0
+    iters = []
+    sink = contextlib.nullcontext() if verbose else contextlib.redirect_stdout(io.StringIO())
+    with sink:
+        while True:
+            print("*** Iteration %i ***" % n)
+            det = {} if records is not None else None
+            dx, dy, dz, static_mask, fig = compute_offset(ref_dem_ds, src_dem_ds_align, None, mode, max_offset=max_offset,
+                                                          mask_list=[], max_dz=max_dz, slope_lim=slope_lim, plot=True,
+                                                          mask_source=mask_source, return_static_mask=False, _details=det)
+            xyz_shift_str_iter = "dx=%+0.2fm, dy=%+0.2fm, dz=%+0.2fm" % (dx, dy, dz)
+            print("Incremental offset: %s" % xyz_shift_str_iter)
+            dx_total += dx
+            dy_total += dy
+            dz_total += dz
+            xyz_shift_str_cum = "dx=%+0.2fm, dy=%+0.2fm, dz=%+0.2fm" % (dx_total, dy_total, dz_total)
+            print("Cumulative offset: %s" % xyz_shift_str_cum)
+            src_dem_ds_align = coreglib.apply_xy_shift(src_dem_ds_align, dx, dy, createcopy=False)
+            src_dem_ds_align = coreglib.apply_z_shift(src_dem_ds_align, dz, createcopy=False)
+            iters.append(dict(n=n, dx=float(dx), dy=float(dy), dz=float(dz)))
+            if records is not None:
+                records.append(det)
+            n += 1
+            print("\n")
+            dm = np.sqrt(dx ** 2 + dy ** 2 + dz ** 2)
+            dm_total = np.sqrt(dx_total ** 2 + dy_total ** 2 + dz_total ** 2)
+            if dm_total > max_offset:
+                sys.exit("Total offset exceeded specified max_offset (%0.2f m). Consider increasing -max_offset argument" % max_offset)
+            if n > max_iter or dm < tol:
+                break
+    return dict(dx=float(dx_total), dy=float(dy_total), dz=float(dz_total), n_iter=n - 1, iters=iters,
+                src_align=src_dem_ds_align)
+
+
+def main(argv=None):
+    """Reference ``dem_align.py:203-631`` (iteration loop + final shift products; plots are not produced)."""
+    from . import rasterio_lite as rio
+    parser = getparser()
+    args = parser.parse_args(argv)
+    ref_dem_fn = args.ref_fn
+    src_dem_fn = args.src_fn
+    mode = args.mode
+    slope_lim = tuple(args.slope_lim)
+    if args.tiltcorr:
+        raise NotImplementedError("-tiltcorr is a 'next' row (SURVEY 8f-2)")
+    outdir = args.outdir
+    if outdir is None:
+        outdir = os.path.splitext(src_dem_fn)[0] + '_dem_align'
+    if not os.path.exists(outdir):
+        os.makedirs(outdir)
+    outprefix = '%s_%s' % (os.path.splitext(os.path.split(src_dem_fn)[-1])[0],
+                           os.path.splitext(os.path.split(ref_dem_fn)[-1])[0])
+    outprefix = os.path.join(outdir, outprefix)
+    print("\nReference: %s" % ref_dem_fn)
+    print("Source: %s" % src_dem_fn)
+    print("Mode: %s" % mode)
+    print("Output: %s\n" % outprefix)
+
+    ref = rio.read_raster(ref_dem_fn)
+    src = rio.read_raster(src_dem_fn)
+    mask_source = None
+    if args.mask_fn:
+        m = rio.read_array(args.mask_fn)
+        mask_source = MaskSource(m['array'].astype(np.uint8), m['gt'])
+    elif args.mask_list:
+        get_mask(None, args.mask_list)
+
+    out = align(ref, src, mode=mode, mask_source=mask_source, tol=args.tol, max_offset=args.max_offset,
+                max_dz=args.max_dz, slope_lim=slope_lim, max_iter=args.max_iter)
+    dx_total, dy_total, dz_total = out['dx'], out['dy'], out['dz']
+    xyz_shift_str_cum_fn = '_%s_x%+0.2f_y%+0.2f_z%+0.2f' % (mode, dx_total, dy_total, dz_total)
+    align_fn = outprefix + xyz_shift_str_cum_fn + '_align.tif'
+    print("Writing out shifted src_dem with median vertical offset removed: %s" % align_fn)
+    sa = out['src_align']
+    rio.write_raster(align_fn, sa.numpy(), sa.gt, sa.ndv, sa.proj)
+    dm_total = float(np.sqrt(dx_total ** 2 + dy_total ** 2 + dz_total ** 2))
+    info = {'src_fn': src_dem_fn, 'ref_fn': ref_dem_fn, 'align_fn': align_fn,
+            'shift': {'dx': dx_total, 'dy': dy_total, 'dz': dz_total, 'dm': dm_total},
+            'n_iter': out['n_iter']}
+    json_fn = outprefix + xyz_shift_str_cum_fn + '_align_stats.json'
+    with open(json_fn, 'w') as f:
+        json.dump(info, f)
+    return info
+
+
+if __name__ == "__main__":
+    main()

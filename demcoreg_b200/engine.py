@@ -1,0 +1,239 @@
+"""Host-side driver of the CUDA hot path: buffers, workspace and the C-ABI calls.
+
+PyTorch is plumbing only (device memory, streams); all arithmetic happens in
+``libdemcoreg_b200.so``.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .raster import Raster, MaskSource, plan_intersection
+
+_ws_cache = {}
+_res_cache = {}
+
+
+def _stream_ptr(torch):
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def workspace(nbytes, device=None):
+    """A cached uint8 device tensor of at least ``nbytes`` (grown on demand) for the C-ABI scratch."""
+    torch = _lib.require_cuda()
+    dev = torch.cuda.current_device() if device is None else device
+    t = _ws_cache.get(dev)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda")
+        _ws_cache[dev] = t
+    return t
+
+
+class IterBuffers(object):
+    """Device outputs of one iteration's front end (dh, slope, aspect, mask bits) on the common grid."""
+
+    def __init__(self, h, w, keep_warped=False):
+        torch = _lib.require_cuda()
+        self.h, self.w = h, w
+        self.dh = torch.empty((h, w), dtype=torch.float32, device="cuda")
+        self.slope = torch.empty((h, w), dtype=torch.float32, device="cuda")
+        self.aspect = torch.empty((h, w), dtype=torch.float32, device="cuda")
+        self.maskbits = torch.empty((h, w), dtype=torch.uint8, device="cuda")
+        self.ref_w = torch.empty((h, w), dtype=torch.float32, device="cuda") if keep_warped else None
+        self.src_w = torch.empty((h, w), dtype=torch.float32, device="cuda") if keep_warped else None
+
+
+def make_front_args(ref, src, mask_source, max_dz, use_max_dz, slope_lim, keep_warped=False, dst_ndv=0.0, bufs=None):
+    """Plan the common grid (memwarp_multi, res='max', extent='intersection') and fill ``dcr_front_args``."""
+    L = _lib.lib()
+    grid, gr, gs = plan_intersection(ref, src, 0.0)
+    h, w = grid.height, grid.width
+    if bufs is None or bufs.h != h or bufs.w != w or (keep_warped and bufs.ref_w is None):
+        bufs = IterBuffers(h, w, keep_warped)
+    a = _lib.FrontArgs()
+    a.ref = ref.data.data_ptr()
+    a.ref_stride = ref.data.stride(0)
+    a.ref_desc = ref.desc()
+    a.ref_geom = gr
+    a.src = src.data.data_ptr()
+    a.src_stride = src.data.stride(0)
+    a.src_desc = src.desc()
+    a.src_geom = gs
+    if mask_source is not None:
+        gm = _lib.WarpGeom()
+        md = mask_source.desc()
+        _lib.check(L.dcr_plan_onto_grid(C.byref(md), C.byref(grid), C.byref(gm)))
+        a.smask = mask_source.data.data_ptr()
+        a.smask_stride = mask_source.data.stride(0)
+        a.smask_h, a.smask_w = md.height, md.width
+        a.smask_nx0, a.smask_ny0 = gm.nx0, gm.ny0
+    else:
+        a.smask = None
+    a.h, a.w = h, w
+    a.ewres = grid.gt[1]
+    a.nsres = grid.gt[5]
+    a.dst_ndv = float(dst_ndv)
+    a.max_dz = float(max_dz)
+    a.use_max_dz = 1 if use_max_dz else 0
+    a.slope_lo, a.slope_hi = float(slope_lim[0]), float(slope_lim[1])
+    a.dh = bufs.dh.data_ptr()
+    a.slope = bufs.slope.data_ptr()
+    a.aspect = bufs.aspect.data_ptr()
+    a.maskbits = bufs.maskbits.data_ptr()
+    a.ref_w = bufs.ref_w.data_ptr() if bufs.ref_w is not None else None
+    a.src_w = bufs.src_w.data_ptr() if bufs.src_w is not None else None
+    return a, grid, bufs
+
+
+def nuth_iteration(ref, src, mask_source=None, remove_outliers=True, max_dz=100, slope_lim=(0.1, 40),
+                   keep_warped=False, bufs=None):
+    """One full Nuth-Kaab iteration on the device (``dcr_nuth_iteration``).
+
+    Returns ``(IterResult, Grid, IterBuffers)``; ``IterResult.dx/dy/dz`` is what
+    ``dem_align.compute_offset`` returns (reference ``dem_align.py:172``).
+    """
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    a, grid, bufs = make_front_args(ref, src, mask_source, max_dz, remove_outliers, slope_lim, keep_warped, bufs=bufs)
+    n = a.h * a.w
+    nbytes = L.dcr_iteration_workspace_bytes(n)
+    ws = workspace(nbytes)
+    res = _lib.IterResult()
+    _lib.check(L.dcr_nuth_iteration(C.byref(a), 1 if remove_outliers else 0, C.byref(res),
+                                    C.c_void_p(ws.data_ptr()), ws.numel(), _stream_ptr(torch)))
+    return res, grid, bufs
+
+
+def front_only(ref, src, mask_source=None, remove_outliers=True, max_dz=100, slope_lim=(0.1, 40), keep_warped=True):
+    """Only the fused warp + dh + masks + Horn kernel (``dcr_warp_diff_horn``)."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    a, grid, bufs = make_front_args(ref, src, mask_source, max_dz, remove_outliers, slope_lim, keep_warped)
+    _lib.check(L.dcr_warp_diff_horn(C.byref(a), _stream_ptr(torch)))
+    return grid, bufs
+
+
+def select_quantiles(x, q_percent, mask=None, reject=0xFF, transform=0, center=0.0):
+    """Exact ``np.percentile`` (linear) of the unmasked elements of a device tensor -> (values f32, count)."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    x = x.contiguous()
+    nq = len(q_percent)
+    q = (C.c_double * nq)(*[float(v) for v in q_percent])
+    out = (C.c_float * nq)()
+    cnt = C.c_int64(0)
+    ws = workspace(L.dcr_select_workspace_bytes())
+    mp = None
+    if mask is not None:
+        mask = mask.contiguous()
+        mp = C.c_void_p(mask.data_ptr())
+    _lib.check(L.dcr_select_quantiles(C.c_void_p(x.data_ptr()), mp, int(reject), x.numel(), int(transform), float(center),
+                                      q, nq, out, C.byref(cnt), C.c_void_p(ws.data_ptr()), ws.numel(), _stream_ptr(torch)))
+    return np.array(list(out), dtype=np.float32), int(cnt.value)
+
+
+def moments(x, mask=None, reject=0xFF):
+    """count, min, max, mean, std (float64 accumulation) of the unmasked elements."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    x = x.contiguous()
+    out = (C.c_double * 6)()
+    ws = workspace(1 << 20)
+    mp = None
+    if mask is not None:
+        mask = mask.contiguous()
+        mp = C.c_void_p(mask.data_ptr())
+    _lib.check(L.dcr_moments(C.c_void_p(x.data_ptr()), mp, int(reject), x.numel(), out, C.c_void_p(ws.data_ptr()),
+                             ws.numel(), _stream_ptr(torch)))
+    return dict(count=int(out[0]), min=out[1], max=out[2], mean=out[3], std=out[4], sumsq=out[5])
+
+
+def compress_strided(x, mask, reject, stride):
+    """``compressed()[::stride]`` of the unmasked elements (row-major) as a device tensor."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    x = x.contiguous()
+    n = x.numel()
+    cap = n // max(1, stride) + 2
+    dense = torch.empty(cap, dtype=torch.float32, device="cuda")
+    nout = C.c_int64(0)
+    ws = workspace((n // 2048 + 2) * 12 + 4096)
+    mp = C.c_void_p(mask.contiguous().data_ptr()) if mask is not None else None
+    _lib.check(L.dcr_compress_strided(C.c_void_p(x.data_ptr()), mp, int(reject), n, int(stride),
+                                      C.c_void_p(dense.data_ptr()), cap, C.byref(nout), C.c_void_p(ws.data_ptr()),
+                                      ws.numel(), _stream_ptr(torch)))
+    return dense[:int(nout.value)]
+
+
+def nuth_bin_stats(dh, slope, aspect, maskbits, reject_dh=_lib.M_DIFF, reject_slope=_lib.M_SLOPE,
+                   reject_aspect=_lib.M_ASPECT, remove_outliers=True):
+    """``dcr_nuth_bin_stats`` on device tensors -> NuthStats."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    n = dh.numel()
+    ws = workspace(L.dcr_nuth_workspace_bytes(n))
+    out = _lib.NuthStats()
+    _lib.check(L.dcr_nuth_bin_stats(C.c_void_p(dh.data_ptr()), C.c_void_p(slope.data_ptr()), C.c_void_p(aspect.data_ptr()),
+                                    C.c_void_p(maskbits.data_ptr()), reject_dh, reject_slope, reject_aspect, n,
+                                    1 if remove_outliers else 0, C.byref(out), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                    _stream_ptr(torch)))
+    return out
+
+
+def fit_nuth(bin_centers, bin_med):
+    """Closed-form least-squares fit of ``nuth_func`` (host, ``dcr_fit_nuth``) -> float64[3]."""
+    L = _lib.lib()
+    n = len(bin_centers)
+    xc = (C.c_double * n)(*[float(v) for v in bin_centers])
+    ym = (C.c_double * n)(*[float(v) for v in bin_med])
+    fit = (C.c_double * 3)()
+    _lib.check(L.dcr_fit_nuth(xc, ym, n, fit))
+    return np.array([fit[0], fit[1], fit[2]], dtype=np.float64)
+
+
+def warp_cubic(src, grid, geom, dst_ndv=0.0):
+    """Standalone cubic warp of a Raster onto ``grid`` (``dcr_warp_cubic``) -> Raster."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    h, w = grid.height, grid.width
+    dst = torch.empty((h, w), dtype=torch.float32, device="cuda")
+    _lib.check(L.dcr_warp_cubic(C.c_void_p(src.data.data_ptr()), src.RasterYSize, src.RasterXSize, src.data.stride(0),
+                                src.ndv if src.ndv is not None else 0.0, 0 if src.ndv is None else 1, C.byref(geom),
+                                C.c_void_p(dst.data_ptr()), h, w, w, float(dst_ndv), _stream_ptr(torch)))
+    return Raster(dst, tuple(grid.gt), dst_ndv, src.proj)
+
+
+def horn(ds, want_slope=True, want_aspect=True):
+    """Standalone Horn slope/aspect (``dcr_horn_slope_aspect``) -> (slope tensor|None, aspect tensor|None)."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    h, w = ds.RasterYSize, ds.RasterXSize
+    s = torch.empty((h, w), dtype=torch.float32, device="cuda") if want_slope else None
+    a = torch.empty((h, w), dtype=torch.float32, device="cuda") if want_aspect else None
+    gt = ds.GetGeoTransform()
+    _lib.check(L.dcr_horn_slope_aspect(C.c_void_p(ds.data.data_ptr()), h, w, ds.data.stride(0),
+                                       ds.ndv if ds.ndv is not None else 0.0, 0 if ds.ndv is None else 1,
+                                       gt[1], gt[5], C.c_void_p(s.data_ptr()) if s is not None else None,
+                                       C.c_void_p(a.data_ptr()) if a is not None else None, _stream_ptr(torch)))
+    return s, a
+
+
+def apply_z_shift_inplace(ds, dz):
+    """``dcr_apply_z_shift`` on a Raster (scalar float32 ``dz`` or a device/numpy grid)."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    h, w = ds.RasterYSize, ds.RasterXSize
+    grid_ptr = None
+    dzs = 0.0
+    keep = None
+    if isinstance(dz, np.ndarray) and dz.ndim == 2:
+        keep = torch.from_numpy(np.ascontiguousarray(dz, dtype=np.float32)).cuda()
+        grid_ptr = C.c_void_p(keep.data_ptr())
+    elif hasattr(dz, "is_cuda"):
+        keep = dz.to(torch.float32).contiguous()
+        grid_ptr = C.c_void_p(keep.data_ptr())
+    else:
+        dzs = float(np.float32(dz))
+    _lib.check(L.dcr_apply_z_shift(C.c_void_p(ds.data.data_ptr()), h, w, ds.data.stride(0),
+                                   ds.ndv if ds.ndv is not None else 0.0, dzs, grid_ptr, _stream_ptr(torch)))
+    return ds

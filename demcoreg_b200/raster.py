@@ -1,0 +1,119 @@
+"""``Raster``: a device-resident stand-in for the ``gdal.Dataset`` (MEM) objects of the hot path.
+
+The reference passes GDAL MEM datasets between ``dem_align.main``, ``compute_offset`` and
+``coreglib.apply_xy_shift/apply_z_shift`` (reference ``dem_align.py:294-343``, ``coreglib.py:14-55``).
+Here the single float32 band lives in HBM as a torch CUDA tensor; the handful of
+``gdal.Dataset`` / ``gdal.Band`` methods those functions touch are duck-typed.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class _Band(object):
+    def __init__(self, ds):
+        self._ds = ds
+
+    def ReadAsArray(self):
+        return self._ds.data.cpu().numpy()
+
+    def WriteArray(self, a):
+        torch = _lib.require_cuda()
+        self._ds.data.copy_(torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)))
+
+    def GetNoDataValue(self):
+        return self._ds.ndv
+
+    def SetNoDataValue(self, v):
+        self._ds.ndv = float(v)
+
+
+class Raster(object):
+    """One float32 band in device memory + geotransform + nodata + projection string."""
+
+    def __init__(self, data, gt, ndv=-9999.0, proj='LOCAL_CS["metres"]', device=None):
+        torch = _lib.require_cuda()
+        if isinstance(data, np.ndarray):
+            t = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32))
+            data = t.to(device or "cuda", non_blocking=False)
+        if data.dtype != torch.float32 or data.dim() != 2 or not data.is_cuda:
+            raise ValueError("Raster needs a 2-D float32 CUDA tensor or numpy array")
+        self.data = data.contiguous()
+        self.gt = tuple(float(g) for g in gt)
+        self.ndv = None if ndv is None else float(ndv)
+        self.proj = proj
+
+    # --- gdal.Dataset duck typing -------------------------------------------------------
+    @property
+    def RasterXSize(self):
+        return int(self.data.shape[1])
+
+    @property
+    def RasterYSize(self):
+        return int(self.data.shape[0])
+
+    def GetGeoTransform(self):
+        return self.gt
+
+    def SetGeoTransform(self, gt):
+        self.gt = tuple(float(g) for g in gt)
+
+    def GetProjection(self):
+        return self.proj
+
+    def GetRasterBand(self, n=1):
+        return _Band(self)
+
+    def copy(self):
+        """``iolib.mem_drv.CreateCopy('', ds, 0)``"""
+        return Raster(self.data.clone(), self.gt, self.ndv, self.proj)
+
+    def numpy(self):
+        return self.data.cpu().numpy()
+
+    def desc(self):
+        d = _lib.RasterDesc()
+        for k in range(6):
+            d.gt[k] = self.gt[k]
+        d.width = self.RasterXSize
+        d.height = self.RasterYSize
+        d.ndv = self.ndv if self.ndv is not None else 0.0
+        d.has_ndv = 0 if self.ndv is None else 1
+        return d
+
+
+class MaskSource(object):
+    """World-fixed uint8 stable-surface mask (1 = masked) in device memory.
+
+    Stands in for the output of ``dem_mask.get_mask`` (reference ``dem_align.py:26-30, 85``), whose
+    external land-cover inputs are out of scope: it is sampled nearest-neighbour onto each
+    iteration's common grid inside the fused kernel.
+    """
+
+    def __init__(self, array, gt, device=None):
+        torch = _lib.require_cuda()
+        if isinstance(array, np.ndarray):
+            array = torch.from_numpy(np.ascontiguousarray(array, dtype=np.uint8)).to(device or "cuda")
+        self.data = array.contiguous()
+        self.gt = tuple(float(g) for g in gt)
+
+    def desc(self):
+        d = _lib.RasterDesc()
+        for k in range(6):
+            d.gt[k] = self.gt[k]
+        d.width = int(self.data.shape[1])
+        d.height = int(self.data.shape[0])
+        d.ndv = 0.0
+        d.has_ndv = 0
+        return d
+
+
+def plan_intersection(a, b, res=0.0):
+    """``memwarp_multi([a, b], res, extent='intersection')`` bookkeeping -> (Grid, WarpGeom a, WarpGeom b)."""
+    L = _lib.lib()
+    grid, ga, gb = _lib.Grid(), _lib.WarpGeom(), _lib.WarpGeom()
+    da, db = a.desc(), b.desc()
+    _lib.check(L.dcr_plan_intersection(C.byref(da), C.byref(db), float(res), C.byref(grid), C.byref(ga), C.byref(gb)))
+    return grid, ga, gb

@@ -1,0 +1,194 @@
+/*
+ * demcoreg_b200 -- C-ABI of the B200-native co-registration hot path of dshean/demcoreg.
+ *
+ * Every entry point takes plain pointers and sizes (no torch types).  Device
+ * pointers are CALLER-OWNED (e.g. torch tensor .data_ptr()); the library never
+ * allocates result buffers.  Scratch comes from a caller-provided workspace whose
+ * size is queried with dcr_*_workspace_bytes().  `stream` is a cudaStream_t passed
+ * as void* (torch.cuda.current_stream().cuda_stream).  All functions return
+ * 0 on success, <0 for an invalid argument, >0 for a CUDA error code; the message
+ * is available (thread-local) from dcr_last_error().  Nothing here calls exit().
+ *
+ * Rasters are float32, row-major, rows north->south, `stride` in ELEMENTS.
+ * Masks are uint8 with 1 = masked, matching numpy.ma.
+ *
+ * Each function cites the reference interface it replaces (file:line in
+ * dshean/demcoreg, or the un-vendored pygeotools/GDAL routine that file calls).
+ */
+#ifndef DEMCOREG_B200_H
+#define DEMCOREG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCR_NBINS 360
+
+/* bits of the per-pixel mask byte written by dcr_warp_diff_horn / updated by the filters */
+#define DCR_M_BASE   0x01u /* ref or src nodata, or static (stable-surface) mask: dem_align.py:79-86 */
+#define DCR_M_MAXDZ  0x02u /* |dh| > max_dz: dem_align.py:39 */
+#define DCR_M_MAD    0x04u /* outside med +- 3*NMAD: dem_align.py:46 (filtlib.mad_fltr) */
+#define DCR_M_SLOPE  0x08u /* slope nodata or outside slope_lim: dem_align.py:51-60, 107 */
+#define DCR_M_ASPECT 0x10u /* aspect nodata (flat / border / nodata window): dem_align.py:100 */
+#define DCR_M_DIFF   (DCR_M_BASE | DCR_M_MAXDZ | DCR_M_MAD | DCR_M_SLOPE) /* final static_mask, dem_align.py:110 */
+
+const char* dcr_last_error(void);
+int dcr_version(void);
+/* sizeof() of the ABI structs, for binding self-checks: 0 raster_desc, 1 warp_geom, 2 grid, 3 front_args,
+ * 4 nuth_stats, 5 iter_result; -1 for an unknown index */
+int dcr_struct_size(int which);
+
+/* ---- geometry (host only) -------------------------------------------------------------
+ * One raster of a warp: geotransform, size, nodata.  Replaces the bookkeeping of
+ * pygeotools warplib.memwarp_multi(extent='intersection') <- dem_align.py:66-67, 298-299. */
+typedef struct dcr_raster_desc {
+    double gt[6];      /* GDAL geotransform (x0, res, 0, y0, 0, -res) */
+    int32_t width;     /* RasterXSize */
+    int32_t height;    /* RasterYSize */
+    double ndv;        /* band nodata value */
+    int32_t has_ndv;
+    int32_t _pad;
+} dcr_raster_desc;
+
+/* Per-raster constants of the translation-only cubic warp. */
+typedef struct dcr_warp_geom {
+    int32_t ix0, iy0;      /* floor(ox), floor(oy): first tap of output (i,j) is source (i+iy0-1, j+ix0-1) */
+    int32_t nx0, ny0;      /* floor(ox+.5), floor(oy+.5): the "nearest" source pixel GDAL tests first */
+    double fx, fy;         /* fractional offsets (bilinear fallback weights) */
+    double wx[4], wy[4];   /* Catmull-Rom (a=-0.5) weights, GDAL GWKCubicComputeWeights */
+    int32_t identity;      /* 1: memwarp_multi returns this dataset unchanged (no resample, ndv kept) */
+    int32_t _pad;
+} dcr_warp_geom;
+
+typedef struct dcr_grid {
+    double gt[6];          /* geotransform of the common grid */
+    int32_t width, height; /* int(round(extent/res)), Python round (half to even) */
+} dcr_grid;
+
+/* memwarp_multi([a, b], res, extent='intersection'): common grid + per-raster geometry.
+ * `res` <= 0 selects res='max' of the two inputs.  Returns -2 when the extents do not intersect,
+ * -3 when the resolutions differ (the down-sampling GWKResample path is not part of this library). */
+int dcr_plan_intersection(const dcr_raster_desc* a, const dcr_raster_desc* b, double res,
+                          dcr_grid* grid, dcr_warp_geom* ga, dcr_warp_geom* gb);
+/* geometry of one raster onto a given grid (used for the world-fixed stable-surface mask) */
+int dcr_plan_onto_grid(const dcr_raster_desc* a, const dcr_grid* grid, dcr_warp_geom* ga);
+
+/* ---- K1: cubic warp -------------------------------------------------------------------
+ * GDAL ReprojectImage(GRA_Cubic) for a pure translation, as reached through
+ * warplib.memwarp_multi <- dem_align.py:66-67 (also 298-299, 368-369).  dst nodata `dst_ndv`. */
+int dcr_warp_cubic(const float* src, int src_h, int src_w, int64_t src_stride, double src_ndv, int has_ndv,
+                   const dcr_warp_geom* geom, float* dst, int h, int w, int64_t dst_stride, float dst_ndv,
+                   void* stream);
+
+/* ---- K2: Horn slope / aspect ----------------------------------------------------------
+ * gdal.DEMProcessing('slope'|'aspect', computeEdges=False) as reached through
+ * geolib.gdaldem_mem_ds <- dem_align.py:54, 100.  Outputs use nodata -9999.  Either output may be NULL. */
+int dcr_horn_slope_aspect(const float* dem, int h, int w, int64_t stride, double ndv, int has_ndv,
+                          double ewres, double nsres, float* slope, float* aspect, void* stream);
+
+/* ---- K1+K2 fused front end of one iteration ---------------------------------------------
+ * dem_align.py:66-107: warp ref and src onto the common grid, dh = src - ref, nodata / static
+ * mask / |dh|<=max_dz, Horn slope (range-filtered) and aspect of the WARPED src.  One kernel. */
+typedef struct dcr_front_args {
+    const float* ref; int64_t ref_stride; dcr_raster_desc ref_desc; dcr_warp_geom ref_geom;
+    const float* src; int64_t src_stride; dcr_raster_desc src_desc; dcr_warp_geom src_geom;
+    const uint8_t* smask; int64_t smask_stride; int32_t smask_h, smask_w; /* world-fixed static mask or NULL */
+    int32_t smask_nx0, smask_ny0;                                        /* nearest-neighbour offsets onto the grid */
+    int32_t h, w;                      /* common grid */
+    double ewres, nsres;               /* gt[1], gt[5] of the common grid */
+    double dst_ndv;                    /* memwarp_multi dst_ndv (0) for resampled rasters */
+    float max_dz; int32_t use_max_dz;  /* dem_align.py:39 */
+    float slope_lo, slope_hi;          /* dem_align.py:58 */
+    /* outputs (device, contiguous h*w): */
+    float* dh; float* slope; float* aspect; uint8_t* maskbits;
+    float* ref_w; float* src_w;        /* optional warped rasters (NULL to skip) */
+} dcr_front_args;
+int dcr_warp_diff_horn(const dcr_front_args* args, void* stream);
+
+/* ---- K3: exact order statistics ---------------------------------------------------------
+ * numpy.percentile (linear interpolation) over the unmasked elements, as used by
+ * malib.fast_median / mad / calcperc <- coreglib.py:88, 214-215; filtlib.mad_fltr <- dem_align.py:46.
+ * Element i takes part iff mask == NULL or (mask[i] & reject) == 0, and the value is not NaN.
+ * transform 0: x ; 1: |x - center| evaluated in float32 (malib.mad).
+ * Results (host): out[q] = interpolated value, count = number of participating elements.
+ * Exact integer rank (float64 virtual index) + numpy's _lerp in float32.  */
+size_t dcr_select_workspace_bytes(void);
+int dcr_select_quantiles(const float* x, const uint8_t* mask, uint32_t reject, int64_t n,
+                         int transform, float center, const double* q_percent, int nq,
+                         float* out, int64_t* count, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K4: moments ------------------------------------------------------------------------
+ * count / min / max / mean / std (float64 accumulation) <- malib.get_stats (dem_align.py:114, 384, 392),
+ * robust_stats.py:55-65.  out = {count, min, max, mean, std(ddof=0), sum_sq} */
+int dcr_moments(const float* x, const uint8_t* mask, uint32_t reject, int64_t n, double out[6],
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K5: strided subsample of the compressed array ---------------------------------------
+ * malib.get_stats: compressed()[::stride] in row-major order of the unmasked pixels
+ * (<- dem_align.py:114).  Writes ceil(count/stride) values to dense; returns their number. */
+int dcr_compress_strided(const float* x, const uint8_t* mask, uint32_t reject, int64_t n, int64_t stride,
+                         float* dense, int64_t dense_capacity, int64_t* n_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K6: Nuth-Kaab aspect-bin statistics ---------------------------------------------------
+ * coreglib.py:221-263: common mask, y = dh/tan(deg2rad(slope)) (float32), 3-sigma trim on y,
+ * 360 one-degree bins: count and exact median (scipy.stats.binned_statistic).  */
+typedef struct dcr_nuth_stats {
+    int64_t n_common;            /* samples after the common mask: coreglib.py:221-228 */
+    int64_t n_final;             /* samples after the 3-sigma trim: coreglib.py:241-245 */
+    float mean_y, std_y;         /* float32 statistics of y: coreglib.py:238 */
+    float rmin, rmax;            /* coreglib.py:240-241 */
+    int64_t bin_count[DCR_NBINS];
+    float bin_med[DCR_NBINS];    /* NaN for empty bins */
+} dcr_nuth_stats;
+size_t dcr_nuth_workspace_bytes(int64_t n);
+int dcr_nuth_bin_stats(const float* dh, const float* slope, const float* aspect, const uint8_t* maskbits,
+                       uint32_t reject_dh, uint32_t reject_slope, uint32_t reject_aspect, int64_t n,
+                       int remove_outliers, dcr_nuth_stats* out /* host */,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- fit (host) -----------------------------------------------------------------------------
+ * scipy.optimize.curve_fit(nuth_func, bin_centers, bin_med, x0) <- coreglib.py:305 with
+ * nuth_func(x,a,b,c) = a*cos(deg2rad(b-x)) + c (coreglib.py:58-63).  The model is linear in
+ * (a cos b, a sin b, c); the unique least-squares minimum is solved in closed form (float64 QR). */
+int dcr_fit_nuth(const double* bin_centers, const double* bin_med, int n, double fit[3]);
+
+/* ---- K8: apply_z_shift ------------------------------------------------------------------------
+ * coreglib.py:42-55: a = b_getma(band); a = a + dz; WriteArray(a.filled()).  In place; pixels within
+ * numpy masked_values tolerance of ndv become exactly ndv.  dz_grid (device, h*w) may replace the scalar. */
+int dcr_apply_z_shift(float* band, int h, int w, int64_t stride, double ndv, float dz, const float* dz_grid,
+                      void* stream);
+
+/* ---- one full Nuth-Kaab iteration (device-resident inputs -> dx,dy,dz on the host) --------------
+ * dem_align.compute_offset(mode='nuth') <- dem_align.py:62-172 and coreglib.compute_offset_nuth
+ * <- coreglib.py:201-315.  All kernels are chained on `stream`; ONE device->host copy of the result. */
+typedef struct dcr_iter_result {
+    int32_t status;              /* 0 ok; 1 no overlapping unmasked pixels (dem_align.py:88-89);
+                                    2 not enough dh samples; 3 not enough slope samples (coreglib.py:206-209);
+                                    4 fit skipped: too few bins / aspect spread (coreglib.py:301) */
+    int32_t n_valid_bins;
+    int64_t count_base;          /* diff.count() after nodata + static mask: dem_align.py:86 */
+    int64_t count_maxdz;         /* after |dh| <= max_dz: dem_align.py:39-40 */
+    int64_t count_mad;           /* after mad_fltr: dem_align.py:46-48 */
+    int64_t count_final;         /* after the slope mask: dem_align.py:107 */
+    int64_t count_slope;         /* slope.count(): dem_align.py:59 */
+    int64_t stats_stride;        /* malib.get_stats subsample stride (1 = none) */
+    float med1, nmad1, mad_lo, mad_hi; /* filtlib.mad_fltr intermediates */
+    float dz_med;                /* diff_stats[5]: dem_align.py:115 */
+    float med_dh, med_slope;     /* coreglib.py:214-215 */
+    float c_seed;                /* coreglib.py:216 */
+    dcr_nuth_stats nuth;
+    double fit[3];               /* a, b (deg), c */
+    double dx, dy, dz;           /* RETURNED shift = (-a sin b, -a cos b, -dz_med): dem_align.py:155-156, 172 */
+} dcr_iter_result;
+size_t dcr_iteration_workspace_bytes(int64_t n);
+int dcr_nuth_iteration(const dcr_front_args* front, int remove_outliers, dcr_iter_result* out /* host */,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEMCOREG_B200_H */

@@ -1,0 +1,256 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): masks, valid-pixel counts and per-bin counts bit-exact;
+warped / dh / slope / aspect rasters within 1e-4 relative (float32); offsets within 1e-3 m.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4   # rasters, float32
+OFFTOL = 1e-3  # metres
+
+
+def _pair(n=768, res=30.0, seed=20260010, **kw):
+    from demcoreg_b200 import synth
+    return synth.make_pair(n=n, res=res, seed=seed, **kw)
+
+
+def _ods(p, key, gt=None):
+    from oracle import pygeotools_restated as pg
+    return pg.MemDataset(p[key], gt or p['gt'], p['ndv'])
+
+
+def _gds(p, key, gt=None):
+    from demcoreg_b200.raster import Raster
+    return Raster(p[key], gt or p['gt'], p['ndv'])
+
+
+def _shifted_gt(gt, dx, dy):
+    g = list(gt)
+    g[0] += dx
+    g[3] += dy
+    return tuple(g)
+
+
+def _check_raster(got, want, ndv, name):
+    gv = got != np.float32(ndv)
+    wv = want != np.float32(ndv)
+    assert np.array_equal(gv, wv), "%s: nodata pattern differs (%d px)" % (name, int((gv != wv).sum()))
+    np.testing.assert_allclose(got[gv], want[wv], rtol=RTOL, atol=0, err_msg=name)
+
+
+@pytest.mark.parametrize("shift", [(0.0, 0.0), (3.4217, -1.8140), (-40.3, 12.9), (95.5, 61.0)])
+def test_front_kernel_matches_oracle(cuda, shift):
+    """warp(ref), warp(src), dh, masks, Horn slope/aspect of one iteration vs the oracle restatement."""
+    from demcoreg_b200 import engine, _lib
+    from oracle import pygeotools_restated as pg, dem_align as oda
+    p = _pair(nodata_frac=0.01)
+    gt_s = _shifted_gt(p['gt'], *shift)
+    ref_o, src_o = _ods(p, 'ref'), _ods(p, 'src', gt_s)
+    grid, bufs = engine.front_only(_gds(p, 'ref'), _gds(p, 'src', gt_s))
+    cuda.cuda.synchronize()
+    rc, sc = pg.memwarp_multi([ref_o, src_o], res='max', extent='intersection')
+    assert (grid.height, grid.width) == rc.array.shape
+    assert tuple(grid.gt) == tuple(sc.GetGeoTransform())
+    _check_raster(bufs.ref_w.cpu().numpy(), rc.array, rc.ndv, "ref_w")
+    _check_raster(bufs.src_w.cpu().numpy(), sc.array, sc.ndv, "src_w")
+    # warped rasters: the FP64 evaluation order is replicated, so they are in fact bit-identical
+    assert np.array_equal(bufs.src_w.cpu().numpy(), sc.array)
+    assert np.array_equal(bufs.ref_w.cpu().numpy(), rc.array)
+    # dh + base / max_dz masks
+    diff = pg.ds_getma(sc) - pg.ds_getma(rc)
+    diff = np.ma.masked_outside(diff, -100, 100)
+    bits = bufs.maskbits.cpu().numpy()
+    gm = (bits & (_lib.M_BASE | _lib.M_MAXDZ)) != 0
+    assert np.array_equal(gm, np.ma.getmaskarray(diff))
+    dh = bufs.dh.cpu().numpy()
+    assert np.array_equal(dh[~gm], diff.compressed())
+    # slope / aspect
+    slope = oda.get_filtered_slope(sc)
+    aspect = pg.gdaldem_mem_ds(sc, 'aspect')
+    assert np.array_equal((bits & _lib.M_SLOPE) != 0, np.ma.getmaskarray(slope))
+    assert np.array_equal((bits & _lib.M_ASPECT) != 0, np.ma.getmaskarray(aspect))
+    sv = ~np.ma.getmaskarray(slope)
+    np.testing.assert_allclose(bufs.slope.cpu().numpy()[sv], slope.data[sv], rtol=RTOL)
+    av = ~np.ma.getmaskarray(aspect)
+    np.testing.assert_allclose(bufs.aspect.cpu().numpy()[av], aspect.data[av], rtol=RTOL, atol=1e-4)
+    # aspect bins are mask-deciding: floor() must agree everywhere
+    assert np.array_equal(np.floor(bufs.aspect.cpu().numpy()[av]), np.floor(aspect.data[av]))
+
+
+def test_standalone_warp_and_horn(cuda):
+    """dcr_warp_cubic / dcr_horn_slope_aspect (the memwarp / gdaldem entry points) vs the oracle."""
+    from demcoreg_b200 import engine
+    from demcoreg_b200.raster import plan_intersection
+    from oracle import pygeotools_restated as pg
+    p = _pair(n=512, nodata_frac=0.01)
+    gt_s = _shifted_gt(p['gt'], 17.3, -44.1)
+    ref_g, src_g = _gds(p, 'ref'), _gds(p, 'src', gt_s)
+    grid, gr, gs = plan_intersection(ref_g, src_g)
+    rw = engine.warp_cubic(ref_g, grid, gr)
+    sw = engine.warp_cubic(src_g, grid, gs)
+    rc, sc = pg.memwarp_multi([_ods(p, 'ref'), _ods(p, 'src', gt_s)], res='max', extent='intersection')
+    assert np.array_equal(rw.numpy(), rc.array)
+    assert np.array_equal(sw.numpy(), sc.array)
+    s, a = engine.horn(sw)
+    so = pg.gdaldem_slope(sc.array, sc.ndv, sc.gt[1], sc.gt[5])
+    ao = pg.gdaldem_aspect(sc.array, sc.ndv)
+    _check_raster(s.cpu().numpy(), so, -9999.0, "slope")
+    ga, wa = a.cpu().numpy(), ao
+    assert np.array_equal(ga == -9999.0, wa == -9999.0)
+    v = wa != -9999.0
+    np.testing.assert_allclose(ga[v], wa[v], rtol=RTOL, atol=1e-4)
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 1000, 100003, 3_000_000])
+def test_select_quantiles_exact(cuda, n):
+    """Exact order statistics + numpy lerp vs the oracle's exact-rank percentile."""
+    from demcoreg_b200 import engine
+    from oracle import pygeotools_restated as pg
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal(n) * 3 + 0.5).astype(np.float32)
+    x[rng.integers(0, n, size=max(1, n // 50))] = 0.5  # duplicates
+    m = (rng.random(n) < 0.3).astype(np.uint8)
+    if m.all():
+        m[0] = 0
+    xt, mt = cuda.from_numpy(x).cuda(), cuda.from_numpy(m).cuda()
+    qs = [50.0, 25.0, 75.0, 15.9, 84.1, 0.0, 100.0]
+    got, cnt = engine.select_quantiles(xt, qs, mt, 1)
+    xv = x[m == 0]
+    assert cnt == xv.size
+    for q, g in zip(qs, got):
+        assert g == pg.exact_percentile(xv, q), (q, g)
+    # |x - c| transform (malib.mad)
+    c = np.float32(got[0])
+    (g,), _ = engine.select_quantiles(xt, [50.0], mt, 1, transform=1, center=float(c))
+    assert g == pg.exact_percentile(np.fabs(xv - c), 50)
+
+
+def test_select_empty_and_negative(cuda):
+    from demcoreg_b200 import engine
+    x = cuda.tensor([-3.0, -1.0, -2.0, 4.0], dtype=cuda.float32, device="cuda")
+    m = cuda.ones(4, dtype=cuda.uint8, device="cuda")
+    got, cnt = engine.select_quantiles(x, [50.0], m, 1)
+    assert cnt == 0 and np.isnan(got[0])
+    got, cnt = engine.select_quantiles(x, [50.0, 0.0, 100.0])
+    assert cnt == 4 and got[0] == np.float32(-1.5) and got[1] == -3.0 and got[2] == 4.0
+
+
+@pytest.mark.parametrize("stride", [1, 2, 11])
+def test_compress_strided(cuda, stride):
+    """compressed()[::stride] in row-major order of the unmasked pixels (malib.get_stats subsample)."""
+    from demcoreg_b200 import engine
+    rng = np.random.default_rng(7)
+    n = 1_000_003
+    x = rng.standard_normal(n).astype(np.float32)
+    m = (rng.random(n) < 0.4).astype(np.uint8) * 4
+    got = engine.compress_strided(cuda.from_numpy(x).cuda(), cuda.from_numpy(m).cuda(), 4, stride).cpu().numpy()
+    want = x[m == 0][::stride]
+    assert np.array_equal(got, want)
+
+
+def test_moments(cuda):
+    from demcoreg_b200 import engine
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal(500_000) * 2 + 1).astype(np.float32)
+    m = (rng.random(x.size) < 0.2).astype(np.uint8)
+    r = engine.moments(cuda.from_numpy(x).cuda(), cuda.from_numpy(m).cuda(), 1)
+    xv = x[m == 0].astype(np.float64)
+    assert r['count'] == xv.size and r['min'] == xv.min() and r['max'] == xv.max()
+    assert abs(r['mean'] - xv.mean()) < 1e-12 * max(1, abs(xv.mean())) + 1e-10
+    assert abs(r['std'] - xv.std()) < 1e-9
+
+
+def _compare_iteration(res, det, odx, ody, odz):
+    assert res.count_base == det['count_base']
+    assert res.count_final == det['count_final']
+    nd = det['nuth']
+    assert res.nuth.n_common == nd['n_common']
+    assert res.nuth.n_final == nd['n_final']
+    assert np.array_equal(np.array(res.nuth.bin_count[:]), nd['bin_count'].astype(np.int64))
+    gm = np.array(res.nuth.bin_med[:], dtype=np.float64)
+    ok = ~np.isnan(nd['bin_med'])
+    assert np.array_equal(np.isnan(gm), ~ok)
+    np.testing.assert_allclose(gm[ok], nd['bin_med'][ok], rtol=1e-4, atol=1e-4)
+    assert res.med_dh == nd['med_dh']
+    assert res.med_slope == nd['med_slope']
+    assert res.dz_med == det['dz_med']
+    assert abs(res.dx - odx) < OFFTOL and abs(res.dy - ody) < OFFTOL and abs(res.dz - odz) < OFFTOL
+
+
+@pytest.mark.parametrize("cfg", [dict(), dict(nodata_frac=0.01, static_mask_frac=0.3),
+                                 dict(shift_gt=(3.4, -1.8)), dict(n=1024, res=8.0, shift_gt=(-13.7, 5.2), nodata_frac=0.01)])
+def test_nuth_iteration_matches_oracle(cuda, cfg):
+    """One full iteration (dcr_nuth_iteration): masks/counts exact, bin medians 1e-4, offsets 1e-3 m."""
+    from demcoreg_b200 import engine, _lib
+    from demcoreg_b200.raster import MaskSource
+    from oracle import dem_align as oda
+    cfg = dict(cfg)
+    sh = cfg.pop('shift_gt', (0.0, 0.0))
+    p = _pair(n=cfg.pop('n', 768), res=cfg.pop('res', 30.0), **cfg)
+    gt_s = _shifted_gt(p['gt'], *sh)
+    ms_g = MaskSource(p['mask'], p['gt']) if p['mask'] is not None else None
+    ms_o = oda.MaskSource(p['mask'], p['gt']) if p['mask'] is not None else None
+    res, grid, bufs = engine.nuth_iteration(_gds(p, 'ref'), _gds(p, 'src', gt_s), ms_g)
+    det = {}
+    odx, ody, odz, omask, _ = oda.compute_offset(_ods(p, 'ref'), _ods(p, 'src', gt_s), mask_source=ms_o, details=det)
+    gmask = ((bufs.maskbits & _lib.M_DIFF) != 0).cpu().numpy()
+    assert np.array_equal(gmask, omask)
+    _compare_iteration(res, det, odx, ody, odz)
+
+
+def test_strided_stats_branch(cuda):
+    """count >= 4e6 -> the dz median is taken on compressed()[::stride] (malib.get_stats)."""
+    from demcoreg_b200 import engine
+    from oracle import dem_align as oda
+    p = _pair(n=3072, res=30.0, period=1024)
+    res, grid, bufs = engine.nuth_iteration(_gds(p, 'ref'), _gds(p, 'src'))
+    det = {}
+    odx, ody, odz, omask, _ = oda.compute_offset(_ods(p, 'ref'), _ods(p, 'src'), details=det)
+    assert res.stats_stride == 2
+    _compare_iteration(res, det, odx, ody, odz)
+
+
+def test_align_loop_matches_oracle(cuda):
+    """The whole dem_align loop (config 1 geometry at reduced size): same iteration count, totals within 1e-3 m."""
+    from demcoreg_b200 import dem_align
+    from oracle import dem_align as oda
+    p = _pair(n=1024, res=30.0)
+    out = dem_align.align(_gds(p, 'ref'), _gds(p, 'src'), verbose=False)
+    oo = oda.align(_ods(p, 'ref'), _ods(p, 'src'), final_stats=False)
+    assert out['n_iter'] == oo['n_iter']
+    for k in ('dx', 'dy', 'dz'):
+        assert abs(out[k] - oo[k]) < OFFTOL, (k, out[k], oo[k])
+    # known answer: injected (+3.2, -1.7, +0.5) m; cubic-warp bias is ~0.005 px
+    assert abs(out['dx'] - 3.2) < 0.2 and abs(out['dy'] + 1.7) < 0.2 and abs(out['dz'] + 0.5) < 0.01
+    # shifted source raster: identical float32 values (same ordered f32 adds of dz)
+    assert np.array_equal(out['src_align'].numpy(), oo['src_align'].array)
+
+
+def test_apply_shifts(cuda):
+    from demcoreg_b200 import coreglib
+    from oracle import coreglib as ocl
+    p = _pair(n=256, nodata_frac=0.02)
+    g, o = _gds(p, 'src'), _ods(p, 'src')
+    g2 = coreglib.apply_z_shift(coreglib.apply_xy_shift(g, 1.25, -2.5), np.float32(-0.4375))
+    o2 = ocl.apply_z_shift(ocl.apply_xy_shift(o, 1.25, -2.5), np.float32(-0.4375))
+    assert g2.GetGeoTransform() == o2.GetGeoTransform()
+    assert np.array_equal(g2.numpy(), o2.array)
+    assert g2 is not g and np.array_equal(g.numpy(), p['src'])
+
+
+def test_compute_offset_nuth_api(cuda):
+    """coreglib.compute_offset_nuth(dh, slope, aspect) with numpy masked arrays vs the oracle's (scipy curve_fit)."""
+    from demcoreg_b200 import coreglib
+    from oracle import dem_align as oda, coreglib as ocl
+    p = _pair(n=512)
+    det = {}
+    oda.compute_offset(_ods(p, 'ref'), _ods(p, 'src'), details=det)
+    fit, fig = coreglib.compute_offset_nuth(det['dh'], det['slope'], det['aspect'])
+    ofit = det['fit']
+    assert fig is None
+    for f in (np.sin, np.cos):
+        assert abs(fit[0] * f(np.deg2rad(fit[1])) - ofit[0] * f(np.deg2rad(ofit[1]))) < 1e-5
+    assert abs(fit[2] - ofit[2]) < 1e-5
