@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- Nuth-Kaab co-registration iteration throughput (BASELINE.json metric).
+
+A "step" is one full dem_align iteration on one DEM pair: compute_offset(mode='nuth')
+(reference dem_align.py:62-172: warp both rasters to the common grid, dh, masks, outlier
+filters, Horn slope/aspect, medians, aspect-bin statistics, fit) followed by apply_xy_shift /
+apply_z_shift (coreglib.py:14-55), with device-resident inputs and (dx, dy, dz) on the host at
+the end of every step.  Workload at N=1: BASELINE.json configs[1] (8192x8192 pair at 8 m with a
+stable-surface mask).  N>1: one independent pair per GPU (pair-sharded, no collective), weak scaling.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size 8192]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES_ITER = 90.0      # algorithmic bytes per pixel per iteration
+# algorithmic bytes per pixel of each profiled stage (SURVEY 8d stage table)
+STAGE_INFO = [
+    ("front_kernel (warp+dh+masks+Horn)", 21.0),
+    ("sel_hist_kernel x6 (median + MAD)", 16.0),
+    ("mask_update+scan+compress", 6.0),
+    ("sel_hist_kernel x9 (med_dh, dz, med_slope)", 16.0),
+    ("nuth_prepare_kernel (y, bin, moments)", 13.0 + 6.0),
+    ("bin_hist_kernel x3 (bin count + median)", 12.0),
+    ("result copy", 0.0),
+]
+KERNELS_PER_STEP = 1 + 12 + 1 + 1 + 1 + 1 + 1 + 18 + 2 + 6 + 1 + 1  # see DESIGN.md "launch count"
+
+
+def peaks():
+    fn = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(fn):
+        with open(fn) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_workload(size, res, rank=0, cfg_id=2):
+    from demcoreg_b200 import synth
+    seed = 20260000 + 10 * cfg_id + 1000 * rank
+    period = min(size, 2048)
+    return synth.make_pair(n=size, res=res, seed=seed, period=period, static_mask_frac=0.3, nodata_frac=0.01,
+                           outlier_frac=0.001)
+
+
+class ClockSampler(object):
+    """Sample SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_iteration_seconds(p, crop, shift_gt):
+    """One oracle iteration (numpy/scipy restatement, 1 thread) on a crop of the workload; returns (seconds, pixels)."""
+    from oracle import pygeotools_restated as pg, dem_align as oda
+    ref = p['ref'][:crop, :crop]
+    src = p['src'][:crop, :crop]
+    msk = p['mask'][:crop, :crop] if p['mask'] is not None else None
+    gt = p['gt']
+    gts = (gt[0] + shift_gt[0], gt[1], 0.0, gt[3] + shift_gt[1], 0.0, gt[5])
+    ms = oda.MaskSource(msk, gt) if msk is not None else None
+    t0 = time.perf_counter()
+    oda.compute_offset(pg.MemDataset(ref, gt, p['ndv']), pg.MemDataset(src, gts, p['ndv']), mask_source=ms)
+    return time.perf_counter() - t0, crop * crop
+
+
+def _ref_worker(args):
+    """One worker = one DEM pair processed by one single-threaded process (the reference's execution model)."""
+    size, res, crop, rank, nrep = args
+    p = make_workload(size, res, rank)
+    return [oracle_iteration_seconds(p, crop, (3.4, -1.8)) for _ in range(nrep)]
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  The reference itself cannot be imported (pygeotools / GDAL are
+    absent), so this times the oracle restatement: one single-threaded process per DEM pair, as many
+    concurrent pairs as host cores (the reference's only parallelism, `parallel -j`, dem_align_parallel.pbs:122)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = min(os.cpu_count() or 1, 32)
+    nrep = args.warmup + args.steps
+    crop = min(args.size, 2048 if nrep <= 16 else 1024)
+    with mp.get_context("spawn").Pool(cores) as pool:
+        out = pool.map(_ref_worker, [(crop, args.res, crop, r, nrep) for r in range(cores)])
+    # per step: all workers run concurrently; the step time is the slowest worker's
+    step_s = [max(out[w][k][0] for w in range(cores)) for k in range(args.warmup, nrep)]
+    px = cores * crop * crop
+    val = px * len(step_s) / sum(step_s) / 1e9
+    line = {"metric": "nuth_kaab_iteration_throughput", "value": val, "unit": "Gpix/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(step_s) / len(step_s),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference",
+            "config": {"workload": "dem_align -mode nuth, one iteration per step on %d concurrent synthetic %dx%d pairs at %g m "
+                                   "(bounded sample of the %dx%d workload) with a 30%% stable-surface mask"
+                                   % (cores, crop, crop, args.res, args.size, args.size)},
+            "cpu_baseline": {"value": val, "unit": "Gpix/s", "cores": cores, "kind": "port",
+                             "sample": "%d concurrent single-thread oracle iterations (numpy/scipy restatement of the "
+                                       "reference, plot path off) on %dx%d pairs" % (cores, crop, crop)},
+            "e2e": {"value": val, "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=8192)
+    ap.add_argument("--res", type=float, default=8.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from demcoreg_b200 import _lib, engine, coreglib
+    from demcoreg_b200.raster import Raster, MaskSource
+    import contextlib
+    import io
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    size, res = args.size, args.res
+    p = make_workload(size, res, rank)
+    ref = Raster(p['ref'], p['gt'], p['ndv'])
+    src0 = Raster(p['src'], p['gt'], p['ndv'])
+    ms = MaskSource(p['mask'], p['gt'])
+
+    quiet = contextlib.redirect_stdout(io.StringIO())
+
+    def step(src, profile=False):
+        r, grid, bufs = engine.nuth_iteration(ref, src, ms, profile=profile)
+        with quiet:
+            coreglib.apply_xy_shift(src, r.dx, r.dy, createcopy=False)
+            coreglib.apply_z_shift(src, np.float32(r.dz), createcopy=False)
+        return r, grid
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm -------------------------------------------------------------
+    src = src0.copy()
+    for _ in range(args.warmup):
+        r, grid = step(src)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pix = 0
+    e0.record()
+    for _ in range(args.steps):
+        r, grid = step(src)
+        pix += grid.height * grid.width
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * pix / (ms_total * 1e-3) / 1e9
+
+    # ---- per-stage CUDA-event timing (same stream, same workload) -> roofline of the dominant stage
+    stage = np.zeros(7)
+    nprof = max(3, min(args.steps, 5))
+    for _ in range(nprof):
+        r, grid = step(src, profile=True)
+        stage += np.array(r.stage_ms[:7])
+    stage /= nprof
+    npx = grid.height * grid.width
+    peak, peak_src = peaks()
+    dom = int(np.argmax(stage[:6]))
+    dom_bytes = STAGE_INFO[dom][1] * npx
+    ach = dom_bytes / (stage[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": STAGE_INFO[dom][0], "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": float(stage[dom]),
+                "stages_ms": {STAGE_INFO[k][0]: float(stage[k]) for k in range(7)}}
+    iter_ach = ALG_BYTES_ITER * npx / (ms_step * 1e-3) / 1e9
+    roofline_iter = {"bound": "hbm", "achieved": iter_ach, "peak": peak, "unit": "GB/s", "frac": iter_ach / peak,
+                     "algorithmic_bytes_per_px": ALG_BYTES_ITER}
+
+    # ---- end-to-end arm: host buffers in, (dx,dy,dz) out, through the public API -------------
+    h_ref = torch.from_numpy(p['ref']).pin_memory()
+    h_src = torch.from_numpy(p['src']).pin_memory()
+    h_msk = torch.from_numpy(p['mask']).pin_memory()
+    gts = src.gt  # a realistic sub-pixel state (after the timed steps)
+    d_src = Raster(src0.data.clone(), gts, p['ndv'])
+
+    def e2e_step():
+        ref.data.copy_(h_ref, non_blocking=True)
+        d_src.data.copy_(h_src, non_blocking=True)
+        ms.data.copy_(h_msk, non_blocking=True)
+        rr, g2, _ = engine.nuth_iteration(ref, d_src, ms)
+        return rr, g2
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    pix2 = 0
+    n_e2e = max(3, min(args.steps, 5))
+    for _ in range(n_e2e):
+        rr, g2 = e2e_step()
+        pix2 += g2.height * g2.width
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * pix2 / (float(t.item()) * 1e-3) / 1e9
+    h2d = int(h_ref.numel() * 4 + h_src.numel() * 4 + h_msk.numel())
+    import ctypes
+    d2h = int(ctypes.sizeof(_lib.IterResult))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline: the oracle on a bounded sample of the same workload (rank 0, N=1 only) ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        crop = min(size, 2048)
+        sec, px = oracle_iteration_seconds(p, crop, (gts[0] - p['gt'][0], gts[3] - p['gt'][3]))
+        cpu = {"value": px / sec / 1e9, "unit": "Gpix/s", "cores": 1, "kind": "port",
+               "sample": "one oracle iteration (numpy/scipy restatement, plot path off) on the %dx%d top-left crop of "
+                         "the workload, %.1f s" % (crop, crop, sec)}
+
+    line = {"metric": "nuth_kaab_iteration_throughput", "value": value, "unit": "Gpix/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "dem_align -mode nuth, one iteration per step on a synthetic %dx%d fractal-terrain pair "
+                                   "at %g m with a 30%% stable-surface mask, 1%% nodata, injected shift (+3.2,-1.7,+0.5) m; "
+                                   "one pair per GPU" % (size, size, res),
+                       "pixels_per_step_per_gpu": npx, "l2": "inputs (2 x %d MB + mask) larger than the 126 MB L2" % (npx * 4 >> 20),
+                       "last_step_shift_m": [r.dx, r.dy, r.dz]},
+            "clocks": clocks, "gpu_launches": KERNELS_PER_STEP * args.steps,
+            "e2e": {"value": e2e_val, "unit": "Gpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "roofline": roofline, "roofline_iteration": roofline_iter, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

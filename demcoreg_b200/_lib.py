@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libdemcoreg_b200.so")
 NBINS = 360
 M_BASE, M_MAXDZ, M_MAD, M_SLOPE, M_ASPECT = 0x01, 0x02, 0x04, 0x08, 0x10
 M_DIFF = M_BASE | M_MAXDZ | M_MAD | M_SLOPE
+ITER_REMOVE_OUTLIERS, ITER_PROFILE = 1, 2
 
 
 class RasterDesc(C.Structure):
@@ -56,7 +57,7 @@ class IterResult(C.Structure):
                 ("med1", C.c_float), ("nmad1", C.c_float), ("mad_lo", C.c_float), ("mad_hi", C.c_float),
                 ("dz_med", C.c_float), ("med_dh", C.c_float), ("med_slope", C.c_float), ("c_seed", C.c_float),
                 ("nuth", NuthStats), ("fit", C.c_double * 3), ("dx", C.c_double), ("dy", C.c_double),
-                ("dz", C.c_double)]
+                ("dz", C.c_double), ("stage_ms", C.c_float * 8)]
 
 
 # every symbol include/demcoreg_b200.h declares: name -> (restype, argtypes)

@@ -257,10 +257,12 @@ static int nuth_ws_carve(DcrBump& ws, long long n, int grid, NuthWs* w) {
 }
 
 static int nuth_enqueue(const float* dh, const float* slope, const float* aspect, const unsigned char* m, unsigned reject,
-                        long long n, int remove_outliers, const NuthWs& w, int grid, cudaStream_t s) {
+                        long long n, int remove_outliers, const NuthWs& w, int grid, cudaStream_t s,
+                        cudaEvent_t after_prepare = nullptr) {
     DCR_CUDA_OK(cudaMemsetAsync(w.ghist, 0, (size_t)2 * NB * 2048 * sizeof(unsigned), s));
     nuth_prepare_kernel<<<grid, 256, 0, s>>>(dh, slope, aspect, m, reject, n, w.y, w.bin, w.part);
     nuth_moments_final_kernel<<<1, 256, 0, s>>>(w.part, grid, remove_outliers, w.nd);
+    if (after_prepare) DCR_CUDA_OK(cudaEventRecord(after_prepare, s));
     bin_hist_kernel<0><<<grid, 256, 0, s>>>(w.y, w.bin, n, w.nd, w.ghist);
     bin_find_kernel<0><<<NB, 256, 0, s>>>(w.nd, w.ghist);
     bin_hist_kernel<1><<<grid, 256, 0, s>>>(w.y, w.bin, n, w.nd, w.ghist);
@@ -457,9 +459,15 @@ extern "C" size_t dcr_iteration_workspace_bytes(int64_t n) { return iter_ws_byte
 
 int dcr_chunk_scan_enqueue(const unsigned* cnt, long long nchunks, long long* off, long long* total, cudaStream_t s);
 
-extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int remove_outliers, dcr_iter_result* out, void* workspace,
+extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_iter_result* out, void* workspace,
                                   size_t workspace_bytes, void* stream) {
     DCR_ARG(front && out && workspace, "null pointer");
+    const int remove_outliers = (flags & DCR_ITER_REMOVE_OUTLIERS) ? 1 : 0;
+    const bool prof = (flags & DCR_ITER_PROFILE) != 0;
+    static thread_local cudaEvent_t ev[8] = {nullptr};
+    if (prof && !ev[0])
+        for (int k = 0; k < 8; ++k) DCR_CUDA_OK(cudaEventCreate(&ev[k]));
+#define STAGE_MARK(k) do { if (prof) DCR_CUDA_OK(cudaEventRecord(ev[k], s)); } while (0)
     const long long n = (long long)front->h * front->w;
     DCR_ARG(n > 0, "empty grid");
     const int grid = dcr_num_sms() * 8;
@@ -477,12 +485,14 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int remove_outlie
     if (nuth_ws_carve(ws, n, grid, &nw)) return -1;
     nw.nd = &d->nuth;
 
+    STAGE_MARK(0);
     DCR_CUDA_OK(cudaMemsetAsync(d, 0, sizeof(IterDev), s));
     dcr_front_args fa = *front;
     if (!remove_outliers) fa.use_max_dz = 0;
     int rc = dcr_front_launch(&fa, d->counters, s);
     if (rc) return rc;
 
+    STAGE_MARK(1);
     SelView v;
     memset(&v, 0, sizeof(v));
     v.x = front->dh; v.m = front->maskbits; v.n = n;
@@ -492,12 +502,14 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int remove_outlie
         v.transform = 1; v.center_ptr = &d->sel[0].result;
         if ((rc = dcr_sel_enqueue(v, 50.0, &d->sel[1], hist, s))) return rc;
     }
+    STAGE_MARK(2);
     mad_thresholds_kernel<<<1, 32, 0, s>>>(d, remove_outliers);
     mask_update_kernel<<<(unsigned)nch, 256, 0, s>>>(front->dh, front->maskbits, n, d, chunk_cnt);
     if ((rc = dcr_chunk_scan_enqueue(chunk_cnt, nch, chunk_off, &d->total_final, s))) return rc;
     stride_kernel<<<1, 32, 0, s>>>(d);
     if ((rc = dcr_compress_enqueue(front->dh, front->maskbits, DCR_M_DIFF, n, chunk_off, 1, &d->stride, dense, dense_cap, s)))
         return rc;
+    STAGE_MARK(3);
     // med_dh over the final mask (coreglib.py:214) and dz on the (possibly strided) subsample (dem_align.py:114-115)
     v.reject = DCR_M_DIFF; v.transform = 0; v.center_ptr = nullptr;
     if ((rc = dcr_sel_enqueue(v, 50.0, &d->sel[2], hist, s))) return rc;
@@ -513,17 +525,22 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int remove_outlie
         vs.x = front->slope; vs.m = front->maskbits; vs.reject = DCR_M_SLOPE; vs.n = n;
         if ((rc = dcr_sel_enqueue(vs, 50.0, &d->sel[4], hist, s))) return rc;
     }
+    STAGE_MARK(4);
     if ((rc = nuth_enqueue(front->dh, front->slope, front->aspect, front->maskbits, DCR_M_DIFF | DCR_M_ASPECT, n,
-                           remove_outliers, nw, grid, s)))
+                           remove_outliers, nw, grid, s, prof ? ev[5] : nullptr)))
         return rc;
     DCR_LAUNCH_OK("iteration kernels");
+    STAGE_MARK(6);
 
     static thread_local IterDev* hd = nullptr;
     if (!hd) DCR_CUDA_OK(cudaHostAlloc((void**)&hd, sizeof(IterDev), cudaHostAllocDefault));
     DCR_CUDA_OK(cudaMemcpyAsync(hd, d, sizeof(IterDev), cudaMemcpyDeviceToHost, s));
+    STAGE_MARK(7);
     DCR_CUDA_OK(cudaStreamSynchronize(s));
 
     memset(out, 0, sizeof(*out));
+    if (prof)
+        for (int k = 0; k < 7; ++k) DCR_CUDA_OK(cudaEventElapsedTime(&out->stage_ms[k], ev[k], ev[k + 1]));
     out->count_base = (int64_t)hd->counters[0];
     out->count_maxdz = (int64_t)hd->counters[1];
     out->count_slope = (int64_t)hd->counters[2];

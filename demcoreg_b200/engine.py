@@ -86,7 +86,7 @@ def make_front_args(ref, src, mask_source, max_dz, use_max_dz, slope_lim, keep_w
 
 
 def nuth_iteration(ref, src, mask_source=None, remove_outliers=True, max_dz=100, slope_lim=(0.1, 40),
-                   keep_warped=False, bufs=None):
+                   keep_warped=False, bufs=None, profile=False):
     """One full Nuth-Kaab iteration on the device (``dcr_nuth_iteration``).
 
     Returns ``(IterResult, Grid, IterBuffers)``; ``IterResult.dx/dy/dz`` is what
@@ -99,7 +99,8 @@ def nuth_iteration(ref, src, mask_source=None, remove_outliers=True, max_dz=100,
     nbytes = L.dcr_iteration_workspace_bytes(n)
     ws = workspace(nbytes)
     res = _lib.IterResult()
-    _lib.check(L.dcr_nuth_iteration(C.byref(a), 1 if remove_outliers else 0, C.byref(res),
+    flags = (_lib.ITER_REMOVE_OUTLIERS if remove_outliers else 0) | (_lib.ITER_PROFILE if profile else 0)
+    _lib.check(L.dcr_nuth_iteration(C.byref(a), flags, C.byref(res),
                                     C.c_void_p(ws.data_ptr()), ws.numel(), _stream_ptr(torch)))
     return res, grid, bufs
 

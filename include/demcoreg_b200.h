@@ -183,9 +183,14 @@ typedef struct dcr_iter_result {
     dcr_nuth_stats nuth;
     double fit[3];               /* a, b (deg), c */
     double dx, dy, dz;           /* RETURNED shift = (-a sin b, -a cos b, -dz_med): dem_align.py:155-156, 172 */
+    float stage_ms[8];           /* DCR_ITER_PROFILE only: CUDA-event time of 0 front kernel, 1 median+MAD selects,
+                                    2 mask update+scan+subsample, 3 med_dh/dz/med_slope selects, 4 y/bin prepare+moments,
+                                    5 bin count+median passes, 6 device->host copy */
 } dcr_iter_result;
+#define DCR_ITER_REMOVE_OUTLIERS 1 /* flags of dcr_nuth_iteration: dem_align.py:91 remove_outliers */
+#define DCR_ITER_PROFILE 2         /* record per-stage CUDA events into stage_ms */
 size_t dcr_iteration_workspace_bytes(int64_t n);
-int dcr_nuth_iteration(const dcr_front_args* front, int remove_outliers, dcr_iter_result* out /* host */,
+int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_iter_result* out /* host */,
                        void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
