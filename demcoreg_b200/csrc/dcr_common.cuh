@@ -121,3 +121,126 @@ __device__ __forceinline__ unsigned long long dcr_warp_sum_u64(unsigned long lon
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+
+// ---- vectorised streaming ------------------------------------------------------------------
+// Each warp iteration covers 512 consecutive elements: lane l takes float4 #(k*32 + l), k = 0..3,
+// so every load instruction is a fully coalesced 512-byte request (128 bytes for the mask) and a
+// thread keeps 8+ independent loads in flight (the scalar grid-stride loops were latency-bound at
+// ~1.2 TB/s: profiles/sel_hist_r1a_raw.csv).  The body f sees (value..., mask byte, element index).
+// Falls back to scalar accesses for the tail and for unaligned pointers.
+#define DCR_AL16(p) ((((uintptr_t)(p)) & 15) == 0)
+#define DCR_AL4(p) ((((uintptr_t)(p)) & 3) == 0)
+#define DCR_AL8(p) ((((uintptr_t)(p)) & 7) == 0)
+
+template <typename F>
+__device__ __forceinline__ void dcr_stream1(const float* __restrict__ x, const unsigned char* __restrict__ m,
+                                            long long n, F&& f) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long nblk = (DCR_AL16(x) && DCR_AL4(m)) ? (n >> 9) : 0;
+    for (long long w = warp; w < nblk; w += nwarps) {
+        const float4* x4 = reinterpret_cast<const float4*>(x) + (w << 7);
+        const unsigned* m4 = m ? reinterpret_cast<const unsigned*>(m) + (w << 7) : nullptr;
+        float4 t[4];
+        unsigned mb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            t[k] = __ldg(x4 + k * 32 + lane);
+            mb[k] = m4 ? __ldg(m4 + k * 32 + lane) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long b = (w << 9) + ((long long)(k * 32 + lane) << 2);
+            f(t[k].x, mb[k] & 0xffu, b);
+            f(t[k].y, (mb[k] >> 8) & 0xffu, b + 1);
+            f(t[k].z, (mb[k] >> 16) & 0xffu, b + 2);
+            f(t[k].w, mb[k] >> 24, b + 3);
+        }
+    }
+    for (long long i = (nblk << 9) + warp * 32 + lane; i < n; i += nwarps * 32) f(x[i], m ? (unsigned)m[i] : 0u, i);
+}
+
+template <typename F>
+__device__ __forceinline__ void dcr_stream3(const float* __restrict__ a, const float* __restrict__ b,
+                                            const float* __restrict__ c, const unsigned char* __restrict__ m,
+                                            long long n, F&& f) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long nblk = (DCR_AL16(a) && DCR_AL16(b) && DCR_AL16(c) && DCR_AL4(m)) ? (n >> 8) : 0;
+    for (long long w = warp; w < nblk; w += nwarps) {  // 256 elements per warp iteration
+        const long long o = (w << 6);
+        const unsigned* m4 = m ? reinterpret_cast<const unsigned*>(m) + o : nullptr;
+        float4 ta[2], tb[2], tc[2];
+        unsigned mb[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            ta[k] = __ldg(reinterpret_cast<const float4*>(a) + o + k * 32 + lane);
+            tb[k] = __ldg(reinterpret_cast<const float4*>(b) + o + k * 32 + lane);
+            tc[k] = __ldg(reinterpret_cast<const float4*>(c) + o + k * 32 + lane);
+            mb[k] = m4 ? __ldg(m4 + k * 32 + lane) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const long long e = (w << 8) + ((long long)(k * 32 + lane) << 2);
+            f(ta[k].x, tb[k].x, tc[k].x, mb[k] & 0xffu, e);
+            f(ta[k].y, tb[k].y, tc[k].y, (mb[k] >> 8) & 0xffu, e + 1);
+            f(ta[k].z, tb[k].z, tc[k].z, (mb[k] >> 16) & 0xffu, e + 2);
+            f(ta[k].w, tb[k].w, tc[k].w, mb[k] >> 24, e + 3);
+        }
+    }
+    for (long long i = (nblk << 8) + warp * 32 + lane; i < n; i += nwarps * 32)
+        f(a[i], b[i], c[i], m ? (unsigned)m[i] : 0u, i);
+}
+
+template <typename F>
+__device__ __forceinline__ void dcr_stream_f_u16(const float* __restrict__ y, const unsigned short* __restrict__ q,
+                                                 long long n, F&& f) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long nblk = (DCR_AL16(y) && DCR_AL8(q)) ? (n >> 9) : 0;
+    for (long long w = warp; w < nblk; w += nwarps) {
+        const float4* y4 = reinterpret_cast<const float4*>(y) + (w << 7);
+        const uint2* q4 = reinterpret_cast<const uint2*>(q) + (w << 7);
+        float4 t[4];
+        uint2 qq[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            t[k] = __ldg(y4 + k * 32 + lane);
+            qq[k] = __ldg(q4 + k * 32 + lane);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long b = (w << 9) + ((long long)(k * 32 + lane) << 2);
+            f(t[k].x, qq[k].x & 0xffffu, b);
+            f(t[k].y, qq[k].x >> 16, b + 1);
+            f(t[k].z, qq[k].y & 0xffffu, b + 2);
+            f(t[k].w, qq[k].y >> 16, b + 3);
+        }
+    }
+    for (long long i = (nblk << 9) + warp * 32 + lane; i < n; i += nwarps * 32) f(y[i], (unsigned)q[i], i);
+}
+
+// 8 consecutive elements starting at `base` (order-sensitive kernels): vector loads when the chunk is
+// fully inside the array and the pointers are aligned, scalar otherwise.  mb[k] = 0xFFFFFFFF marks "past the end".
+__device__ __forceinline__ void dcr_load8(const float* __restrict__ x, const unsigned char* __restrict__ m,
+                                          long long base, long long n, float v[8], unsigned mb[8]) {
+    if (base + 8 <= n && DCR_AL16(x) && (m == nullptr || DCR_AL8(m)) && (base & 7) == 0) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x + base));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(x + base) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        uint2 q = make_uint2(0u, 0u);
+        if (m) q = __ldg(reinterpret_cast<const uint2*>(m + base));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { mb[k] = (q.x >> (8 * k)) & 0xffu; mb[4 + k] = (q.y >> (8 * k)) & 0xffu; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const long long i = base + k;
+            if (i < n) { v[k] = x[i]; mb[k] = m ? (unsigned)m[i] : 0u; }
+            else { v[k] = 0.f; mb[k] = 0xffffffffu; }
+        }
+    }
+}

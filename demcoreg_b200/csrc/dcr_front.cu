@@ -214,7 +214,7 @@ __device__ __noinline__ float bilinear_fallback(float ul, float ur, float lr, fl
 
 // Horn slope + aspect from a 3x3 float32 window (GDAL GDALSlopeHornAlg / GDALAspectAlg), A.2.
 // Returns false when any input is NaN (nodata).  aspect = NaN for flat.
-__device__ __forceinline__ bool horn(float w0, float w1, float w2, float w3, float w4, float w5, float w6,
+__device__ __noinline__ bool horn(float w0, float w1, float w2, float w3, float w4, float w5, float w6,
                                      float w7, float w8, double ewres, double nsres, bool want_slope,
                                      bool want_aspect, float* slope, float* aspect) {
     (void)w4;
@@ -244,6 +244,39 @@ __device__ __forceinline__ bool horn(float w0, float w1, float w2, float w3, flo
             *aspect = asp;
         }
     }
+    return true;
+}
+
+// FP32 fast path of the Horn slope/aspect with certified guard bands (DESIGN.md "front kernel"):
+// the 3x3 sums are the exact float32 sums of GDAL; atan/atan2 are evaluated in FP32 (<= ~4 ulp), and every
+// pixel whose result could change a mask-deciding quantity -- slope within 2e-6 (relative) of a slope
+// limit, aspect within 2e-4 degrees of an integer degree (the 1-degree bin edges) -- is recomputed with
+// the FP64 formulation above.  Returns false when any input is NaN; *exact = true -> caller must call horn().
+__device__ __forceinline__ bool horn_fast(float w0, float w1, float w2, float w3, float w4, float w5, float w6,
+                                          float w7, float w8, float inv8ew, float inv8ns, float slope_lo,
+                                          float slope_hi, float* slope, float* aspect, bool* exact) {
+    const float probe = ((w0 + w1) + (w2 + w3)) + ((w4 + w5) + (w6 + w7)) + w8;
+    if (isnan(probe)) return false;
+    const float a = (w0 + w3 + w3 + w6);
+    const float b = (w2 + w5 + w5 + w8);
+    const float c = (w6 + w7 + w7 + w8);
+    const float d = (w0 + w1 + w1 + w2);
+    const float dxs = a - b;  // slope numerator; aspect uses b - a = -dxs exactly
+    const float dyf = c - d;
+    const float gx = dxs * inv8ew, gy = dyf * inv8ns;
+    const float s = atanf(sqrtf(gx * gx + gy * gy)) * 57.29577951308232f;
+    bool ex = (fabsf(s - slope_lo) <= 2e-6f * slope_lo) || (fabsf(s - slope_hi) <= 2e-6f * slope_hi);
+    *slope = s;
+    if (dxs == 0.0f && dyf == 0.0f) {
+        *aspect = __int_as_float(0x7fc00000);
+    } else {
+        float af = atan2f(dyf, dxs) * 57.29577951308232f;  // atan2(dy, -dx_aspect), dx_aspect = -dxs
+        af = (af > 90.0f) ? (450.0f - af) : (90.0f - af);
+        const float fr = af - floorf(af);
+        ex = ex || (fr < 2e-4f) || (fr > 1.0f - 2e-4f) || !(af >= 0.0f) || (af >= 360.0f);
+        *aspect = af;
+    }
+    *exact = ex;
     return true;
 }
 
@@ -362,6 +395,7 @@ struct FrontParams {
     int smask_h, smask_w, smask_nx0, smask_ny0;
     int h, w;
     double ewres, nsres;
+    float inv8ew, inv8ns;
     double ref_gm_ndv, ref_gm_tol, src_gm_ndv, src_gm_tol;  // ds_getma masked_values(|x-ndv| <= tol)
     float ref_fill, src_fill;                               // value written to ref_w/src_w for invalid pixels
     float max_dz;
@@ -406,17 +440,68 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
     const int tid = threadIdx.x;
     if (tid < 3) s_cnt[tid] = 0ull;
 
-    // ---- stage the two source footprints (coalesced rows), nodata / out-of-bounds -> NaN
+    // ---- stage the two source footprints: one warp per tile row, all loads of a row pair issued before
+    //      their first use (memory-level parallelism), nodata / out-of-bounds -> NaN
     {
-        const int r_base = ti0 - 2 + p.sg.iy0, c_base = tj0 - 2 + p.sg.ix0;
-        for (int k = tid; k < F_SRC_R * F_SRC_C; k += 256) {
-            int r = k / F_SRC_C, c = k - r * F_SRC_C;
-            s_src[k] = load_px(p.src, p.sg, r_base + r, c_base + c);
+        const int lane = tid & 31, wrp = tid >> 5;
+        const float qnan = __int_as_float(0x7fc00000);
+        {
+            const int r_base = ti0 - 2 + p.sg.iy0, c_base = tj0 - 2 + p.sg.ix0;
+            for (int r = wrp; r < F_SRC_R; r += 16) {
+                float v[2][5];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int rr = r + 8 * u, gr = r_base + rr;
+                    const bool rok = rr < F_SRC_R && gr >= 0 && gr < p.sg.hs;
+                    const float* rowp = p.src + (long long)gr * p.sg.stride;
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) {
+                        const int cc = q * 32 + lane, gc = c_base + cc;
+                        v[u][q] = qnan;
+                        if (rok && cc < F_SRC_C && gc >= 0 && gc < p.sg.ws) v[u][q] = __ldg(rowp + gc);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int rr = r + 8 * u;
+                    if (rr < F_SRC_R) {
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) {
+                            const int cc = q * 32 + lane;
+                            if (cc < F_SRC_C) s_src[rr * F_SRC_C + cc] = (p.sg.has_ndv && v[u][q] == p.sg.ndv) ? qnan : v[u][q];
+                        }
+                    }
+                }
+            }
         }
-        const int rr_base = ti0 - 1 + p.rg.iy0, rc_base = tj0 - 1 + p.rg.ix0;
-        for (int k = tid; k < F_REF_R * F_REF_C; k += 256) {
-            int r = k / F_REF_C, c = k - r * F_REF_C;
-            s_ref[k] = load_px(p.ref, p.rg, rr_base + r, rc_base + c);
+        {
+            const int r_base = ti0 - 1 + p.rg.iy0, c_base = tj0 - 1 + p.rg.ix0;
+            for (int r = wrp; r < F_REF_R; r += 16) {
+                float v[2][5];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int rr = r + 8 * u, gr = r_base + rr;
+                    const bool rok = rr < F_REF_R && gr >= 0 && gr < p.rg.hs;
+                    const float* rowp = p.ref + (long long)gr * p.rg.stride;
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) {
+                        const int cc = q * 32 + lane, gc = c_base + cc;
+                        v[u][q] = qnan;
+                        if (rok && cc < F_REF_C && gc >= 0 && gc < p.rg.ws) v[u][q] = __ldg(rowp + gc);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int rr = r + 8 * u;
+                    if (rr < F_REF_R) {
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) {
+                            const int cc = q * 32 + lane;
+                            if (cc < F_REF_C) s_ref[rr * F_REF_C + cc] = (p.rg.has_ndv && v[u][q] == p.rg.ndv) ? qnan : v[u][q];
+                        }
+                    }
+                }
+            }
         }
     }
     __syncthreads();
@@ -434,13 +519,16 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
         s_sw[rr * F_SW_C + cc] = v;
     }
 
-    // ---- main pass: thread = (column c, half hf), 16 consecutive rows, sliding x-pass window
+    // ---- main pass: thread = (column c, half hf), 16 consecutive rows, sliding x-pass window.
+    //      Partial unrolling only: the fully unrolled kernel was 137 KB of SASS and stalled on
+    //      instruction fetch (profiles/front_kernel_r1b: stall_no_instruction 4.5 per issue).
     const int c = tid & (F_TW - 1);
     const int hf = tid >> 7;
     const int rbeg = hf * F_ROWS_PER_THREAD;
     const int j = tj0 + c;
-    float dh_reg[F_ROWS_PER_THREAD];
-    unsigned valid_bits = 0;  // bit r: base-valid (ref & src unmasked, static mask clear)
+    unsigned valid_bits = 0;  // bit rr: base-valid (ref & src unmasked, static mask clear)
+    unsigned maxdz_bits = 0;  // bit rr: |dh| > max_dz
+    unsigned n_base = 0, n_maxdz = 0, n_slope = 0;
     {
         double xs0, xs1, xs2, xr0, xr1, xr2;
         {
@@ -457,7 +545,9 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
             u += F_REF_C;
             xr2 = xpass(p.rg.wx, u[0], u[1], u[2], u[3]);
         }
-#pragma unroll
+        const int s_near = (p.sg.ny0 - p.sg.iy0) * F_SRC_C + (p.sg.nx0 - p.sg.ix0);
+        const int r_near = (p.rg.ny0 - p.rg.iy0) * F_REF_C + (p.rg.nx0 - p.rg.ix0);
+#pragma unroll 4
         for (int rr = 0; rr < F_ROWS_PER_THREAD; ++rr) {
             const int r = rbeg + rr;
             const int i = ti0 + r;
@@ -465,45 +555,45 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
             const double xs3 = xpass(p.sg.wx, q[0], q[1], q[2], q[3]);
             const float* u = s_ref + (r + 3) * F_REF_C + c;
             const double xr3 = xpass(p.rg.wx, u[0], u[1], u[2], u[3]);
-            double so = ypass(p.sg.wy, xs0, xs1, xs2, xs3);
-            double ro = ypass(p.rg.wy, xr0, xr1, xr2, xr3);
+            const double so = ypass(p.sg.wy, xs0, xs1, xs2, xs3);
+            const double ro = ypass(p.rg.wy, xr0, xr1, xr2, xr3);
             xs0 = xs1; xs1 = xs2; xs2 = xs3;
             xr0 = xr1; xr1 = xr2; xr2 = xr3;
             float sv, rv;
             {
-                const float nearest = s_src[(r + 2 + (p.sg.ny0 - p.sg.iy0)) * F_SRC_C + (c + 2 + (p.sg.nx0 - p.sg.ix0))];
-                if (isnan(so))
-                    sv = bilinear_fallback(s_src[(r + 2) * F_SRC_C + c + 2], s_src[(r + 2) * F_SRC_C + c + 3],
-                                           s_src[(r + 3) * F_SRC_C + c + 3], s_src[(r + 3) * F_SRC_C + c + 2], nearest,
-                                           p.sg.fx, p.sg.fy);
-                else
-                    sv = isnan(nearest) ? nearest : (float)so;
+                const float* t = s_src + (r + 2) * F_SRC_C + (c + 2);  // UL pixel of the 2x2
+                const float nearest = t[s_near];
+                if (isnan(so)) sv = bilinear_fallback(t[0], t[1], t[F_SRC_C + 1], t[F_SRC_C], nearest, p.sg.fx, p.sg.fy);
+                else sv = isnan(nearest) ? nearest : (float)so;
             }
             {
-                const float nearest = s_ref[(r + 1 + (p.rg.ny0 - p.rg.iy0)) * F_REF_C + (c + 1 + (p.rg.nx0 - p.rg.ix0))];
-                if (isnan(ro))
-                    rv = bilinear_fallback(s_ref[(r + 1) * F_REF_C + c + 1], s_ref[(r + 1) * F_REF_C + c + 2],
-                                           s_ref[(r + 2) * F_REF_C + c + 2], s_ref[(r + 2) * F_REF_C + c + 1], nearest,
-                                           p.rg.fx, p.rg.fy);
-                else
-                    rv = isnan(nearest) ? nearest : (float)ro;
+                const float* t = s_ref + (r + 1) * F_REF_C + (c + 1);
+                const float nearest = t[r_near];
+                if (isnan(ro)) rv = bilinear_fallback(t[0], t[1], t[F_REF_C + 1], t[F_REF_C], nearest, p.rg.fx, p.rg.fy);
+                else rv = isnan(nearest) ? nearest : (float)ro;
             }
             const bool inside = (i < p.h) && (j < p.w);
             if (!inside) sv = __int_as_float(0x7fc00000);
             s_sw[(r + 1) * F_SW_C + (c + 1)] = sv;
             // ds_getma masks: |x - ndv| <= tol in double (numpy masked_values)
-            bool sm = isnan(sv) || fabs((double)sv - p.src_gm_ndv) <= p.src_gm_tol;
-            bool rm = isnan(rv) || fabs((double)rv - p.ref_gm_ndv) <= p.ref_gm_tol;
+            const bool sm = isnan(sv) || fabs((double)sv - p.src_gm_ndv) <= p.src_gm_tol;
+            const bool rm = isnan(rv) || fabs((double)rv - p.ref_gm_ndv) <= p.ref_gm_tol;
             bool base_ok = inside && !sm && !rm;
             if (base_ok && p.smask) {
                 const int mi = i + p.smask_ny0, mj = j + p.smask_nx0;
                 if (mi < 0 || mj < 0 || mi >= p.smask_h || mj >= p.smask_w) base_ok = false;
                 else if (__ldg(p.smask + (long long)mi * p.smask_stride + mj)) base_ok = false;
             }
-            dh_reg[rr] = base_ok ? (sv - rv) : 0.0f;
-            if (base_ok) valid_bits |= (1u << rr);
+            const float dh = base_ok ? (sv - rv) : 0.0f;
+            if (base_ok) {
+                valid_bits |= (1u << rr);
+                ++n_base;
+                if (p.use_max_dz && (dh < -p.max_dz || dh > p.max_dz)) maxdz_bits |= (1u << rr);
+                else ++n_maxdz;
+            }
             if (inside) {
                 const long long o = (long long)i * p.w + j;
+                p.dh[o] = dh;
                 if (p.ref_w) p.ref_w[o] = isnan(rv) ? p.ref_fill : rv;
                 if (p.src_w) p.src_w[o] = isnan(sv) ? p.src_fill : sv;
             }
@@ -511,15 +601,14 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
     }
     __syncthreads();
 
-    // ---- Horn stencil on the warped src + epilogue (masks, counters, stores)
-    unsigned n_base = 0, n_maxdz = 0, n_slope = 0;
+    // ---- Horn stencil on the warped src + mask byte
     {
         float w0, w1, w2, w3, w4, w5, w6, w7, w8;
         const float* q = s_sw + rbeg * F_SW_C + c;
         w0 = q[0]; w1 = q[1]; w2 = q[2];
         q += F_SW_C;
         w3 = q[0]; w4 = q[1]; w5 = q[2];
-#pragma unroll
+#pragma unroll 2
         for (int rr = 0; rr < F_ROWS_PER_THREAD; ++rr) {
             const int r = rbeg + rr;
             const int i = ti0 + r;
@@ -527,30 +616,22 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
             w6 = q[0]; w7 = q[1]; w8 = q[2];
             if (i < p.h && j < p.w) {
                 float sl = DCR_GDALDEM_NDV, as = DCR_GDALDEM_NDV;
-                unsigned bits = 0;
-                bool s_ok = false, a_ok = false;
+                unsigned bits = DCR_M_SLOPE | DCR_M_ASPECT;
                 if (i > 0 && j > 0 && i < p.h - 1 && j < p.w - 1) {
                     float sv, av;
-                    if (horn(w0, w1, w2, w3, w4, w5, w6, w7, w8, p.ewres, p.nsres, true, true, &sv, &av)) {
+                    bool ex;
+                    if (horn_fast(w0, w1, w2, w3, w4, w5, w6, w7, w8, p.inv8ew, p.inv8ns, p.slope_lo, p.slope_hi, &sv, &av,
+                                  &ex)) {
+                        if (ex) horn(w0, w1, w2, w3, w4, w5, w6, w7, w8, p.ewres, p.nsres, true, true, &sv, &av);
                         sl = sv;
-                        s_ok = true;
-                        if (!isnan(av)) { as = av; a_ok = true; }
+                        // range_fltr(slope, slope_lim): masked_outside keeps lo <= s <= hi
+                        if (!(sl < p.slope_lo) && !(sl > p.slope_hi)) { bits &= ~DCR_M_SLOPE; ++n_slope; }
+                        if (!isnan(av)) { as = av; bits &= ~DCR_M_ASPECT; }
                     }
                 }
-                // range_fltr(slope, slope_lim): masked_outside keeps lo <= s <= hi
-                const bool s_keep = s_ok && !(sl < p.slope_lo) && !(sl > p.slope_hi);
-                if (s_keep) ++n_slope;
-                if (!s_keep) bits |= DCR_M_SLOPE;
-                if (!a_ok) bits |= DCR_M_ASPECT;
-                const float dh = dh_reg[rr];
                 if (!(valid_bits & (1u << rr))) bits |= DCR_M_BASE;
-                else {
-                    ++n_base;
-                    if (p.use_max_dz && (dh < -p.max_dz || dh > p.max_dz)) bits |= DCR_M_MAXDZ;
-                    else ++n_maxdz;
-                }
+                else if (maxdz_bits & (1u << rr)) bits |= DCR_M_MAXDZ;
                 const long long o = (long long)i * p.w + j;
-                p.dh[o] = dh;
                 p.slope[o] = sl;
                 p.aspect[o] = as;
                 p.maskbits[o] = (unsigned char)bits;
@@ -592,6 +673,8 @@ int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cuda
     p.w = a->w;
     p.ewres = a->ewres;
     p.nsres = a->nsres;
+    p.inv8ew = (float)(1.0 / (8.0 * a->ewres));
+    p.inv8ns = (float)(1.0 / (8.0 * a->nsres));
     // memwarp_multi: identity -> dataset unchanged (own ndv); resampled -> dst_ndv
     const double rn = a->ref_geom.identity ? a->ref_desc.ndv : a->dst_ndv;
     const double sn = a->src_geom.identity ? a->src_desc.ndv : a->dst_ndv;

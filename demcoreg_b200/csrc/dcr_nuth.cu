@@ -29,11 +29,11 @@ struct NuthPartial {
     double s, ss;
 };
 
-// y = dh / tan(deg2rad(slope)) in float32 (numpy: deg2rad = x * f32(pi/180); tan correctly rounded via FP64)
+// y = dh / tan(deg2rad(slope)) in float32, like numpy (deg2rad = x * f32(pi/180); np.tan on float32 is a
+// few-ulp libm/SVML routine, so FP32 tanf -- also a few ulp -- is as close as any implementation can get).
 __device__ __forceinline__ float nuth_y(float dh, float slope) {
     const float rad = slope * 0.017453292519943295f;
-    const float t = (float)tan((double)rad);
-    return dh / t;
+    return dh / tanf(rad);
 }
 
 __global__ void __launch_bounds__(256) nuth_prepare_kernel(const float* __restrict__ dh, const float* __restrict__ slope,
@@ -44,13 +44,12 @@ __global__ void __launch_bounds__(256) nuth_prepare_kernel(const float* __restri
     __shared__ NuthPartial sp[8];
     unsigned long long cnt = 0;
     double s = 0.0, ss = 0.0;
-    const long long step = (long long)gridDim.x * 256;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += step) {
+    const unsigned rej = m ? reject : 0u;
+    dcr_stream3(dh, slope, aspect, m, n, [&](float d, float sl, float a, unsigned mb, long long i) {
         unsigned short b = BIN_INVALID;
         float yv = 0.f;
-        if (!(m && (m[i] & reject))) {
-            const float a = aspect[i];
-            yv = nuth_y(dh[i], slope[i]);
+        if (!(mb & rej)) {
+            yv = nuth_y(d, sl);
             ++cnt;
             s += (double)yv;
             ss += (double)yv * (double)yv;
@@ -65,7 +64,7 @@ __global__ void __launch_bounds__(256) nuth_prepare_kernel(const float* __restri
         }
         y[i] = yv;
         bin[i] = b;
-    }
+    });
     cnt = dcr_warp_sum_u64(cnt);
     s = dcr_warp_sum(s);
     ss = dcr_warp_sum(ss);
@@ -142,12 +141,9 @@ __global__ void __launch_bounds__(256) bin_hist_kernel(const float* __restrict__
     constexpr int shift_prev = (PASS == 1) ? 21 : 10;
     constexpr int dshift = (PASS == 0) ? 21 : (PASS == 1 ? 10 : 0);
     constexpr unsigned dmask = (PASS == 2) ? 1023u : 2047u;
-    const long long step = (long long)gridDim.x * 256;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += step) {
-        const unsigned b = bin[i];
-        if (b >= NB) continue;
-        const float yv = y[i];
-        if (!(yv >= rmin && yv <= rmax)) continue;
+    dcr_stream_f_u16(y, bin, n, [&](float yv, unsigned b, long long) {
+        if (b >= NB) return;
+        if (!(yv >= rmin && yv <= rmax)) return;
         const unsigned key = dcr_f2key(yv);
         if (PASS == 0) {
             atomicAdd(&s_cnt[b], 1u);
@@ -157,7 +153,7 @@ __global__ void __launch_bounds__(256) bin_hist_kernel(const float* __restrict__
             if (!s_same[b] && ((key ^ s_phi[b]) >> shift_prev) == 0u)
                 atomicAdd(&ghist[(NB + b) * 2048u + ((key >> dshift) & dmask)], 1u);
         }
-    }
+    });
     if (PASS == 0) {
         __syncthreads();
         for (int k = threadIdx.x; k < NB; k += 256)
@@ -359,6 +355,26 @@ __global__ void __launch_bounds__(256) zshift_kernel(float* __restrict__ band, i
                                                      double tol, float ndv32, float dz, const float* __restrict__ dzg) {
     const long long n = (long long)h * w;
     const long long step = (long long)gridDim.x * 256;
+    if (stride == w && DCR_AL16(band) && (dzg == nullptr || DCR_AL16(dzg))) {
+        // contiguous band: float4 read-modify-write
+        const long long n4 = n >> 2;
+        float4* b4 = reinterpret_cast<float4*>(band);
+        for (long long k = (long long)blockIdx.x * 256 + threadIdx.x; k < n4; k += step) {
+            float4 v = b4[k];
+            float4 z = make_float4(dz, dz, dz, dz);
+            if (dzg) z = __ldg(reinterpret_cast<const float4*>(dzg) + k);
+            v.x = (fabs((double)v.x - ndv) <= tol) ? ndv32 : v.x + z.x;
+            v.y = (fabs((double)v.y - ndv) <= tol) ? ndv32 : v.y + z.y;
+            v.z = (fabs((double)v.z - ndv) <= tol) ? ndv32 : v.z + z.z;
+            v.w = (fabs((double)v.w - ndv) <= tol) ? ndv32 : v.w + z.w;
+            b4[k] = v;
+        }
+        for (long long k = (n4 << 2) + (long long)blockIdx.x * 256 + threadIdx.x; k < n; k += step) {
+            const float v = band[k];
+            band[k] = (fabs((double)v - ndv) <= tol) ? ndv32 : v + (dzg ? dzg[k] : dz);
+        }
+        return;
+    }
     for (long long k = (long long)blockIdx.x * 256 + threadIdx.x; k < n; k += step) {
         const int i = (int)(k / w), j = (int)(k - (long long)i * w);
         float* p = band + (long long)i * stride + j;
@@ -407,23 +423,38 @@ __global__ void mad_thresholds_kernel(IterDev* d, int remove_outliers) {
 }
 
 #define MU_CHUNK 2048
-__global__ void __launch_bounds__(256) mask_update_kernel(const float* __restrict__ dh, unsigned char* __restrict__ m,
+__global__ void __launch_bounds__(256) mask_update_kernel(const float* __restrict__ dh, unsigned char* m,
                                                           long long n, IterDev* d, unsigned* __restrict__ chunk_cnt) {
     __shared__ unsigned s_a[8], s_b[8];
     const float lo = d->mad_lo, hi = d->mad_hi;
     const long long base = (long long)blockIdx.x * MU_CHUNK + threadIdx.x * 8;
     unsigned n_mad = 0, n_fin = 0;
+    float v[8];
+    unsigned mb[8];
+    dcr_load8(dh, m, base, n, v, mb);
+    unsigned changed = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const long long i = base + k;
-        if (i >= n) break;
-        unsigned bits = m[i];
+        if (mb[k] > 0xffu) continue;  // past the end
+        unsigned bits = mb[k];
         if (!(bits & (DCR_M_BASE | DCR_M_MAXDZ))) {
-            const float v = dh[i];
-            if (v < lo || v > hi) { bits |= DCR_M_MAD; m[i] = (unsigned char)bits; }
+            if (v[k] < lo || v[k] > hi) { bits |= DCR_M_MAD; changed |= 1u << k; }
             else ++n_mad;
         }
+        mb[k] = bits;
         if (!(bits & DCR_M_DIFF)) ++n_fin;
+    }
+    if (changed) {
+        if (base + 8 <= n && DCR_AL8(m)) {
+            uint2 q;
+            q.x = mb[0] | (mb[1] << 8) | (mb[2] << 16) | (mb[3] << 24);
+            q.y = mb[4] | (mb[5] << 8) | (mb[6] << 16) | (mb[7] << 24);
+            *reinterpret_cast<uint2*>(m + base) = q;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (changed & (1u << k)) m[base + k] = (unsigned char)mb[k];
+        }
     }
     n_mad = __reduce_add_sync(0xffffffffu, n_mad);
     n_fin = __reduce_add_sync(0xffffffffu, n_fin);

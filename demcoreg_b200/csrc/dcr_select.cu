@@ -41,18 +41,20 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_hist_kernel(const SelView v, 
     constexpr int shift_prev = (PASS == 1) ? 21 : 10;
     constexpr int dshift = (PASS == 0) ? 21 : (PASS == 1 ? 10 : 0);
     constexpr unsigned dmask = (PASS == 2) ? 1023u : 2047u;
-    const long long step = (long long)gridDim.x * SEL_THREADS;
-    for (long long i = (long long)blockIdx.x * SEL_THREADS + threadIdx.x; i < n; i += step) {
-        float val;
-        if (!sel_get(v, i, center, &val)) continue;
-        const unsigned key = dcr_f2key(val);
+    const unsigned reject = v.m ? v.reject : 0u;
+    const int transform = v.transform;
+    dcr_stream1(v.x, v.m, n, [&](float t, unsigned mb, long long) {
+        if (mb & reject) return;
+        if (transform == 1) t = fabsf(t - center);
+        if (isnan(t)) return;
+        const unsigned key = dcr_f2key(t);
         if (PASS == 0) {
             atomicAdd(&h[0][key >> 21], 1u);
         } else {
             if (((key ^ plo) >> shift_prev) == 0u) atomicAdd(&h[0][(key >> dshift) & dmask], 1u);
             if (!same && ((key ^ phi) >> shift_prev) == 0u) atomicAdd(&h[1][(key >> dshift) & dmask], 1u);
         }
-    }
+    });
     __syncthreads();
     for (int k = threadIdx.x; k < 2 * 2048; k += SEL_THREADS) {
         unsigned c = (&h[0][0])[k];
@@ -188,17 +190,15 @@ __global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ 
     unsigned long long cnt = 0;
     double s = 0.0, ss = 0.0;
     float mn = INFINITY, mx = -INFINITY;
-    const long long step = (long long)gridDim.x * 256;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += step) {
-        if (m && (m[i] & reject)) continue;
-        const float v = x[i];
-        if (isnan(v)) continue;
+    const unsigned rej = m ? reject : 0u;
+    dcr_stream1(x, m, n, [&](float v, unsigned mb, long long) {
+        if ((mb & rej) || isnan(v)) return;
         ++cnt;
         s += (double)v;
         ss += (double)v * (double)v;
         mn = fminf(mn, v);
         mx = fmaxf(mx, v);
-    }
+    });
     cnt = dcr_warp_sum_u64(cnt);
     s = dcr_warp_sum(s);
     ss = dcr_warp_sum(ss);
@@ -261,11 +261,12 @@ __global__ void __launch_bounds__(256) chunk_count_kernel(const unsigned char* _
     __shared__ unsigned sw[8];
     const long long base = (long long)blockIdx.x * CHUNK + threadIdx.x * 8;
     unsigned c = 0;
+    float v[8];
+    unsigned mb[8];
+    dcr_load8(x, m, base, n, v, mb);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const long long i = base + k;
-        if (i < n && !(m && (m[i] & reject)) && !isnan(x[i])) ++c;
-    }
+    for (int k = 0; k < 8; ++k)
+        if (!(mb[k] & (reject | 0xffffff00u)) && !isnan(v[k])) ++c;
     c = __reduce_add_sync(0xffffffffu, c);
     if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = c;
     __syncthreads();
@@ -307,16 +308,12 @@ __global__ void __launch_bounds__(256) compress_strided_kernel(const float* __re
     if (stride_ptr && stride <= 1) return;  // iteration driver: no subsample needed
     const long long base = (long long)blockIdx.x * CHUNK + threadIdx.x * 8;
     float vals[8];
+    unsigned mb[8];
     unsigned flags = 0, c = 0;
+    dcr_load8(x, m, base, n, vals, mb);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const long long i = base + k;
-        vals[k] = 0.f;
-        if (i < n && !(m && (m[i] & reject))) {
-            const float v = x[i];
-            if (!isnan(v)) { vals[k] = v; flags |= 1u << k; ++c; }
-        }
-    }
+    for (int k = 0; k < 8; ++k)
+        if (!(mb[k] & (reject | 0xffffff00u)) && !isnan(vals[k])) { flags |= 1u << k; ++c; }
     unsigned total;
     unsigned ex = dcr_block_excl_scan(c, s_scratch, &total);
     long long rank = off[blockIdx.x] + ex;

@@ -175,7 +175,7 @@ def _compare_iteration(res, det, odx, ody, odz):
     assert np.array_equal(np.isnan(gm), ~ok)
     np.testing.assert_allclose(gm[ok], nd['bin_med'][ok], rtol=1e-4, atol=1e-4)
     assert res.med_dh == nd['med_dh']
-    assert res.med_slope == nd['med_slope']
+    assert abs(res.med_slope - nd['med_slope']) <= 1e-5 * abs(nd['med_slope'])  # FP32 Horn fast path: few ulp
     assert res.dz_med == det['dz_med']
     assert abs(res.dx - odx) < OFFTOL and abs(res.dy - ody) < OFFTOL and abs(res.dz - odz) < OFFTOL
 
