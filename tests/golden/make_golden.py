@@ -1,0 +1,41 @@
+"""Generate the regression vectors under tests/golden/.
+
+The reference (dshean/demcoreg) ships no golden vectors and cannot be imported in this image
+(pygeotools / GDAL absent), so these vectors are produced by the CPU oracle restatement
+(oracle/) and pin ITS behaviour: they are regression vectors, not reference outputs
+("parity unpinned").  Run from the repo root:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from demcoreg_b200 import synth  # noqa: E402
+from oracle import pygeotools_restated as pg, dem_align as oda  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def nuth_iter(n=128, name="nuth_iter_128.npz"):
+    p = synth.make_pair(n=n, res=30.0, seed=20260777, static_mask_frac=0.2, nodata_frac=0.02, median_slope=14.0)
+    gt = p['gt']
+    gt_src = (gt[0] + 3.4217, gt[1], 0.0, gt[3] - 1.8140, 0.0, gt[5])
+    det = {}
+    ms = oda.MaskSource(p['mask'], gt)
+    dx, dy, dz, sm, _ = oda.compute_offset(pg.MemDataset(p['ref'], gt, p['ndv']), pg.MemDataset(p['src'], gt_src, p['ndv']),
+                                           mask_source=ms, details=det)
+    np.savez_compressed(os.path.join(HERE, name), ref=p['ref'], src=p['src'], mask=p['mask'], gt=np.array(gt),
+                        gt_src=np.array(gt_src), ref_w=det['ref_w'], src_w=det['src_w'],
+                        static_mask_packed=np.packbits(sm), bin_count=det['nuth']['bin_count'].astype(np.int64),
+                        bin_med=det['nuth']['bin_med'], shift=np.array([dx, dy, dz], dtype=np.float64),
+                        fit=np.array(det['fit'], dtype=np.float64), dz_med=np.float32(det['dz_med']),
+                        counts=np.array([det['count_base'], det['count_final'], det['nuth']['n_common'],
+                                         det['nuth']['n_final']], dtype=np.int64))
+    print(name, "shift", dx, dy, dz, "bins>=9:", int((det['nuth']['bin_count'] >= 9).sum()))
+
+
+if __name__ == "__main__":
+    nuth_iter()

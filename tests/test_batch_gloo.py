@@ -1,0 +1,61 @@
+"""Pair-sharded batch logic under a real world_size-2 process group (gloo, CPU)."""
+import os
+import socket
+
+import numpy as np
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _fake_align(pair):
+    # deterministic stand-in for dem_align.align: "recovers" the shift stored in the pair
+    return dict(dx=pair["shift"][0], dy=pair["shift"][1], dz=-pair["shift"][2], n_iter=3 + pair["id"] % 2)
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from demcoreg_b200 import batch
+    pairs = [dict(id=k, shift=(0.5 * k, -0.25 * k, 0.1 * k)) for k in range(7)]
+    mine = batch.shard(len(pairs), rank, world)
+    out = batch.align_batch(pairs, _fake_align)
+    q.put((rank, mine, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pair_sharding_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res.sort()
+    assert res[0][1] == [0, 2, 4, 6] and res[1][1] == [1, 3, 5]
+    for rank, mine, out in res:
+        assert len(out) == 7
+        for k, r in enumerate(out):
+            assert r == dict(dx=0.5 * k, dy=-0.25 * k, dz=-0.1 * k, n_iter=3 + k % 2)
+
+
+def test_shard_single_process():
+    from demcoreg_b200 import batch
+    assert batch.shard(5, 0, 1) == [0, 1, 2, 3, 4]
+    assert sorted(sum((batch.shard(10, r, 4) for r in range(4)), [])) == list(range(10))
+    out = batch.align_batch([dict(id=0, shift=(1.0, 2.0, 3.0))], _fake_align)
+    assert out == [dict(dx=1.0, dy=2.0, dz=-3.0, n_iter=3)]

@@ -254,3 +254,23 @@ def test_compute_offset_nuth_api(cuda):
     for f in (np.sin, np.cos):
         assert abs(fit[0] * f(np.deg2rad(fit[1])) - ofit[0] * f(np.deg2rad(ofit[1]))) < 1e-5
     assert abs(fit[2] - ofit[2]) < 1e-5
+
+
+def test_gpu_against_golden_vectors(cuda):
+    """The CUDA path against the committed regression vectors (tests/golden/make_golden.py)."""
+    import os
+    from demcoreg_b200 import engine, _lib
+    from demcoreg_b200.raster import Raster, MaskSource
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "nuth_iter_128.npz"))
+    ref = Raster(g['ref'], tuple(g['gt']), -9999.0)
+    src = Raster(g['src'], tuple(g['gt_src']), -9999.0)
+    res, grid, bufs = engine.nuth_iteration(ref, src, MaskSource(g['mask'], tuple(g['gt'])), keep_warped=True)
+    assert np.array_equal(bufs.src_w.cpu().numpy(), g['src_w']) and np.array_equal(bufs.ref_w.cpu().numpy(), g['ref_w'])
+    sm = ((bufs.maskbits & _lib.M_DIFF) != 0).cpu().numpy()
+    assert np.array_equal(np.packbits(sm), g['static_mask_packed'])
+    assert np.array_equal(np.array(res.nuth.bin_count[:]), g['bin_count'])
+    assert [res.count_base, res.count_final, res.nuth.n_common, res.nuth.n_final] == list(g['counts'])
+    np.testing.assert_allclose(np.array(res.nuth.bin_med[:], dtype=np.float64), g['bin_med'], rtol=1e-4, atol=1e-4,
+                               equal_nan=True)
+    assert res.dz_med == g['dz_med']
+    np.testing.assert_allclose([res.dx, res.dy, res.dz], g['shift'], rtol=0, atol=OFFTOL)
