@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libdemcoreg_b200.so")
 NBINS = 360
 M_BASE, M_MAXDZ, M_MAD, M_SLOPE, M_ASPECT = 0x01, 0x02, 0x04, 0x08, 0x10
 M_DIFF = M_BASE | M_MAXDZ | M_MAD | M_SLOPE
-ITER_REMOVE_OUTLIERS, ITER_PROFILE = 1, 2
+ITER_REMOVE_OUTLIERS, ITER_PROFILE, ITER_RADIX_ONLY = 1, 2, 4
 
 
 class RasterDesc(C.Structure):
@@ -57,7 +57,8 @@ class IterResult(C.Structure):
                 ("med1", C.c_float), ("nmad1", C.c_float), ("mad_lo", C.c_float), ("mad_hi", C.c_float),
                 ("dz_med", C.c_float), ("med_dh", C.c_float), ("med_slope", C.c_float), ("c_seed", C.c_float),
                 ("nuth", NuthStats), ("fit", C.c_double * 3), ("dx", C.c_double), ("dy", C.c_double),
-                ("dz", C.c_double), ("stage_ms", C.c_float * 8)]
+                ("dz", C.c_double), ("stage_ms", C.c_float * 8), ("select_engine", C.c_int32),
+                ("_pad", C.c_int32)]
 
 
 # every symbol include/demcoreg_b200.h declares: name -> (restype, argtypes)
@@ -77,6 +78,9 @@ SYMBOLS = {
     "dcr_select_workspace_bytes": (C.c_size_t, []),
     "dcr_select_quantiles": (C.c_int, [_P, _P, C.c_uint32, C.c_int64, C.c_int, C.c_float, C.POINTER(C.c_double),
                                        C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int64), _P, C.c_size_t, _P]),
+    "dcr_select_workspace_bytes_n": (C.c_size_t, [C.c_int64]),
+    "dcr_select_quantiles_radix": (C.c_int, [_P, _P, C.c_uint32, C.c_int64, C.c_int, C.c_float, C.POINTER(C.c_double),
+                                             C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int64), _P, C.c_size_t, _P]),
     "dcr_moments": (C.c_int, [_P, _P, C.c_uint32, C.c_int64, C.POINTER(C.c_double), _P, C.c_size_t, _P]),
     "dcr_compress_strided": (C.c_int, [_P, _P, C.c_uint32, C.c_int64, C.c_int64, _P, C.c_int64,
                                        C.POINTER(C.c_int64), _P, C.c_size_t, _P]),

@@ -1,0 +1,341 @@
+// K3 fast path: exact order statistics by sample-bracketing ("bsel").
+//
+// The radix select of dcr_select.cu needs three histogram passes over all the data, each limited by
+// shared-memory atomics.  Here ONE streaming pass suffices:
+//   1. bsel_sample_kernel  - one CTA gathers S = 8192 strided samples, sorts them (bitonic, shared memory)
+//                            and takes the keys at sample ranks r -+ 5 sigma as a bracket [klo, khi] that
+//                            contains the wanted order statistic(s) with overwhelming probability.
+//   2. bsel_main_kernel    - bandwidth-bound pass: counts the elements below klo in registers, appends the
+//                            few per cent inside the bracket to a candidate buffer and histograms them
+//                            (2048 linear bins of the bracket) -- atomics only for those few per cent.
+//   3. bsel_find_kernel    - locates the histogram bin(s) holding the exact global rank(s) and VERIFIES that
+//                            the rank really lies inside the bracket (exactness does not depend on luck:
+//                            a miss, an overflow or heavy ties raise `fallback`, and the caller reruns the
+//                            3-pass radix select).
+//   4. bsel_refine_kernel  - radix-refines the remaining <= 21 key bits over the candidate buffer only (11 bits per
+//                            launch, last-CTA-done finalisation), then applies numpy's linear interpolation.
+// Same semantics as dcr_sel_enqueue (numpy.percentile, linear, exact float64 rank).
+#include <string.h>
+#include "dcr_common.cuh"
+#include "dcr_internal.cuh"
+
+#define BS_S 8192          // samples
+#define BS_THREADS 256
+
+__device__ __forceinline__ void bitonic_sort_smem(unsigned* s, int n /* power of two */) {
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // j is a power of two
+                const int l = i + j;
+                const bool up = ((i & k) == 0);
+                const unsigned a = s[i], b = s[l];
+                if ((a > b) == up) { s[i] = b; s[l] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ bool bsel_key(const SelView& v, float center, float x, unsigned mb, unsigned* key) {
+    if (mb & v.reject) return false;
+    if (v.transform == 1) x = fabsf(x - center);
+    if (isnan(x)) return false;
+    *key = dcr_f2key(x);
+    return true;
+}
+
+__device__ __forceinline__ void bsel_ranks(long long count, double q_percent, long long* klo, long long* khi, double* g) {
+    const double vi = (double)(count - 1) * (q_percent / 100.0);  // exact rank in float64
+    *klo = (long long)floor(vi);
+    *khi = *klo + 1 < count ? *klo + 1 : count - 1;
+    *g = vi - (double)(*klo);
+}
+
+__global__ void __launch_bounds__(1024) bsel_sample_kernel(const SelView v, double q_percent, BselState* st) {
+    __shared__ unsigned s[BS_S];
+    __shared__ unsigned s_valid;
+    const long long n = v.n_ptr ? *v.n_ptr : v.n;
+    const float center = v.center_ptr ? *v.center_ptr : v.center_imm;
+    if (threadIdx.x == 0) s_valid = 0;
+    __syncthreads();
+    unsigned nv = 0;
+    const bool all = n <= BS_S;  // small input: the "sample" is the whole array and the answer is exact
+    for (int k = threadIdx.x; k < BS_S; k += 1024) {
+        unsigned key = 0xFFFFFFFFu;
+        // stratified positions with a hashed offset inside each stratum: a plain stride of n/S aliases with the
+        // raster width (8192 x 8192: every sample would sit in column 0, where the Horn border is masked)
+        long long i = k;
+        if (!all) {
+            const unsigned long long lo = ((unsigned long long)k * (unsigned long long)n) / BS_S;
+            const unsigned long long hi = ((unsigned long long)(k + 1) * (unsigned long long)n) / BS_S;
+            const unsigned long long hsh = ((unsigned long long)k * 0x9E3779B97F4A7C15ull) >> 20;
+            i = (long long)(lo + hsh % (hi - lo));
+        }
+        if (i < n) {
+            unsigned kk;
+            if (bsel_key(v, center, v.x[i], v.m ? (unsigned)v.m[i] : 0u, &kk)) { key = kk; ++nv; }
+        }
+        s[k] = key;
+    }
+    nv = __reduce_add_sync(0xffffffffu, nv);
+    if ((threadIdx.x & 31) == 0 && nv) atomicAdd(&s_valid, nv);
+    __syncthreads();
+    bitonic_sort_smem(s, BS_S);
+    if (threadIdx.x == 0) {
+        const long long m = s_valid;
+        st->fallback = 0;
+        st->done = 0;
+        st->empty = 0;
+        st->below = 0; st->total = 0; st->ncand = 0; st->nsmall = 0; st->ticket = 0;
+        if (all) {
+            st->done = 1;
+            st->count = m;
+            if (m == 0) {
+                st->empty = 1;
+                st->v_lo = st->v_hi = st->result = __int_as_float(0x7fc00000);
+            } else {
+                long long klo, khi; double g;
+                bsel_ranks(m, q_percent, &klo, &khi, &g);
+                st->gamma = g;
+                st->v_lo = dcr_key2f(s[klo]); st->v_hi = dcr_key2f(s[khi]);
+                st->result = dcr_lerp32(st->v_lo, st->v_hi, g);
+            }
+        } else {
+            unsigned klo = 0u, khi = 0xFFFFFFFEu;
+            if (m > 0) {
+                const double f = q_percent / 100.0;
+                const double r = f * (double)(m - 1);
+                const double d = 5.0 * sqrt((double)m * f * (1.0 - f)) + 8.0;
+                const long long a = (long long)floor(r - d), b = (long long)ceil(r + d);
+                if (a >= 0) klo = s[a];
+                if (b < m) khi = s[b];
+            }
+            st->klo = klo; st->khi = khi;
+            // linear bins of the bracket: (key - klo) >> shift < 2048
+            const unsigned long long span = (unsigned long long)khi - klo + 1ull;
+            int shift = 0;
+            while ((span >> shift) > 2048ull) ++shift;
+            st->shift = shift;
+        }
+    }
+}
+
+#define BS_STAGE 6144  // per-CTA staging of in-bracket keys (one global reservation per CTA instead of per warp)
+__global__ void __launch_bounds__(BS_THREADS) bsel_main_kernel(const SelView v, BselState* st, unsigned* __restrict__ ghist,
+                                                               unsigned* __restrict__ cand, unsigned cap) {
+    __shared__ unsigned h[2048];
+    __shared__ unsigned s_buf[BS_STAGE];
+    __shared__ unsigned s_n, s_gbase;
+    __shared__ unsigned long long s_below, s_total;
+    if (st->done) return;
+    for (int k = threadIdx.x; k < 2048; k += BS_THREADS) h[k] = 0u;
+    if (threadIdx.x == 0) { s_below = 0ull; s_total = 0ull; s_n = 0u; }
+    __syncthreads();
+    const long long n = v.n_ptr ? *v.n_ptr : v.n;
+    const float center = v.center_ptr ? *v.center_ptr : v.center_imm;
+    const unsigned klo = st->klo, khi = st->khi;
+    const int shift = st->shift;
+    const unsigned reject = v.m ? v.reject : 0u;
+    const int transform = v.transform;
+    const int lane = threadIdx.x & 31;
+    unsigned below = 0, total = 0;
+    unsigned keys[16];
+    unsigned flags = 0;
+    dcr_stream1_groups(v.x, v.m, n,
+        [&](float x, unsigned mb, long long, int slot) {
+            if (mb <= 0xffu && !(mb & reject)) {
+                if (transform == 1) x = fabsf(x - center);
+                if (!isnan(x)) {
+                    const unsigned key = dcr_f2key(x);
+                    ++total;
+                    if (key < klo) ++below;
+                    else if (key <= khi) { keys[slot] = key; flags |= 1u << slot; }
+                }
+            }
+        },
+        [&]() {
+            // one warp-aggregated reservation in the CTA staging buffer per group of 512 elements
+            if (__any_sync(0xffffffffu, flags != 0u)) {
+                const unsigned mine = __popc(flags);
+                const unsigned inc = dcr_warp_incl_scan(mine);
+                unsigned base = 0;
+                if (lane == 31) base = atomicAdd(&s_n, inc);
+                base = __shfl_sync(0xffffffffu, base, 31);
+                unsigned pos = base + inc - mine;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    if (flags & (1u << k)) {
+                        const unsigned key = keys[k];
+                        if (pos < BS_STAGE) s_buf[pos] = key;
+                        else {  // staging full (dense bracket): straight to the global buffer
+                            const unsigned gq = atomicAdd(&st->ncand, 1u);
+                            if (gq < cap) cand[gq] = key;
+                        }
+                        ++pos;
+                        atomicAdd(&h[(key - klo) >> shift], 1u);
+                    }
+                }
+            }
+            flags = 0;
+        });
+    below = __reduce_add_sync(0xffffffffu, below);
+    total = __reduce_add_sync(0xffffffffu, total);
+    if (lane == 0) {
+        if (below) atomicAdd(&s_below, (unsigned long long)below);
+        if (total) atomicAdd(&s_total, (unsigned long long)total);
+    }
+    __syncthreads();
+    const unsigned nst = s_n < BS_STAGE ? s_n : BS_STAGE;
+    if (threadIdx.x == 0) {
+        s_gbase = nst ? atomicAdd(&st->ncand, nst) : 0u;
+        if (s_below) atomicAdd(&st->below, s_below);
+        if (s_total) atomicAdd(&st->total, s_total);
+    }
+    for (int k = threadIdx.x; k < 2048; k += BS_THREADS)
+        if (h[k]) atomicAdd(&ghist[k], h[k]);
+    __syncthreads();
+    const unsigned gb = s_gbase;
+    for (unsigned k = threadIdx.x; k < nst; k += BS_THREADS)
+        if (gb + k < cap) cand[gb + k] = s_buf[k];
+}
+
+// Level-0 find: the bracket-histogram bin of each of the two ranks, after VERIFYING that both ranks fall
+// inside the bracket and that no candidate was dropped.  off = key - klo; bin0 = off >> shift.
+__global__ void __launch_bounds__(1024) bsel_find_kernel(BselState* st, unsigned* ghist, double q_percent, unsigned cap) {
+    __shared__ unsigned s_scratch[33];
+    __shared__ unsigned s_cum[2049];
+    if (st->done) return;
+    const int t = threadIdx.x;
+    const unsigned a = ghist[2 * t], b = ghist[2 * t + 1];
+    unsigned total;
+    const unsigned ex = dcr_block_excl_scan(a + b, s_scratch, &total);
+    s_cum[2 * t] = ex;
+    s_cum[2 * t + 1] = ex + a;
+    if (t == 0) s_cum[2048] = total;
+    __syncthreads();
+    ghist[2 * t] = 0u;
+    ghist[2 * t + 1] = 0u;
+    if (t == 0) {
+        const long long count = (long long)st->total;
+        st->count = count;
+        if (count == 0) {
+            st->empty = 1; st->done = 1;
+            st->v_lo = st->v_hi = st->result = __int_as_float(0x7fc00000);
+        } else {
+            long long klo, khi; double g;
+            bsel_ranks(count, q_percent, &klo, &khi, &g);
+            st->gamma = g;
+            const long long c[2] = {klo - (long long)st->below, khi - (long long)st->below};
+            const long long nin = (long long)total;
+            const bool ok = (c[0] >= 0) && (c[1] < nin) && (st->ncand <= cap) && ((long long)st->ncand == nin);
+            if (!ok) { st->fallback = 1; st->done = 1; }
+            else {
+                for (int r = 0; r < 2; ++r) {
+                    int lo = 0, hi = 2047;
+                    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((long long)s_cum[mid] <= c[r]) lo = mid; else hi = mid - 1; }
+                    st->prefix[r] = (unsigned)lo << st->shift;
+                    st->rem[r] = c[r] - (long long)s_cum[lo];
+                }
+                st->cur_shift = st->shift;
+                if (st->shift == 0) {  // bins are single keys already
+                    const float x0 = dcr_key2f(st->klo + st->prefix[0]), x1 = dcr_key2f(st->klo + st->prefix[1]);
+                    st->v_lo = x0; st->v_hi = x1;
+                    st->result = dcr_lerp32(x0, x1, g);
+                    st->done = 1;
+                }
+            }
+        }
+    }
+}
+
+// Refinement over the candidate buffer only (a few per cent of the data): histogram the next <= 11 bits of
+// the candidates sharing the resolved prefix of each rank; the last CTA to finish locates the sub-bins.
+// Ties of any multiplicity are handled (the final level has one bin per distinct key).
+__global__ void __launch_bounds__(BS_THREADS) bsel_refine_kernel(BselState* st, const unsigned* __restrict__ cand,
+                                                                 unsigned* ghist /* [2][2048] */) {
+    __shared__ bool s_last;
+    if (st->done) return;
+    const unsigned ncand = st->ncand;
+    const unsigned klo = st->klo;
+    const int cs = st->cur_shift;
+    const int ns = cs > 11 ? cs - 11 : 0;
+    const unsigned smask = (1u << (cs - ns)) - 1u;
+    const unsigned p0 = st->prefix[0] >> cs, p1 = st->prefix[1] >> cs;
+    for (unsigned i = blockIdx.x * BS_THREADS + threadIdx.x; i < ncand; i += gridDim.x * BS_THREADS) {
+        const unsigned off = cand[i] - klo;
+        const unsigned pre = off >> cs;
+        if (pre == p0) atomicAdd(&ghist[(off >> ns) & smask], 1u);
+        if (p1 != p0 && pre == p1) atomicAdd(&ghist[2048 + ((off >> ns) & smask)], 1u);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    {
+        __shared__ unsigned s_scratch[33];
+        __shared__ unsigned s_sel[2];
+        __shared__ long long s_cumsel[2];
+        for (int r = 0; r < 2; ++r) {
+            const unsigned* h = ghist + ((r == 1 && p1 != p0) ? 2048 : 0);
+            const long long k = st->rem[r];
+            unsigned vv[8], sum = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { vv[q] = __ldcg(h + threadIdx.x * 8 + q); sum += vv[q]; }
+            unsigned tot;
+            long long ex = dcr_block_excl_scan(sum, s_scratch, &tot);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (ex <= k && k < ex + vv[q]) { s_sel[r] = threadIdx.x * 8 + q; s_cumsel[r] = ex; }
+                ex += vv[q];
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x < 2) {
+            const int r = threadIdx.x;
+            st->prefix[r] |= s_sel[r] << ns;
+            st->rem[r] = st->rem[r] - s_cumsel[r];
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 4096; k += BS_THREADS) ghist[k] = 0u;
+    if (threadIdx.x == 0) {
+        st->cur_shift = ns;
+        st->ticket = 0;
+        if (ns == 0) {
+            const float x0 = dcr_key2f(klo + st->prefix[0]), x1 = dcr_key2f(klo + st->prefix[1]);
+            st->v_lo = x0; st->v_hi = x1;
+            st->result = dcr_lerp32(x0, x1, st->gamma);
+            st->done = 1;
+        }
+    }
+}
+
+size_t dcr_bsel_scratch_bytes(long long n) {
+    return dcr_al256(4096 * sizeof(unsigned)) + dcr_al256(dcr_bsel_cap(n) * sizeof(unsigned));
+}
+unsigned dcr_bsel_cap(long long n) {
+    long long c = n / 6;
+    if (c < 65536) c = 65536;
+    if (c > 0x7fffffffLL) c = 0x7fffffffLL;
+    return (unsigned)c;
+}
+
+int dcr_bsel_enqueue(const SelView& v, double q_percent, BselState* st, void* scratch, long long n_max, cudaStream_t s) {
+    const unsigned cap = dcr_bsel_cap(n_max);
+    char* p = (char*)scratch;
+    unsigned* hist = (unsigned*)p;
+    p += dcr_al256(4096 * sizeof(unsigned));
+    unsigned* cand = (unsigned*)p;
+    const int grid = dcr_num_sms() * 8;
+    DCR_CUDA_OK(cudaMemsetAsync(hist, 0, 4096 * sizeof(unsigned), s));
+    bsel_sample_kernel<<<1, 1024, 0, s>>>(v, q_percent, st);
+    bsel_main_kernel<<<grid, BS_THREADS, 0, s>>>(v, st, hist, cand, cap);
+    bsel_find_kernel<<<1, 1024, 0, s>>>(st, hist, q_percent, cap);
+    bsel_refine_kernel<<<dcr_num_sms(), BS_THREADS, 0, s>>>(st, cand, hist);  // shift -> max(shift-11, 0)
+    bsel_refine_kernel<<<dcr_num_sms(), BS_THREADS, 0, s>>>(st, cand, hist);  // -> 0 (returns at once if done)
+    DCR_LAUNCH_OK("bsel kernels");
+    return 0;
+}

@@ -161,6 +161,79 @@ __device__ __forceinline__ void dcr_stream1(const float* __restrict__ x, const u
     for (long long i = (nblk << 9) + warp * 32 + lane; i < n; i += nwarps * 32) f(x[i], m ? (unsigned)m[i] : 0u, i);
 }
 
+// Warp-uniform variant: every lane of a warp calls f the same number of times (so f may use warp
+// collectives); out-of-range lanes of the tail get mb = 0xFFFFFFFF (callers must skip mb > 0xFF).
+template <typename F>
+__device__ __forceinline__ void dcr_stream1_uniform(const float* __restrict__ x, const unsigned char* __restrict__ m,
+                                                    long long n, F&& f) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long nblk = (DCR_AL16(x) && DCR_AL4(m)) ? (n >> 9) : 0;
+    for (long long w = warp; w < nblk; w += nwarps) {
+        const float4* x4 = reinterpret_cast<const float4*>(x) + (w << 7);
+        const unsigned* m4 = m ? reinterpret_cast<const unsigned*>(m) + (w << 7) : nullptr;
+        float4 t[4];
+        unsigned mb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            t[k] = __ldg(x4 + k * 32 + lane);
+            mb[k] = m4 ? __ldg(m4 + k * 32 + lane) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long b = (w << 9) + ((long long)(k * 32 + lane) << 2);
+            f(t[k].x, mb[k] & 0xffu, b);
+            f(t[k].y, (mb[k] >> 8) & 0xffu, b + 1);
+            f(t[k].z, (mb[k] >> 16) & 0xffu, b + 2);
+            f(t[k].w, mb[k] >> 24, b + 3);
+        }
+    }
+    for (long long base = (nblk << 9) + warp * 32; base < n; base += nwarps * 32) {
+        const long long i = base + lane;
+        const bool in = i < n;
+        f(in ? x[i] : 0.f, in ? (m ? (unsigned)m[i] : 0u) : 0xFFFFFFFFu, i);
+    }
+}
+
+// Group variant: f(value, mask byte, index, slot) is called for the 16 elements of a lane's group
+// (slot = 0..15, a compile-time constant after unrolling), then g() once per group -- warp-uniform,
+// so g may use warp collectives to aggregate what the 16 f calls gathered in registers.
+template <typename F, typename G>
+__device__ __forceinline__ void dcr_stream1_groups(const float* __restrict__ x, const unsigned char* __restrict__ m,
+                                                   long long n, F&& f, G&& g) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long nblk = (DCR_AL16(x) && DCR_AL4(m)) ? (n >> 9) : 0;
+    for (long long w = warp; w < nblk; w += nwarps) {
+        const float4* x4 = reinterpret_cast<const float4*>(x) + (w << 7);
+        const unsigned* m4 = m ? reinterpret_cast<const unsigned*>(m) + (w << 7) : nullptr;
+        float4 t[4];
+        unsigned mb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            t[k] = __ldg(x4 + k * 32 + lane);
+            mb[k] = m4 ? __ldg(m4 + k * 32 + lane) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long b = (w << 9) + ((long long)(k * 32 + lane) << 2);
+            f(t[k].x, mb[k] & 0xffu, b, 4 * k);
+            f(t[k].y, (mb[k] >> 8) & 0xffu, b + 1, 4 * k + 1);
+            f(t[k].z, (mb[k] >> 16) & 0xffu, b + 2, 4 * k + 2);
+            f(t[k].w, mb[k] >> 24, b + 3, 4 * k + 3);
+        }
+        g();
+    }
+    for (long long base = (nblk << 9) + warp * 32; base < n; base += nwarps * 32) {
+        const long long i = base + lane;
+        const bool in = i < n;
+        f(in ? x[i] : 0.f, in ? (m ? (unsigned)m[i] : 0u) : 0xFFFFFFFFu, i, 0);
+        g();
+    }
+}
+
 template <typename F>
 __device__ __forceinline__ void dcr_stream3(const float* __restrict__ a, const float* __restrict__ b,
                                             const float* __restrict__ c, const unsigned char* __restrict__ m,

@@ -35,6 +35,26 @@ struct SelState {
 // hist: device scratch of DCR_SEL_HIST_WORDS u32.
 int dcr_sel_enqueue(const SelView& v, double q_percent, SelState* st, unsigned* hist, cudaStream_t stream);
 
+// ---- sample-bracket selection (dcr_bsel.cu): one streaming pass, verified, with radix fallback ----
+struct BselState {
+    unsigned klo, khi;               // bracket keys (inclusive)
+    int shift;                       // (key - klo) >> shift indexes the 2048-bin bracket histogram
+    int fallback;                    // 1: bracket missed / overflow / heavy ties -> result invalid, use the radix select
+    int done, empty;
+    unsigned long long below, total; // valid elements with key < klo ; all valid elements
+    unsigned ncand, nsmall, ticket, ncollect;
+    unsigned prefix[2];              // resolved high bits of (key - klo) for the two ranks
+    int cur_shift, pad2;             // bits of (key - klo) still unresolved
+    long long rem[2];                // ranks inside the resolved prefixes
+    long long count;
+    double gamma;
+    float v_lo, v_hi, result;
+    int pad;
+};
+unsigned dcr_bsel_cap(long long n);
+size_t dcr_bsel_scratch_bytes(long long n);
+int dcr_bsel_enqueue(const SelView& v, double q_percent, BselState* st, void* scratch, long long n_max, cudaStream_t s);
+
 // ---- nuth (dcr_nuth.cu) ----
 struct NuthDev;  // device block
 

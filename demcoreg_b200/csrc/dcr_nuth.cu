@@ -7,6 +7,7 @@
 // Nuth branch of dem_align.compute_offset (dem_align.py:62-172).
 #include <string.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "dcr_common.cuh"
 #include "dcr_internal.cuh"
 
@@ -402,6 +403,9 @@ struct IterDev {
     unsigned long long counters[4];  // base, after max_dz, slope-valid, (pad)
     unsigned long long count_mad, count_final;
     SelState sel[5];                 // 0 med(dh|A)  1 med|dh-med|  2 med(dh|F)  3 med(subsample)  4 med(slope)
+    BselState bsel[5];               // the same five selections through the one-pass sample-bracket select
+    float selres[5];                 // results of whichever engine ran (device-side consumers read these)
+    int selpad;
     float nmad, mad_lo, mad_hi, pad0;
     long long total_final, stride, dense_n;
     NuthDev nuth;
@@ -409,13 +413,13 @@ struct IterDev {
 
 __global__ void mad_thresholds_kernel(IterDev* d, int remove_outliers) {
     if (threadIdx.x) return;
-    if (!remove_outliers || d->sel[0].empty) {
+    if (!remove_outliers || isnan(d->selres[0])) {
         d->nmad = 0.f; d->mad_lo = -INFINITY; d->mad_hi = INFINITY;
         return;
     }
     // filtlib.mad_fltr: mad = 1.4826 * median(|x - med|) ; keep med - 3*mad <= x <= med + 3*mad  (float32)
-    const float med = d->sel[0].result;
-    const float nmad = d->sel[1].result * 1.4826f;
+    const float med = d->selres[0];
+    const float nmad = d->selres[1] * 1.4826f;
     const float t = 3.0f * nmad;
     d->nmad = nmad;
     d->mad_lo = med - t;
@@ -484,11 +488,93 @@ static size_t iter_ws_bytes(long long n, int grid) {
     const long long nch = (n + MU_CHUNK - 1) / MU_CHUNK;
     return nuth_ws_bytes(n, grid) + dcr_al256(sizeof(IterDev)) + dcr_al256(DCR_SEL_HIST_WORDS * sizeof(unsigned)) +
            dcr_al256(nch * sizeof(unsigned)) + dcr_al256(nch * sizeof(long long)) +
-           dcr_al256((size_t)(n < 6000016 ? n : 6000016) * sizeof(float)) + 4096;
+           dcr_al256((size_t)(n < 6000016 ? n : 6000016) * sizeof(float)) + dcr_bsel_scratch_bytes(n) + 4096;
 }
 extern "C" size_t dcr_iteration_workspace_bytes(int64_t n) { return iter_ws_bytes(n, dcr_num_sms() * 8); }
 
 int dcr_chunk_scan_enqueue(const unsigned* cnt, long long nchunks, long long* off, long long* total, cudaStream_t s);
+
+__global__ void sel_publish_kernel(IterDev* d, int k, int use_bsel) {
+    if (threadIdx.x == 0) d->selres[k] = use_bsel ? d->bsel[k].result : d->sel[k].result;
+}
+
+struct IterWs {
+    IterDev* d;
+    unsigned* hist;
+    unsigned* chunk_cnt;
+    long long* chunk_off;
+    float* dense;
+    long long dense_cap;
+    void* bsel_scratch;
+    NuthWs nw;
+};
+
+// one exact median (q = 50) of view v into d->selres[k], through either engine
+static int iter_select(const SelView& v, int k, const IterWs& w, long long n, int use_bsel, cudaStream_t s) {
+    int rc;
+    if (use_bsel) rc = dcr_bsel_enqueue(v, 50.0, &w.d->bsel[k], w.bsel_scratch, n, s);
+    else rc = dcr_sel_enqueue(v, 50.0, &w.d->sel[k], w.hist, s);
+    if (rc) return rc;
+    sel_publish_kernel<<<1, 32, 0, s>>>(w.d, k, use_bsel);
+    return 0;
+}
+
+static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, int use_bsel, const IterWs& w, int grid,
+                             cudaStream_t s, cudaEvent_t* ev) {
+    const long long n = (long long)front->h * front->w;
+    const long long nch = (n + MU_CHUNK - 1) / MU_CHUNK;
+    IterDev* d = w.d;
+    int rc;
+#define STAGE_MARK(k) do { if (ev) DCR_CUDA_OK(cudaEventRecord(ev[k], s)); } while (0)
+    STAGE_MARK(0);
+    DCR_CUDA_OK(cudaMemsetAsync(d, 0, sizeof(IterDev), s));
+    dcr_front_args fa = *front;
+    if (!remove_outliers) fa.use_max_dz = 0;
+    if ((rc = dcr_front_launch(&fa, d->counters, s))) return rc;
+
+    STAGE_MARK(1);
+    SelView v;
+    memset(&v, 0, sizeof(v));
+    v.x = front->dh; v.m = front->maskbits; v.n = n;
+    if (remove_outliers) {
+        v.reject = DCR_M_BASE | DCR_M_MAXDZ; v.transform = 0;
+        if ((rc = iter_select(v, 0, w, n, use_bsel, s))) return rc;
+        v.transform = 1; v.center_ptr = &d->selres[0];
+        if ((rc = iter_select(v, 1, w, n, use_bsel, s))) return rc;
+    }
+    STAGE_MARK(2);
+    mad_thresholds_kernel<<<1, 32, 0, s>>>(d, remove_outliers);
+    mask_update_kernel<<<(unsigned)nch, 256, 0, s>>>(front->dh, front->maskbits, n, d, w.chunk_cnt);
+    if ((rc = dcr_chunk_scan_enqueue(w.chunk_cnt, nch, w.chunk_off, &d->total_final, s))) return rc;
+    stride_kernel<<<1, 32, 0, s>>>(d);
+    if ((rc = dcr_compress_enqueue(front->dh, front->maskbits, DCR_M_DIFF, n, w.chunk_off, 1, &d->stride, w.dense,
+                                   w.dense_cap, s)))
+        return rc;
+    STAGE_MARK(3);
+    // med_dh over the final mask (coreglib.py:214) and dz on the (possibly strided) subsample (dem_align.py:114-115)
+    v.reject = DCR_M_DIFF; v.transform = 0; v.center_ptr = nullptr;
+    if ((rc = iter_select(v, 2, w, n, use_bsel, s))) return rc;
+    {
+        SelView vd;
+        memset(&vd, 0, sizeof(vd));
+        vd.x = w.dense; vd.m = nullptr; vd.n = 0; vd.n_ptr = &d->dense_n;
+        if ((rc = iter_select(vd, 3, w, w.dense_cap, use_bsel, s))) return rc;
+    }
+    {
+        SelView vs;
+        memset(&vs, 0, sizeof(vs));
+        vs.x = front->slope; vs.m = front->maskbits; vs.reject = DCR_M_SLOPE; vs.n = n;
+        if ((rc = iter_select(vs, 4, w, n, use_bsel, s))) return rc;
+    }
+    STAGE_MARK(4);
+    if ((rc = nuth_enqueue(front->dh, front->slope, front->aspect, front->maskbits, DCR_M_DIFF | DCR_M_ASPECT, n,
+                           remove_outliers, w.nw, grid, s, ev ? ev[5] : nullptr)))
+        return rc;
+    DCR_LAUNCH_OK("iteration kernels");
+    STAGE_MARK(6);
+#undef STAGE_MARK
+    return 0;
+}
 
 extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_iter_result* out, void* workspace,
                                   size_t workspace_bytes, void* stream) {
@@ -498,93 +584,71 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_it
     static thread_local cudaEvent_t ev[8] = {nullptr};
     if (prof && !ev[0])
         for (int k = 0; k < 8; ++k) DCR_CUDA_OK(cudaEventCreate(&ev[k]));
-#define STAGE_MARK(k) do { if (prof) DCR_CUDA_OK(cudaEventRecord(ev[k], s)); } while (0)
     const long long n = (long long)front->h * front->w;
     DCR_ARG(n > 0, "empty grid");
     const int grid = dcr_num_sms() * 8;
     DCR_ARG(workspace_bytes >= iter_ws_bytes(n, grid), "workspace too small");
     cudaStream_t s = (cudaStream_t)stream;
     DcrBump ws(workspace, workspace_bytes);
-    IterDev* d = ws.take<IterDev>(1);
-    unsigned* hist = ws.take<unsigned>(DCR_SEL_HIST_WORDS);
+    IterWs w;
+    w.d = ws.take<IterDev>(1);
+    w.hist = ws.take<unsigned>(DCR_SEL_HIST_WORDS);
     const long long nch = (n + MU_CHUNK - 1) / MU_CHUNK;
-    unsigned* chunk_cnt = ws.take<unsigned>(nch);
-    long long* chunk_off = ws.take<long long>(nch);
-    const long long dense_cap = n < 6000016 ? n : 6000016;
-    float* dense = ws.take<float>(dense_cap);
-    NuthWs nw;
-    if (nuth_ws_carve(ws, n, grid, &nw)) return -1;
-    nw.nd = &d->nuth;
-
-    STAGE_MARK(0);
-    DCR_CUDA_OK(cudaMemsetAsync(d, 0, sizeof(IterDev), s));
-    dcr_front_args fa = *front;
-    if (!remove_outliers) fa.use_max_dz = 0;
-    int rc = dcr_front_launch(&fa, d->counters, s);
-    if (rc) return rc;
-
-    STAGE_MARK(1);
-    SelView v;
-    memset(&v, 0, sizeof(v));
-    v.x = front->dh; v.m = front->maskbits; v.n = n;
-    if (remove_outliers) {
-        v.reject = DCR_M_BASE | DCR_M_MAXDZ; v.transform = 0;
-        if ((rc = dcr_sel_enqueue(v, 50.0, &d->sel[0], hist, s))) return rc;
-        v.transform = 1; v.center_ptr = &d->sel[0].result;
-        if ((rc = dcr_sel_enqueue(v, 50.0, &d->sel[1], hist, s))) return rc;
-    }
-    STAGE_MARK(2);
-    mad_thresholds_kernel<<<1, 32, 0, s>>>(d, remove_outliers);
-    mask_update_kernel<<<(unsigned)nch, 256, 0, s>>>(front->dh, front->maskbits, n, d, chunk_cnt);
-    if ((rc = dcr_chunk_scan_enqueue(chunk_cnt, nch, chunk_off, &d->total_final, s))) return rc;
-    stride_kernel<<<1, 32, 0, s>>>(d);
-    if ((rc = dcr_compress_enqueue(front->dh, front->maskbits, DCR_M_DIFF, n, chunk_off, 1, &d->stride, dense, dense_cap, s)))
-        return rc;
-    STAGE_MARK(3);
-    // med_dh over the final mask (coreglib.py:214) and dz on the (possibly strided) subsample (dem_align.py:114-115)
-    v.reject = DCR_M_DIFF; v.transform = 0; v.center_ptr = nullptr;
-    if ((rc = dcr_sel_enqueue(v, 50.0, &d->sel[2], hist, s))) return rc;
-    {
-        SelView vd;
-        memset(&vd, 0, sizeof(vd));
-        vd.x = dense; vd.m = nullptr; vd.n = 0; vd.n_ptr = &d->dense_n;
-        if ((rc = dcr_sel_enqueue(vd, 50.0, &d->sel[3], hist, s))) return rc;
-    }
-    {
-        SelView vs;
-        memset(&vs, 0, sizeof(vs));
-        vs.x = front->slope; vs.m = front->maskbits; vs.reject = DCR_M_SLOPE; vs.n = n;
-        if ((rc = dcr_sel_enqueue(vs, 50.0, &d->sel[4], hist, s))) return rc;
-    }
-    STAGE_MARK(4);
-    if ((rc = nuth_enqueue(front->dh, front->slope, front->aspect, front->maskbits, DCR_M_DIFF | DCR_M_ASPECT, n,
-                           remove_outliers, nw, grid, s, prof ? ev[5] : nullptr)))
-        return rc;
-    DCR_LAUNCH_OK("iteration kernels");
-    STAGE_MARK(6);
+    w.chunk_cnt = ws.take<unsigned>(nch);
+    w.chunk_off = ws.take<long long>(nch);
+    w.dense_cap = n < 6000016 ? n : 6000016;
+    w.dense = ws.take<float>(w.dense_cap);
+    w.bsel_scratch = ws.take<char>(dcr_bsel_scratch_bytes(n));
+    if (nuth_ws_carve(ws, n, grid, &w.nw)) return -1;
+    w.nw.nd = &w.d->nuth;
+    IterDev* d = w.d;
 
     static thread_local IterDev* hd = nullptr;
     if (!hd) DCR_CUDA_OK(cudaHostAlloc((void**)&hd, sizeof(IterDev), cudaHostAllocDefault));
-    DCR_CUDA_OK(cudaMemcpyAsync(hd, d, sizeof(IterDev), cudaMemcpyDeviceToHost, s));
-    STAGE_MARK(7);
-    DCR_CUDA_OK(cudaStreamSynchronize(s));
+    int engine_used = (flags & DCR_ITER_RADIX_ONLY) ? 0 : 1;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        int rc = iteration_enqueue(front, remove_outliers, engine_used, w, grid, s, prof ? ev : nullptr);
+        if (rc) return rc;
+        DCR_CUDA_OK(cudaMemcpyAsync(hd, d, sizeof(IterDev), cudaMemcpyDeviceToHost, s));
+        if (prof) DCR_CUDA_OK(cudaEventRecord(ev[7], s));
+        DCR_CUDA_OK(cudaStreamSynchronize(s));
+        if (!engine_used) break;
+        // the one-pass selects verify themselves on the device; if any bracket missed (or hit heavy ties)
+        // the whole iteration is redone with the 3-pass radix select (exact by construction)
+        bool fb = false;
+        for (int k = 0; k < 5; ++k) fb = fb || (hd->bsel[k].fallback != 0);
+        if (!fb) break;
+        if (getenv("DCR_DEBUG")) {
+            for (int k = 0; k < 5; ++k) {
+                const BselState& b = hd->bsel[k];
+                fprintf(stderr, "[dcr] bsel[%d] fallback=%d klo=%08x khi=%08x shift=%d below=%llu total=%llu ncand=%u "
+                        "prefix=[%u,%u] rem=[%lld,%lld] count=%lld done=%d\n", k, b.fallback, b.klo, b.khi,
+                        b.shift, b.below, b.total, b.ncand, b.prefix[0], b.prefix[1], b.rem[0], b.rem[1], b.count, b.done);
+            }
+        }
+        engine_used = 0;
+        // the front kernel's mask bytes were updated in place by mask_update: rerun from scratch
+    }
 
     memset(out, 0, sizeof(*out));
     if (prof)
         for (int k = 0; k < 7; ++k) DCR_CUDA_OK(cudaEventElapsedTime(&out->stage_ms[k], ev[k], ev[k + 1]));
+    out->select_engine = engine_used;
+    float selres[5];
+    for (int k = 0; k < 5; ++k) selres[k] = engine_used ? hd->bsel[k].result : hd->sel[k].result;
     out->count_base = (int64_t)hd->counters[0];
     out->count_maxdz = (int64_t)hd->counters[1];
     out->count_slope = (int64_t)hd->counters[2];
     out->count_mad = (int64_t)hd->count_mad;
     out->count_final = (int64_t)hd->count_final;
     out->stats_stride = hd->stride;
-    out->med1 = hd->sel[0].result;
+    out->med1 = selres[0];
     out->nmad1 = hd->nmad;
     out->mad_lo = hd->mad_lo;
     out->mad_hi = hd->mad_hi;
-    out->med_dh = hd->sel[2].result;
-    out->dz_med = hd->stride > 1 ? hd->sel[3].result : hd->sel[2].result;
-    out->med_slope = hd->sel[4].result;
+    out->med_dh = selres[2];
+    out->dz_med = hd->stride > 1 ? selres[3] : selres[2];
+    out->med_slope = selres[4];
     nuth_dev_to_stats(hd->nuth, &out->nuth);
     out->dz = -(double)out->dz_med;
     if (out->count_base == 0) { out->status = 1; return 0; }
@@ -607,7 +671,7 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_it
     }
     out->n_valid_bins = nb;
     if (nb >= 90 && (cmax - cmin) >= 1.0) {
-        rc = dcr_fit_nuth(xc, ym, nb, out->fit);
+        int rc = dcr_fit_nuth(xc, ym, nb, out->fit);
         if (rc) return rc;
         const double br = out->fit[1] * (M_PI / 180.0);
         out->dx = -(out->fit[0] * sin(br));

@@ -146,12 +146,64 @@ int dcr_sel_enqueue(const SelView& v, double q_percent, SelState* st, unsigned* 
 }
 
 extern "C" size_t dcr_select_workspace_bytes(void) {
-    return dcr_al256(DCR_SEL_HIST_WORDS * sizeof(unsigned)) + dcr_al256(16 * sizeof(SelState)) + 1024;
+    // worst case used by engine.py for any n: query with dcr_select_workspace_bytes_n for large inputs
+    return dcr_al256(DCR_SEL_HIST_WORDS * sizeof(unsigned)) + dcr_al256(16 * sizeof(SelState)) +
+           dcr_al256(16 * sizeof(BselState)) + dcr_bsel_scratch_bytes(0) + 1024;
+}
+extern "C" size_t dcr_select_workspace_bytes_n(int64_t n) {
+    return dcr_al256(DCR_SEL_HIST_WORDS * sizeof(unsigned)) + dcr_al256(16 * sizeof(SelState)) +
+           dcr_al256(16 * sizeof(BselState)) + dcr_bsel_scratch_bytes(n) + 1024;
 }
 
 extern "C" int dcr_select_quantiles(const float* x, const uint8_t* mask, uint32_t reject, int64_t n, int transform,
                                     float center, const double* q_percent, int nq, float* out, int64_t* count,
                                     void* workspace, size_t workspace_bytes, void* stream) {
+    DCR_ARG(x && q_percent && out && workspace, "null pointer");
+    DCR_ARG(nq >= 1 && nq <= 16, "1 <= nq <= 16");
+    DCR_ARG(n >= 0, "n >= 0");
+    DCR_ARG(workspace_bytes >= dcr_select_workspace_bytes_n(n), "workspace too small (dcr_select_workspace_bytes_n)");
+    cudaStream_t s = (cudaStream_t)stream;
+    DcrBump ws(workspace, workspace_bytes);
+    unsigned* hist = ws.take<unsigned>(DCR_SEL_HIST_WORDS);
+    SelState* st = ws.take<SelState>(16);
+    BselState* bst = ws.take<BselState>(16);
+    void* scratch = ws.take<char>(dcr_bsel_scratch_bytes(n));
+    SelView v;
+    v.x = x; v.m = mask; v.reject = reject; v.transform = transform; v.center_ptr = nullptr; v.center_imm = center;
+    v.n = n; v.n_ptr = nullptr;
+    // fast path: one streaming pass per quantile (dcr_bsel.cu) ...
+    for (int k = 0; k < nq; ++k) {
+        int rc = dcr_bsel_enqueue(v, q_percent[k], bst + k, scratch, n, s);
+        if (rc) return rc;
+    }
+    BselState hb[16];
+    DCR_CUDA_OK(cudaMemcpyAsync(hb, bst, nq * sizeof(BselState), cudaMemcpyDeviceToHost, s));
+    DCR_CUDA_OK(cudaStreamSynchronize(s));
+    // ... verified on the device; a quantile whose bracket missed is redone with the 3-pass radix select
+    bool any = false;
+    for (int k = 0; k < nq; ++k) {
+        out[k] = hb[k].result;
+        if (hb[k].fallback) {
+            any = true;
+            int rc = dcr_sel_enqueue(v, q_percent[k], st + k, hist, s);
+            if (rc) return rc;
+        }
+    }
+    if (count) *count = hb[0].count;
+    if (any) {
+        SelState hst[16];
+        DCR_CUDA_OK(cudaMemcpyAsync(hst, st, nq * sizeof(SelState), cudaMemcpyDeviceToHost, s));
+        DCR_CUDA_OK(cudaStreamSynchronize(s));
+        for (int k = 0; k < nq; ++k)
+            if (hb[k].fallback) { out[k] = hst[k].result; if (count && k == 0) *count = hst[0].count; }
+    }
+    return 0;
+}
+
+// radix-only variant (tests, and the reference point for profiles)
+extern "C" int dcr_select_quantiles_radix(const float* x, const uint8_t* mask, uint32_t reject, int64_t n, int transform,
+                                          float center, const double* q_percent, int nq, float* out, int64_t* count,
+                                          void* workspace, size_t workspace_bytes, void* stream) {
     DCR_ARG(x && q_percent && out && workspace, "null pointer");
     DCR_ARG(nq >= 1 && nq <= 16, "1 <= nq <= 16");
     DCR_ARG(n >= 0, "n >= 0");

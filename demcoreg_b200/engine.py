@@ -86,7 +86,7 @@ def make_front_args(ref, src, mask_source, max_dz, use_max_dz, slope_lim, keep_w
 
 
 def nuth_iteration(ref, src, mask_source=None, remove_outliers=True, max_dz=100, slope_lim=(0.1, 40),
-                   keep_warped=False, bufs=None, profile=False):
+                   keep_warped=False, bufs=None, profile=False, radix_only=False):
     """One full Nuth-Kaab iteration on the device (``dcr_nuth_iteration``).
 
     Returns ``(IterResult, Grid, IterBuffers)``; ``IterResult.dx/dy/dz`` is what
@@ -99,7 +99,8 @@ def nuth_iteration(ref, src, mask_source=None, remove_outliers=True, max_dz=100,
     nbytes = L.dcr_iteration_workspace_bytes(n)
     ws = workspace(nbytes)
     res = _lib.IterResult()
-    flags = (_lib.ITER_REMOVE_OUTLIERS if remove_outliers else 0) | (_lib.ITER_PROFILE if profile else 0)
+    flags = (_lib.ITER_REMOVE_OUTLIERS if remove_outliers else 0) | (_lib.ITER_PROFILE if profile else 0) \
+        | (_lib.ITER_RADIX_ONLY if radix_only else 0)
     _lib.check(L.dcr_nuth_iteration(C.byref(a), flags, C.byref(res),
                                     C.c_void_p(ws.data_ptr()), ws.numel(), _stream_ptr(torch)))
     return res, grid, bufs
@@ -114,8 +115,10 @@ def front_only(ref, src, mask_source=None, remove_outliers=True, max_dz=100, slo
     return grid, bufs
 
 
-def select_quantiles(x, q_percent, mask=None, reject=0xFF, transform=0, center=0.0):
-    """Exact ``np.percentile`` (linear) of the unmasked elements of a device tensor -> (values f32, count)."""
+def select_quantiles(x, q_percent, mask=None, reject=0xFF, transform=0, center=0.0, radix_only=False):
+    """Exact ``np.percentile`` (linear) of the unmasked elements of a device tensor -> (values f32, count).
+
+    ``radix_only`` forces the 3-pass radix select (the fallback of the one-pass sample-bracket select)."""
     torch = _lib.require_cuda()
     L = _lib.lib()
     x = x.contiguous()
@@ -123,12 +126,13 @@ def select_quantiles(x, q_percent, mask=None, reject=0xFF, transform=0, center=0
     q = (C.c_double * nq)(*[float(v) for v in q_percent])
     out = (C.c_float * nq)()
     cnt = C.c_int64(0)
-    ws = workspace(L.dcr_select_workspace_bytes())
+    ws = workspace(L.dcr_select_workspace_bytes_n(x.numel()))
     mp = None
     if mask is not None:
         mask = mask.contiguous()
         mp = C.c_void_p(mask.data_ptr())
-    _lib.check(L.dcr_select_quantiles(C.c_void_p(x.data_ptr()), mp, int(reject), x.numel(), int(transform), float(center),
+    fn = L.dcr_select_quantiles_radix if radix_only else L.dcr_select_quantiles
+    _lib.check(fn(C.c_void_p(x.data_ptr()), mp, int(reject), x.numel(), int(transform), float(center),
                                       q, nq, out, C.byref(cnt), C.c_void_p(ws.data_ptr()), ws.numel(), _stream_ptr(torch)))
     return np.array(list(out), dtype=np.float32), int(cnt.value)
 

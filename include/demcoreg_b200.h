@@ -115,10 +115,17 @@ int dcr_warp_diff_horn(const dcr_front_args* args, void* stream);
  * transform 0: x ; 1: |x - center| evaluated in float32 (malib.mad).
  * Results (host): out[q] = interpolated value, count = number of participating elements.
  * Exact integer rank (float64 virtual index) + numpy's _lerp in float32.  */
-size_t dcr_select_workspace_bytes(void);
+size_t dcr_select_workspace_bytes(void);          /* enough for the radix variant and for n <= 393216 */
+size_t dcr_select_workspace_bytes_n(int64_t n);   /* dcr_select_quantiles on n elements */
 int dcr_select_quantiles(const float* x, const uint8_t* mask, uint32_t reject, int64_t n,
                          int transform, float center, const double* q_percent, int nq,
                          float* out, int64_t* count, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same result through the 3-pass radix select only (dcr_select_quantiles tries the one-pass
+ * sample-bracket select first and falls back to this when its on-device verification fails). */
+int dcr_select_quantiles_radix(const float* x, const uint8_t* mask, uint32_t reject, int64_t n,
+                               int transform, float center, const double* q_percent, int nq,
+                               float* out, int64_t* count, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K4: moments ------------------------------------------------------------------------
  * count / min / max / mean / std (float64 accumulation) <- malib.get_stats (dem_align.py:114, 384, 392),
@@ -186,9 +193,12 @@ typedef struct dcr_iter_result {
     float stage_ms[8];           /* DCR_ITER_PROFILE only: CUDA-event time of 0 front kernel, 1 median+MAD selects,
                                     2 mask update+scan+subsample, 3 med_dh/dz/med_slope selects, 4 y/bin prepare+moments,
                                     5 bin count+median passes, 6 device->host copy */
+    int32_t select_engine;       /* 1: one-pass sample-bracket selects verified ok; 0: 3-pass radix selects (fallback) */
+    int32_t _pad;
 } dcr_iter_result;
 #define DCR_ITER_REMOVE_OUTLIERS 1 /* flags of dcr_nuth_iteration: dem_align.py:91 remove_outliers */
 #define DCR_ITER_PROFILE 2         /* record per-stage CUDA events into stage_ms */
+#define DCR_ITER_RADIX_ONLY 4      /* skip the one-pass sample-bracket selects (tests / profiling) */
 size_t dcr_iteration_workspace_bytes(int64_t n);
 int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_iter_result* out /* host */,
                        void* workspace, size_t workspace_bytes, void* stream);

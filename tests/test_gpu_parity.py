@@ -274,3 +274,49 @@ def test_gpu_against_golden_vectors(cuda):
                                equal_nan=True)
     assert res.dz_med == g['dz_med']
     np.testing.assert_allclose([res.dx, res.dy, res.dz], g['shift'], rtol=0, atol=OFFTOL)
+
+
+@pytest.mark.parametrize("kind", ["normal", "ties", "constant", "two_values", "heavy_tail", "sorted"])
+@pytest.mark.parametrize("n", [8192, 8193, 70001, 2_000_003])
+def test_bracket_select_equals_radix_and_oracle(cuda, kind, n):
+    """One-pass sample-bracket select (with its verified fallback) == 3-pass radix select == oracle."""
+    from demcoreg_b200 import engine
+    from oracle import pygeotools_restated as pg
+    rng = np.random.default_rng(n + len(kind))
+    if kind == "normal":
+        x = rng.standard_normal(n)
+    elif kind == "ties":
+        x = np.round(rng.standard_normal(n) * 3)          # integer-valued: massive ties -> fallback path
+    elif kind == "constant":
+        x = np.full(n, 2.5)
+    elif kind == "two_values":
+        x = (rng.random(n) < 0.5).astype(np.float64) * 7 - 3
+    elif kind == "heavy_tail":
+        x = rng.standard_cauchy(n)
+    else:
+        x = np.linspace(-5, 5, n)
+    x = x.astype(np.float32)
+    m = (rng.random(n) < 0.25).astype(np.uint8) * 2
+    xt, mt = cuda.from_numpy(x).cuda(), cuda.from_numpy(m).cuda()
+    qs = [50.0, 25.0, 84.1, 0.5, 99.9]
+    a, ca = engine.select_quantiles(xt, qs, mt, 2)
+    b, cb = engine.select_quantiles(xt, qs, mt, 2, radix_only=True)
+    xv = x[m == 0]
+    assert ca == cb == xv.size
+    for q, ga, gb in zip(qs, a, b):
+        want = pg.exact_percentile(xv, q)
+        assert ga == want and gb == want, (kind, n, q, ga, gb, want)
+
+
+def test_iteration_uses_fast_selects_and_matches_radix(cuda):
+    from demcoreg_b200 import engine
+    p = _pair(n=1024, nodata_frac=0.01, static_mask_frac=0.3)
+    from demcoreg_b200.raster import MaskSource
+    ms = MaskSource(p['mask'], p['gt'])
+    gt_s = _shifted_gt(p['gt'], 3.4, -1.8)
+    r1, _, _ = engine.nuth_iteration(_gds(p, 'ref'), _gds(p, 'src', gt_s), ms)
+    r2, _, _ = engine.nuth_iteration(_gds(p, 'ref'), _gds(p, 'src', gt_s), ms, radix_only=True)
+    assert r1.select_engine == 1 and r2.select_engine == 0
+    for f in ("med1", "nmad1", "mad_lo", "mad_hi", "dz_med", "med_dh", "med_slope", "count_mad", "count_final", "dx", "dy", "dz"):
+        assert getattr(r1, f) == getattr(r2, f), f
+    assert list(r1.nuth.bin_count) == list(r2.nuth.bin_count)
