@@ -87,6 +87,12 @@ SYMBOLS = {
     "dcr_nuth_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "dcr_nuth_bin_stats": (C.c_int, [_P, _P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int64, C.c_int,
                                      C.POINTER(NuthStats), _P, C.c_size_t, _P]),
+    "dcr_ncc_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "dcr_ncc_corr": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P, C.POINTER(C.c_double),
+                               C.POINTER(C.c_double), _P, C.c_size_t, _P]),
+    "dcr_sad_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "dcr_sad_search": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_double), _P,
+                                 C.c_size_t, _P]),
     "dcr_fit_nuth": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]),
     "dcr_apply_z_shift": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_float, _P, _P]),
     "dcr_iteration_workspace_bytes": (C.c_size_t, [C.c_int64]),

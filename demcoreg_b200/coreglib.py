@@ -114,6 +114,60 @@ def compute_offset_nuth(dh, slope, aspect, min_count=100, remove_outliers=True, 
     return fit, fit_fig
 
 
+def compute_offset_sad(dem1, dem2, pad=(9, 9), plot=False):
+    """Sub-pixel offset by sum of absolute differences (reference ``coreglib.py:65-115``) -> ``(m, int_offset, sp_offset)``.
+
+    Every offset of the (2*pad+1)^2 window: ``diff = dem1 window - dem2[pad:-pad]``, trimmed to its inter-quartile
+    range, mean absolute value; all on the device (``dcr_sad_search``).  ``m`` is negated like the reference's.
+    """
+    if pad[0] != pad[1]:
+        raise ValueError("square search windows only (the reference's slicing mixes pad[0]/pad[1], coreglib.py:139)")
+    d1, m1 = _to_device_masked(dem1)
+    d2, m2 = _to_device_masked(dem2)
+    m = engine.sad_search(d1, m1, d2, m2, int(pad[0]))
+    m = -m
+    int_argmax = np.array(np.unravel_index(m.argmax(), m.shape))
+    int_offset = int_argmax - pad
+    sp_argmax = np.array(find_subpixel_peak_position(m, 'parabolic'))
+    sp_offset = sp_argmax - pad
+    return m, int_offset, sp_offset
+
+
+def compute_offset_ncc(dem1, dem2, pad=(9, 9), prefilter=False, plot=False, noise=None):
+    """Offset by normalized cross-correlation (reference ``coreglib.py:118-198``) -> ``(m, int_offset, sp_offset, fig)``.
+
+    ``noise`` (extension): ``(ref_noise, kernel_noise)`` standard-normal arrays for the masked pixels; ``None``
+    reproduces the reference, which draws them from the unseeded global ``np.random.randn`` (``coreglib.py:158-159``).
+    """
+    torch = _lib.require_cuda()
+    if prefilter:
+        raise NotImplementedError("prefilter=True (LoG edge filter via malib.nanfill) is outside the hot path; "
+                                  "dem_align always passes prefilter=False (dem_align.py:140)")
+    if pad[0] != pad[1]:
+        raise ValueError("square search windows only (the reference's slicing mixes pad[0]/pad[1], coreglib.py:139)")
+    p = int(pad[0])
+    d1, m1 = _to_device_masked(dem1)
+    d2, m2 = _to_device_masked(dem2)
+    print("Adding random noise to masked regions")
+    rn = kn = None
+    kshape = (d2.shape[0] - 2 * p, d2.shape[1] - 2 * p)
+    if noise is not None:
+        rn = torch.from_numpy(np.ascontiguousarray(noise[0], dtype=np.float32)).cuda()
+        kn = torch.from_numpy(np.ascontiguousarray(noise[1], dtype=np.float32)).cuda()
+    elif bool(m1.any()) or bool(m2[p:-p, p:-p].any()):
+        rn = torch.from_numpy(np.random.randn(*d1.shape).astype(np.float32)).cuda()
+        kn = torch.from_numpy(np.random.randn(*kshape).astype(np.float32)).cuda()
+    print("Running 2D correlation with search window (x,y): %i, %i" % (pad[1], pad[0]))
+    m, _ = engine.ncc_corr(d1, m1, d2, m2, p, rn, kn)
+    print("Computing sub-pixel peak")
+    int_argmax = np.array(np.unravel_index(m.argmax(), m.shape))
+    int_offset = int_argmax - pad
+    sp_argmax = np.array(find_subpixel_peak_position(m, 'parabolic'))
+    sp_offset = sp_argmax - pad
+    fig = None
+    return m, int_offset, sp_offset, fig
+
+
 def find_first_peak(corr):
     """Reference ``coreglib.py:387-416``."""
     ind = corr.argmax()

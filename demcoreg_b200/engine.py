@@ -242,3 +242,44 @@ def apply_z_shift_inplace(ds, dz):
     _lib.check(L.dcr_apply_z_shift(C.c_void_p(ds.data.data_ptr()), h, w, ds.data.stride(0),
                                    ds.ndv if ds.ndv is not None else 0.0, dzs, grid_ptr, _stream_ptr(torch)))
     return ds
+
+
+def ncc_corr(ref, ref_mask, src, src_mask, pad, ref_noise=None, kernel_noise=None):
+    """``dcr_ncc_corr``: z-scored 'valid' cross-correlation map (float64, (2p+1)^2) of two device rasters."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    h, w = int(ref.shape[0]), int(ref.shape[1])
+    ref, src = ref.contiguous(), src.contiguous()
+    J = 2 * pad + 1
+    m = (C.c_double * (J * J))()
+    stats = (C.c_double * 4)()
+    ws = workspace(L.dcr_ncc_workspace_bytes(h, w, pad))
+
+    def ptr(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+    rm = ref_mask.to(torch.uint8).contiguous() if ref_mask is not None else None
+    sm = src_mask.to(torch.uint8).contiguous() if src_mask is not None else None
+    rn = ref_noise.to(torch.float32).contiguous() if ref_noise is not None else None
+    kn = kernel_noise.to(torch.float32).contiguous() if kernel_noise is not None else None
+    _lib.check(L.dcr_ncc_corr(ptr(ref), ptr(rm), ptr(src), ptr(sm), h, w, w, int(pad), ptr(rn), ptr(kn), m, stats,
+                              C.c_void_p(ws.data_ptr()), ws.numel(), _stream_ptr(torch)))
+    return np.array(m[:], dtype=np.float64).reshape(J, J), tuple(stats[:])
+
+
+def sad_search(ref, ref_mask, src, src_mask, pad):
+    """``dcr_sad_search``: IQR-trimmed mean absolute difference for every offset (float64, (2p+1)^2)."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    h, w = int(ref.shape[0]), int(ref.shape[1])
+    ref, src = ref.contiguous(), src.contiguous()
+    J = 2 * pad + 1
+    m = (C.c_double * (J * J))()
+    ws = workspace(L.dcr_sad_workspace_bytes(h, w, pad))
+    rm = ref_mask.to(torch.uint8).contiguous() if ref_mask is not None else None
+    sm = src_mask.to(torch.uint8).contiguous() if src_mask is not None else None
+
+    def ptr(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+    _lib.check(L.dcr_sad_search(ptr(ref), ptr(rm), ptr(src), ptr(sm), h, w, w, int(pad), m,
+                                C.c_void_p(ws.data_ptr()), ws.numel(), _stream_ptr(torch)))
+    return np.array(m[:], dtype=np.float64).reshape(J, J)

@@ -157,6 +157,25 @@ int dcr_nuth_bin_stats(const float* dh, const float* slope, const float* aspect,
                        int remove_outliers, dcr_nuth_stats* out /* host */,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- K7a: NCC offset search -------------------------------------------------------------------
+ * coreglib.compute_offset_ncc <- coreglib.py:118-198: z-score ref and kernel = src[p:-p, p:-p] over their
+ * valid pixels (float64 mean/std), masked pixels <- noise (device arrays of the ref / kernel shapes, or NULL
+ * for zeros; the reference draws unseeded np.random.randn), m = correlate2d(ref, kernel, 'valid').
+ * ref/src: h x w float32 with the same element stride; masks uint8 (1 = masked) or NULL.
+ * m_out (host): (2p+1) x (2p+1) float64, row-major.  stats_out (host): ref mean, std, kernel mean, std. */
+size_t dcr_ncc_workspace_bytes(int h, int w, int pad);
+int dcr_ncc_corr(const float* ref, const uint8_t* ref_mask, const float* src, const uint8_t* src_mask, int h, int w,
+                 int64_t stride, int pad, const float* ref_noise, const float* kernel_noise, double* m_out,
+                 double stats_out[4], void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K7b: SAD offset search -------------------------------------------------------------------
+ * coreglib.compute_offset_sad <- coreglib.py:65-115: for every offset, diff = ref window - kernel (float32),
+ * trim outside its [P25, P75] (exact percentiles, malib.calcperc), m = sum|diff| / count.
+ * m_out (host): (2p+1)^2 float64 of the mean absolute difference (the caller negates it, coreglib.py:100). */
+size_t dcr_sad_workspace_bytes(int h, int w, int pad);
+int dcr_sad_search(const float* ref, const uint8_t* ref_mask, const float* src, const uint8_t* src_mask, int h, int w,
+                   int64_t stride, int pad, double* m_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- fit (host) -----------------------------------------------------------------------------
  * scipy.optimize.curve_fit(nuth_func, bin_centers, bin_med, x0) <- coreglib.py:305 with
  * nuth_func(x,a,b,c) = a*cos(deg2rad(b-x)) + c (coreglib.py:58-63).  The model is linear in

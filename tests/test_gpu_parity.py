@@ -320,3 +320,91 @@ def test_iteration_uses_fast_selects_and_matches_radix(cuda):
     for f in ("med1", "nmad1", "mad_lo", "mad_hi", "dz_med", "med_dh", "med_slope", "count_mad", "count_final", "dx", "dy", "dz"):
         assert getattr(r1, f) == getattr(r2, f), f
     assert list(r1.nuth.bin_count) == list(r2.nuth.bin_count)
+
+
+def _ncc_pair(n=320, p=6, masked=False, seed=5):
+    pr = _pair(n=n, noise=0.05, outlier_frac=0.0, shift=(0.0, 0.0, 0.0), seed=20260030 + seed)
+    ref = pr['ref']
+    # src = ref shifted by a non-integer amount: roll + blend -> sub-pixel peak
+    a = np.roll(ref, (2, -3), axis=(0, 1)).astype(np.float64)
+    b = np.roll(ref, (3, -3), axis=(0, 1)).astype(np.float64)
+    src = (0.65 * a + 0.35 * b).astype(np.float32)
+    m1 = np.zeros(ref.shape, dtype=bool)
+    m2 = np.zeros(ref.shape, dtype=bool)
+    if masked:
+        rng = np.random.default_rng(seed)
+        m1[rng.integers(0, n, 40), rng.integers(0, n, 40)] = True
+        m2[40:60, 100:130] = True
+    return np.ma.array(ref, mask=m1), np.ma.array(src, mask=m2)
+
+
+@pytest.mark.parametrize("masked", [False, True])
+@pytest.mark.parametrize("p", [4, 9, 16])
+def test_ncc_matches_oracle(cuda, masked, p):
+    """compute_offset_ncc vs the oracle (scipy.signal.correlate2d in float64), shared noise arrays."""
+    from demcoreg_b200 import coreglib
+    from oracle import coreglib as ocl
+    ref, src = _ncc_pair(n=200 + 8 * p, p=p, masked=masked)
+    rng = np.random.default_rng(9)
+    noise = (rng.standard_normal(ref.shape), rng.standard_normal((ref.shape[0] - 2 * p, ref.shape[1] - 2 * p)))
+    m, io, so, fig = coreglib.compute_offset_ncc(ref, src, pad=(p, p), noise=noise)
+    mo, ioo, soo, _ = ocl.compute_offset_ncc(ref, src, pad=(p, p), noise=noise)
+    assert m.shape == mo.shape == (2 * p + 1, 2 * p + 1) and fig is None
+    np.testing.assert_allclose(m, mo, rtol=0, atol=2e-6 * np.abs(mo).max())
+    assert tuple(io) == tuple(ioo)
+    np.testing.assert_allclose(so, soo, atol=1e-4)
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_sad_matches_oracle(cuda, masked):
+    from demcoreg_b200 import coreglib
+    from oracle import coreglib as ocl
+    p = 3
+    ref, src = _ncc_pair(n=160, p=p, masked=masked)
+    m, io, so = coreglib.compute_offset_sad(ref, src, pad=(p, p))
+    mo, ioo, soo = ocl.compute_offset_sad(ref, src, pad=(p, p))
+    np.testing.assert_allclose(m, mo, rtol=2e-6)
+    assert tuple(io) == tuple(ioo)
+    np.testing.assert_allclose(so, soo, atol=1e-4)
+
+
+@pytest.mark.parametrize("mode", ["ncc", "sad"])
+def test_dem_align_corr_modes(cuda, mode):
+    """dem_align.compute_offset(mode='ncc'|'sad') vs the oracle's (noise injected for NCC)."""
+    from demcoreg_b200 import dem_align, corr
+    from oracle import dem_align as oda
+    n, res = 192, 30.0
+    p = _pair(n=n, res=res, shift=(33.0, -21.0, 0.5), noise=0.05)
+    max_offset = 60.0 if mode == 'ncc' else 45.0   # pad = int(max_offset/res + 1)
+    pad = int(max_offset / res + 1)
+    rng = np.random.default_rng(1)
+    noise = (rng.standard_normal((n, n)), rng.standard_normal((n - 2 * pad, n - 2 * pad)))
+    det = {}
+    gdx, gdy, gdz, gmask, _ = corr.compute_offset_corr(_gds(p, 'ref'), _gds(p, 'src'), mode, True, max_offset, 100, (0.1, 40),
+                                                       None, False, ncc_noise=noise, _details=det)
+    odx, ody, odz, omask, _ = oda.compute_offset(_ods(p, 'ref'), _ods(p, 'src'), mode=mode, max_offset=max_offset,
+                                                 ncc_noise=noise)
+    assert np.array_equal(gmask, omask)
+    assert abs(gdx - odx) < OFFTOL and abs(gdy - ody) < OFFTOL and abs(gdz - odz) < OFFTOL, (gdx, odx, gdy, ody)
+
+
+def test_robust_stats_and_stats_dict(cuda):
+    """robust_stats.py outputs and malib.get_stats_dict(full=True) vs the oracle."""
+    from demcoreg_b200 import robust_stats as grs
+    from oracle import robust_stats as ors, pygeotools_restated as pg
+    rng = np.random.default_rng(11)
+    a = (rng.standard_normal((700, 900)) * 0.8 + 0.1).astype(np.float32)
+    a = np.round(a * 512) / 512   # quantised like real dz rasters -> meaningful mode
+    mask = rng.random(a.shape) < 0.2
+    ma = np.ma.array(a, mask=mask)
+    g = grs.robust_stats(ma)
+    o = ors.robust_stats(ma.compressed())
+    assert g['count'] == o['count']
+    for k in ('rmse', 'mean', 'std', 'med', 'p16', 'p84', 'spread', 'absmed', 'nmad', 'p68', 'p95'):
+        assert abs(g[k] - float(o[k])) <= 1e-5 * max(1.0, abs(float(o[k]))), k
+    gd = grs.get_stats_dict(ma)
+    od = pg.get_stats_dict(ma, full=True)
+    assert set(gd) == set(od)
+    assert gd['count'] == od['count'] and gd['min'] == od['min'] and gd['max'] == od['max'] and gd['mode'] == od['mode']
+    for k in ('ptp', 'mean', 'std', 'nmad', 'med', 'median', 'p16', 'p84', 'spread'):
+        assert abs(gd[k] - od[k]) <= 1e-6 * max(1.0, abs(od[k])), k
