@@ -41,6 +41,9 @@ class FrontArgs(C.Structure):
         ("max_dz", C.c_float), ("use_max_dz", C.c_int32), ("slope_lo", C.c_float), ("slope_hi", C.c_float),
         ("dh", C.c_void_p), ("slope", C.c_void_p), ("aspect", C.c_void_p), ("maskbits", C.c_void_p),
         ("ref_w", C.c_void_p), ("src_w", C.c_void_p),
+        ("row_begin", C.c_int32), ("row_end", C.c_int32),
+        ("ref_row0", C.c_int32), ("ref_nrows", C.c_int32), ("src_row0", C.c_int32), ("src_nrows", C.c_int32),
+        ("smask_row0", C.c_int32), ("smask_nrows", C.c_int32),
     ]
 
 
@@ -96,6 +99,10 @@ SYMBOLS = {
     "dcr_fit_nuth": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]),
     "dcr_apply_z_shift": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_float, _P, _P]),
     "dcr_iteration_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "dcr_band_nphases": (C.c_int, []),
+    "dcr_band_phase": (C.c_int, [C.POINTER(FrontArgs), C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_size_t,
+                                 C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
+    "dcr_band_result": (C.c_int, [C.POINTER(FrontArgs), _P, C.c_size_t, C.POINTER(IterResult), _P]),
     "dcr_nuth_iteration": (C.c_int, [C.POINTER(FrontArgs), C.c_int, C.POINTER(IterResult), _P, C.c_size_t, _P]),
 }
 

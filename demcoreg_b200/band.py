@@ -1,0 +1,294 @@
+"""Row-band mode: one very large DEM pair split into bands of rows, one band per GPU (BASELINE.json configs[4]).
+
+The reference never tiles -- it loads whole arrays into RAM (reference ``dem_align.py:79-80``; memory note
+``dem_align_parallel.pbs:3,121``).  Here every rank keeps rows ``[r0, r1)`` of both rasters (and of the
+stable-surface mask) plus ``halo`` rows on each side, obtained from its neighbours with NCCL send/recv over
+NVLink (``exchange_halos``).  An iteration runs the phases of ``dcr_band_phase``; between phases the integer
+histograms / counters (and three FP64 sums) are all-reduced, so every rank ends up with the same
+``dcr_iter_result`` -- bit-identical in its integer parts to the single-GPU path.
+
+The same code runs G "virtual ranks" on one device (``VirtualGroup``) with an in-process sum standing in for
+the collective; that is how the band logic is tested without a multi-GPU box.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .raster import Raster
+
+
+def band_rows(height, rank, world):
+    """Owned rows ``[r0, r1)`` of rank ``rank``: contiguous, near-equal bands."""
+    r0 = (height * rank) // world
+    r1 = (height * (rank + 1)) // world
+    return r0, r1
+
+
+class BandRaster(object):
+    """Rows ``[row0, row0 + data.shape[0])`` of a raster of ``height`` rows (band + halos), in device memory."""
+
+    def __init__(self, data, row0, height, gt, ndv):
+        self.data = data.contiguous()
+        self.row0 = int(row0)
+        self.height = int(height)
+        self.gt = tuple(float(g) for g in gt)
+        self.ndv = None if ndv is None else float(ndv)
+
+    @property
+    def width(self):
+        return int(self.data.shape[1])
+
+    def desc(self):
+        d = _lib.RasterDesc()
+        for k in range(6):
+            d.gt[k] = self.gt[k]
+        d.width = self.width
+        d.height = self.height
+        d.ndv = self.ndv if self.ndv is not None else 0.0
+        d.has_ndv = 0 if self.ndv is None else 1
+        return d
+
+
+def make_band(array_rows, r0, r1, height, halo, gt, ndv, torch, fill=None, device="cuda"):
+    """Allocate band + halo storage and place the OWNED rows; halo rows are filled by ``exchange_halos``."""
+    lo = max(0, r0 - halo)
+    hi = min(height, r1 + halo)
+    t = torch.empty((hi - lo, array_rows.shape[1]), dtype=array_rows.dtype, device=device)
+    if fill is not None:
+        t.fill_(fill)
+    t[r0 - lo:r1 - lo] = array_rows
+    b = BandRaster(t, lo, height, gt, ndv)
+    b.halo = halo
+    return b, (r0 - lo, r1 - lo)
+
+
+def exchange_halos(band, owned, rank, world, group=None):
+    """Fill the halo rows of ``band`` from the neighbouring ranks (NCCL send/recv, one batch per call).
+
+    ``owned`` = (first, last) stored-row indices of the rows this rank owns.  Rank r sends its top owned rows to
+    r-1 and its bottom owned rows to r+1 and receives its halos from them."""
+    import torch.distributed as dist
+    a, b = owned
+    nrows = band.data.shape[0]
+    top_halo, bot_halo = a, nrows - b
+    ops = []
+    keep = []
+    if rank > 0 and top_halo > 0:
+        ops.append(dist.P2POp(dist.irecv, band.data[0:a], rank - 1, group))
+    if rank < world - 1 and bot_halo > 0:
+        ops.append(dist.P2POp(dist.irecv, band.data[b:nrows], rank + 1, group))
+    # what the neighbours need: the same halo depth (bands are symmetric), clipped by their raster edge
+    if rank > 0:
+        up = band.data[a:a + _halo_of_neighbour(band, rank - 1, world, below=True)].contiguous()
+        keep.append(up)
+        ops.append(dist.P2POp(dist.isend, up, rank - 1, group))
+    if rank < world - 1:
+        k = _halo_of_neighbour(band, rank + 1, world, below=False)
+        dn = band.data[b - k:b].contiguous()
+        keep.append(dn)
+        ops.append(dist.P2POp(dist.isend, dn, rank + 1, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return band
+
+
+def _halo_of_neighbour(band, nrank, world, below):
+    """Rows the neighbour ``nrank`` stores beyond its owned band on the side facing us."""
+    halo = band.halo
+    r0, r1 = band_rows(band.height, nrank, world)
+    if below:   # neighbour is above us; its bottom halo
+        return min(band.height, r1 + halo) - r1
+    return r0 - max(0, r0 - halo)
+
+
+class BandAligner(object):
+    """One rank's state of the row-band iteration."""
+
+    def __init__(self, ref_rows, src_rows, mask_rows, height, gt, ndv, rank, world, halo=16):
+        torch = _lib.require_cuda()
+        self.torch = torch
+        self.rank, self.world, self.halo = rank, world, halo
+        self.height = height
+        self.r0, self.r1 = band_rows(height, rank, world)
+        self.ref, self.owned = make_band(ref_rows, self.r0, self.r1, height, halo, gt, ndv, torch)
+        self.src, _ = make_band(src_rows, self.r0, self.r1, height, halo, gt, ndv, torch)
+        self.mask = None
+        if mask_rows is not None:
+            self.mask, _ = make_band(mask_rows, self.r0, self.r1, height, halo, gt, None, torch)
+        for b in (self.ref, self.src, self.mask):
+            if b is not None:
+                b.halo = halo
+        self.ws = None
+        self.bufs = None
+
+    def bands(self):
+        return [b for b in (self.ref, self.src, self.mask) if b is not None]
+
+    def exchange_halos(self, group=None):
+        """NCCL halo exchange of all three rasters with the neighbouring ranks."""
+        for b in self.bands():
+            exchange_halos(b, self.owned, self.rank, self.world, group)
+
+    # ---- one iteration, phase by phase -------------------------------------------------------
+    def begin_iteration(self, remove_outliers=True, max_dz=100, slope_lim=(0.1, 40)):
+        torch = self.torch
+        L = _lib.lib()
+        grid, gr, gs = _lib.Grid(), _lib.WarpGeom(), _lib.WarpGeom()
+        dr, dsrc = self.ref.desc(), self.src.desc()
+        _lib.check(L.dcr_plan_intersection(C.byref(dr), C.byref(dsrc), 0.0, C.byref(grid), C.byref(gr), C.byref(gs)))
+        H, W = grid.height, grid.width
+        rb = min(max(self.r0 - gr.iy0, 0), H)
+        re = min(max(self.r1 - gr.iy0, 0), H)
+        if self.rank == self.world - 1:
+            re = H
+        if self.rank == 0:
+            rb = 0
+        if re <= rb:
+            raise _lib.DcrError("empty band on rank %d: use fewer ranks for this raster" % self.rank)
+        nrows = re - rb
+        if self.bufs is None or self.bufs[0].shape != (nrows, W):
+            self.bufs = (torch.empty((nrows, W), dtype=torch.float32, device="cuda"),
+                         torch.empty((nrows, W), dtype=torch.float32, device="cuda"),
+                         torch.empty((nrows, W), dtype=torch.float32, device="cuda"),
+                         torch.empty((nrows, W), dtype=torch.uint8, device="cuda"))
+        a = _lib.FrontArgs()
+        a.ref = self.ref.data.data_ptr()
+        a.ref_stride = self.ref.data.stride(0)
+        a.ref_desc = dr
+        a.ref_geom = gr
+        a.src = self.src.data.data_ptr()
+        a.src_stride = self.src.data.stride(0)
+        a.src_desc = dsrc
+        a.src_geom = gs
+        a.ref_row0, a.ref_nrows = self.ref.row0, int(self.ref.data.shape[0])
+        a.src_row0, a.src_nrows = self.src.row0, int(self.src.data.shape[0])
+        if self.mask is not None:
+            gm = _lib.WarpGeom()
+            md = self.mask.desc()
+            _lib.check(L.dcr_plan_onto_grid(C.byref(md), C.byref(grid), C.byref(gm)))
+            a.smask = self.mask.data.data_ptr()
+            a.smask_stride = self.mask.data.stride(0)
+            a.smask_h, a.smask_w = md.height, md.width
+            a.smask_nx0, a.smask_ny0 = gm.nx0, gm.ny0
+            a.smask_row0, a.smask_nrows = self.mask.row0, int(self.mask.data.shape[0])
+        a.h, a.w = H, W
+        a.row_begin, a.row_end = rb, re
+        a.ewres, a.nsres = grid.gt[1], grid.gt[5]
+        a.dst_ndv = 0.0
+        a.max_dz = float(max_dz)
+        a.use_max_dz = 1 if remove_outliers else 0
+        a.slope_lo, a.slope_hi = float(slope_lim[0]), float(slope_lim[1])
+        a.dh, a.slope, a.aspect, a.maskbits = (t.data_ptr() for t in self.bufs)
+        self.args = a
+        self.grid = grid
+        self.flags = _lib.ITER_REMOVE_OUTLIERS if remove_outliers else 0
+        nbytes = L.dcr_iteration_workspace_bytes(nrows * W)
+        if self.ws is None or self.ws.numel() < nbytes:
+            self.ws = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda")
+        return L.dcr_band_nphases()
+
+    def run_phase(self, phase):
+        """Run one phase; returns the tensors (views into the workspace) that must be sum-all-reduced."""
+        torch = self.torch
+        L = _lib.lib()
+        ptrs = (C.c_void_p * 2)()
+        counts = (C.c_int64 * 2)()
+        kinds = (C.c_int * 2)()
+        nred = C.c_int(0)
+        _lib.check(L.dcr_band_phase(C.byref(self.args), self.flags, self.rank, self.world, phase,
+                                    C.c_void_p(self.ws.data_ptr()), self.ws.numel(), ptrs, counts, kinds, C.byref(nred),
+                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        out = []
+        dt = {0: (torch.int32, 4), 1: (torch.int64, 8), 2: (torch.float64, 8)}
+        for k in range(nred.value):
+            dtype, sz = dt[kinds[k]]
+            off = ptrs[k] - self.ws.data_ptr()
+            out.append(self.ws[off:off + counts[k] * sz].view(dtype))
+        return out
+
+    def result(self):
+        torch = self.torch
+        L = _lib.lib()
+        res = _lib.IterResult()
+        _lib.check(L.dcr_band_result(C.byref(self.args), C.c_void_p(self.ws.data_ptr()), self.ws.numel(), C.byref(res),
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return res
+
+    def apply_shift(self, dx, dy, dz):
+        """``apply_xy_shift`` + ``apply_z_shift`` on this rank's band (halo rows included: they stay consistent)."""
+        L = _lib.lib()
+        torch = self.torch
+        g = list(self.src.gt)
+        g[0] += dx
+        g[3] += dy
+        self.src.gt = tuple(g)
+        b = self.src
+        _lib.check(L.dcr_apply_z_shift(C.c_void_p(b.data.data_ptr()), int(b.data.shape[0]), b.width, b.data.stride(0),
+                                       b.ndv if b.ndv is not None else 0.0, float(np.float32(dz)), None,
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+
+def iteration_distributed(al, group=None, **kw):
+    """One row-band iteration under ``torch.distributed`` (NCCL): phases + all-reduces.  Returns IterResult."""
+    import torch.distributed as dist
+    nph = al.begin_iteration(**kw)
+    for ph in range(nph):
+        for t in al.run_phase(ph):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return al.result()
+
+
+class VirtualGroup(object):
+    """G virtual ranks on ONE device: the same phases, with an in-process sum instead of the collective."""
+
+    def __init__(self, ref, src, mask, gt, ndv, world, halo=16):
+        torch = _lib.require_cuda()
+        H = ref.shape[0]
+        self.world = world
+        self.ranks = []
+        for r in range(world):
+            r0, r1 = band_rows(H, r, world)
+            self.ranks.append(BandAligner(torch.from_numpy(np.ascontiguousarray(ref[r0:r1])).cuda(),
+                                          torch.from_numpy(np.ascontiguousarray(src[r0:r1])).cuda(),
+                                          torch.from_numpy(np.ascontiguousarray(mask[r0:r1])).cuda() if mask is not None else None,
+                                          H, gt, ndv, r, world, halo))
+        self.exchange_halos()
+
+    def exchange_halos(self):
+        """In-process stand-in for the NCCL halo exchange: copy the neighbours' owned rows into the halos."""
+        for r, al in enumerate(self.ranks):
+            for name in ("ref", "src", "mask"):
+                b = getattr(al, name)
+                if b is None:
+                    continue
+                a, e = al.owned
+                nrows = b.data.shape[0]
+                if r > 0 and a > 0:
+                    nb = getattr(self.ranks[r - 1], name)
+                    na, ne = self.ranks[r - 1].owned
+                    b.data[0:a] = nb.data[ne - a:ne]
+                if r < self.world - 1 and nrows > e:
+                    nb = getattr(self.ranks[r + 1], name)
+                    na, ne = self.ranks[r + 1].owned
+                    b.data[e:nrows] = nb.data[na:na + (nrows - e)]
+
+    def iteration(self, **kw):
+        nph = 0
+        for al in self.ranks:
+            nph = al.begin_iteration(**kw)
+        for ph in range(nph):
+            outs = [al.run_phase(ph) for al in self.ranks]
+            for k in range(len(outs[0])):
+                tot = outs[0][k].clone()
+                for o in outs[1:]:
+                    tot += o[k]
+                for o in outs:
+                    o[k].copy_(tot)
+        res = [al.result() for al in self.ranks]
+        return res
+
+    def apply_shift(self, dx, dy, dz):
+        for al in self.ranks:
+            al.apply_shift(dx, dy, dz)

@@ -169,6 +169,8 @@ struct DevGeom {
     long long stride;
     float ndv;
     int has_ndv;
+    int row0;  // global index of the first row held in memory (row-band mode; 0 = whole raster)
+    int row1;  // one past the last row held in memory
 };
 
 static DevGeom make_devgeom(const dcr_warp_geom& g, int hs, int ws, long long stride, double ndv, int has_ndv) {
@@ -177,13 +179,15 @@ static DevGeom make_devgeom(const dcr_warp_geom& g, int hs, int ws, long long st
     d.fx = g.fx; d.fy = g.fy;
     for (int k = 0; k < 4; ++k) { d.wx[k] = g.wx[k]; d.wy[k] = g.wy[k]; }
     d.hs = hs; d.ws = ws; d.stride = stride; d.ndv = (float)ndv; d.has_ndv = has_ndv;
+    d.row0 = 0;
+    d.row1 = hs;
     return d;
 }
 
 // source pixel -> value, NaN when out of bounds / nodata / NaN
 __device__ __forceinline__ float load_px(const float* __restrict__ p, const DevGeom& g, int r, int c) {
-    if (r < 0 || c < 0 || r >= g.hs || c >= g.ws) return __int_as_float(0x7fc00000);
-    float v = __ldg(p + (long long)r * g.stride + c);
+    if (r < g.row0 || c < 0 || r >= g.row1 || c >= g.ws) return __int_as_float(0x7fc00000);
+    float v = __ldg(p + (long long)(r - g.row0) * g.stride + c);
     if (g.has_ndv && v == g.ndv) return __int_as_float(0x7fc00000);
     return v;
 }
@@ -394,6 +398,8 @@ struct FrontParams {
     long long smask_stride;
     int smask_h, smask_w, smask_nx0, smask_ny0;
     int h, w;
+    int row_begin, row_end;  // output rows computed by this launch (row-band mode; whole grid otherwise)
+    int smask_row0;
     double ewres, nsres;
     float inv8ew, inv8ns;
     double ref_gm_ndv, ref_gm_tol, src_gm_ndv, src_gm_tol;  // ds_getma masked_values(|x-ndv| <= tol)
@@ -436,7 +442,7 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
     float* s_sw = s_ref + F_REF_R * F_REF_C;              // F_SW_R x F_SW_C : warped src (NaN = nodata)
     __shared__ unsigned long long s_cnt[3];
 
-    const int tj0 = blockIdx.x * F_TW, ti0 = blockIdx.y * F_TH;
+    const int tj0 = blockIdx.x * F_TW, ti0 = p.row_begin + blockIdx.y * F_TH;
     const int tid = threadIdx.x;
     if (tid < 3) s_cnt[tid] = 0ull;
 
@@ -452,8 +458,8 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int rr = r + 8 * u, gr = r_base + rr;
-                    const bool rok = rr < F_SRC_R && gr >= 0 && gr < p.sg.hs;
-                    const float* rowp = p.src + (long long)gr * p.sg.stride;
+                    const bool rok = rr < F_SRC_R && gr >= p.sg.row0 && gr < p.sg.row1;
+                    const float* rowp = p.src + (long long)(gr - p.sg.row0) * p.sg.stride;
 #pragma unroll
                     for (int q = 0; q < 5; ++q) {
                         const int cc = q * 32 + lane, gc = c_base + cc;
@@ -481,8 +487,8 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int rr = r + 8 * u, gr = r_base + rr;
-                    const bool rok = rr < F_REF_R && gr >= 0 && gr < p.rg.hs;
-                    const float* rowp = p.ref + (long long)gr * p.rg.stride;
+                    const bool rok = rr < F_REF_R && gr >= p.rg.row0 && gr < p.rg.row1;
+                    const float* rowp = p.ref + (long long)(gr - p.rg.row0) * p.rg.stride;
 #pragma unroll
                     for (int q = 0; q < 5; ++q) {
                         const int cc = q * 32 + lane, gc = c_base + cc;
@@ -572,8 +578,9 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
                 if (isnan(ro)) rv = bilinear_fallback(t[0], t[1], t[F_REF_C + 1], t[F_REF_C], nearest, p.rg.fx, p.rg.fy);
                 else rv = isnan(nearest) ? nearest : (float)ro;
             }
-            const bool inside = (i < p.h) && (j < p.w);
-            if (!inside) sv = __int_as_float(0x7fc00000);
+            const bool inside = (i < p.row_end) && (j < p.w);
+            // rows past this launch's band still feed the 3x3 stencil of its last row (row-band mode)
+            if (!((i < p.h) && (j < p.w))) sv = __int_as_float(0x7fc00000);
             s_sw[(r + 1) * F_SW_C + (c + 1)] = sv;
             // ds_getma masks: |x - ndv| <= tol in double (numpy masked_values)
             const bool sm = isnan(sv) || fabs((double)sv - p.src_gm_ndv) <= p.src_gm_tol;
@@ -582,7 +589,7 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
             if (base_ok && p.smask) {
                 const int mi = i + p.smask_ny0, mj = j + p.smask_nx0;
                 if (mi < 0 || mj < 0 || mi >= p.smask_h || mj >= p.smask_w) base_ok = false;
-                else if (__ldg(p.smask + (long long)mi * p.smask_stride + mj)) base_ok = false;
+                else if (__ldg(p.smask + (long long)(mi - p.smask_row0) * p.smask_stride + mj)) base_ok = false;
             }
             const float dh = base_ok ? (sv - rv) : 0.0f;
             if (base_ok) {
@@ -592,7 +599,7 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
                 else ++n_maxdz;
             }
             if (inside) {
-                const long long o = (long long)i * p.w + j;
+                const long long o = (long long)(i - p.row_begin) * p.w + j;
                 p.dh[o] = dh;
                 if (p.ref_w) p.ref_w[o] = isnan(rv) ? p.ref_fill : rv;
                 if (p.src_w) p.src_w[o] = isnan(sv) ? p.src_fill : sv;
@@ -614,7 +621,7 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
             const int i = ti0 + r;
             q = s_sw + (r + 2) * F_SW_C + c;
             w6 = q[0]; w7 = q[1]; w8 = q[2];
-            if (i < p.h && j < p.w) {
+            if (i < p.row_end && j < p.w) {
                 float sl = DCR_GDALDEM_NDV, as = DCR_GDALDEM_NDV;
                 unsigned bits = DCR_M_SLOPE | DCR_M_ASPECT;
                 if (i > 0 && j > 0 && i < p.h - 1 && j < p.w - 1) {
@@ -631,7 +638,7 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
                 }
                 if (!(valid_bits & (1u << rr))) bits |= DCR_M_BASE;
                 else if (maxdz_bits & (1u << rr)) bits |= DCR_M_MAXDZ;
-                const long long o = (long long)i * p.w + j;
+                const long long o = (long long)(i - p.row_begin) * p.w + j;
                 p.slope[o] = sl;
                 p.aspect[o] = as;
                 p.maskbits[o] = (unsigned char)bits;
@@ -695,13 +702,53 @@ int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cuda
     p.ref_w = a->ref_w;
     p.src_w = a->src_w;
     p.counters = counters;
+    // row-band mode: this launch computes output rows [row_begin, row_end) only, from rasters of which only
+    // the rows [row0, row0 + nrows) are in memory (the band plus its halo); outputs are band-local.
+    p.row_begin = 0;
+    p.row_end = a->h;
+    if (a->row_end > 0) {
+        DCR_ARG(a->row_begin >= 0 && a->row_end <= a->h && a->row_begin < a->row_end, "bad row band");
+        p.row_begin = a->row_begin;
+        p.row_end = a->row_end;
+    }
+    if (a->ref_nrows > 0) { p.rg.row0 = a->ref_row0; p.rg.row1 = a->ref_row0 + a->ref_nrows; }
+    if (a->src_nrows > 0) { p.sg.row0 = a->src_row0; p.sg.row1 = a->src_row0 + a->src_nrows; }
+    DCR_ARG(p.rg.row0 >= 0 && p.rg.row1 <= p.rg.hs && p.sg.row0 >= 0 && p.sg.row1 <= p.sg.hs, "stored rows outside the raster");
+    p.smask_row0 = a->smask_nrows > 0 ? a->smask_row0 : 0;
+    {
+        // every source row the launch touches must be in memory: 4 taps (+1 row each side for the Horn halo)
+        const int lo = p.row_begin - 1, hi = p.row_end + 1;  // warped-src rows needed (clipped below)
+        struct { const DevGeom* g; int nrows; const char* name; int extra; } chk[2] = {
+            {&p.rg, a->ref_nrows, "ref", 0}, {&p.sg, a->src_nrows, "src", 1}};
+        for (int k = 0; k < 2; ++k) {
+            if (chk[k].nrows <= 0) continue;
+            int first = (chk[k].extra ? lo : p.row_begin) + chk[k].g->iy0 - 1;
+            int last = (chk[k].extra ? hi : p.row_end) + chk[k].g->iy0 + 2;  // exclusive
+            if (first < 0) first = 0;
+            if (last > chk[k].g->hs) last = chk[k].g->hs;
+            if (first < chk[k].g->row0 || last > chk[k].g->row0 + chk[k].nrows) {
+                dcr_set_error("row band of %s too small: rows [%d, %d) needed, [%d, %d) in memory -- re-exchange halos",
+                              chk[k].name, first, last, chk[k].g->row0, chk[k].g->row0 + chk[k].nrows);
+                return -5;
+            }
+        }
+        if (a->smask && a->smask_nrows > 0) {
+            int first = p.row_begin + a->smask_ny0, last = p.row_end + a->smask_ny0;
+            if (first < 0) first = 0;
+            if (last > a->smask_h) last = a->smask_h;
+            if (first < p.smask_row0 || last > p.smask_row0 + a->smask_nrows) {
+                dcr_set_error("row band of the static mask too small");
+                return -5;
+            }
+        }
+    }
     const size_t smem = (size_t)(F_SRC_R * F_SRC_C + F_REF_R * F_REF_C + F_SW_R * F_SW_C) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         DCR_CUDA_OK(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    dim3 grid((a->w + F_TW - 1) / F_TW, (a->h + F_TH - 1) / F_TH);
+    dim3 grid((a->w + F_TW - 1) / F_TW, (p.row_end - p.row_begin + F_TH - 1) / F_TH);
     front_kernel<<<grid, 256, smem, stream>>>(p);
     DCR_LAUNCH_OK("front_kernel");
     return 0;

@@ -402,6 +402,9 @@ extern "C" int dcr_apply_z_shift(float* band, int h, int w, int64_t stride, doub
 struct IterDev {
     unsigned long long counters[4];  // base, after max_dz, slope-valid, (pad)
     unsigned long long count_mad, count_final;
+    long long rank_counts[8];        // row-band mode: unmasked-pixel count of every band (own slot written, all-reduced)
+    long long band_base;             // row-band mode: unmasked pixels in the bands above this one
+    double mom3[4];                  // row-band mode: {n, sum y, sum y^2, pad} of the common-mask samples (all-reduced)
     SelState sel[5];                 // 0 med(dh|A)  1 med|dh-med|  2 med(dh|F)  3 med(subsample)  4 med(slope)
     BselState bsel[5];               // the same five selections through the one-pass sample-bracket select
     float selres[5];                 // results of whichever engine ran (device-side consumers read these)
@@ -492,7 +495,6 @@ static size_t iter_ws_bytes(long long n, int grid) {
 }
 extern "C" size_t dcr_iteration_workspace_bytes(int64_t n) { return iter_ws_bytes(n, dcr_num_sms() * 8); }
 
-int dcr_chunk_scan_enqueue(const unsigned* cnt, long long nchunks, long long* off, long long* total, cudaStream_t s);
 
 __global__ void sel_publish_kernel(IterDev* d, int k, int use_bsel) {
     if (threadIdx.x == 0) d->selres[k] = use_bsel ? d->bsel[k].result : d->sel[k].result;
@@ -576,6 +578,59 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
     return 0;
 }
 
+// host part of an iteration: counts, guards, bin selection, fit, shift (coreglib.py:206-305, dem_align.py:150-172)
+static int iter_finalize(const IterDev* hd, int engine_used, dcr_iter_result* out) {
+    out->select_engine = engine_used;
+    float selres[5];
+    for (int k = 0; k < 5; ++k) selres[k] = engine_used ? hd->bsel[k].result : hd->sel[k].result;
+    out->count_base = (int64_t)hd->counters[0];
+    out->count_maxdz = (int64_t)hd->counters[1];
+    out->count_slope = (int64_t)hd->counters[2];
+    out->count_mad = (int64_t)hd->count_mad;
+    out->count_final = (int64_t)hd->count_final;
+    out->stats_stride = hd->stride;
+    out->med1 = selres[0];
+    out->nmad1 = hd->nmad;
+    out->mad_lo = hd->mad_lo;
+    out->mad_hi = hd->mad_hi;
+    out->med_dh = selres[2];
+    out->dz_med = hd->stride > 1 ? selres[3] : selres[2];
+    out->med_slope = selres[4];
+    nuth_dev_to_stats(hd->nuth, &out->nuth);
+    out->dz = -(double)out->dz_med;
+    if (out->count_base == 0) { out->status = 1; return 0; }
+    if (out->count_final < 100) { out->status = 2; return 0; }
+    if (out->count_slope < 100) { out->status = 3; return 0; }
+    // c_seed (coreglib.py:216), float32
+    out->c_seed = out->med_dh / tanf(out->med_slope * 0.017453292519943295f);
+    // keep bins with >= 9 samples; need >= 90 bins and ptp(cos(centres)) >= 1 (coreglib.py:280-301)
+    double xc[NB], ym[NB];
+    int nb = 0;
+    double cmin = INFINITY, cmax = -INFINITY;
+    for (int k = 0; k < NB; ++k) {
+        if (out->nuth.bin_count[k] >= 9) {
+            xc[nb] = k + 0.5;
+            ym[nb] = (double)out->nuth.bin_med[k];
+            const double c = cos(xc[nb] * (M_PI / 180.0));
+            cmin = fmin(cmin, c); cmax = fmax(cmax, c);
+            ++nb;
+        }
+    }
+    out->n_valid_bins = nb;
+    if (nb >= 90 && (cmax - cmin) >= 1.0) {
+        int rc = dcr_fit_nuth(xc, ym, nb, out->fit);
+        if (rc) return rc;
+        const double br = out->fit[1] * (M_PI / 180.0);
+        out->dx = -(out->fit[0] * sin(br));
+        out->dy = -(out->fit[0] * cos(br));
+    } else {
+        out->status = 4;
+        out->fit[0] = out->fit[1] = out->fit[2] = NAN;
+        out->dx = -0.0; out->dy = -0.0;
+    }
+    return 0;
+}
+
 extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_iter_result* out, void* workspace,
                                   size_t workspace_bytes, void* stream) {
     DCR_ARG(front && out && workspace, "null pointer");
@@ -633,53 +688,230 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_it
     memset(out, 0, sizeof(*out));
     if (prof)
         for (int k = 0; k < 7; ++k) DCR_CUDA_OK(cudaEventElapsedTime(&out->stage_ms[k], ev[k], ev[k + 1]));
-    out->select_engine = engine_used;
-    float selres[5];
-    for (int k = 0; k < 5; ++k) selres[k] = engine_used ? hd->bsel[k].result : hd->sel[k].result;
-    out->count_base = (int64_t)hd->counters[0];
-    out->count_maxdz = (int64_t)hd->counters[1];
-    out->count_slope = (int64_t)hd->counters[2];
-    out->count_mad = (int64_t)hd->count_mad;
-    out->count_final = (int64_t)hd->count_final;
-    out->stats_stride = hd->stride;
-    out->med1 = selres[0];
-    out->nmad1 = hd->nmad;
-    out->mad_lo = hd->mad_lo;
-    out->mad_hi = hd->mad_hi;
-    out->med_dh = selres[2];
-    out->dz_med = hd->stride > 1 ? selres[3] : selres[2];
-    out->med_slope = selres[4];
-    nuth_dev_to_stats(hd->nuth, &out->nuth);
-    out->dz = -(double)out->dz_med;
-    if (out->count_base == 0) { out->status = 1; return 0; }
-    if (out->count_final < 100) { out->status = 2; return 0; }
-    if (out->count_slope < 100) { out->status = 3; return 0; }
-    // c_seed (coreglib.py:216), float32
-    out->c_seed = out->med_dh / tanf(out->med_slope * 0.017453292519943295f);
-    // keep bins with >= 9 samples; need >= 90 bins and ptp(cos(centres)) >= 1 (coreglib.py:280-301)
-    double xc[NB], ym[NB];
-    int nb = 0;
-    double cmin = INFINITY, cmax = -INFINITY;
-    for (int k = 0; k < NB; ++k) {
-        if (out->nuth.bin_count[k] >= 9) {
-            xc[nb] = k + 0.5;
-            ym[nb] = (double)out->nuth.bin_med[k];
-            const double c = cos(xc[nb] * (M_PI / 180.0));
-            cmin = fmin(cmin, c); cmax = fmax(cmax, c);
-            ++nb;
+    return iter_finalize(hd, engine_used, out);
+}
+
+// ------------------------------------------------------------------------------------------
+// Row-band mode: one very large raster split into bands of output rows, one band per GPU.
+// The iteration is cut into phases; after a phase the caller all-reduces (sum) the buffers the phase
+// declares -- integer histograms / counters and three FP64 sums -- and calls the next phase.  All selections
+// use the 3-pass radix select (its histograms are what gets all-reduced), so the integer results are
+// bit-identical to the single-GPU path.  (BASELINE.json configs[4].)
+// ------------------------------------------------------------------------------------------
+enum {
+    BP_FRONT = 0,
+    BP_SEL0 = 1,       // 4 phases per selection: H0 | F0+H1 | F1+H2 | F2+publish
+    BP_SEL1 = 5,
+    BP_MASK = 9,
+    BP_COMPRESS = 10,
+    BP_SEL2 = 11,
+    BP_SEL3 = 15,
+    BP_SEL4 = 19,
+    BP_PREPARE = 23,
+    BP_BIN0 = 24,
+    BP_BIN1 = 25,
+    BP_BIN2 = 26,
+    BP_FINAL = 27,
+    BP_COUNT = 28
+};
+
+__global__ void band_rank_count_kernel(IterDev* d, int rank) {
+    if (threadIdx.x == 0) d->rank_counts[rank] = (long long)d->count_final;
+}
+__global__ void band_base_kernel(IterDev* d, int rank, int nranks) {
+    if (threadIdx.x) return;
+    long long base = 0, tot = 0;
+    for (int r = 0; r < nranks; ++r) { if (r < rank) base += d->rank_counts[r]; tot += d->rank_counts[r]; }
+    d->band_base = base;
+    d->total_final = tot;
+}
+__global__ void band_dense_n_kernel(IterDev* d, int rank) {
+    if (threadIdx.x) return;
+    const long long stride = d->stride, base = d->band_base, cnt = d->rank_counts[rank];
+    d->dense_n = stride > 1 ? ((base + cnt + stride - 1) / stride - (base + stride - 1) / stride) : 0;
+}
+__global__ void __launch_bounds__(256) band_mom_reduce_kernel(const NuthPartial* __restrict__ part, int nparts, IterDev* d) {
+    __shared__ NuthPartial sp[256];
+    NuthPartial q; q.n = 0; q.s = 0; q.ss = 0;
+    for (int k = threadIdx.x; k < nparts; k += 256) { q.n += part[k].n; q.s += part[k].s; q.ss += part[k].ss; }
+    sp[threadIdx.x] = q;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { sp[threadIdx.x].n += sp[threadIdx.x + o].n; sp[threadIdx.x].s += sp[threadIdx.x + o].s; sp[threadIdx.x].ss += sp[threadIdx.x + o].ss; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { d->mom3[0] = (double)sp[0].n; d->mom3[1] = sp[0].s; d->mom3[2] = sp[0].ss; d->mom3[3] = 0.0; }
+}
+// moments_final from the all-reduced sums (same arithmetic as nuth_moments_final_kernel)
+__global__ void band_moments_final_kernel(IterDev* d, int remove_outliers) {
+    NuthDev* nd = &d->nuth;
+    if (threadIdx.x == 0) {
+        const unsigned long long cnt = (unsigned long long)d->mom3[0];
+        nd->n_common = cnt;
+        nd->n_final = 0;
+        float mean = __int_as_float(0x7fc00000), sd = mean;
+        if (cnt) {
+            const double mu = d->mom3[1] / (double)cnt;
+            double var = d->mom3[2] / (double)cnt - mu * mu;
+            if (var < 0) var = 0;
+            mean = (float)mu;
+            sd = (float)sqrt(var);
         }
+        nd->mean_y = mean; nd->std_y = sd;
+        if (remove_outliers) { const float fs = 3.0f * sd; nd->rmin = mean - fs; nd->rmax = mean + fs; }
+        else { nd->rmin = -INFINITY; nd->rmax = INFINITY; }
     }
-    out->n_valid_bins = nb;
-    if (nb >= 90 && (cmax - cmin) >= 1.0) {
-        int rc = dcr_fit_nuth(xc, ym, nb, out->fit);
-        if (rc) return rc;
-        const double br = out->fit[1] * (M_PI / 180.0);
-        out->dx = -(out->fit[0] * sin(br));
-        out->dy = -(out->fit[0] * cos(br));
-    } else {
-        out->status = 4;
-        out->fit[0] = out->fit[1] = out->fit[2] = NAN;
-        out->dx = -0.0; out->dy = -0.0;
+    for (int k = threadIdx.x; k < NB; k += blockDim.x) {
+        nd->bin_count[k] = 0ull;
+        nd->prefix_lo[k] = nd->prefix_hi[k] = 0u;
+        nd->same[k] = 1;
+        nd->bin_med[k] = __int_as_float(0x7fc00000);
     }
+}
+
+static int band_carve(void* workspace, size_t workspace_bytes, long long n, int grid, IterWs* w) {
+    DcrBump ws(workspace, workspace_bytes);
+    w->d = ws.take<IterDev>(1);
+    w->hist = ws.take<unsigned>(DCR_SEL_HIST_WORDS);
+    const long long nch = (n + MU_CHUNK - 1) / MU_CHUNK;
+    w->chunk_cnt = ws.take<unsigned>(nch);
+    w->chunk_off = ws.take<long long>(nch);
+    w->dense_cap = n < 6000016 ? n : 6000016;
+    w->dense = ws.take<float>(w->dense_cap);
+    w->bsel_scratch = ws.take<char>(dcr_bsel_scratch_bytes(n));
+    if (nuth_ws_carve(ws, n, grid, &w->nw)) return -1;
+    w->nw.nd = &w->d->nuth;
     return 0;
+}
+
+extern "C" int dcr_band_nphases(void) { return BP_COUNT; }
+
+// Runs phase `phase` of the iteration on this rank's band (front->row_begin/row_end).  On return reduce_ptr[k] /
+// reduce_count[k] / reduce_kind[k] (k < *nreduce <= 2) describe device buffers inside `workspace` that must be
+// summed over all ranks before the next phase: kind 0 = int32 (histograms), 1 = int64 (counters), 2 = float64.
+extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, int nranks, int phase, void* workspace,
+                              size_t workspace_bytes, void** reduce_ptr, int64_t* reduce_count, int* reduce_kind,
+                              int* nreduce, void* stream) {
+    DCR_ARG(front && workspace && reduce_ptr && reduce_count && reduce_kind && nreduce, "null pointer");
+    DCR_ARG(nranks >= 1 && nranks <= 8 && rank >= 0 && rank < nranks, "1 <= nranks <= 8");
+    DCR_ARG(phase >= 0 && phase < BP_COUNT, "bad phase");
+    const int remove_outliers = (flags & DCR_ITER_REMOVE_OUTLIERS) ? 1 : 0;
+    const int rb = front->row_end > 0 ? front->row_begin : 0, re = front->row_end > 0 ? front->row_end : front->h;
+    const long long n = (long long)(re - rb) * front->w;
+    DCR_ARG(n > 0, "empty band");
+    const int grid = dcr_num_sms() * 8;
+    DCR_ARG(workspace_bytes >= iter_ws_bytes(n, grid), "workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    IterWs w;
+    if (band_carve(workspace, workspace_bytes, n, grid, &w)) return -1;
+    IterDev* d = w.d;
+    const long long nch = (n + MU_CHUNK - 1) / MU_CHUNK;
+    *nreduce = 0;
+    auto want = [&](void* p, int64_t cnt, int kind) { reduce_ptr[*nreduce] = p; reduce_count[*nreduce] = cnt; reduce_kind[*nreduce] = kind; ++*nreduce; };
+    int rc = 0;
+
+    // selections: view k
+    auto view_of = [&](int k) {
+        SelView v;
+        memset(&v, 0, sizeof(v));
+        v.x = front->dh; v.m = front->maskbits; v.n = n;
+        if (k == 0) { v.reject = DCR_M_BASE | DCR_M_MAXDZ; }
+        else if (k == 1) { v.reject = DCR_M_BASE | DCR_M_MAXDZ; v.transform = 1; v.center_ptr = &d->selres[0]; }
+        else if (k == 2) { v.reject = DCR_M_DIFF; }
+        else if (k == 3) { v.x = w.dense; v.m = nullptr; v.n = 0; v.n_ptr = &d->dense_n; }
+        else { v.x = front->slope; v.reject = DCR_M_SLOPE; }
+        return v;
+    };
+    auto sel_phase = [&](int k, int sub) -> int {
+        // sub 0: H0 | 1: F0+H1 | 2: F1+H2 | 3: F2 + publish
+        if ((k == 0 || k == 1) && !remove_outliers) return 0;
+        SelView v = view_of(k);
+        int r2 = 0;
+        if (sub == 0) DCR_CUDA_OK(cudaMemsetAsync(w.hist, 0, DCR_SEL_HIST_WORDS * sizeof(unsigned), s));
+        if (sub > 0) r2 = dcr_sel_find_pass(&d->sel[k], w.hist, 50.0, sub - 1, s);
+        if (r2) return r2;
+        if (sub < 3) {
+            r2 = dcr_sel_hist_pass(v, &d->sel[k], w.hist, sub, s);
+            if (r2) return r2;
+            want(w.hist, DCR_SEL_HIST_WORDS, 0);
+        } else {
+            sel_publish_kernel<<<1, 32, 0, s>>>(d, k, 0);
+        }
+        return 0;
+    };
+
+    if (phase == BP_FRONT) {
+        DCR_CUDA_OK(cudaMemsetAsync(d, 0, sizeof(IterDev), s));
+        dcr_front_args fa = *front;
+        if (!remove_outliers) fa.use_max_dz = 0;
+        if ((rc = dcr_front_launch(&fa, d->counters, s))) return rc;
+        want(d->counters, 4, 1);
+    } else if (phase >= BP_SEL0 && phase < BP_SEL1) {
+        rc = sel_phase(0, phase - BP_SEL0);
+    } else if (phase >= BP_SEL1 && phase < BP_MASK) {
+        rc = sel_phase(1, phase - BP_SEL1);
+    } else if (phase == BP_MASK) {
+        mad_thresholds_kernel<<<1, 32, 0, s>>>(d, remove_outliers);
+        mask_update_kernel<<<(unsigned)nch, 256, 0, s>>>(front->dh, front->maskbits, n, d, w.chunk_cnt);
+        band_rank_count_kernel<<<1, 32, 0, s>>>(d, rank);
+        want(&d->count_mad, 2 + 8, 1);  // count_mad, count_final, rank_counts[8] are contiguous
+    } else if (phase == BP_COMPRESS) {
+        // after the all-reduce count_final is global; the per-band counts give this band's rank offset
+        band_base_kernel<<<1, 32, 0, s>>>(d, rank, nranks);
+        if ((rc = dcr_chunk_scan_enqueue(w.chunk_cnt, nch, w.chunk_off, &d->dense_n /* scratch */, s))) return rc;
+        stride_kernel<<<1, 32, 0, s>>>(d);
+        band_dense_n_kernel<<<1, 32, 0, s>>>(d, rank);
+        if ((rc = dcr_compress_enqueue(front->dh, front->maskbits, DCR_M_DIFF, n, w.chunk_off, 1, &d->stride, w.dense,
+                                       w.dense_cap, s, &d->band_base)))
+            return rc;
+    } else if (phase >= BP_SEL2 && phase < BP_SEL3) {
+        rc = sel_phase(2, phase - BP_SEL2);
+    } else if (phase >= BP_SEL3 && phase < BP_SEL4) {
+        rc = sel_phase(3, phase - BP_SEL3);
+    } else if (phase >= BP_SEL4 && phase < BP_PREPARE) {
+        rc = sel_phase(4, phase - BP_SEL4);
+    } else if (phase == BP_PREPARE) {
+        DCR_CUDA_OK(cudaMemsetAsync(w.nw.ghist, 0, (size_t)2 * NB * 2048 * sizeof(unsigned), s));
+        nuth_prepare_kernel<<<grid, 256, 0, s>>>(front->dh, front->slope, front->aspect, front->maskbits,
+                                                 DCR_M_DIFF | DCR_M_ASPECT, n, w.nw.y, w.nw.bin, w.nw.part);
+        band_mom_reduce_kernel<<<1, 256, 0, s>>>(w.nw.part, grid, d);
+        want(d->mom3, 4, 2);
+    } else if (phase == BP_BIN0) {
+        band_moments_final_kernel<<<1, 256, 0, s>>>(d, remove_outliers);
+        bin_hist_kernel<0><<<grid, 256, 0, s>>>(w.nw.y, w.nw.bin, n, &d->nuth, w.nw.ghist);
+        want(w.nw.ghist, (int64_t)2 * NB * 2048, 0);
+        want(d->nuth.bin_count, NB, 1);
+    } else if (phase == BP_BIN1) {
+        bin_find_kernel<0><<<NB, 256, 0, s>>>(&d->nuth, w.nw.ghist);
+        bin_hist_kernel<1><<<grid, 256, 0, s>>>(w.nw.y, w.nw.bin, n, &d->nuth, w.nw.ghist);
+        want(w.nw.ghist, (int64_t)2 * NB * 2048, 0);
+    } else if (phase == BP_BIN2) {
+        bin_find_kernel<1><<<NB, 256, 0, s>>>(&d->nuth, w.nw.ghist);
+        bin_hist_kernel<2><<<grid, 256, 0, s>>>(w.nw.y, w.nw.bin, n, &d->nuth, w.nw.ghist);
+        want(w.nw.ghist, (int64_t)2 * NB * 2048, 0);
+    } else if (phase == BP_FINAL) {
+        bin_find_kernel<2><<<NB, 256, 0, s>>>(&d->nuth, w.nw.ghist);
+        nuth_count_final_kernel<<<1, 32, 0, s>>>(&d->nuth);
+    }
+    if (rc) return rc;
+    DCR_LAUNCH_OK("band phase kernels");
+    return 0;
+}
+
+// After the last phase: copy the (identical on every rank) result block to the host and finish like dcr_nuth_iteration.
+extern "C" int dcr_band_result(const dcr_front_args* front, void* workspace, size_t workspace_bytes, dcr_iter_result* out,
+                               void* stream) {
+    DCR_ARG(front && workspace && out, "null pointer");
+    const int rb = front->row_end > 0 ? front->row_begin : 0, re = front->row_end > 0 ? front->row_end : front->h;
+    const long long n = (long long)(re - rb) * front->w;
+    const int grid = dcr_num_sms() * 8;
+    IterWs w;
+    if (band_carve(workspace, workspace_bytes, n, grid, &w)) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    static thread_local IterDev* hd = nullptr;
+    if (!hd) DCR_CUDA_OK(cudaHostAlloc((void**)&hd, sizeof(IterDev), cudaHostAllocDefault));
+    DCR_CUDA_OK(cudaMemcpyAsync(hd, w.d, sizeof(IterDev), cudaMemcpyDeviceToHost, s));
+    DCR_CUDA_OK(cudaStreamSynchronize(s));
+    memset(out, 0, sizeof(*out));
+    return iter_finalize(hd, 0, out);
 }

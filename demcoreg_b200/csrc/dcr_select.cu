@@ -145,6 +145,23 @@ int dcr_sel_enqueue(const SelView& v, double q_percent, SelState* st, unsigned* 
     return 0;
 }
 
+// single passes of the radix select (row-band mode all-reduces `hist` between the hist and find steps)
+int dcr_sel_hist_pass(const SelView& v, SelState* st, unsigned* hist, int pass, cudaStream_t s) {
+    const int grid = dcr_num_sms() * 8;
+    if (pass == 0) sel_hist_kernel<0><<<grid, SEL_THREADS, 0, s>>>(v, st, hist);
+    else if (pass == 1) sel_hist_kernel<1><<<grid, SEL_THREADS, 0, s>>>(v, st, hist);
+    else sel_hist_kernel<2><<<grid, SEL_THREADS, 0, s>>>(v, st, hist);
+    DCR_LAUNCH_OK("sel_hist_kernel");
+    return 0;
+}
+int dcr_sel_find_pass(SelState* st, unsigned* hist, double q_percent, int pass, cudaStream_t s) {
+    if (pass == 0) sel_find_kernel<0><<<1, 1024, 0, s>>>(st, hist, q_percent);
+    else if (pass == 1) sel_find_kernel<1><<<1, 1024, 0, s>>>(st, hist, q_percent);
+    else sel_find_kernel<2><<<1, 1024, 0, s>>>(st, hist, q_percent);
+    DCR_LAUNCH_OK("sel_find_kernel");
+    return 0;
+}
+
 extern "C" size_t dcr_select_workspace_bytes(void) {
     // worst case used by engine.py for any n: query with dcr_select_workspace_bytes_n for large inputs
     return dcr_al256(DCR_SEL_HIST_WORDS * sizeof(unsigned)) + dcr_al256(16 * sizeof(SelState)) +
@@ -354,7 +371,7 @@ __global__ void __launch_bounds__(256) compress_strided_kernel(const float* __re
                                                                unsigned reject, long long n,
                                                                const long long* __restrict__ off, long long stride_imm,
                                                                const long long* stride_ptr, float* __restrict__ dense,
-                                                               long long cap) {
+                                                               long long cap, const long long* base_ptr) {
     __shared__ unsigned s_scratch[33];
     const long long stride = stride_ptr ? *stride_ptr : stride_imm;
     if (stride_ptr && stride <= 1) return;  // iteration driver: no subsample needed
@@ -368,12 +385,15 @@ __global__ void __launch_bounds__(256) compress_strided_kernel(const float* __re
         if (!(mb[k] & (reject | 0xffffff00u)) && !isnan(vals[k])) { flags |= 1u << k; ++c; }
     unsigned total;
     unsigned ex = dcr_block_excl_scan(c, s_scratch, &total);
-    long long rank = off[blockIdx.x] + ex;
+    // row-band mode: this band's elements follow `base` unmasked elements of the bands above it
+    const long long gbase = base_ptr ? *base_ptr : 0;
+    const long long dfirst = (gbase + stride - 1) / stride;  // global subsample index of this band's first pick
+    long long rank = gbase + off[blockIdx.x] + ex;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         if (flags & (1u << k)) {
             if (rank % stride == 0) {
-                const long long d = rank / stride;
+                const long long d = rank / stride - dfirst;
                 if (d < cap) dense[d] = vals[k];
             }
             ++rank;
@@ -383,9 +403,10 @@ __global__ void __launch_bounds__(256) compress_strided_kernel(const float* __re
 
 int dcr_compress_enqueue(const float* x, const unsigned char* m, unsigned reject, long long n, const long long* chunk_off,
                          long long stride_imm, const long long* stride_ptr, float* dense, long long cap,
-                         cudaStream_t s) {
+                         cudaStream_t s, const long long* base_ptr) {
     const long long nchunks = (n + CHUNK - 1) / CHUNK;
-    compress_strided_kernel<<<(unsigned)nchunks, 256, 0, s>>>(x, m, reject, n, chunk_off, stride_imm, stride_ptr, dense, cap);
+    compress_strided_kernel<<<(unsigned)nchunks, 256, 0, s>>>(x, m, reject, n, chunk_off, stride_imm, stride_ptr, dense, cap,
+                                                              base_ptr);
     DCR_LAUNCH_OK("compress_strided_kernel");
     return 0;
 }

@@ -105,6 +105,11 @@ typedef struct dcr_front_args {
     /* outputs (device, contiguous h*w): */
     float* dh; float* slope; float* aspect; uint8_t* maskbits;
     float* ref_w; float* src_w;        /* optional warped rasters (NULL to skip) */
+    /* row-band mode (all zero = whole rasters): compute output rows [row_begin, row_end) only; `ref`, `src`, `smask`
+     * then point at the first row HELD IN MEMORY, global row index *_row0, *_nrows rows (band + halo); outputs are
+     * band-local ((row_end - row_begin) x w).  -5 is returned when a halo is too small for the current shift. */
+    int32_t row_begin, row_end;
+    int32_t ref_row0, ref_nrows, src_row0, src_nrows, smask_row0, smask_nrows;
 } dcr_front_args;
 int dcr_warp_diff_horn(const dcr_front_args* args, void* stream);
 
@@ -221,6 +226,21 @@ typedef struct dcr_iter_result {
 size_t dcr_iteration_workspace_bytes(int64_t n);
 int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_iter_result* out /* host */,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- row-band mode: one very large raster split into bands of output rows, one band per GPU ----------------
+ * (BASELINE.json configs[4]; the reference does not tile -- it loads whole arrays, dem_align.py:79-80.)
+ * The iteration of dcr_nuth_iteration is cut into dcr_band_nphases() phases.  Each rank calls dcr_band_phase for
+ * its band (front->row_begin/row_end, rasters held as band + halo, see dcr_front_args), then all-reduces (sum)
+ * the device buffers the phase declares -- kind 0 = int32 histograms, 1 = int64 counters, 2 = float64 sums -- over
+ * all ranks (ncclAllReduce / torch.distributed.all_reduce on `stream`) and calls the next phase.  Halo rows of the
+ * rasters are exchanged by the caller (ncclSend/Recv).  After the last phase dcr_band_result() returns the same
+ * dcr_iter_result on every rank.  Workspace: dcr_iteration_workspace_bytes(rows_in_band * w). */
+int dcr_band_nphases(void);
+int dcr_band_phase(const dcr_front_args* front, int flags, int rank, int nranks, int phase, void* workspace,
+                   size_t workspace_bytes, void** reduce_ptr, int64_t* reduce_count, int* reduce_kind, int* nreduce,
+                   void* stream);
+int dcr_band_result(const dcr_front_args* front, void* workspace, size_t workspace_bytes, dcr_iter_result* out,
+                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -59,3 +59,46 @@ def test_shard_single_process():
     assert sorted(sum((batch.shard(10, r, 4) for r in range(4)), [])) == list(range(10))
     out = batch.align_batch([dict(id=0, shift=(1.0, 2.0, 3.0))], _fake_align)
     assert out == [dict(dx=1.0, dy=2.0, dz=-3.0, n_iter=3)]
+
+
+def _halo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from demcoreg_b200 import band
+    H, W, halo = 37, 5, 3
+    full = torch.arange(H * W, dtype=torch.float32).reshape(H, W)
+    r0, r1 = band.band_rows(H, rank, world)
+    b, owned = band.make_band(full[r0:r1], r0, r1, H, halo, (0, 1, 0, H, 0, -1), -9999.0, torch, fill=-1.0, device="cpu")
+    band.exchange_halos(b, owned, rank, world)
+    lo = max(0, r0 - halo)
+    hi = min(H, r1 + halo)
+    q.put((rank, bool(torch.equal(b.data, full[lo:hi])), b.row0 == lo))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_halo_exchange_world3():
+    """Row-band halo exchange (send/recv with both neighbours) under a real 3-rank gloo group on CPU tensors."""
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_halo_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True, True), (1, True, True), (2, True, True)]
+
+
+def test_band_rows_partition():
+    from demcoreg_b200 import band
+    for H, G in ((32768, 8), (1000, 3), (7, 4)):
+        rows = [band.band_rows(H, r, G) for r in range(G)]
+        assert rows[0][0] == 0 and rows[-1][1] == H
+        assert all(rows[k][1] == rows[k + 1][0] for k in range(G - 1))

@@ -408,3 +408,55 @@ def test_robust_stats_and_stats_dict(cuda):
     assert gd['count'] == od['count'] and gd['min'] == od['min'] and gd['max'] == od['max'] and gd['mode'] == od['mode']
     for k in ('ptp', 'mean', 'std', 'nmad', 'med', 'median', 'p16', 'p84', 'spread'):
         assert abs(gd[k] - od[k]) <= 1e-6 * max(1.0, abs(od[k])), k
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_row_band_virtual_ranks_match_single_gpu(cuda, world):
+    """Row-band mode with G virtual ranks on one device (in-process sum instead of the all-reduce) reproduces
+    the single-GPU iteration: integer results bit-identical, FP64-sum-derived values to rounding."""
+    from demcoreg_b200 import engine, band
+    from demcoreg_b200.raster import MaskSource
+    p = _pair(n=1024, res=8.0, nodata_frac=0.01, static_mask_frac=0.3)
+    gt_s = _shifted_gt(p['gt'], 13.7, -21.3)   # 1.7 px / 2.7 px: halos and intersection rows in play
+    ms = MaskSource(p['mask'], p['gt'])
+    r1, grid, bufs = engine.nuth_iteration(_gds(p, 'ref'), _gds(p, 'src', gt_s), ms, radix_only=True)
+    vg = band.VirtualGroup(p['ref'], p['src'], p['mask'], p['gt'], p['ndv'], world, halo=8)
+    for al in vg.ranks:
+        al.src.gt = gt_s
+    res = vg.iteration()
+    rows = 0
+    for al, r in zip(vg.ranks, res):
+        for f in ("count_base", "count_maxdz", "count_mad", "count_final", "count_slope", "stats_stride", "med1", "nmad1",
+                  "mad_lo", "mad_hi", "dz_med", "med_dh", "med_slope"):
+            assert getattr(r, f) == getattr(r1, f), (f, getattr(r, f), getattr(r1, f))
+        assert list(r.nuth.bin_count) == list(r1.nuth.bin_count)
+        assert r.nuth.n_common == r1.nuth.n_common and r.nuth.n_final == r1.nuth.n_final
+        np.testing.assert_allclose(np.array(r.nuth.bin_med[:]), np.array(r1.nuth.bin_med[:]), rtol=0, atol=0, equal_nan=True)
+        assert abs(r.dx - r1.dx) < 1e-9 and abs(r.dy - r1.dy) < 1e-9 and r.dz == r1.dz
+        # band outputs are the matching rows of the single-GPU rasters
+        rb, re = al.args.row_begin, al.args.row_end
+        assert np.array_equal(al.bufs[0].cpu().numpy(), bufs.dh[rb:re].cpu().numpy())
+        assert np.array_equal(al.bufs[3].cpu().numpy(), bufs.maskbits[rb:re].cpu().numpy())
+        rows += re - rb
+    assert rows == grid.height
+
+
+def test_row_band_strided_stats_and_loop(cuda):
+    """count >= 4e6 in band mode (global compressed ranks across bands) + a 2-iteration loop with shifts applied."""
+    from demcoreg_b200 import engine, band, coreglib
+    p = _pair(n=3072, res=30.0, period=1024)
+    vg = band.VirtualGroup(p['ref'], p['src'], None, p['gt'], p['ndv'], 4, halo=8)
+    ref, src = _gds(p, 'ref'), _gds(p, 'src')
+    import contextlib, io
+    for it in range(2):
+        r1, _, _ = engine.nuth_iteration(ref, src, radix_only=True)
+        rs = vg.iteration()
+        assert r1.stats_stride == 2
+        for r in rs:
+            assert r.dz_med == r1.dz_med and r.count_final == r1.count_final
+            assert list(r.nuth.bin_count) == list(r1.nuth.bin_count)
+            assert abs(r.dx - r1.dx) < 1e-9 and abs(r.dy - r1.dy) < 1e-9
+        with contextlib.redirect_stdout(io.StringIO()):
+            coreglib.apply_xy_shift(src, r1.dx, r1.dy, createcopy=False)
+            coreglib.apply_z_shift(src, np.float32(r1.dz), createcopy=False)
+        vg.apply_shift(rs[0].dx, rs[0].dy, rs[0].dz)
