@@ -27,14 +27,14 @@ ALG_BYTES_ITER = 90.0      # algorithmic bytes per pixel per iteratio
 # algorithmic bytes per pixel of each profiled stage (SURVEY 8d stage table)
 STAGE_INFO = [
     ("front_kernel (warp+dh+masks+Horn)", 21.0),
-    ("sel_hist_kernel x6 (median + MAD)", 16.0),
+    ("bsel_main_kernel x2 + sample/find/refine (median + MAD of dh)", 16.0),
     ("mask_update+scan+compress", 6.0),
-    ("sel_hist_kernel x9 (med_dh, dz, med_slope)", 16.0),
+    ("bsel_main_kernel x3 + sample/find/refine (med_dh, dz, med_slope)", 16.0),
     ("nuth_prepare_kernel (y, bin, moments)", 13.0 + 6.0),
     ("bin_hist_kernel x3 (bin count + median)", 12.0),
     ("result copy", 0.0),
 ]
-KERNELS_PER_STEP = 1 + 12 + 1 + 1 + 1 + 1 + 1 + 18 + 2 + 6 + 1 + 1  # see DESIGN.md "launch count"
+KERNELS_PER_STEP = 1 + 30 + 5 + 9 + 1  # see DESIGN.md section 6 "launch count"
 
 
 def peaks():
