@@ -119,3 +119,30 @@ def test_compute_entry_points_fail_loudly_without_cuda(built_lib):
     from demcoreg_b200.raster import Raster
     with pytest.raises(_lib.DcrError):
         Raster(np.zeros((4, 4), dtype=np.float32), (0, 1, 0, 4, 0, -1))
+
+
+def test_rasterio_lite_roundtrip(tmp_path):
+    from demcoreg_b200 import rasterio_lite as rio
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((37, 53)).astype(np.float32)
+    gt = (500000.0, 30.0, 0.0, 4100000.0, 0.0, -30.0)
+    for ext in (".tif", ".npz"):
+        fn = str(tmp_path / ("r" + ext))
+        rio.write_raster(fn, a, gt, -9999.0)
+        r = rio.read_array(fn)
+        assert np.array_equal(r["array"], a) and tuple(r["gt"]) == gt and r["ndv"] == -9999.0
+    fn = str(tmp_path / "m.tif")
+    m = (rng.random((20, 10)) < 0.5).astype(np.uint8)
+    rio.write_raster(fn, m, gt, None)
+    r = rio.read_array(fn)
+    assert np.array_equal(r["array"], m) and r["ndv"] is None
+
+
+def test_cli_parser_matches_reference_options():
+    from demcoreg_b200 import dem_align
+    p = dem_align.getparser()
+    a = p.parse_args(["ref.tif", "src.tif"])
+    assert (a.mode, a.mask_list, a.tiltcorr, a.polyorder, a.tol, a.max_offset, a.max_dz, a.res, tuple(a.slope_lim),
+            a.max_iter, a.outdir) == ('nuth', [], False, 1, 0.02, 100, 100, 'mean', (0.1, 40), 30, None)
+    a = p.parse_args(["r", "s", "-mode", "ncc", "-max_offset", "200", "-res", "min", "-slope_lim", "1", "30"])
+    assert a.mode == 'ncc' and a.max_offset == 200 and a.res == 'min' and a.slope_lim == [1.0, 30.0]

@@ -460,3 +460,23 @@ def test_row_band_strided_stats_and_loop(cuda):
             coreglib.apply_xy_shift(src, r1.dx, r1.dy, createcopy=False)
             coreglib.apply_z_shift(src, np.float32(r1.dz), createcopy=False)
         vg.apply_shift(rs[0].dx, rs[0].dy, rs[0].dz)
+
+
+def test_cli_end_to_end(cuda, tmp_path):
+    """dem_align.main on GeoTIFF files: same cumulative shift as the oracle loop, output raster + json written."""
+    import json
+    from demcoreg_b200 import dem_align, rasterio_lite as rio
+    from oracle import dem_align as oda
+    p = _pair(n=512)
+    rfn, sfn = str(tmp_path / "ref.tif"), str(tmp_path / "src.tif")
+    rio.write_raster(rfn, p['ref'], p['gt'], p['ndv'])
+    rio.write_raster(sfn, p['src'], p['gt'], p['ndv'])
+    info = dem_align.main([rfn, sfn, "-outdir", str(tmp_path / "out")])
+    oo = oda.align(_ods(p, 'ref'), _ods(p, 'src'), final_stats=False)
+    for k in ('dx', 'dy', 'dz'):
+        assert abs(info['shift'][k] - oo[k]) < OFFTOL
+    out = rio.read_array(info['align_fn'])
+    assert np.array_equal(out['array'], oo['src_align'].array)
+    assert abs(out['gt'][0] - oo['src_align'].gt[0]) < 1e-9 and abs(out['gt'][3] - oo['src_align'].gt[3]) < 1e-9
+    assert "_nuth_x%+0.2f_y%+0.2f_z%+0.2f" % (oo['dx'], oo['dy'], oo['dz']) in info['align_fn']
+    assert json.load(open(info['align_fn'].replace('_align.tif', '_align_stats.json')))['n_iter'] == oo['n_iter']
