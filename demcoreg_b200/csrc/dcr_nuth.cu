@@ -23,6 +23,14 @@ struct NuthDev {
     long long k_lo[NB], k_hi[NB];
     int same[NB];
     float bin_med[NB];
+    // fast path (linear two-level bracket): fine cell f = (y - rmin) * 65536/(rmax - rmin) in [0, 65535], coarse = f >> 10
+    unsigned short fa_cell[2][NB];   // coarse cell of the lower / upper median element
+    unsigned short fb_cell[2][NB];   // fine cell of the lower / upper median element
+    unsigned fa_rank[2][NB];         // rank of the element inside its coarse cell, then inside its fine cell
+    unsigned fast_ncand;             // candidates appended by pass B
+    int fast_fallback;               // 1: fast path not applicable / overflow / heavy ties -> 3-pass radix bins
+    float fast_scale;
+    int fast_pad;
 };
 
 struct NuthPartial {
@@ -232,16 +240,227 @@ __global__ void nuth_count_final_kernel(NuthDev* nd) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K6 fast path: per-bin count + exact per-bin median in TWO streaming passes with shared-memory atomics.
+// All samples of the bin statistics lie in [rmin, rmax] (the 3-sigma trim), so a monotone linear map
+//   f = min(65535, (int)((y - rmin) * 65536/(rmax - rmin)))        (float32: monotone non-decreasing in y)
+// brackets ranks exactly: pass A histograms the coarse cell f >> 10 (64 cells x 360 bins, 92 KB of shared
+// memory per CTA) -> exact per-bin counts and the coarse cell of each bin's two median elements; pass B
+// histograms the 1024 fine cells of those coarse cells only (~4 % of the samples, global atomics) and stages the
+// same samples as candidates; pass C / D pick the candidates of the final fine cells (a handful per bin) and
+// select exactly among their float keys.  Heavy ties / degenerate ranges raise fast_fallback and the caller
+// runs the 3-pass radix bins instead.
+// ------------------------------------------------------------------------------------------
+#define FB_COARSE 64
+#define FB_FINE 1024
+#define FB_SLOT 128
+#define FB_HB_WORDS (2 * NB * FB_FINE)              // histB [2][NB][1024]
+#define FB_HA_OFF FB_HB_WORDS                       // histA [NB][64]
+#define FB_SLOT_OFF (FB_HA_OFF + NB * FB_COARSE)    // slots [NB][2][FB_SLOT]
+#define FB_SLOTN_OFF (FB_SLOT_OFF + NB * 2 * FB_SLOT)  // slot counters [NB][2]
+#define FB_WORDS (FB_SLOTN_OFF + NB * 2)
+
+__device__ __forceinline__ unsigned fb_fine(float y, float rmin, float scale) {
+    const float t = (y - rmin) * scale;
+    int f = (int)t;
+    f = f < 0 ? 0 : (f > 65535 ? 65535 : f);
+    return (unsigned)f;
+}
+
+__global__ void fb_init_kernel(NuthDev* nd) {
+    if (threadIdx.x) return;
+    const float span = nd->rmax - nd->rmin;
+    nd->fast_ncand = 0;
+    nd->fast_fallback = 0;
+    if (!(span > 0.0f) || isinf(span) || isnan(span)) { nd->fast_fallback = 1; nd->fast_scale = 0.f; return; }
+    nd->fast_scale = 65536.0f / span;
+}
+
+__global__ void __launch_bounds__(512) fb_passA_kernel(const float* __restrict__ y, const unsigned short* __restrict__ bin,
+                                                       long long n, const NuthDev* nd, unsigned* __restrict__ ghist) {
+    extern __shared__ unsigned sh[];  // [NB][64]
+    if (nd->fast_fallback) return;
+    for (int k = threadIdx.x; k < NB * FB_COARSE; k += blockDim.x) sh[k] = 0u;
+    __syncthreads();
+    const float rmin = nd->rmin, rmax = nd->rmax, scale = nd->fast_scale;
+    dcr_stream_f_u16(y, bin, n, [&](float yv, unsigned b, long long) {
+        if (b >= NB) return;
+        if (!(yv >= rmin && yv <= rmax)) return;
+        atomicAdd(&sh[b * FB_COARSE + (fb_fine(yv, rmin, scale) >> 10)], 1u);
+    });
+    __syncthreads();
+    unsigned* ha = ghist + FB_HA_OFF;
+    for (int k = threadIdx.x; k < NB * FB_COARSE; k += blockDim.x)
+        if (sh[k]) atomicAdd(&ha[k], sh[k]);
+}
+
+// one thread per bin: exact count, coarse cells of the two median elements
+__global__ void fb_findA_kernel(NuthDev* nd, const unsigned* __restrict__ ghist) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= NB || nd->fast_fallback) return;
+    const unsigned* ha = ghist + FB_HA_OFF + b * FB_COARSE;
+    unsigned long long cnt = 0;
+    for (int c = 0; c < FB_COARSE; ++c) cnt += ha[c];
+    nd->bin_count[b] = cnt;
+    if (cnt == 0) { nd->fa_cell[0][b] = nd->fa_cell[1][b] = 0xFFFF; return; }
+    const unsigned long long k[2] = {(cnt - 1) >> 1, cnt >> 1};  // scipy 'median': floor/ceil((n-1)/2)
+    for (int r = 0; r < 2; ++r) {
+        unsigned long long cum = 0;
+        for (int c = 0; c < FB_COARSE; ++c) {
+            const unsigned v = ha[c];
+            if (k[r] < cum + v) { nd->fa_cell[r][b] = (unsigned short)c; nd->fa_rank[r][b] = (unsigned)(k[r] - cum); break; }
+            cum += v;
+        }
+    }
+}
+
+#define FB_STAGE 4096
+__global__ void __launch_bounds__(256) fb_passB_kernel(const float* __restrict__ y, const unsigned short* __restrict__ bin,
+                                                       long long n, NuthDev* nd, unsigned* __restrict__ ghist,
+                                                       unsigned long long* __restrict__ cand, unsigned cap) {
+    __shared__ unsigned short s_c0[NB], s_c1[NB];
+    __shared__ unsigned long long s_buf[FB_STAGE];
+    __shared__ unsigned s_n, s_gbase;
+    if (nd->fast_fallback) return;
+    for (int k = threadIdx.x; k < NB; k += 256) { s_c0[k] = nd->fa_cell[0][k]; s_c1[k] = nd->fa_cell[1][k]; }
+    if (threadIdx.x == 0) s_n = 0u;
+    __syncthreads();
+    const float rmin = nd->rmin, rmax = nd->rmax, scale = nd->fast_scale;
+    dcr_stream_f_u16(y, bin, n, [&](float yv, unsigned b, long long) {
+        if (b >= NB) return;
+        if (!(yv >= rmin && yv <= rmax)) return;
+        const unsigned f = fb_fine(yv, rmin, scale);
+        const unsigned c = f >> 10;
+        const unsigned c0 = s_c0[b], c1 = s_c1[b];
+        if (c != c0 && c != c1) return;
+        // ~4 % of the samples get here
+        const int plane = (c == c0) ? 0 : 1;
+        atomicAdd(&ghist[(plane * NB + b) * FB_FINE + (f & (FB_FINE - 1))], 1u);
+        const unsigned long long rec = ((unsigned long long)dcr_f2key(yv) << 32) | ((unsigned long long)b << 16) | f;
+        const unsigned pos = atomicAdd(&s_n, 1u);
+        if (pos < FB_STAGE) s_buf[pos] = rec;
+        else {
+            const unsigned g = atomicAdd(&nd->fast_ncand, 1u);
+            if (g < cap) cand[g] = rec;
+        }
+    });
+    __syncthreads();
+    const unsigned nst = s_n < FB_STAGE ? s_n : FB_STAGE;
+    if (threadIdx.x == 0) s_gbase = nst ? atomicAdd(&nd->fast_ncand, nst) : 0u;
+    __syncthreads();
+    const unsigned gb = s_gbase;
+    for (unsigned k = threadIdx.x; k < nst; k += 256)
+        if (gb + k < cap) cand[gb + k] = s_buf[k];
+}
+
+// one warp per bin: fine cells of the two median elements (scan of 1024 fine cells)
+__global__ void __launch_bounds__(256) fb_findB_kernel(NuthDev* nd, unsigned* __restrict__ ghist, unsigned cap) {
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= NB || nd->fast_fallback) return;
+    if (b == 0 && lane == 0 && nd->fast_ncand > cap) nd->fast_fallback = 1;
+    if (nd->bin_count[b] == 0) return;
+    const unsigned c0 = nd->fa_cell[0][b], c1 = nd->fa_cell[1][b];
+    for (int r = 0; r < 2; ++r) {
+        const int plane = (r == 1 && c1 != c0) ? 1 : 0;
+        const unsigned* h = ghist + (plane * NB + b) * FB_FINE;
+        const unsigned k = nd->fa_rank[r][b];
+        // lane l owns fine cells [32 l, 32 l + 32)
+        unsigned v[32], sum = 0;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) { v[q] = h[lane * 32 + q]; sum += v[q]; }
+        const unsigned inc = dcr_warp_incl_scan(sum);
+        unsigned ex = inc - sum;
+        if (k >= ex && k < inc) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                if (k >= ex && k < ex + v[q]) {
+                    nd->fb_cell[r][b] = (unsigned short)(((r == 1 ? c1 : c0) << 10) | (lane * 32 + q));
+                    nd->fa_rank[r][b] = k - ex;   // now the rank inside the fine cell
+                    if (v[q] > FB_SLOT) nd->fast_fallback = 1;  // heavy ties: too many samples in one fine cell
+                }
+                ex += v[q];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(256) fb_passC_kernel(NuthDev* nd, const unsigned long long* __restrict__ cand,
+                                                       unsigned* __restrict__ ghist) {
+    if (nd->fast_fallback) return;
+    const unsigned ncand = nd->fast_ncand;
+    unsigned* slots = ghist + FB_SLOT_OFF;
+    unsigned* slotn = ghist + FB_SLOTN_OFF;
+    for (unsigned i = blockIdx.x * 256 + threadIdx.x; i < ncand; i += gridDim.x * 256) {
+        const unsigned long long rec = cand[i];
+        const unsigned f = (unsigned)(rec & 0xFFFFu), b = (unsigned)((rec >> 16) & 0xFFFFu), key = (unsigned)(rec >> 32);
+        const unsigned f0 = nd->fb_cell[0][b], f1 = nd->fb_cell[1][b];
+        if (f == f0) {
+            const unsigned pos = atomicAdd(&slotn[b * 2], 1u);
+            if (pos < FB_SLOT) slots[(b * 2) * FB_SLOT + pos] = key;
+        } else if (f == f1) {
+            const unsigned pos = atomicAdd(&slotn[b * 2 + 1], 1u);
+            if (pos < FB_SLOT) slots[(b * 2 + 1) * FB_SLOT + pos] = key;
+        }
+    }
+}
+
+// one warp per bin: exact selection among the <= 128 keys of the final fine cell(s)
+__global__ void __launch_bounds__(256) fb_passD_kernel(NuthDev* nd, const unsigned* __restrict__ ghist) {
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= NB || nd->fast_fallback) return;
+    if (nd->bin_count[b] == 0) return;
+    const unsigned* slots = ghist + FB_SLOT_OFF;
+    const unsigned* slotn = ghist + FB_SLOTN_OFF;
+    const unsigned f0 = nd->fb_cell[0][b], f1 = nd->fb_cell[1][b];
+    float val[2];
+    bool bad = false;
+    for (int r = 0; r < 2; ++r) {
+        const int sl = (r == 1 && f1 != f0) ? 1 : 0;
+        const unsigned m = slotn[b * 2 + sl];
+        const unsigned k = nd->fa_rank[r][b];
+        if (m > FB_SLOT || k >= m) { bad = true; val[r] = 0.f; continue; }
+        const unsigned* q = slots + (b * 2 + sl) * FB_SLOT;
+        unsigned found = 0;
+        bool have = false;
+        for (unsigned i = lane; i < m; i += 32) {
+            const unsigned e = q[i];
+            unsigned rank = 0;
+            for (unsigned j = 0; j < m; ++j) { const unsigned o = q[j]; rank += (o < e) || (o == e && j < i); }
+            if (rank == k) { found = e; have = true; }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, have);
+        if (!bal) { bad = true; val[r] = 0.f; continue; }
+        found = __shfl_sync(0xffffffffu, found, __ffs(bal) - 1);
+        val[r] = dcr_key2f(found);
+    }
+    if (lane == 0) {
+        if (bad) nd->fast_fallback = 1;
+        else nd->bin_med[b] = (val[0] + val[1]) / 2.0f;
+    }
+}
+
 struct NuthWs {
     float* y;
     unsigned short* bin;
     NuthPartial* part;
     unsigned* ghist;
     NuthDev* nd;
+    unsigned long long* cand;   // fast bin path: (key << 32 | bin << 16 | fine cell) of the elements in the median coarse cells
+    unsigned cand_cap;
 };
+static unsigned nuth_cand_cap(long long n) {
+    long long c = n / 8;
+    if (c < 65536) c = 65536;
+    if (c > 0x7fffffffLL) c = 0x7fffffffLL;
+    return (unsigned)c;
+}
 static size_t nuth_ws_bytes(long long n, int grid) {
     return dcr_al256(n * sizeof(float)) + dcr_al256(n * sizeof(unsigned short)) + dcr_al256(grid * sizeof(NuthPartial)) +
-           dcr_al256((size_t)2 * NB * 2048 * sizeof(unsigned)) + dcr_al256(sizeof(NuthDev));
+           dcr_al256((size_t)2 * NB * 2048 * sizeof(unsigned)) + dcr_al256(sizeof(NuthDev)) +
+           dcr_al256((size_t)nuth_cand_cap(n) * sizeof(unsigned long long));
 }
 static int nuth_ws_carve(DcrBump& ws, long long n, int grid, NuthWs* w) {
     w->y = ws.take<float>(n);
@@ -249,17 +468,16 @@ static int nuth_ws_carve(DcrBump& ws, long long n, int grid, NuthWs* w) {
     w->part = ws.take<NuthPartial>(grid);
     w->ghist = ws.take<unsigned>((size_t)2 * NB * 2048);
     w->nd = ws.take<NuthDev>(1);
-    if (!w->y || !w->bin || !w->part || !w->ghist || !w->nd) { dcr_set_error("workspace too small"); return -1; }
+    w->cand_cap = nuth_cand_cap(n);
+    w->cand = ws.take<unsigned long long>(w->cand_cap);
+    if (!w->y || !w->bin || !w->part || !w->ghist || !w->nd || !w->cand) { dcr_set_error("workspace too small"); return -1; }
     return 0;
 }
 
-static int nuth_enqueue(const float* dh, const float* slope, const float* aspect, const unsigned char* m, unsigned reject,
-                        long long n, int remove_outliers, const NuthWs& w, int grid, cudaStream_t s,
-                        cudaEvent_t after_prepare = nullptr) {
+// radix bins (3 passes of global-atomic histograms): the exact fallback of the fast path
+static int nuth_bins_radix_enqueue(long long n, const NuthWs& w, int grid, cudaStream_t s) {
     DCR_CUDA_OK(cudaMemsetAsync(w.ghist, 0, (size_t)2 * NB * 2048 * sizeof(unsigned), s));
-    nuth_prepare_kernel<<<grid, 256, 0, s>>>(dh, slope, aspect, m, reject, n, w.y, w.bin, w.part);
-    nuth_moments_final_kernel<<<1, 256, 0, s>>>(w.part, grid, remove_outliers, w.nd);
-    if (after_prepare) DCR_CUDA_OK(cudaEventRecord(after_prepare, s));
+    DCR_CUDA_OK(cudaMemsetAsync(w.nd->bin_count, 0, sizeof(unsigned long long) * NB, s));
     bin_hist_kernel<0><<<grid, 256, 0, s>>>(w.y, w.bin, n, w.nd, w.ghist);
     bin_find_kernel<0><<<NB, 256, 0, s>>>(w.nd, w.ghist);
     bin_hist_kernel<1><<<grid, 256, 0, s>>>(w.y, w.bin, n, w.nd, w.ghist);
@@ -267,8 +485,40 @@ static int nuth_enqueue(const float* dh, const float* slope, const float* aspect
     bin_hist_kernel<2><<<grid, 256, 0, s>>>(w.y, w.bin, n, w.nd, w.ghist);
     bin_find_kernel<2><<<NB, 256, 0, s>>>(w.nd, w.ghist);
     nuth_count_final_kernel<<<1, 32, 0, s>>>(w.nd);
-    DCR_LAUNCH_OK("nuth kernels");
+    DCR_LAUNCH_OK("radix bin kernels");
     return 0;
+}
+
+static int nuth_bins_fast_enqueue(long long n, const NuthWs& w, cudaStream_t s) {
+    static bool attr_set = false;
+    const size_t smemA = (size_t)NB * FB_COARSE * sizeof(unsigned);
+    if (!attr_set) {
+        DCR_CUDA_OK(cudaFuncSetAttribute(fb_passA_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+        attr_set = true;
+    }
+    const int nsm = dcr_num_sms();
+    DCR_CUDA_OK(cudaMemsetAsync(w.ghist, 0, (size_t)FB_WORDS * sizeof(unsigned), s));
+    fb_init_kernel<<<1, 32, 0, s>>>(w.nd);
+    fb_passA_kernel<<<nsm * 2, 512, smemA, s>>>(w.y, w.bin, n, w.nd, w.ghist);
+    fb_findA_kernel<<<(NB + 127) / 128, 128, 0, s>>>(w.nd, w.ghist);
+    fb_passB_kernel<<<nsm * 16, 256, 0, s>>>(w.y, w.bin, n, w.nd, w.ghist, w.cand, w.cand_cap);  // small CTAs: the 4 % candidates of a CTA must fit its staging buffer
+    fb_findB_kernel<<<(NB + 7) / 8, 256, 0, s>>>(w.nd, w.ghist, w.cand_cap);
+    fb_passC_kernel<<<nsm * 2, 256, 0, s>>>(w.nd, w.cand, w.ghist);
+    fb_passD_kernel<<<(NB + 7) / 8, 256, 0, s>>>(w.nd, w.ghist);
+    nuth_count_final_kernel<<<1, 32, 0, s>>>(w.nd);
+    DCR_LAUNCH_OK("fast bin kernels");
+    return 0;
+}
+
+static int nuth_enqueue(const float* dh, const float* slope, const float* aspect, const unsigned char* m, unsigned reject,
+                        long long n, int remove_outliers, const NuthWs& w, int grid, cudaStream_t s,
+                        cudaEvent_t after_prepare = nullptr, int fast_bins = 1) {
+    nuth_prepare_kernel<<<grid, 256, 0, s>>>(dh, slope, aspect, m, reject, n, w.y, w.bin, w.part);
+    nuth_moments_final_kernel<<<1, 256, 0, s>>>(w.part, grid, remove_outliers, w.nd);
+    if (after_prepare) DCR_CUDA_OK(cudaEventRecord(after_prepare, s));
+    DCR_LAUNCH_OK("nuth prepare kernels");
+    if (fast_bins) return nuth_bins_fast_enqueue(n, w, s);
+    return nuth_bins_radix_enqueue(n, w, grid, s);
 }
 
 static void nuth_dev_to_stats(const NuthDev& d, dcr_nuth_stats* o) {
@@ -296,6 +546,11 @@ extern "C" int dcr_nuth_bin_stats(const float* dh, const float* slope, const flo
     static thread_local NuthDev host;
     DCR_CUDA_OK(cudaMemcpyAsync(&host, w.nd, sizeof(NuthDev), cudaMemcpyDeviceToHost, s));
     DCR_CUDA_OK(cudaStreamSynchronize(s));
+    if (host.fast_fallback) {  // heavy ties / degenerate range: exact 3-pass radix bins
+        if ((rc = nuth_bins_radix_enqueue(n, w, grid, s))) return rc;
+        DCR_CUDA_OK(cudaMemcpyAsync(&host, w.nd, sizeof(NuthDev), cudaMemcpyDeviceToHost, s));
+        DCR_CUDA_OK(cudaStreamSynchronize(s));
+    }
     nuth_dev_to_stats(host, out);
     return 0;
 }
@@ -522,7 +777,7 @@ static int iter_select(const SelView& v, int k, const IterWs& w, long long n, in
 }
 
 static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, int use_bsel, const IterWs& w, int grid,
-                             cudaStream_t s, cudaEvent_t* ev) {
+                             cudaStream_t s, cudaEvent_t* ev, int fast_bins) {
     const long long n = (long long)front->h * front->w;
     const long long nch = (n + MU_CHUNK - 1) / MU_CHUNK;
     IterDev* d = w.d;
@@ -570,7 +825,7 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
     }
     STAGE_MARK(4);
     if ((rc = nuth_enqueue(front->dh, front->slope, front->aspect, front->maskbits, DCR_M_DIFF | DCR_M_ASPECT, n,
-                           remove_outliers, w.nw, grid, s, ev ? ev[5] : nullptr)))
+                           remove_outliers, w.nw, grid, s, ev ? ev[5] : nullptr, fast_bins)))
         return rc;
     DCR_LAUNCH_OK("iteration kernels");
     STAGE_MARK(6);
@@ -662,11 +917,21 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_it
     if (!hd) DCR_CUDA_OK(cudaHostAlloc((void**)&hd, sizeof(IterDev), cudaHostAllocDefault));
     int engine_used = (flags & DCR_ITER_RADIX_ONLY) ? 0 : 1;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        int rc = iteration_enqueue(front, remove_outliers, engine_used, w, grid, s, prof ? ev : nullptr);
+        int rc = iteration_enqueue(front, remove_outliers, engine_used, w, grid, s, prof ? ev : nullptr,
+                                   (flags & DCR_ITER_RADIX_ONLY) ? 0 : 1);
         if (rc) return rc;
         DCR_CUDA_OK(cudaMemcpyAsync(hd, d, sizeof(IterDev), cudaMemcpyDeviceToHost, s));
         if (prof) DCR_CUDA_OK(cudaEventRecord(ev[7], s));
         DCR_CUDA_OK(cudaStreamSynchronize(s));
+        if (hd->nuth.fast_fallback && getenv("DCR_DEBUG"))
+            fprintf(stderr, "[dcr] fast bin path declined: ncand=%u scale=%g rmin=%g rmax=%g\n", hd->nuth.fast_ncand,
+                    hd->nuth.fast_scale, hd->nuth.rmin, hd->nuth.rmax);
+        if (hd->nuth.fast_fallback) {
+            // fast bin path declined (heavy ties / degenerate 3-sigma range): exact 3-pass radix bins, same inputs
+            if ((rc = nuth_bins_radix_enqueue(n, w.nw, grid, s))) return rc;
+            DCR_CUDA_OK(cudaMemcpyAsync(hd, d, sizeof(IterDev), cudaMemcpyDeviceToHost, s));
+            DCR_CUDA_OK(cudaStreamSynchronize(s));
+        }
         if (!engine_used) break;
         // the one-pass selects verify themselves on the device; if any bracket missed (or hit heavy ties)
         // the whole iteration is redone with the 3-pass radix select (exact by construction)

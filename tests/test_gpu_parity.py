@@ -320,6 +320,31 @@ def test_iteration_uses_fast_selects_and_matches_radix(cuda):
     for f in ("med1", "nmad1", "mad_lo", "mad_hi", "dz_med", "med_dh", "med_slope", "count_mad", "count_final", "dx", "dy", "dz"):
         assert getattr(r1, f) == getattr(r2, f), f
     assert list(r1.nuth.bin_count) == list(r2.nuth.bin_count)
+    # fast two-pass bin medians == 3-pass radix bin medians, bit for bit
+    assert np.array_equal(np.array(r1.nuth.bin_med[:]), np.array(r2.nuth.bin_med[:]), equal_nan=True)
+    assert r1.nuth.n_final == r2.nuth.n_final
+
+
+def test_bin_stats_fast_path_fallback_on_ties(cuda):
+    """Heavily tied y values (quantised dh, constant slope) force the fast bin path to decline; the radix bins
+    take over and the result still equals the oracle's binned_statistic."""
+    from demcoreg_b200 import engine, _lib
+    from oracle import pygeotools_restated as pg
+    rng = np.random.default_rng(4)
+    n = 400_000
+    dh = np.round(rng.standard_normal(n) * 2).astype(np.float32)       # ~10 distinct values
+    slope = np.full(n, 10.0, dtype=np.float32)
+    aspect = (rng.random(n) * 360).astype(np.float32)
+    bits = np.zeros(n, dtype=np.uint8)
+    st = engine.nuth_bin_stats(cuda.from_numpy(dh).cuda(), cuda.from_numpy(slope).cuda(), cuda.from_numpy(aspect).cuda(),
+                               cuda.from_numpy(bits).cuda())
+    y = (dh / np.tan(np.deg2rad(slope))).astype(np.float32)
+    u, sg = y.mean(), y.std()
+    keep = (y >= u - 3 * sg) & (y <= u + 3 * sg)
+    cnt, _, _ = pg.bin_stats(aspect[keep], y[keep], stat='count', nbins=360, bin_range=(0., 360.))
+    med, _, _ = pg.bin_stats(aspect[keep], y[keep], stat='median', nbins=360, bin_range=(0., 360.))
+    assert np.array_equal(np.array(st.bin_count[:]), cnt.filled(0).astype(np.int64))
+    np.testing.assert_allclose(np.array(st.bin_med[:]), med.filled(np.nan), rtol=1e-5, equal_nan=True)
 
 
 def _ncc_pair(n=320, p=6, masked=False, seed=5):
