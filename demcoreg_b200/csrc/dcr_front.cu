@@ -251,33 +251,58 @@ __device__ __noinline__ bool horn(float w0, float w1, float w2, float w3, float 
     return true;
 }
 
+// atan(t) for 0 <= t <= 1: odd minimax polynomial (<= 1 ulp), t + t*(t^2*P(t^2))
+__device__ __forceinline__ float atan01(float t) {
+    const float z = t * t;
+    float p = 0.0024500289000570774f;
+    p = fmaf(p, z, -0.014396979473531246f);
+    p = fmaf(p, z, 0.039849750697612762f);
+    p = fmaf(p, z, -0.072529748082160950f);
+    p = fmaf(p, z, 0.10518480092287064f);
+    p = fmaf(p, z, -0.14171802997589111f);
+    p = fmaf(p, z, 0.19988775253295898f);
+    p = fmaf(p, z, -0.33332940936088562f);
+    return fmaf(t, z * p, t);
+}
+
 // FP32 fast path of the Horn slope/aspect with certified guard bands (DESIGN.md "front kernel"):
 // the 3x3 sums are the exact float32 sums of GDAL; atan/atan2 are evaluated in FP32 (<= ~4 ulp), and every
 // pixel whose result could change a mask-deciding quantity -- slope within 2e-6 (relative) of a slope
-// limit, aspect within 2e-4 degrees of an integer degree (the 1-degree bin edges) -- is recomputed with
+// limit, aspect within 3e-4 degrees of an integer degree (the 1-degree bin edges) -- is recomputed with
 // the FP64 formulation above.  Returns false when any input is NaN; *exact = true -> caller must call horn().
 __device__ __forceinline__ bool horn_fast(float w0, float w1, float w2, float w3, float w4, float w5, float w6,
                                           float w7, float w8, float inv8ew, float inv8ns, float slope_lo,
                                           float slope_hi, float* slope, float* aspect, bool* exact) {
-    const float probe = ((w0 + w1) + (w2 + w3)) + ((w4 + w5) + (w6 + w7)) + w8;
-    if (isnan(probe)) return false;
     const float a = (w0 + w3 + w3 + w6);
     const float b = (w2 + w5 + w5 + w8);
     const float c = (w6 + w7 + w7 + w8);
     const float d = (w0 + w1 + w1 + w2);
     const float dxs = a - b;  // slope numerator; aspect uses b - a = -dxs exactly
     const float dyf = c - d;
+    // any NaN (nodata) among the 8 neighbours poisons dxs or dyf; the centre is tested separately
+    if (isnan(dxs + dyf) || isnan(w4)) return false;
     const float gx = dxs * inv8ew, gy = dyf * inv8ns;
-    const float s = atanf(sqrtf(gx * gx + gy * gy)) * 57.29577951308232f;
+    const float g = sqrtf(gx * gx + gy * gy);
+    const bool big = g > 1.0f;
+    float sa = atan01(big ? __fdividef(1.0f, g) : g);
+    if (big) sa = 1.5707963267948966f - sa;
+    const float s = sa * 57.29577951308232f;
     bool ex = (fabsf(s - slope_lo) <= 2e-6f * slope_lo) || (fabsf(s - slope_hi) <= 2e-6f * slope_hi);
     *slope = s;
     if (dxs == 0.0f && dyf == 0.0f) {
         *aspect = __int_as_float(0x7fc00000);
     } else {
-        float af = atan2f(dyf, dxs) * 57.29577951308232f;  // atan2(dy, -dx_aspect), dx_aspect = -dxs
+        // atan2(dy, -dx_aspect) with dx_aspect = -dxs, i.e. atan2(dyf, dxs), built from the [0,1] polynomial
+        const float ax = fabsf(dxs), ay = fabsf(dyf);
+        const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+        float a = atan01(__fdividef(mn, mx));
+        if (ay > ax) a = 1.5707963267948966f - a;
+        if (dxs < 0.0f) a = 3.141592653589793f - a;
+        a = copysignf(a, dyf);
+        float af = a * 57.29577951308232f;
         af = (af > 90.0f) ? (450.0f - af) : (90.0f - af);
         const float fr = af - floorf(af);
-        ex = ex || (fr < 2e-4f) || (fr > 1.0f - 2e-4f) || !(af >= 0.0f) || (af >= 360.0f);
+        ex = ex || (fr < 3e-4f) || (fr > 1.0f - 3e-4f) || !(af >= 0.0f) || (af >= 360.0f) || isinf(mx);
         *aspect = af;
     }
     *exact = ex;
@@ -402,7 +427,7 @@ struct FrontParams {
     int smask_row0;
     double ewres, nsres;
     float inv8ew, inv8ns;
-    double ref_gm_ndv, ref_gm_tol, src_gm_ndv, src_gm_tol;  // ds_getma masked_values(|x-ndv| <= tol)
+    float ref_gm_lo, ref_gm_hi, src_gm_lo, src_gm_hi;  // ds_getma masked_values: masked iff lo <= x <= hi (float32 bounds of |x-ndv| <= tol)
     float ref_fill, src_fill;                               // value written to ref_w/src_w for invalid pixels
     float max_dz;
     int use_max_dz;
@@ -435,6 +460,50 @@ __device__ __forceinline__ float warp_px_tile(const float* t, int r0, int c0, co
     return (float)o;
 }
 
+// Stage an R x C footprint whose top-left source pixel is (r_base, c_base) into shared memory: one warp per
+// tile row, two rows (10 loads) in flight per lane, column predicates hoisted out of the row loop.
+template <int R, int C>
+__device__ __forceinline__ void stage_tile(const float* __restrict__ src, const DevGeom& g, int r_base, int c_base,
+                                           float* __restrict__ tile, int tid) {
+    const int lane = tid & 31, wrp = tid >> 5;
+    const float qnan = __int_as_float(0x7fc00000);
+    constexpr int NQ = (C + 31) / 32;
+    unsigned cmask = 0;   // bit q: column chunk q of this lane is inside the tile and the raster
+    unsigned smask = 0;   // bit q: inside the tile (needs a store)
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const int cc = q * 32 + lane, gc = c_base + cc;
+        if (cc < C) {
+            smask |= 1u << q;
+            if (gc >= 0 && gc < g.ws) cmask |= 1u << q;
+        }
+    }
+    const float* colp = src + (c_base + lane);
+    const bool has_ndv = g.has_ndv != 0;
+    const float ndv = g.ndv;
+    for (int r = wrp; r < R; r += 16) {
+        float v[2][NQ];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int rr = r + 8 * u, gr = r_base + rr;
+            const bool rok = rr < R && gr >= g.row0 && gr < g.row1;
+            const float* rowp = colp + (long long)(gr - g.row0) * g.stride;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) v[u][q] = (rok && (cmask >> q & 1u)) ? __ldg(rowp + q * 32) : qnan;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int rr = r + 8 * u;
+            if (rr < R) {
+                float* trow = tile + rr * C + lane;
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+                    if (smask >> q & 1u) trow[q * 32] = (has_ndv && v[u][q] == ndv) ? qnan : v[u][q];
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ FrontParams p) {
     extern __shared__ float smem[];
     float* s_src = smem;                                  // F_SRC_R x F_SRC_C
@@ -446,70 +515,9 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
     const int tid = threadIdx.x;
     if (tid < 3) s_cnt[tid] = 0ull;
 
-    // ---- stage the two source footprints: one warp per tile row, all loads of a row pair issued before
-    //      their first use (memory-level parallelism), nodata / out-of-bounds -> NaN
-    {
-        const int lane = tid & 31, wrp = tid >> 5;
-        const float qnan = __int_as_float(0x7fc00000);
-        {
-            const int r_base = ti0 - 2 + p.sg.iy0, c_base = tj0 - 2 + p.sg.ix0;
-            for (int r = wrp; r < F_SRC_R; r += 16) {
-                float v[2][5];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int rr = r + 8 * u, gr = r_base + rr;
-                    const bool rok = rr < F_SRC_R && gr >= p.sg.row0 && gr < p.sg.row1;
-                    const float* rowp = p.src + (long long)(gr - p.sg.row0) * p.sg.stride;
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) {
-                        const int cc = q * 32 + lane, gc = c_base + cc;
-                        v[u][q] = qnan;
-                        if (rok && cc < F_SRC_C && gc >= 0 && gc < p.sg.ws) v[u][q] = __ldg(rowp + gc);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int rr = r + 8 * u;
-                    if (rr < F_SRC_R) {
-#pragma unroll
-                        for (int q = 0; q < 5; ++q) {
-                            const int cc = q * 32 + lane;
-                            if (cc < F_SRC_C) s_src[rr * F_SRC_C + cc] = (p.sg.has_ndv && v[u][q] == p.sg.ndv) ? qnan : v[u][q];
-                        }
-                    }
-                }
-            }
-        }
-        {
-            const int r_base = ti0 - 1 + p.rg.iy0, c_base = tj0 - 1 + p.rg.ix0;
-            for (int r = wrp; r < F_REF_R; r += 16) {
-                float v[2][5];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int rr = r + 8 * u, gr = r_base + rr;
-                    const bool rok = rr < F_REF_R && gr >= p.rg.row0 && gr < p.rg.row1;
-                    const float* rowp = p.ref + (long long)(gr - p.rg.row0) * p.rg.stride;
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) {
-                        const int cc = q * 32 + lane, gc = c_base + cc;
-                        v[u][q] = qnan;
-                        if (rok && cc < F_REF_C && gc >= 0 && gc < p.rg.ws) v[u][q] = __ldg(rowp + gc);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int rr = r + 8 * u;
-                    if (rr < F_REF_R) {
-#pragma unroll
-                        for (int q = 0; q < 5; ++q) {
-                            const int cc = q * 32 + lane;
-                            if (cc < F_REF_C) s_ref[rr * F_REF_C + cc] = (p.rg.has_ndv && v[u][q] == p.rg.ndv) ? qnan : v[u][q];
-                        }
-                    }
-                }
-            }
-        }
-    }
+    // ---- stage the two source footprints (nodata / out-of-bounds -> NaN)
+    stage_tile<F_SRC_R, F_SRC_C>(p.src, p.sg, ti0 - 2 + p.sg.iy0, tj0 - 2 + p.sg.ix0, s_src, tid);
+    stage_tile<F_REF_R, F_REF_C>(p.ref, p.rg, ti0 - 1 + p.rg.iy0, tj0 - 1 + p.rg.ix0, s_ref, tid);
     __syncthreads();
 
     // ---- halo ring of the warped-src tile (needed by the 3x3 stencil only)
@@ -565,26 +573,24 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
             const double ro = ypass(p.rg.wy, xr0, xr1, xr2, xr3);
             xs0 = xs1; xs1 = xs2; xs2 = xs3;
             xr0 = xr1; xr1 = xr2; xr2 = xr3;
-            float sv, rv;
-            {
-                const float* t = s_src + (r + 2) * F_SRC_C + (c + 2);  // UL pixel of the 2x2
-                const float nearest = t[s_near];
-                if (isnan(so)) sv = bilinear_fallback(t[0], t[1], t[F_SRC_C + 1], t[F_SRC_C], nearest, p.sg.fx, p.sg.fy);
-                else sv = isnan(nearest) ? nearest : (float)so;
-            }
-            {
-                const float* t = s_ref + (r + 1) * F_REF_C + (c + 1);
-                const float nearest = t[r_near];
-                if (isnan(ro)) rv = bilinear_fallback(t[0], t[1], t[F_REF_C + 1], t[F_REF_C], nearest, p.rg.fx, p.rg.fy);
-                else rv = isnan(nearest) ? nearest : (float)ro;
+            // common case: every tap valid -> the cubic value; anything else (nodata / edge) takes ONE rare branch
+            const float* ts = s_src + (r + 2) * F_SRC_C + (c + 2);  // UL pixel of the 2x2
+            const float* tr = s_ref + (r + 1) * F_REF_C + (c + 1);
+            float sv = (float)so, rv = (float)ro;
+            if (isnan(sv + rv)) {
+                const float ns = ts[s_near], nr = tr[r_near];
+                sv = isnan(so) ? bilinear_fallback(ts[0], ts[1], ts[F_SRC_C + 1], ts[F_SRC_C], ns, p.sg.fx, p.sg.fy)
+                               : (isnan(ns) ? ns : sv);
+                rv = isnan(ro) ? bilinear_fallback(tr[0], tr[1], tr[F_REF_C + 1], tr[F_REF_C], nr, p.rg.fx, p.rg.fy)
+                               : (isnan(nr) ? nr : rv);
             }
             const bool inside = (i < p.row_end) && (j < p.w);
             // rows past this launch's band still feed the 3x3 stencil of its last row (row-band mode)
             if (!((i < p.h) && (j < p.w))) sv = __int_as_float(0x7fc00000);
             s_sw[(r + 1) * F_SW_C + (c + 1)] = sv;
             // ds_getma masks: |x - ndv| <= tol in double (numpy masked_values)
-            const bool sm = isnan(sv) || fabs((double)sv - p.src_gm_ndv) <= p.src_gm_tol;
-            const bool rm = isnan(rv) || fabs((double)rv - p.ref_gm_ndv) <= p.ref_gm_tol;
+            const bool sm = !(sv < p.src_gm_lo || sv > p.src_gm_hi);  // NaN -> masked
+            const bool rm = !(rv < p.ref_gm_lo || rv > p.ref_gm_hi);
             bool base_ok = inside && !sm && !rm;
             if (base_ok && p.smask) {
                 const int mi = i + p.smask_ny0, mj = j + p.smask_nx0;
@@ -660,6 +666,17 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
     if (tid < 3 && p.counters) atomicAdd(&p.counters[tid], s_cnt[tid]);
 }
 
+// float32 interval equivalent to numpy masked_values' |x - ndv| <= 1e-8 + 1e-5*|ndv| evaluated in float64
+static void gm_bounds(double ndv, float* lo, float* hi) {
+    const double tol = 1e-8 + 1e-5 * fabs(ndv);
+    const double dl = ndv - tol, dh = ndv + tol;
+    float fl = (float)dl, fh = (float)dh;
+    if ((double)fl < dl) fl = nextafterf(fl, INFINITY);
+    if ((double)fh > dh) fh = nextafterf(fh, -INFINITY);
+    *lo = fl;
+    *hi = fh;
+}
+
 int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cudaStream_t stream) {
     DCR_ARG(a, "null args");
     DCR_ARG(a->ref && a->src && a->dh && a->slope && a->aspect && a->maskbits, "null raster pointer");
@@ -685,10 +702,8 @@ int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cuda
     // memwarp_multi: identity -> dataset unchanged (own ndv); resampled -> dst_ndv
     const double rn = a->ref_geom.identity ? a->ref_desc.ndv : a->dst_ndv;
     const double sn = a->src_geom.identity ? a->src_desc.ndv : a->dst_ndv;
-    p.ref_gm_ndv = rn;
-    p.ref_gm_tol = 1e-8 + 1e-5 * fabs(rn);
-    p.src_gm_ndv = sn;
-    p.src_gm_tol = 1e-8 + 1e-5 * fabs(sn);
+    gm_bounds(rn, &p.ref_gm_lo, &p.ref_gm_hi);
+    gm_bounds(sn, &p.src_gm_lo, &p.src_gm_hi);
     p.ref_fill = (float)rn;
     p.src_fill = (float)sn;
     p.max_dz = a->max_dz;
