@@ -424,7 +424,7 @@ struct FrontParams {
     int smask_h, smask_w, smask_nx0, smask_ny0;
     int h, w;
     int row_begin, row_end;  // output rows computed by this launch (row-band mode; whole grid otherwise)
-    int smask_row0;
+    int smask_row0, smask_row1;  // rows of the static mask held in memory
     double ewres, nsres;
     float inv8ew, inv8ns;
     float ref_gm_lo, ref_gm_hi, src_gm_lo, src_gm_hi;  // ds_getma masked_values: masked iff lo <= x <= hi (float32 bounds of |x-ndv| <= tol)
@@ -510,6 +510,7 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
     float* s_ref = s_src + F_SRC_R * F_SRC_C;             // F_REF_R x F_REF_C
     float* s_sw = s_ref + F_REF_R * F_REF_C;              // F_SW_R x F_SW_C : warped src (NaN = nodata)
     __shared__ unsigned long long s_cnt[3];
+    __shared__ unsigned char s_mask[F_TH * F_TW];       // static (stable-surface) mask of the tile, 1 = masked
 
     const int tj0 = blockIdx.x * F_TW, ti0 = p.row_begin + blockIdx.y * F_TH;
     const int tid = threadIdx.x;
@@ -518,6 +519,21 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
     // ---- stage the two source footprints (nodata / out-of-bounds -> NaN)
     stage_tile<F_SRC_R, F_SRC_C>(p.src, p.sg, ti0 - 2 + p.sg.iy0, tj0 - 2 + p.sg.ix0, s_src, tid);
     stage_tile<F_REF_R, F_REF_C>(p.ref, p.rg, ti0 - 1 + p.rg.iy0, tj0 - 1 + p.rg.ix0, s_ref, tid);
+    if (p.smask) {
+        // nearest-neighbour sample of the world-fixed mask; all 16 byte loads of a thread are issued before their
+        // first use (a dependent load per pixel inside the main pass cost ~600 cycles of latency per row)
+        unsigned char mv[(F_TH * F_TW) / 256];
+#pragma unroll
+        for (int k = 0; k < (F_TH * F_TW) / 256; ++k) {
+            const int e = k * 256 + tid;
+            const int mi = ti0 + (e >> 7) + p.smask_ny0, mj = tj0 + (e & (F_TW - 1)) + p.smask_nx0;
+            mv[k] = 1;
+            if (mi >= p.smask_row0 && mj >= 0 && mi < p.smask_row1 && mj < p.smask_w)
+                mv[k] = __ldg(p.smask + (long long)(mi - p.smask_row0) * p.smask_stride + mj);
+        }
+#pragma unroll
+        for (int k = 0; k < (F_TH * F_TW) / 256; ++k) s_mask[k * 256 + tid] = mv[k];
+    }
     __syncthreads();
 
     // ---- halo ring of the warped-src tile (needed by the 3x3 stencil only)
@@ -592,11 +608,7 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
             const bool sm = !(sv < p.src_gm_lo || sv > p.src_gm_hi);  // NaN -> masked
             const bool rm = !(rv < p.ref_gm_lo || rv > p.ref_gm_hi);
             bool base_ok = inside && !sm && !rm;
-            if (base_ok && p.smask) {
-                const int mi = i + p.smask_ny0, mj = j + p.smask_nx0;
-                if (mi < 0 || mj < 0 || mi >= p.smask_h || mj >= p.smask_w) base_ok = false;
-                else if (__ldg(p.smask + (long long)(mi - p.smask_row0) * p.smask_stride + mj)) base_ok = false;
-            }
+            if (p.smask && s_mask[r * F_TW + c]) base_ok = false;
             const float dh = base_ok ? (sv - rv) : 0.0f;
             if (base_ok) {
                 valid_bits |= (1u << rr);
@@ -730,6 +742,7 @@ int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cuda
     if (a->src_nrows > 0) { p.sg.row0 = a->src_row0; p.sg.row1 = a->src_row0 + a->src_nrows; }
     DCR_ARG(p.rg.row0 >= 0 && p.rg.row1 <= p.rg.hs && p.sg.row0 >= 0 && p.sg.row1 <= p.sg.hs, "stored rows outside the raster");
     p.smask_row0 = a->smask_nrows > 0 ? a->smask_row0 : 0;
+    p.smask_row1 = a->smask_nrows > 0 ? a->smask_row0 + a->smask_nrows : a->smask_h;
     {
         // every source row the launch touches must be in memory: 4 taps (+1 row each side for the Horn halo)
         const int lo = p.row_begin - 1, hi = p.row_end + 1;  // warped-src rows needed (clipped below)
