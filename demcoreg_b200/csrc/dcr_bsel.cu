@@ -41,7 +41,7 @@ __device__ __forceinline__ bool bsel_key(const SelView& v, float center, float x
     if (mb & v.reject) return false;
     if (v.transform == 1) x = fabsf(x - center);
     if (isnan(x)) return false;
-    *key = dcr_f2key(x);
+    *key = dcr_f2key(x + 0.0f);  // -0 -> +0: float comparisons (main pass) and key order must agree
     return true;
 }
 
@@ -61,22 +61,36 @@ __global__ void __launch_bounds__(1024) bsel_sample_kernel(const SelView v, doub
     __syncthreads();
     unsigned nv = 0;
     const bool all = n <= BS_S;  // small input: the "sample" is the whole array and the answer is exact
-    for (int k = threadIdx.x; k < BS_S; k += 1024) {
-        unsigned key = 0xFFFFFFFFu;
-        // stratified positions with a hashed offset inside each stratum: a plain stride of n/S aliases with the
-        // raster width (8192 x 8192: every sample would sit in column 0, where the Horn border is masked)
-        long long i = k;
-        if (!all) {
-            const unsigned long long lo = ((unsigned long long)k * (unsigned long long)n) / BS_S;
-            const unsigned long long hi = ((unsigned long long)(k + 1) * (unsigned long long)n) / BS_S;
-            const unsigned long long hsh = ((unsigned long long)k * 0x9E3779B97F4A7C15ull) >> 20;
-            i = (long long)(lo + hsh % (hi - lo));
+    {
+        // all 8 (value, mask) gathers of a thread are issued before their first use: the positions are scattered
+        // over the whole array (TLB + DRAM latency ~2 us each), so they must overlap
+        float xv[BS_S / 1024];
+        unsigned mv[BS_S / 1024];
+#pragma unroll
+        for (int q = 0; q < BS_S / 1024; ++q) {
+            const int k = q * 1024 + threadIdx.x;
+            // stratified positions with a hashed offset inside each stratum: a plain stride of n/S aliases with the
+            // raster width (8192 x 8192: every sample would sit in column 0, where the Horn border is masked)
+            long long i = k;
+            if (!all) {
+                const unsigned long long lo = ((unsigned long long)k * (unsigned long long)n) / BS_S;
+                const unsigned long long hi = ((unsigned long long)(k + 1) * (unsigned long long)n) / BS_S;
+                const unsigned long long hsh = ((unsigned long long)k * 0x9E3779B97F4A7C15ull) >> 20;
+                i = (long long)(lo + hsh % (hi - lo));
+            }
+            xv[q] = 0.f;
+            mv[q] = 0xFFFFFFFFu;
+            if (i < n) {
+                xv[q] = v.x[i];
+                mv[q] = v.m ? (unsigned)v.m[i] : 0u;
+            }
         }
-        if (i < n) {
-            unsigned kk;
-            if (bsel_key(v, center, v.x[i], v.m ? (unsigned)v.m[i] : 0u, &kk)) { key = kk; ++nv; }
+#pragma unroll
+        for (int q = 0; q < BS_S / 1024; ++q) {
+            unsigned key = 0xFFFFFFFFu, kk;
+            if (mv[q] <= 0xffu && bsel_key(v, center, xv[q], mv[q], &kk)) { key = kk; ++nv; }
+            s[q * 1024 + threadIdx.x] = key;
         }
-        s[k] = key;
     }
     nv = __reduce_add_sync(0xffffffffu, nv);
     if ((threadIdx.x & 31) == 0 && nv) atomicAdd(&s_valid, nv);
@@ -102,7 +116,7 @@ __global__ void __launch_bounds__(1024) bsel_sample_kernel(const SelView v, doub
                 st->result = dcr_lerp32(st->v_lo, st->v_hi, g);
             }
         } else {
-            unsigned klo = 0u, khi = 0xFFFFFFFEu;
+            unsigned klo = dcr_f2key(-INFINITY), khi = dcr_f2key(INFINITY);
             if (m > 0) {
                 const double f = q_percent / 100.0;
                 const double r = f * (double)(m - 1);
@@ -112,6 +126,7 @@ __global__ void __launch_bounds__(1024) bsel_sample_kernel(const SelView v, doub
                 if (b < m) khi = s[b];
             }
             st->klo = klo; st->khi = khi;
+            st->flo = dcr_key2f(klo); st->fhi = dcr_key2f(khi);
             // linear bins of the bracket: (key - klo) >> shift < 2048
             const unsigned long long span = (unsigned long long)khi - klo + 1ull;
             int shift = 0;
@@ -134,30 +149,31 @@ __global__ void __launch_bounds__(BS_THREADS) bsel_main_kernel(const SelView v, 
     __syncthreads();
     const long long n = v.n_ptr ? *v.n_ptr : v.n;
     const float center = v.center_ptr ? *v.center_ptr : v.center_imm;
-    const unsigned klo = st->klo, khi = st->khi;
+    const unsigned klo = st->klo;
     const int shift = st->shift;
     const unsigned reject = v.m ? v.reject : 0u;
     const int transform = v.transform;
     const int lane = threadIdx.x & 31;
-    unsigned below = 0, total = 0;
-    unsigned keys[16];
+    const float flo = st->flo, fhi = st->fhi;
+    unsigned below = 0, total = 0;   // total accumulates below + above + in-bracket (NaNs fail every comparison)
+    float cv[16];
     unsigned flags = 0;
     dcr_stream1_groups(v.x, v.m, n,
         [&](float x, unsigned mb, long long, int slot) {
-            if (mb <= 0xffu && !(mb & reject)) {
-                if (transform == 1) x = fabsf(x - center);
-                if (!isnan(x)) {
-                    const unsigned key = dcr_f2key(x);
-                    ++total;
-                    if (key < klo) ++below;
-                    else if (key <= khi) { keys[slot] = key; flags |= 1u << slot; }
-                }
+            // float-domain bracket test: ~10 instructions per element (the key transform is only needed for
+            // the few per cent inside the bracket)
+            if (transform == 1) x = fabsf(x - center);
+            if (!(mb & reject)) {
+                if (x < flo) { ++below; ++total; }
+                else if (x > fhi) ++total;
+                else if (x >= flo && x <= fhi) { cv[slot] = x; flags |= 1u << slot; }
             }
         },
         [&]() {
             // one warp-aggregated reservation in the CTA staging buffer per group of 512 elements
             if (__any_sync(0xffffffffu, flags != 0u)) {
                 const unsigned mine = __popc(flags);
+                total += mine;
                 const unsigned inc = dcr_warp_incl_scan(mine);
                 unsigned base = 0;
                 if (lane == 31) base = atomicAdd(&s_n, inc);
@@ -166,7 +182,7 @@ __global__ void __launch_bounds__(BS_THREADS) bsel_main_kernel(const SelView v, 
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     if (flags & (1u << k)) {
-                        const unsigned key = keys[k];
+                        const unsigned key = dcr_f2key(cv[k] + 0.0f);
                         if (pos < BS_STAGE) s_buf[pos] = key;
                         else {  // staging full (dense bracket): straight to the global buffer
                             const unsigned gq = atomicAdd(&st->ncand, 1u);
@@ -262,11 +278,21 @@ __global__ void __launch_bounds__(BS_THREADS) bsel_refine_kernel(BselState* st, 
     const int ns = cs > 11 ? cs - 11 : 0;
     const unsigned smask = (1u << (cs - ns)) - 1u;
     const unsigned p0 = st->prefix[0] >> cs, p1 = st->prefix[1] >> cs;
-    for (unsigned i = blockIdx.x * BS_THREADS + threadIdx.x; i < ncand; i += gridDim.x * BS_THREADS) {
-        const unsigned off = cand[i] - klo;
-        const unsigned pre = off >> cs;
-        if (pre == p0) atomicAdd(&ghist[(off >> ns) & smask], 1u);
-        if (p1 != p0 && pre == p1) atomicAdd(&ghist[2048 + ((off >> ns) & smask)], 1u);
+    {
+        const unsigned step = gridDim.x * BS_THREADS;
+        for (unsigned i0 = blockIdx.x * BS_THREADS + threadIdx.x; i0 < ncand; i0 += 4 * step) {
+            unsigned kv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) kv[u] = (i0 + u * step < ncand) ? __ldg(cand + i0 + u * step) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i0 + u * step >= ncand) break;
+                const unsigned off = kv[u] - klo;
+                const unsigned pre = off >> cs;
+                if (pre == p0) atomicAdd(&ghist[(off >> ns) & smask], 1u);
+                if (p1 != p0 && pre == p1) atomicAdd(&ghist[2048 + ((off >> ns) & smask)], 1u);
+            }
+        }
     }
     __threadfence();
     __syncthreads();
@@ -334,8 +360,8 @@ int dcr_bsel_enqueue(const SelView& v, double q_percent, BselState* st, void* sc
     bsel_sample_kernel<<<1, 1024, 0, s>>>(v, q_percent, st);
     bsel_main_kernel<<<grid, BS_THREADS, 0, s>>>(v, st, hist, cand, cap);
     bsel_find_kernel<<<1, 1024, 0, s>>>(st, hist, q_percent, cap);
-    bsel_refine_kernel<<<dcr_num_sms(), BS_THREADS, 0, s>>>(st, cand, hist);  // shift -> max(shift-11, 0)
-    bsel_refine_kernel<<<dcr_num_sms(), BS_THREADS, 0, s>>>(st, cand, hist);  // -> 0 (returns at once if done)
+    bsel_refine_kernel<<<dcr_num_sms() * 4, BS_THREADS, 0, s>>>(st, cand, hist);  // shift -> max(shift-11, 0)
+    bsel_refine_kernel<<<dcr_num_sms() * 4, BS_THREADS, 0, s>>>(st, cand, hist);  // -> 0 (returns at once if done)
     DCR_LAUNCH_OK("bsel kernels");
     return 0;
 }

@@ -229,7 +229,7 @@ __device__ __forceinline__ void dcr_stream1_groups(const float* __restrict__ x, 
     for (long long base = (nblk << 9) + warp * 32; base < n; base += nwarps * 32) {
         const long long i = base + lane;
         const bool in = i < n;
-        f(in ? x[i] : 0.f, in ? (m ? (unsigned)m[i] : 0u) : 0xFFFFFFFFu, i, 0);
+        f(in ? x[i] : __int_as_float(0x7fc00000), in ? (m ? (unsigned)m[i] : 0u) : 0xFFFFFFFFu, i, 0);  // NaN: never counted
         g();
     }
 }

@@ -38,6 +38,7 @@ int dcr_sel_enqueue(const SelView& v, double q_percent, SelState* st, unsigned* 
 // ---- sample-bracket selection (dcr_bsel.cu): one streaming pass, verified, with radix fallback ----
 struct BselState {
     unsigned klo, khi;               // bracket keys (inclusive)
+    float flo, fhi;                  // the same bracket as floats (the streaming pass compares floats, not keys)
     int shift;                       // (key - klo) >> shift indexes the 2048-bin bracket histogram
     int fallback;                    // 1: bracket missed / overflow / heavy ties -> result invalid, use the radix select
     int done, empty;

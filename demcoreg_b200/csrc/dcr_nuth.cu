@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(256) nuth_prepare_kernel(const float* __restri
     unsigned long long cnt = 0;
     double s = 0.0, ss = 0.0;
     const unsigned rej = m ? reject : 0u;
-    dcr_stream3(dh, slope, aspect, m, n, [&](float d, float sl, float a, unsigned mb, long long i) {
-        unsigned short b = BIN_INVALID;
+    auto one = [&](float d, float sl, float a, unsigned mb, float* yo, unsigned* bo) {
+        unsigned b = BIN_INVALID;
         float yv = 0.f;
         if (!(mb & rej)) {
             yv = nuth_y(d, sl);
@@ -64,16 +64,56 @@ __global__ void __launch_bounds__(256) nuth_prepare_kernel(const float* __restri
             ss += (double)yv * (double)yv;
             // np.digitize on float32 integer edges 0..360: bin = floor(x); x == 360 joins the last bin
             if (a >= 0.0f && a <= 360.0f) {
-                int bi = (int)floorf(a);
+                int bi = (int)a;  // a >= 0: truncation == floor
                 if (bi > NB - 1) bi = NB - 1;
-                b = (unsigned short)bi;
+                b = (unsigned)bi;
             } else {
                 b = BIN_INVALID - 1;  // in the common mask (counts for mean/std) but outside the bin range
             }
         }
-        y[i] = yv;
-        bin[i] = b;
-    });
+        *yo = yv;
+        *bo = b;
+    };
+    // 4 consecutive pixels per thread and iteration: 16-byte loads of dh/slope/aspect, 16-byte store of y and
+    // 8-byte store of bin (scalar stores throttled the LSU: profiles/sel_r1h, stall_lg_throttle 2.0)
+    const bool vec = DCR_AL16(dh) && DCR_AL16(slope) && DCR_AL16(aspect) && DCR_AL4(m) && DCR_AL16(y) && DCR_AL8(bin);
+    const long long n4 = vec ? (n >> 2) : 0;
+    const long long step = (long long)gridDim.x * 256;
+    for (long long q0 = (long long)blockIdx.x * 256 + threadIdx.x; q0 < n4; q0 += 2 * step) {
+        float4 vd[2], vs[2], va[2];
+        unsigned vm[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const long long q = q0 + u * step;
+            if (q < n4) {
+                vd[u] = __ldg(reinterpret_cast<const float4*>(dh) + q);
+                vs[u] = __ldg(reinterpret_cast<const float4*>(slope) + q);
+                va[u] = __ldg(reinterpret_cast<const float4*>(aspect) + q);
+                vm[u] = m ? __ldg(reinterpret_cast<const unsigned*>(m) + q) : 0u;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const long long q = q0 + u * step;
+            if (q < n4) {
+                float4 yo;
+                unsigned b0, b1, b2, b3;
+                one(vd[u].x, vs[u].x, va[u].x, vm[u] & 0xffu, &yo.x, &b0);
+                one(vd[u].y, vs[u].y, va[u].y, (vm[u] >> 8) & 0xffu, &yo.y, &b1);
+                one(vd[u].z, vs[u].z, va[u].z, (vm[u] >> 16) & 0xffu, &yo.z, &b2);
+                one(vd[u].w, vs[u].w, va[u].w, vm[u] >> 24, &yo.w, &b3);
+                reinterpret_cast<float4*>(y)[q] = yo;
+                reinterpret_cast<uint2*>(bin)[q] = make_uint2(b0 | (b1 << 16), b2 | (b3 << 16));
+            }
+        }
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += step) {
+        float yo;
+        unsigned bo;
+        one(dh[i], slope[i], aspect[i], m ? (unsigned)m[i] : 0u, &yo, &bo);
+        y[i] = yo;
+        bin[i] = (unsigned short)bo;
+    }
     cnt = dcr_warp_sum_u64(cnt);
     s = dcr_warp_sum(s);
     ss = dcr_warp_sum(ss);

@@ -388,15 +388,17 @@ __global__ void __launch_bounds__(256) compress_strided_kernel(const float* __re
     // row-band mode: this band's elements follow `base` unmasked elements of the bands above it
     const long long gbase = base_ptr ? *base_ptr : 0;
     const long long dfirst = (gbase + stride - 1) / stride;  // global subsample index of this band's first pick
-    long long rank = gbase + off[blockIdx.x] + ex;
+    // one 64-bit division per thread; the 8 elements then advance (quotient, remainder) incrementally
+    const long long rank0 = gbase + off[blockIdx.x] + ex;
+    if (c == 0) return;
+    long long quo = rank0 / stride;
+    long long rem = rank0 - quo * stride;
+    quo -= dfirst;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         if (flags & (1u << k)) {
-            if (rank % stride == 0) {
-                const long long d = rank / stride - dfirst;
-                if (d < cap) dense[d] = vals[k];
-            }
-            ++rank;
+            if (rem == 0 && quo < cap) dense[quo] = vals[k];
+            if (++rem == stride) { rem = 0; ++quo; }
         }
     }
 }
