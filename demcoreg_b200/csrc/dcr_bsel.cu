@@ -200,11 +200,12 @@ __global__ void __launch_bounds__(1024) bsel_sample_kernel(const SelView v, doub
     }
 }
 
-#define BS_STAGE 6144  // per-CTA staging of in-bracket keys (one global reservation per CTA instead of per warp)
+#define BS_STAGE 4096  // per-CTA staging of in-bracket keys (one global reservation per CTA instead of per warp)
 __global__ void __launch_bounds__(BS_THREADS) bsel_main_kernel(const SelView v, BselState* st, unsigned* __restrict__ ghist,
                                                                unsigned* __restrict__ cand, unsigned cap) {
     __shared__ unsigned h[2048];
     __shared__ unsigned s_buf[BS_STAGE];
+    __shared__ float s_priv[16 * BS_THREADS];
     __shared__ unsigned s_n, s_gbase;
     __shared__ unsigned long long s_below, s_total;
     if (st->done) return;
@@ -220,33 +221,31 @@ __global__ void __launch_bounds__(BS_THREADS) bsel_main_kernel(const SelView v, 
     const int lane = threadIdx.x & 31;
     const float flo = st->flo, fhi = st->fhi;
     unsigned below = 0, total = 0;   // total accumulates below + above + in-bracket (NaNs fail every comparison)
-    float cv[16];
-    unsigned flags = 0;
+    // in-bracket values go to thread-private shared-memory slots first (no warp collective per element); the group
+    // end then moves them with a warp-uniform trip count of max(count) ~ 3 instead of 16 divergent passes
+    float* mine = s_priv + threadIdx.x;   // slot k of this thread: mine[k * BS_THREADS]
+    unsigned c = 0;
     dcr_stream1_groups(v.x, v.m, n,
-        [&](float x, unsigned mb, long long, int slot) {
-            // float-domain bracket test: ~10 instructions per element (the key transform is only needed for
-            // the few per cent inside the bracket)
+        [&](float x, unsigned mb, long long, int) {
             if (transform == 1) x = fabsf(x - center);
-            if (!(mb & reject)) {
-                if (x < flo) { ++below; ++total; }
-                else if (x > fhi) ++total;
-                else if (x >= flo && x <= fhi) { cv[slot] = x; flags |= 1u << slot; }
-            }
+            const bool ok = !(mb & reject);
+            const bool lo = ok && (x < flo), hi = ok && (x > fhi), in = ok && (x >= flo) && (x <= fhi);
+            below += lo;
+            total += lo | hi;
+            if (in) { mine[c * BS_THREADS] = x; ++c; }
         },
         [&]() {
-            // one warp-aggregated reservation in the CTA staging buffer per group of 512 elements
-            if (__any_sync(0xffffffffu, flags != 0u)) {
-                const unsigned mine = __popc(flags);
-                total += mine;
-                const unsigned inc = dcr_warp_incl_scan(mine);
+            const unsigned cmax = __reduce_max_sync(0xffffffffu, c);
+            if (cmax) {
+                total += c;
+                const unsigned inc = dcr_warp_incl_scan(c);
                 unsigned base = 0;
                 if (lane == 31) base = atomicAdd(&s_n, inc);
                 base = __shfl_sync(0xffffffffu, base, 31);
-                unsigned pos = base + inc - mine;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    if (flags & (1u << k)) {
-                        const unsigned key = dcr_f2key(cv[k] + 0.0f);
+                unsigned pos = base + inc - c;
+                for (unsigned k = 0; k < cmax; ++k) {
+                    if (k < c) {
+                        const unsigned key = dcr_f2key(mine[k * BS_THREADS] + 0.0f);
                         if (pos < BS_STAGE) s_buf[pos] = key;
                         else {  // staging full (dense bracket): straight to the global buffer
                             const unsigned gq = atomicAdd(&st->ncand, 1u);
@@ -257,7 +256,7 @@ __global__ void __launch_bounds__(BS_THREADS) bsel_main_kernel(const SelView v, 
                     }
                 }
             }
-            flags = 0;
+            c = 0;
         });
     below = __reduce_add_sync(0xffffffffu, below);
     total = __reduce_add_sync(0xffffffffu, total);
