@@ -577,51 +577,63 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
         }
         const int s_near = (p.sg.ny0 - p.sg.iy0) * F_SRC_C + (p.sg.nx0 - p.sg.ix0);
         const int r_near = (p.rg.ny0 - p.rg.iy0) * F_REF_C + (p.rg.nx0 - p.rg.ix0);
+        // per-thread invariants hoisted out of the row loop: column validity, row limits, output offset
+        const bool col_ok = j < p.w;
+        const int i0 = ti0 + rbeg;
+        const int n_store = col_ok ? min(F_ROWS_PER_THREAD, p.row_end - i0) : 0;   // rows rr < n_store are stored
+        const int n_grid = col_ok ? min(F_ROWS_PER_THREAD, p.h - i0) : 0;          // rows rr < n_grid exist in the grid
+        long long o = (long long)(i0 - p.row_begin) * p.w + j;
+        const float* qs = s_src + (rbeg + 4) * F_SRC_C + (c + 1);
+        const float* qr = s_ref + (rbeg + 3) * F_REF_C + c;
+        float* swp = s_sw + (rbeg + 1) * F_SW_C + (c + 1);
+        const unsigned char* mk = s_mask + rbeg * F_TW + c;
+        const bool has_mask = p.smask != nullptr;
+        const bool has_warped = (p.ref_w != nullptr) || (p.src_w != nullptr);
+        const float qnan = __int_as_float(0x7fc00000);
 #pragma unroll 4
         for (int rr = 0; rr < F_ROWS_PER_THREAD; ++rr) {
-            const int r = rbeg + rr;
-            const int i = ti0 + r;
-            const float* q = s_src + (r + 4) * F_SRC_C + (c + 1);
-            const double xs3 = xpass(p.sg.wx, q[0], q[1], q[2], q[3]);
-            const float* u = s_ref + (r + 3) * F_REF_C + c;
-            const double xr3 = xpass(p.rg.wx, u[0], u[1], u[2], u[3]);
+            const double xs3 = xpass(p.sg.wx, qs[0], qs[1], qs[2], qs[3]);
+            const double xr3 = xpass(p.rg.wx, qr[0], qr[1], qr[2], qr[3]);
             const double so = ypass(p.sg.wy, xs0, xs1, xs2, xs3);
             const double ro = ypass(p.rg.wy, xr0, xr1, xr2, xr3);
             xs0 = xs1; xs1 = xs2; xs2 = xs3;
             xr0 = xr1; xr1 = xr2; xr2 = xr3;
             // common case: every tap valid -> the cubic value; anything else (nodata / edge) takes ONE rare branch
-            const float* ts = s_src + (r + 2) * F_SRC_C + (c + 2);  // UL pixel of the 2x2
-            const float* tr = s_ref + (r + 1) * F_REF_C + (c + 1);
             float sv = (float)so, rv = (float)ro;
             if (isnan(sv + rv)) {
+                const float* ts = qs - 2 * F_SRC_C + 1;  // UL pixel of the 2x2
+                const float* tr = qr - 2 * F_REF_C + 1;
                 const float ns = ts[s_near], nr = tr[r_near];
                 sv = isnan(so) ? bilinear_fallback(ts[0], ts[1], ts[F_SRC_C + 1], ts[F_SRC_C], ns, p.sg.fx, p.sg.fy)
                                : (isnan(ns) ? ns : sv);
                 rv = isnan(ro) ? bilinear_fallback(tr[0], tr[1], tr[F_REF_C + 1], tr[F_REF_C], nr, p.rg.fx, p.rg.fy)
                                : (isnan(nr) ? nr : rv);
             }
-            const bool inside = (i < p.row_end) && (j < p.w);
             // rows past this launch's band still feed the 3x3 stencil of its last row (row-band mode)
-            if (!((i < p.h) && (j < p.w))) sv = __int_as_float(0x7fc00000);
-            s_sw[(r + 1) * F_SW_C + (c + 1)] = sv;
-            // ds_getma masks: |x - ndv| <= tol in double (numpy masked_values)
-            const bool sm = !(sv < p.src_gm_lo || sv > p.src_gm_hi);  // NaN -> masked
-            const bool rm = !(rv < p.ref_gm_lo || rv > p.ref_gm_hi);
-            bool base_ok = inside && !sm && !rm;
-            if (p.smask && s_mask[r * F_TW + c]) base_ok = false;
-            const float dh = base_ok ? (sv - rv) : 0.0f;
-            if (base_ok) {
-                valid_bits |= (1u << rr);
-                ++n_base;
-                if (p.use_max_dz && (dh < -p.max_dz || dh > p.max_dz)) maxdz_bits |= (1u << rr);
-                else ++n_maxdz;
-            }
-            if (inside) {
-                const long long o = (long long)(i - p.row_begin) * p.w + j;
+            if (rr >= n_grid) sv = qnan;
+            *swp = sv;
+            if (rr < n_store) {
+                // ds_getma masks as float32 intervals of numpy masked_values' |x - ndv| <= tol (NaN -> masked)
+                bool base_ok = (sv < p.src_gm_lo || sv > p.src_gm_hi) && (rv < p.ref_gm_lo || rv > p.ref_gm_hi);
+                if (has_mask && *mk) base_ok = false;
+                const float dh = base_ok ? (sv - rv) : 0.0f;
+                if (base_ok) {
+                    valid_bits |= (1u << rr);
+                    ++n_base;
+                    if (p.use_max_dz && (dh < -p.max_dz || dh > p.max_dz)) maxdz_bits |= (1u << rr);
+                    else ++n_maxdz;
+                }
                 p.dh[o] = dh;
-                if (p.ref_w) p.ref_w[o] = isnan(rv) ? p.ref_fill : rv;
-                if (p.src_w) p.src_w[o] = isnan(sv) ? p.src_fill : sv;
+                if (has_warped) {
+                    if (p.ref_w) p.ref_w[o] = isnan(rv) ? p.ref_fill : rv;
+                    if (p.src_w) p.src_w[o] = isnan(sv) ? p.src_fill : sv;
+                }
             }
+            o += p.w;
+            qs += F_SRC_C;
+            qr += F_REF_C;
+            swp += F_SW_C;
+            mk += F_TW;
         }
     }
     __syncthreads();
@@ -633,16 +645,23 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
         w0 = q[0]; w1 = q[1]; w2 = q[2];
         q += F_SW_C;
         w3 = q[0]; w4 = q[1]; w5 = q[2];
+        q += F_SW_C;
+        // hoisted invariants: stored rows, interior rows [r_lo, r_hi) of this thread (borders are nodata), offset
+        const bool col_ok = j < p.w;
+        const bool col_in = j > 0 && j < p.w - 1;
+        const int i0 = ti0 + rbeg;
+        const int n_store = col_ok ? min(F_ROWS_PER_THREAD, p.row_end - i0) : 0;
+        const int r_lo = col_in ? max(0, 1 - i0) : F_ROWS_PER_THREAD;
+        const int r_hi = col_in ? min(F_ROWS_PER_THREAD, p.h - 1 - i0) : 0;
+        long long o = (long long)(i0 - p.row_begin) * p.w + j;
 #pragma unroll 2
         for (int rr = 0; rr < F_ROWS_PER_THREAD; ++rr) {
-            const int r = rbeg + rr;
-            const int i = ti0 + r;
-            q = s_sw + (r + 2) * F_SW_C + c;
             w6 = q[0]; w7 = q[1]; w8 = q[2];
-            if (i < p.row_end && j < p.w) {
+            q += F_SW_C;
+            if (rr < n_store) {
                 float sl = DCR_GDALDEM_NDV, as = DCR_GDALDEM_NDV;
                 unsigned bits = DCR_M_SLOPE | DCR_M_ASPECT;
-                if (i > 0 && j > 0 && i < p.h - 1 && j < p.w - 1) {
+                if (rr >= r_lo && rr < r_hi) {
                     float sv, av;
                     bool ex;
                     if (horn_fast(w0, w1, w2, w3, w4, w5, w6, w7, w8, p.inv8ew, p.inv8ns, p.slope_lo, p.slope_hi, &sv, &av,
@@ -656,11 +675,11 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
                 }
                 if (!(valid_bits & (1u << rr))) bits |= DCR_M_BASE;
                 else if (maxdz_bits & (1u << rr)) bits |= DCR_M_MAXDZ;
-                const long long o = (long long)(i - p.row_begin) * p.w + j;
                 p.slope[o] = sl;
                 p.aspect[o] = as;
                 p.maskbits[o] = (unsigned char)bits;
             }
+            o += p.w;
             w0 = w3; w1 = w4; w2 = w5;
             w3 = w6; w4 = w7; w5 = w8;
         }
