@@ -354,36 +354,97 @@ __global__ void fb_findA_kernel(NuthDev* nd, const unsigned* __restrict__ ghist)
     }
 }
 
-#define FB_STAGE 4096
+#define FB_STAGE 3072
+#define FB_PRIV 8
+// Pass B: ~4 % of the samples fall in the median coarse cell(s) of their bin.  They are first parked in
+// thread-private shared-memory slots; each warp then drains its slots with a uniform trip count (max per-lane
+// count, ~2) -- fine-cell histogram (global atomics, spread over 360 x 1024 counters) + CTA staging of the record.
 __global__ void __launch_bounds__(256) fb_passB_kernel(const float* __restrict__ y, const unsigned short* __restrict__ bin,
                                                        long long n, NuthDev* nd, unsigned* __restrict__ ghist,
                                                        unsigned long long* __restrict__ cand, unsigned cap) {
     __shared__ unsigned short s_c0[NB], s_c1[NB];
     __shared__ unsigned long long s_buf[FB_STAGE];
+    __shared__ unsigned long long s_priv[FB_PRIV * 256];   // thread-private slots: slot k of thread t at [k * 256 + t]
     __shared__ unsigned s_n, s_gbase;
     if (nd->fast_fallback) return;
     for (int k = threadIdx.x; k < NB; k += 256) { s_c0[k] = nd->fa_cell[0][k]; s_c1[k] = nd->fa_cell[1][k]; }
     if (threadIdx.x == 0) s_n = 0u;
     __syncthreads();
     const float rmin = nd->rmin, rmax = nd->rmax, scale = nd->fast_scale;
-    dcr_stream_f_u16(y, bin, n, [&](float yv, unsigned b, long long) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long* mine = s_priv + threadIdx.x;
+    unsigned c = 0;
+    auto elem = [&](float yv, unsigned b) {
         if (b >= NB) return;
         if (!(yv >= rmin && yv <= rmax)) return;
         const unsigned f = fb_fine(yv, rmin, scale);
-        const unsigned c = f >> 10;
+        const unsigned cc = f >> 10;
         const unsigned c0 = s_c0[b], c1 = s_c1[b];
-        if (c != c0 && c != c1) return;
-        // ~4 % of the samples get here
-        const int plane = (c == c0) ? 0 : 1;
-        atomicAdd(&ghist[(plane * NB + b) * FB_FINE + (f & (FB_FINE - 1))], 1u);
+        if (cc != c0 && cc != c1) return;
+        const unsigned plane = (cc == c0) ? 0u : 1u;
         const unsigned long long rec = ((unsigned long long)dcr_f2key(yv) << 32) | ((unsigned long long)b << 16) | f;
-        const unsigned pos = atomicAdd(&s_n, 1u);
-        if (pos < FB_STAGE) s_buf[pos] = rec;
-        else {
+        if (c < FB_PRIV) {
+            mine[c * 256] = rec | ((unsigned long long)plane << 31);
+            ++c;
+        } else {  // > 8 hits among 16 consecutive samples of one thread: unaggregated path
+            atomicAdd(&ghist[(plane * NB + b) * FB_FINE + (f & (FB_FINE - 1))], 1u);
             const unsigned g = atomicAdd(&nd->fast_ncand, 1u);
             if (g < cap) cand[g] = rec;
         }
-    });
+    };
+    auto drain = [&]() {
+        const unsigned cmax = __reduce_max_sync(0xffffffffu, c);
+        if (cmax) {
+            const unsigned inc = dcr_warp_incl_scan(c);
+            unsigned base = 0;
+            if (lane == 31) base = atomicAdd(&s_n, inc);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            unsigned pos = base + inc - c;
+            for (unsigned k = 0; k < cmax; ++k) {
+                if (k < c) {
+                    unsigned long long rec = mine[k * 256];
+                    const unsigned plane = (unsigned)(rec >> 31) & 1u;
+                    rec &= ~(1ull << 31);
+                    const unsigned f = (unsigned)(rec & 0xFFFFu), b = (unsigned)(rec >> 16) & 0x7FFFu;
+                    atomicAdd(&ghist[(plane * NB + b) * FB_FINE + (f & (FB_FINE - 1))], 1u);
+                    if (pos < FB_STAGE) s_buf[pos] = rec;
+                    else {
+                        const unsigned g = atomicAdd(&nd->fast_ncand, 1u);
+                        if (g < cap) cand[g] = rec;
+                    }
+                    ++pos;
+                }
+            }
+        }
+        c = 0;
+    };
+    // same 512-element warp groups as dcr_stream_f_u16, with a warp-uniform drain after every group
+    {
+        const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+        const long long nblk = (DCR_AL16(y) && DCR_AL8(bin)) ? (n >> 9) : 0;
+        for (long long w = warp; w < nblk; w += nwarps) {
+            const float4* y4 = reinterpret_cast<const float4*>(y) + (w << 7);
+            const uint2* q4 = reinterpret_cast<const uint2*>(bin) + (w << 7);
+            float4 t[4];
+            uint2 qq[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { t[k] = __ldg(y4 + k * 32 + lane); qq[k] = __ldg(q4 + k * 32 + lane); }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                elem(t[k].x, qq[k].x & 0xffffu);
+                elem(t[k].y, qq[k].x >> 16);
+                elem(t[k].z, qq[k].y & 0xffffu);
+                elem(t[k].w, qq[k].y >> 16);
+            }
+            drain();
+        }
+        for (long long base = (nblk << 9) + warp * 32; base < n; base += nwarps * 32) {
+            const long long i = base + lane;
+            if (i < n) elem(y[i], (unsigned)bin[i]);
+            drain();
+        }
+    }
     __syncthreads();
     const unsigned nst = s_n < FB_STAGE ? s_n : FB_STAGE;
     if (threadIdx.x == 0) s_gbase = nst ? atomicAdd(&nd->fast_ncand, nst) : 0u;
