@@ -24,6 +24,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALG_BYTES_ITER = 90.0      # algorithmic bytes per pixel per iteration
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of front_kernel on the default 8192^2 workload, from the
+# `ncu --set full` capture summarised in profiles/front_kernel_r1_final_raw.csv (604.03 MB + 823.26 MB)
+FRONT_KERNEL_DRAM_BYTES_8192 = 1427290880
 # algorithmic bytes per pixel of each profiled stage (SURVEY 8d stage table)
 STAGE_INFO = [
     ("front_kernel (warp+dh+masks+Horn)", 21.0),
@@ -157,6 +160,94 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_band(args):
+    """Row-band mode (BASELINE.json configs[4]): one size x size pair, rows split over the ranks; NCCL send/recv for the
+    halos, all-reduce of the selection / bin histograms between the phases of dcr_band_phase.  Strong scaling."""
+    import torch
+    import torch.distributed as dist
+    from demcoreg_b200 import band, synth, _lib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, res = args.size, args.res
+    period = min(n, 2048)
+    # every rank builds ONLY its own rows from the periodic tile (the halos come from the neighbours over NCCL)
+    p = synth.make_pair(n=period, res=res, seed=20260050, static_mask_frac=0.3, nodata_frac=0.01)
+    r0, r1 = band.band_rows(n, rank, world)
+    rows = np.arange(r0, r1) % period
+    reps = n // period
+
+    def band_of(a):
+        return torch.from_numpy(np.ascontiguousarray(np.tile(a[rows], (1, reps)))).cuda()
+    gt = p['gt']
+    al = band.BandAligner(band_of(p['ref']), band_of(p['src']), band_of(p['mask']), n, gt, p['ndv'], rank, world, halo=16)
+    if world > 1:
+        al.exchange_halos()
+    else:
+        pass  # single band: no neighbours
+
+    def reduce_fn(t):
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    def step():
+        nph = al.begin_iteration()
+        for ph in range(nph):
+            for t in al.run_phase(ph):
+                reduce_fn(t)
+        r = al.result()
+        al.apply_shift(r.dx, r.dy, r.dz)
+        return r
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        r = step()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    pix = 0
+    for _ in range(args.steps):
+        r = step()
+        pix += al.grid.height * al.grid.width
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    if rank == 0:
+        peak, peak_src = peaks()
+        ms_step = ms_total / args.steps
+        value = pix / (ms_total * 1e-3) / 1e9
+        ach = ALG_BYTES_ITER * (pix / args.steps) / (ms_step * 1e-3) / 1e9
+        line = {"metric": "nuth_kaab_iteration_throughput", "value": value, "unit": "Gpix/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "dem_align -mode nuth, one iteration per step on ONE synthetic %dx%d pair at %g m (30%% "
+                                       "stable-surface mask, 1%% nodata) split into %d row bands, NCCL halo exchange + "
+                                       "histogram all-reduce (radix selects)" % (n, n, res, world),
+                           "collectives_per_step": 22, "halo_rows": 16,
+                           "l2": "inputs larger than the 126 MB L2", "last_step_shift_m": [r.dx, r.dy, r.dz]},
+                "clocks": clocks, "gpu_launches": (1 + 5 * 6 + 6 + 9 + 1) * args.steps,
+                "roofline_iteration": {"bound": "hbm", "achieved": ach, "peak": peak * world, "unit": "GB/s",
+                                       "frac": ach / (peak * world), "algorithmic_bytes_per_px": ALG_BYTES_ITER,
+                                       "peak_source": peak_src + " x n_gpus"},
+                "e2e": None, "roofline": None, "cpu_baseline": None}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -166,11 +257,16 @@ def main():
     ap.add_argument("--size", type=int, default=8192)
     ap.add_argument("--res", type=float, default=8.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="pairs", choices=["pairs", "band"],
+                    help="pairs: one pair per GPU, no collective (default; configs[1]/[3]); band: ONE size x size pair "
+                         "split into row bands over the GPUs with NCCL halo exchange + all-reduces (configs[4])")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
+    if args.mode == "band":
+        return run_band(args)
 
     import torch
     import torch.distributed as dist
@@ -246,7 +342,8 @@ def main():
     dom_bytes = STAGE_INFO[dom][1] * npx
     ach = dom_bytes / (stage[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": STAGE_INFO[dom][0], "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "frac": ach / peak, "traffic": (FRONT_KERNEL_DRAM_BYTES_8192 if (dom == 0 and size == 8192) else None),
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": float(stage[dom]),
                 "stages_ms": {STAGE_INFO[k][0]: float(stage[k]) for k in range(7)}}
     iter_ach = ALG_BYTES_ITER * npx / (ms_step * 1e-3) / 1e9
