@@ -52,7 +52,11 @@ __device__ __forceinline__ void bsel_ranks(long long count, double q_percent, lo
     *g = vi - (double)(*klo);
 }
 
-__global__ void __launch_bounds__(1024) bsel_sample_kernel(const SelView v, double q_percent, BselState* st) {
+__device__ __forceinline__ void bsel_publish(BselState* st) {
+    if (st->publish) *st->publish = st->result;
+}
+
+__global__ void __launch_bounds__(1024) bsel_sample_kernel(const SelView v, double q_percent, BselState* st, float* publish) {
     __shared__ unsigned s[BS_S];
     __shared__ unsigned s_valid;
     const long long n = v.n_ptr ? *v.n_ptr : v.n;
@@ -100,6 +104,7 @@ __global__ void __launch_bounds__(1024) bsel_sample_kernel(const SelView v, doub
         st->done = 0;
         st->empty = 0;
         st->below = 0; st->total = 0; st->ncand = 0; st->nsmall = 0; st->ticket = 0;
+        st->publish = publish;
     }
     const long long m = s_valid;
     if (all) {
@@ -118,6 +123,7 @@ __global__ void __launch_bounds__(1024) bsel_sample_kernel(const SelView v, doub
                 st->v_lo = dcr_key2f(s[klo]); st->v_hi = dcr_key2f(s[khi]);
                 st->result = dcr_lerp32(st->v_lo, st->v_hi, g);
             }
+            bsel_publish(st);
         }
         return;
     }
@@ -201,8 +207,10 @@ __global__ void __launch_bounds__(1024) bsel_sample_kernel(const SelView v, doub
 }
 
 #define BS_STAGE 4096  // per-CTA staging of in-bracket keys (one global reservation per CTA instead of per warp)
-__global__ void __launch_bounds__(BS_THREADS) bsel_main_kernel(const SelView v, BselState* st, unsigned* __restrict__ ghist,
-                                                               unsigned* __restrict__ cand, unsigned cap) {
+__device__ void bsel_find_block(BselState* st, unsigned* ghist, double q_percent, unsigned cap, unsigned* s_cum, unsigned* s_scratch);
+
+__global__ void __launch_bounds__(BS_THREADS) bsel_main_kernel(const SelView v, BselState* st, unsigned* ghist,
+                                                               unsigned* __restrict__ cand, unsigned cap, double q_percent) {
     __shared__ unsigned h[2048];
     __shared__ unsigned s_buf[BS_STAGE];
     __shared__ float s_priv[16 * BS_THREADS];
@@ -277,30 +285,43 @@ __global__ void __launch_bounds__(BS_THREADS) bsel_main_kernel(const SelView v, 
     const unsigned gb = s_gbase;
     for (unsigned k = threadIdx.x; k < nst; k += BS_THREADS)
         if (gb + k < cap) cand[gb + k] = s_buf[k];
+    // the last CTA to finish locates the ranks in the bracket histogram (saves a dependent launch)
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    unsigned* s_cum = s_buf;            // reuse the staging buffer (>= 2049 words)
+    __shared__ unsigned s_scr[33];
+    bsel_find_block(st, ghist, q_percent, cap, s_cum, s_scr);
 }
 
-// Level-0 find: the bracket-histogram bin of each of the two ranks, after VERIFYING that both ranks fall
-// inside the bracket and that no candidate was dropped.  off = key - klo; bin0 = off >> shift.
-__global__ void __launch_bounds__(1024) bsel_find_kernel(BselState* st, unsigned* ghist, double q_percent, unsigned cap) {
-    __shared__ unsigned s_scratch[33];
-    __shared__ unsigned s_cum[2049];
-    if (st->done) return;
+// Level-0 find (run by the LAST CTA of bsel_main_kernel): the bracket-histogram bin of each of the two ranks,
+// after VERIFYING that both ranks fall inside the bracket and that no candidate was dropped.
+// off = key - klo; bin0 = off >> shift.  256 threads, 8 bins each.
+__device__ void bsel_find_block(BselState* st, unsigned* ghist, double q_percent, unsigned cap, unsigned* s_cum /*[2049]*/,
+                                unsigned* s_scratch /*[33]*/) {
     const int t = threadIdx.x;
-    const unsigned a = ghist[2 * t], b = ghist[2 * t + 1];
+    unsigned v[8], sum = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { v[q] = __ldcg(ghist + t * 8 + q); sum += v[q]; }
     unsigned total;
-    const unsigned ex = dcr_block_excl_scan(a + b, s_scratch, &total);
-    s_cum[2 * t] = ex;
-    s_cum[2 * t + 1] = ex + a;
+    unsigned ex = dcr_block_excl_scan(sum, s_scratch, &total);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { s_cum[t * 8 + q] = ex; ex += v[q]; }
     if (t == 0) s_cum[2048] = total;
     __syncthreads();
-    ghist[2 * t] = 0u;
-    ghist[2 * t + 1] = 0u;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) ghist[t * 8 + q] = 0u;
     if (t == 0) {
         const long long count = (long long)st->total;
         st->count = count;
         if (count == 0) {
             st->empty = 1; st->done = 1;
             st->v_lo = st->v_hi = st->result = __int_as_float(0x7fc00000);
+            bsel_publish(st);
         } else {
             long long klo, khi; double g;
             bsel_ranks(count, q_percent, &klo, &khi, &g);
@@ -322,9 +343,11 @@ __global__ void __launch_bounds__(1024) bsel_find_kernel(BselState* st, unsigned
                     st->v_lo = x0; st->v_hi = x1;
                     st->result = dcr_lerp32(x0, x1, g);
                     st->done = 1;
+                    bsel_publish(st);
                 }
             }
         }
+        st->ticket = 0;
     }
 }
 
@@ -398,6 +421,7 @@ __global__ void __launch_bounds__(BS_THREADS) bsel_refine_kernel(BselState* st, 
             st->v_lo = x0; st->v_hi = x1;
             st->result = dcr_lerp32(x0, x1, st->gamma);
             st->done = 1;
+            bsel_publish(st);
         }
     }
 }
@@ -412,7 +436,8 @@ unsigned dcr_bsel_cap(long long n) {
     return (unsigned)c;
 }
 
-int dcr_bsel_enqueue(const SelView& v, double q_percent, BselState* st, void* scratch, long long n_max, cudaStream_t s) {
+int dcr_bsel_enqueue(const SelView& v, double q_percent, BselState* st, void* scratch, long long n_max, cudaStream_t s,
+                     float* publish) {
     const unsigned cap = dcr_bsel_cap(n_max);
     char* p = (char*)scratch;
     unsigned* hist = (unsigned*)p;
@@ -420,9 +445,8 @@ int dcr_bsel_enqueue(const SelView& v, double q_percent, BselState* st, void* sc
     unsigned* cand = (unsigned*)p;
     const int grid = dcr_num_sms() * 8;
     DCR_CUDA_OK(cudaMemsetAsync(hist, 0, 4096 * sizeof(unsigned), s));
-    bsel_sample_kernel<<<1, 1024, 0, s>>>(v, q_percent, st);
-    bsel_main_kernel<<<grid, BS_THREADS, 0, s>>>(v, st, hist, cand, cap);
-    bsel_find_kernel<<<1, 1024, 0, s>>>(st, hist, q_percent, cap);
+    bsel_sample_kernel<<<1, 1024, 0, s>>>(v, q_percent, st, publish);
+    bsel_main_kernel<<<grid, BS_THREADS, 0, s>>>(v, st, hist, cand, cap, q_percent);  // + level-0 find in its last CTA
     bsel_refine_kernel<<<dcr_num_sms() * 4, BS_THREADS, 0, s>>>(st, cand, hist);  // shift -> max(shift-11, 0)
     bsel_refine_kernel<<<dcr_num_sms() * 4, BS_THREADS, 0, s>>>(st, cand, hist);  // -> 0 (returns at once if done)
     DCR_LAUNCH_OK("bsel kernels");

@@ -51,10 +51,12 @@ struct BselState {
     double gamma;
     float v_lo, v_hi, result;
     int pad;
+    float* publish;                  // optional device scalar that receives `result` as soon as it is final
 };
 unsigned dcr_bsel_cap(long long n);
 size_t dcr_bsel_scratch_bytes(long long n);
-int dcr_bsel_enqueue(const SelView& v, double q_percent, BselState* st, void* scratch, long long n_max, cudaStream_t s);
+int dcr_bsel_enqueue(const SelView& v, double q_percent, BselState* st, void* scratch, long long n_max, cudaStream_t s,
+                     float* publish = nullptr);
 
 // ---- nuth (dcr_nuth.cu) ----
 struct NuthDev;  // device block

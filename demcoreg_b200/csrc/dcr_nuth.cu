@@ -870,10 +870,10 @@ struct IterWs {
 // one exact median (q = 50) of view v into d->selres[k], through either engine
 static int iter_select(const SelView& v, int k, const IterWs& w, long long n, int use_bsel, cudaStream_t s) {
     int rc;
-    if (use_bsel) rc = dcr_bsel_enqueue(v, 50.0, &w.d->bsel[k], w.bsel_scratch, n, s);
-    else rc = dcr_sel_enqueue(v, 50.0, &w.d->sel[k], w.hist, s);
+    if (use_bsel) return dcr_bsel_enqueue(v, 50.0, &w.d->bsel[k], w.bsel_scratch, n, s, &w.d->selres[k]);
+    rc = dcr_sel_enqueue(v, 50.0, &w.d->sel[k], w.hist, s);
     if (rc) return rc;
-    sel_publish_kernel<<<1, 32, 0, s>>>(w.d, k, use_bsel);
+    sel_publish_kernel<<<1, 32, 0, s>>>(w.d, k, 0);
     return 0;
 }
 
