@@ -203,6 +203,27 @@ def align(ref_dem_ds, src_dem_ds, mode='nuth', mask_source=None, tol=0.02, max_o
                 src_align=src_dem_ds_align)
 
 
+def diff_stats(ref_dem_ds, src_dem_ds, mask_source=None, max_dz=100):
+    """Final-difference products of reference ``dem_align.py:366-392`` (and ``:506-530`` for the original pair).
+
+    Warp both rasters to their common grid, ``diff = src - ref``, then ``malib.get_stats_dict(full=True)`` of the
+    difference over valid, un-masked pixels and of its filtered version (``outlier_filter`` + the slope mask with the
+    DEFAULT ``slope_lim`` -- the reference ignores the user's limits here, ``dem_align.py:390, 528``).
+    Returns ``dict(stats, stats_filt, diff, diff_filt, gt)`` with the rasters as masked arrays.
+    """
+    from . import robust_stats
+    res, grid, bufs = engine.nuth_iteration(ref_dem_ds, src_dem_ds, mask_source, True, max_dz, (0.1, 40))
+    base = (bufs.maskbits & _lib.M_BASE) != 0
+    filt = (bufs.maskbits & _lib.M_DIFF) != 0
+    out = dict(stats=robust_stats.get_stats_dict(bufs.dh, base, full=True),
+               stats_filt=robust_stats.get_stats_dict(bufs.dh, filt, full=True),
+               gt=tuple(grid.gt))
+    dh = bufs.dh.cpu().numpy()
+    out['diff'] = np.ma.array(dh, mask=base.cpu().numpy())
+    out['diff_filt'] = np.ma.array(dh, mask=filt.cpu().numpy())
+    return out
+
+
 def main(argv=None):
     """Reference ``dem_align.py:203-631`` (iteration loop + final shift products; plots are not produced)."""
     from . import rasterio_lite as rio
@@ -245,8 +266,25 @@ def main(argv=None):
     sa = out['src_align']
     rio.write_raster(align_fn, sa.numpy(), sa.gt, sa.ndv, sa.proj)
     dm_total = float(np.sqrt(dx_total ** 2 + dy_total ** 2 + dz_total ** 2))
+    # final elevation difference (dem_align.py:366-392) and the original one (dem_align.py:506-530)
+    after = diff_stats(ref, sa, mask_source, args.max_dz)
+    before = diff_stats(ref, src, mask_source, args.max_dz)
+    ndv_out = -9999.0
+    rio.write_raster(outprefix + xyz_shift_str_cum_fn + '_align_diff.tif', after['diff'].filled(ndv_out), after['gt'], ndv_out)
+    rio.write_raster(outprefix + xyz_shift_str_cum_fn + '_align_diff_filt.tif', after['diff_filt'].filled(ndv_out),
+                     after['gt'], ndv_out)
+    rio.write_raster(outprefix + '_orig_diff.tif', before['diff'].filled(ndv_out), before['gt'], ndv_out)
+    res_ref = float((ref.gt[1] + abs(ref.gt[5])) / 2.0)
+    res_src = float((src.gt[1] + abs(src.gt[5])) / 2.0)
+    g = after['gt']
+    h, w = after['diff'].shape
+    # json schema of dem_align.py:540-564 (consumed by dem_align_post.py:133-147); lon/lat need PROJ -> None
     info = {'src_fn': src_dem_fn, 'ref_fn': ref_dem_fn, 'align_fn': align_fn,
-            'shift': {'dx': dx_total, 'dy': dy_total, 'dz': dz_total, 'dm': dm_total},
+            'res': {'src': res_src, 'ref': res_ref, 'coreg': float(g[1])},
+            'center_coord': {'lon': None, 'lat': None, 'x': g[0] + 0.5 * w * g[1], 'y': g[3] + 0.5 * h * g[5]},
+            'shift': {'dx': dx_total, 'dy': dy_total, 'dz': float(dz_total), 'dm': dm_total},
+            'before': before['stats'], 'before_filt': before['stats_filt'],
+            'after': after['stats'], 'after_filt': after['stats_filt'],
             'n_iter': out['n_iter']}
     json_fn = outprefix + xyz_shift_str_cum_fn + '_align_stats.json'
     with open(json_fn, 'w') as f:

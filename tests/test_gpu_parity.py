@@ -504,4 +504,28 @@ def test_cli_end_to_end(cuda, tmp_path):
     assert np.array_equal(out['array'], oo['src_align'].array)
     assert abs(out['gt'][0] - oo['src_align'].gt[0]) < 1e-6 and abs(out['gt'][3] - oo['src_align'].gt[3]) < 1e-6
     assert "_nuth_x%+0.2f_y%+0.2f_z%+0.2f" % (oo['dx'], oo['dy'], oo['dz']) in info['align_fn']
-    assert json.load(open(info['align_fn'].replace('_align.tif', '_align_stats.json')))['n_iter'] == oo['n_iter']
+    js = json.load(open(info['align_fn'].replace('_align.tif', '_align_stats.json')))
+    assert js['n_iter'] == oo['n_iter']
+    # final-difference statistics (dem_align.py:366-392) vs the oracle's get_stats_dict(full=True)
+    oo = oda.align(_ods(p, 'ref'), _ods(p, 'src'), final_stats=True)
+    for key, okey in (('after', 'diff_align_stats'), ('after_filt', 'diff_align_filt_stats')):
+        assert set(js[key]) == set(oo[okey])
+        assert js[key]['count'] == oo[okey]['count'], key
+        for k in ('min', 'max', 'ptp', 'mean', 'std', 'nmad', 'med', 'median', 'p16', 'p84', 'spread', 'mode'):
+            assert abs(js[key][k] - oo[okey][k]) <= 1e-5 * max(1.0, abs(oo[okey][k])), (key, k, js[key][k], oo[okey][k])
+    assert set(js) >= {'src_fn', 'ref_fn', 'align_fn', 'res', 'center_coord', 'shift', 'before', 'before_filt', 'after', 'after_filt'}
+    d = rio.read_array(info['align_fn'].replace('_align.tif', '_align_diff.tif'))
+    dm = np.ma.masked_values(d['array'], -9999.0)
+    assert dm.count() == oo['diff_align_stats']['count']
+
+
+def test_compute_diff(cuda, tmp_path):
+    from demcoreg_b200 import compute_diff
+    from oracle import pygeotools_restated as pg
+    p = _pair(n=300, nodata_frac=0.02)
+    gt_s = _shifted_gt(p['gt'], 47.0, -13.0)
+    diff, gt = compute_diff.compute_diff(_gds(p, 'ref'), _gds(p, 'src', gt_s))
+    rc, sc = pg.memwarp_multi([_ods(p, 'ref'), _ods(p, 'src', gt_s)])
+    want = pg.ds_getma(sc) - pg.ds_getma(rc)
+    assert np.array_equal(np.ma.getmaskarray(diff), np.ma.getmaskarray(want))
+    assert np.array_equal(diff.compressed(), want.compressed()) and gt == tuple(sc.gt)
