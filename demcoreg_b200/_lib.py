@@ -44,6 +44,7 @@ class FrontArgs(C.Structure):
         ("row_begin", C.c_int32), ("row_end", C.c_int32),
         ("ref_row0", C.c_int32), ("ref_nrows", C.c_int32), ("src_row0", C.c_int32), ("src_nrows", C.c_int32),
         ("smask_row0", C.c_int32), ("smask_nrows", C.c_int32),
+        ("src_ndz", C.c_int32), ("_pad2", C.c_int32), ("src_dz", C.c_float * 16),
     ]
 
 
@@ -98,6 +99,7 @@ SYMBOLS = {
                                  C.c_size_t, _P]),
     "dcr_fit_nuth": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]),
     "dcr_apply_z_shift": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_float, _P, _P]),
+    "dcr_apply_z_shift_seq": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.c_double, C.POINTER(C.c_float), C.c_int, _P]),
     "dcr_iteration_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "dcr_band_nphases": (C.c_int, []),
     "dcr_band_phase": (C.c_int, [C.POINTER(FrontArgs), C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_size_t,

@@ -171,6 +171,9 @@ struct DevGeom {
     int has_ndv;
     int row0;  // global index of the first row held in memory (row-band mode; 0 = whole raster)
     int row1;  // one past the last row held in memory
+    int ndz;          // deferred apply_z_shift steps (source raster only)
+    float dz[16];
+    float zlo, zhi;   // float32 interval of numpy masked_values(|x - ndv| <= tol) for the z-shift masking
 };
 
 static DevGeom make_devgeom(const dcr_warp_geom& g, int hs, int ws, long long stride, double ndv, int has_ndv) {
@@ -181,6 +184,9 @@ static DevGeom make_devgeom(const dcr_warp_geom& g, int hs, int ws, long long st
     d.hs = hs; d.ws = ws; d.stride = stride; d.ndv = (float)ndv; d.has_ndv = has_ndv;
     d.row0 = 0;
     d.row1 = hs;
+    d.ndz = 0;
+    d.zlo = d.zhi = 0.f;
+    for (int k = 0; k < 16; ++k) d.dz[k] = 0.f;
     return d;
 }
 
@@ -462,7 +468,7 @@ __device__ __forceinline__ float warp_px_tile(const float* t, int r0, int c0, co
 
 // Stage an R x C footprint whose top-left source pixel is (r_base, c_base) into shared memory: one warp per
 // tile row, two rows (10 loads) in flight per lane, column predicates hoisted out of the row loop.
-template <int R, int C>
+template <int R, int C, bool HAS_DZ>
 __device__ __forceinline__ void stage_tile(const float* __restrict__ src, const DevGeom& g, int r_base, int c_base,
                                            float* __restrict__ tile, int tid) {
     const int lane = tid & 31, wrp = tid >> 5;
@@ -481,6 +487,7 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ src, const 
     const float* colp = src + (c_base + lane);
     const bool has_ndv = g.has_ndv != 0;
     const float ndv = g.ndv;
+    const int ndz = g.ndz;
     for (int r = wrp; r < R; r += 16) {
         float v[2][NQ];
 #pragma unroll
@@ -497,8 +504,13 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ src, const 
             if (rr < R) {
                 float* trow = tile + rr * C + lane;
 #pragma unroll
-                for (int q = 0; q < NQ; ++q)
-                    if (smask >> q & 1u) trow[q * 32] = (has_ndv && v[u][q] == ndv) ? qnan : v[u][q];
+                for (int q = 0; q < NQ; ++q) {
+                    float x = v[u][q];
+                    // deferred z shifts: a = b_getma(band); a = a + dz; filled() -- one float32 add per pending step
+                    if (HAS_DZ)
+                        for (int k = 0; k < ndz; ++k) x = (x >= g.zlo && x <= g.zhi) ? ndv : x + g.dz[k];
+                    if (smask >> q & 1u) trow[q * 32] = (has_ndv && x == ndv) ? qnan : x;
+                }
             }
         }
     }
@@ -517,8 +529,9 @@ __global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ F
     if (tid < 3) s_cnt[tid] = 0ull;
 
     // ---- stage the two source footprints (nodata / out-of-bounds -> NaN)
-    stage_tile<F_SRC_R, F_SRC_C>(p.src, p.sg, ti0 - 2 + p.sg.iy0, tj0 - 2 + p.sg.ix0, s_src, tid);
-    stage_tile<F_REF_R, F_REF_C>(p.ref, p.rg, ti0 - 1 + p.rg.iy0, tj0 - 1 + p.rg.ix0, s_ref, tid);
+    if (p.sg.ndz) stage_tile<F_SRC_R, F_SRC_C, true>(p.src, p.sg, ti0 - 2 + p.sg.iy0, tj0 - 2 + p.sg.ix0, s_src, tid);
+    else stage_tile<F_SRC_R, F_SRC_C, false>(p.src, p.sg, ti0 - 2 + p.sg.iy0, tj0 - 2 + p.sg.ix0, s_src, tid);
+    stage_tile<F_REF_R, F_REF_C, false>(p.ref, p.rg, ti0 - 1 + p.rg.iy0, tj0 - 1 + p.rg.ix0, s_ref, tid);
     if (p.smask) {
         // nearest-neighbour sample of the world-fixed mask; all 16 byte loads of a thread are issued before their
         // first use (a dependent load per pixel inside the main pass cost ~600 cycles of latency per row)
@@ -748,6 +761,10 @@ int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cuda
     p.ref_w = a->ref_w;
     p.src_w = a->src_w;
     p.counters = counters;
+    DCR_ARG(a->src_ndz >= 0 && a->src_ndz <= 16, "0 <= src_ndz <= 16");
+    p.sg.ndz = a->src_ndz;
+    for (int k = 0; k < a->src_ndz; ++k) p.sg.dz[k] = a->src_dz[k];
+    gm_bounds(a->src_desc.ndv, &p.sg.zlo, &p.sg.zhi);
     // row-band mode: this launch computes output rows [row_begin, row_end) only, from rasters of which only
     // the rows [row0, row0 + nrows) are in memory (the band plus its halo); outputs are band-local.
     p.row_begin = 0;

@@ -752,6 +752,35 @@ extern "C" int dcr_apply_z_shift(float* band, int h, int w, int64_t stride, doub
     return 0;
 }
 
+// several deferred scalar shifts in ONE read-modify-write pass (same ordered float32 adds as separate calls)
+struct ZSeq { float dz[16]; int n; };
+__global__ void __launch_bounds__(256) zshift_seq_kernel(float* __restrict__ band, int h, int w, long long stride, double ndv,
+                                                         double tol, float ndv32, ZSeq z) {
+    const long long n = (long long)h * w;
+    const long long step = (long long)gridDim.x * 256;
+    for (long long k = (long long)blockIdx.x * 256 + threadIdx.x; k < n; k += step) {
+        const int i = (int)(k / w), j = (int)(k - (long long)i * w);
+        float* p = band + (long long)i * stride + j;
+        float v = *p;
+        for (int q = 0; q < z.n; ++q) v = (fabs((double)v - ndv) <= tol) ? ndv32 : v + z.dz[q];
+        *p = v;
+    }
+}
+
+extern "C" int dcr_apply_z_shift_seq(float* band, int h, int w, int64_t stride, double ndv, const float* dz, int n,
+                                     void* stream) {
+    DCR_ARG(band && dz, "null pointer");
+    DCR_ARG(h > 0 && w > 0, "empty raster");
+    DCR_ARG(n >= 1 && n <= 16, "1 <= n <= 16");
+    ZSeq z;
+    z.n = n;
+    for (int k = 0; k < 16; ++k) z.dz[k] = k < n ? dz[k] : 0.f;
+    const double tol = 1e-8 + 1e-5 * fabs(ndv);
+    zshift_seq_kernel<<<dcr_num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(band, h, w, stride, ndv, tol, (float)ndv, z);
+    DCR_LAUNCH_OK("zshift_seq_kernel");
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // one chained iteration
 // ------------------------------------------------------------------------------------------

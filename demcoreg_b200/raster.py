@@ -40,19 +40,52 @@ class Raster(object):
             data = t.to(device or "cuda", non_blocking=False)
         if data.dtype != torch.float32 or data.dim() != 2 or not data.is_cuda:
             raise ValueError("Raster needs a 2-D float32 CUDA tensor or numpy array")
-        self.data = data.contiguous()
+        self._data = data.contiguous()
+        # scalar z shifts not yet written to the band (coreglib.apply_z_shift defers them: the next iteration's
+        # front kernel applies them while loading, bit-identically; any other reader goes through `.data`)
+        self.pending_dz = []
         self.gt = tuple(float(g) for g in gt)
         self.ndv = None if ndv is None else float(ndv)
         self.proj = proj
 
+    @property
+    def data(self):
+        """The band tensor with every deferred z shift applied."""
+        self.materialize()
+        return self._data
+
+    @data.setter
+    def data(self, t):
+        self._data = t
+        self.pending_dz = []
+
+    def materialize(self):
+        if self.pending_dz:
+            import ctypes as C
+            torch = _lib.require_cuda()
+            L = _lib.lib()
+            h, w = int(self._data.shape[0]), int(self._data.shape[1])
+            while self.pending_dz:
+                chunk, self.pending_dz = self.pending_dz[:16], self.pending_dz[16:]
+                if len(chunk) == 1:   # the common case: vectorised single-shift kernel
+                    _lib.check(L.dcr_apply_z_shift(C.c_void_p(self._data.data_ptr()), h, w, self._data.stride(0),
+                                                   self.ndv if self.ndv is not None else 0.0, float(chunk[0]), None,
+                                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                    continue
+                arr = (C.c_float * len(chunk))(*chunk)
+                _lib.check(L.dcr_apply_z_shift_seq(C.c_void_p(self._data.data_ptr()), h, w, self._data.stride(0),
+                                                   self.ndv if self.ndv is not None else 0.0, arr, len(chunk),
+                                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            self.pending_dz = []
+
     # --- gdal.Dataset duck typing -------------------------------------------------------
     @property
     def RasterXSize(self):
-        return int(self.data.shape[1])
+        return int(self._data.shape[1])
 
     @property
     def RasterYSize(self):
-        return int(self.data.shape[0])
+        return int(self._data.shape[0])
 
     def GetGeoTransform(self):
         return self.gt
@@ -68,7 +101,9 @@ class Raster(object):
 
     def copy(self):
         """``iolib.mem_drv.CreateCopy('', ds, 0)``"""
-        return Raster(self.data.clone(), self.gt, self.ndv, self.proj)
+        r = Raster(self._data.clone(), self.gt, self.ndv, self.proj)
+        r.pending_dz = list(self.pending_dz)
+        return r
 
     def numpy(self):
         return self.data.cpu().numpy()

@@ -110,6 +110,12 @@ typedef struct dcr_front_args {
      * band-local ((row_end - row_begin) x w).  -5 is returned when a halo is too small for the current shift. */
     int32_t row_begin, row_end;
     int32_t ref_row0, ref_nrows, src_row0, src_nrows, smask_row0, smask_nrows;
+    /* deferred apply_z_shift (coreglib.py:42-55): up to 16 scalar shifts of the SOURCE band that have not been written
+     * back yet; the kernel applies them, in order and in float32, to every source pixel it loads (pixels within numpy's
+     * masked_values tolerance of ndv become ndv) -- bit-identical to running dcr_apply_z_shift first, without the extra
+     * read-modify-write pass over the raster. */
+    int32_t src_ndz, _pad2;
+    float src_dz[16];
 } dcr_front_args;
 int dcr_warp_diff_horn(const dcr_front_args* args, void* stream);
 
@@ -192,6 +198,8 @@ int dcr_fit_nuth(const double* bin_centers, const double* bin_med, int n, double
  * numpy masked_values tolerance of ndv become exactly ndv.  dz_grid (device, h*w) may replace the scalar. */
 int dcr_apply_z_shift(float* band, int h, int w, int64_t stride, double ndv, float dz, const float* dz_grid,
                       void* stream);
+/* n (<= 16) successive scalar apply_z_shift calls in one pass: the same ordered float32 adds (dz: host array). */
+int dcr_apply_z_shift_seq(float* band, int h, int w, int64_t stride, double ndv, const float* dz, int n, void* stream);
 
 /* ---- one full Nuth-Kaab iteration (device-resident inputs -> dx,dy,dz on the host) --------------
  * dem_align.compute_offset(mode='nuth') <- dem_align.py:62-172 and coreglib.compute_offset_nuth

@@ -529,3 +529,23 @@ def test_compute_diff(cuda, tmp_path):
     want = pg.ds_getma(sc) - pg.ds_getma(rc)
     assert np.array_equal(np.ma.getmaskarray(diff), np.ma.getmaskarray(want))
     assert np.array_equal(diff.compressed(), want.compressed()) and gt == tuple(sc.gt)
+
+
+def test_deferred_z_shift_equals_eager(cuda):
+    """dcr_front_args.src_dz (z shifts applied while the front kernel loads the source) == dcr_apply_z_shift first."""
+    from demcoreg_b200 import engine
+    p = _pair(n=512, nodata_frac=0.02)
+    gt_s = _shifted_gt(p['gt'], 3.4, -1.8)
+    dzs = [np.float32(-0.4375), np.float32(0.0013), np.float32(0.25)]
+    eager = _gds(p, 'src', gt_s)
+    for dz in dzs:
+        engine.apply_z_shift_inplace(eager, dz)
+    lazy = _gds(p, 'src', gt_s)
+    lazy.pending_dz = [float(d) for d in dzs]
+    r1, _, b1 = engine.nuth_iteration(_gds(p, 'ref'), eager, keep_warped=True)
+    r2, _, b2 = engine.nuth_iteration(_gds(p, 'ref'), lazy, keep_warped=True)
+    assert len(lazy.pending_dz) == 3   # still deferred
+    assert np.array_equal(b1.src_w.cpu().numpy(), b2.src_w.cpu().numpy())
+    assert np.array_equal(b1.maskbits.cpu().numpy(), b2.maskbits.cpu().numpy())
+    assert (r1.dx, r1.dy, r1.dz) == (r2.dx, r2.dy, r2.dz)
+    assert np.array_equal(lazy.numpy(), eager.numpy()) and lazy.pending_dz == []
