@@ -186,6 +186,7 @@ extern "C" int dcr_select_quantiles(const float* x, const uint8_t* mask, uint32_
     BselState* bst = ws.take<BselState>(16);
     void* scratch = ws.take<char>(dcr_bsel_scratch_bytes(n));
     SelView v;
+    memset(&v, 0, sizeof(v));
     v.x = x; v.m = mask; v.reject = reject; v.transform = transform; v.center_ptr = nullptr; v.center_imm = center;
     v.n = n; v.n_ptr = nullptr;
     // fast path: one streaming pass per quantile (dcr_bsel.cu) ...
@@ -230,6 +231,7 @@ extern "C" int dcr_select_quantiles_radix(const float* x, const uint8_t* mask, u
     unsigned* hist = ws.take<unsigned>(DCR_SEL_HIST_WORDS);
     SelState* st = ws.take<SelState>(16);
     SelView v;
+    memset(&v, 0, sizeof(v));
     v.x = x; v.m = mask; v.reject = reject; v.transform = transform; v.center_ptr = nullptr; v.center_imm = center;
     v.n = n; v.n_ptr = nullptr;
     for (int k = 0; k < nq; ++k) {
