@@ -293,10 +293,13 @@ def main():
     quiet = contextlib.redirect_stdout(io.StringIO())
 
     def step(src, profile=False):
-        r, grid, bufs = engine.nuth_iteration(ref, src, ms, profile=profile)
+        # exactly what demcoreg_b200.dem_align.align does per iteration: compute_offset (+ the z shift applied on the
+        # device in the same kernel chain), then apply_xy_shift on the host
+        r, grid, bufs = engine.nuth_iteration(ref, src, ms, profile=profile, apply_z=True)
         with quiet:
             coreglib.apply_xy_shift(src, r.dx, r.dy, createcopy=False)
-            coreglib.apply_z_shift(src, np.float32(r.dz), createcopy=False)
+            if not r.z_applied:
+                coreglib.apply_z_shift(src, np.float32(r.dz), createcopy=False)
         return r, grid
 
     def barrier():

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libdemcoreg_b200.so")
 NBINS = 360
 M_BASE, M_MAXDZ, M_MAD, M_SLOPE, M_ASPECT = 0x01, 0x02, 0x04, 0x08, 0x10
 M_DIFF = M_BASE | M_MAXDZ | M_MAD | M_SLOPE
-ITER_REMOVE_OUTLIERS, ITER_PROFILE, ITER_RADIX_ONLY = 1, 2, 4
+ITER_REMOVE_OUTLIERS, ITER_PROFILE, ITER_RADIX_ONLY, ITER_APPLY_Z = 1, 2, 4, 8
 
 
 class RasterDesc(C.Structure):
@@ -62,7 +62,7 @@ class IterResult(C.Structure):
                 ("dz_med", C.c_float), ("med_dh", C.c_float), ("med_slope", C.c_float), ("c_seed", C.c_float),
                 ("nuth", NuthStats), ("fit", C.c_double * 3), ("dx", C.c_double), ("dy", C.c_double),
                 ("dz", C.c_double), ("stage_ms", C.c_float * 8), ("select_engine", C.c_int32),
-                ("_pad", C.c_int32)]
+                ("z_applied", C.c_int32)]
 
 
 # every symbol include/demcoreg_b200.h declares: name -> (restype, argtypes)

@@ -288,12 +288,11 @@ __global__ void __launch_bounds__(256) bin_find_kernel(NuthDev* nd, unsigned* __
 }
 
 __global__ void nuth_count_final_kernel(NuthDev* nd) {
-    // n_final = sum of the bin counts + in-range samples outside [0,360] (none for gdaldem aspect)
-    if (threadIdx.x == 0) {
-        unsigned long long t = 0;
-        for (int k = 0; k < NB; ++k) t += nd->bin_count[k];
-        nd->n_final = t;
-    }
+    // n_final = sum of the bin counts + in-range samples outside [0,360] (none for gdaldem aspect); one warp
+    unsigned long long t = 0;
+    for (int k = threadIdx.x; k < NB; k += 32) t += nd->bin_count[k];
+    t = dcr_warp_sum_u64(t);
+    if (threadIdx.x == 0) nd->n_final = t;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -505,20 +504,30 @@ __global__ void __launch_bounds__(256) fb_findB_kernel(NuthDev* nd, unsigned* __
 
 __global__ void __launch_bounds__(256) fb_passC_kernel(NuthDev* nd, const unsigned long long* __restrict__ cand,
                                                        unsigned* __restrict__ ghist) {
+    __shared__ unsigned short s_f0[NB], s_f1[NB];
     if (nd->fast_fallback) return;
+    for (int k = threadIdx.x; k < NB; k += 256) { s_f0[k] = nd->fb_cell[0][k]; s_f1[k] = nd->fb_cell[1][k]; }
+    __syncthreads();
     const unsigned ncand = nd->fast_ncand;
     unsigned* slots = ghist + FB_SLOT_OFF;
     unsigned* slotn = ghist + FB_SLOTN_OFF;
-    for (unsigned i = blockIdx.x * 256 + threadIdx.x; i < ncand; i += gridDim.x * 256) {
-        const unsigned long long rec = cand[i];
-        const unsigned f = (unsigned)(rec & 0xFFFFu), b = (unsigned)((rec >> 16) & 0xFFFFu), key = (unsigned)(rec >> 32);
-        const unsigned f0 = nd->fb_cell[0][b], f1 = nd->fb_cell[1][b];
-        if (f == f0) {
-            const unsigned pos = atomicAdd(&slotn[b * 2], 1u);
-            if (pos < FB_SLOT) slots[(b * 2) * FB_SLOT + pos] = key;
-        } else if (f == f1) {
-            const unsigned pos = atomicAdd(&slotn[b * 2 + 1], 1u);
-            if (pos < FB_SLOT) slots[(b * 2 + 1) * FB_SLOT + pos] = key;
+    const unsigned step = gridDim.x * 256;
+    for (unsigned i0 = blockIdx.x * 256 + threadIdx.x; i0 < ncand; i0 += 4 * step) {
+        unsigned long long rec[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) rec[u] = (i0 + u * step < ncand) ? __ldg(cand + i0 + u * step) : ~0ull;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i0 + u * step >= ncand) break;
+            const unsigned f = (unsigned)(rec[u] & 0xFFFFu), b = (unsigned)((rec[u] >> 16) & 0xFFFFu), key = (unsigned)(rec[u] >> 32);
+            const unsigned f0 = s_f0[b], f1 = s_f1[b];
+            if (f == f0) {
+                const unsigned pos = atomicAdd(&slotn[b * 2], 1u);
+                if (pos < FB_SLOT) slots[(b * 2) * FB_SLOT + pos] = key;
+            } else if (f == f1) {
+                const unsigned pos = atomicAdd(&slotn[b * 2 + 1], 1u);
+                if (pos < FB_SLOT) slots[(b * 2 + 1) * FB_SLOT + pos] = key;
+            }
         }
     }
 }
@@ -620,7 +629,7 @@ static int nuth_bins_fast_enqueue(long long n, const NuthWs& w, cudaStream_t s) 
     fb_findA_kernel<<<(NB + 127) / 128, 128, 0, s>>>(w.nd, w.ghist);
     fb_passB_kernel<<<nsm * 16, 256, 0, s>>>(w.y, w.bin, n, w.nd, w.ghist, w.cand, w.cand_cap);  // small CTAs: the 4 % candidates of a CTA must fit its staging buffer
     fb_findB_kernel<<<(NB + 7) / 8, 256, 0, s>>>(w.nd, w.ghist, w.cand_cap);
-    fb_passC_kernel<<<nsm * 2, 256, 0, s>>>(w.nd, w.cand, w.ghist);
+    fb_passC_kernel<<<nsm * 8, 256, 0, s>>>(w.nd, w.cand, w.ghist);
     fb_passD_kernel<<<(NB + 7) / 8, 256, 0, s>>>(w.nd, w.ghist);
     nuth_count_final_kernel<<<1, 32, 0, s>>>(w.nd);
     DCR_LAUNCH_OK("fast bin kernels");
@@ -897,6 +906,47 @@ static size_t iter_ws_bytes(long long n, int grid) {
 extern "C" size_t dcr_iteration_workspace_bytes(int64_t n) { return iter_ws_bytes(n, dcr_num_sms() * 8); }
 
 
+// apply_z_shift (coreglib.py:42-55) with dz taken from the device-resident result of THIS iteration
+// (dz = -median, dem_align.py:115, 172), enqueued before the host even sees the result: the 0.1 ms
+// read-modify-write pass overlaps the host's fit / bookkeeping instead of sitting between two iterations.
+// Skipped when a one-pass selection asked for the radix fallback (the rerun applies it).
+__global__ void __launch_bounds__(256) zshift_dev_kernel(float* __restrict__ band, int h, int w, long long stride, double ndv,
+                                                         double tol, float ndv32, const IterDev* d, int use_bsel) {
+    if (use_bsel) {
+        bool fb = false;
+        for (int k = 0; k < 5; ++k) fb = fb || (d->bsel[k].fallback != 0);
+        if (fb) return;
+    }
+    const float med = d->stride > 1 ? d->selres[3] : d->selres[2];
+    if (isnan(med)) return;
+    const float dz = -med;
+    const long long n = (long long)h * w;
+    const long long step = (long long)gridDim.x * 256;
+    if (stride == w && DCR_AL16(band)) {
+        const long long n4 = n >> 2;
+        float4* b4 = reinterpret_cast<float4*>(band);
+        for (long long k = (long long)blockIdx.x * 256 + threadIdx.x; k < n4; k += step) {
+            float4 v = b4[k];
+            v.x = (fabs((double)v.x - ndv) <= tol) ? ndv32 : v.x + dz;
+            v.y = (fabs((double)v.y - ndv) <= tol) ? ndv32 : v.y + dz;
+            v.z = (fabs((double)v.z - ndv) <= tol) ? ndv32 : v.z + dz;
+            v.w = (fabs((double)v.w - ndv) <= tol) ? ndv32 : v.w + dz;
+            b4[k] = v;
+        }
+        for (long long k = (n4 << 2) + (long long)blockIdx.x * 256 + threadIdx.x; k < n; k += step) {
+            const float v = band[k];
+            band[k] = (fabs((double)v - ndv) <= tol) ? ndv32 : v + dz;
+        }
+        return;
+    }
+    for (long long k = (long long)blockIdx.x * 256 + threadIdx.x; k < n; k += step) {
+        const int i = (int)(k / w), j = (int)(k - (long long)i * w);
+        float* p = band + (long long)i * stride + j;
+        const float v = *p;
+        *p = (fabs((double)v - ndv) <= tol) ? ndv32 : v + dz;
+    }
+}
+
 __global__ void sel_publish_kernel(IterDev* d, int k, int use_bsel) {
     if (threadIdx.x == 0) d->selres[k] = use_bsel ? d->bsel[k].result : d->sel[k].result;
 }
@@ -923,7 +973,7 @@ static int iter_select(const SelView& v, int k, const IterWs& w, long long n, in
 }
 
 static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, int use_bsel, const IterWs& w, int grid,
-                             cudaStream_t s, cudaEvent_t* ev, int fast_bins) {
+                             cudaStream_t s, cudaEvent_t* ev, int fast_bins, int apply_z) {
     const long long n = (long long)front->h * front->w;
     const long long nch = (n + MU_CHUNK - 1) / MU_CHUNK;
     IterDev* d = w.d;
@@ -975,6 +1025,7 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
         return rc;
     DCR_LAUNCH_OK("iteration kernels");
     STAGE_MARK(6);
+    (void)apply_z;
 #undef STAGE_MARK
     return 0;
 }
@@ -1064,11 +1115,25 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_it
     int engine_used = (flags & DCR_ITER_RADIX_ONLY) ? 0 : 1;
     for (int attempt = 0; attempt < 2; ++attempt) {
         int rc = iteration_enqueue(front, remove_outliers, engine_used, w, grid, s, prof ? ev : nullptr,
-                                   (flags & DCR_ITER_RADIX_ONLY) ? 0 : 1);
+                                   (flags & DCR_ITER_RADIX_ONLY) ? 0 : 1, (flags & DCR_ITER_APPLY_Z) ? 1 : 0);
         if (rc) return rc;
         DCR_CUDA_OK(cudaMemcpyAsync(hd, d, sizeof(IterDev), cudaMemcpyDeviceToHost, s));
         if (prof) DCR_CUDA_OK(cudaEventRecord(ev[7], s));
-        DCR_CUDA_OK(cudaStreamSynchronize(s));
+        if (flags & DCR_ITER_APPLY_Z) {
+            // the result copy is already queued: wait for IT (event), not for the z-shift pass enqueued behind it --
+            // the 0.1 ms read-modify-write of the source band then overlaps the host's fit and bookkeeping
+            static thread_local cudaEvent_t ev_copy = nullptr;
+            if (!ev_copy) DCR_CUDA_OK(cudaEventCreateWithFlags(&ev_copy, cudaEventDisableTiming));
+            DCR_CUDA_OK(cudaEventRecord(ev_copy, s));
+            const double zn = front->src_desc.ndv;
+            zshift_dev_kernel<<<dcr_num_sms() * 8, 256, 0, s>>>(const_cast<float*>(front->src), front->src_desc.height,
+                                                                 front->src_desc.width, front->src_stride, zn,
+                                                                 1e-8 + 1e-5 * fabs(zn), (float)zn, d, engine_used);
+            DCR_LAUNCH_OK("zshift_dev_kernel");
+            DCR_CUDA_OK(cudaEventSynchronize(ev_copy));
+        } else {
+            DCR_CUDA_OK(cudaStreamSynchronize(s));
+        }
         if (hd->nuth.fast_fallback && getenv("DCR_DEBUG"))
             fprintf(stderr, "[dcr] fast bin path declined: ncand=%u scale=%g rmin=%g rmax=%g\n", hd->nuth.fast_ncand,
                     hd->nuth.fast_scale, hd->nuth.rmin, hd->nuth.rmax);
@@ -1099,7 +1164,11 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_it
     memset(out, 0, sizeof(*out));
     if (prof)
         for (int k = 0; k < 7; ++k) DCR_CUDA_OK(cudaEventElapsedTime(&out->stage_ms[k], ev[k], ev[k + 1]));
-    return iter_finalize(hd, engine_used, out);
+    {
+        const int rcf = iter_finalize(hd, engine_used, out);
+        out->z_applied = ((flags & DCR_ITER_APPLY_Z) && !isnan(out->dz_med)) ? 1 : 0;
+        return rcf;
+    }
 }
 
 // ------------------------------------------------------------------------------------------

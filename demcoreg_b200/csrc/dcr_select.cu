@@ -355,12 +355,20 @@ __global__ void __launch_bounds__(1024) chunk_scan_kernel(const unsigned* __rest
     __shared__ long long s_carry;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
-    for (long long b = 0; b < nchunks; b += 1024) {
-        const long long i = b + threadIdx.x;
-        unsigned v = i < nchunks ? cnt[i] : 0u;
+    // 16 chunk counts per thread and round (16384 per round): one block scan + two barriers per round instead of per 1024
+    for (long long b = 0; b < nchunks; b += 16384) {
+        const long long i0 = b + (long long)threadIdx.x * 16;
+        unsigned v[16], sum = 0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) { v[q] = (i0 + q < nchunks) ? __ldg(cnt + i0 + q) : 0u; sum += v[q]; }
         unsigned total;
-        unsigned ex = dcr_block_excl_scan(v, s_scratch, &total);
-        if (i < nchunks) off[i] = s_carry + ex;
+        unsigned ex = dcr_block_excl_scan(sum, s_scratch, &total);
+        long long run = s_carry + ex;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            if (i0 + q < nchunks) off[i0 + q] = run;
+            run += v[q];
+        }
         __syncthreads();
         if (threadIdx.x == 0) s_carry += total;
         __syncthreads();

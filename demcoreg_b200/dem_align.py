@@ -82,7 +82,7 @@ _EXIT_MSG = {
 
 def compute_offset(ref_dem_ds, src_dem_ds, src_dem_fn, mode='nuth', remove_outliers=True, max_offset=100,
                    max_dz=100, slope_lim=(0.1, 40), mask_list=['glaciers', ], plot=True, mask_source=None,
-                   return_static_mask=True, _details=None):
+                   return_static_mask=True, _details=None, _apply_z=False):
     """Reference ``dem_align.py:62-172`` -> ``(dx, dy, dz, static_mask, fig)``.
 
     ``mask_source`` (extension): a ``MaskSource`` standing in for ``dem_mask.get_mask``; with it
@@ -93,7 +93,8 @@ def compute_offset(ref_dem_ds, src_dem_ds, src_dem_fn, mode='nuth', remove_outli
         get_mask(None, mask_list)
     fig = None
     if mode == 'nuth':
-        res, grid, bufs = engine.nuth_iteration(ref_dem_ds, src_dem_ds, mask_source, remove_outliers, max_dz, slope_lim)
+        res, grid, bufs = engine.nuth_iteration(ref_dem_ds, src_dem_ds, mask_source, remove_outliers, max_dz, slope_lim,
+                                                apply_z=_apply_z)
         if res.status in _EXIT_MSG:
             sys.exit(_EXIT_MSG[res.status])
         if _details is not None:
@@ -175,10 +176,12 @@ def align(ref_dem_ds, src_dem_ds, mode='nuth', mask_source=None, tol=0.02, max_o
     with sink:
         while True:
             print("*** Iteration %i ***" % n)
-            det = {} if records is not None else None
+            det = {}
+            # Nuth mode: the z shift of this iteration is applied on the device inside the same kernel chain
             dx, dy, dz, static_mask, fig = compute_offset(ref_dem_ds, src_dem_ds_align, None, mode, max_offset=max_offset,
                                                           mask_list=[], max_dz=max_dz, slope_lim=slope_lim, plot=True,
-                                                          mask_source=mask_source, return_static_mask=False, _details=det)
+                                                          mask_source=mask_source, return_static_mask=False, _details=det,
+                                                          _apply_z=(mode == 'nuth'))
             xyz_shift_str_iter = "dx=%+0.2fm, dy=%+0.2fm, dz=%+0.2fm" % (dx, dy, dz)
             print("Incremental offset: %s" % xyz_shift_str_iter)
             dx_total += dx
@@ -187,7 +190,10 @@ def align(ref_dem_ds, src_dem_ds, mode='nuth', mask_source=None, tol=0.02, max_o
             xyz_shift_str_cum = "dx=%+0.2fm, dy=%+0.2fm, dz=%+0.2fm" % (dx_total, dy_total, dz_total)
             print("Cumulative offset: %s" % xyz_shift_str_cum)
             src_dem_ds_align = coreglib.apply_xy_shift(src_dem_ds_align, dx, dy, createcopy=False)
-            src_dem_ds_align = coreglib.apply_z_shift(src_dem_ds_align, dz, createcopy=False)
+            if 'result' in det and det['result'].z_applied:
+                print("Z shift offset: ", dz)
+            else:
+                src_dem_ds_align = coreglib.apply_z_shift(src_dem_ds_align, dz, createcopy=False)
             iters.append(dict(n=n, dx=float(dx), dy=float(dy), dz=float(dz)))
             if records is not None:
                 records.append(det)

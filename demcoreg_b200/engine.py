@@ -91,21 +91,25 @@ def make_front_args(ref, src, mask_source, max_dz, use_max_dz, slope_lim, keep_w
 
 
 def nuth_iteration(ref, src, mask_source=None, remove_outliers=True, max_dz=100, slope_lim=(0.1, 40),
-                   keep_warped=False, bufs=None, profile=False, radix_only=False):
+                   keep_warped=False, bufs=None, profile=False, radix_only=False, apply_z=False):
     """One full Nuth-Kaab iteration on the device (``dcr_nuth_iteration``).
 
     Returns ``(IterResult, Grid, IterBuffers)``; ``IterResult.dx/dy/dz`` is what
-    ``dem_align.compute_offset`` returns (reference ``dem_align.py:172``).
+    ``dem_align.compute_offset`` returns (reference ``dem_align.py:172``).  ``apply_z=True`` additionally runs
+    ``coreglib.apply_z_shift(src, dz)`` on the device before returning (``IterResult.z_applied``); the caller must
+    then not apply ``dz`` again.
     """
     torch = _lib.require_cuda()
     L = _lib.lib()
+    if apply_z:
+        src.materialize()   # the device-side z shift writes the band itself: no deferred shifts may be pending
     a, grid, bufs = make_front_args(ref, src, mask_source, max_dz, remove_outliers, slope_lim, keep_warped, bufs=bufs)
     n = a.h * a.w
     nbytes = L.dcr_iteration_workspace_bytes(n)
     ws = workspace(nbytes)
     res = _lib.IterResult()
     flags = (_lib.ITER_REMOVE_OUTLIERS if remove_outliers else 0) | (_lib.ITER_PROFILE if profile else 0) \
-        | (_lib.ITER_RADIX_ONLY if radix_only else 0)
+        | (_lib.ITER_RADIX_ONLY if radix_only else 0) | (_lib.ITER_APPLY_Z if apply_z else 0)
     _lib.check(L.dcr_nuth_iteration(C.byref(a), flags, C.byref(res),
                                     C.c_void_p(ws.data_ptr()), ws.numel(), _stream_ptr(torch)))
     return res, grid, bufs

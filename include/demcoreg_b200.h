@@ -226,11 +226,13 @@ typedef struct dcr_iter_result {
                                     2 mask update+scan+subsample, 3 med_dh/dz/med_slope selects, 4 y/bin prepare+moments,
                                     5 bin count+median passes, 6 device->host copy */
     int32_t select_engine;       /* 1: one-pass sample-bracket selects verified ok; 0: 3-pass radix selects (fallback) */
-    int32_t _pad;
+    int32_t z_applied;           /* DCR_ITER_APPLY_Z: the source band has already been shifted by `dz` on the device */
 } dcr_iter_result;
 #define DCR_ITER_REMOVE_OUTLIERS 1 /* flags of dcr_nuth_iteration: dem_align.py:91 remove_outliers */
 #define DCR_ITER_PROFILE 2         /* record per-stage CUDA events into stage_ms */
 #define DCR_ITER_RADIX_ONLY 4      /* skip the one-pass sample-bracket selects (tests / profiling) */
+#define DCR_ITER_APPLY_Z 8         /* also run coreglib.apply_z_shift(src, dz) on the device (front->src must be writable,
+                                      whole raster); the host must then NOT apply dz again (see z_applied) */
 size_t dcr_iteration_workspace_bytes(int64_t n);
 int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_iter_result* out /* host */,
                        void* workspace, size_t workspace_bytes, void* stream);
