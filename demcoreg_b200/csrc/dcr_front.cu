@@ -412,14 +412,14 @@ extern "C" int dcr_horn_slope_aspect(const float* dem, int h, int w, int64_t str
 // Fused front end: warp(ref), warp(src), dh, masks, Horn(slope, aspect of warped src)
 // ------------------------------------------------------------------------------------------
 #define F_TW 128
-#define F_TH 32
+#define F_TH 28
 #define F_SRC_R (F_TH + 5)
 #define F_SRC_C (F_TW + 5)
 #define F_REF_R (F_TH + 3)
 #define F_REF_C (F_TW + 3)
 #define F_SW_R (F_TH + 2)
 #define F_SW_C (F_TW + 2)
-#define F_ROWS_PER_THREAD 16
+#define F_ROWS_PER_THREAD (F_TH / 2)
 
 struct FrontParams {
     DevGeom rg, sg;
@@ -516,7 +516,7 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ src, const 
     }
 }
 
-__global__ void __launch_bounds__(256, 3) front_kernel(const __grid_constant__ FrontParams p) {
+__global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ FrontParams p) {
     extern __shared__ float smem[];
     float* s_src = smem;                                  // F_SRC_R x F_SRC_C
     float* s_ref = s_src + F_SRC_R * F_SRC_C;             // F_REF_R x F_REF_C
