@@ -30,14 +30,14 @@ FRONT_KERNEL_DRAM_BYTES_8192 = 1427290880
 # algorithmic bytes per pixel of each profiled stage (SURVEY 8d stage table)
 STAGE_INFO = [
     ("front_kernel (warp+dh+masks+Horn)", 21.0),
-    ("bsel_main_kernel x2 + sample/find/refine (median + MAD of dh)", 16.0),
-    ("mask_update+scan+compress", 6.0),
-    ("bsel_main_kernel x3 + sample/find/refine (med_dh, dz, med_slope)", 16.0),
+    ("bsel_* x2: median + MAD of dh (slope median overlapped on the side stream)", 16.0),
+    ("mad_thresholds + mask_update_kernel", 6.0),
+    ("bsel_*: med_dh (scan/compress/dz median overlapped on the side stream)", 8.0),
     ("nuth_prepare_kernel (y, bin, moments)", 13.0 + 6.0),
-    ("bin_hist_kernel x3 (bin count + median)", 12.0),
+    ("fb_pass* (bin count + exact bin medians)", 12.0),
     ("result copy", 0.0),
 ]
-KERNELS_PER_STEP = 1 + 30 + 5 + 9 + 1  # see DESIGN.md section 6 "launch count"
+KERNELS_PER_STEP = 1 + 5 * 4 + 5 + 2 + 8 + 1  # see DESIGN.md section 6 "launch count"
 
 
 def peaks():

@@ -901,7 +901,7 @@ static size_t iter_ws_bytes(long long n, int grid) {
     const long long nch = (n + MU_CHUNK - 1) / MU_CHUNK;
     return nuth_ws_bytes(n, grid) + dcr_al256(sizeof(IterDev)) + dcr_al256(DCR_SEL_HIST_WORDS * sizeof(unsigned)) +
            dcr_al256(nch * sizeof(unsigned)) + dcr_al256(nch * sizeof(long long)) +
-           dcr_al256((size_t)(n < 6000016 ? n : 6000016) * sizeof(float)) + dcr_bsel_scratch_bytes(n) + 4096;
+           dcr_al256((size_t)(n < 6000016 ? n : 6000016) * sizeof(float)) + 2 * dcr_bsel_scratch_bytes(n) + 4096;
 }
 extern "C" size_t dcr_iteration_workspace_bytes(int64_t n) { return iter_ws_bytes(n, dcr_num_sms() * 8); }
 
@@ -959,6 +959,7 @@ struct IterWs {
     float* dense;
     long long dense_cap;
     void* bsel_scratch;
+    void* bsel_scratch2;   // selections running on the side stream
     NuthWs nw;
 };
 
@@ -985,6 +986,30 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
     if (!remove_outliers) fa.use_max_dz = 0;
     if ((rc = dcr_front_launch(&fa, d->counters, s))) return rc;
 
+    // Side stream (one-pass-select path): work that does not sit on the dependency chain of the MAD filter runs
+    // concurrently -- the slope median right after the front kernel, and the strided-subsample chain (scan, stride,
+    // compress, dz median) right after the mask update -- so that their latency-bound small kernels hide behind the
+    // bandwidth-bound passes of the main stream.  Joined before the result copy.
+    static thread_local cudaStream_t s2 = nullptr;
+    static thread_local cudaEvent_t e_front = nullptr, e_mask = nullptr, e_join = nullptr;
+    const bool side = use_bsel != 0;
+    if (side && !s2) {
+        DCR_CUDA_OK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+        DCR_CUDA_OK(cudaEventCreateWithFlags(&e_front, cudaEventDisableTiming));
+        DCR_CUDA_OK(cudaEventCreateWithFlags(&e_mask, cudaEventDisableTiming));
+        DCR_CUDA_OK(cudaEventCreateWithFlags(&e_join, cudaEventDisableTiming));
+    }
+    cudaStream_t sb = side ? s2 : s;      // stream of the side work
+    IterWs wb = w;                        // side selections use their own scratch
+    if (side) wb.bsel_scratch = w.bsel_scratch2;
+    if (side) {
+        DCR_CUDA_OK(cudaEventRecord(e_front, s));
+        DCR_CUDA_OK(cudaStreamWaitEvent(s2, e_front, 0));
+        SelView vs;
+        memset(&vs, 0, sizeof(vs));
+        vs.x = front->slope; vs.m = front->maskbits; vs.reject = DCR_M_SLOPE; vs.n = n;
+        if ((rc = iter_select(vs, 4, wb, n, use_bsel, sb))) return rc;   // med_slope (coreglib.py:215)
+    }
     STAGE_MARK(1);
     SelView v;
     memset(&v, 0, sizeof(v));
@@ -998,22 +1023,28 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
     STAGE_MARK(2);
     mad_thresholds_kernel<<<1, 32, 0, s>>>(d, remove_outliers);
     mask_update_kernel<<<(unsigned)nch, 256, 0, s>>>(front->dh, front->maskbits, n, d, w.chunk_cnt);
-    if ((rc = dcr_chunk_scan_enqueue(w.chunk_cnt, nch, w.chunk_off, &d->total_final, s))) return rc;
-    stride_kernel<<<1, 32, 0, s>>>(d);
+    if (side) {
+        DCR_CUDA_OK(cudaEventRecord(e_mask, s));
+        DCR_CUDA_OK(cudaStreamWaitEvent(s2, e_mask, 0));
+    }
+    // strided subsample of the final mask + dz on it (malib.get_stats <- dem_align.py:114-115)
+    if ((rc = dcr_chunk_scan_enqueue(w.chunk_cnt, nch, w.chunk_off, &d->total_final, sb))) return rc;
+    stride_kernel<<<1, 32, 0, sb>>>(d);
     if ((rc = dcr_compress_enqueue(front->dh, front->maskbits, DCR_M_DIFF, n, w.chunk_off, 1, &d->stride, w.dense,
-                                   w.dense_cap, s)))
+                                   w.dense_cap, sb)))
         return rc;
-    STAGE_MARK(3);
-    // med_dh over the final mask (coreglib.py:214) and dz on the (possibly strided) subsample (dem_align.py:114-115)
-    v.reject = DCR_M_DIFF; v.transform = 0; v.center_ptr = nullptr;
-    if ((rc = iter_select(v, 2, w, n, use_bsel, s))) return rc;
     {
         SelView vd;
         memset(&vd, 0, sizeof(vd));
         vd.x = w.dense; vd.m = nullptr; vd.n = 0; vd.n_ptr = &d->dense_n;
-        if ((rc = iter_select(vd, 3, w, w.dense_cap, use_bsel, s))) return rc;
+        if ((rc = iter_select(vd, 3, wb, w.dense_cap, use_bsel, sb))) return rc;
     }
-    {
+    if (side) DCR_CUDA_OK(cudaEventRecord(e_join, s2));
+    STAGE_MARK(3);
+    // med_dh over the final mask (coreglib.py:214)
+    v.reject = DCR_M_DIFF; v.transform = 0; v.center_ptr = nullptr;
+    if ((rc = iter_select(v, 2, w, n, use_bsel, s))) return rc;
+    if (!side) {
         SelView vs;
         memset(&vs, 0, sizeof(vs));
         vs.x = front->slope; vs.m = front->maskbits; vs.reject = DCR_M_SLOPE; vs.n = n;
@@ -1023,6 +1054,7 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
     if ((rc = nuth_enqueue(front->dh, front->slope, front->aspect, front->maskbits, DCR_M_DIFF | DCR_M_ASPECT, n,
                            remove_outliers, w.nw, grid, s, ev ? ev[5] : nullptr, fast_bins)))
         return rc;
+    if (side) DCR_CUDA_OK(cudaStreamWaitEvent(s, e_join, 0));
     DCR_LAUNCH_OK("iteration kernels");
     STAGE_MARK(6);
     (void)apply_z;
@@ -1106,6 +1138,7 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_it
     w.dense_cap = n < 6000016 ? n : 6000016;
     w.dense = ws.take<float>(w.dense_cap);
     w.bsel_scratch = ws.take<char>(dcr_bsel_scratch_bytes(n));
+    w.bsel_scratch2 = ws.take<char>(dcr_bsel_scratch_bytes(n));
     if (nuth_ws_carve(ws, n, grid, &w.nw)) return -1;
     w.nw.nd = &w.d->nuth;
     IterDev* d = w.d;
@@ -1259,6 +1292,7 @@ static int band_carve(void* workspace, size_t workspace_bytes, long long n, int 
     w->dense_cap = n < 6000016 ? n : 6000016;
     w->dense = ws.take<float>(w->dense_cap);
     w->bsel_scratch = ws.take<char>(dcr_bsel_scratch_bytes(n));
+    w->bsel_scratch2 = ws.take<char>(dcr_bsel_scratch_bytes(n));
     if (nuth_ws_carve(ws, n, grid, &w->nw)) return -1;
     w->nw.nd = &w->d->nuth;
     return 0;
