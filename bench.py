@@ -32,7 +32,7 @@ STAGE_INFO = [
     ("front_kernel (warp+dh+masks+Horn)", 21.0),
     ("bsel_* x2: median + MAD of dh (slope median overlapped on the side stream)", 16.0),
     ("mad_thresholds + mask_update_kernel", 6.0),
-    ("bsel_*: med_dh (scan/compress/dz median overlapped on the side stream)", 8.0),
+    ("(side stream only: scan/compress/dz median/med_dh)", 0.0),
     ("nuth_prepare_kernel (y, bin, moments)", 13.0 + 6.0),
     ("fb_pass* (bin count + exact bin medians)", 12.0),
     ("result copy", 0.0),
