@@ -1039,11 +1039,12 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
         vd.x = w.dense; vd.m = nullptr; vd.n = 0; vd.n_ptr = &d->dense_n;
         if ((rc = iter_select(vd, 3, wb, w.dense_cap, use_bsel, sb))) return rc;
     }
-    if (side) DCR_CUDA_OK(cudaEventRecord(e_join, s2));
     STAGE_MARK(3);
-    // med_dh over the final mask (coreglib.py:214)
+    // med_dh over the final mask (coreglib.py:214): also off the critical path (the bin statistics below only need
+    // the mask), so it follows the subsample chain on the side stream
     v.reject = DCR_M_DIFF; v.transform = 0; v.center_ptr = nullptr;
-    if ((rc = iter_select(v, 2, w, n, use_bsel, s))) return rc;
+    if ((rc = iter_select(v, 2, wb, n, use_bsel, sb))) return rc;
+    if (side) DCR_CUDA_OK(cudaEventRecord(e_join, s2));
     if (!side) {
         SelView vs;
         memset(&vs, 0, sizeof(vs));
