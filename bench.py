@@ -25,8 +25,8 @@ sys.path.insert(0, ROOT)
 
 ALG_BYTES_ITER = 90.0      # algorithmic bytes per pixel per iteration
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of front_kernel on the default 8192^2 workload, from the
-# `ncu --set full` capture summarised in profiles/front_kernel_r1_final_raw.csv (604.03 MB + 823.26 MB)
-FRONT_KERNEL_DRAM_BYTES_8192 = 1427290880
+# `ncu --set full` capture summarised in profiles/front_kernel_r1_final_raw.csv (604.20 MB + 828.15 MB)
+FRONT_KERNEL_DRAM_BYTES_8192 = 1432348672
 # algorithmic bytes per pixel of each profiled stage (SURVEY 8d stage table)
 STAGE_INFO = [
     ("front_kernel (warp+dh+masks+Horn)", 21.0),
@@ -353,6 +353,21 @@ def main():
     roofline_iter = {"bound": "hbm", "achieved": iter_ach, "peak": peak, "unit": "GB/s", "frac": iter_ach / peak,
                      "algorithmic_bytes_per_px": ALG_BYTES_ITER}
 
+    # ---- DEM pairs/s (second half of the BASELINE metric): the whole dem_align loop to convergence on the
+    #      device-resident pair (reference dem_align.py:306-357), per GPU, aggregated over the ranks
+    from demcoreg_b200 import dem_align as _da
+    barrier()
+    npairs = 3
+    e0.record()
+    for _ in range(npairs):
+        res_loop = _da.align(ref, src0, mask_source=ms, verbose=False)
+    e1.record()
+    barrier()
+    tp = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+    pairs_per_s = world * npairs / (float(tp.item()) * 1e-3)
+
     # ---- end-to-end arm: host buffers in, (dx,dy,dz) out, through the public API -------------
     h_ref = torch.from_numpy(p['ref']).pin_memory()
     h_src = torch.from_numpy(p['src']).pin_memory()
@@ -394,7 +409,7 @@ def main():
     # ---- CPU baseline: the oracle on a bounded sample of the same workload (rank 0, N=1 only) ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        crop = min(size, 2048)
+        crop = min(size, 4096)
         sec, px = oracle_iteration_seconds(p, crop, (gts[0] - p['gt'][0], gts[3] - p['gt'][3]))
         cpu = {"value": px / sec / 1e9, "unit": "Gpix/s", "cores": 1, "kind": "port",
                "sample": "one oracle iteration (numpy/scipy restatement, plot path off) on the %dx%d top-left crop of "
@@ -407,7 +422,10 @@ def main():
                                    "at %g m with a 30%% stable-surface mask, 1%% nodata, injected shift (+3.2,-1.7,+0.5) m; "
                                    "one pair per GPU" % (size, size, res),
                        "pixels_per_step_per_gpu": npx, "l2": "inputs (2 x %d MB + mask) larger than the 126 MB L2" % (npx * 4 >> 20),
-                       "last_step_shift_m": [r.dx, r.dy, r.dz]},
+                       "last_step_shift_m": [r.dx, r.dy, r.dz],
+                       "pairs_per_s": pairs_per_s, "pairs_loop": {"n_iter": res_loop['n_iter'], "dx": res_loop['dx'],
+                                                                  "dy": res_loop['dy'], "dz": res_loop['dz'],
+                                                                  "note": "dem_align.align to convergence (tol 0.02 m), device-resident pair, incl. the src copy"}},
             "clocks": clocks, "gpu_launches": KERNELS_PER_STEP * args.steps,
             "e2e": {"value": e2e_val, "unit": "Gpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": roofline, "roofline_iteration": roofline_iter, "cpu_baseline": cpu}
