@@ -11,7 +11,9 @@
 // FP32; Horn 3x3 sums in FP32 in GDAL's order, FP64 atan/atan2, one rounding to FP32.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <cuda.h>
 #include "dcr_common.cuh"
 #include "dcr_internal.cuh"
 
@@ -414,14 +416,20 @@ extern "C" int dcr_horn_slope_aspect(const float* dem, int h, int w, int64_t str
 #define F_TW 128
 #define F_TH 28
 #define F_SRC_R (F_TH + 5)
-#define F_SRC_C (F_TW + 5)
+#define F_SRC_C (F_TW + 8)   // 133 columns needed; 136 = multiple of 4 floats (TMA box rows are multiples of 16 bytes)
 #define F_REF_R (F_TH + 3)
-#define F_REF_C (F_TW + 3)
+#define F_REF_C (F_TW + 8)   // 131 columns needed (+ up to 3 of TMA start alignment); 136
 #define F_SW_R (F_TH + 2)
 #define F_SW_C (F_TW + 2)
 #define F_ROWS_PER_THREAD (F_TH / 2)
+#define F_SRC_WORDS (((F_SRC_R * F_SRC_C + 31) / 32) * 32)
+#define F_REF_WORDS (((F_REF_R * F_REF_C + 31) / 32) * 32)
 
 struct FrontParams {
+    alignas(64) CUtensorMap tm_src;   // TMA descriptors of the two rasters (valid iff use_tma)
+    alignas(64) CUtensorMap tm_ref;
+    int use_tma;
+    int tma_dx_src, tma_dx_ref;       // TMA boxes must start on a 16-byte column: extra leading columns (0..3)
     DevGeom rg, sg;
     const float* ref;
     const float* src;
@@ -464,6 +472,30 @@ __device__ __forceinline__ float warp_px_tile(const float* t, int r0, int c0, co
     }
     if (isnan(nearest)) return nearest;
     return (float)o;
+}
+
+// ---- TMA (cp.async.bulk.tensor) staging of a 2-D footprint: one elected thread issues the copy, the bytes land in
+// shared memory asynchronously and complete on an mbarrier; out-of-bounds elements are filled with NaN by the copy
+// engine (CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA), which is exactly the "outside the raster" encoding.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int x, int y, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
 }
 
 // Stage an R x C footprint whose top-left source pixel is (r_base, c_base) into shared memory: one warp per
@@ -517,10 +549,13 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ src, const 
 }
 
 __global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ FrontParams p) {
-    extern __shared__ float smem[];
-    float* s_src = smem;                                  // F_SRC_R x F_SRC_C
-    float* s_ref = s_src + F_SRC_R * F_SRC_C;             // F_REF_R x F_REF_C
-    float* s_sw = s_ref + F_REF_R * F_REF_C;              // F_SW_R x F_SW_C : warped src (NaN = nodata)
+    extern __shared__ __align__(128) float smem[];
+    float* s_src_base = smem;                             // F_SRC_R x F_SRC_C
+    float* s_ref_base = s_src_base + F_SRC_WORDS;         // F_REF_R x F_REF_C (128-byte aligned: TMA destination)
+    float* s_sw = s_ref_base + F_REF_WORDS;               // F_SW_R x F_SW_C : warped src (NaN = nodata)
+    // tile views: with TMA the box starts on the 16-byte column at or before the first needed one
+    float* s_src = s_src_base + (p.use_tma ? p.tma_dx_src : 0);
+    float* s_ref = s_ref_base + (p.use_tma ? p.tma_dx_ref : 0);
     __shared__ unsigned long long s_cnt[3];
     __shared__ unsigned char s_mask[F_TH * F_TW];       // static (stable-surface) mask of the tile, 1 = masked
 
@@ -529,9 +564,21 @@ __global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ F
     if (tid < 3) s_cnt[tid] = 0ull;
 
     // ---- stage the two source footprints (nodata / out-of-bounds -> NaN)
-    if (p.sg.ndz) stage_tile<F_SRC_R, F_SRC_C, true>(p.src, p.sg, ti0 - 2 + p.sg.iy0, tj0 - 2 + p.sg.ix0, s_src, tid);
-    else stage_tile<F_SRC_R, F_SRC_C, false>(p.src, p.sg, ti0 - 2 + p.sg.iy0, tj0 - 2 + p.sg.ix0, s_src, tid);
-    stage_tile<F_REF_R, F_REF_C, false>(p.ref, p.rg, ti0 - 1 + p.rg.iy0, tj0 - 1 + p.rg.ix0, s_ref, tid);
+    __shared__ __align__(8) unsigned long long s_bar;
+    if (p.use_tma) {
+        // both footprints by TMA: thread 0 arms the mbarrier with the byte count and issues the two tensor copies
+        if (tid == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&s_bar, (unsigned)((F_SRC_R * F_SRC_C + F_REF_R * F_REF_C) * sizeof(float)));
+            tma_load_2d(s_src_base, &p.tm_src, tj0 - 2 + p.sg.ix0 - p.tma_dx_src, ti0 - 2 + p.sg.iy0 - p.sg.row0, &s_bar);
+            tma_load_2d(s_ref_base, &p.tm_ref, tj0 - 1 + p.rg.ix0 - p.tma_dx_ref, ti0 - 1 + p.rg.iy0 - p.rg.row0, &s_bar);
+        }
+    } else {
+        if (p.sg.ndz) stage_tile<F_SRC_R, F_SRC_C, true>(p.src, p.sg, ti0 - 2 + p.sg.iy0, tj0 - 2 + p.sg.ix0, s_src, tid);
+        else stage_tile<F_SRC_R, F_SRC_C, false>(p.src, p.sg, ti0 - 2 + p.sg.iy0, tj0 - 2 + p.sg.ix0, s_src, tid);
+        stage_tile<F_REF_R, F_REF_C, false>(p.ref, p.rg, ti0 - 1 + p.rg.iy0, tj0 - 1 + p.rg.ix0, s_ref, tid);
+    }
     if (p.smask) {
         // nearest-neighbour sample of the world-fixed mask; all 16 byte loads of a thread are issued before their
         // first use (a dependent load per pixel inside the main pass cost ~600 cycles of latency per row)
@@ -546,6 +593,24 @@ __global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ F
         }
 #pragma unroll
         for (int k = 0; k < (F_TH * F_TW) / 256; ++k) s_mask[k * 256 + tid] = mv[k];
+    }
+    if (p.use_tma) {
+        // wait for the bytes (bounded spin: a mis-programmed copy must fault, not hang the GPU), then nodata -> NaN
+        unsigned spins = 0;
+        while (!mbar_try_wait(&s_bar, 0)) {
+            if (++spins > (1u << 26)) __trap();
+        }
+        const float qnan = __int_as_float(0x7fc00000);
+        if (p.sg.has_ndv) {
+            const float nd = p.sg.ndv;
+            for (int k = tid; k < F_SRC_R * F_SRC_C; k += 256)
+                if (s_src_base[k] == nd) s_src_base[k] = qnan;
+        }
+        if (p.rg.has_ndv) {
+            const float nd = p.rg.ndv;
+            for (int k = tid; k < F_REF_R * F_REF_C; k += 256)
+                if (s_ref_base[k] == nd) s_ref_base[k] = qnan;
+        }
     }
     __syncthreads();
 
@@ -721,6 +786,37 @@ static void gm_bounds(double ndv, float* lo, float* hi) {
     *hi = fh;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)f;
+    }
+    return fn;
+}
+// 2-D float32 tensor map over the rows held in memory; box = (box_w x box_h); OOB elements read as NaN
+static bool make_tmap(CUtensorMap* tm, const float* base, int rows, int cols, long long stride_elems, int box_w, int box_h) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return false;
+    if ((((uintptr_t)base) & 15) != 0 || (stride_elems & 3) != 0 || rows <= 0 || cols <= 0) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)stride_elems * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,  // (L2_128B promotion faults with this 544-byte box)
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA) == CUDA_SUCCESS;
+}
+
 int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cudaStream_t stream) {
     DCR_ARG(a, "null args");
     DCR_ARG(a->ref && a->src && a->dh && a->slope && a->aspect && a->maskbits, "null raster pointer");
@@ -806,7 +902,19 @@ int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cuda
             }
         }
     }
-    const size_t smem = (size_t)(F_SRC_R * F_SRC_C + F_REF_R * F_REF_C + F_SW_R * F_SW_C) * sizeof(float);
+    // TMA staging of the two footprints when the layout allows it (16-byte aligned base and row pitch, no deferred z
+    // shifts); otherwise the kernel stages them with coalesced row loads (stage_tile)
+    p.use_tma = 0;
+    if (p.sg.ndz == 0 && !getenv("DCR_NO_TMA")) {
+        const bool ok = make_tmap(&p.tm_src, a->src, p.sg.row1 - p.sg.row0, p.sg.ws, p.sg.stride, F_SRC_C, F_SRC_R) &&
+                        make_tmap(&p.tm_ref, a->ref, p.rg.row1 - p.rg.row0, p.rg.ws, p.rg.stride, F_REF_C, F_REF_R);
+        p.use_tma = ok ? 1 : 0;
+        // the copy engine wants every box to start on a 16-byte boundary of the row (measured: other starts raise
+        // "illegal instruction"): start up to 3 columns early (the 136-wide boxes have the room) and shift the views
+        p.tma_dx_src = ((p.sg.ix0 - 2) % 4 + 4) % 4;
+        p.tma_dx_ref = ((p.rg.ix0 - 1) % 4 + 4) % 4;
+    }
+    const size_t smem = (size_t)(F_SRC_WORDS + F_REF_WORDS + F_SW_R * F_SW_C) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         DCR_CUDA_OK(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -24,7 +24,7 @@ def _ods(p, key, gt=None):
 
 def _gds(p, key, gt=None):
     from demcoreg_b200.raster import Raster
-    return Raster(p[key], gt or p['gt'], p['ndv'])
+    return Raster(p[key], gt or p['gt'], p.get('ndv', -9999.0))
 
 
 def _shifted_gt(gt, dx, dy):
@@ -549,3 +549,35 @@ def test_deferred_z_shift_equals_eager(cuda):
     assert np.array_equal(b1.maskbits.cpu().numpy(), b2.maskbits.cpu().numpy())
     assert (r1.dx, r1.dy, r1.dz) == (r2.dx, r2.dy, r2.dz)
     assert np.array_equal(lazy.numpy(), eager.numpy()) and lazy.pending_dz == []
+
+
+def test_front_kernel_tma_equals_manual_staging(cuda, monkeypatch):
+    """The TMA-staged front kernel and the coalesced-row-load staging (DCR_NO_TMA=1, also the path for rasters whose
+    row pitch is not a multiple of 16 bytes) produce bit-identical outputs."""
+    from demcoreg_b200 import engine
+    p = _pair(n=640, nodata_frac=0.02, static_mask_frac=0.2)
+    from demcoreg_b200.raster import MaskSource
+    outs = []
+    for gt_shift in ((0.0, 0.0), (37.3, -95.2), (-61.0, 8.4)):
+        gt_s = _shifted_gt(p['gt'], *gt_shift)
+        res = []
+        for no_tma in (False, True):
+            if no_tma:
+                monkeypatch.setenv("DCR_NO_TMA", "1")
+            else:
+                monkeypatch.delenv("DCR_NO_TMA", raising=False)
+            grid, bufs = engine.front_only(_gds(p, 'ref'), _gds(p, 'src', gt_s), MaskSource(p['mask'], p['gt']))
+            res.append([t.cpu().numpy() for t in (bufs.dh, bufs.slope, bufs.aspect, bufs.maskbits, bufs.ref_w, bufs.src_w)])
+        for a, b in zip(*res):
+            assert np.array_equal(a, b, equal_nan=True)
+    monkeypatch.delenv("DCR_NO_TMA", raising=False)
+    # odd width: row pitch not a multiple of 16 bytes -> the library must pick the manual path by itself
+    q = _pair(n=256)
+    ref = _gds(dict(ref=q['ref'][:, :253].copy()), 'ref', q['gt'])
+    src = _gds(dict(src=q['src'][:, :253].copy()), 'src', q['gt'])
+    from oracle import pygeotools_restated as pg, dem_align as oda
+    grid, bufs = engine.front_only(ref, src)
+    det = {}
+    oda.compute_offset(pg.MemDataset(q['ref'][:, :253], q['gt'], q['ndv']), pg.MemDataset(q['src'][:, :253], q['gt'], q['ndv']),
+                       details=det)
+    assert np.array_equal(bufs.src_w.cpu().numpy(), det['src_w'])
