@@ -292,15 +292,19 @@ def main():
 
     quiet = contextlib.redirect_stdout(io.StringIO())
 
-    def step(src, profile=False):
-        # exactly what demcoreg_b200.dem_align.align does per iteration: compute_offset (+ the z shift applied on the
-        # device in the same kernel chain), then apply_xy_shift on the host
-        r, grid, bufs = engine.nuth_iteration(ref, src, ms, profile=profile, apply_z=True)
-        with quiet:
-            coreglib.apply_xy_shift(src, r.dx, r.dy, createcopy=False)
-            if not r.z_applied:
-                coreglib.apply_z_shift(src, np.float32(r.dz), createcopy=False)
-        return r, grid
+    class Grid2(object):
+        pass
+
+    def make_stepper(src):
+        # dem_align's loop body (compute_offset + apply_xy_shift + apply_z_shift, reference dem_align.py:306-343), one
+        # native call per iteration; tol = 0 and a huge max_iter so that the loop never "converges" during the bench
+        return engine.NuthAligner(ref, src, ms, tol=0.0, max_offset=1e9, max_iter=1 << 30)
+
+    def step(al, profile=False):
+        r = al.step(profile=profile)
+        g = Grid2()
+        g.height, g.width = al.grid_hw
+        return r, g
 
     def barrier():
         if world > 1:
@@ -309,8 +313,9 @@ def main():
 
     # ---- device-resident arm -------------------------------------------------------------
     src = src0.copy()
+    al = make_stepper(src)
     for _ in range(args.warmup):
-        r, grid = step(src)
+        r, grid = step(al)
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -319,7 +324,7 @@ def main():
     pix = 0
     e0.record()
     for _ in range(args.steps):
-        r, grid = step(src)
+        r, grid = step(al)
         pix += grid.height * grid.width
     e1.record()
     barrier()
@@ -336,7 +341,7 @@ def main():
     stage = np.zeros(7)
     nprof = max(3, min(args.steps, 5))
     for _ in range(nprof):
-        r, grid = step(src, profile=True)
+        r, grid = step(al, profile=True)
         stage += np.array(r.stage_ms[:7])
     stage /= nprof
     npx = grid.height * grid.width
@@ -372,6 +377,7 @@ def main():
     h_ref = torch.from_numpy(p['ref']).pin_memory()
     h_src = torch.from_numpy(p['src']).pin_memory()
     h_msk = torch.from_numpy(p['mask']).pin_memory()
+    al.finish()
     gts = src.gt  # a realistic sub-pixel state (after the timed steps)
     d_src = Raster(src0.data.clone(), gts, p['ndv'])
 

@@ -65,6 +65,31 @@ class IterResult(C.Structure):
                 ("z_applied", C.c_int32)]
 
 
+ALIGN_MAX_PENDING = 4
+
+
+class AlignIter(C.Structure):
+    _fields_ = [("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double), ("status", C.c_int32),
+                ("select_engine", C.c_int32), ("h", C.c_int32), ("w", C.c_int32)]
+
+
+class AlignState(C.Structure):
+    _fields_ = [
+        ("ref", C.c_void_p), ("ref_stride", C.c_int64), ("ref_desc", RasterDesc),
+        ("src", C.c_void_p), ("src_stride", C.c_int64), ("src_desc", RasterDesc),
+        ("smask", C.c_void_p), ("smask_stride", C.c_int64), ("smask_desc", RasterDesc),
+        ("dh", C.c_void_p), ("slope", C.c_void_p), ("aspect", C.c_void_p), ("maskbits", C.c_void_p),
+        ("out_capacity", C.c_int64),
+        ("tol", C.c_double), ("max_offset", C.c_double),
+        ("max_dz", C.c_float), ("slope_lo", C.c_float), ("slope_hi", C.c_float),
+        ("max_iter", C.c_int32), ("remove_outliers", C.c_int32),
+        ("n_done", C.c_int32), ("finished", C.c_int32), ("exit_code", C.c_int32), ("src_ndz", C.c_int32),
+        ("src_dz", C.c_float * 16),
+        ("dx_total", C.c_double), ("dy_total", C.c_double), ("dz_total", C.c_float), ("_pad", C.c_float),
+        ("last", IterResult),
+    ]
+
+
 # every symbol include/demcoreg_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -106,6 +131,9 @@ SYMBOLS = {
                                  C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
     "dcr_band_result": (C.c_int, [C.POINTER(FrontArgs), _P, C.c_size_t, C.POINTER(IterResult), _P]),
     "dcr_nuth_iteration": (C.c_int, [C.POINTER(FrontArgs), C.c_int, C.POINTER(IterResult), _P, C.c_size_t, _P]),
+    "dcr_align_nuth": (C.c_int, [C.POINTER(AlignState), C.c_int, C.c_int, C.POINTER(AlignIter), C.c_int,
+                                 C.POINTER(C.c_int), _P, C.c_size_t, _P]),
+    "dcr_align_flush_z": (C.c_int, [C.POINTER(AlignState), _P]),
 }
 
 _lib = None

@@ -37,6 +37,8 @@ extern "C" int dcr_struct_size(int which) {
         case 3: return (int)sizeof(dcr_front_args);
         case 4: return (int)sizeof(dcr_nuth_stats);
         case 5: return (int)sizeof(dcr_iter_result);
+        case 6: return (int)sizeof(dcr_align_iter);
+        case 7: return (int)sizeof(dcr_align_state);
         default: return -1;
     }
 }
@@ -600,16 +602,52 @@ __global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ F
         while (!mbar_try_wait(&s_bar, 0)) {
             if (++spins > (1u << 26)) __trap();
         }
+        // fix-up pass over the landed tiles, 4 elements per access (tiles are 128-byte aligned, sizes multiples of 4)
         const float qnan = __int_as_float(0x7fc00000);
-        if (p.sg.has_ndv) {
+        static_assert((F_SRC_R * F_SRC_C) % 4 == 0 && (F_REF_R * F_REF_C) % 4 == 0, "tile sizes must be float4 multiples");
+        if (p.sg.ndz) {
+            // deferred z shifts (coreglib.apply_z_shift not yet written back): a = b_getma(band); a = a + dz; filled()
+            // -- one float32 add per pending step (<= 4 on this path) on every loaded pixel, then nodata -> NaN
+            const float nd = p.sg.ndv, zlo = p.sg.zlo, zhi = p.sg.zhi;
+            const bool hn = p.sg.has_ndv != 0;
+            const int ndz = p.sg.ndz;
+            const float z0 = p.sg.dz[0], z1 = p.sg.dz[1], z2 = p.sg.dz[2], z3 = p.sg.dz[3];
+            auto fix = [&](float x) {
+                x = (x >= zlo && x <= zhi) ? nd : x + z0;
+                if (ndz > 1) x = (x >= zlo && x <= zhi) ? nd : x + z1;
+                if (ndz > 2) x = (x >= zlo && x <= zhi) ? nd : x + z2;
+                if (ndz > 3) x = (x >= zlo && x <= zhi) ? nd : x + z3;
+                return (hn && x == nd) ? qnan : x;
+            };
+            float4* t4 = reinterpret_cast<float4*>(s_src_base);
+            for (int k = tid; k < (F_SRC_R * F_SRC_C) / 4; k += 256) {
+                float4 v = t4[k];
+                v.x = fix(v.x); v.y = fix(v.y); v.z = fix(v.z); v.w = fix(v.w);
+                t4[k] = v;
+            }
+        } else if (p.sg.has_ndv) {
             const float nd = p.sg.ndv;
-            for (int k = tid; k < F_SRC_R * F_SRC_C; k += 256)
-                if (s_src_base[k] == nd) s_src_base[k] = qnan;
+            float4* t4 = reinterpret_cast<float4*>(s_src_base);
+            for (int k = tid; k < (F_SRC_R * F_SRC_C) / 4; k += 256) {
+                float4 v = t4[k];
+                if (v.x == nd || v.y == nd || v.z == nd || v.w == nd) {   // rare: nodata in this quad
+                    v.x = v.x == nd ? qnan : v.x; v.y = v.y == nd ? qnan : v.y;
+                    v.z = v.z == nd ? qnan : v.z; v.w = v.w == nd ? qnan : v.w;
+                    t4[k] = v;
+                }
+            }
         }
         if (p.rg.has_ndv) {
             const float nd = p.rg.ndv;
-            for (int k = tid; k < F_REF_R * F_REF_C; k += 256)
-                if (s_ref_base[k] == nd) s_ref_base[k] = qnan;
+            float4* t4 = reinterpret_cast<float4*>(s_ref_base);
+            for (int k = tid; k < (F_REF_R * F_REF_C) / 4; k += 256) {
+                float4 v = t4[k];
+                if (v.x == nd || v.y == nd || v.z == nd || v.w == nd) {
+                    v.x = v.x == nd ? qnan : v.x; v.y = v.y == nd ? qnan : v.y;
+                    v.z = v.z == nd ? qnan : v.z; v.w = v.w == nd ? qnan : v.w;
+                    t4[k] = v;
+                }
+            }
         }
     }
     __syncthreads();
@@ -902,10 +940,10 @@ int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cuda
             }
         }
     }
-    // TMA staging of the two footprints when the layout allows it (16-byte aligned base and row pitch, no deferred z
-    // shifts); otherwise the kernel stages them with coalesced row loads (stage_tile)
+    // TMA staging of the two footprints when the layout allows it (16-byte aligned base and row pitch); otherwise
+    // the kernel stages them with coalesced row loads (stage_tile)
     p.use_tma = 0;
-    if (p.sg.ndz == 0 && !getenv("DCR_NO_TMA")) {
+    if (p.sg.ndz <= 4 && !getenv("DCR_NO_TMA")) {   // (the fix-up pass of the TMA path unrolls at most 4 deferred shifts)
         const bool ok = make_tmap(&p.tm_src, a->src, p.sg.row1 - p.sg.row0, p.sg.ws, p.sg.stride, F_SRC_C, F_SRC_R) &&
                         make_tmap(&p.tm_ref, a->ref, p.rg.row1 - p.rg.row0, p.rg.ws, p.rg.stride, F_REF_C, F_REF_R);
         p.use_tma = ok ? 1 : 0;

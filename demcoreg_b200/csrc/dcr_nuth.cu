@@ -783,12 +783,25 @@ __global__ void __launch_bounds__(256) zshift_seq_kernel(float* __restrict__ ban
                                                          double tol, float ndv32, ZSeq z) {
     const long long n = (long long)h * w;
     const long long step = (long long)gridDim.x * 256;
+    auto shift = [&](float v) {
+        for (int q = 0; q < z.n; ++q) v = (fabs((double)v - ndv) <= tol) ? ndv32 : v + z.dz[q];
+        return v;
+    };
+    if (stride == w && DCR_AL16(band)) {   // contiguous band: float4 read-modify-write
+        const long long n4 = n >> 2;
+        float4* b4 = reinterpret_cast<float4*>(band);
+        for (long long k = (long long)blockIdx.x * 256 + threadIdx.x; k < n4; k += step) {
+            float4 v = b4[k];
+            v.x = shift(v.x); v.y = shift(v.y); v.z = shift(v.z); v.w = shift(v.w);
+            b4[k] = v;
+        }
+        for (long long k = (n4 << 2) + (long long)blockIdx.x * 256 + threadIdx.x; k < n; k += step) band[k] = shift(band[k]);
+        return;
+    }
     for (long long k = (long long)blockIdx.x * 256 + threadIdx.x; k < n; k += step) {
         const int i = (int)(k / w), j = (int)(k - (long long)i * w);
         float* p = band + (long long)i * stride + j;
-        float v = *p;
-        for (int q = 0; q < z.n; ++q) v = (fabs((double)v - ndv) <= tol) ? ndv32 : v + z.dz[q];
-        *p = v;
+        *p = shift(*p);
     }
 }
 
@@ -1203,6 +1216,87 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_it
         out->z_applied = ((flags & DCR_ITER_APPLY_Z) && !isnan(out->dz_med)) ? 1 : 0;
         return rcf;
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// The dem_align loop (dem_align.py:291-357, mode 'nuth') as one native call: no interpreter work between iterations
+// ------------------------------------------------------------------------------------------
+extern "C" int dcr_align_flush_z(dcr_align_state* st, void* stream) {
+    DCR_ARG(st && st->src, "null pointer");
+    if (st->src_ndz > 0) {
+        int rc = dcr_apply_z_shift_seq(st->src, st->src_desc.height, st->src_desc.width, st->src_stride,
+                                       st->src_desc.has_ndv ? st->src_desc.ndv : 0.0, st->src_dz, st->src_ndz, stream);
+        if (rc) return rc;
+        st->src_ndz = 0;
+    }
+    return 0;
+}
+
+extern "C" int dcr_align_nuth(dcr_align_state* st, int max_steps, int flags, dcr_align_iter* iters, int iters_cap,
+                              int* n_iters, void* workspace, size_t workspace_bytes, void* stream) {
+    DCR_ARG(st && workspace, "null pointer");
+    DCR_ARG(st->ref && st->src && st->dh && st->slope && st->aspect && st->maskbits, "null raster pointer");
+    DCR_ARG(st->src_ndz >= 0 && st->src_ndz <= 16, "0 <= src_ndz <= 16");
+    int done_here = 0;
+    if (n_iters) *n_iters = 0;
+    while (!st->finished && st->exit_code == 0 && (max_steps <= 0 || done_here < max_steps)) {
+        // compute_offset: memwarp_multi bookkeeping for the CURRENT source geotransform
+        dcr_front_args a;
+        memset(&a, 0, sizeof(a));
+        dcr_grid grid;
+        int rc = dcr_plan_intersection(&st->ref_desc, &st->src_desc, 0.0, &grid, &a.ref_geom, &a.src_geom);
+        if (rc) return rc;
+        if ((long long)grid.height * grid.width > st->out_capacity) {
+            dcr_set_error("iteration outputs too small: %d x %d grid, capacity %lld pixels", grid.height, grid.width,
+                          (long long)st->out_capacity);
+            return -1;
+        }
+        a.ref = st->ref; a.ref_stride = st->ref_stride; a.ref_desc = st->ref_desc;
+        a.src = st->src; a.src_stride = st->src_stride; a.src_desc = st->src_desc;
+        if (st->smask) {
+            dcr_warp_geom gm;
+            if ((rc = dcr_plan_onto_grid(&st->smask_desc, &grid, &gm))) return rc;
+            a.smask = st->smask; a.smask_stride = st->smask_stride;
+            a.smask_h = st->smask_desc.height; a.smask_w = st->smask_desc.width;
+            a.smask_nx0 = gm.nx0; a.smask_ny0 = gm.ny0;
+        }
+        a.h = grid.height; a.w = grid.width;
+        a.ewres = grid.gt[1]; a.nsres = grid.gt[5];
+        a.dst_ndv = 0.0;
+        a.max_dz = st->max_dz; a.use_max_dz = st->remove_outliers ? 1 : 0;
+        a.slope_lo = st->slope_lo; a.slope_hi = st->slope_hi;
+        a.dh = st->dh; a.slope = st->slope; a.aspect = st->aspect; a.maskbits = st->maskbits;
+        a.src_ndz = st->src_ndz;
+        for (int k = 0; k < st->src_ndz; ++k) a.src_dz[k] = st->src_dz[k];
+        const int f = (st->remove_outliers ? DCR_ITER_REMOVE_OUTLIERS : 0) | (flags & (DCR_ITER_PROFILE | DCR_ITER_RADIX_ONLY));
+        if ((rc = dcr_nuth_iteration(&a, f, &st->last, workspace, workspace_bytes, stream))) return rc;
+        const dcr_iter_result& r = st->last;
+        if (iters && done_here < iters_cap) {
+            dcr_align_iter& it = iters[done_here];
+            it.dx = r.dx; it.dy = r.dy; it.dz = r.dz; it.status = r.status; it.select_engine = r.select_engine;
+            it.h = grid.height; it.w = grid.width;
+        }
+        ++done_here;
+        if (n_iters) *n_iters = done_here;
+        if (r.status >= 1 && r.status <= 3) { st->exit_code = r.status; break; }   // compute_offset's sys.exit paths
+        // totals (dz is np.float32 in the reference: float32 accumulation and float32 squares)
+        const float dz32 = -r.dz_med;
+        st->dx_total += r.dx;
+        st->dy_total += r.dy;
+        st->dz_total = st->dz_total + dz32;
+        // apply_xy_shift: geotransform origin; apply_z_shift: deferred, folded into the band every few iterations
+        st->src_desc.gt[0] += r.dx;
+        st->src_desc.gt[3] += r.dy;
+        st->src_dz[st->src_ndz++] = dz32;
+        if (st->src_ndz >= DCR_ALIGN_MAX_PENDING && (rc = dcr_align_flush_z(st, stream))) return rc;
+        ++st->n_done;
+        const double dm = sqrt(r.dx * r.dx + r.dy * r.dy + (double)(dz32 * dz32));
+        const double dm_total = sqrt(st->dx_total * st->dx_total + st->dy_total * st->dy_total +
+                                     (double)(st->dz_total * st->dz_total));
+        if (dm_total > st->max_offset) { st->exit_code = 5; break; }
+        if (st->n_done >= st->max_iter || dm < st->tol) st->finished = 1;
+    }
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------

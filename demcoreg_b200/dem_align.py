@@ -167,6 +167,9 @@ def align(ref_dem_ds, src_dem_ds, mode='nuth', mask_source=None, tol=0.02, max_o
     import contextlib
     import io
     src_dem_ds_align = src_dem_ds.copy()
+    if mode == 'nuth' and records is None:
+        return _align_nuth_native(ref_dem_ds, src_dem_ds_align, mask_source, tol, max_offset, max_dz, slope_lim, max_iter,
+                                  verbose)
     n = 1
     dx_total = 0
     dy_total = 0
@@ -207,6 +210,36 @@ def align(ref_dem_ds, src_dem_ds, mode='nuth', mask_source=None, tol=0.02, max_o
                 break
     return dict(dx=float(dx_total), dy=float(dy_total), dz=float(dz_total), n_iter=n - 1, iters=iters,
                 src_align=src_dem_ds_align)
+
+
+def _align_nuth_native(ref_dem_ds, src_dem_ds_align, mask_source, tol, max_offset, max_dz, slope_lim, max_iter, verbose):
+    """The same loop through ``dcr_align_nuth``: every iteration is chained natively (no interpreter work between the
+    kernels of consecutive iterations); the reference's per-iteration messages are replayed afterwards."""
+    al = engine.NuthAligner(ref_dem_ds, src_dem_ds_align, mask_source, tol, max_offset, max_dz, slope_lim, max_iter)
+    al.run()
+    iters = []
+    dx_total = dy_total = 0.0
+    dz_total = np.float32(0)
+    for it in al.iters:
+        if it['status'] in _EXIT_MSG:
+            sys.exit(_EXIT_MSG[it['status']])
+        dz = np.float32(it['dz'])
+        dx_total += it['dx']
+        dy_total += it['dy']
+        dz_total = dz_total + dz
+        if verbose:
+            print("*** Iteration %i ***" % it['n'])
+            if it['status'] == 4:
+                print("Failed to calculate horizontal shift")
+            print("Incremental offset: dx=%+0.2fm, dy=%+0.2fm, dz=%+0.2fm" % (it['dx'], it['dy'], dz))
+            print("Cumulative offset: dx=%+0.2fm, dy=%+0.2fm, dz=%+0.2fm" % (dx_total, dy_total, dz_total))
+            print("\n")
+        iters.append(dict(n=it['n'], dx=float(it['dx']), dy=float(it['dy']), dz=float(dz)))
+    if al.st.exit_code == 5:
+        sys.exit("Total offset exceeded specified max_offset (%0.2f m). Consider increasing -max_offset argument" % max_offset)
+    al.finish()
+    dxt, dyt, dzt = al.totals
+    return dict(dx=dxt, dy=dyt, dz=dzt, n_iter=len(iters), iters=iters, src_align=src_dem_ds_align)
 
 
 def diff_stats(ref_dem_ds, src_dem_ds, mask_source=None, max_dz=100):

@@ -115,6 +115,91 @@ def nuth_iteration(ref, src, mask_source=None, remove_outliers=True, max_dz=100,
     return res, grid, bufs
 
 
+class NuthAligner(object):
+    """The ``dem_align`` iteration loop (reference ``dem_align.py:291-357``, mode ``nuth``) behind ONE native call
+    per loop -- or per iteration (``step``) -- through ``dcr_align_nuth``.
+
+    ``src`` is shifted IN PLACE: its geotransform after every iteration, its band through deferred z shifts that the
+    front kernel applies while loading (``Raster.pending_dz``; ``Raster.data`` / ``finish()`` fold them into the band).
+    """
+
+    def __init__(self, ref, src, mask_source=None, tol=0.02, max_offset=100, max_dz=100, slope_lim=(0.1, 40), max_iter=30,
+                 remove_outliers=True):
+        torch = _lib.require_cuda()
+        self.L = _lib.lib()
+        self.ref, self.src, self.mask_source = ref, src, mask_source
+        st = self.st = _lib.AlignState()
+        st.ref = ref.data.data_ptr()
+        st.ref_stride = ref.data.stride(0)
+        st.ref_desc = ref.desc()
+        src.materialize()
+        st.src = src._data.data_ptr()
+        st.src_stride = src._data.stride(0)
+        st.src_desc = src.desc()
+        if mask_source is not None:
+            st.smask = mask_source.data.data_ptr()
+            st.smask_stride = mask_source.data.stride(0)
+            st.smask_desc = mask_source.desc()
+        h = min(ref.RasterYSize, src.RasterYSize) + 2
+        w = min(ref.RasterXSize, src.RasterXSize) + 2
+        self.cap = h * w
+        self._dh = torch.empty(self.cap, dtype=torch.float32, device="cuda")
+        self._slope = torch.empty(self.cap, dtype=torch.float32, device="cuda")
+        self._aspect = torch.empty(self.cap, dtype=torch.float32, device="cuda")
+        self._maskbits = torch.empty(self.cap, dtype=torch.uint8, device="cuda")
+        st.dh, st.slope, st.aspect, st.maskbits = (self._dh.data_ptr(), self._slope.data_ptr(), self._aspect.data_ptr(),
+                                                   self._maskbits.data_ptr())
+        st.out_capacity = self.cap
+        st.tol, st.max_offset = float(tol), float(max_offset)
+        st.max_dz, st.slope_lo, st.slope_hi = float(max_dz), float(slope_lim[0]), float(slope_lim[1])
+        st.max_iter = int(max_iter)
+        st.remove_outliers = 1 if remove_outliers else 0
+        self.ws = workspace(self.L.dcr_iteration_workspace_bytes(self.cap))
+        self._iters = (_lib.AlignIter * min(max(1, int(max_iter)), 1024))()
+        self.grid_hw = (0, 0)
+        self._n = C.c_int(0)
+        self.iters = []
+
+    def _sync_src(self):
+        st = self.st
+        self.src.gt = tuple(st.src_desc.gt[k] for k in range(6))
+        self.src.pending_dz = [st.src_dz[k] for k in range(st.src_ndz)]
+
+    def run(self, max_steps=0, profile=False, radix_only=False):
+        """Run the loop to the end (``max_steps=0``) or at most ``max_steps`` iterations; returns the records of the
+        iterations this call ran (``_lib.AlignIter``: dx, dy, dz, status, grid size)."""
+        torch = _lib.require_cuda()
+        flags = (_lib.ITER_PROFILE if profile else 0) | (_lib.ITER_RADIX_ONLY if radix_only else 0)
+        _lib.check(self.L.dcr_align_nuth(C.byref(self.st), int(max_steps), flags, self._iters, len(self._iters),
+                                         C.byref(self._n), C.c_void_p(self.ws.data_ptr()), self.ws.numel(),
+                                         _stream_ptr(torch)))
+        self._sync_src()
+        out = [dict(n=len(self.iters) + k + 1, dx=it.dx, dy=it.dy, dz=it.dz, status=it.status, h=it.h, w=it.w,
+                    select_engine=it.select_engine) for k, it in enumerate(self._iters[:self._n.value])]
+        self.iters.extend(out)
+        return out
+
+    def step(self, profile=False):
+        """Exactly one iteration (compute_offset + apply_xy_shift + apply_z_shift); returns the last ``IterResult``."""
+        torch = _lib.require_cuda()
+        flags = _lib.ITER_PROFILE if profile else 0
+        _lib.check(self.L.dcr_align_nuth(C.byref(self.st), 1, flags, self._iters, 1, None, C.c_void_p(self.ws.data_ptr()),
+                                         self.ws.numel(), _stream_ptr(torch)))
+        self.grid_hw = (self._iters[0].h, self._iters[0].w)
+        return self.st.last
+
+    def finish(self):
+        """Fold the pending z shifts into the band and publish the geotransform on ``src``."""
+        torch = _lib.require_cuda()
+        _lib.check(self.L.dcr_align_flush_z(C.byref(self.st), _stream_ptr(torch)))
+        self._sync_src()
+        return self.src
+
+    @property
+    def totals(self):
+        return float(self.st.dx_total), float(self.st.dy_total), float(self.st.dz_total)
+
+
 def front_only(ref, src, mask_source=None, remove_outliers=True, max_dz=100, slope_lim=(0.1, 40), keep_warped=True):
     """Only the fused warp + dh + masks + Horn kernel (``dcr_warp_diff_horn``)."""
     torch = _lib.require_cuda()

@@ -38,7 +38,7 @@ extern "C" {
 const char* dcr_last_error(void);
 int dcr_version(void);
 /* sizeof() of the ABI structs, for binding self-checks: 0 raster_desc, 1 warp_geom, 2 grid, 3 front_args,
- * 4 nuth_stats, 5 iter_result; -1 for an unknown index */
+ * 4 nuth_stats, 5 iter_result, 6 align_iter, 7 align_state; -1 for an unknown index */
 int dcr_struct_size(int which);
 
 /* ---- geometry (host only) -------------------------------------------------------------
@@ -236,6 +236,51 @@ typedef struct dcr_iter_result {
 size_t dcr_iteration_workspace_bytes(int64_t n);
 int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_iter_result* out /* host */,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- the dem_align iteration loop, mode 'nuth' (dem_align.py:291-357) ---------------------------------------
+ * while True: compute_offset -> totals -> apply_xy_shift (geotransform) -> apply_z_shift (band) -> stop when the
+ * incremental shift magnitude < tol or after max_iter iterations.  The state lives in a caller-owned struct so that
+ * one call can run the whole loop (max_steps <= 0) or a bounded number of iterations (max_steps > 0), with no host
+ * work between iterations other than the fit.  The source raster is modified IN PLACE (pass a copy to keep the
+ * original, as the reference does with mem_drv.CreateCopy, dem_align.py:294): its geotransform in src_desc.gt; its band
+ * through deferred z shifts (src_ndz/src_dz, applied by the front kernel while loading, folded into the band every
+ * DCR_ALIGN_MAX_PENDING iterations and by dcr_align_flush_z). */
+#define DCR_ALIGN_MAX_PENDING 4
+typedef struct dcr_align_iter {
+    double dx, dy, dz;           /* incremental shift returned by compute_offset */
+    int32_t status;              /* dcr_iter_result.status */
+    int32_t select_engine;
+    int32_t h, w;                /* common grid of the iteration */
+} dcr_align_iter;
+typedef struct dcr_align_state {
+    /* inputs (device pointers, caller-owned) */
+    const float* ref; int64_t ref_stride; dcr_raster_desc ref_desc;
+    float* src; int64_t src_stride; dcr_raster_desc src_desc;                 /* shifted in place */
+    const uint8_t* smask; int64_t smask_stride; dcr_raster_desc smask_desc;   /* world-fixed static mask or NULL */
+    float* dh; float* slope; float* aspect; uint8_t* maskbits;                /* iteration outputs, out_capacity pixels each */
+    int64_t out_capacity;
+    double tol, max_offset;      /* dem_align.py -tol, -max_offset */
+    float max_dz, slope_lo, slope_hi;
+    int32_t max_iter;
+    int32_t remove_outliers;
+    /* loop state: zero before the first call, carried across calls */
+    int32_t n_done;              /* iterations finished */
+    int32_t finished;            /* 1: converged (dm < tol) or max_iter reached */
+    int32_t exit_code;           /* 0 ok; 1-3: compute_offset sys.exit (dcr_iter_result.status); 5: total offset > max_offset */
+    int32_t src_ndz;             /* pending z shifts of the band */
+    float src_dz[16];
+    double dx_total, dy_total;
+    float dz_total;              /* accumulated in float32 like the reference (dz is np.float32) */
+    float _pad;
+    dcr_iter_result last;        /* full result of the last iteration */
+} dcr_align_state;
+/* Runs iterations until the loop finishes or max_steps (> 0) iterations were done in this call; appends one record per
+ * iteration to iters[0..iters_cap) (may be NULL); *n_iters = iterations run by this call.  flags: DCR_ITER_PROFILE,
+ * DCR_ITER_RADIX_ONLY.  Workspace: dcr_iteration_workspace_bytes(out_capacity). */
+int dcr_align_nuth(dcr_align_state* st, int max_steps, int flags, dcr_align_iter* iters, int iters_cap, int* n_iters,
+                   void* workspace, size_t workspace_bytes, void* stream);
+/* Writes the pending z shifts into the source band (call before reading the aligned band). */
+int dcr_align_flush_z(dcr_align_state* st, void* stream);
 
 /* ---- row-band mode: one very large raster split into bands of output rows, one band per GPU ----------------
  * (BASELINE.json configs[4]; the reference does not tile -- it loads whole arrays, dem_align.py:79-80.)

