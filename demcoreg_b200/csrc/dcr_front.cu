@@ -281,8 +281,8 @@ __device__ __forceinline__ float atan01(float t) {
 // limit, aspect within 3e-4 degrees of an integer degree (the 1-degree bin edges) -- is recomputed with
 // the FP64 formulation above.  Returns false when any input is NaN; *exact = true -> caller must call horn().
 __device__ __forceinline__ bool horn_fast(float w0, float w1, float w2, float w3, float w4, float w5, float w6,
-                                          float w7, float w8, float inv8ew, float inv8ns, float slope_lo,
-                                          float slope_hi, float* slope, float* aspect, bool* exact) {
+                                          float w7, float w8, float inv8ew, float inv8ns, float slope_mid,
+                                          float slope_half, float slope_tol, float* slope, float* aspect, bool* exact) {
     const float a = (w0 + w3 + w3 + w6);
     const float b = (w2 + w5 + w5 + w8);
     const float c = (w6 + w7 + w7 + w8);
@@ -292,12 +292,15 @@ __device__ __forceinline__ bool horn_fast(float w0, float w1, float w2, float w3
     // any NaN (nodata) among the 8 neighbours poisons dxs or dyf; the centre is tested separately
     if (isnan(dxs + dyf) || isnan(w4)) return false;
     const float gx = dxs * inv8ew, gy = dyf * inv8ns;
-    const float g = sqrtf(gx * gx + gy * gy);
+    // MUFU.SQRT (sqrt.approx, <= 1 ulp-class) instead of the IEEE sqrtf sequence: the guard bands below absorb it
+    float g;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(gx * gx + gy * gy));
     const bool big = g > 1.0f;
     float sa = atan01(big ? __fdividef(1.0f, g) : g);
     if (big) sa = 1.5707963267948966f - sa;
     const float s = sa * 57.29577951308232f;
-    bool ex = (fabsf(s - slope_lo) <= 2e-6f * slope_lo) || (fabsf(s - slope_hi) <= 2e-6f * slope_hi);
+    // slope within guard of either limit <=> | |s - mid| - half | small (one band of width 2e-6 * slope_hi for both)
+    bool ex = !(fabsf(fabsf(s - slope_mid) - slope_half) > slope_tol);
     *slope = s;
     if (dxs == 0.0f && dyf == 0.0f) {
         *aspect = __int_as_float(0x7fc00000);
@@ -312,7 +315,9 @@ __device__ __forceinline__ bool horn_fast(float w0, float w1, float w2, float w3
         float af = a * 57.29577951308232f;
         af = (af > 90.0f) ? (450.0f - af) : (90.0f - af);
         const float fr = af - floorf(af);
-        ex = ex || (fr < 3e-4f) || (fr > 1.0f - 3e-4f) || !(af >= 0.0f) || (af >= 360.0f) || isinf(mx);
+        // within 3e-4 deg of an integer degree (bin edge, incl. af == 0 / 360 and the exact multiples of 90 that an
+        // infinite gradient produces) or NaN -> exact path.  af lies in [0, 360] by construction.
+        ex = ex || !(fabsf(fr - 0.5f) <= 0.5f - 3e-4f);
         *aspect = af;
     }
     *exact = ex;
@@ -421,6 +426,7 @@ extern "C" int dcr_horn_slope_aspect(const float* dem, int h, int w, int64_t str
 #define F_SRC_C (F_TW + 8)   // 133 columns needed; 136 = multiple of 4 floats (TMA box rows are multiples of 16 bytes)
 #define F_REF_R (F_TH + 3)
 #define F_REF_C (F_TW + 8)   // 131 columns needed (+ up to 3 of TMA start alignment); 136
+#define F_MSK_C (F_TW + 16)  // mask tile pitch: 128 columns + up to 15 bytes of TMA start alignment
 #define F_SW_R (F_TH + 2)
 #define F_SW_C (F_TW + 2)
 #define F_ROWS_PER_THREAD (F_TH / 2)
@@ -430,8 +436,10 @@ extern "C" int dcr_horn_slope_aspect(const float* dem, int h, int w, int64_t str
 struct FrontParams {
     alignas(64) CUtensorMap tm_src;   // TMA descriptors of the two rasters (valid iff use_tma)
     alignas(64) CUtensorMap tm_ref;
+    alignas(64) CUtensorMap tm_msk;   // uint8 static mask (valid iff use_tma_mask)
     int use_tma;
     int tma_dx_src, tma_dx_ref;       // TMA boxes must start on a 16-byte column: extra leading columns (0..3)
+    int use_tma_mask, tma_dx_msk;     // same for the mask tile (0..15 leading bytes)
     DevGeom rg, sg;
     const float* ref;
     const float* src;
@@ -448,6 +456,7 @@ struct FrontParams {
     float max_dz;
     int use_max_dz;
     float slope_lo, slope_hi;
+    float slope_mid, slope_half, slope_tol;   // guard band of the FP32 Horn path around both slope limits
     float* dh;
     float* slope;
     float* aspect;
@@ -559,7 +568,8 @@ __global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ F
     float* s_src = s_src_base + (p.use_tma ? p.tma_dx_src : 0);
     float* s_ref = s_ref_base + (p.use_tma ? p.tma_dx_ref : 0);
     __shared__ unsigned long long s_cnt[3];
-    __shared__ unsigned char s_mask[F_TH * F_TW];       // static (stable-surface) mask of the tile, 1 = masked
+    __shared__ __align__(128) unsigned char s_mask_base[F_TH * F_MSK_C];   // static (stable-surface) mask tile, 1 = masked
+    unsigned char* s_mask = s_mask_base + (p.use_tma_mask ? p.tma_dx_msk : 0);
 
     const int tj0 = blockIdx.x * F_TW, ti0 = p.row_begin + blockIdx.y * F_TH;
     const int tid = threadIdx.x;
@@ -572,7 +582,10 @@ __global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ F
         if (tid == 0) mbar_init(&s_bar, 1);
         __syncthreads();
         if (tid == 0) {
-            mbar_expect_tx(&s_bar, (unsigned)((F_SRC_R * F_SRC_C + F_REF_R * F_REF_C) * sizeof(float)));
+            mbar_expect_tx(&s_bar, (unsigned)((F_SRC_R * F_SRC_C + F_REF_R * F_REF_C) * sizeof(float)) +
+                                       (p.use_tma_mask ? (unsigned)(F_TH * F_MSK_C) : 0u));
+            if (p.use_tma_mask)
+                tma_load_2d(s_mask_base, &p.tm_msk, tj0 + p.smask_nx0 - p.tma_dx_msk, ti0 + p.smask_ny0 - p.smask_row0, &s_bar);
             tma_load_2d(s_src_base, &p.tm_src, tj0 - 2 + p.sg.ix0 - p.tma_dx_src, ti0 - 2 + p.sg.iy0 - p.sg.row0, &s_bar);
             tma_load_2d(s_ref_base, &p.tm_ref, tj0 - 1 + p.rg.ix0 - p.tma_dx_ref, ti0 - 1 + p.rg.iy0 - p.rg.row0, &s_bar);
         }
@@ -581,7 +594,7 @@ __global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ F
         else stage_tile<F_SRC_R, F_SRC_C, false>(p.src, p.sg, ti0 - 2 + p.sg.iy0, tj0 - 2 + p.sg.ix0, s_src, tid);
         stage_tile<F_REF_R, F_REF_C, false>(p.ref, p.rg, ti0 - 1 + p.rg.iy0, tj0 - 1 + p.rg.ix0, s_ref, tid);
     }
-    if (p.smask) {
+    if (p.smask && !p.use_tma_mask) {
         // nearest-neighbour sample of the world-fixed mask; all 16 byte loads of a thread are issued before their
         // first use (a dependent load per pixel inside the main pass cost ~600 cycles of latency per row)
         unsigned char mv[(F_TH * F_TW) / 256];
@@ -594,13 +607,24 @@ __global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ F
                 mv[k] = __ldg(p.smask + (long long)(mi - p.smask_row0) * p.smask_stride + mj);
         }
 #pragma unroll
-        for (int k = 0; k < (F_TH * F_TW) / 256; ++k) s_mask[k * 256 + tid] = mv[k];
+        for (int k = 0; k < (F_TH * F_TW) / 256; ++k) s_mask[((k * 256 + tid) >> 7) * F_MSK_C + ((k * 256 + tid) & (F_TW - 1))] = mv[k];
     }
     if (p.use_tma) {
         // wait for the bytes (bounded spin: a mis-programmed copy must fault, not hang the GPU), then nodata -> NaN
         unsigned spins = 0;
         while (!mbar_try_wait(&s_bar, 0)) {
             if (++spins > (1u << 26)) __trap();
+        }
+        if (p.use_tma_mask) {
+            // the copy engine fills bytes outside the mask raster with 0; outside = masked (1): edge tiles only
+            const int mi0 = ti0 + p.smask_ny0, mj0 = tj0 + p.smask_nx0;
+            if (mi0 < p.smask_row0 || mj0 < 0 || mi0 + F_TH > p.smask_row1 || mj0 + F_TW > p.smask_w) {
+                for (int e = tid; e < F_TH * F_TW; e += 256) {
+                    const int mi = mi0 + (e >> 7), mj = mj0 + (e & (F_TW - 1));
+                    if (mi < p.smask_row0 || mj < 0 || mi >= p.smask_row1 || mj >= p.smask_w)
+                        s_mask[(e >> 7) * F_MSK_C + (e & (F_TW - 1))] = 1;
+                }
+            }
         }
         // fix-up pass over the landed tiles, 4 elements per access (tiles are 128-byte aligned, sizes multiples of 4)
         const float qnan = __int_as_float(0x7fc00000);
@@ -702,7 +726,7 @@ __global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ F
         const float* qs = s_src + (rbeg + 4) * F_SRC_C + (c + 1);
         const float* qr = s_ref + (rbeg + 3) * F_REF_C + c;
         float* swp = s_sw + (rbeg + 1) * F_SW_C + (c + 1);
-        const unsigned char* mk = s_mask + rbeg * F_TW + c;
+        const unsigned char* mk = s_mask + rbeg * F_MSK_C + c;
         const bool has_mask = p.smask != nullptr;
         const bool has_warped = (p.ref_w != nullptr) || (p.src_w != nullptr);
         const float qnan = __int_as_float(0x7fc00000);
@@ -749,7 +773,7 @@ __global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ F
             qs += F_SRC_C;
             qr += F_REF_C;
             swp += F_SW_C;
-            mk += F_TW;
+            mk += F_MSK_C;
         }
     }
     __syncthreads();
@@ -780,8 +804,8 @@ __global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ F
                 if (rr >= r_lo && rr < r_hi) {
                     float sv, av;
                     bool ex;
-                    if (horn_fast(w0, w1, w2, w3, w4, w5, w6, w7, w8, p.inv8ew, p.inv8ns, p.slope_lo, p.slope_hi, &sv, &av,
-                                  &ex)) {
+                    if (horn_fast(w0, w1, w2, w3, w4, w5, w6, w7, w8, p.inv8ew, p.inv8ns, p.slope_mid, p.slope_half,
+                                  p.slope_tol, &sv, &av, &ex)) {
                         if (ex) horn(w0, w1, w2, w3, w4, w5, w6, w7, w8, p.ewres, p.nsres, true, true, &sv, &av);
                         sl = sv;
                         // range_fltr(slope, slope_lim): masked_outside keeps lo <= s <= hi
@@ -841,18 +865,21 @@ static EncodeTiledFn get_encode_tiled() {
     }
     return fn;
 }
-// 2-D float32 tensor map over the rows held in memory; box = (box_w x box_h); OOB elements read as NaN
-static bool make_tmap(CUtensorMap* tm, const float* base, int rows, int cols, long long stride_elems, int box_w, int box_h) {
+// 2-D tensor map (float32, OOB -> NaN; or uint8, OOB -> 0) over the rows held in memory; box = (box_w x box_h)
+static bool make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, long long stride_elems, int box_w, int box_h,
+                      bool u8 = false) {
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) return false;
-    if ((((uintptr_t)base) & 15) != 0 || (stride_elems & 3) != 0 || rows <= 0 || cols <= 0) return false;
+    const size_t esz = u8 ? 1 : sizeof(float);
+    if ((((uintptr_t)base) & 15) != 0 || ((stride_elems * esz) & 15) != 0 || rows <= 0 || cols <= 0) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)stride_elems * sizeof(float)};
+    const cuuint64_t strides[1] = {(cuuint64_t)stride_elems * esz};
     const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
     const cuuint32_t estr[2] = {1, 1};
-    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,  // (L2_128B promotion faults with this 544-byte box)
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA) == CUDA_SUCCESS;
+    return enc(tm, u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box,
+               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE,  // (L2_128B promotion faults with this 544-byte box)
+               u8 ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE : CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA) == CUDA_SUCCESS;
 }
 
 int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cudaStream_t stream) {
@@ -888,6 +915,9 @@ int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cuda
     p.use_max_dz = a->use_max_dz;
     p.slope_lo = a->slope_lo;
     p.slope_hi = a->slope_hi;
+    p.slope_mid = 0.5f * (a->slope_lo + a->slope_hi);
+    p.slope_half = 0.5f * (a->slope_hi - a->slope_lo);
+    p.slope_tol = 2e-6f * fmaxf(fabsf(a->slope_lo), fabsf(a->slope_hi)) + 4e-7f * fabsf(p.slope_mid);
     p.dh = a->dh;
     p.slope = a->slope;
     p.aspect = a->aspect;
@@ -951,6 +981,11 @@ int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cuda
         // "illegal instruction"): start up to 3 columns early (the 136-wide boxes have the room) and shift the views
         p.tma_dx_src = ((p.sg.ix0 - 2) % 4 + 4) % 4;
         p.tma_dx_ref = ((p.rg.ix0 - 1) % 4 + 4) % 4;
+        if (ok && a->smask &&
+            make_tmap(&p.tm_msk, a->smask, p.smask_row1 - p.smask_row0, a->smask_w, a->smask_stride, F_MSK_C, F_TH, true)) {
+            p.use_tma_mask = 1;
+            p.tma_dx_msk = (a->smask_nx0 % 16 + 16) % 16;
+        }
     }
     const size_t smem = (size_t)(F_SRC_WORDS + F_REF_WORDS + F_SW_R * F_SW_C) * sizeof(float);
     static bool attr_set = false;
