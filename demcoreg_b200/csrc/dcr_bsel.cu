@@ -16,8 +16,11 @@
 //                            launch, last-CTA-done finalisation), then applies numpy's linear interpolation.
 // Same semantics as dcr_sel_enqueue (numpy.percentile, linear, exact float64 rank).
 #include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include "dcr_common.cuh"
 #include "dcr_internal.cuh"
+#include "dcr_bsel_collect.cuh"
 
 #define BS_S 8192          // samples
 #define BS_THREADS 256
@@ -43,17 +46,6 @@ __device__ __forceinline__ bool bsel_key(const SelView& v, float center, float x
     if (isnan(x)) return false;
     *key = dcr_f2key(x + 0.0f);  // -0 -> +0: float comparisons (main pass) and key order must agree
     return true;
-}
-
-__device__ __forceinline__ void bsel_ranks(long long count, double q_percent, long long* klo, long long* khi, double* g) {
-    const double vi = (double)(count - 1) * (q_percent / 100.0);  // exact rank in float64
-    *klo = (long long)floor(vi);
-    *khi = *klo + 1 < count ? *klo + 1 : count - 1;
-    *g = vi - (double)(*klo);
-}
-
-__device__ __forceinline__ void bsel_publish(BselState* st) {
-    if (st->publish) *st->publish = st->result;
 }
 
 __global__ void __launch_bounds__(1024) bsel_sample_kernel(const SelView v, double q_percent, BselState* st, float* publish) {
@@ -206,149 +198,28 @@ __global__ void __launch_bounds__(1024) bsel_sample_kernel(const SelView v, doub
     }
 }
 
-#define BS_STAGE 4096  // per-CTA staging of in-bracket keys (one global reservation per CTA instead of per warp)
-__device__ void bsel_find_block(BselState* st, unsigned* ghist, double q_percent, unsigned cap, unsigned* s_cum, unsigned* s_scratch);
-
+// One streaming pass: the collector (dcr_bsel_collect.cuh) does the counting / candidate gathering / level-0 find.
+typedef BselCollector<16, 4096> MainCollector;
 __global__ void __launch_bounds__(BS_THREADS) bsel_main_kernel(const SelView v, BselState* st, unsigned* ghist,
                                                                unsigned* __restrict__ cand, unsigned cap, double q_percent) {
-    __shared__ unsigned h[2048];
-    __shared__ unsigned s_buf[BS_STAGE];
-    __shared__ float s_priv[16 * BS_THREADS];
-    __shared__ unsigned s_n, s_gbase;
-    __shared__ unsigned long long s_below, s_total;
+    extern __shared__ __align__(16) unsigned char bsel_smem[];
+    MainCollector::Shared* sh = reinterpret_cast<MainCollector::Shared*>(bsel_smem);
+    __shared__ unsigned s_scr[33];
     if (st->done) return;
-    for (int k = threadIdx.x; k < 2048; k += BS_THREADS) h[k] = 0u;
-    if (threadIdx.x == 0) { s_below = 0ull; s_total = 0ull; s_n = 0u; }
+    MainCollector col;
+    col.init(sh, st, cand, cap);
     __syncthreads();
     const long long n = v.n_ptr ? *v.n_ptr : v.n;
     const float center = v.center_ptr ? *v.center_ptr : v.center_imm;
-    const unsigned klo = st->klo;
-    const int shift = st->shift;
     const unsigned reject = v.m ? v.reject : 0u;
     const int transform = v.transform;
-    const int lane = threadIdx.x & 31;
-    const float flo = st->flo, fhi = st->fhi;
-    unsigned below = 0, total = 0;   // total accumulates below + above + in-bracket (NaNs fail every comparison)
-    // in-bracket values go to thread-private shared-memory slots first (no warp collective per element); the group
-    // end then moves them with a warp-uniform trip count of max(count) ~ 3 instead of 16 divergent passes
-    float* mine = s_priv + threadIdx.x;   // slot k of this thread: mine[k * BS_THREADS]
-    unsigned c = 0;
     dcr_stream1_groups(v.x, v.m, n,
         [&](float x, unsigned mb, long long, int) {
             if (transform == 1) x = fabsf(x - center);
-            const bool ok = !(mb & reject);
-            const bool lo = ok && (x < flo), hi = ok && (x > fhi), in = ok && (x >= flo) && (x <= fhi);
-            below += lo;
-            total += lo | hi;
-            if (in) { mine[c * BS_THREADS] = x; ++c; }
+            col.add(x, !(mb & reject));
         },
-        [&]() {
-            const unsigned cmax = __reduce_max_sync(0xffffffffu, c);
-            if (cmax) {
-                total += c;
-                const unsigned inc = dcr_warp_incl_scan(c);
-                unsigned base = 0;
-                if (lane == 31) base = atomicAdd(&s_n, inc);
-                base = __shfl_sync(0xffffffffu, base, 31);
-                unsigned pos = base + inc - c;
-                for (unsigned k = 0; k < cmax; ++k) {
-                    if (k < c) {
-                        const unsigned key = dcr_f2key(mine[k * BS_THREADS] + 0.0f);
-                        if (pos < BS_STAGE) s_buf[pos] = key;
-                        else {  // staging full (dense bracket): straight to the global buffer
-                            const unsigned gq = atomicAdd(&st->ncand, 1u);
-                            if (gq < cap) cand[gq] = key;
-                        }
-                        ++pos;
-                        atomicAdd(&h[(key - klo) >> shift], 1u);
-                    }
-                }
-            }
-            c = 0;
-        });
-    below = __reduce_add_sync(0xffffffffu, below);
-    total = __reduce_add_sync(0xffffffffu, total);
-    if (lane == 0) {
-        if (below) atomicAdd(&s_below, (unsigned long long)below);
-        if (total) atomicAdd(&s_total, (unsigned long long)total);
-    }
-    __syncthreads();
-    const unsigned nst = s_n < BS_STAGE ? s_n : BS_STAGE;
-    if (threadIdx.x == 0) {
-        s_gbase = nst ? atomicAdd(&st->ncand, nst) : 0u;
-        if (s_below) atomicAdd(&st->below, s_below);
-        if (s_total) atomicAdd(&st->total, s_total);
-    }
-    for (int k = threadIdx.x; k < 2048; k += BS_THREADS)
-        if (h[k]) atomicAdd(&ghist[k], h[k]);
-    __syncthreads();
-    const unsigned gb = s_gbase;
-    for (unsigned k = threadIdx.x; k < nst; k += BS_THREADS)
-        if (gb + k < cap) cand[gb + k] = s_buf[k];
-    // the last CTA to finish locates the ranks in the bracket histogram (saves a dependent launch)
-    __shared__ bool s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    unsigned* s_cum = s_buf;            // reuse the staging buffer (>= 2049 words)
-    __shared__ unsigned s_scr[33];
-    bsel_find_block(st, ghist, q_percent, cap, s_cum, s_scr);
-}
-
-// Level-0 find (run by the LAST CTA of bsel_main_kernel): the bracket-histogram bin of each of the two ranks,
-// after VERIFYING that both ranks fall inside the bracket and that no candidate was dropped.
-// off = key - klo; bin0 = off >> shift.  256 threads, 8 bins each.
-__device__ void bsel_find_block(BselState* st, unsigned* ghist, double q_percent, unsigned cap, unsigned* s_cum /*[2049]*/,
-                                unsigned* s_scratch /*[33]*/) {
-    const int t = threadIdx.x;
-    unsigned v[8], sum = 0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) { v[q] = __ldcg(ghist + t * 8 + q); sum += v[q]; }
-    unsigned total;
-    unsigned ex = dcr_block_excl_scan(sum, s_scratch, &total);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) { s_cum[t * 8 + q] = ex; ex += v[q]; }
-    if (t == 0) s_cum[2048] = total;
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 8; ++q) ghist[t * 8 + q] = 0u;
-    if (t == 0) {
-        const long long count = (long long)st->total;
-        st->count = count;
-        if (count == 0) {
-            st->empty = 1; st->done = 1;
-            st->v_lo = st->v_hi = st->result = __int_as_float(0x7fc00000);
-            bsel_publish(st);
-        } else {
-            long long klo, khi; double g;
-            bsel_ranks(count, q_percent, &klo, &khi, &g);
-            st->gamma = g;
-            const long long c[2] = {klo - (long long)st->below, khi - (long long)st->below};
-            const long long nin = (long long)total;
-            const bool ok = (c[0] >= 0) && (c[1] < nin) && (st->ncand <= cap) && ((long long)st->ncand == nin);
-            if (!ok) { st->fallback = 1; st->done = 1; }
-            else {
-                for (int r = 0; r < 2; ++r) {
-                    int lo = 0, hi = 2047;
-                    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((long long)s_cum[mid] <= c[r]) lo = mid; else hi = mid - 1; }
-                    st->prefix[r] = (unsigned)lo << st->shift;
-                    st->rem[r] = c[r] - (long long)s_cum[lo];
-                }
-                st->cur_shift = st->shift;
-                if (st->shift == 0) {  // bins are single keys already
-                    const float x0 = dcr_key2f(st->klo + st->prefix[0]), x1 = dcr_key2f(st->klo + st->prefix[1]);
-                    st->v_lo = x0; st->v_hi = x1;
-                    st->result = dcr_lerp32(x0, x1, g);
-                    st->done = 1;
-                    bsel_publish(st);
-                }
-            }
-        }
-        st->ticket = 0;
-    }
+        [&]() { col.drain(); });
+    col.finish(ghist, q_percent, gridDim.x, s_scr);
 }
 
 // Refinement over the candidate buffer only (a few per cent of the data): histogram the next <= 11 bits of
@@ -436,19 +307,51 @@ unsigned dcr_bsel_cap(long long n) {
     return (unsigned)c;
 }
 
-int dcr_bsel_enqueue(const SelView& v, double q_percent, BselState* st, void* scratch, long long n_max, cudaStream_t s,
-                     float* publish) {
-    const unsigned cap = dcr_bsel_cap(n_max);
+// scratch layout: [4096 u32 histogram][cap u32 candidate keys]
+void dcr_bsel_buffers(void* scratch, long long n_max, unsigned** hist, unsigned** cand, unsigned* cap) {
     char* p = (char*)scratch;
-    unsigned* hist = (unsigned*)p;
-    p += dcr_al256(4096 * sizeof(unsigned));
-    unsigned* cand = (unsigned*)p;
-    const int grid = dcr_num_sms() * 8;
+    *hist = (unsigned*)p;
+    *cand = (unsigned*)(p + dcr_al256(4096 * sizeof(unsigned)));
+    *cap = dcr_bsel_cap(n_max);
+}
+
+// step 1 of a selection whose streaming pass is fused into another kernel (BselCollector): clear + sample + bracket
+int dcr_bsel_sample_enqueue(const SelView& v, double q_percent, BselState* st, void* scratch, long long n_max, cudaStream_t s,
+                            float* publish) {
+    unsigned *hist, *cand, cap;
+    dcr_bsel_buffers(scratch, n_max, &hist, &cand, &cap);
     DCR_CUDA_OK(cudaMemsetAsync(hist, 0, 4096 * sizeof(unsigned), s));
     bsel_sample_kernel<<<1, 1024, 0, s>>>(v, q_percent, st, publish);
-    bsel_main_kernel<<<grid, BS_THREADS, 0, s>>>(v, st, hist, cand, cap, q_percent);  // + level-0 find in its last CTA
+    DCR_LAUNCH_OK("bsel_sample_kernel");
+    return 0;
+}
+// step 3: radix refinement over the candidates gathered by the collector
+int dcr_bsel_refine_enqueue(BselState* st, void* scratch, long long n_max, cudaStream_t s) {
+    unsigned *hist, *cand, cap;
+    dcr_bsel_buffers(scratch, n_max, &hist, &cand, &cap);
     bsel_refine_kernel<<<dcr_num_sms() * 4, BS_THREADS, 0, s>>>(st, cand, hist);  // shift -> max(shift-11, 0)
     bsel_refine_kernel<<<dcr_num_sms() * 4, BS_THREADS, 0, s>>>(st, cand, hist);  // -> 0 (returns at once if done)
-    DCR_LAUNCH_OK("bsel kernels");
+    DCR_LAUNCH_OK("bsel_refine_kernel");
     return 0;
+}
+
+int dcr_bsel_enqueue(const SelView& v, double q_percent, BselState* st, void* scratch, long long n_max, cudaStream_t s,
+                     float* publish) {
+    unsigned *hist, *cand, cap;
+    dcr_bsel_buffers(scratch, n_max, &hist, &cand, &cap);
+    int rc = dcr_bsel_sample_enqueue(v, q_percent, st, scratch, n_max, s, publish);
+    if (rc) return rc;
+    static int grid0 = 0;   // SMs x 8, like the other streaming kernels
+    if (!grid0) {
+        DCR_CUDA_OK(cudaFuncSetAttribute(bsel_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(MainCollector::Shared)));
+        grid0 = dcr_num_sms() * 8;
+    }
+    // a CTA stages up to 4096 in-bracket keys (~6 % of what it streams): keep its share below 57k elements
+    long long grid = (n_max + 57343) / 57344;
+    if (grid < grid0) grid = grid0;
+    if (grid > (1 << 20)) grid = 1 << 20;
+    bsel_main_kernel<<<(unsigned)grid, BS_THREADS, sizeof(MainCollector::Shared), s>>>(v, st, hist, cand, cap, q_percent);  // + level-0 find
+    DCR_LAUNCH_OK("bsel_main_kernel");
+    return dcr_bsel_refine_enqueue(st, scratch, n_max, s);
 }

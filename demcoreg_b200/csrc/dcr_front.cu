@@ -463,6 +463,7 @@ struct FrontParams {
     unsigned char* maskbits;
     float* ref_w;
     float* src_w;
+    unsigned short* bin;       // optional aspect-bin code per pixel (see the Horn loop), or nullptr
     unsigned long long* counters;  // [0]=count_base [1]=count_maxdz [2]=count_slope
 };
 
@@ -816,8 +817,14 @@ __global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ F
                 if (!(valid_bits & (1u << rr))) bits |= DCR_M_BASE;
                 else if (maxdz_bits & (1u << rr)) bits |= DCR_M_MAXDZ;
                 p.slope[o] = sl;
-                p.aspect[o] = as;
+                if (p.aspect) p.aspect[o] = as;
                 p.maskbits[o] = (unsigned char)bits;
+                if (p.bin) {
+                    // aspect bin of the Nuth-Kaab sample (coreglib.py:246-262: floor(aspect), 360 joins the last bin) for the
+                    // pixels inside every mask known here; only the MAD filter (decided later) can still remove them
+                    int bi = (int)as;
+                    p.bin[o] = (unsigned short)(bits == 0u ? (bi > DCR_NBINS - 1 ? DCR_NBINS - 1 : bi) : DCR_BIN_INVALID);
+                }
             }
             o += p.w;
             w0 = w3; w1 = w4; w2 = w5;
@@ -882,9 +889,9 @@ static bool make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, lon
                u8 ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE : CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA) == CUDA_SUCCESS;
 }
 
-int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cudaStream_t stream) {
+int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cudaStream_t stream, unsigned short* bin) {
     DCR_ARG(a, "null args");
-    DCR_ARG(a->ref && a->src && a->dh && a->slope && a->aspect && a->maskbits, "null raster pointer");
+    DCR_ARG(a->ref && a->src && a->dh && a->slope && a->maskbits, "null raster pointer");
     DCR_ARG(a->h > 0 && a->w > 0, "empty grid");
     FrontParams p;
     memset(&p, 0, sizeof(p));
@@ -925,6 +932,7 @@ int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cuda
     p.ref_w = a->ref_w;
     p.src_w = a->src_w;
     p.counters = counters;
+    p.bin = bin;
     DCR_ARG(a->src_ndz >= 0 && a->src_ndz <= 16, "0 <= src_ndz <= 16");
     p.sg.ndz = a->src_ndz;
     for (int k = 0; k < a->src_ndz; ++k) p.sg.dz[k] = a->src_dz[k];
@@ -1000,5 +1008,5 @@ int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cuda
 }
 
 extern "C" int dcr_warp_diff_horn(const dcr_front_args* args, void* stream) {
-    return dcr_front_launch(args, nullptr, (cudaStream_t)stream);
+    return dcr_front_launch(args, nullptr, (cudaStream_t)stream, nullptr);
 }

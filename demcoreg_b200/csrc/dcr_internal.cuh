@@ -4,7 +4,9 @@
 
 // ---- front end (dcr_front.cu) ----
 // counters (device, 3 x u64, zeroed by the caller): base-valid, after max_dz, slope-valid
-int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cudaStream_t stream);
+// bin (device, h*w, optional): also emit the aspect-bin code of every pixel (DCR_BIN_INVALID outside the masks known to
+// the front end)
+int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cudaStream_t stream, unsigned short* bin = nullptr);
 
 // ---- exact selection (dcr_select.cu) ----
 // A "view" of the values taking part in a selection; all device pointers.
@@ -57,6 +59,11 @@ unsigned dcr_bsel_cap(long long n);
 size_t dcr_bsel_scratch_bytes(long long n);
 int dcr_bsel_enqueue(const SelView& v, double q_percent, BselState* st, void* scratch, long long n_max, cudaStream_t s,
                      float* publish = nullptr);
+// the same selection in three steps, for callers that fuse the streaming pass into a kernel of their own (BselCollector)
+void dcr_bsel_buffers(void* scratch, long long n_max, unsigned** hist, unsigned** cand, unsigned* cap);
+int dcr_bsel_sample_enqueue(const SelView& v, double q_percent, BselState* st, void* scratch, long long n_max, cudaStream_t s,
+                            float* publish = nullptr);
+int dcr_bsel_refine_enqueue(BselState* st, void* scratch, long long n_max, cudaStream_t s);
 
 // ---- nuth (dcr_nuth.cu) ----
 struct NuthDev;  // device block
@@ -67,7 +74,7 @@ int dcr_chunk_count_scan_enqueue(const float* x, const unsigned char* m, unsigne
                                  long long* chunk_off, long long* total, cudaStream_t s);
 int dcr_compress_enqueue(const float* x, const unsigned char* m, unsigned reject, long long n, const long long* chunk_off,
                          long long stride_imm, const long long* stride_ptr, float* dense, long long cap,
-                         cudaStream_t s, const long long* base_ptr = nullptr);
+                         cudaStream_t s, const long long* base_ptr = nullptr, bool mask_only_validity = false);
 int dcr_chunk_scan_enqueue(const unsigned* cnt, long long nchunks, long long* off, long long* total, cudaStream_t s);
 int dcr_sel_hist_pass(const SelView& v, SelState* st, unsigned* hist, int pass, cudaStream_t s);
 int dcr_sel_find_pass(SelState* st, unsigned* hist, double q_percent, int pass, cudaStream_t s);

@@ -38,29 +38,6 @@ struct NuthPartial {
     double s, ss;
 };
 
-// y = dh / tan(deg2rad(slope)) in float32, like numpy (deg2rad = x * f32(pi/180); np.tan on float32 is a
-// few-ulp libm/SVML routine, so FP32 tanf -- also a few ulp -- is as close as any implementation can get).
-__device__ __forceinline__ float nuth_y(float dh, float slope) {
-    const float rad = slope * 0.017453292519943295f;
-    float t;
-    if (fabsf(rad) <= 0.78539816f) {
-        // |x| <= pi/4 (slopes up to 45 deg; the default filter keeps 0.1..40): odd minimax polynomial (Cephes tanf),
-        // max 1.3 ulp / 14 % not correctly rounded -- numpy's own float32 tan: 1.5 ulp / 24 % (measured on 2e6 samples);
-        // avoids the inlined Payne-Hanek slow path of tanf (code size) and its range reduction
-        const float z = rad * rad;
-        float p = 9.38540185543e-3f;
-        p = fmaf(p, z, 3.11992232697e-3f);
-        p = fmaf(p, z, 2.44301354525e-2f);
-        p = fmaf(p, z, 5.34112807005e-2f);
-        p = fmaf(p, z, 1.33387994085e-1f);
-        p = fmaf(p, z, 3.33331568548e-1f);
-        t = fmaf(p * z, rad, rad);
-    } else {
-        t = tanf(rad);
-    }
-    return dh / t;
-}
-
 __global__ void __launch_bounds__(256) nuth_prepare_kernel(const float* __restrict__ dh, const float* __restrict__ slope,
                                                            const float* __restrict__ aspect,
                                                            const unsigned char* __restrict__ m, unsigned reject, long long n,
@@ -142,12 +119,56 @@ __global__ void __launch_bounds__(256) nuth_prepare_kernel(const float* __restri
     }
 }
 
+// first level for many partials (one per 2048-element chunk): CTA b reduces a contiguous range, fixed order
+#define NUTH_RED_CTAS 64
+__global__ void __launch_bounds__(256) nuth_moments_reduce_kernel(const NuthPartial* __restrict__ part, int nparts,
+                                                                  NuthPartial* __restrict__ out) {
+    __shared__ NuthPartial sp[256];
+    const int len = (nparts + NUTH_RED_CTAS - 1) / NUTH_RED_CTAS;
+    const int lo = blockIdx.x * len, hi = min(nparts, lo + len);
+    NuthPartial q; q.n = 0; q.s = 0; q.ss = 0;
+    for (int k0 = lo + threadIdx.x; k0 < hi; k0 += 256 * 4) {
+        NuthPartial t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u * 256;
+            if (k < hi) t[u] = part[k];
+            else { t[u].n = 0; t[u].s = 0; t[u].ss = 0; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { q.n += t[u].n; q.s += t[u].s; q.ss += t[u].ss; }
+    }
+    sp[threadIdx.x] = q;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            sp[threadIdx.x].n += sp[threadIdx.x + o].n;
+            sp[threadIdx.x].s += sp[threadIdx.x + o].s;
+            sp[threadIdx.x].ss += sp[threadIdx.x + o].ss;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = sp[0];
+}
+
 // single thread block: fixed-order reduction of the partials -> mean/std (float32) -> rmin/rmax
 __global__ void __launch_bounds__(256) nuth_moments_final_kernel(const NuthPartial* __restrict__ part, int nparts,
                                                                  int remove_outliers, NuthDev* nd) {
     __shared__ NuthPartial sp[256];
     NuthPartial q; q.n = 0; q.s = 0; q.ss = 0;
-    for (int k = threadIdx.x; k < nparts; k += 256) { q.n += part[k].n; q.s += part[k].s; q.ss += part[k].ss; }
+    // (8 independent loads in flight per thread; the additions keep their order: one partial per chunk = 32k of them
+    //  for an 8192^2 raster when the fused mask update produced them)
+    for (int k0 = threadIdx.x; k0 < nparts; k0 += 256 * 8) {
+        NuthPartial t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = k0 + u * 256;
+            if (k < nparts) t[u] = part[k];
+            else { t[u].n = 0; t[u].s = 0; t[u].ss = 0; }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { q.n += t[u].n; q.s += t[u].s; q.ss += t[u].ss; }
+    }
     sp[threadIdx.x] = q;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
@@ -577,6 +598,11 @@ struct NuthWs {
     unsigned long long* cand;   // fast bin path: (key << 32 | bin << 16 | fine cell) of the elements in the median coarse cells
     unsigned cand_cap;
 };
+// partial moments: one per CTA of the prepare kernel, or one per 2048-element chunk of the fused mask update
+static long long nuth_nparts(long long n, int grid) {
+    const long long nch = (n + 2047) / 2048;
+    return (nch > grid ? nch : grid) + NUTH_RED_CTAS;   // + the first-level results of nuth_moments_reduce_kernel
+}
 static unsigned nuth_cand_cap(long long n) {
     long long c = n / 8;
     if (c < 65536) c = 65536;
@@ -584,14 +610,14 @@ static unsigned nuth_cand_cap(long long n) {
     return (unsigned)c;
 }
 static size_t nuth_ws_bytes(long long n, int grid) {
-    return dcr_al256(n * sizeof(float)) + dcr_al256(n * sizeof(unsigned short)) + dcr_al256(grid * sizeof(NuthPartial)) +
+    return dcr_al256(n * sizeof(float)) + dcr_al256(n * sizeof(unsigned short)) + dcr_al256((size_t)nuth_nparts(n, grid) * sizeof(NuthPartial)) +
            dcr_al256((size_t)2 * NB * 2048 * sizeof(unsigned)) + dcr_al256(sizeof(NuthDev)) +
            dcr_al256((size_t)nuth_cand_cap(n) * sizeof(unsigned long long));
 }
 static int nuth_ws_carve(DcrBump& ws, long long n, int grid, NuthWs* w) {
     w->y = ws.take<float>(n);
     w->bin = ws.take<unsigned short>(n);
-    w->part = ws.take<NuthPartial>(grid);
+    w->part = ws.take<NuthPartial>(nuth_nparts(n, grid));
     w->ghist = ws.take<unsigned>((size_t)2 * NB * 2048);
     w->nd = ws.take<NuthDev>(1);
     w->cand_cap = nuth_cand_cap(n);
@@ -643,6 +669,20 @@ static int nuth_enqueue(const float* dh, const float* slope, const float* aspect
     nuth_moments_final_kernel<<<1, 256, 0, s>>>(w.part, grid, remove_outliers, w.nd);
     if (after_prepare) DCR_CUDA_OK(cudaEventRecord(after_prepare, s));
     DCR_LAUNCH_OK("nuth prepare kernels");
+    if (fast_bins) return nuth_bins_fast_enqueue(n, w, s);
+    return nuth_bins_radix_enqueue(n, w, grid, s);
+}
+// the same when y / bin / the partial moments already exist (front kernel + fused mask update of the iteration driver)
+static int nuth_enqueue_prepared(long long n, long long nparts, int remove_outliers, const NuthWs& w, int grid, cudaStream_t s,
+                                 cudaEvent_t after_prepare, int fast_bins) {
+    if (nparts > 4096) {
+        nuth_moments_reduce_kernel<<<NUTH_RED_CTAS, 256, 0, s>>>(w.part, (int)nparts, w.part + nparts);
+        nuth_moments_final_kernel<<<1, 256, 0, s>>>(w.part + nparts, NUTH_RED_CTAS, remove_outliers, w.nd);
+    } else {
+        nuth_moments_final_kernel<<<1, 256, 0, s>>>(w.part, (int)nparts, remove_outliers, w.nd);
+    }
+    if (after_prepare) DCR_CUDA_OK(cudaEventRecord(after_prepare, s));
+    DCR_LAUNCH_OK("nuth_moments_final_kernel");
     if (fast_bins) return nuth_bins_fast_enqueue(n, w, s);
     return nuth_bins_radix_enqueue(n, w, grid, s);
 }
@@ -779,12 +819,13 @@ extern "C" int dcr_apply_z_shift(float* band, int h, int w, int64_t stride, doub
 
 // several deferred scalar shifts in ONE read-modify-write pass (same ordered float32 adds as separate calls)
 struct ZSeq { float dz[16]; int n; };
-__global__ void __launch_bounds__(256) zshift_seq_kernel(float* __restrict__ band, int h, int w, long long stride, double ndv,
-                                                         double tol, float ndv32, ZSeq z) {
+__global__ void __launch_bounds__(256) zshift_seq_kernel(float* __restrict__ band, int h, int w, long long stride, float zlo,
+                                                         float zhi, float ndv32, ZSeq z) {
+    // masked_values(|x - ndv| <= tol) as the equivalent float32 interval [zlo, zhi] (see gm_bounds in dcr_front.cu)
     const long long n = (long long)h * w;
     const long long step = (long long)gridDim.x * 256;
     auto shift = [&](float v) {
-        for (int q = 0; q < z.n; ++q) v = (fabs((double)v - ndv) <= tol) ? ndv32 : v + z.dz[q];
+        for (int q = 0; q < z.n; ++q) v = (v >= zlo && v <= zhi) ? ndv32 : v + z.dz[q];
         return v;
     };
     if (stride == w && DCR_AL16(band)) {   // contiguous band: float4 read-modify-write
@@ -813,8 +854,13 @@ extern "C" int dcr_apply_z_shift_seq(float* band, int h, int w, int64_t stride, 
     ZSeq z;
     z.n = n;
     for (int k = 0; k < 16; ++k) z.dz[k] = k < n ? dz[k] : 0.f;
+    // float32 interval equivalent to |x - ndv| <= 1e-8 + 1e-5|ndv| evaluated in float64
     const double tol = 1e-8 + 1e-5 * fabs(ndv);
-    zshift_seq_kernel<<<dcr_num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(band, h, w, stride, ndv, tol, (float)ndv, z);
+    const double dl = ndv - tol, dh = ndv + tol;
+    float zlo = (float)dl, zhi = (float)dh;
+    if ((double)zlo < dl) zlo = nextafterf(zlo, INFINITY);
+    if ((double)zhi > dh) zhi = nextafterf(zhi, -INFINITY);
+    zshift_seq_kernel<<<dcr_num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(band, h, w, stride, zlo, zhi, (float)ndv, z);
     DCR_LAUNCH_OK("zshift_seq_kernel");
     return 0;
 }
@@ -853,29 +899,76 @@ __global__ void mad_thresholds_kernel(IterDev* d, int remove_outliers) {
 }
 
 #define MU_CHUNK 2048
+// MAD filter (filtlib.mad_fltr <- dem_align.py:46) applied to the mask bytes + per-chunk counts of the final mask.
+// NUTH: this pass decides the last mask, so it also produces the Nuth-Kaab samples of compute_offset_nuth right away
+// (no separate "prepare" pass over dh/slope/aspect/mask): y = dh / tan(slope) for the pixels of the final common mask
+// (coreglib.py:229-233), count / sum / sum of squares of y (coreglib.py:238; one partial per chunk, reduced in a fixed
+// order), and the bin code -- emitted by the front kernel from the aspect -- invalidated where the MAD filter removes
+// a pixel.  The arithmetic of a bandwidth-bound pass is free; the front kernel is issue-bound and could not host it.
+template <bool NUTH>
 __global__ void __launch_bounds__(256) mask_update_kernel(const float* __restrict__ dh, unsigned char* m,
-                                                          long long n, IterDev* d, unsigned* __restrict__ chunk_cnt) {
+                                                          long long n, IterDev* d, unsigned* __restrict__ chunk_cnt,
+                                                          const float* __restrict__ slope, float* __restrict__ y,
+                                                          unsigned short* __restrict__ bin, NuthPartial* __restrict__ part) {
     __shared__ unsigned s_a[8], s_b[8];
+    __shared__ NuthPartial sp[8];
     const float lo = d->mad_lo, hi = d->mad_hi;
     const long long base = (long long)blockIdx.x * MU_CHUNK + threadIdx.x * 8;
     unsigned n_mad = 0, n_fin = 0;
     float v[8];
     unsigned mb[8];
     dcr_load8(dh, m, base, n, v, mb);
+    float sl[8];
+    const bool full = base + 8 <= n;
+    if (NUTH) {
+        if (full && DCR_AL16(slope)) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(slope + base));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(slope + base) + 1);
+            sl[0] = a.x; sl[1] = a.y; sl[2] = a.z; sl[3] = a.w; sl[4] = b.x; sl[5] = b.y; sl[6] = b.z; sl[7] = b.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sl[k] = (base + k < n) ? slope[base + k] : 0.f;
+        }
+    }
     unsigned changed = 0;
+    unsigned long long cnt = 0;
+    double s = 0.0, ss = 0.0;
+    float yv[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
+        yv[k] = 0.f;
         if (mb[k] > 0xffu) continue;  // past the end
         unsigned bits = mb[k];
         if (!(bits & (DCR_M_BASE | DCR_M_MAXDZ))) {
-            if (v[k] < lo || v[k] > hi) { bits |= DCR_M_MAD; changed |= 1u << k; }
+            if (v[k] < lo || v[k] > hi) {
+                bits |= DCR_M_MAD; changed |= 1u << k;
+                // the pixel leaves the common mask: its bin code was valid iff no other mask bit is set
+                if (NUTH && mb[k] == 0u) bin[base + k] = (unsigned short)BIN_INVALID;
+            }
             else ++n_mad;
         }
         mb[k] = bits;
         if (!(bits & DCR_M_DIFF)) ++n_fin;
+        if (NUTH && bits == 0u) {   // common mask of compute_offset_nuth: dh, slope and aspect all unmasked
+            const float t = nuth_y(v[k], sl[k]);
+            yv[k] = t;
+            ++cnt;
+            s += (double)t;
+            ss += (double)t * (double)t;
+        }
+    }
+    if (NUTH) {
+        if (full && DCR_AL16(y)) {
+            reinterpret_cast<float4*>(y + base)[0] = make_float4(yv[0], yv[1], yv[2], yv[3]);
+            reinterpret_cast<float4*>(y + base)[1] = make_float4(yv[4], yv[5], yv[6], yv[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (base + k < n) y[base + k] = yv[k];
+        }
     }
     if (changed) {
-        if (base + 8 <= n && DCR_AL8(m)) {
+        if (full && DCR_AL8(m)) {
             uint2 q;
             q.x = mb[0] | (mb[1] << 8) | (mb[2] << 16) | (mb[3] << 24);
             q.y = mb[4] | (mb[5] << 8) | (mb[6] << 16) | (mb[7] << 24);
@@ -888,7 +981,15 @@ __global__ void __launch_bounds__(256) mask_update_kernel(const float* __restric
     }
     n_mad = __reduce_add_sync(0xffffffffu, n_mad);
     n_fin = __reduce_add_sync(0xffffffffu, n_fin);
-    if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = n_mad; s_b[threadIdx.x >> 5] = n_fin; }
+    if (NUTH) {
+        cnt = dcr_warp_sum_u64(cnt);
+        s = dcr_warp_sum(s);
+        ss = dcr_warp_sum(ss);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_a[threadIdx.x >> 5] = n_mad; s_b[threadIdx.x >> 5] = n_fin;
+        if (NUTH) { NuthPartial q; q.n = cnt; q.s = s; q.ss = ss; sp[threadIdx.x >> 5] = q; }
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned a = 0, b = 0;
@@ -896,6 +997,11 @@ __global__ void __launch_bounds__(256) mask_update_kernel(const float* __restric
         chunk_cnt[blockIdx.x] = b;
         if (a) atomicAdd(&d->count_mad, (unsigned long long)a);
         if (b) atomicAdd(&d->count_final, (unsigned long long)b);
+        if (NUTH) {
+            NuthPartial q = sp[0];
+            for (int k = 1; k < 8; ++k) { q.n += sp[k].n; q.s += sp[k].s; q.ss += sp[k].ss; }
+            part[blockIdx.x] = q;
+        }
     }
 }
 
@@ -914,7 +1020,7 @@ static size_t iter_ws_bytes(long long n, int grid) {
     const long long nch = (n + MU_CHUNK - 1) / MU_CHUNK;
     return nuth_ws_bytes(n, grid) + dcr_al256(sizeof(IterDev)) + dcr_al256(DCR_SEL_HIST_WORDS * sizeof(unsigned)) +
            dcr_al256(nch * sizeof(unsigned)) + dcr_al256(nch * sizeof(long long)) +
-           dcr_al256((size_t)(n < 6000016 ? n : 6000016) * sizeof(float)) + 2 * dcr_bsel_scratch_bytes(n) + 4096;
+           dcr_al256((size_t)(n < 6000016 ? n : 6000016) * sizeof(float)) + 3 * dcr_bsel_scratch_bytes(n) + 4096;
 }
 extern "C" size_t dcr_iteration_workspace_bytes(int64_t n) { return iter_ws_bytes(n, dcr_num_sms() * 8); }
 
@@ -973,6 +1079,7 @@ struct IterWs {
     long long dense_cap;
     void* bsel_scratch;
     void* bsel_scratch2;   // selections running on the side stream
+    void* bsel_scratch3;   // med_dh on its own side stream
     NuthWs nw;
 };
 
@@ -997,20 +1104,22 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
     DCR_CUDA_OK(cudaMemsetAsync(d, 0, sizeof(IterDev), s));
     dcr_front_args fa = *front;
     if (!remove_outliers) fa.use_max_dz = 0;
-    if ((rc = dcr_front_launch(&fa, d->counters, s))) return rc;
+    if ((rc = dcr_front_launch(&fa, d->counters, s, w.nw.bin))) return rc;   // + aspect-bin codes
 
     // Side stream (one-pass-select path): work that does not sit on the dependency chain of the MAD filter runs
     // concurrently -- the slope median right after the front kernel, and the strided-subsample chain (scan, stride,
     // compress, dz median) right after the mask update -- so that their latency-bound small kernels hide behind the
     // bandwidth-bound passes of the main stream.  Joined before the result copy.
-    static thread_local cudaStream_t s2 = nullptr;
-    static thread_local cudaEvent_t e_front = nullptr, e_mask = nullptr, e_join = nullptr;
+    static thread_local cudaStream_t s2 = nullptr, s3 = nullptr;
+    static thread_local cudaEvent_t e_front = nullptr, e_mask = nullptr, e_join = nullptr, e_join3 = nullptr;
     const bool side = use_bsel != 0;
     if (side && !s2) {
         DCR_CUDA_OK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
         DCR_CUDA_OK(cudaEventCreateWithFlags(&e_front, cudaEventDisableTiming));
         DCR_CUDA_OK(cudaEventCreateWithFlags(&e_mask, cudaEventDisableTiming));
         DCR_CUDA_OK(cudaEventCreateWithFlags(&e_join, cudaEventDisableTiming));
+        DCR_CUDA_OK(cudaStreamCreateWithFlags(&s3, cudaStreamNonBlocking));
+        DCR_CUDA_OK(cudaEventCreateWithFlags(&e_join3, cudaEventDisableTiming));
     }
     cudaStream_t sb = side ? s2 : s;      // stream of the side work
     IterWs wb = w;                        // side selections use their own scratch
@@ -1035,10 +1144,12 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
     }
     STAGE_MARK(2);
     mad_thresholds_kernel<<<1, 32, 0, s>>>(d, remove_outliers);
-    mask_update_kernel<<<(unsigned)nch, 256, 0, s>>>(front->dh, front->maskbits, n, d, w.chunk_cnt);
+    mask_update_kernel<true><<<(unsigned)nch, 256, 0, s>>>(front->dh, front->maskbits, n, d, w.chunk_cnt, front->slope,
+                                                           w.nw.y, w.nw.bin, w.nw.part);
     if (side) {
         DCR_CUDA_OK(cudaEventRecord(e_mask, s));
         DCR_CUDA_OK(cudaStreamWaitEvent(s2, e_mask, 0));
+        DCR_CUDA_OK(cudaStreamWaitEvent(s3, e_mask, 0));
     }
     // strided subsample of the final mask + dz on it (malib.get_stats <- dem_align.py:114-115)
     if ((rc = dcr_chunk_scan_enqueue(w.chunk_cnt, nch, w.chunk_off, &d->total_final, sb))) return rc;
@@ -1054,10 +1165,17 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
     }
     STAGE_MARK(3);
     // med_dh over the final mask (coreglib.py:214): also off the critical path (the bin statistics below only need
-    // the mask), so it follows the subsample chain on the side stream
+    // the mask); its own side stream, concurrent with the subsample chain
     v.reject = DCR_M_DIFF; v.transform = 0; v.center_ptr = nullptr;
-    if ((rc = iter_select(v, 2, wb, n, use_bsel, sb))) return rc;
-    if (side) DCR_CUDA_OK(cudaEventRecord(e_join, s2));
+    {
+        IterWs w3 = w;
+        if (side) w3.bsel_scratch = w.bsel_scratch3;
+        if ((rc = iter_select(v, 2, w3, n, use_bsel, side ? s3 : s))) return rc;
+    }
+    if (side) {
+        DCR_CUDA_OK(cudaEventRecord(e_join, s2));
+        DCR_CUDA_OK(cudaEventRecord(e_join3, s3));
+    }
     if (!side) {
         SelView vs;
         memset(&vs, 0, sizeof(vs));
@@ -1065,10 +1183,11 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
         if ((rc = iter_select(vs, 4, w, n, use_bsel, s))) return rc;
     }
     STAGE_MARK(4);
-    if ((rc = nuth_enqueue(front->dh, front->slope, front->aspect, front->maskbits, DCR_M_DIFF | DCR_M_ASPECT, n,
-                           remove_outliers, w.nw, grid, s, ev ? ev[5] : nullptr, fast_bins)))
-        return rc;
-    if (side) DCR_CUDA_OK(cudaStreamWaitEvent(s, e_join, 0));
+    if ((rc = nuth_enqueue_prepared(n, nch, remove_outliers, w.nw, grid, s, ev ? ev[5] : nullptr, fast_bins))) return rc;
+    if (side) {
+        DCR_CUDA_OK(cudaStreamWaitEvent(s, e_join, 0));
+        DCR_CUDA_OK(cudaStreamWaitEvent(s, e_join3, 0));
+    }
     DCR_LAUNCH_OK("iteration kernels");
     STAGE_MARK(6);
     (void)apply_z;
@@ -1153,6 +1272,7 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_it
     w.dense = ws.take<float>(w.dense_cap);
     w.bsel_scratch = ws.take<char>(dcr_bsel_scratch_bytes(n));
     w.bsel_scratch2 = ws.take<char>(dcr_bsel_scratch_bytes(n));
+    w.bsel_scratch3 = ws.take<char>(dcr_bsel_scratch_bytes(n));
     if (nuth_ws_carve(ws, n, grid, &w.nw)) return -1;
     w.nw.nd = &w.d->nuth;
     IterDev* d = w.d;
@@ -1388,6 +1508,7 @@ static int band_carve(void* workspace, size_t workspace_bytes, long long n, int 
     w->dense = ws.take<float>(w->dense_cap);
     w->bsel_scratch = ws.take<char>(dcr_bsel_scratch_bytes(n));
     w->bsel_scratch2 = ws.take<char>(dcr_bsel_scratch_bytes(n));
+    w->bsel_scratch3 = ws.take<char>(dcr_bsel_scratch_bytes(n));
     if (nuth_ws_carve(ws, n, grid, &w->nw)) return -1;
     w->nw.nd = &w->d->nuth;
     return 0;
@@ -1461,7 +1582,8 @@ extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, 
         rc = sel_phase(1, phase - BP_SEL1);
     } else if (phase == BP_MASK) {
         mad_thresholds_kernel<<<1, 32, 0, s>>>(d, remove_outliers);
-        mask_update_kernel<<<(unsigned)nch, 256, 0, s>>>(front->dh, front->maskbits, n, d, w.chunk_cnt);
+        mask_update_kernel<false><<<(unsigned)nch, 256, 0, s>>>(front->dh, front->maskbits, n, d, w.chunk_cnt, nullptr, nullptr,
+                                                                nullptr, nullptr);
         band_rank_count_kernel<<<1, 32, 0, s>>>(d, rank);
         want(&d->count_mad, 2 + 8, 1);  // count_mad, count_final, rank_counts[8] are contiguous
     } else if (phase == BP_COMPRESS) {

@@ -376,7 +376,11 @@ __global__ void __launch_bounds__(1024) chunk_scan_kernel(const unsigned* __rest
     if (threadIdx.x == 0) *total_out = s_carry;
 }
 
-// stride from device (stride_ptr) or immediate; writes element with compressed rank r to dense[r/stride] when r % stride == 0
+// stride from device (stride_ptr) or immediate; writes element with compressed rank r to dense[r/stride] when r % stride == 0.
+// SPARSE (iteration driver: validity is decided by the mask byte alone, and the chunk counts came from the same
+// bytes): only the mask is streamed (1 byte/element); the value of a picked element is gathered on demand -- with the
+// strides malib.get_stats produces (>= 2) that touches a fraction of the value sectors instead of all of them.
+template <bool SPARSE>
 __global__ void __launch_bounds__(256) compress_strided_kernel(const float* __restrict__ x, const unsigned char* __restrict__ m,
                                                                unsigned reject, long long n,
                                                                const long long* __restrict__ off, long long stride_imm,
@@ -389,10 +393,24 @@ __global__ void __launch_bounds__(256) compress_strided_kernel(const float* __re
     float vals[8];
     unsigned mb[8];
     unsigned flags = 0, c = 0;
-    dcr_load8(x, m, base, n, vals, mb);
+    if (SPARSE) {
+        if (base + 8 <= n && DCR_AL8(m)) {
+            const uint2 q = __ldg(reinterpret_cast<const uint2*>(m + base));
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-        if (!(mb[k] & (reject | 0xffffff00u)) && !isnan(vals[k])) { flags |= 1u << k; ++c; }
+            for (int k = 0; k < 4; ++k) { mb[k] = (q.x >> (8 * k)) & 0xffu; mb[4 + k] = (q.y >> (8 * k)) & 0xffu; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mb[k] = (base + k < n) ? (unsigned)m[base + k] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (!(mb[k] & (reject | 0xffffff00u))) { flags |= 1u << k; ++c; }
+    } else {
+        dcr_load8(x, m, base, n, vals, mb);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (!(mb[k] & (reject | 0xffffff00u)) && !isnan(vals[k])) { flags |= 1u << k; ++c; }
+    }
     unsigned total;
     unsigned ex = dcr_block_excl_scan(c, s_scratch, &total);
     // row-band mode: this band's elements follow `base` unmasked elements of the bands above it
@@ -407,7 +425,7 @@ __global__ void __launch_bounds__(256) compress_strided_kernel(const float* __re
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         if (flags & (1u << k)) {
-            if (rem == 0 && quo < cap) dense[quo] = vals[k];
+            if (rem == 0 && quo < cap) dense[quo] = SPARSE ? __ldg(x + base + k) : vals[k];
             if (++rem == stride) { rem = 0; ++quo; }
         }
     }
@@ -415,10 +433,14 @@ __global__ void __launch_bounds__(256) compress_strided_kernel(const float* __re
 
 int dcr_compress_enqueue(const float* x, const unsigned char* m, unsigned reject, long long n, const long long* chunk_off,
                          long long stride_imm, const long long* stride_ptr, float* dense, long long cap,
-                         cudaStream_t s, const long long* base_ptr) {
+                         cudaStream_t s, const long long* base_ptr, bool mask_only_validity) {
     const long long nchunks = (n + CHUNK - 1) / CHUNK;
-    compress_strided_kernel<<<(unsigned)nchunks, 256, 0, s>>>(x, m, reject, n, chunk_off, stride_imm, stride_ptr, dense, cap,
-                                                              base_ptr);
+    if (mask_only_validity && m)
+        compress_strided_kernel<true><<<(unsigned)nchunks, 256, 0, s>>>(x, m, reject, n, chunk_off, stride_imm, stride_ptr,
+                                                                        dense, cap, base_ptr);
+    else
+        compress_strided_kernel<false><<<(unsigned)nchunks, 256, 0, s>>>(x, m, reject, n, chunk_off, stride_imm, stride_ptr,
+                                                                         dense, cap, base_ptr);
     DCR_LAUNCH_OK("compress_strided_kernel");
     return 0;
 }
