@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(1024) bsel_sample_kernel(const SelView v, doub
 
 // One streaming pass: the collector (dcr_bsel_collect.cuh) does the counting / candidate gathering / level-0 find.
 typedef BselCollector<16, 4096> MainCollector;
+template <int TRANSFORM>
 __global__ void __launch_bounds__(BS_THREADS) bsel_main_kernel(const SelView v, BselState* st, unsigned* ghist,
                                                                unsigned* __restrict__ cand, unsigned cap, double q_percent) {
     extern __shared__ __align__(16) unsigned char bsel_smem[];
@@ -212,10 +213,9 @@ __global__ void __launch_bounds__(BS_THREADS) bsel_main_kernel(const SelView v, 
     const long long n = v.n_ptr ? *v.n_ptr : v.n;
     const float center = v.center_ptr ? *v.center_ptr : v.center_imm;
     const unsigned reject = v.m ? v.reject : 0u;
-    const int transform = v.transform;
     dcr_stream1_groups(v.x, v.m, n,
         [&](float x, unsigned mb, long long, int) {
-            if (transform == 1) x = fabsf(x - center);
+            if (TRANSFORM == 1) x = fabsf(x - center);
             col.add(x, !(mb & reject));
         },
         [&]() { col.drain(); });
@@ -343,7 +343,9 @@ int dcr_bsel_enqueue(const SelView& v, double q_percent, BselState* st, void* sc
     if (rc) return rc;
     static int grid0 = 0;   // SMs x 8, like the other streaming kernels
     if (!grid0) {
-        DCR_CUDA_OK(cudaFuncSetAttribute(bsel_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        DCR_CUDA_OK(cudaFuncSetAttribute(bsel_main_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(MainCollector::Shared)));
+        DCR_CUDA_OK(cudaFuncSetAttribute(bsel_main_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(MainCollector::Shared)));
         grid0 = dcr_num_sms() * 8;
     }
@@ -351,7 +353,10 @@ int dcr_bsel_enqueue(const SelView& v, double q_percent, BselState* st, void* sc
     long long grid = (n_max + 57343) / 57344;
     if (grid < grid0) grid = grid0;
     if (grid > (1 << 20)) grid = 1 << 20;
-    bsel_main_kernel<<<(unsigned)grid, BS_THREADS, sizeof(MainCollector::Shared), s>>>(v, st, hist, cand, cap, q_percent);  // + level-0 find
+    if (v.transform == 1)
+        bsel_main_kernel<1><<<(unsigned)grid, BS_THREADS, sizeof(MainCollector::Shared), s>>>(v, st, hist, cand, cap, q_percent);
+    else
+        bsel_main_kernel<0><<<(unsigned)grid, BS_THREADS, sizeof(MainCollector::Shared), s>>>(v, st, hist, cand, cap, q_percent);
     DCR_LAUNCH_OK("bsel_main_kernel");
     return dcr_bsel_refine_enqueue(st, scratch, n_max, s);
 }

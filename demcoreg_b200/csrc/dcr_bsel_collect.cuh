@@ -117,9 +117,11 @@ struct BselCollector {
 
     // x: the (already transformed) value; ok: element takes part in the selection.  NaN fails every comparison.
     __device__ __forceinline__ void add(float x, bool ok) {
-        const bool lo = ok && (x < flo), hi = ok && (x > fhi), in = ok && (x >= flo) && (x <= fhi);
+        // three chained compares: below the bracket | at or above its lower edge | of those, inside.  total = below +
+        // nge, so a NaN (false in every comparison) takes part in neither; `total` holds nge until finish()
+        const bool lo = ok && (x < flo), ge = ok && (x >= flo), in = ge && (x <= fhi);
         below += lo;
-        total += lo | hi;
+        total += ge;
         if (in) { mine[c * BSC_THREADS] = x; ++c; }
     }
 
@@ -131,7 +133,6 @@ struct BselCollector {
         const unsigned cmax = __reduce_max_sync(0xffffffffu, c);
         if (cmax == 0) return;
         const int lane = threadIdx.x & 31;
-        total += c;
         const unsigned inc = dcr_warp_incl_scan(c);
         const unsigned wt = __shfl_sync(0xffffffffu, inc, 31);
         unsigned base = 0, gb = 0;
@@ -162,7 +163,7 @@ struct BselCollector {
         const int lane = threadIdx.x & 31;
         drain();
         below = __reduce_add_sync(0xffffffffu, below);
-        total = __reduce_add_sync(0xffffffffu, total);
+        total = __reduce_add_sync(0xffffffffu, total) + below;
         if (lane == 0) {
             if (below) atomicAdd(&sh->below, (unsigned long long)below);
             if (total) atomicAdd(&sh->total, (unsigned long long)total);

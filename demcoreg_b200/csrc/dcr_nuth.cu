@@ -398,12 +398,12 @@ __global__ void fb_findA_kernel(NuthDev* nd, const unsigned* __restrict__ ghist)
 __global__ void __launch_bounds__(256) fb_passB_kernel(const float* __restrict__ y, const unsigned short* __restrict__ bin,
                                                        long long n, NuthDev* nd, unsigned* __restrict__ ghist,
                                                        unsigned long long* __restrict__ cand, unsigned cap) {
-    __shared__ unsigned short s_c0[NB], s_c1[NB];
+    __shared__ unsigned s_c01[NB];   // coarse cells of the two median elements of each bin, packed (one shared load per sample)
     __shared__ unsigned long long s_buf[FB_STAGE];
     __shared__ unsigned long long s_priv[FB_PRIV * 256];   // thread-private slots: slot k of thread t at [k * 256 + t]
     __shared__ unsigned s_n, s_gbase;
     if (nd->fast_fallback) return;
-    for (int k = threadIdx.x; k < NB; k += 256) { s_c0[k] = nd->fa_cell[0][k]; s_c1[k] = nd->fa_cell[1][k]; }
+    for (int k = threadIdx.x; k < NB; k += 256) s_c01[k] = (unsigned)nd->fa_cell[0][k] | ((unsigned)nd->fa_cell[1][k] << 16);
     if (threadIdx.x == 0) s_n = 0u;
     __syncthreads();
     const float rmin = nd->rmin, rmax = nd->rmax, scale = nd->fast_scale;
@@ -415,7 +415,8 @@ __global__ void __launch_bounds__(256) fb_passB_kernel(const float* __restrict__
         if (!(yv >= rmin && yv <= rmax)) return;
         const unsigned f = fb_fine(yv, rmin, scale);
         const unsigned cc = f >> 10;
-        const unsigned c0 = s_c0[b], c1 = s_c1[b];
+        const unsigned c01 = s_c01[b];
+        const unsigned c0 = c01 & 0xffffu, c1 = c01 >> 16;
         if (cc != c0 && cc != c1) return;
         const unsigned plane = (cc == c0) ? 0u : 1u;
         const unsigned long long rec = ((unsigned long long)dcr_f2key(yv) << 32) | ((unsigned long long)b << 16) | f;
@@ -905,98 +906,107 @@ __global__ void mad_thresholds_kernel(IterDev* d, int remove_outliers) {
 // (coreglib.py:229-233), count / sum / sum of squares of y (coreglib.py:238; one partial per chunk, reduced in a fixed
 // order), and the bin code -- emitted by the front kernel from the aspect -- invalidated where the MAD filter removes
 // a pixel.  The arithmetic of a bandwidth-bound pass is free; the front kernel is issue-bound and could not host it.
+#define MU_KCH 4   // consecutive chunks per CTA: one partial-moment reduction and one pair of global atomics per CTA
 template <bool NUTH>
 __global__ void __launch_bounds__(256) mask_update_kernel(const float* __restrict__ dh, unsigned char* m,
                                                           long long n, IterDev* d, unsigned* __restrict__ chunk_cnt,
                                                           const float* __restrict__ slope, float* __restrict__ y,
                                                           unsigned short* __restrict__ bin, NuthPartial* __restrict__ part) {
-    __shared__ unsigned s_a[8], s_b[8];
+    __shared__ unsigned s_a[2][8], s_b[2][8];
     __shared__ NuthPartial sp[8];
     const float lo = d->mad_lo, hi = d->mad_hi;
-    const long long base = (long long)blockIdx.x * MU_CHUNK + threadIdx.x * 8;
-    unsigned n_mad = 0, n_fin = 0;
-    float v[8];
-    unsigned mb[8];
-    dcr_load8(dh, m, base, n, v, mb);
-    float sl[8];
-    const bool full = base + 8 <= n;
-    if (NUTH) {
-        if (full && DCR_AL16(slope)) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(slope + base));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(slope + base) + 1);
-            sl[0] = a.x; sl[1] = a.y; sl[2] = a.z; sl[3] = a.w; sl[4] = b.x; sl[5] = b.y; sl[6] = b.z; sl[7] = b.w;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) sl[k] = (base + k < n) ? slope[base + k] : 0.f;
-        }
-    }
-    unsigned changed = 0;
+    const long long nch = (n + MU_CHUNK - 1) / MU_CHUNK;
     unsigned long long cnt = 0;
     double s = 0.0, ss = 0.0;
-    float yv[8];
+    unsigned a_tot = 0, b_tot = 0;   // thread 0 only
+    for (int kc = 0; kc < MU_KCH; ++kc) {
+        const long long chunk = (long long)blockIdx.x * MU_KCH + kc;
+        if (chunk >= nch) break;     // CTA-uniform
+        const long long base = chunk * MU_CHUNK + threadIdx.x * 8;
+        unsigned n_mad = 0, n_fin = 0;
+        float v[8];
+        unsigned mb[8];
+        dcr_load8(dh, m, base, n, v, mb);
+        float sl[8];
+        const bool full = base + 8 <= n;
+        if (NUTH) {
+            if (full && DCR_AL16(slope)) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(slope + base));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(slope + base) + 1);
+                sl[0] = a.x; sl[1] = a.y; sl[2] = a.z; sl[3] = a.w; sl[4] = b.x; sl[5] = b.y; sl[6] = b.z; sl[7] = b.w;
+            } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        yv[k] = 0.f;
-        if (mb[k] > 0xffu) continue;  // past the end
-        unsigned bits = mb[k];
-        if (!(bits & (DCR_M_BASE | DCR_M_MAXDZ))) {
-            if (v[k] < lo || v[k] > hi) {
-                bits |= DCR_M_MAD; changed |= 1u << k;
-                // the pixel leaves the common mask: its bin code was valid iff no other mask bit is set
-                if (NUTH && mb[k] == 0u) bin[base + k] = (unsigned short)BIN_INVALID;
+                for (int k = 0; k < 8; ++k) sl[k] = (base + k < n) ? slope[base + k] : 0.f;
             }
-            else ++n_mad;
         }
-        mb[k] = bits;
-        if (!(bits & DCR_M_DIFF)) ++n_fin;
-        if (NUTH && bits == 0u) {   // common mask of compute_offset_nuth: dh, slope and aspect all unmasked
-            const float t = nuth_y(v[k], sl[k]);
-            yv[k] = t;
-            ++cnt;
-            s += (double)t;
-            ss += (double)t * (double)t;
-        }
-    }
-    if (NUTH) {
-        if (full && DCR_AL16(y)) {
-            reinterpret_cast<float4*>(y + base)[0] = make_float4(yv[0], yv[1], yv[2], yv[3]);
-            reinterpret_cast<float4*>(y + base)[1] = make_float4(yv[4], yv[5], yv[6], yv[7]);
-        } else {
+        unsigned changed = 0;
+        float yv[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (base + k < n) y[base + k] = yv[k];
+        for (int k = 0; k < 8; ++k) {
+            yv[k] = 0.f;
+            if (mb[k] > 0xffu) continue;  // past the end
+            unsigned bits = mb[k];
+            if (!(bits & (DCR_M_BASE | DCR_M_MAXDZ))) {
+                if (v[k] < lo || v[k] > hi) {
+                    bits |= DCR_M_MAD; changed |= 1u << k;
+                    // the pixel leaves the common mask: its bin code was valid iff no other mask bit is set
+                    if (NUTH && mb[k] == 0u) bin[base + k] = (unsigned short)BIN_INVALID;
+                }
+                else ++n_mad;
+            }
+            mb[k] = bits;
+            if (!(bits & DCR_M_DIFF)) ++n_fin;
+            if (NUTH && bits == 0u) {   // common mask of compute_offset_nuth: dh, slope and aspect all unmasked
+                const float t = nuth_y(v[k], sl[k]);
+                yv[k] = t;
+                ++cnt;
+                s += (double)t;
+                ss += (double)t * (double)t;
+            }
         }
-    }
-    if (changed) {
-        if (full && DCR_AL8(m)) {
-            uint2 q;
-            q.x = mb[0] | (mb[1] << 8) | (mb[2] << 16) | (mb[3] << 24);
-            q.y = mb[4] | (mb[5] << 8) | (mb[6] << 16) | (mb[7] << 24);
-            *reinterpret_cast<uint2*>(m + base) = q;
-        } else {
+        if (NUTH) {
+            if (full && DCR_AL16(y)) {
+                reinterpret_cast<float4*>(y + base)[0] = make_float4(yv[0], yv[1], yv[2], yv[3]);
+                reinterpret_cast<float4*>(y + base)[1] = make_float4(yv[4], yv[5], yv[6], yv[7]);
+            } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (changed & (1u << k)) m[base + k] = (unsigned char)mb[k];
+                for (int k = 0; k < 8; ++k)
+                    if (base + k < n) y[base + k] = yv[k];
+            }
+        }
+        if (changed) {
+            if (full && DCR_AL8(m)) {
+                uint2 q;
+                q.x = mb[0] | (mb[1] << 8) | (mb[2] << 16) | (mb[3] << 24);
+                q.y = mb[4] | (mb[5] << 8) | (mb[6] << 16) | (mb[7] << 24);
+                *reinterpret_cast<uint2*>(m + base) = q;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (changed & (1u << k)) m[base + k] = (unsigned char)mb[k];
+            }
+        }
+        n_mad = __reduce_add_sync(0xffffffffu, n_mad);
+        n_fin = __reduce_add_sync(0xffffffffu, n_fin);
+        if ((threadIdx.x & 31) == 0) { s_a[kc & 1][threadIdx.x >> 5] = n_mad; s_b[kc & 1][threadIdx.x >> 5] = n_fin; }
+        __syncthreads();   // (double-buffered counts: one barrier per chunk)
+        if (threadIdx.x == 0) {
+            unsigned a = 0, b = 0;
+            for (int k = 0; k < 8; ++k) { a += s_a[kc & 1][k]; b += s_b[kc & 1][k]; }
+            chunk_cnt[chunk] = b;
+            a_tot += a; b_tot += b;
         }
     }
-    n_mad = __reduce_add_sync(0xffffffffu, n_mad);
-    n_fin = __reduce_add_sync(0xffffffffu, n_fin);
     if (NUTH) {
         cnt = dcr_warp_sum_u64(cnt);
         s = dcr_warp_sum(s);
         ss = dcr_warp_sum(ss);
+        if ((threadIdx.x & 31) == 0) { NuthPartial q; q.n = cnt; q.s = s; q.ss = ss; sp[threadIdx.x >> 5] = q; }
+        __syncthreads();
     }
-    if ((threadIdx.x & 31) == 0) {
-        s_a[threadIdx.x >> 5] = n_mad; s_b[threadIdx.x >> 5] = n_fin;
-        if (NUTH) { NuthPartial q; q.n = cnt; q.s = s; q.ss = ss; sp[threadIdx.x >> 5] = q; }
-    }
-    __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned a = 0, b = 0;
-        for (int k = 0; k < 8; ++k) { a += s_a[k]; b += s_b[k]; }
-        chunk_cnt[blockIdx.x] = b;
-        if (a) atomicAdd(&d->count_mad, (unsigned long long)a);
-        if (b) atomicAdd(&d->count_final, (unsigned long long)b);
+        if (a_tot) atomicAdd(&d->count_mad, (unsigned long long)a_tot);
+        if (b_tot) atomicAdd(&d->count_final, (unsigned long long)b_tot);
         if (NUTH) {
             NuthPartial q = sp[0];
             for (int k = 1; k < 8; ++k) { q.n += sp[k].n; q.s += sp[k].s; q.ss += sp[k].ss; }
@@ -1144,7 +1154,7 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
     }
     STAGE_MARK(2);
     mad_thresholds_kernel<<<1, 32, 0, s>>>(d, remove_outliers);
-    mask_update_kernel<true><<<(unsigned)nch, 256, 0, s>>>(front->dh, front->maskbits, n, d, w.chunk_cnt, front->slope,
+    mask_update_kernel<true><<<(unsigned)((nch + MU_KCH - 1) / MU_KCH), 256, 0, s>>>(front->dh, front->maskbits, n, d, w.chunk_cnt, front->slope,
                                                            w.nw.y, w.nw.bin, w.nw.part);
     if (side) {
         DCR_CUDA_OK(cudaEventRecord(e_mask, s));
@@ -1183,7 +1193,9 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
         if ((rc = iter_select(vs, 4, w, n, use_bsel, s))) return rc;
     }
     STAGE_MARK(4);
-    if ((rc = nuth_enqueue_prepared(n, nch, remove_outliers, w.nw, grid, s, ev ? ev[5] : nullptr, fast_bins))) return rc;
+    if ((rc = nuth_enqueue_prepared(n, (nch + MU_KCH - 1) / MU_KCH, remove_outliers, w.nw, grid, s, ev ? ev[5] : nullptr,
+                                    fast_bins)))
+        return rc;
     if (side) {
         DCR_CUDA_OK(cudaStreamWaitEvent(s, e_join, 0));
         DCR_CUDA_OK(cudaStreamWaitEvent(s, e_join3, 0));
@@ -1582,7 +1594,7 @@ extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, 
         rc = sel_phase(1, phase - BP_SEL1);
     } else if (phase == BP_MASK) {
         mad_thresholds_kernel<<<1, 32, 0, s>>>(d, remove_outliers);
-        mask_update_kernel<false><<<(unsigned)nch, 256, 0, s>>>(front->dh, front->maskbits, n, d, w.chunk_cnt, nullptr, nullptr,
+        mask_update_kernel<false><<<(unsigned)((nch + MU_KCH - 1) / MU_KCH), 256, 0, s>>>(front->dh, front->maskbits, n, d, w.chunk_cnt, nullptr, nullptr,
                                                                 nullptr, nullptr);
         band_rank_count_kernel<<<1, 32, 0, s>>>(d, rank);
         want(&d->count_mad, 2 + 8, 1);  // count_mad, count_final, rank_counts[8] are contiguous
