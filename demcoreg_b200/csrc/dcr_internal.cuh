@@ -74,7 +74,7 @@ int dcr_chunk_count_scan_enqueue(const float* x, const unsigned char* m, unsigne
                                  long long* chunk_off, long long* total, cudaStream_t s);
 int dcr_compress_enqueue(const float* x, const unsigned char* m, unsigned reject, long long n, const long long* chunk_off,
                          long long stride_imm, const long long* stride_ptr, float* dense, long long cap,
-                         cudaStream_t s, const long long* base_ptr = nullptr, bool mask_only_validity = false);
+                         cudaStream_t s, const long long* base_ptr = nullptr, int groups = 1);
 int dcr_chunk_scan_enqueue(const unsigned* cnt, long long nchunks, long long* off, long long* total, cudaStream_t s);
 int dcr_sel_hist_pass(const SelView& v, SelState* st, unsigned* hist, int pass, cudaStream_t s);
 int dcr_sel_find_pass(SelState* st, unsigned* hist, double q_percent, int pass, cudaStream_t s);

@@ -912,18 +912,17 @@ __global__ void __launch_bounds__(256) mask_update_kernel(const float* __restric
                                                           long long n, IterDev* d, unsigned* __restrict__ chunk_cnt,
                                                           const float* __restrict__ slope, float* __restrict__ y,
                                                           unsigned short* __restrict__ bin, NuthPartial* __restrict__ part) {
-    __shared__ unsigned s_a[2][8], s_b[2][8];
+    __shared__ unsigned s_a[8], s_b[8];
     __shared__ NuthPartial sp[8];
     const float lo = d->mad_lo, hi = d->mad_hi;
     const long long nch = (n + MU_CHUNK - 1) / MU_CHUNK;
     unsigned long long cnt = 0;
     double s = 0.0, ss = 0.0;
-    unsigned a_tot = 0, b_tot = 0;   // thread 0 only
+    unsigned n_mad = 0, n_fin = 0;
     for (int kc = 0; kc < MU_KCH; ++kc) {
         const long long chunk = (long long)blockIdx.x * MU_KCH + kc;
         if (chunk >= nch) break;     // CTA-uniform
         const long long base = chunk * MU_CHUNK + threadIdx.x * 8;
-        unsigned n_mad = 0, n_fin = 0;
         float v[8];
         unsigned mb[8];
         dcr_load8(dh, m, base, n, v, mb);
@@ -986,27 +985,26 @@ __global__ void __launch_bounds__(256) mask_update_kernel(const float* __restric
                     if (changed & (1u << k)) m[base + k] = (unsigned char)mb[k];
             }
         }
-        n_mad = __reduce_add_sync(0xffffffffu, n_mad);
-        n_fin = __reduce_add_sync(0xffffffffu, n_fin);
-        if ((threadIdx.x & 31) == 0) { s_a[kc & 1][threadIdx.x >> 5] = n_mad; s_b[kc & 1][threadIdx.x >> 5] = n_fin; }
-        __syncthreads();   // (double-buffered counts: one barrier per chunk)
-        if (threadIdx.x == 0) {
-            unsigned a = 0, b = 0;
-            for (int k = 0; k < 8; ++k) { a += s_a[kc & 1][k]; b += s_b[kc & 1][k]; }
-            chunk_cnt[chunk] = b;
-            a_tot += a; b_tot += b;
-        }
     }
+    // one block reduction per CTA: MU_KCH chunks = one 8192-element group of the compress / scan kernels
+    n_mad = __reduce_add_sync(0xffffffffu, n_mad);
+    n_fin = __reduce_add_sync(0xffffffffu, n_fin);
     if (NUTH) {
         cnt = dcr_warp_sum_u64(cnt);
         s = dcr_warp_sum(s);
         ss = dcr_warp_sum(ss);
-        if ((threadIdx.x & 31) == 0) { NuthPartial q; q.n = cnt; q.s = s; q.ss = ss; sp[threadIdx.x >> 5] = q; }
-        __syncthreads();
     }
+    if ((threadIdx.x & 31) == 0) {
+        s_a[threadIdx.x >> 5] = n_mad; s_b[threadIdx.x >> 5] = n_fin;
+        if (NUTH) { NuthPartial q; q.n = cnt; q.s = s; q.ss = ss; sp[threadIdx.x >> 5] = q; }
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        if (a_tot) atomicAdd(&d->count_mad, (unsigned long long)a_tot);
-        if (b_tot) atomicAdd(&d->count_final, (unsigned long long)b_tot);
+        unsigned a = 0, b = 0;
+        for (int k = 0; k < 8; ++k) { a += s_a[k]; b += s_b[k]; }
+        chunk_cnt[blockIdx.x] = b;
+        if (a) atomicAdd(&d->count_mad, (unsigned long long)a);
+        if (b) atomicAdd(&d->count_final, (unsigned long long)b);
         if (NUTH) {
             NuthPartial q = sp[0];
             for (int k = 1; k < 8; ++k) { q.n += sp[k].n; q.s += sp[k].s; q.ss += sp[k].ss; }
@@ -1162,10 +1160,11 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
         DCR_CUDA_OK(cudaStreamWaitEvent(s3, e_mask, 0));
     }
     // strided subsample of the final mask + dz on it (malib.get_stats <- dem_align.py:114-115)
-    if ((rc = dcr_chunk_scan_enqueue(w.chunk_cnt, nch, w.chunk_off, &d->total_final, sb))) return rc;
+    const long long nch4 = (nch + MU_KCH - 1) / MU_KCH;   // the mask update counts per CTA = 8192 elements
+    if ((rc = dcr_chunk_scan_enqueue(w.chunk_cnt, nch4, w.chunk_off, &d->total_final, sb))) return rc;
     stride_kernel<<<1, 32, 0, sb>>>(d);
     if ((rc = dcr_compress_enqueue(front->dh, front->maskbits, DCR_M_DIFF, n, w.chunk_off, 1, &d->stride, w.dense,
-                                   w.dense_cap, sb)))
+                                   w.dense_cap, sb, nullptr, MU_KCH)))
         return rc;
     {
         SelView vd;
@@ -1601,11 +1600,12 @@ extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, 
     } else if (phase == BP_COMPRESS) {
         // after the all-reduce count_final is global; the per-band counts give this band's rank offset
         band_base_kernel<<<1, 32, 0, s>>>(d, rank, nranks);
-        if ((rc = dcr_chunk_scan_enqueue(w.chunk_cnt, nch, w.chunk_off, &d->dense_n /* scratch */, s))) return rc;
+        if ((rc = dcr_chunk_scan_enqueue(w.chunk_cnt, (nch + MU_KCH - 1) / MU_KCH, w.chunk_off, &d->dense_n /* scratch */, s)))
+            return rc;
         stride_kernel<<<1, 32, 0, s>>>(d);
         band_dense_n_kernel<<<1, 32, 0, s>>>(d, rank);
         if ((rc = dcr_compress_enqueue(front->dh, front->maskbits, DCR_M_DIFF, n, w.chunk_off, 1, &d->stride, w.dense,
-                                       w.dense_cap, s, &d->band_base)))
+                                       w.dense_cap, s, &d->band_base, MU_KCH)))
             return rc;
     } else if (phase >= BP_SEL2 && phase < BP_SEL3) {
         rc = sel_phase(2, phase - BP_SEL2);

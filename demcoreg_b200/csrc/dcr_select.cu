@@ -377,10 +377,9 @@ __global__ void __launch_bounds__(1024) chunk_scan_kernel(const unsigned* __rest
 }
 
 // stride from device (stride_ptr) or immediate; writes element with compressed rank r to dense[r/stride] when r % stride == 0.
-// SPARSE (iteration driver: validity is decided by the mask byte alone, and the chunk counts came from the same
-// bytes): only the mask is streamed (1 byte/element); the value of a picked element is gathered on demand -- with the
-// strides malib.get_stats produces (>= 2) that touches a fraction of the value sectors instead of all of them.
-template <bool SPARSE>
+// A CTA handles one chunk of 2048 * G elements (off[] holds the exclusive prefix of the per-chunk counts): thread t owns the
+// 8 * G consecutive elements starting at t * 8 * G, so one block scan orders the whole chunk.
+template <int G>
 __global__ void __launch_bounds__(256) compress_strided_kernel(const float* __restrict__ x, const unsigned char* __restrict__ m,
                                                                unsigned reject, long long n,
                                                                const long long* __restrict__ off, long long stride_imm,
@@ -389,58 +388,50 @@ __global__ void __launch_bounds__(256) compress_strided_kernel(const float* __re
     __shared__ unsigned s_scratch[33];
     const long long stride = stride_ptr ? *stride_ptr : stride_imm;
     if (stride_ptr && stride <= 1) return;  // iteration driver: no subsample needed
-    const long long base = (long long)blockIdx.x * CHUNK + threadIdx.x * 8;
-    float vals[8];
-    unsigned mb[8];
+    const long long base = (long long)blockIdx.x * (CHUNK * G) + threadIdx.x * (8 * G);
+    float vals[8 * G];
     unsigned flags = 0, c = 0;
-    if (SPARSE) {
-        if (base + 8 <= n && DCR_AL8(m)) {
-            const uint2 q = __ldg(reinterpret_cast<const uint2*>(m + base));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { mb[k] = (q.x >> (8 * k)) & 0xffu; mb[4 + k] = (q.y >> (8 * k)) & 0xffu; }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) mb[k] = (base + k < n) ? (unsigned)m[base + k] : 0xffffffffu;
-        }
+    for (int g = 0; g < G; ++g) {
+        unsigned mb[8];
+        dcr_load8(x, m, base + 8 * g, n, vals + 8 * g, mb);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            if (!(mb[k] & (reject | 0xffffff00u))) { flags |= 1u << k; ++c; }
-    } else {
-        dcr_load8(x, m, base, n, vals, mb);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (!(mb[k] & (reject | 0xffffff00u)) && !isnan(vals[k])) { flags |= 1u << k; ++c; }
+            if (!(mb[k] & (reject | 0xffffff00u)) && !isnan(vals[8 * g + k])) { flags |= 1u << (8 * g + k); ++c; }
     }
     unsigned total;
     unsigned ex = dcr_block_excl_scan(c, s_scratch, &total);
     // row-band mode: this band's elements follow `base` unmasked elements of the bands above it
     const long long gbase = base_ptr ? *base_ptr : 0;
     const long long dfirst = (gbase + stride - 1) / stride;  // global subsample index of this band's first pick
-    // one 64-bit division per thread; the 8 elements then advance (quotient, remainder) incrementally
+    // one 64-bit division per thread; the elements then advance (quotient, remainder) incrementally
     const long long rank0 = gbase + off[blockIdx.x] + ex;
     if (c == 0) return;
     long long quo = rank0 / stride;
     long long rem = rank0 - quo * stride;
     quo -= dfirst;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < 8 * G; ++k) {
         if (flags & (1u << k)) {
-            if (rem == 0 && quo < cap) dense[quo] = SPARSE ? __ldg(x + base + k) : vals[k];
+            if (rem == 0 && quo < cap) dense[quo] = vals[k];
             if (++rem == stride) { rem = 0; ++quo; }
         }
     }
 }
 
+// groups: 1 -> chunks of 2048 elements (dcr_chunk_count_scan_enqueue), 4 -> chunks of 8192 (the iteration's mask update)
 int dcr_compress_enqueue(const float* x, const unsigned char* m, unsigned reject, long long n, const long long* chunk_off,
                          long long stride_imm, const long long* stride_ptr, float* dense, long long cap,
-                         cudaStream_t s, const long long* base_ptr, bool mask_only_validity) {
-    const long long nchunks = (n + CHUNK - 1) / CHUNK;
-    if (mask_only_validity && m)
-        compress_strided_kernel<true><<<(unsigned)nchunks, 256, 0, s>>>(x, m, reject, n, chunk_off, stride_imm, stride_ptr,
-                                                                        dense, cap, base_ptr);
-    else
-        compress_strided_kernel<false><<<(unsigned)nchunks, 256, 0, s>>>(x, m, reject, n, chunk_off, stride_imm, stride_ptr,
-                                                                         dense, cap, base_ptr);
+                         cudaStream_t s, const long long* base_ptr, int groups) {
+    if (groups == 4) {
+        const long long nchunks = (n + 4 * CHUNK - 1) / (4 * CHUNK);
+        compress_strided_kernel<4><<<(unsigned)nchunks, 256, 0, s>>>(x, m, reject, n, chunk_off, stride_imm, stride_ptr, dense,
+                                                                     cap, base_ptr);
+    } else {
+        const long long nchunks = (n + CHUNK - 1) / CHUNK;
+        compress_strided_kernel<1><<<(unsigned)nchunks, 256, 0, s>>>(x, m, reject, n, chunk_off, stride_imm, stride_ptr, dense,
+                                                                     cap, base_ptr);
+    }
     DCR_LAUNCH_OK("compress_strided_kernel");
     return 0;
 }
