@@ -209,6 +209,15 @@ __global__ void __launch_bounds__(256) nuth_moments_final_kernel(const NuthParti
         nd->same[k] = 1;
         nd->bin_med[k] = __int_as_float(0x7fc00000);
     }
+    if (threadIdx.x == 0) {
+        // set-up of the fast bin path (linear cell map over [rmin, rmax]); degenerate ranges take the radix bins
+        const float span = nd->rmax - nd->rmin;
+        nd->fast_ncand = 0;
+        nd->fast_fallback = 0;
+        nd->fast_scale = 0.f;
+        if (!(span > 0.0f) || isinf(span) || isnan(span)) nd->fast_fallback = 1;
+        else nd->fast_scale = 65536.0f / span;
+    }
 }
 
 // ghist layout: [2][NB][2048] u32 (second plane = the upper-median state when it left the lower one's bucket)
@@ -341,15 +350,6 @@ __device__ __forceinline__ unsigned fb_fine(float y, float rmin, float scale) {
     int f = (int)t;
     f = f < 0 ? 0 : (f > 65535 ? 65535 : f);
     return (unsigned)f;
-}
-
-__global__ void fb_init_kernel(NuthDev* nd) {
-    if (threadIdx.x) return;
-    const float span = nd->rmax - nd->rmin;
-    nd->fast_ncand = 0;
-    nd->fast_fallback = 0;
-    if (!(span > 0.0f) || isinf(span) || isnan(span)) { nd->fast_fallback = 1; nd->fast_scale = 0.f; return; }
-    nd->fast_scale = 65536.0f / span;
 }
 
 __global__ void __launch_bounds__(512) fb_passA_kernel(const float* __restrict__ y, const unsigned short* __restrict__ bin,
@@ -651,15 +651,13 @@ static int nuth_bins_fast_enqueue(long long n, const NuthWs& w, cudaStream_t s) 
     }
     const int nsm = dcr_num_sms();
     DCR_CUDA_OK(cudaMemsetAsync(w.ghist, 0, (size_t)FB_WORDS * sizeof(unsigned), s));
-    fb_init_kernel<<<1, 32, 0, s>>>(w.nd);
     fb_passA_kernel<<<nsm * 2, 512, smemA, s>>>(w.y, w.bin, n, w.nd, w.ghist);
     fb_findA_kernel<<<(NB + 127) / 128, 128, 0, s>>>(w.nd, w.ghist);
     fb_passB_kernel<<<nsm * 16, 256, 0, s>>>(w.y, w.bin, n, w.nd, w.ghist, w.cand, w.cand_cap);  // small CTAs: the 4 % candidates of a CTA must fit its staging buffer
     fb_findB_kernel<<<(NB + 7) / 8, 256, 0, s>>>(w.nd, w.ghist, w.cand_cap);
     fb_passC_kernel<<<nsm * 8, 256, 0, s>>>(w.nd, w.cand, w.ghist);
     fb_passD_kernel<<<(NB + 7) / 8, 256, 0, s>>>(w.nd, w.ghist);
-    nuth_count_final_kernel<<<1, 32, 0, s>>>(w.nd);
-    DCR_LAUNCH_OK("fast bin kernels");
+    DCR_LAUNCH_OK("fast bin kernels");   // (n_final = sum of the bin counts: nuth_dev_to_stats, on the host)
     return 0;
 }
 
@@ -690,7 +688,10 @@ static int nuth_enqueue_prepared(long long n, long long nparts, int remove_outli
 
 static void nuth_dev_to_stats(const NuthDev& d, dcr_nuth_stats* o) {
     o->n_common = (int64_t)d.n_common;
-    o->n_final = (int64_t)d.n_final;
+    // n_final = sum of the bin counts (+ in-range samples outside [0,360]: none for gdaldem aspect)
+    unsigned long long nf = 0;
+    for (int k = 0; k < NB; ++k) nf += d.bin_count[k];
+    o->n_final = (int64_t)nf;
     o->mean_y = d.mean_y; o->std_y = d.std_y; o->rmin = d.rmin; o->rmax = d.rmax;
     for (int k = 0; k < NB; ++k) { o->bin_count[k] = (int64_t)d.bin_count[k]; o->bin_med[k] = d.bin_med[k]; }
 }
@@ -911,10 +912,26 @@ template <bool NUTH>
 __global__ void __launch_bounds__(256) mask_update_kernel(const float* __restrict__ dh, unsigned char* m,
                                                           long long n, IterDev* d, unsigned* __restrict__ chunk_cnt,
                                                           const float* __restrict__ slope, float* __restrict__ y,
-                                                          unsigned short* __restrict__ bin, NuthPartial* __restrict__ part) {
+                                                          unsigned short* __restrict__ bin, NuthPartial* __restrict__ part,
+                                                          int thr_mode /* 0: thresholds in d; 1: compute; 2: no filter */) {
     __shared__ unsigned s_a[8], s_b[8];
     __shared__ NuthPartial sp[8];
-    const float lo = d->mad_lo, hi = d->mad_hi;
+    float lo, hi;
+    if (thr_mode == 0) {
+        lo = d->mad_lo; hi = d->mad_hi;   // set by mad_thresholds_kernel (row-band mode: after the all-reduced selects)
+    } else {
+        // filtlib.mad_fltr: mad = 1.4826 * median(|x - med|) ; keep med - 3*mad <= x <= med + 3*mad  (float32)
+        float nmad = 0.f;
+        lo = -INFINITY; hi = INFINITY;
+        const float med = d->selres[0];
+        if (thr_mode == 1 && !isnan(med)) {
+            nmad = d->selres[1] * 1.4826f;
+            const float t = 3.0f * nmad;
+            lo = med - t;
+            hi = med + t;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) { d->nmad = nmad; d->mad_lo = lo; d->mad_hi = hi; }
+    }
     const long long nch = (n + MU_CHUNK - 1) / MU_CHUNK;
     unsigned long long cnt = 0;
     double s = 0.0, ss = 0.0;
@@ -1151,9 +1168,8 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
         if ((rc = iter_select(v, 1, w, n, use_bsel, s))) return rc;
     }
     STAGE_MARK(2);
-    mad_thresholds_kernel<<<1, 32, 0, s>>>(d, remove_outliers);
-    mask_update_kernel<true><<<(unsigned)((nch + MU_KCH - 1) / MU_KCH), 256, 0, s>>>(front->dh, front->maskbits, n, d, w.chunk_cnt, front->slope,
-                                                           w.nw.y, w.nw.bin, w.nw.part);
+    mask_update_kernel<true><<<(unsigned)((nch + MU_KCH - 1) / MU_KCH), 256, 0, s>>>(
+        front->dh, front->maskbits, n, d, w.chunk_cnt, front->slope, w.nw.y, w.nw.bin, w.nw.part, remove_outliers ? 1 : 2);
     if (side) {
         DCR_CUDA_OK(cudaEventRecord(e_mask, s));
         DCR_CUDA_OK(cudaStreamWaitEvent(s2, e_mask, 0));
@@ -1594,7 +1610,7 @@ extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, 
     } else if (phase == BP_MASK) {
         mad_thresholds_kernel<<<1, 32, 0, s>>>(d, remove_outliers);
         mask_update_kernel<false><<<(unsigned)((nch + MU_KCH - 1) / MU_KCH), 256, 0, s>>>(front->dh, front->maskbits, n, d, w.chunk_cnt, nullptr, nullptr,
-                                                                nullptr, nullptr);
+                                                                nullptr, nullptr, 0);
         band_rank_count_kernel<<<1, 32, 0, s>>>(d, rank);
         want(&d->count_mad, 2 + 8, 1);  // count_mad, count_final, rank_counts[8] are contiguous
     } else if (phase == BP_COMPRESS) {
