@@ -25,19 +25,21 @@ sys.path.insert(0, ROOT)
 
 ALG_BYTES_ITER = 90.0      # algorithmic bytes per pixel per iteration
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of front_kernel on the default 8192^2 workload, from the
-# `ncu --set full` capture summarised in profiles/front_kernel_r1_final_raw.csv (604.20 MB + 828.15 MB)
-FRONT_KERNEL_DRAM_BYTES_8192 = 1432348672
-# algorithmic bytes per pixel of each profiled stage (SURVEY 8d stage table)
+# `ncu --set full` capture summarised in profiles/front_kernel_r1_final_raw.csv
+FRONT_KERNEL_DRAM_BYTES_8192 = 1559338240   # 604.63 MB read + 954.70 MB written
+# algorithmic bytes per pixel of each profiled stage
 STAGE_INFO = [
-    ("front_kernel (warp+dh+masks+Horn)", 21.0),
-    ("bsel_* x2: median + MAD of dh (slope median overlapped on the side stream)", 16.0),
-    ("mad_thresholds + mask_update_kernel", 6.0),
-    ("(side stream only: scan/compress/dz median/med_dh)", 0.0),
-    ("nuth_prepare_kernel (y, bin, moments)", 13.0 + 6.0),
-    ("fb_pass* (bin count + exact bin medians)", 12.0),
+    ("front_kernel (TMA-staged warp + dh + masks + Horn + aspect-bin codes)", 9.0 + 15.0),
+    ("bsel_* x2 on the main stream: median + MAD of dh (slope median on a side stream)", 10.0),
+    ("mask_update_kernel (MAD filter + y + moments of y, fused)", 9.0 + 4.0),
+    ("(side streams only: scan/compress/dz median, med_dh)", 0.0),
+    ("nuth_moments_reduce/final", 0.0),
+    ("fb_pass* (bin count + exact bin medians; shares bandwidth with the side streams)", 12.0),
     ("result copy", 0.0),
 ]
-KERNELS_PER_STEP = 1 + 5 * 4 + 5 + 2 + 8 + 1  # see DESIGN.md section 6 "launch count"
+# front 1 + 5 selections x (sample, main, 2 refine) 20 + mask update 1 + scan/stride/compress 3 + moments 2 + bins 6 = 33
+# (+ one z-shift fold every 4th step)
+KERNELS_PER_STEP = 1 + 5 * 4 + 1 + 3 + 2 + 6
 
 
 def peaks():
