@@ -622,3 +622,26 @@ def test_native_align_stepper_many_steps(cuda):
     assert np.array_equal(src.numpy(), b['src_align'].numpy())
     dxt, dyt, dzt = al.totals
     assert dxt == b['dx'] and dyt == b['dy'] and dzt == b['dz']
+
+
+def test_bracket_select_staging_overflow(cuda):
+    """10 % of the elements tie exactly at the median: the bracket then holds ~16 % of the data, more than a CTA's
+    staging buffer (4096 keys) at this size, so the collector's overflow path (direct global reservations per warp)
+    runs -- the result must stay exact (candidate buffer n/6 is still large enough: no radix fallback needed)."""
+    from demcoreg_b200 import engine
+    n = 40_000_000
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(n).astype(np.float32)
+    x[rng.random(n) < 0.10] = np.float32(0.0)
+    m = (rng.random(n) < 0.25).astype(np.uint8)
+    xt, mt = cuda.from_numpy(x).cuda(), cuda.from_numpy(m).cuda()
+    a, ca = engine.select_quantiles(xt, [50.0], mt, 1)
+    b, cb = engine.select_quantiles(xt, [50.0], mt, 1, radix_only=True)
+    xv = x[m == 0]
+    want = np.float32(np.percentile(xv, 50.0))   # ranks sit inside the tie block: value 0 exactly
+    assert ca == cb == xv.size
+    assert a[0] == b[0] == want == np.float32(0.0)
+    # a quantile outside the tie block on the same data
+    a, _ = engine.select_quantiles(xt, [90.0], mt, 1)
+    b, _ = engine.select_quantiles(xt, [90.0], mt, 1, radix_only=True)
+    assert a[0] == b[0]
