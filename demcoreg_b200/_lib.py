@@ -70,7 +70,8 @@ ALIGN_MAX_PENDING = 4
 
 class AlignIter(C.Structure):
     _fields_ = [("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double), ("status", C.c_int32),
-                ("select_engine", C.c_int32), ("h", C.c_int32), ("w", C.c_int32)]
+                ("select_engine", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("fit", C.c_double * 3), ("dz_med", C.c_float), ("med_slope", C.c_float)]
 
 
 class AlignState(C.Structure):

@@ -1422,6 +1422,8 @@ extern "C" int dcr_align_nuth(dcr_align_state* st, int max_steps, int flags, dcr
             dcr_align_iter& it = iters[done_here];
             it.dx = r.dx; it.dy = r.dy; it.dz = r.dz; it.status = r.status; it.select_engine = r.select_engine;
             it.h = grid.height; it.w = grid.width;
+            it.fit[0] = r.fit[0]; it.fit[1] = r.fit[1]; it.fit[2] = r.fit[2];
+            it.dz_med = r.dz_med; it.med_slope = r.med_slope;
         }
         ++done_here;
         if (n_iters) *n_iters = done_here;

@@ -231,6 +231,9 @@ def _align_nuth_native(ref_dem_ds, src_dem_ds_align, mask_source, tol, max_offse
             print("*** Iteration %i ***" % it['n'])
             if it['status'] == 4:
                 print("Failed to calculate horizontal shift")
+            else:   # dem_align.py:157-159
+                nuth_dz = it['fit'][2] * np.tan(np.deg2rad(it['med_slope']))
+                print('Median dz: %0.2f\nNuth dz: %0.2f' % (np.float32(it['dz_med']), nuth_dz))
             print("Incremental offset: dx=%+0.2fm, dy=%+0.2fm, dz=%+0.2fm" % (it['dx'], it['dy'], dz))
             print("Cumulative offset: dx=%+0.2fm, dy=%+0.2fm, dz=%+0.2fm" % (dx_total, dy_total, dz_total))
             print("\n")

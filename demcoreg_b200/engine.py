@@ -175,7 +175,8 @@ class NuthAligner(object):
                                          _stream_ptr(torch)))
         self._sync_src()
         out = [dict(n=len(self.iters) + k + 1, dx=it.dx, dy=it.dy, dz=it.dz, status=it.status, h=it.h, w=it.w,
-                    select_engine=it.select_engine) for k, it in enumerate(self._iters[:self._n.value])]
+                    select_engine=it.select_engine, fit=(it.fit[0], it.fit[1], it.fit[2]), dz_med=it.dz_med,
+                    med_slope=it.med_slope) for k, it in enumerate(self._iters[:self._n.value])]
         self.iters.extend(out)
         return out
 

@@ -251,6 +251,8 @@ typedef struct dcr_align_iter {
     int32_t status;              /* dcr_iter_result.status */
     int32_t select_engine;
     int32_t h, w;                /* common grid of the iteration */
+    double fit[3];               /* a, b (deg), c of the iteration (NaN when status == 4) */
+    float dz_med, med_slope;     /* for the reference's per-iteration 'Median dz / Nuth dz' message (dem_align.py:157-159) */
 } dcr_align_iter;
 typedef struct dcr_align_state {
     /* inputs (device pointers, caller-owned) */
