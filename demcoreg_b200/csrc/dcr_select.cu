@@ -407,15 +407,17 @@ __global__ void __launch_bounds__(256) compress_strided_kernel(const float* __re
     // one 64-bit division per thread; the elements then advance (quotient, remainder) incrementally
     const long long rank0 = gbase + off[blockIdx.x] + ex;
     if (c == 0) return;
+    // one 64-bit division per thread; then only the PICKED elements are visited: the j-th unmasked element of this thread
+    // (j = 0 .. c-1) has rank rank0 + j, so the picks are j0, j0 + stride, ... with j0 = (-rank0) mod stride, and __fns
+    // maps j to its bit in `flags` (a per-element walk cost 35 instructions per element for ~1 pick in 11)
     long long quo = rank0 / stride;
-    long long rem = rank0 - quo * stride;
+    const long long rem = rank0 - quo * stride;
     quo -= dfirst;
-#pragma unroll
-    for (int k = 0; k < 8 * G; ++k) {
-        if (flags & (1u << k)) {
-            if (rem == 0 && quo < cap) dense[quo] = vals[k];
-            if (++rem == stride) { rem = 0; ++quo; }
-        }
+    long long j = 0;
+    if (rem != 0) { j = stride - rem; ++quo; }
+    for (; j < (long long)c; j += stride, ++quo) {
+        const int k = (int)__fns(flags, 0u, (int)j + 1);
+        if (quo < cap) dense[quo] = __ldg(x + base + k);   // (a cached re-load: indexing vals[] dynamically would spill it)
     }
 }
 
