@@ -360,9 +360,9 @@ __global__ void __launch_bounds__(512) fb_passA_kernel(const float* __restrict__
     __syncthreads();
     const float rmin = nd->rmin, rmax = nd->rmax, scale = nd->fast_scale;
     dcr_stream_f_u16(y, bin, n, [&](float yv, unsigned b, long long) {
-        if (b >= NB) return;
-        if (!(yv >= rmin && yv <= rmax)) return;
-        atomicAdd(&sh[b * FB_COARSE + (fb_fine(yv, rmin, scale) >> 10)], 1u);
+        // one predicate, one (predicated) shared-memory atomic: early returns cost a divergent branch each
+        const bool ok = (b < NB) && (yv >= rmin) && (yv <= rmax);
+        if (ok) atomicAdd(&sh[b * FB_COARSE + (fb_fine(yv, rmin, scale) >> 10)], 1u);
     });
     __syncthreads();
     unsigned* ha = ghist + FB_HA_OFF;
@@ -411,13 +411,13 @@ __global__ void __launch_bounds__(256) fb_passB_kernel(const float* __restrict__
     unsigned long long* mine = s_priv + threadIdx.x;
     unsigned c = 0;
     auto elem = [&](float yv, unsigned b) {
-        if (b >= NB) return;
-        if (!(yv >= rmin && yv <= rmax)) return;
+        // straight-line classification (one rare branch): early returns cost a divergent branch each
+        const bool ok = (b < NB) && (yv >= rmin) && (yv <= rmax);
         const unsigned f = fb_fine(yv, rmin, scale);
         const unsigned cc = f >> 10;
-        const unsigned c01 = s_c01[b];
+        const unsigned c01 = s_c01[b < NB ? b : 0u];
         const unsigned c0 = c01 & 0xffffu, c1 = c01 >> 16;
-        if (cc != c0 && cc != c1) return;
+        if (!(ok && (cc == c0 || cc == c1))) return;
         const unsigned plane = (cc == c0) ? 0u : 1u;
         const unsigned long long rec = ((unsigned long long)dcr_f2key(yv) << 32) | ((unsigned long long)b << 16) | f;
         if (c < FB_PRIV) {
