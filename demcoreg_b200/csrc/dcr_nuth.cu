@@ -730,10 +730,27 @@ extern "C" int dcr_fit_nuth(const double* xc, const double* ym, int n, double fi
     DCR_ARG(xc && ym && fit, "null pointer");
     DCR_ARG(n >= 3 && n <= 4096, "3 <= n <= 4096");
     static thread_local double M[4096 * 4];
+    // cos / sin of the 360 bin centres k + 0.5 (the only abscissae the iteration ever passes): computed once
+    static thread_local double tab_c[NB], tab_s[NB];
+    static thread_local bool tab_ok = false;
+    if (!tab_ok) {
+        for (int k = 0; k < NB; ++k) {
+            const double xr = ((double)k + 0.5) * (M_PI / 180.0);
+            tab_c[k] = cos(xr);
+            tab_s[k] = sin(xr);
+        }
+        tab_ok = true;
+    }
     for (int r = 0; r < n; ++r) {
-        const double xr = xc[r] * (M_PI / 180.0);
-        M[r * 4 + 0] = cos(xr);
-        M[r * 4 + 1] = sin(xr);
+        const int k = (int)xc[r];
+        if (k >= 0 && k < NB && xc[r] == (double)k + 0.5) {
+            M[r * 4 + 0] = tab_c[k];
+            M[r * 4 + 1] = tab_s[k];
+        } else {
+            const double xr = xc[r] * (M_PI / 180.0);
+            M[r * 4 + 0] = cos(xr);
+            M[r * 4 + 1] = sin(xr);
+        }
         M[r * 4 + 2] = 1.0;
         M[r * 4 + 3] = ym[r];
     }
@@ -833,10 +850,18 @@ __global__ void __launch_bounds__(256) zshift_seq_kernel(float* __restrict__ ban
     if (stride == w && DCR_AL16(band)) {   // contiguous band: float4 read-modify-write
         const long long n4 = n >> 2;
         float4* b4 = reinterpret_cast<float4*>(band);
-        for (long long k = (long long)blockIdx.x * 256 + threadIdx.x; k < n4; k += step) {
-            float4 v = b4[k];
-            v.x = shift(v.x); v.y = shift(v.y); v.z = shift(v.z); v.w = shift(v.w);
-            b4[k] = v;
+        for (long long k0 = (long long)blockIdx.x * 256 + threadIdx.x; k0 < n4; k0 += 4 * step) {
+            float4 v[4];   // 4 independent 16-byte loads in flight per thread
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (k0 + u * step < n4) v[u] = b4[k0 + u * step];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (k0 + u * step < n4) {
+                    v[u].x = shift(v[u].x); v[u].y = shift(v[u].y); v[u].z = shift(v[u].z); v[u].w = shift(v[u].w);
+                    b4[k0 + u * step] = v[u];
+                }
+            }
         }
         for (long long k = (n4 << 2) + (long long)blockIdx.x * 256 + threadIdx.x; k < n; k += step) band[k] = shift(band[k]);
         return;
@@ -1251,11 +1276,17 @@ static int iter_finalize(const IterDev* hd, int engine_used, dcr_iter_result* ou
     double xc[NB], ym[NB];
     int nb = 0;
     double cmin = INFINITY, cmax = -INFINITY;
+    static thread_local double cos_center[NB];
+    static thread_local bool cos_ok = false;
+    if (!cos_ok) {
+        for (int k = 0; k < NB; ++k) cos_center[k] = cos(((double)k + 0.5) * (M_PI / 180.0));
+        cos_ok = true;
+    }
     for (int k = 0; k < NB; ++k) {
         if (out->nuth.bin_count[k] >= 9) {
             xc[nb] = k + 0.5;
             ym[nb] = (double)out->nuth.bin_med[k];
-            const double c = cos(xc[nb] * (M_PI / 180.0));
+            const double c = cos_center[k];
             cmin = fmin(cmin, c); cmax = fmax(cmax, c);
             ++nb;
         }
