@@ -645,3 +645,77 @@ def test_bracket_select_staging_overflow(cuda):
     a, _ = engine.select_quantiles(xt, [90.0], mt, 1)
     b, _ = engine.select_quantiles(xt, [90.0], mt, 1, radix_only=True)
     assert a[0] == b[0]
+
+
+def _crop(p, key, r0, r1, c0, c1):
+    """A sub-raster with its own geotransform (north-up): rows [r0, r1), cols [c0, c1)."""
+    gt = list(p['gt'])
+    gt[0] += c0 * gt[1]
+    gt[3] += r0 * gt[5]
+    return np.ascontiguousarray(p[key][r0:r1, c0:c1]), tuple(gt)
+
+
+@pytest.mark.parametrize("case", ["partial_overlap", "src_inside_ref", "non_square_shifted"])
+def test_iteration_ragged_inputs(cuda, case):
+    """Rasters of different sizes / origins (partial overlap, containment, non-square grids with a sub-pixel shift):
+    the intersection grid, masks and counts must equal the oracle's memwarp_multi(extent='intersection') path."""
+    from demcoreg_b200 import engine, _lib
+    from demcoreg_b200.raster import Raster, MaskSource
+    from oracle import dem_align as oda, pygeotools_restated as pg
+    p = _pair(n=1024, res=30.0, nodata_frac=0.01, static_mask_frac=0.2)
+    if case == "partial_overlap":
+        (ra, rgt), (sa, sgt) = _crop(p, 'ref', 40, 900, 25, 1000), _crop(p, 'src', 0, 801, 131, 1024)
+        sh = (0.0, 0.0)
+    elif case == "src_inside_ref":
+        (ra, rgt), (sa, sgt) = _crop(p, 'ref', 0, 1024, 0, 1024), _crop(p, 'src', 200, 777, 150, 905)
+        sh = (7.3, -11.9)
+    else:
+        (ra, rgt), (sa, sgt) = _crop(p, 'ref', 100, 600, 0, 1024), _crop(p, 'src', 64, 700, 301, 1001)
+        sh = (-44.1, 17.6)
+    sgt = _shifted_gt(sgt, *sh)
+    res, grid, bufs = engine.nuth_iteration(Raster(ra, rgt, p['ndv']), Raster(sa, sgt, p['ndv']), MaskSource(p['mask'], p['gt']))
+    det = {}
+    odx, ody, odz, omask, _ = oda.compute_offset(pg.MemDataset(ra, rgt, p['ndv']), pg.MemDataset(sa, sgt, p['ndv']),
+                                                 mask_source=oda.MaskSource(p['mask'], p['gt']), details=det)
+    assert (grid.height, grid.width) == omask.shape
+    assert grid.height != grid.width
+    gmask = ((bufs.maskbits & _lib.M_DIFF) != 0).cpu().numpy()
+    assert np.array_equal(gmask, omask)
+    _compare_iteration(res, det, odx, ody, odz)
+
+
+def test_exits_and_degenerate_inputs(cuda):
+    """The reference's sys.exit paths (dem_align.py:88-89, coreglib.py:206-209) and library errors."""
+    from demcoreg_b200 import engine, dem_align, _lib
+    from demcoreg_b200.raster import Raster, MaskSource
+    p = _pair(n=256, res=30.0)
+    ref, src = _gds(p, 'ref'), _gds(p, 'src')
+    # 1. disjoint extents: no intersection (library error -2, as memwarp_multi would fail)
+    far = Raster(p['src'], _shifted_gt(p['gt'], 1e6, 0.0), p['ndv'])
+    with pytest.raises(_lib.DcrError, match="no intersection"):
+        engine.nuth_iteration(ref, far)
+    # 2. everything masked by the static mask -> "No overlapping, unmasked pixels shared between input DEMs"
+    allm = MaskSource(np.ones((256, 256), np.uint8), p['gt'])
+    res, _, _ = engine.nuth_iteration(ref, src, allm)
+    assert res.status == 1 and res.count_base == 0
+    with pytest.raises(SystemExit, match="No overlapping"):
+        dem_align.compute_offset(ref, src, None, mask_list=[], mask_source=allm)
+    with pytest.raises(SystemExit, match="No overlapping"):
+        dem_align.align(ref, src, mask_source=allm, verbose=False)          # native loop: same exit
+    # 3. fewer than 100 samples left -> "Not enough dh samples"
+    few = np.ones((256, 256), np.uint8); few[100:108, 100:110] = 0          # 80 unmasked pixels
+    res, _, _ = engine.nuth_iteration(ref, src, MaskSource(few, p['gt']))
+    assert res.status == 2 and 0 < res.count_final < 100
+    with pytest.raises(SystemExit, match="Not enough dh samples"):
+        dem_align.align(ref, src, mask_source=MaskSource(few, p['gt']), verbose=False)
+    # 4. a raster smaller than one kernel tile (40 x 50): runs, too few bins for a fit -> dx = dy = 0 (status 4)
+    from oracle import dem_align as oda, pygeotools_restated as pg
+    (ra, rgt), (sa, sgt) = _crop(p, 'ref', 10, 50, 20, 70), _crop(p, 'src', 10, 50, 20, 70)
+    res, grid, bufs = engine.nuth_iteration(Raster(ra, rgt, p['ndv']), Raster(sa, sgt, p['ndv']))
+    det = {}
+    odx, ody, odz, omask, _ = oda.compute_offset(pg.MemDataset(ra, rgt, p['ndv']), pg.MemDataset(sa, sgt, p['ndv']), details=det)
+    assert (grid.height, grid.width) == (40, 50)
+    assert np.array_equal(((bufs.maskbits & _lib.M_DIFF) != 0).cpu().numpy(), omask)
+    assert res.count_final == det['count_final'] and res.dz_med == det['dz_med']
+    assert (res.status == 4) == (det.get('fit') is None)
+    assert abs(res.dx - odx) < OFFTOL and abs(res.dy - ody) < OFFTOL
