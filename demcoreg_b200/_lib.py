@@ -91,6 +91,11 @@ class AlignState(C.Structure):
     ]
 
 
+class Poly2d(C.Structure):
+    _fields_ = [("order", C.c_int32), ("_pad", C.c_int32), ("x0", C.c_double), ("y0", C.c_double), ("xs", C.c_double),
+                ("ys", C.c_double), ("coeff_norm", C.c_double * 16), ("coeff", C.c_double * 16)]
+
+
 # every symbol include/demcoreg_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -135,6 +140,12 @@ SYMBOLS = {
     "dcr_align_nuth": (C.c_int, [C.POINTER(AlignState), C.c_int, C.c_int, C.POINTER(AlignIter), C.c_int,
                                  C.POINTER(C.c_int), _P, C.c_size_t, _P]),
     "dcr_align_flush_z": (C.c_int, [C.POINTER(AlignState), _P]),
+    "dcr_polyfit2d_workspace_bytes": (C.c_size_t, []),
+    "dcr_polyfit2d": (C.c_int, [_P, _P, C.c_uint32, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_double), C.c_int,
+                                C.POINTER(Poly2d), C.POINTER(C.c_int64), _P, C.c_size_t, _P]),
+    "dcr_polyval2d": (C.c_int, [C.POINTER(Poly2d), C.POINTER(C.c_double), C.c_int, C.c_int, _P, C.c_int64, _P]),
+    "dcr_polyval2d_apply": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_double), C.c_double, C.c_int,
+                                      C.POINTER(Poly2d), C.c_double, _P]),
 }
 
 _lib = None

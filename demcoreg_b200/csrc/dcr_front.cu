@@ -39,6 +39,7 @@ extern "C" int dcr_struct_size(int which) {
         case 5: return (int)sizeof(dcr_iter_result);
         case 6: return (int)sizeof(dcr_align_iter);
         case 7: return (int)sizeof(dcr_align_state);
+        case 8: return (int)sizeof(dcr_poly2d);
         default: return -1;
     }
 }

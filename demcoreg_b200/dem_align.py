@@ -158,7 +158,7 @@ def getparser():
 
 
 def align(ref_dem_ds, src_dem_ds, mode='nuth', mask_source=None, tol=0.02, max_offset=100, max_dz=100,
-          slope_lim=(0.1, 40), max_iter=30, verbose=True, records=None):
+          slope_lim=(0.1, 40), max_iter=30, verbose=True, records=None, tiltcorr=False, polyorder=1):
     """The iteration loop of reference ``dem_align.py:291-357`` on device-resident rasters.
 
     ``src_dem_ds`` is copied; the copy is shifted in place each iteration (geotransform + band) exactly
@@ -169,7 +169,9 @@ def align(ref_dem_ds, src_dem_ds, mode='nuth', mask_source=None, tol=0.02, max_o
     src_dem_ds_align = src_dem_ds.copy()
     if mode == 'nuth' and records is None:
         return _align_nuth_native(ref_dem_ds, src_dem_ds_align, mask_source, tol, max_offset, max_dz, slope_lim, max_iter,
-                                  verbose)
+                                  verbose, tiltcorr, polyorder)
+    if tiltcorr:
+        raise NotImplementedError("-tiltcorr is wired to the native nuth loop (mode='nuth', records=None)")
     n = 1
     dx_total = 0
     dy_total = 0
@@ -212,11 +214,41 @@ def align(ref_dem_ds, src_dem_ds, mode='nuth', mask_source=None, tol=0.02, max_o
                 src_align=src_dem_ds_align)
 
 
-def _align_nuth_native(ref_dem_ds, src_dem_ds_align, mask_source, tol, max_offset, max_dz, slope_lim, max_iter, verbose):
+def _align_nuth_native(ref_dem_ds, src_dem_ds_align, mask_source, tol, max_offset, max_dz, slope_lim, max_iter, verbose,
+                       tiltcorr=False, polyorder=1):
     """The same loop through ``dcr_align_nuth``: every iteration is chained natively (no interpreter work between the
-    kernels of consecutive iterations); the reference's per-iteration messages are replayed afterwards."""
+    kernels of consecutive iterations); the reference's per-iteration messages are replayed afterwards.
+
+    ``tiltcorr`` (reference ``dem_align.py:396-447``): when the loop first stops, ONE polynomial of order ``polyorder`` is
+    fitted to the filtered final difference and removed from the source; the loop then goes on for up to ``max_iter``
+    more iterations."""
     al = engine.NuthAligner(ref_dem_ds, src_dem_ds_align, mask_source, tol, max_offset, max_dz, slope_lim, max_iter)
     al.run()
+    tilt = None
+    if tiltcorr and al.st.exit_code == 0:
+        from . import tiltcorr as tc, robust_stats
+        al.finish()
+        if verbose:
+            print("\n************")
+            print("Calculating 'tiltcorr' 2D polynomial fit to residuals with order %i" % polyorder)
+            print("************\n")
+        # final difference on the common grid + its filtered version (dem_align.py:366-392): the masks of one more
+        # front/filter pass with the DEFAULT slope limits, exactly what diff_stats() reports
+        res, grid, bufs = engine.nuth_iteration(ref_dem_ds, src_dem_ds_align, mask_source, True, max_dz, (0.1, 40))
+        if res.status in _EXIT_MSG:
+            sys.exit(_EXIT_MSG[res.status])
+        gt_clip = tuple(grid.gt)
+        model, cnt = tc.polyfit2d(bufs.dh, bufs.maskbits, _lib.M_DIFF, gt_clip, polyorder)
+        vals = tc.polyval2d(model, gt_clip, grid.height, grid.width)
+        tilt = dict(coeff=tc.coeff_list(model), model=model, count=cnt, gt=gt_clip, vals=vals,
+                    val_stats=robust_stats.get_stats_dict(vals, None, full=True))
+        if verbose:
+            print(np.array(tilt['coeff']))
+        tc.apply_polyval(src_dem_ds_align, model, -1.0)          # apply_z_shift(src_dem_ds_align, -valgrid)
+        # "Now use original tolerance, and number of iterations": max_iter = n + args.max_iter with n the NEXT iteration
+        al.st.finished = 0
+        al.st.max_iter = al.st.n_done + 1 + int(max_iter)
+        al.run()
     iters = []
     dx_total = dy_total = 0.0
     dz_total = np.float32(0)
@@ -242,7 +274,10 @@ def _align_nuth_native(ref_dem_ds, src_dem_ds_align, mask_source, tol, max_offse
         sys.exit("Total offset exceeded specified max_offset (%0.2f m). Consider increasing -max_offset argument" % max_offset)
     al.finish()
     dxt, dyt, dzt = al.totals
-    return dict(dx=dxt, dy=dyt, dz=dzt, n_iter=len(iters), iters=iters, src_align=src_dem_ds_align)
+    out = dict(dx=dxt, dy=dyt, dz=dzt, n_iter=len(iters), iters=iters, src_align=src_dem_ds_align)
+    if tilt is not None:
+        out['tiltcorr'] = tilt
+    return out
 
 
 def diff_stats(ref_dem_ds, src_dem_ds, mask_source=None, max_dz=100):
@@ -275,11 +310,13 @@ def main(argv=None):
     src_dem_fn = args.src_fn
     mode = args.mode
     slope_lim = tuple(args.slope_lim)
-    if args.tiltcorr:
-        raise NotImplementedError("-tiltcorr is a 'next' row (SURVEY 8f-2)")
+    tiltcorr = args.tiltcorr
+    polyorder = args.polyorder
     outdir = args.outdir
     if outdir is None:
         outdir = os.path.splitext(src_dem_fn)[0] + '_dem_align'
+    if tiltcorr:
+        outdir += '_tiltcorr'          # dem_align.py:233-234
     if not os.path.exists(outdir):
         os.makedirs(outdir)
     outprefix = '%s_%s' % (os.path.splitext(os.path.split(src_dem_fn)[-1])[0],
@@ -300,16 +337,22 @@ def main(argv=None):
         get_mask(None, args.mask_list)
 
     out = align(ref, src, mode=mode, mask_source=mask_source, tol=args.tol, max_offset=args.max_offset,
-                max_dz=args.max_dz, slope_lim=slope_lim, max_iter=args.max_iter)
+                max_dz=args.max_dz, slope_lim=slope_lim, max_iter=args.max_iter, tiltcorr=tiltcorr, polyorder=polyorder)
     dx_total, dy_total, dz_total = out['dx'], out['dy'], out['dz']
     xyz_shift_str_cum_fn = '_%s_x%+0.2f_y%+0.2f_z%+0.2f' % (mode, dx_total, dy_total, dz_total)
     align_fn = outprefix + xyz_shift_str_cum_fn + '_align.tif'
     print("Writing out shifted src_dem with median vertical offset removed: %s" % align_fn)
-    sa = out['src_align']
+    # dem_align.py:466-483: the ORIGINAL dataset with the TOTAL shifts applied once (not the loop's copy, whose band went
+    # through one float32 add per iteration), then the tilt surface on its own grid
+    sa = coreglib.apply_xy_shift(src.copy(), dx_total, dy_total, createcopy=False)
+    sa = coreglib.apply_z_shift(sa, np.float32(dz_total), createcopy=False)
+    if tiltcorr and 'tiltcorr' in out:
+        from . import tiltcorr as tc
+        tc.apply_polyval(sa, out['tiltcorr']['model'], -1.0)
     rio.write_raster(align_fn, sa.numpy(), sa.gt, sa.ndv, sa.proj)
     dm_total = float(np.sqrt(dx_total ** 2 + dy_total ** 2 + dz_total ** 2))
-    # final elevation difference (dem_align.py:366-392) and the original one (dem_align.py:506-530)
-    after = diff_stats(ref, sa, mask_source, args.max_dz)
+    # final elevation difference (dem_align.py:366-392, from the loop's dataset) and the original one (dem_align.py:506-530)
+    after = diff_stats(ref, out['src_align'], mask_source, args.max_dz)
     before = diff_stats(ref, src, mask_source, args.max_dz)
     ndv_out = -9999.0
     rio.write_raster(outprefix + xyz_shift_str_cum_fn + '_align_diff.tif', after['diff'].filled(ndv_out), after['gt'], ndv_out)
@@ -328,6 +371,8 @@ def main(argv=None):
             'before': before['stats'], 'before_filt': before['stats_filt'],
             'after': after['stats'], 'after_filt': after['stats_filt'],
             'n_iter': out['n_iter']}
+    if tiltcorr and 'tiltcorr' in out:   # dem_align.py:553-556
+        info['tiltcorr'] = {'coeff': out['tiltcorr']['coeff'], 'val_stats': out['tiltcorr']['val_stats']}
     json_fn = outprefix + xyz_shift_str_cum_fn + '_align_stats.json'
     with open(json_fn, 'w') as f:
         json.dump(info, f)

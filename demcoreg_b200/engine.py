@@ -155,7 +155,7 @@ class NuthAligner(object):
         st.max_iter = int(max_iter)
         st.remove_outliers = 1 if remove_outliers else 0
         self.ws = workspace(self.L.dcr_iteration_workspace_bytes(self.cap))
-        self._iters = (_lib.AlignIter * min(max(1, int(max_iter)), 1024))()
+        self._iters = (_lib.AlignIter * (min(max(1, int(max_iter)), 1024) + 2))()
         self.grid_hw = (0, 0)
         self._n = C.c_int(0)
         self.iters = []

@@ -38,7 +38,7 @@ extern "C" {
 const char* dcr_last_error(void);
 int dcr_version(void);
 /* sizeof() of the ABI structs, for binding self-checks: 0 raster_desc, 1 warp_geom, 2 grid, 3 front_args,
- * 4 nuth_stats, 5 iter_result, 6 align_iter, 7 align_state; -1 for an unknown index */
+ * 4 nuth_stats, 5 iter_result, 6 align_iter, 7 align_state, 8 poly2d; -1 for an unknown index */
 int dcr_struct_size(int which);
 
 /* ---- geometry (host only) -------------------------------------------------------------
@@ -283,6 +283,31 @@ int dcr_align_nuth(dcr_align_state* st, int max_steps, int flags, dcr_align_iter
                    void* workspace, size_t workspace_bytes, void* stream);
 /* Writes the pending z shifts into the source band (call before reading the aligned band). */
 int dcr_align_flush_z(dcr_align_state* st, void* stream);
+
+/* ---- -tiltcorr: 2-D polynomial fit of the filtered residuals and its removal --------------------------------
+ * dem_align.py:396-447, 478-483: geolib.ma_fitpoly(diff_align_filt, order, gt, perc=(0,100), origmask=False) ->
+ * geolib.polyfit2d (least squares on x^i y^j, (i, j) in product(range(order+1), repeat=2), x / y = map coordinates of the
+ * pixel centres), geolib.polyval2d, coreglib.apply_z_shift(ds, -valgrid), diff_align -= vals.
+ * The fit runs in centred / scaled coordinates u = (x - x0)/xs, v = (y - y0)/ys (same surface: the tensor-product basis is
+ * closed under affine maps; well-conditioned normal equations); `coeff` is that surface expanded in the reference's raw
+ * basis (informational: in raw coordinates the coefficients are ill-determined, parity is on the surface). */
+typedef struct dcr_poly2d {
+    int32_t order, _pad;
+    double x0, y0, xs, ys;
+    double coeff_norm[16];       /* c[i*(order+1)+j] of u^i v^j */
+    double coeff[16];            /* m[i*(order+1)+j] of x^i y^j (geolib.polyfit2d ordering) */
+} dcr_poly2d;
+size_t dcr_polyfit2d_workspace_bytes(void);
+/* z: device h x w float32 (element stride `stride`); mask: device h*w uint8 (contiguous) or NULL; a pixel takes part iff
+ * (mask & reject) == 0 and z is not NaN.  1 <= order <= 3.  model / count: host.  -6: too few samples / singular. */
+int dcr_polyfit2d(const float* z, const uint8_t* mask, uint32_t reject, int h, int w, int64_t stride, const double gt[6],
+                  int order, dcr_poly2d* model, int64_t* count, void* workspace, size_t workspace_bytes, void* stream);
+/* vals (device h x w float32) = polynomial at the pixel centres of the grid with geotransform gt */
+int dcr_polyval2d(const dcr_poly2d* model, const double gt[6], int h, int w, float* vals, int64_t vals_stride, void* stream);
+/* band <- float32(float64(band) + sign * polynomial), nodata pixels (numpy masked_values tolerance) left at ndv:
+ * coreglib.apply_z_shift(ds, sign * valgrid) for a float64 valgrid, and `diff_align -= vals` (has_ndv = 0, sign = -1) */
+int dcr_polyval2d_apply(float* band, int h, int w, int64_t stride, const double gt[6], double ndv, int has_ndv,
+                        const dcr_poly2d* model, double sign, void* stream);
 
 /* ---- row-band mode: one very large raster split into bands of output rows, one band per GPU ----------------
  * (BASELINE.json configs[4]; the reference does not tile -- it loads whole arrays, dem_align.py:79-80.)

@@ -165,9 +165,29 @@ def compute_offset(ref_dem_ds, src_dem_ds, src_dem_fn=None, mode='nuth', remove_
     return -dx, -dy, -dz, static_mask, fig
 
 
+def _final_diff(ref_dem_ds, src_dem_ds_align, res, mask_source, max_dz):
+    """Reference ``dem_align.py:366-392``: final difference on the common grid, its statistics and the filtered version."""
+    ref_c, src_c = pg.memwarp_multi([ref_dem_ds, src_dem_ds_align], res=res, extent='intersection', r='cubic')
+    ref_a = pg.ds_getma(ref_c, 1)
+    src_a = pg.ds_getma(src_c, 1)
+    diff_align = src_a - ref_a
+    smf = get_mask(src_c, [], None, mask_source=mask_source)
+    smf = np.logical_or(np.ma.getmaskarray(diff_align), smf)
+    out = dict(gt=src_c.GetGeoTransform())
+    out['diff_align_stats'] = pg.get_stats_dict(diff_align[~smf], full=True)
+    filt = np.ma.array(diff_align, mask=smf)
+    filt = outlier_filter(filt, f=3, max_dz=max_dz)
+    slope = get_filtered_slope(src_c)
+    filt = np.ma.array(filt, mask=np.ma.getmaskarray(slope))
+    out['diff_align_filt_stats'] = pg.get_stats_dict(filt, full=True)
+    out['diff_align'] = diff_align
+    out['diff_align_filt'] = filt
+    return out
+
+
 def align(ref_dem_ds, src_dem_ds, mode='nuth', mask_source=None, tol=0.02, max_offset=100, max_dz=100,
           slope_lim=(0.1, 40), max_iter=30, res='mean', verbose=False, time_plot_path=False, records=None,
-          final_stats=True):
+          final_stats=True, tiltcorr=False, polyorder=1):
     """The iteration loop of reference ``dem_align.py:291-392`` (no file I/O, no plots).
 
     Returns a dict with the cumulative shift, iteration count, per-iteration wall
@@ -183,6 +203,10 @@ def align(ref_dem_ds, src_dem_ds, mode='nuth', mask_source=None, tol=0.02, max_o
     dy_total = 0
     dz_total = 0
     iters = []
+    tiltcorr_done = False
+    tilt = None
+    fin = None
+    max_iter0 = max_iter
     while True:
         t0 = time.perf_counter()
         det = {} if records is not None else None
@@ -208,24 +232,25 @@ def align(ref_dem_ds, src_dem_ds, mode='nuth', mask_source=None, tol=0.02, max_o
         if dm_total > max_offset:
             sys.exit("Total offset exceeded specified max_offset (%0.2f m). Consider increasing -max_offset argument" % max_offset)
         if n > max_iter or dm < tol:
-            break
+            # final difference (dem_align.py:366-392); with -tiltcorr: ONE polynomial fit of the filtered residuals,
+            # removed from the source, then the loop goes on with max_iter more iterations (dem_align.py:396-447)
+            fin = _final_diff(ref_dem_ds, src_dem_ds_align, res, mask_source, max_dz) if (final_stats or tiltcorr) else None
+            if tiltcorr and not tiltcorr_done:
+                gt = fin['gt']
+                vals, resid, coeff = pg.ma_fitpoly(fin['diff_align_filt'], order=polyorder, gt=gt, perc=(0, 100), origmask=False)
+                tilt = dict(coeff=coeff, vals=vals, val_stats=pg.get_stats_dict(vals))
+                xgrid, ygrid = pg.get_xy_grids(src_dem_ds_align)
+                valgrid = coeff(xgrid, ygrid)   # geolib.polyval2d(xgrid, ygrid, coeff) on the model (see pg.ma_fitpoly)
+                src_dem_ds_align = coreglib.apply_z_shift(src_dem_ds_align, -valgrid, createcopy=False)
+                tiltcorr_done = True
+                max_iter = n + max_iter0
+            else:
+                break
 
     out = dict(dx=float(dx_total), dy=float(dy_total), dz=float(dz_total), n_iter=n - 1, iters=iters,
                src_align=src_dem_ds_align, ref=ref_dem_ds, res=res)
-    if final_stats:
-        ref_c, src_c = pg.memwarp_multi([ref_dem_ds, src_dem_ds_align], res=res, extent='intersection', r='cubic')
-        ref_a = pg.ds_getma(ref_c, 1)
-        src_a = pg.ds_getma(src_c, 1)
-        diff_align = src_a - ref_a
-        smf = get_mask(src_c, [], None, mask_source=mask_source)
-        smf = np.logical_or(np.ma.getmaskarray(diff_align), smf)
-        diff_align_compressed = diff_align[~smf]
-        out['diff_align_stats'] = pg.get_stats_dict(diff_align_compressed, full=True)
-        filt = np.ma.array(diff_align, mask=smf)
-        filt = outlier_filter(filt, f=3, max_dz=max_dz)
-        slope = get_filtered_slope(src_c)
-        filt = np.ma.array(filt, mask=np.ma.getmaskarray(slope))
-        out['diff_align_filt_stats'] = pg.get_stats_dict(filt, full=True)
-        out['diff_align'] = diff_align
-        out['diff_align_filt'] = filt
+    if tilt is not None:
+        out['tiltcorr'] = tilt
+    if fin is not None:
+        out.update({k: fin[k] for k in ('diff_align_stats', 'diff_align_filt_stats', 'diff_align', 'diff_align_filt')})
     return out

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(built_lib):
 def test_struct_layouts_match(built_lib):
     from demcoreg_b200 import _lib
     for i, t in enumerate([_lib.RasterDesc, _lib.WarpGeom, _lib.Grid, _lib.FrontArgs, _lib.NuthStats, _lib.IterResult,
-                           _lib.AlignIter, _lib.AlignState]):
+                           _lib.AlignIter, _lib.AlignState, _lib.Poly2d]):
         assert C.sizeof(t) == built_lib.dcr_struct_size(i), t.__name__
     assert built_lib.dcr_struct_size(99) == -1
 

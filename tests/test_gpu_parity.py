@@ -501,7 +501,10 @@ def test_cli_end_to_end(cuda, tmp_path):
     for k in ('dx', 'dy', 'dz'):
         assert abs(info['shift'][k] - oo[k]) < OFFTOL
     out = rio.read_array(info['align_fn'])
-    assert np.array_equal(out['array'], oo['src_align'].array)
+    # dem_align.py:466-483: the written product is the ORIGINAL source with the TOTAL shifts applied once
+    from oracle import coreglib as ocl
+    want = ocl.apply_z_shift(ocl.apply_xy_shift(_ods(p, 'src'), oo['dx'], oo['dy']), np.float32(oo['dz']))
+    assert np.array_equal(out['array'], want.array)
     assert abs(out['gt'][0] - oo['src_align'].gt[0]) < 1e-6 and abs(out['gt'][3] - oo['src_align'].gt[3]) < 1e-6
     assert "_nuth_x%+0.2f_y%+0.2f_z%+0.2f" % (oo['dx'], oo['dy'], oo['dz']) in info['align_fn']
     js = json.load(open(info['align_fn'].replace('_align.tif', '_align_stats.json')))
@@ -719,3 +722,91 @@ def test_exits_and_degenerate_inputs(cuda):
     assert res.count_final == det['count_final'] and res.dz_med == det['dz_med']
     assert (res.status == 4) == (det.get('fit') is None)
     assert abs(res.dx - odx) < OFFTOL and abs(res.dy - ody) < OFFTOL
+
+
+def _tilted_pair(n=512, res=30.0):
+    p = _pair(n=n, res=res, nodata_frac=0.01)
+    jj, ii = np.meshgrid(np.arange(n), np.arange(n))
+    tilt = (0.8 + 2.0 * (jj / n - 0.5) - 1.2 * (ii / n - 0.5)).astype(np.float32)
+    src = p['src'].copy()
+    v = src != p['ndv']
+    src[v] += tilt[v]
+    p['src'] = src
+    return p
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_polyfit2d_surface(cuda, order):
+    """dcr_polyfit2d / dcr_polyval2d against least squares in float64: the oracle's geolib.ma_fitpoly restatement for
+    order 1 (raw map coordinates), a centred-coordinate lstsq for order 2 (where raw coordinates are rank-deficient in
+    float64 and np.linalg.lstsq returns its regularised answer).  See the note in oracle ma_fitpoly."""
+    from demcoreg_b200 import tiltcorr as tc
+    from oracle import pygeotools_restated as pg
+    rng = np.random.default_rng(5 + order)
+    h, w = 300, 420
+    gt = (512345.0, 30.0, 0.0, 4101234.0, 0.0, -30.0)
+    pX, pY = np.meshgrid(np.arange(w), np.arange(h))
+    x, y = pg.pixel_to_map(pX, pY, gt)
+    u, v = (x - x.mean()) / 6000.0, (y - y.mean()) / 6000.0
+    z = 0.3 + 1.5 * u - 0.7 * v + 0.4 * u * v + (0.25 * u * u - 0.1 * v * v if order == 2 else 0.0)
+    z = (z + 0.05 * rng.standard_normal(z.shape)).astype(np.float32)
+    m = (rng.random(z.shape) < 0.3).astype(np.uint8) * 4
+    zt, mt = cuda.from_numpy(z).cuda(), cuda.from_numpy(m).cuda()
+    model, cnt = tc.polyfit2d(zt, mt, 4, gt, order)
+    assert cnt == int((m == 0).sum())
+    vals = tc.polyval2d(model, gt, h, w).cpu().numpy().astype(np.float64)
+    bma = np.ma.array(z, mask=m != 0)
+    ovals, _, omodel = pg.ma_fitpoly(bma, order=order, gt=gt, perc=(0, 100), origmask=False)
+    np.testing.assert_allclose([model.x0, model.y0, model.xs, model.ys], [omodel.x0, omodel.y0, omodel.xs, omodel.ys], rtol=1e-15)
+    np.testing.assert_allclose([model.coeff_norm[k] for k in range((order + 1) ** 2)], omodel.coeff_norm, rtol=0, atol=1e-8)
+    if order == 1:
+        # the raw-basis expansion (json 'coeff') describes the same surface
+        mine = pg.polyval2d(x, y, np.array(tc.coeff_list(model)))
+        assert np.abs(mine - vals).max() < 1e-3
+    assert np.abs(vals - ovals).max() < 1e-4, np.abs(vals - ovals).max()
+    # removal: diff -= vals in float64, rounded once
+    d = zt.clone()
+    tc.subtract_polyval(d, gt, model)
+    assert np.abs(d.cpu().numpy().astype(np.float64) - (z.astype(np.float64) - ovals)).max() < 2e-4
+
+
+def test_tiltcorr_align_matches_oracle(cuda):
+    """dem_align -tiltcorr (dem_align.py:396-447): loop, ONE plane fit of the filtered residuals, removal, loop again."""
+    from demcoreg_b200 import dem_align
+    from oracle import dem_align as oda
+    p = _tilted_pair()
+    out = dem_align.align(_gds(p, 'ref'), _gds(p, 'src'), verbose=False, tiltcorr=True, polyorder=1)
+    oo = oda.align(_ods(p, 'ref'), _ods(p, 'src'), final_stats=False, tiltcorr=True, polyorder=1)
+    assert out['n_iter'] == oo['n_iter']
+    for k in ('dx', 'dy', 'dz'):
+        assert abs(out[k] - oo[k]) < OFFTOL, (k, out[k], oo[k])
+    gv = out['tiltcorr']['vals'].cpu().numpy().astype(np.float64)
+    ov = np.asarray(oo['tiltcorr']['vals'], dtype=np.float64)
+    assert gv.shape == ov.shape
+    assert np.abs(gv - ov).max() < 1e-3
+    assert np.ptp(ov) > 2.5                                   # the injected +-1.6 m tilt was found ...
+    a, b = out['src_align'].numpy(), oo['src_align'].array
+    valid = b != np.float32(p['ndv'])
+    assert np.array_equal(a != np.float32(p['ndv']), valid)
+    assert np.abs(a[valid].astype(np.float64) - b[valid]).max() < 2e-3   # ... and removed identically (f32 elevations ~1e3 m)
+    for k in ('count', 'min', 'max', 'mean', 'std', 'med'):
+        assert abs(out['tiltcorr']['val_stats'][k] - oo['tiltcorr']['val_stats'][k]) <= 1e-3 * max(1.0, abs(oo['tiltcorr']['val_stats'][k]))
+    # without the correction the residual tilt stays in the difference map
+    plain = dem_align.align(_gds(p, 'ref'), _gds(p, 'src'), verbose=False)
+    d0 = dem_align.diff_stats(_gds(p, 'ref'), plain['src_align'])['stats_filt']['std']
+    d1 = dem_align.diff_stats(_gds(p, 'ref'), out['src_align'])['stats_filt']['std']
+    assert d1 < 0.7 * d0
+
+
+def test_cli_tiltcorr(cuda, tmp_path):
+    import json
+    from demcoreg_b200 import dem_align, rasterio_lite as rio
+    p = _tilted_pair(n=384)
+    rfn, sfn = str(tmp_path / "ref.tif"), str(tmp_path / "src.tif")
+    rio.write_raster(rfn, p['ref'], p['gt'], p['ndv'])
+    rio.write_raster(sfn, p['src'], p['gt'], p['ndv'])
+    info = dem_align.main([rfn, sfn, "-tiltcorr", "-outdir", str(tmp_path / "out")])
+    assert "out_tiltcorr" in info['align_fn']
+    js = json.load(open(info['align_fn'].replace('_align.tif', '_align_stats.json')))
+    assert len(js['tiltcorr']['coeff']) == 4 and js['tiltcorr']['val_stats']['count'] > 0
+    assert js['after_filt']['std'] < js['before_filt']['std']
