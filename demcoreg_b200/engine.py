@@ -43,10 +43,15 @@ class IterBuffers(object):
         self.src_w = torch.empty((h, w), dtype=torch.float32, device="cuda") if keep_warped else None
 
 
-def make_front_args(ref, src, mask_source, max_dz, use_max_dz, slope_lim, keep_warped=False, dst_ndv=0.0, bufs=None):
-    """Plan the common grid (memwarp_multi, res='max', extent='intersection') and fill ``dcr_front_args``."""
+def make_front_args(ref, src, mask_source, max_dz, use_max_dz, slope_lim, keep_warped=False, dst_ndv=0.0, bufs=None,
+                    extent='intersection'):
+    """Plan the common grid (memwarp_multi, res='max', extent='intersection' by default) and fill ``dcr_front_args``."""
     L = _lib.lib()
-    grid, gr, gs = plan_intersection(ref, src, 0.0)
+    if extent == 'intersection':
+        grid, gr, gs = plan_intersection(ref, src, 0.0)
+    else:
+        from .raster import plan_extent
+        grid, gr, gs = plan_extent(ref, src, extent)
     h, w = grid.height, grid.width
     if bufs is None or bufs.h != h or bufs.w != w or (keep_warped and bufs.ref_w is None):
         bufs = IterBuffers(h, w, keep_warped)
@@ -201,11 +206,12 @@ class NuthAligner(object):
         return float(self.st.dx_total), float(self.st.dy_total), float(self.st.dz_total)
 
 
-def front_only(ref, src, mask_source=None, remove_outliers=True, max_dz=100, slope_lim=(0.1, 40), keep_warped=True):
+def front_only(ref, src, mask_source=None, remove_outliers=True, max_dz=100, slope_lim=(0.1, 40), keep_warped=True,
+               extent='intersection'):
     """Only the fused warp + dh + masks + Horn kernel (``dcr_warp_diff_horn``)."""
     torch = _lib.require_cuda()
     L = _lib.lib()
-    a, grid, bufs = make_front_args(ref, src, mask_source, max_dz, remove_outliers, slope_lim, keep_warped)
+    a, grid, bufs = make_front_args(ref, src, mask_source, max_dz, remove_outliers, slope_lim, keep_warped, extent=extent)
     _lib.check(L.dcr_warp_diff_horn(C.byref(a), _stream_ptr(torch)))
     return grid, bufs
 

@@ -152,3 +152,39 @@ def plan_intersection(a, b, res=0.0):
     da, db = a.desc(), b.desc()
     _lib.check(L.dcr_plan_intersection(C.byref(da), C.byref(db), float(res), C.byref(grid), C.byref(ga), C.byref(gb)))
     return grid, ga, gb
+
+
+def plan_extent(a, b, extent="union"):
+    """``memwarp_multi([a, b], res='max', extent=...)`` bookkeeping for the extents other than 'intersection'
+    (``warplib.parse_extent``: 'union' = bounding box, 'first' / 'last' = that raster's extent) -> (Grid, WarpGeom a, b)."""
+    L = _lib.lib()
+    if extent == "intersection":
+        return plan_intersection(a, b, 0.0)
+
+    def ext(r):
+        gt = r.gt
+        return [gt[0], gt[3] + gt[5] * r.RasterYSize, gt[0] + gt[1] * r.RasterXSize, gt[3]]
+    ea, eb = ext(a), ext(b)
+    ra, rb = (a.gt[1] + abs(a.gt[5])) / 2.0, (b.gt[1] + abs(b.gt[5])) / 2.0
+    res = max(ra, rb)
+    if abs(ra - res) > 1e-3 * res or abs(rb - res) > 1e-3 * res:
+        raise _lib.DcrError("input resolutions differ (%.6f, %.6f): the down-sampling warp is out of scope" % (ra, rb))
+    if extent == "union":
+        te = [min(ea[0], eb[0]), min(ea[1], eb[1]), max(ea[2], eb[2]), max(ea[3], eb[3])]
+    elif extent == "first":
+        te = ea
+    elif extent == "last":
+        te = eb
+    else:
+        raise ValueError("extent must be one of intersection, union, first, last")
+    grid = _lib.Grid()
+    for k, v in enumerate((te[0], res, 0.0, te[3], 0.0, -res)):
+        grid.gt[k] = v
+    grid.width = int(round((te[2] - te[0]) / res))     # Python round(): half to even, like pygeotools
+    grid.height = int(round((te[3] - te[1]) / res))
+    ga, gb = _lib.WarpGeom(), _lib.WarpGeom()
+    da, db = a.desc(), b.desc()
+    _lib.check(L.dcr_plan_onto_grid(C.byref(da), C.byref(grid), C.byref(ga)))
+    _lib.check(L.dcr_plan_onto_grid(C.byref(db), C.byref(grid), C.byref(gb)))
+    return grid, ga, gb
+

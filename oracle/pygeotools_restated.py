@@ -222,8 +222,8 @@ def memwarp_multi(ds_list, res="max", extent="intersection", t_srs=None, r="cubi
     resampled with the GDAL cubic kernel onto ``[xmin, res, 0, ymax, 0, -res]`` with
     band nodata ``dst_ndv`` (0 by default, as in pygeotools).
     """
-    if extent != "intersection" or r != "cubic":
-        raise NotImplementedError("oracle restates extent='intersection', r='cubic' only")
+    if extent not in ("intersection", "union", "first", "last") or r != "cubic":
+        raise NotImplementedError("oracle restates extent in intersection/union/first/last, r='cubic' only")
     res_list = [get_res(ds, square=True)[0] for ds in ds_list]
     if isinstance(res, str):
         if res == "max":
@@ -239,7 +239,18 @@ def memwarp_multi(ds_list, res="max", extent="intersection", t_srs=None, r="cubi
     for rr in res_list:
         if abs(rr - tres) > 1e-3 * tres:
             raise NotImplementedError("oracle restates the equal-resolution (no down-sampling) case only")
-    xmin, ymax, W, H, text = intersection_grid(ds_list, tres)
+    if extent == "intersection":
+        xmin, ymax, W, H, text = intersection_grid(ds_list, tres)
+    else:
+        # warplib.parse_extent: 'union' = bounding box of all extents, 'first' / 'last' = that dataset's extent
+        exts = [ds_extent(ds) for ds in ds_list]
+        if extent == "union":
+            text = [min(e[0] for e in exts), min(e[1] for e in exts), max(e[2] for e in exts), max(e[3] for e in exts)]
+        else:
+            text = list(exts[0] if extent == "first" else exts[-1])
+        xmin, ymax = text[0], text[3]
+        W = int(round((text[2] - text[0]) / tres))
+        H = int(round((text[3] - text[1]) / tres))
     out = []
     for ds in ds_list:
         e = ds_extent(ds)

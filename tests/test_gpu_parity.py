@@ -810,3 +810,30 @@ def test_cli_tiltcorr(cuda, tmp_path):
     js = json.load(open(info['align_fn'].replace('_align.tif', '_align_stats.json')))
     assert len(js['tiltcorr']['coeff']) == 4 and js['tiltcorr']['val_stats']['count'] > 0
     assert js['after_filt']['std'] < js['before_filt']['std']
+
+
+@pytest.mark.parametrize("extent", ["union", "first", "last"])
+def test_compute_diff_extents(cuda, extent, tmp_path):
+    """compute_diff -te union / first / last (memwarp_multi extents beyond 'intersection'): output pixels outside a raster
+    are nodata, the rest is the same cubic warp -- bit-identical to the oracle."""
+    from demcoreg_b200 import compute_diff, rasterio_lite as rio
+    from demcoreg_b200.raster import Raster
+    from oracle import pygeotools_restated as pg
+    p = _pair(n=512, nodata_frac=0.02)
+    (ra, rgt), (sa, sgt) = _crop(p, 'ref', 40, 400, 25, 480), _crop(p, 'src', 100, 512, 131, 500)
+    sgt = _shifted_gt(sgt, 47.0, -13.0)
+    diff, gt = compute_diff.compute_diff(Raster(ra, rgt, p['ndv']), Raster(sa, sgt, p['ndv']), extent=extent)
+    rc, sc = pg.memwarp_multi([pg.MemDataset(ra, rgt, p['ndv']), pg.MemDataset(sa, sgt, p['ndv'])], extent=extent)
+    want = pg.ds_getma(sc) - pg.ds_getma(rc)
+    assert diff.shape == want.shape and diff.count() > 0
+    assert np.array_equal(np.ma.getmaskarray(diff), np.ma.getmaskarray(want))
+    assert np.array_equal(diff.compressed(), want.compressed())
+    np.testing.assert_allclose(gt, sc.gt if hasattr(sc, 'gt') else sc.GetGeoTransform(), rtol=0, atol=1e-9)
+    if extent == "union":   # the CLI path
+        f1, f2 = str(tmp_path / "a.tif"), str(tmp_path / "b.tif")
+        rio.write_raster(f1, ra, rgt, p['ndv'])
+        rio.write_raster(f2, sa, sgt, p['ndv'])
+        dst = compute_diff.main([f1, f2, "-te", "union", "-outdir", str(tmp_path)])
+        d = rio.read_array(dst)
+        assert d['array'].shape == want.shape
+        assert np.array_equal(d['array'] == -9999.0, np.ma.getmaskarray(want))
