@@ -1225,7 +1225,9 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
         if ((rc = iter_select(vs, 4, w, n, use_bsel, s))) return rc;
     }
     STAGE_MARK(4);
-    if ((rc = nuth_enqueue_prepared(n, (nch + MU_KCH - 1) / MU_KCH, remove_outliers, w.nw, grid, s, ev ? ev[5] : nullptr,
+    // (dem_align.py:147 calls coreglib.compute_offset_nuth WITHOUT forwarding remove_outliers: the 3-sigma trim of y is
+    //  always on -- its default -- whatever dem_align's own flag says)
+    if ((rc = nuth_enqueue_prepared(n, (nch + MU_KCH - 1) / MU_KCH, 1, w.nw, grid, s, ev ? ev[5] : nullptr,
                                     fast_bins)))
         return rc;
     if (side) {
@@ -1661,7 +1663,7 @@ extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, 
         band_mom_reduce_kernel<<<1, 256, 0, s>>>(w.nw.part, grid, d);
         want(d->mom3, 4, 2);
     } else if (phase == BP_BIN0) {
-        band_moments_final_kernel<<<1, 256, 0, s>>>(d, remove_outliers);
+        band_moments_final_kernel<<<1, 256, 0, s>>>(d, 1);   // trim of y always on (dem_align.py:147)
         bin_hist_kernel<0><<<grid, 256, 0, s>>>(w.nw.y, w.nw.bin, n, &d->nuth, w.nw.ghist);
         want(w.nw.ghist, (int64_t)2 * NB * 2048, 0);
         want(d->nuth.bin_count, NB, 1);

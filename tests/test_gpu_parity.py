@@ -837,3 +837,21 @@ def test_compute_diff_extents(cuda, extent, tmp_path):
         d = rio.read_array(dst)
         assert d['array'].shape == want.shape
         assert np.array_equal(d['array'] == -9999.0, np.ma.getmaskarray(want))
+
+
+def test_iteration_without_outlier_removal(cuda):
+    """compute_offset(remove_outliers=False) (dem_align.py:91): no max_dz / MAD filter on dh and no 3-sigma trim of y."""
+    from demcoreg_b200 import engine, _lib
+    from oracle import dem_align as oda
+    p = _pair(n=768, res=30.0, nodata_frac=0.01, outlier_frac=0.01)
+    gt_s = _shifted_gt(p['gt'], 3.4, -1.8)
+    res, grid, bufs = engine.nuth_iteration(_gds(p, 'ref'), _gds(p, 'src', gt_s), None, remove_outliers=False)
+    det = {}
+    odx, ody, odz, omask, _ = oda.compute_offset(_ods(p, 'ref'), _ods(p, 'src', gt_s), remove_outliers=False, details=det)
+    gmask = ((bufs.maskbits & _lib.M_DIFF) != 0).cpu().numpy()
+    assert np.array_equal(gmask, omask)
+    assert res.count_mad == res.count_maxdz == res.count_base      # nothing filtered
+    _compare_iteration(res, det, odx, ody, odz)
+    # and it differs from the filtered run (the 1 % injected outliers are kept)
+    res2, _, _ = engine.nuth_iteration(_gds(p, 'ref'), _gds(p, 'src', gt_s), None, remove_outliers=True)
+    assert res2.count_final < res.count_final
