@@ -855,3 +855,45 @@ def test_iteration_without_outlier_removal(cuda):
     # and it differs from the filtered run (the 1 % injected outliers are kept)
     res2, _, _ = engine.nuth_iteration(_gds(p, 'ref'), _gds(p, 'src', gt_s), None, remove_outliers=True)
     assert res2.count_final < res.count_final
+
+
+@pytest.mark.parametrize("case", ["max_dz_5", "slope_lim_1_20", "mask_other_grid", "different_ndv"])
+def test_iteration_parameter_corners(cuda, case):
+    from demcoreg_b200 import engine, _lib
+    from demcoreg_b200.raster import Raster, MaskSource
+    from oracle import dem_align as oda, pygeotools_restated as pg
+    p = _pair(n=768, res=30.0, nodata_frac=0.01, static_mask_frac=0.25, outlier_frac=0.01)
+    gt_s = _shifted_gt(p['gt'], -7.7, 4.4)
+    kw_g, kw_o = {}, {}
+    ref_g, src_g = _gds(p, 'ref'), _gds(p, 'src', gt_s)
+    ref_o, src_o = _ods(p, 'ref'), _ods(p, 'src', gt_s)
+    ms_g, ms_o = MaskSource(p['mask'], p['gt']), oda.MaskSource(p['mask'], p['gt'])
+    if case == "max_dz_5":
+        kw_g = dict(max_dz=5); kw_o = dict(max_dz=5)
+    elif case == "slope_lim_1_20":
+        kw_g = dict(slope_lim=(1.0, 20.0)); kw_o = dict(slope_lim=(1.0, 20.0))
+    elif case == "mask_other_grid":
+        # the world-fixed mask raster covers another extent, offset by a non-integer number of pixels
+        mk, mgt = _crop(p, 'mask', 30, 700, 55, 768)
+        mgt = _shifted_gt(mgt, 11.0, -4.0)
+        ms_g, ms_o = MaskSource(mk, mgt), oda.MaskSource(mk, mgt)
+    else:
+        ref2 = p['ref'].copy(); ref2[ref2 == p['ndv']] = np.float32(-32768.0)
+        ref_g, ref_o = Raster(ref2, p['gt'], -32768.0), pg.MemDataset(ref2, p['gt'], -32768.0)
+    res, grid, bufs = engine.nuth_iteration(ref_g, src_g, ms_g, **kw_g)
+    det = {}
+    odx, ody, odz, omask, _ = oda.compute_offset(ref_o, src_o, mask_source=ms_o, details=det, **kw_o)
+    gmask = ((bufs.maskbits & _lib.M_DIFF) != 0).cpu().numpy()
+    assert np.array_equal(gmask, omask)
+    _compare_iteration(res, det, odx, ody, odz)
+
+
+def test_max_offset_exit(cuda):
+    from demcoreg_b200 import dem_align
+    p = _pair(n=512, res=30.0)
+    with pytest.raises(SystemExit, match="Total offset exceeded specified max_offset"):
+        dem_align.align(_gds(p, 'ref'), _gds(p, 'src'), max_offset=1.0, verbose=False)
+    with pytest.raises(SystemExit, match="Total offset exceeded specified max_offset"):
+        dem_align.align(_gds(p, 'ref'), _gds(p, 'src'), max_offset=1.0, verbose=False, records=[])
+    out = dem_align.align(_gds(p, 'ref'), _gds(p, 'src'), max_iter=2, tol=0.0, verbose=False)
+    assert out['n_iter'] == 2
