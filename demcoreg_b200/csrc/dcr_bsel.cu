@@ -2,17 +2,18 @@
 //
 // The radix select of dcr_select.cu needs three histogram passes over all the data, each limited by
 // shared-memory atomics.  Here ONE streaming pass suffices:
-//   1. bsel_sample_kernel  - one CTA gathers S = 8192 strided samples, sorts them (bitonic, shared memory)
-//                            and takes the keys at sample ranks r -+ 5 sigma as a bracket [klo, khi] that
-//                            contains the wanted order statistic(s) with overwhelming probability.
-//   2. bsel_main_kernel    - bandwidth-bound pass: counts the elements below klo in registers, appends the
-//                            few per cent inside the bracket to a candidate buffer and histograms them
-//                            (2048 linear bins of the bracket) -- atomics only for those few per cent.
-//   3. bsel_find_kernel    - locates the histogram bin(s) holding the exact global rank(s) and VERIFIES that
-//                            the rank really lies inside the bracket (exactness does not depend on luck:
-//                            a miss, an overflow or heavy ties raise `fallback`, and the caller reruns the
-//                            3-pass radix select).
-//   4. bsel_refine_kernel  - radix-refines the remaining <= 21 key bits over the candidate buffer only (11 bits per
+//   1. bsel_sample_kernel  - one CTA gathers S = 8192 stratified, hash-jittered samples and localises the keys at the
+//                            sample ranks r -+ 5 sigma by three rounds of a 1024-bin shared-memory histogram over a
+//                            shrinking key range: a bracket [klo, khi] that contains the wanted order statistic(s)
+//                            with overwhelming probability (n <= 8192: the sample is the input, sorted, exact).
+//   2. bsel_main_kernel    - the streaming pass (BselCollector, dcr_bsel_collect.cuh): counts the elements below klo
+//                            in registers, parks the few per cent inside the bracket in thread-private shared-memory
+//                            slots, drains them per warp into a CTA staging buffer + bracket histogram (2048 linear
+//                            bins), one global reservation per CTA.  Its LAST CTA locates the histogram bin(s) holding
+//                            the exact global rank(s) and VERIFIES that the rank really lies inside the bracket
+//                            (exactness does not depend on luck: a miss, an overflow or heavy ties raise `fallback`,
+//                            and the caller reruns the 3-pass radix select).
+//   3. bsel_refine_kernel  - radix-refines the remaining <= 21 key bits over the candidate buffer only (11 bits per
 //                            launch, last-CTA-done finalisation), then applies numpy's linear interpolation.
 // Same semantics as dcr_sel_enqueue (numpy.percentile, linear, exact float64 rank).
 #include <string.h>
