@@ -45,3 +45,68 @@ def align_batch(pairs, align_fn, group=None):
 
 def env_rank_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def stream_pairs(host_pairs, device=None):
+    """Double-buffered upload of host-resident pairs: yields ``(ref, src, mask_source)`` device objects for pair ``k`` while
+    pair ``k+1`` is being copied on a separate CUDA stream, so that a batch streaming through one GPU is bound by
+    max(PCIe, kernels) instead of their sum.
+
+    ``host_pairs``: sequence of dicts ``ref, src`` (float32 arrays or PINNED torch tensors), ``ref_gt, src_gt, ndv`` and
+    optionally ``mask`` (uint8) + ``mask_gt``.  All pairs must share the raster shapes (two device buffer sets are reused).
+    The consumer must finish its GPU work on the yielded rasters (``align`` / ``nuth_iteration`` synchronise on their
+    result) before advancing the generator."""
+    import numpy as np
+    import torch
+    from .raster import Raster, MaskSource
+
+    def pinned(a, dtype):
+        if isinstance(a, np.ndarray):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).pin_memory()
+        return a
+
+    host_pairs = list(host_pairs)
+    if not host_pairs:
+        return
+    first = host_pairs[0]
+    has_mask = first.get('mask') is not None
+    sets = []
+    for _ in range(2):
+        r = Raster(torch.empty(first['ref'].shape, dtype=torch.float32, device=device or "cuda"), first['ref_gt'], first['ndv'])
+        s_ = Raster(torch.empty(first['src'].shape, dtype=torch.float32, device=device or "cuda"), first['src_gt'], first['ndv'])
+        m = MaskSource(torch.empty(first['mask'].shape, dtype=torch.uint8, device=device or "cuda"), first['mask_gt']) if has_mask else None
+        sets.append((r, s_, m))
+    cs = torch.cuda.Stream()
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    free = [torch.cuda.Event(), torch.cuda.Event()]
+    for ev in free:
+        ev.record()
+
+    def upload(k):
+        b = k & 1
+        hp = host_pairs[k]
+        r, s_, m = sets[b]
+        with torch.cuda.stream(cs):
+            cs.wait_event(free[b])
+            r.data.copy_(pinned(hp['ref'], np.float32), non_blocking=True)
+            s_.data.copy_(pinned(hp['src'], np.float32), non_blocking=True)
+            if m is not None:
+                m.data.copy_(pinned(hp['mask'], np.uint8), non_blocking=True)
+            ready[b].record(cs)
+        r.gt = tuple(float(g) for g in hp['ref_gt'])
+        s_.gt = tuple(float(g) for g in hp['src_gt'])
+        r.ndv = s_.ndv = hp['ndv']
+        s_.pending_dz = []
+        if m is not None:
+            m.gt = tuple(float(g) for g in hp['mask_gt'])
+
+    upload(0)
+    for k in range(len(host_pairs)):
+        b = k & 1
+        torch.cuda.current_stream().wait_event(ready[b])
+        # NB the next upload overwrites the OTHER buffer set, whose consumer finished before this generator was advanced
+        if k + 1 < len(host_pairs):
+            upload(k + 1)
+        yield sets[b]
+        free[b].record()
+

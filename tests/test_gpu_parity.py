@@ -897,3 +897,21 @@ def test_max_offset_exit(cuda):
         dem_align.align(_gds(p, 'ref'), _gds(p, 'src'), max_offset=1.0, verbose=False, records=[])
     out = dem_align.align(_gds(p, 'ref'), _gds(p, 'src'), max_iter=2, tol=0.0, verbose=False)
     assert out['n_iter'] == 2
+
+
+def test_stream_pairs_prefetch(cuda):
+    """batch.stream_pairs: double-buffered uploads give the same iteration results as direct uploads, pair by pair."""
+    from demcoreg_b200 import batch, engine
+    from demcoreg_b200.raster import MaskSource
+    pairs, want = [], []
+    for k in range(3):
+        p = _pair(n=384, res=30.0, seed=20260010 + 7 * k, static_mask_frac=0.2)
+        gt_s = _shifted_gt(p['gt'], 2.0 * k - 1.5, 0.7 * k)
+        pairs.append(dict(ref=p['ref'], src=p['src'], mask=p['mask'], ref_gt=p['gt'], src_gt=gt_s, mask_gt=p['gt'], ndv=p['ndv']))
+        r, _, _ = engine.nuth_iteration(_gds(p, 'ref'), _gds(p, 'src', gt_s), MaskSource(p['mask'], p['gt']))
+        want.append((r.dx, r.dy, r.dz, r.count_final))
+    got = []
+    for ref, src, ms in batch.stream_pairs(pairs):
+        r, _, _ = engine.nuth_iteration(ref, src, ms)
+        got.append((r.dx, r.dy, r.dz, r.count_final))
+    assert got == want
