@@ -37,5 +37,30 @@ def nuth_iter(n=128, name="nuth_iter_128.npz"):
     print(name, "shift", dx, dy, dz, "bins>=9:", int((det['nuth']['bin_count'] >= 9).sum()))
 
 
+def horn_and_loop(n=96, name="horn_loop_96.npz"):
+    """Horn slope / aspect of a raster with voids, and the whole loop with -tiltcorr on a tilted pair."""
+    p = synth.make_pair(n=n, res=30.0, seed=20260888, nodata_frac=0.02, median_slope=14.0)
+    gt = p['gt']
+    ds = pg.MemDataset(p['src'], gt, p['ndv'])
+    slope = pg.gdaldem_mem_ds(ds, 'slope', returnma=True)
+    aspect = pg.gdaldem_mem_ds(ds, 'aspect', returnma=True)
+    jj, ii = np.meshgrid(np.arange(n), np.arange(n))
+    tilt = (0.4 + 1.0 * (jj / n - 0.5) - 0.6 * (ii / n - 0.5)).astype(np.float32)
+    src_t = p['src'].copy()
+    v = src_t != p['ndv']
+    src_t[v] += tilt[v]
+    out = oda.align(pg.MemDataset(p['ref'], gt, p['ndv']), pg.MemDataset(src_t, gt, p['ndv']), final_stats=False,
+                    tiltcorr=True, polyorder=1)
+    np.savez_compressed(os.path.join(HERE, name), ref=p['ref'], src=p['src'], src_tilted=src_t, gt=np.array(gt),
+                        slope=slope.filled(-9999.0).astype(np.float32), aspect=aspect.filled(-9999.0).astype(np.float32),
+                        loop_shift=np.array([out['dx'], out['dy'], out['dz']], dtype=np.float64),
+                        loop_n_iter=np.int64(out['n_iter']),
+                        tilt_coeff_norm=np.asarray(out['tiltcorr']['coeff'].coeff_norm, dtype=np.float64),
+                        tilt_vals=np.asarray(out['tiltcorr']['vals'], dtype=np.float64),
+                        src_align=out['src_align'].array, src_align_gt=np.array(out['src_align'].gt))
+    print(name, "loop", out['dx'], out['dy'], out['dz'], out['n_iter'], "tilt ptp", float(np.ptp(out['tiltcorr']['vals'])))
+
+
 if __name__ == "__main__":
     nuth_iter()
+    horn_and_loop()

@@ -915,3 +915,25 @@ def test_stream_pairs_prefetch(cuda):
         r, _, _ = engine.nuth_iteration(ref, src, ms)
         got.append((r.dx, r.dy, r.dz, r.count_final))
     assert got == want
+
+
+def test_gpu_against_golden_horn_and_tiltcorr_loop(cuda):
+    """The CUDA path against the second committed fixture: standalone Horn kernel, loop with -tiltcorr."""
+    import os
+    from demcoreg_b200 import engine, dem_align
+    from demcoreg_b200.raster import Raster
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "horn_loop_96.npz"))
+    gt = tuple(g['gt'])
+    s, a = engine.horn(Raster(g['src'], gt, -9999.0), True, True)
+    _check_raster(s.cpu().numpy(), g['slope'], -9999.0, "slope")
+    _check_raster(a.cpu().numpy(), g['aspect'], -9999.0, "aspect")
+    assert np.array_equal(np.floor(a.cpu().numpy()), np.floor(g['aspect']))
+    out = dem_align.align(Raster(g['ref'], gt, -9999.0), Raster(g['src_tilted'], gt, -9999.0), verbose=False, tiltcorr=True)
+    assert out['n_iter'] == int(g['loop_n_iter'])
+    np.testing.assert_allclose([out['dx'], out['dy'], out['dz']], g['loop_shift'], rtol=0, atol=OFFTOL)
+    m = out['tiltcorr']['model']
+    np.testing.assert_allclose([m.coeff_norm[k] for k in range(4)], g['tilt_coeff_norm'], rtol=0, atol=1e-4)
+    got, want = out['src_align'].numpy(), g['src_align']
+    valid = want != np.float32(-9999.0)
+    assert np.array_equal(got != np.float32(-9999.0), valid)
+    assert np.abs(got[valid].astype(np.float64) - want[valid]).max() < 2e-3
