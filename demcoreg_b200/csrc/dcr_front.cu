@@ -282,12 +282,13 @@ __device__ __forceinline__ float atan01(float t) {
 // limit, aspect within 3e-4 degrees of an integer degree (the 1-degree bin edges) -- is recomputed with
 // the FP64 formulation above.  Returns false when any input is NaN; *exact = true -> caller must call horn().
 __device__ __forceinline__ bool horn_fast(float w0, float w1, float w2, float w3, float w4, float w5, float w6,
-                                          float w7, float w8, float inv8ew, float inv8ns, float slope_mid,
+                                          float w7, float w8, float c, float d, float inv8ew, float inv8ns, float slope_mid,
                                           float slope_half, float slope_tol, float* slope, float* aspect, bool* exact) {
+    // c = (w6 + w7 + w7 + w8), d = (w0 + w1 + w1 + w2): the row sums slide down the column with the window (the top row
+    // of this window was the bottom row two pixels ago), so the caller carries them instead of re-adding them
+    (void)w1; (void)w7;
     const float a = (w0 + w3 + w3 + w6);
     const float b = (w2 + w5 + w5 + w8);
-    const float c = (w6 + w7 + w7 + w8);
-    const float d = (w0 + w1 + w1 + w2);
     const float dxs = a - b;  // slope numerator; aspect uses b - a = -dxs exactly
     const float dyf = c - d;
     // any NaN (nodata) among the 8 neighbours poisons dxs or dyf; the centre is tested separately
@@ -788,6 +789,7 @@ __global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ F
         q += F_SW_C;
         w3 = q[0]; w4 = q[1]; w5 = q[2];
         q += F_SW_C;
+        float rs0 = (w0 + w1 + w1 + w2), rs1 = (w3 + w4 + w4 + w5);   // row sums of the window's top / middle row
         // hoisted invariants: stored rows, interior rows [r_lo, r_hi) of this thread (borders are nodata), offset
         const bool col_ok = j < p.w;
         const bool col_in = j > 0 && j < p.w - 1;
@@ -800,13 +802,14 @@ __global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ F
         for (int rr = 0; rr < F_ROWS_PER_THREAD; ++rr) {
             w6 = q[0]; w7 = q[1]; w8 = q[2];
             q += F_SW_C;
+            const float rs2 = (w6 + w7 + w7 + w8);
             if (rr < n_store) {
                 float sl = DCR_GDALDEM_NDV, as = DCR_GDALDEM_NDV;
                 unsigned bits = DCR_M_SLOPE | DCR_M_ASPECT;
                 if (rr >= r_lo && rr < r_hi) {
                     float sv, av;
                     bool ex;
-                    if (horn_fast(w0, w1, w2, w3, w4, w5, w6, w7, w8, p.inv8ew, p.inv8ns, p.slope_mid, p.slope_half,
+                    if (horn_fast(w0, w1, w2, w3, w4, w5, w6, w7, w8, rs2, rs0, p.inv8ew, p.inv8ns, p.slope_mid, p.slope_half,
                                   p.slope_tol, &sv, &av, &ex)) {
                         if (ex) horn(w0, w1, w2, w3, w4, w5, w6, w7, w8, p.ewres, p.nsres, true, true, &sv, &av);
                         sl = sv;
@@ -830,6 +833,7 @@ __global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ F
             o += p.w;
             w0 = w3; w1 = w4; w2 = w5;
             w3 = w6; w4 = w7; w5 = w8;
+            rs0 = rs1; rs1 = rs2;
         }
     }
     // block-level counter reduction -> 3 global integer atomics per CTA
