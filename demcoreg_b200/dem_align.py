@@ -167,6 +167,9 @@ def align(ref_dem_ds, src_dem_ds, mode='nuth', mask_source=None, tol=0.02, max_o
     import contextlib
     import io
     src_dem_ds_align = src_dem_ds.copy()
+    # dem_align.py:294-299: both rasters are clipped / resampled ONCE to their intersection before the loop (rasters that
+    # already share extent and lattice pass through untouched); the loop then works on these
+    ref_dem_ds, src_dem_ds_align = engine.memwarp_multi([ref_dem_ds, src_dem_ds_align])
     if mode == 'nuth' and records is None:
         return _align_nuth_native(ref_dem_ds, src_dem_ds_align, mask_source, tol, max_offset, max_dz, slope_lim, max_iter,
                                   verbose, tiltcorr, polyorder)
@@ -211,7 +214,7 @@ def align(ref_dem_ds, src_dem_ds, mode='nuth', mask_source=None, tol=0.02, max_o
             if n > max_iter or dm < tol:
                 break
     return dict(dx=float(dx_total), dy=float(dy_total), dz=float(dz_total), n_iter=n - 1, iters=iters,
-                src_align=src_dem_ds_align)
+                src_align=src_dem_ds_align, ref=ref_dem_ds)
 
 
 def _align_nuth_native(ref_dem_ds, src_dem_ds_align, mask_source, tol, max_offset, max_dz, slope_lim, max_iter, verbose,
@@ -274,7 +277,7 @@ def _align_nuth_native(ref_dem_ds, src_dem_ds_align, mask_source, tol, max_offse
         sys.exit("Total offset exceeded specified max_offset (%0.2f m). Consider increasing -max_offset argument" % max_offset)
     al.finish()
     dxt, dyt, dzt = al.totals
-    out = dict(dx=dxt, dy=dyt, dz=dzt, n_iter=len(iters), iters=iters, src_align=src_dem_ds_align)
+    out = dict(dx=dxt, dy=dyt, dz=dzt, n_iter=len(iters), iters=iters, src_align=src_dem_ds_align, ref=ref_dem_ds)
     if tilt is not None:
         out['tiltcorr'] = tilt
     return out
@@ -352,8 +355,8 @@ def main(argv=None):
     rio.write_raster(align_fn, sa.numpy(), sa.gt, sa.ndv, sa.proj)
     dm_total = float(np.sqrt(dx_total ** 2 + dy_total ** 2 + dz_total ** 2))
     # final elevation difference (dem_align.py:366-392, from the loop's dataset) and the original one (dem_align.py:506-530)
-    after = diff_stats(ref, out['src_align'], mask_source, args.max_dz)
-    before = diff_stats(ref, src, mask_source, args.max_dz)
+    after = diff_stats(out['ref'], out['src_align'], mask_source, args.max_dz)
+    before = diff_stats(out['ref'], src, mask_source, args.max_dz)
     ndv_out = -9999.0
     rio.write_raster(outprefix + xyz_shift_str_cum_fn + '_align_diff.tif', after['diff'].filled(ndv_out), after['gt'], ndv_out)
     rio.write_raster(outprefix + xyz_shift_str_cum_fn + '_align_diff_filt.tif', after['diff_filt'].filled(ndv_out),

@@ -309,6 +309,20 @@ def warp_cubic(src, grid, geom, dst_ndv=0.0):
     return Raster(dst, tuple(grid.gt), dst_ndv, src.proj)
 
 
+def memwarp_multi(ds_list, extent='intersection'):
+    """``warplib.memwarp_multi([a, b], res=..., extent=..., r='cubic')`` for two rasters of equal resolution: a raster whose
+    extent already equals the target grid is returned unchanged (same object); the other one is resampled with the GDAL
+    cubic kernel onto the grid, band nodata 0 (pygeotools' ``dst_ndv``).  Reference ``dem_align.py:294-299`` does this
+    once before the loop (both rasters clipped to their intersection)."""
+    from .raster import plan_extent
+    a, b = ds_list
+    grid, ga, gb = plan_extent(a, b, extent)
+    out = []
+    for ds, g in ((a, ga), (b, gb)):
+        out.append(ds if g.identity else warp_cubic(ds, grid, g, 0.0))
+    return out
+
+
 def horn(ds, want_slope=True, want_aspect=True):
     """Standalone Horn slope/aspect (``dcr_horn_slope_aspect``) -> (slope tensor|None, aspect tensor|None)."""
     torch = _lib.require_cuda()

@@ -937,3 +937,25 @@ def test_gpu_against_golden_horn_and_tiltcorr_loop(cuda):
     valid = want != np.float32(-9999.0)
     assert np.array_equal(got != np.float32(-9999.0), valid)
     assert np.abs(got[valid].astype(np.float64) - want[valid]).max() < 2e-3
+
+
+@pytest.mark.parametrize("case", ["same_lattice", "fractional_lattice"])
+def test_align_loop_ragged_inputs(cuda, case):
+    """The whole loop on rasters of different extents: like the reference (dem_align.py:294-299) both are first clipped --
+    or, when their pixel lattices differ by a fraction of a pixel, cubic-resampled -- onto their intersection."""
+    from demcoreg_b200 import dem_align
+    from demcoreg_b200.raster import Raster
+    from oracle import dem_align as oda, pygeotools_restated as pg
+    p = _pair(n=768, res=30.0, nodata_frac=0.01)
+    (ra, rgt), (sa, sgt) = _crop(p, 'ref', 30, 700, 20, 768), _crop(p, 'src', 0, 640, 100, 740)
+    if case == "fractional_lattice":
+        sgt = _shifted_gt(sgt, 11.3, -7.9)       # the source grid sits between the reference's pixels
+    out = dem_align.align(Raster(ra, rgt, p['ndv']), Raster(sa, sgt, p['ndv']), verbose=False)
+    oo = oda.align(pg.MemDataset(ra, rgt, p['ndv']), pg.MemDataset(sa, sgt, p['ndv']), final_stats=False)
+    assert out['n_iter'] == oo['n_iter']
+    for k in ('dx', 'dy', 'dz'):
+        assert abs(out[k] - oo[k]) < OFFTOL, (k, out[k], oo[k])
+    assert out['src_align'].numpy().shape == oo['src_align'].array.shape
+    assert np.array_equal(out['src_align'].numpy(), oo['src_align'].array)
+    np.testing.assert_allclose(out['src_align'].gt, oo['src_align'].gt, rtol=0, atol=OFFTOL)   # origin + cumulative shift
+    assert np.array_equal(out['ref'].numpy(), oo['ref'].array)
