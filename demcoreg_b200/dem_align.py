@@ -362,6 +362,24 @@ def main(argv=None):
     rio.write_raster(outprefix + xyz_shift_str_cum_fn + '_align_diff_filt.tif', after['diff_filt'].filled(ndv_out),
                      after['gt'], ndv_out)
     rio.write_raster(outprefix + '_orig_diff.tif', before['diff'].filled(ndv_out), before['gt'], ndv_out)
+    # dem_align.py:488-499: the aligned source masked so that only the pixels of the filtered difference map survive -- the
+    # filtered difference (nodata ndv_out) is cubic-warped onto the full source grid (band nodata 0) and lends its mask
+    print("Applying filter to shiftec src_dem")
+    dfr = Raster(after['diff_filt'].filled(ndv_out).astype(np.float32), after['gt'], ndv_out)
+    g_full = _lib.Grid()
+    for k in range(6):
+        g_full.gt[k] = sa.gt[k]
+    g_full.width, g_full.height = sa.RasterXSize, sa.RasterYSize
+    geom = _lib.WarpGeom()
+    import ctypes as _C
+    dd = dfr.desc()
+    _lib.check(_lib.lib().dcr_plan_onto_grid(_C.byref(dd), _C.byref(g_full), _C.byref(geom)))
+    dfw = engine.warp_cubic(dfr, g_full, geom, 0.0).numpy()
+    keep = ~np.ma.getmaskarray(np.ma.masked_values(dfw, 0.0))
+    sa_arr = sa.numpy()
+    fill = sa.ndv if sa.ndv is not None else ndv_out
+    rio.write_raster(outprefix + xyz_shift_str_cum_fn + '_align_filt.tif', np.where(keep, sa_arr, np.float32(fill)), sa.gt,
+                     fill, sa.proj)
     res_ref = float((ref.gt[1] + abs(ref.gt[5])) / 2.0)
     res_src = float((src.gt[1] + abs(src.gt[5])) / 2.0)
     g = after['gt']

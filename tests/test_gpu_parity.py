@@ -491,7 +491,7 @@ def test_cli_end_to_end(cuda, tmp_path):
     """dem_align.main on GeoTIFF files: same cumulative shift as the oracle loop, output raster + json written."""
     import json
     from demcoreg_b200 import dem_align, rasterio_lite as rio
-    from oracle import dem_align as oda
+    from oracle import dem_align as oda, pygeotools_restated as pg
     p = _pair(n=512)
     rfn, sfn = str(tmp_path / "ref.tif"), str(tmp_path / "src.tif")
     rio.write_raster(rfn, p['ref'], p['gt'], p['ndv'])
@@ -520,6 +520,15 @@ def test_cli_end_to_end(cuda, tmp_path):
     d = rio.read_array(info['align_fn'].replace('_align.tif', '_align_diff.tif'))
     dm = np.ma.masked_values(d['array'], -9999.0)
     assert dm.count() == oo['diff_align_stats']['count']
+    # *_align_filt.tif (dem_align.py:488-499): the aligned source, masked by the cubic-warped filtered difference map
+    f = rio.read_array(info['align_fn'].replace('_align.tif', '_align_filt.tif'))
+    dfilt = pg.MemDataset(oo['diff_align_filt'].filled(-9999.0).astype(np.float32), tuple(d['gt']), -9999.0)
+    res_px = want.gt[1]
+    geom = pg.warp_geometry(dfilt, want.gt[0], want.gt[3], res_px)
+    dfw = pg.gdal_cubic_warp(dfilt.array, -9999.0, geom, want.array.shape[0], want.array.shape[1], dst_ndv=0.0)
+    keep = ~np.ma.getmaskarray(np.ma.masked_values(dfw, 0.0))
+    assert np.array_equal(f['array'] != np.float32(-9999.0), keep & (want.array != np.float32(-9999.0)))
+    assert np.array_equal(f['array'][keep], want.array[keep])
 
 
 def test_compute_diff(cuda, tmp_path):
