@@ -142,15 +142,25 @@ struct BselCollector {
         }
         base = __shfl_sync(0xffffffffu, base, 31);
         gb = __shfl_sync(0xffffffffu, gb, 31);
-        const unsigned ov0 = base > STAGE ? base : STAGE;   // first position that overflows
         unsigned pos = base + inc - c;
-        for (unsigned k = 0; k < cmax; ++k) {
-            if (k < c) {
-                const unsigned key = dcr_f2key(mine[k * BSC_THREADS] + 0.0f);  // -0 -> +0
-                if (pos < STAGE) sh->buf[pos] = key;
-                else if (gb + (pos - ov0) < cap) cand[gb + (pos - ov0)] = key;
-                ++pos;
-                atomicAdd(&sh->h[(key - klo) >> shift], 1u);
+        if (base + wt <= STAGE) {   // warp-uniform common case: everything fits the staging buffer
+            for (unsigned k = 0; k < cmax; ++k) {
+                if (k < c) {
+                    const unsigned key = dcr_f2key(mine[k * BSC_THREADS] + 0.0f);  // -0 -> +0
+                    sh->buf[pos++] = key;
+                    atomicAdd(&sh->h[(key - klo) >> shift], 1u);
+                }
+            }
+        } else {
+            const unsigned ov0 = base > STAGE ? base : STAGE;   // first position that overflows
+            for (unsigned k = 0; k < cmax; ++k) {
+                if (k < c) {
+                    const unsigned key = dcr_f2key(mine[k * BSC_THREADS] + 0.0f);
+                    if (pos < STAGE) sh->buf[pos] = key;
+                    else if (gb + (pos - ov0) < cap) cand[gb + (pos - ov0)] = key;
+                    ++pos;
+                    atomicAdd(&sh->h[(key - klo) >> shift], 1u);
+                }
             }
         }
         c = 0;
