@@ -139,7 +139,7 @@ def run_reference(args):
     if rank != 0:
         return
     import multiprocessing as mp
-    cores = min(os.cpu_count() or 1, 32)
+    cores = min(len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1), 128)
     nrep = args.warmup + args.steps
     crop = min(args.size, 2048 if nrep <= 16 else 1024)
     with mp.get_context("spawn").Pool(cores) as pool:
