@@ -8,7 +8,15 @@ apply_z_shift (coreglib.py:14-55), with device-resident inputs and (dx, dy, dz) 
 the end of every step.  Workload at N=1: BASELINE.json configs[1] (8192x8192 pair at 8 m with a
 stable-surface mask).  N>1: one independent pair per GPU (pair-sharded, no collective), weak scaling.
 
+The same JSON line carries three more measured objects (BASELINE.json configs[2..4]):
+  "config3"  N=1: compute_offset_ncc / compute_offset_sad, +-16 px window on a 4096^2 pair (time, GFLOP/s, bytes);
+  "batch"    every N: 256 DISTINCT host-resident 4096^2 pairs sharded p % N over the ranks, each streamed through
+             batch.align_stream (pinned upload overlapped with the previous pair's loop, dem_align to convergence,
+             final statistics pass): pairs/s WITH the uploads, next to a measured all-ranks H2D bandwidth;
+  "band"     N>1: ONE 32768^2 pair at 2 m split into row bands (NCCL halo exchange + histogram all-reduces).
+
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size 8192]
+                    [--no-config3] [--no-batch] [--no-band] [--batch-pairs 256] [--band-size 32768]
 """
 import argparse
 import json
@@ -53,9 +61,9 @@ def peaks():
 def make_workload(size, res, rank=0, cfg_id=2):
     from demcoreg_b200 import synth
     seed = 20260000 + 10 * cfg_id + 1000 * rank
-    period = min(size, 2048)
+    period = min(size, 8192)      # an 8192^2 period; nothing repeats at the bench size
     return synth.make_pair(n=size, res=res, seed=seed, period=period, static_mask_frac=0.3, nodata_frac=0.01,
-                           outlier_frac=0.001)
+                           outlier_frac=0.001, mask_tile=period)
 
 
 class ClockSampler(object):
@@ -250,6 +258,223 @@ def run_band(args):
         dist.destroy_process_group()
 
 
+
+def bench_config3(args, torch):
+    """BASELINE configs[2]: compute_offset_ncc and compute_offset_sad with a +-16 px window on a 4096^2 pair
+    (device-resident masked rasters in, (2p+1)^2 float64 map + sub-pixel offset on the host out).  N = 1, rank 0."""
+    from demcoreg_b200 import coreglib, engine, synth
+    n, res, p = 4096, 8.0, 16
+    pr = synth.make_pair_torch(n=n, res=res, seed=20260030, shift=(5.3 * res, -3.6 * res, 0.5), noise=0.3, outlier_frac=0.0,
+                               static_mask_frac=0.05, nodata_frac=0.0)
+    m = pr['mask']
+    d1, d2 = pr['ref'], pr['src']
+    J = 2 * p + 1
+    kh = n - 2 * p
+    g = torch.Generator(device="cuda")
+    g.manual_seed(9)
+    rn = torch.randn((n, n), generator=g, device="cuda")
+    kn = torch.randn((kh, kh), generator=g, device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, out
+    ncc_ms, (mn, _) = timed(lambda: engine.ncc_corr(d1, m, d2, m, p, rn, kn), 3)
+    info = {}
+    sad_ms, ms_ = timed(lambda: engine.sad_search(d1, m, d2, m, p, info=info), 3)
+    peak, _src = peaks()
+    mneg = -ms_
+    so = np.array(coreglib.find_subpixel_peak_position(mneg, 'parabolic')) - p
+    sn = np.array(coreglib.find_subpixel_peak_position(mn, 'parabolic')) - p
+    flops = 2.0 * J * J * kh * kh
+    ndiff = float(J * J) * kh * kh
+    return {"workload": "compute_offset_ncc / compute_offset_sad, pad=(16,16), synthetic 4096x4096 pair at 8 m displaced by "
+                        "(5.3, -3.6) px, 5 % masked, device-resident",
+            "ncc": {"ms": ncc_ms, "gflops": flops / (ncc_ms * 1e-3) / 1e9, "flop": flops,
+                    "fp32_fma_peak_frac": flops / (ncc_ms * 1e-3) / (148 * 128 * 2 * 1.965e9),
+                    "hbm_frac_at_8_B_per_px": 8.0 * n * n / (ncc_ms * 1e-3) / 1e9 / peak,
+                    "sp_offset_px": [float(sn[0]), float(sn[1])],
+                    "note": "direct shared-memory correlation, FP32 FMA over one tile row, FP64 beyond; includes the z-score passes"},
+            "sad": {"ms": sad_ms, "gdiff_per_s": ndiff / (sad_ms * 1e-3) / 1e9,
+                    "hbm_frac_at_24_B_per_px": 24.0 * n * n / (sad_ms * 1e-3) / 1e9 / peak,
+                    "stages_ms": info.get('stage_ms'), "offsets_per_offset_path": info.get('n_per_offset'),
+                    "sp_offset_px": [float(so[0]), float(so[1])],
+                    "note": "batched over all 1089 offsets: sample brackets, 2 passes of 1.8e10 differences out of shared "
+                            "memory, exact P25/P75 per offset"}}
+
+
+def bench_h2d(torch, world, dist, nbytes=1 << 30, reps=6):
+    """All ranks copy a pinned 1 GiB buffer host->device at the same time: the measured ceiling of the upload path."""
+    h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        d.copy_(h, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return nbytes * reps / (float(t.item()) * 1e-3) / 1e9   # GB/s per GPU with all GPUs copying
+
+
+def bench_batch(args, torch, rank, world, local, dist):
+    """BASELINE configs[3]: a batch of DISTINCT host-resident 4096^2 pairs, pair p on rank p % world (no collective on the
+    data path), every pair uploaded from pinned host memory and aligned to convergence through batch.align_stream."""
+    from demcoreg_b200 import batch as _batch, synth
+    n, res = args.batch_size, 8.0
+    mine = _batch.shard(args.batch_pairs, rank, world)
+    # each rank keeps to its own slice of the host cores (the per-pair host work is one thread)
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        per = max(2, len(cpus) // max(1, world))
+        sl = cpus[(local * per) % len(cpus):(local * per) % len(cpus) + per]
+        if len(sl) >= 2:
+            os.sched_setaffinity(0, sl)
+    except Exception:
+        cpus = None
+    rng = np.random.default_rng(20260040)
+    shifts = rng.uniform(-8.0, 8.0, size=(args.batch_pairs, 2))
+    dzs = rng.uniform(-1.0, 1.0, size=args.batch_pairs)
+    nloc = len(mine)
+    h_ref = torch.empty((nloc, n, n), dtype=torch.float32, pin_memory=True)
+    h_src = torch.empty((nloc, n, n), dtype=torch.float32, pin_memory=True)
+    h_msk = torch.empty((nloc, n, n), dtype=torch.uint8, pin_memory=True)
+    scale = synth.terrain_scale_torch(torch, n, res, 20260040, "cuda")
+    gt = None
+    for k, pidx in enumerate(mine):
+        pr = synth.make_pair_torch(n=n, res=res, seed=20260040 + 7 * pidx, shift=(float(shifts[pidx, 0]), float(shifts[pidx, 1]),
+                                   float(dzs[pidx])), scale=scale, static_mask_frac=0.3, nodata_frac=0.01)
+        h_ref[k].copy_(pr['ref'])
+        h_src[k].copy_(pr['src'])
+        h_msk[k].copy_(pr['mask'])
+        gt = pr['gt']
+    torch.cuda.synchronize()
+    del pr
+    torch.cuda.empty_cache()
+    pairs = [dict(ref=h_ref[k], src=h_src[k], mask=h_msk[k], ref_gt=gt, src_gt=gt, mask_gt=gt, ndv=synth.NDV) for k in range(nloc)]
+    h2d_gbs = bench_h2d(torch, world, dist)
+    _batch.align_stream(pairs[:2])          # warm-up: buffers, workspace, first-use initialisation
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res_list = _batch.align_stream(pairs)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3, wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    err = 0.0
+    iters = 0
+    fb = 0
+    bad = 0
+    for k, pidx in enumerate(mine):
+        r = res_list[k]
+        if r['exit_code']:
+            bad += 1
+            continue
+        err = max(err, abs(r['dx'] - shifts[pidx, 0]), abs(r['dy'] - shifts[pidx, 1]), abs(r['dz'] + dzs[pidx]))
+        iters += r['n_iter']
+        fb += r['select_fallbacks'] + r['bin_fallbacks']
+    agg = torch.tensor([err, float(iters), float(fb), float(bad)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = agg[:1].clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = agg[1:].clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        agg = torch.cat([mx, sm])
+    agg = agg.cpu().numpy()
+    secs = float(t[0].item())
+    bytes_pair = n * n * 9
+    return {"workload": "%d distinct synthetic %dx%d pairs at %g m (30 %% stable-surface mask, 1 %% nodata, shifts U(-8,8) m), "
+                        "host-resident (pinned), pair p on rank p %% %d, dem_align -mode nuth to tol 0.02 m + final statistics pass"
+                        % (args.batch_pairs, n, n, res, world),
+            "pairs": args.batch_pairs, "pairs_per_s": args.batch_pairs / secs, "seconds": secs, "wall_seconds": float(t[1].item()),
+            "h2d_bytes_per_pair": bytes_pair, "upload_gbs_per_gpu_needed": bytes_pair * (args.batch_pairs / world) / secs / 1e9,
+            "h2d_gbs_per_gpu_measured_all_ranks_copying": h2d_gbs,
+            "upload_bound_pairs_per_s": world * h2d_gbs * 1e9 / bytes_pair,
+            "mean_iterations": float(agg[1]) / max(1, args.batch_pairs - int(agg[3])),
+            "max_abs_error_vs_injected_m": float(agg[0]), "engine_fallbacks": int(agg[2]), "pairs_failed": int(agg[3])}
+
+
+def bench_band(args, torch, rank, world, local, dist):
+    """BASELINE configs[4]: ONE band_size^2 pair at 2 m split into row bands over the ranks (NCCL halo exchange, all-reduced
+    histograms).  Every rank builds only its own rows, on the device: an 8192^2-periodic clean terrain pair tiled across
+    the raster + white noise that is unique to every pixel of the big raster (seeded per 1024-row block, so the raster
+    does not depend on the number of ranks)."""
+    from demcoreg_b200 import band, synth
+    n, res, per = args.band_size, 2.0, min(args.band_size, 8192)
+    base = synth.make_pair_torch(n=per, res=res, seed=20260050, noise=0.0, outlier_frac=0.0, static_mask_frac=0.3, nodata_frac=0.01)
+    r0, r1 = band.band_rows(n, rank, world)
+    reps = n // per
+    rows = torch.arange(r0, r1, device="cuda") % per
+
+    def band_of(a):
+        return a[rows].repeat(1, reps)
+    ref_b = band_of(base['ref'])
+    msk_b = band_of(base['mask'])
+    src_b = band_of(base['src'])
+    hole = src_b == synth.NDV
+    blk = 1024
+    for b0 in range((r0 // blk) * blk, r1, blk):
+        g = torch.Generator(device="cuda")
+        g.manual_seed(20260051 + b0 // blk)
+        nz = torch.randn((blk, n), generator=g, device="cuda", dtype=torch.float32) * 0.3
+        lo, hi = max(b0, r0), min(b0 + blk, r1)
+        src_b[lo - r0:hi - r0] += nz[lo - b0:hi - b0]
+    src_b[hole] = synth.NDV
+    del base, hole, nz
+    torch.cuda.empty_cache()
+    al = band.BandAligner(ref_b, src_b, msk_b, n, (500000.0, res, 0.0, 4100000.0, 0.0, -res), synth.NDV, rank, world, halo=64)
+    del ref_b, src_b, msk_b
+    torch.cuda.empty_cache()
+    al.exchange_halos()
+
+    def step():
+        r = band.iteration_distributed(al)
+        al.apply_shift(r.dx, r.dy, r.dz)
+        return r
+    for _ in range(2):
+        r = step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    nst = 4
+    pix = 0
+    for _ in range(nst):
+        r = step()
+        pix += al.grid.height * al.grid.width
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / nst
+    peak, _ = peaks()
+    ach = ALG_BYTES_ITER * (pix / nst) / (ms_step * 1e-3) / 1e9
+    return {"workload": "dem_align -mode nuth, one iteration per step on ONE synthetic %dx%d pair at %g m (30 %% stable-surface "
+                        "mask, 1 %% nodata) split into %d row bands; NCCL halo exchange + histogram all-reduces" % (n, n, res, world),
+            "ms_per_iteration": ms_step, "gpix_per_s": pix / nst / (ms_step * 1e-3) / 1e9, "steps": nst,
+            "roofline_frac_of_n_x_peak": ach / (peak * world), "halo_rows": 64,
+            "last_step_shift_m": [r.dx, r.dy, r.dz], "select_engine": int(r.select_engine), "bin_engine": int(r.bin_engine)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -259,6 +484,12 @@ def main():
     ap.add_argument("--size", type=int, default=8192)
     ap.add_argument("--res", type=float, default=8.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config3", action="store_true", help="skip the NCC / SAD object (BASELINE configs[2])")
+    ap.add_argument("--no-batch", action="store_true", help="skip the 256-pair batch object (BASELINE configs[3])")
+    ap.add_argument("--no-band", action="store_true", help="skip the row-band object at N > 1 (BASELINE configs[4])")
+    ap.add_argument("--batch-pairs", type=int, default=256)
+    ap.add_argument("--batch-size", type=int, default=4096)
+    ap.add_argument("--band-size", type=int, default=32768)
     ap.add_argument("--mode", default="pairs", choices=["pairs", "band"],
                     help="pairs: one pair per GPU, no collective (default; configs[1]/[3]); band: ONE size x size pair "
                          "split into row bands over the GPUs with NCCL halo exchange + all-reduces (configs[4])")
@@ -331,6 +562,10 @@ def main():
     barrier()
     assert len(recs) == args.steps and all(rc['status'] == 0 for rc in recs), "bench iterations did not all run"
     pix = sum(rc['h'] * rc['w'] for rc in recs)
+    engines = {"select_engine": "one-pass sample-bracket" if all(rc['select_engine'] for rc in recs) else "radix fallback seen",
+               "radix_reruns": sum(1 for rc in recs if not rc['select_engine']),
+               "bin_engine": "two-pass shared-memory bins" if all(rc['bin_engine'] for rc in recs) else "radix bins seen",
+               "fast_fallback": sum(1 for rc in recs if not rc['bin_engine'])}
     r = al.st.last
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
@@ -412,10 +647,25 @@ def main():
     import ctypes
     d2h = int(ctypes.sizeof(_lib.IterResult))
 
+    # free the 8192^2 working set before the other configurations
+    del al, src, src0, ref, ms, h_ref, h_src, h_msk, hp
+    engine._ws_cache.clear()
+    torch.cuda.empty_cache()
+    batch_obj = band_obj = config3_obj = None
+    if not args.no_batch:
+        batch_obj = bench_batch(args, torch, rank, world, local, dist)
+        engine._ws_cache.clear()
+        torch.cuda.empty_cache()
+    if world > 1 and not args.no_band:
+        band_obj = bench_band(args, torch, rank, world, local, dist)
+        engine._ws_cache.clear()
+        torch.cuda.empty_cache()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    if world == 1 and not args.no_config3:
+        config3_obj = bench_config3(args, torch)
 
     # ---- CPU baseline: the oracle on a bounded sample of the same workload (rank 0, N=1 only) ----
     cpu = None
@@ -433,7 +683,8 @@ def main():
                                    "at %g m with a 30%% stable-surface mask, 1%% nodata, injected shift (+3.2,-1.7,+0.5) m; "
                                    "one pair per GPU" % (size, size, res),
                        "pixels_per_step_per_gpu": npx, "l2": "inputs (2 x %d MB + mask) larger than the 126 MB L2" % (npx * 4 >> 20),
-                       "last_step_shift_m": [r.dx, r.dy, r.dz],
+                       "last_step_shift_m": [r.dx, r.dy, r.dz], "engines": engines,
+                       "period": "terrain and masks generated at the full %d^2 size (no tiling)" % min(size, 8192),
                        "pairs_per_s": pairs_per_s, "pairs_loop": {"n_iter": res_loop['n_iter'], "dx": res_loop['dx'],
                                                                   "dy": res_loop['dy'], "dz": res_loop['dz'],
                                                                   "note": "dem_align.align to convergence (tol 0.02 m), device-resident pair, incl. the src copy"}},
@@ -441,7 +692,8 @@ def main():
             "e2e": {"value": e2e_val, "unit": "Gpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "engine.nuth_iteration on host-resident pinned rasters through batch.stream_pairs: uploads double-"
                             "buffered on a copy stream (step k+1's H2D overlaps step k's kernels); PCIe-bound"},
-            "roofline": roofline, "roofline_iteration": roofline_iter, "cpu_baseline": cpu}
+            "roofline": roofline, "roofline_iteration": roofline_iter, "cpu_baseline": cpu,
+            "config3": config3_obj, "batch": batch_obj, "band": band_obj}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

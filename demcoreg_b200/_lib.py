@@ -13,6 +13,7 @@ NBINS = 360
 M_BASE, M_MAXDZ, M_MAD, M_SLOPE, M_ASPECT = 0x01, 0x02, 0x04, 0x08, 0x10
 M_DIFF = M_BASE | M_MAXDZ | M_MAD | M_SLOPE
 ITER_REMOVE_OUTLIERS, ITER_PROFILE, ITER_RADIX_ONLY, ITER_APPLY_Z = 1, 2, 4, 8
+SAD_PER_OFFSET = 1
 
 
 class RasterDesc(C.Structure):
@@ -62,7 +63,7 @@ class IterResult(C.Structure):
                 ("dz_med", C.c_float), ("med_dh", C.c_float), ("med_slope", C.c_float), ("c_seed", C.c_float),
                 ("nuth", NuthStats), ("fit", C.c_double * 3), ("dx", C.c_double), ("dy", C.c_double),
                 ("dz", C.c_double), ("stage_ms", C.c_float * 8), ("select_engine", C.c_int32),
-                ("z_applied", C.c_int32)]
+                ("z_applied", C.c_int32), ("bin_engine", C.c_int32), ("_pad", C.c_int32)]
 
 
 ALIGN_MAX_PENDING = 4
@@ -71,7 +72,7 @@ ALIGN_MAX_PENDING = 4
 class AlignIter(C.Structure):
     _fields_ = [("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double), ("status", C.c_int32),
                 ("select_engine", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
-                ("fit", C.c_double * 3), ("dz_med", C.c_float), ("med_slope", C.c_float)]
+                ("bin_engine", C.c_int32), ("_pad", C.c_int32), ("fit", C.c_double * 3), ("dz_med", C.c_float), ("med_slope", C.c_float)]
 
 
 class AlignState(C.Structure):
@@ -128,6 +129,8 @@ SYMBOLS = {
     "dcr_sad_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "dcr_sad_search": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_double), _P,
                                  C.c_size_t, _P]),
+    "dcr_sad_search_ex": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                    C.POINTER(C.c_int), C.POINTER(C.c_float), _P, C.c_size_t, _P]),
     "dcr_fit_nuth": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]),
     "dcr_apply_z_shift": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_float, _P, _P]),
     "dcr_apply_z_shift_seq": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.c_double, C.POINTER(C.c_float), C.c_int, _P]),

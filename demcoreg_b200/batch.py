@@ -110,3 +110,37 @@ def stream_pairs(host_pairs, device=None):
         yield sets[b]
         free[b].record()
 
+
+
+def align_stream(host_pairs, mode_kw=None, final_pass=True, device=None):
+    """Align a stream of host-resident pairs on this rank's GPU: ``dem_align`` (mode nuth) to convergence per pair.
+
+    ``stream_pairs`` uploads pair ``k+1`` (pinned host memory, copy stream) while the whole loop of pair ``k`` runs;
+    ONE ``NuthAligner`` serves every pair (``reset``: iteration outputs, workspace and record array are allocated
+    once).  The source rasters are shifted in place in the upload buffers (the reference works on a copy; here the buffer
+    is overwritten by the next upload anyway).  ``final_pass``: one more front + filter pass on the aligned pair, the
+    basis of the reference's after-alignment statistics (``dem_align.py:366-392``).
+    Returns a list of dicts ``dx, dy, dz, n_iter`` (+ ``after_med, after_nmad, after_count`` with ``final_pass``).
+    """
+    from . import engine
+    kw = dict(tol=0.02, max_offset=100, max_dz=100, slope_lim=(0.1, 40), max_iter=30)
+    if mode_kw:
+        kw.update(mode_kw)
+    al = None
+    bufs = None
+    out = []
+    for d_ref, d_src, d_ms in stream_pairs(host_pairs, device=device):
+        if al is None:
+            al = engine.NuthAligner(d_ref, d_src, d_ms, **kw)
+        else:
+            al.reset(d_ref, d_src, d_ms, **kw)
+        recs = al.run()
+        dx, dy, dz = al.totals
+        r = dict(dx=dx, dy=dy, dz=dz, n_iter=len(recs), exit_code=int(al.st.exit_code),
+                 select_fallbacks=sum(1 for it in recs if not it['select_engine']),
+                 bin_fallbacks=sum(1 for it in recs if not it['bin_engine']))
+        if final_pass and al.st.exit_code == 0:
+            res, grid, bufs = engine.nuth_iteration(d_ref, d_src, d_ms, True, kw['max_dz'], (0.1, 40), bufs=bufs)
+            r.update(after_med=float(res.med1), after_nmad=float(res.nmad1), after_count=int(res.count_mad))
+        out.append(r)
+    return out

@@ -342,14 +342,16 @@ int dcr_bsel_enqueue(const SelView& v, double q_percent, BselState* st, void* sc
     dcr_bsel_buffers(scratch, n_max, &hist, &cand, &cap);
     int rc = dcr_bsel_sample_enqueue(v, q_percent, st, scratch, n_max, s, publish);
     if (rc) return rc;
-    static int grid0 = 0;   // SMs x 8, like the other streaming kernels
-    if (!grid0) {
+    DcrCtx* ctx = dcr_ctx();
+    if (!ctx) return -1;
+    if (!(ctx->attrs & DCR_ATTR_BSEL)) {   // per device
         DCR_CUDA_OK(cudaFuncSetAttribute(bsel_main_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(MainCollector::Shared)));
         DCR_CUDA_OK(cudaFuncSetAttribute(bsel_main_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(MainCollector::Shared)));
-        grid0 = dcr_num_sms() * 8;
+        ctx->attrs |= DCR_ATTR_BSEL;
     }
+    const int grid0 = ctx->sms * 8;   // SMs x 8, like the other streaming kernels
     // a CTA stages up to 4096 in-bracket keys (~6 % of what it streams): keep its share below 57k elements
     long long grid = (n_max + 57343) / 57344;
     if (grid < grid0) grid = grid0;

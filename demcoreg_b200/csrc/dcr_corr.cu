@@ -1,16 +1,17 @@
-// K7a NCC and K7b SAD offset search.
+// K7a NCC offset search (K7b SAD: dcr_sad.cu).
 //
 // Replaces reference coreglib.compute_offset_ncc (coreglib.py:118-198: z-score both rasters over their
-// valid pixels, fill masked pixels with noise, scipy.signal.correlate2d(ref, kernel, 'valid')) and
-// coreglib.compute_offset_sad (coreglib.py:65-115: per offset, diff = ref window - kernel, trim outside the
-// [P25, P75] interquartile range, mean absolute difference).  The argmax / parabolic sub-pixel step
-// (coreglib.py:387-485) stays on the host.
+// valid pixels, fill masked pixels with noise, scipy.signal.correlate2d(ref, kernel, 'valid')).  The argmax /
+// parabolic sub-pixel step (coreglib.py:387-485) stays on the host.
 //
 // NCC is a direct shared-memory correlation (2*(2p+1)^2 flop per 8 bytes: FP32-issue bound, not HBM
-// bound): a CTA stages a kernel tile and the matching reference tile (+2p halo); a thread owns one offset
-// row and NCC_CJ consecutive offset columns and slides a register window along the tile row, so every
-// shared-memory load feeds NCC_CJ FMAs.  Partial sums are FP32 per tile (<= 2048 products) and are reduced
-// across tiles in FP64 in a fixed order (deterministic, ~1e-10 relative on the map).
+// bound): persistent CTAs walk over 16 x 128 kernel tiles; a CTA stages the tile and the matching reference
+// tile (+ halo); a thread owns one offset row and NCC_CJ consecutive offset columns and slides a register window
+// along the tile row, so every shared-memory load feeds NCC_CJ FMAs (the kernel values arrive four at a time
+// by one broadcast 16-byte load).  Products are accumulated in FP32 over ONE tile row (128 terms) and from
+// there in FP64 registers across all the tiles of the CTA; the per-CTA partial maps are summed in FP64 in a
+// fixed order (deterministic; ~1e-9 relative on the map against scipy's float64 correlate2d).  Search radii
+// whose offset rows do not fit one CTA (p > 19) are split into blocks of offset rows (grid.y).
 #include <string.h>
 #include "dcr_common.cuh"
 #include "dcr_internal.cuh"
@@ -73,104 +74,127 @@ __global__ void __launch_bounds__(256) zscore_kernel(const float* __restrict__ x
 // ------------------------------------------------------------------------------------------
 // NCC: direct correlation
 // ------------------------------------------------------------------------------------------
-#define NCC_TU 16    // kernel-tile rows per CTA
-#define NCC_TV 128   // kernel-tile columns per CTA
+#define NCC_TU 16    // kernel-tile rows
+#define NCC_TV 128   // kernel-tile columns
 #define NCC_CJ 8     // offset columns per thread (register window)
-#define NCC_MAXP 24  // largest supported pad (search radius in pixels)
+#define NCC_THREADS 512
+#define NCC_MAXP 127 // largest supported pad (search radius in pixels)
 
 // zr: [H x W] z-scored reference; zk: [kh x kw] z-scored kernel (kh = H - 2p, kw = W - 2p).
-// part: [ntiles][J*J] float partial maps, J = 2p + 1.
-__global__ void __launch_bounds__(512) ncc_tile_kernel(const float* __restrict__ zr, const float* __restrict__ zk, int H, int W,
-                                                       int kh, int kw, int p, float* __restrict__ part) {
-    extern __shared__ float sm[];
+// CTA (x, y): tiles x, x + gridDim.x, ...; offset rows [y * IB, min(J, (y + 1) * IB)).
+// part: [gridDim.x][J*J] float64 partial maps, J = 2p + 1.
+__global__ void __launch_bounds__(NCC_THREADS) ncc_tile_kernel(const float* __restrict__ zr, const float* __restrict__ zk, int H,
+                                                               int W, int kh, int kw, int p, int IB,
+                                                               double* __restrict__ part) {
+    extern __shared__ __align__(16) float sm[];
     const int J = 2 * p + 1;
     const int nchunk = (J + NCC_CJ - 1) / NCC_CJ;
+    const int i0 = blockIdx.y * IB;
+    const int ni = min(IB, J - i0);
     const int RW = NCC_TV + 2 * p;             // reference tile width actually used
     const int RA = NCC_TV + nchunk * NCC_CJ;   // allocated width: the last column chunk may run past J (zero-filled)
     const int RP = RA | 1;                     // odd pitch: lanes on different rows hit different banks
+    const int RR = NCC_TU + ni - 1;            // reference tile rows
     float* s_k = sm;                           // NCC_TU x NCC_TV
-    float* s_r = sm + NCC_TU * NCC_TV;         // (NCC_TU + 2p) x RP
-    const int u0 = blockIdx.y * NCC_TU, v0 = blockIdx.x * NCC_TV;
-    for (int k = threadIdx.x; k < NCC_TU * NCC_TV; k += blockDim.x) {
-        const int u = k / NCC_TV, v = k - u * NCC_TV;
-        s_k[k] = (u0 + u < kh && v0 + v < kw) ? __ldg(zk + (long long)(u0 + u) * kw + v0 + v) : 0.0f;
-    }
-    for (int k = threadIdx.x; k < (NCC_TU + 2 * p) * RP; k += blockDim.x) {
-        const int r = k / RP, c = k - r * RP;
-        s_r[k] = (c < RW && u0 + r < H && v0 + c < W) ? __ldg(zr + (long long)(u0 + r) * W + v0 + c) : 0.0f;
-    }
-    __syncthreads();
+    float* s_r = sm + NCC_TU * NCC_TV;         // RR x RP
     // work items: (offset row i, column chunk jc, tile-row phase ph); item -> lane mapping keeps i fastest
-    const int nitems = J * nchunk;
-    const int nphase = blockDim.x / nitems > 0 ? blockDim.x / nitems : 1;
+    const int nitems = ni * nchunk;
+    const int nphase = NCC_THREADS / nitems > 0 ? NCC_THREADS / nitems : 1;
     const int item = threadIdx.x % nitems, ph = threadIdx.x / nitems;
-    float* out = part + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * (J * J);
-    float acc[NCC_CJ];
+    const bool active = ph < nphase && threadIdx.x < nitems * nphase;
+    const int i = item % ni, jc = item / ni;
+    const int j0 = jc * NCC_CJ;
+    double accd[NCC_CJ];
 #pragma unroll
-    for (int q = 0; q < NCC_CJ; ++q) acc[q] = 0.0f;
-    if (ph < nphase) {
-        const int i = item % J, jc = item / J;
-        const int j0 = jc * NCC_CJ;
-        for (int u = ph; u < NCC_TU; u += nphase) {
-            const float* rrow = s_r + (u + i) * RP + j0;
-            const float* krow = s_k + u * NCC_TV;
-            float win[NCC_CJ];
+    for (int q = 0; q < NCC_CJ; ++q) accd[q] = 0.0;
+    const int ntx = (kw + NCC_TV - 1) / NCC_TV, nty = (kh + NCC_TU - 1) / NCC_TU;
+    for (int t = blockIdx.x; t < ntx * nty; t += gridDim.x) {
+        const int ty = t / ntx, tx = t - ty * ntx;
+        const int u0 = ty * NCC_TU, v0 = tx * NCC_TV;
+        __syncthreads();
+        for (int k = threadIdx.x; k < NCC_TU * NCC_TV; k += NCC_THREADS) {
+            const int u = k / NCC_TV, v = k - u * NCC_TV;
+            s_k[k] = (u0 + u < kh && v0 + v < kw) ? __ldg(zk + (long long)(u0 + u) * kw + v0 + v) : 0.0f;
+        }
+        for (int k = threadIdx.x; k < RR * RP; k += NCC_THREADS) {
+            const int r = k / RP, c = k - r * RP;
+            s_r[k] = (c < RW && u0 + i0 + r < H && v0 + c < W) ? __ldg(zr + (long long)(u0 + i0 + r) * W + v0 + c) : 0.0f;
+        }
+        __syncthreads();
+        if (active) {
+            for (int u = ph; u < NCC_TU; u += nphase) {
+                const float* rrow = s_r + (u + i) * RP + j0;
+                const float4* krow = reinterpret_cast<const float4*>(s_k + u * NCC_TV);
+                float acc[NCC_CJ], win[NCC_CJ];
 #pragma unroll
-            for (int q = 0; q < NCC_CJ - 1; ++q) win[q + 1] = rrow[q];
-            // slide along the tile row; unrolled by NCC_CJ so the register window rotates for free
-            for (int v = 0; v < NCC_TV; v += NCC_CJ) {
+                for (int q = 0; q < NCC_CJ; ++q) acc[q] = 0.0f;
 #pragma unroll
-                for (int s = 0; s < NCC_CJ; ++s) {
-                    // window holds rrow[v+s .. v+s+CJ-1]; shift in the newest element
+                for (int q = 0; q < NCC_CJ - 1; ++q) win[q + 1] = rrow[q];
+                // slide along the tile row; unrolled by NCC_CJ so the register window rotates for free
+                for (int v = 0; v < NCC_TV; v += NCC_CJ) {
+                    const float4 ka = krow[v >> 2], kb = krow[(v >> 2) + 1];
+                    const float kk[NCC_CJ] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
 #pragma unroll
-                    for (int q = 0; q < NCC_CJ - 1; ++q) win[q] = win[q + 1];
-                    win[NCC_CJ - 1] = rrow[v + s + NCC_CJ - 1];
-                    const float kv = krow[v + s];
+                    for (int s = 0; s < NCC_CJ; ++s) {
+                        // window holds rrow[v+s .. v+s+CJ-1]; shift in the newest element
 #pragma unroll
-                    for (int q = 0; q < NCC_CJ; ++q) acc[q] = fmaf(win[q], kv, acc[q]);
+                        for (int q = 0; q < NCC_CJ - 1; ++q) win[q] = win[q + 1];
+                        win[NCC_CJ - 1] = rrow[v + s + NCC_CJ - 1];
+#pragma unroll
+                        for (int q = 0; q < NCC_CJ; ++q) acc[q] = fmaf(win[q], kk[s], acc[q]);
+                    }
                 }
+#pragma unroll
+                for (int q = 0; q < NCC_CJ; ++q) accd[q] += (double)acc[q];   // FP32 over one tile row, FP64 beyond
             }
         }
     }
     // combine the phases of one item through shared memory (fixed order)
     __syncthreads();
-    if (ph < nphase) {
+    double* sd = reinterpret_cast<double*>(sm);
+    if (active) {
 #pragma unroll
-        for (int q = 0; q < NCC_CJ; ++q) sm[(ph * nitems + item) * NCC_CJ + q] = acc[q];
+        for (int q = 0; q < NCC_CJ; ++q) sd[(ph * nitems + item) * NCC_CJ + q] = accd[q];
     }
     __syncthreads();
     if (threadIdx.x < nitems) {
-        const int i = item % J, jc = item / J;
+        double* out = part + (long long)blockIdx.x * (J * J);
         for (int q = 0; q < NCC_CJ; ++q) {
-            const int j = jc * NCC_CJ + q;
+            const int j = j0 + q;
             if (j >= J) break;
-            float t = 0.0f;
-            for (int f = 0; f < nphase; ++f) t += sm[(f * nitems + item) * NCC_CJ + q];
-            out[i * J + j] = t;
+            double t = 0.0;
+            for (int f = 0; f < nphase; ++f) t += sd[(f * nitems + item) * NCC_CJ + q];
+            out[(i0 + i) * J + j] = t;
         }
     }
 }
 
-__global__ void ncc_reduce_kernel(const float* __restrict__ part, int ntiles, int JJ, double* __restrict__ m) {
-    const int o = blockIdx.x;  // one block per map element
-    __shared__ double sd[256];
+__global__ void ncc_reduce_kernel(const double* __restrict__ part, int nparts, int JJ, double* __restrict__ m) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per map element, partials in CTA order
+    if (o >= JJ) return;
     double t = 0.0;
-    for (int k = threadIdx.x; k < ntiles; k += 256) t += (double)part[(long long)k * JJ + o];
-    sd[threadIdx.x] = t;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (threadIdx.x < s) sd[threadIdx.x] += sd[threadIdx.x + s];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) m[o] = sd[0];
+    for (int k = 0; k < nparts; ++k) t += part[(long long)k * JJ + o];
+    m[o] = t;
+}
+
+// rows of offsets per CTA: every (offset row, column chunk) item of a block needs its own thread
+static int ncc_rows_per_block(int pad) {
+    const int J = 2 * pad + 1, nchunk = (J + NCC_CJ - 1) / NCC_CJ;
+    int ib = NCC_THREADS / nchunk;
+    return ib > J ? J : ib;
+}
+static int ncc_grid_x(int pad) {
+    const int J = 2 * pad + 1, ib = ncc_rows_per_block(pad);
+    const int nib = (J + ib - 1) / ib;
+    int gx = (dcr_num_sms() * 2 + nib - 1) / nib;
+    return gx < 1 ? 1 : gx;
 }
 
 extern "C" size_t dcr_ncc_workspace_bytes(int h, int w, int pad) {
     const long long kh = h - 2 * pad, kw = w - 2 * pad;
-    if (kh <= 0 || kw <= 0) return 0;
+    if (kh <= 0 || kw <= 0 || pad < 1 || pad > NCC_MAXP) return 0;
     const long long J = 2 * pad + 1;
-    const long long ntiles = ((kh + NCC_TU - 1) / NCC_TU) * ((kw + NCC_TV - 1) / NCC_TV);
-    return dcr_al256((size_t)h * w * 4) + dcr_al256((size_t)kh * kw * 4) + dcr_al256((size_t)ntiles * J * J * 4) +
+    return dcr_al256((size_t)h * w * 4) + dcr_al256((size_t)kh * kw * 4) + dcr_al256((size_t)ncc_grid_x(pad) * J * J * 8) +
            dcr_al256((size_t)J * J * 8) + dcr_al256(2048 * sizeof(WinPartial)) + dcr_al256(64) + 4096;
 }
 
@@ -179,18 +203,22 @@ extern "C" int dcr_ncc_corr(const float* ref, const uint8_t* ref_mask, const flo
                             double stats_out[4] /* host: ref mean,std, kernel mean,std */, void* workspace,
                             size_t workspace_bytes, void* stream) {
     DCR_ARG(ref && src && m_out && workspace, "null pointer");
-    DCR_ARG(pad >= 1 && pad <= NCC_MAXP, "1 <= pad <= 24");
+    DCR_ARG(pad >= 1 && pad <= NCC_MAXP, "1 <= pad <= 127");
     const int kh = h - 2 * pad, kw = w - 2 * pad;
     DCR_ARG(kh > 0 && kw > 0, "raster smaller than the search window");
     DCR_ARG(workspace_bytes >= dcr_ncc_workspace_bytes(h, w, pad), "workspace too small");
     cudaStream_t s = (cudaStream_t)stream;
     const int J = 2 * pad + 1;
-    dim3 tiles((kw + NCC_TV - 1) / NCC_TV, (kh + NCC_TU - 1) / NCC_TU);
-    const long long ntiles = (long long)tiles.x * tiles.y;
+    const int ib = ncc_rows_per_block(pad), nib = (J + ib - 1) / ib;
+    int gx = ncc_grid_x(pad);
+    {
+        const long long ntiles = (long long)((kw + NCC_TV - 1) / NCC_TV) * ((kh + NCC_TU - 1) / NCC_TU);
+        if (gx > ntiles) gx = (int)ntiles;
+    }
     DcrBump ws(workspace, workspace_bytes);
     float* zr = ws.take<float>((size_t)h * w);
     float* zk = ws.take<float>((size_t)kh * kw);
-    float* part = ws.take<float>((size_t)ntiles * J * J);
+    double* part = ws.take<double>((size_t)ncc_grid_x(pad) * J * J);
     double* dm = ws.take<double>((size_t)J * J);
     WinPartial* wp = ws.take<WinPartial>(2048);
     double* stats = ws.take<double>(8);
@@ -204,154 +232,18 @@ extern "C" int dcr_ncc_corr(const float* ref, const uint8_t* ref_mask, const flo
     win_moments_final_kernel<<<1, 32, 0, s>>>(wp + 1024, g, stats + 4);
     zscore_kernel<<<g, 256, 0, s>>>(src, src_mask, stride, stride, pad, pad, kh, kw, stats + 4, kernel_noise, zk);
     const int nchunk = (J + NCC_CJ - 1) / NCC_CJ;
-    const int nitems = J * nchunk;
-    int threads = 512;
-    if (nitems > 512) { dcr_set_error("pad too large for the NCC kernel"); return -1; }
-    const size_t smem_tiles = (size_t)(NCC_TU * NCC_TV + (NCC_TU + 2 * pad) * ((NCC_TV + nchunk * NCC_CJ) | 1)) * sizeof(float);
-    const size_t smem_red = (size_t)threads * NCC_CJ * sizeof(float);
+    const size_t smem_tiles = (size_t)(NCC_TU * NCC_TV + (NCC_TU + ib - 1) * ((NCC_TV + nchunk * NCC_CJ) | 1)) * sizeof(float);
+    const size_t smem_red = (size_t)NCC_THREADS * NCC_CJ * sizeof(double);
     const size_t smem = smem_tiles > smem_red ? smem_tiles : smem_red;
+    if (smem > 227 * 1024) { dcr_set_error("pad too large for the NCC kernel"); return -1; }
     DCR_CUDA_OK(cudaFuncSetAttribute(ncc_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ncc_tile_kernel<<<tiles, threads, smem, s>>>(zr, zk, h, w, kh, kw, pad, part);
-    ncc_reduce_kernel<<<J * J, 256, 0, s>>>(part, (int)ntiles, J * J, dm);
+    ncc_tile_kernel<<<dim3(gx, nib), NCC_THREADS, smem, s>>>(zr, zk, h, w, kh, kw, pad, ib, part);
+    ncc_reduce_kernel<<<(J * J + 255) / 256, 256, 0, s>>>(part, gx, J * J, dm);
     DCR_LAUNCH_OK("ncc kernels");
     double hs[8];
     DCR_CUDA_OK(cudaMemcpyAsync(m_out, dm, (size_t)J * J * sizeof(double), cudaMemcpyDeviceToHost, s));
     DCR_CUDA_OK(cudaMemcpyAsync(hs, stats, sizeof(hs), cudaMemcpyDeviceToHost, s));
     DCR_CUDA_OK(cudaStreamSynchronize(s));
     if (stats_out) { stats_out[0] = hs[0]; stats_out[1] = hs[1]; stats_out[2] = hs[4]; stats_out[3] = hs[5]; }
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------------
-// SAD: per offset, diff = ref window - kernel (float32), trim outside [P25, P75], mean |diff|
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sad_diff_kernel(const float* __restrict__ ref, const unsigned char* __restrict__ rm,
-                                                       const float* __restrict__ src, const unsigned char* __restrict__ smk,
-                                                       long long stride, int oi, int oj, int pad, int kh, int kw,
-                                                       float* __restrict__ diff, unsigned char* __restrict__ dmask) {
-    const long long n = (long long)kh * kw;
-    for (long long k = (long long)blockIdx.x * 256 + threadIdx.x; k < n; k += (long long)gridDim.x * 256) {
-        const int u = (int)(k / kw), v = (int)(k - (long long)u * kw);
-        const long long ri = (long long)(oi + u) * stride + oj + v;
-        const long long si = (long long)(pad + u) * stride + pad + v;
-        const bool masked = (rm && rm[ri]) || (smk && smk[si]);
-        diff[k] = masked ? 0.0f : (ref[ri] - src[si]);
-        dmask[k] = masked ? 1 : 0;
-    }
-}
-
-struct SadPartial { unsigned long long n; double s; };
-
-// sum of |d| over unmasked d with lo <= d <= hi (np.ma.masked_outside keeps the closed interval)
-__global__ void __launch_bounds__(256) sad_sum_kernel(const float* __restrict__ diff, const unsigned char* __restrict__ dmask,
-                                                      long long n, const BselState* qlo, const BselState* qhi,
-                                                      SadPartial* __restrict__ part) {
-    __shared__ SadPartial sp[8];
-    const float lo = qlo->result, hi = qhi->result;
-    unsigned long long cnt = 0;
-    double s = 0;
-    dcr_stream1(diff, dmask, n, [&](float d, unsigned mb, long long) {
-        if (mb) return;
-        if (d < lo || d > hi) return;
-        ++cnt;
-        s += (double)fabsf(d);
-    });
-    cnt = dcr_warp_sum_u64(cnt); s = dcr_warp_sum(s);
-    if ((threadIdx.x & 31) == 0) { SadPartial q; q.n = cnt; q.s = s; sp[threadIdx.x >> 5] = q; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        SadPartial q = sp[0];
-        for (int k = 1; k < 8; ++k) { q.n += sp[k].n; q.s += sp[k].s; }
-        part[blockIdx.x] = q;
-    }
-}
-
-__global__ void sad_final_kernel(const SadPartial* __restrict__ part, int nparts, const BselState* qlo, const BselState* qhi,
-                                 double* m_out, int* fallback_flag) {
-    if (threadIdx.x) return;
-    unsigned long long n = 0; double s = 0;
-    for (int k = 0; k < nparts; ++k) { n += part[k].n; s += part[k].s; }
-    *m_out = n ? s / (double)n : NAN;
-    if (qlo->fallback || qhi->fallback) *fallback_flag = 1;
-}
-
-extern "C" size_t dcr_sad_workspace_bytes(int h, int w, int pad) {
-    const long long kh = h - 2 * pad, kw = w - 2 * pad;
-    if (kh <= 0 || kw <= 0) return 0;
-    const long long n = kh * kw;
-    const long long J = 2 * pad + 1;
-    return dcr_al256((size_t)n * 4) + dcr_al256((size_t)n) + dcr_bsel_scratch_bytes(n) + dcr_al256(4 * sizeof(BselState)) +
-           dcr_al256(4 * sizeof(SelState)) + dcr_al256(DCR_SEL_HIST_WORDS * 4) + dcr_al256(4096 * sizeof(SadPartial)) +
-           dcr_al256((size_t)J * J * 8) + dcr_al256((size_t)J * J * 4) + 4096;
-}
-
-extern "C" int dcr_sad_search(const float* ref, const uint8_t* ref_mask, const float* src, const uint8_t* src_mask, int h, int w,
-                              int64_t stride, int pad, double* m_out /* host, (2p+1)^2, mean |diff| (not negated) */,
-                              void* workspace, size_t workspace_bytes, void* stream) {
-    DCR_ARG(ref && src && m_out && workspace, "null pointer");
-    DCR_ARG(pad >= 1 && pad <= 64, "1 <= pad <= 64");
-    const int kh = h - 2 * pad, kw = w - 2 * pad;
-    DCR_ARG(kh > 0 && kw > 0, "raster smaller than the search window");
-    DCR_ARG(workspace_bytes >= dcr_sad_workspace_bytes(h, w, pad), "workspace too small");
-    cudaStream_t s = (cudaStream_t)stream;
-    const long long n = (long long)kh * kw;
-    const int J = 2 * pad + 1;
-    DcrBump ws(workspace, workspace_bytes);
-    float* diff = ws.take<float>(n);
-    unsigned char* dmask = ws.take<unsigned char>(n);
-    void* scratch = ws.take<char>(dcr_bsel_scratch_bytes(n));
-    BselState* bst = ws.take<BselState>(4);
-    SelState* sst = ws.take<SelState>(4);
-    unsigned* hist = ws.take<unsigned>(DCR_SEL_HIST_WORDS);
-    SadPartial* part = ws.take<SadPartial>(4096);
-    double* dm = ws.take<double>((size_t)J * J);
-    int* fb = ws.take<int>((size_t)J * J);
-    const int g = dcr_num_sms() * 8;
-    DCR_CUDA_OK(cudaMemsetAsync(fb, 0, (size_t)J * J * sizeof(int), s));
-    SelView v;
-    memset(&v, 0, sizeof(v));
-    v.x = diff; v.m = dmask; v.reject = 1; v.n = n;
-    for (int i = 0; i < J; ++i) {
-        for (int j = 0; j < J; ++j) {
-            sad_diff_kernel<<<g, 256, 0, s>>>(ref, ref_mask, src, src_mask, stride, i, j, pad, kh, kw, diff, dmask);
-            int rc = dcr_bsel_enqueue(v, 25.0, bst, scratch, n, s);
-            if (rc) return rc;
-            rc = dcr_bsel_enqueue(v, 75.0, bst + 1, scratch, n, s);
-            if (rc) return rc;
-            sad_sum_kernel<<<g, 256, 0, s>>>(diff, dmask, n, bst, bst + 1, part);
-            sad_final_kernel<<<1, 32, 0, s>>>(part, g, bst, bst + 1, dm + i * J + j, fb + i * J + j);
-        }
-    }
-    DCR_LAUNCH_OK("sad kernels");
-    int* hfb = new int[(size_t)J * J];
-    cudaError_t e = cudaMemcpyAsync(m_out, dm, (size_t)J * J * sizeof(double), cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(hfb, fb, (size_t)J * J * sizeof(int), cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) { delete[] hfb; dcr_set_error("sad copy failed: %s", cudaGetErrorString(e)); return (int)e; }
-    // offsets whose one-pass quantile verification failed (heavy ties etc.): redo with the radix select
-    for (int o = 0; o < J * J; ++o) {
-        if (!hfb[o]) continue;
-        const int i = o / J, j = o % J;
-        sad_diff_kernel<<<g, 256, 0, s>>>(ref, ref_mask, src, src_mask, stride, i, j, pad, kh, kw, diff, dmask);
-        int rc = dcr_sel_enqueue(v, 25.0, sst, hist, s);
-        if (!rc) rc = dcr_sel_enqueue(v, 75.0, sst + 1, hist, s);
-        if (rc) { delete[] hfb; return rc; }
-        SelState h2[2];
-        e = cudaMemcpyAsync(h2, sst, sizeof(h2), cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess) { delete[] hfb; dcr_set_error("sad copy failed: %s", cudaGetErrorString(e)); return (int)e; }
-        // host-side trimmed mean via the moments path is not needed: reuse the device sum with patched quantiles
-        BselState patch[2];
-        memset(patch, 0, sizeof(patch));
-        patch[0].result = h2[0].result; patch[1].result = h2[1].result;
-        e = cudaMemcpyAsync(bst + 2, patch, sizeof(patch), cudaMemcpyHostToDevice, s);
-        if (e != cudaSuccess) { delete[] hfb; dcr_set_error("sad copy failed: %s", cudaGetErrorString(e)); return (int)e; }
-        sad_sum_kernel<<<g, 256, 0, s>>>(diff, dmask, n, bst + 2, bst + 3, part);
-        sad_final_kernel<<<1, 32, 0, s>>>(part, g, bst + 2, bst + 3, dm + o, fb + o);
-        e = cudaMemcpyAsync(m_out + o, dm + o, sizeof(double), cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess) { delete[] hfb; dcr_set_error("sad copy failed: %s", cudaGetErrorString(e)); return (int)e; }
-    }
-    delete[] hfb;
     return 0;
 }

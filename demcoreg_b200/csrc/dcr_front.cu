@@ -44,17 +44,38 @@ extern "C" int dcr_struct_size(int which) {
     }
 }
 
-int dcr_num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
-            n = v;
-        else
-            n = DCR_NSM_DEFAULT;
+DcrCtx* dcr_ctx() {
+    static thread_local DcrCtx slots[DCR_MAX_DEVICES];
+    static thread_local bool init[DCR_MAX_DEVICES];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { dcr_set_error("cudaGetDevice failed: %s", cudaGetErrorString(e)); return nullptr; }
+    if (dev < 0 || dev >= DCR_MAX_DEVICES) { dcr_set_error("device ordinal %d out of range", dev); return nullptr; }
+    DcrCtx* c = &slots[dev];
+    if (!init[dev]) {
+        memset(c, 0, sizeof(*c));
+        c->dev = dev;
+        int v = 0;
+        c->sms = (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) ? v : DCR_NSM_DEFAULT;
+        init[dev] = true;
     }
-    return n;
+    return c;
+}
+
+void* dcr_ctx_pinned(DcrCtx* c, size_t bytes) {
+    if (c->pinned_bytes < bytes) {
+        if (c->pinned) cudaFreeHost(c->pinned);
+        c->pinned = nullptr;
+        c->pinned_bytes = 0;
+        if (cudaHostAlloc(&c->pinned, bytes, cudaHostAllocDefault) != cudaSuccess) { c->pinned = nullptr; return nullptr; }
+        c->pinned_bytes = bytes;
+    }
+    return c->pinned;
+}
+
+int dcr_num_sms() {
+    DcrCtx* c = dcr_ctx();
+    return c ? c->sms : DCR_NSM_DEFAULT;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1001,10 +1022,11 @@ int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cuda
         }
     }
     const size_t smem = (size_t)(F_SRC_WORDS + F_REF_WORDS + F_SW_R * F_SW_C) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    DcrCtx* ctx = dcr_ctx();
+    if (!ctx) return -1;
+    if (!(ctx->attrs & DCR_ATTR_FRONT)) {   // per device
         DCR_CUDA_OK(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        ctx->attrs |= DCR_ATTR_FRONT;
     }
     dim3 grid((a->w + F_TW - 1) / F_TW, (p.row_end - p.row_begin + F_TH - 1) / F_TH);
     front_kernel<<<grid, 256, smem, stream>>>(p);

@@ -2,6 +2,26 @@
 #pragma once
 #include "dcr_common.cuh"
 
+// ---- per-(host thread, device) context (dcr_front.cu) ----
+// Everything the library caches between calls is keyed by the CURRENT device of the calling thread: SM count, the
+// >48 KB dynamic shared-memory opt-ins (cudaFuncSetAttribute is per device), the side streams / events of the iteration
+// and the pinned result block.  One process may therefore drive several GPUs (one host thread per GPU, or one thread
+// switching devices); there is no process-global mutable state.
+#define DCR_MAX_DEVICES 64
+enum { DCR_ATTR_FRONT = 1, DCR_ATTR_FBA = 2, DCR_ATTR_BSEL = 4 };
+struct DcrCtx {
+    int dev;                 // device ordinal this slot belongs to
+    int sms;                 // multiprocessors
+    unsigned attrs;          // DCR_ATTR_* opt-ins already done on this device
+    cudaStream_t s2, s3;     // side streams of the iteration (created on first use)
+    cudaEvent_t e_front, e_mask, e_join, e_join3, e_copy;
+    cudaEvent_t prof[8];     // DCR_ITER_PROFILE stage marks
+    void* pinned;            // pinned host block (result copies), pinned_bytes long
+    size_t pinned_bytes;
+};
+DcrCtx* dcr_ctx();           // context of the calling thread's current device; nullptr (+ error text) on failure
+void* dcr_ctx_pinned(DcrCtx* c, size_t bytes);   // pinned host scratch of at least `bytes` (grown on demand)
+
 // ---- front end (dcr_front.cu) ----
 // counters (device, 3 x u64, zeroed by the caller): base-valid, after max_dz, slope-valid
 // bin (device, h*w, optional): also emit the aspect-bin code of every pixel (DCR_BIN_INVALID outside the masks known to

@@ -643,11 +643,12 @@ static int nuth_bins_radix_enqueue(long long n, const NuthWs& w, int grid, cudaS
 }
 
 static int nuth_bins_fast_enqueue(long long n, const NuthWs& w, cudaStream_t s) {
-    static bool attr_set = false;
     const size_t smemA = (size_t)NB * FB_COARSE * sizeof(unsigned);
-    if (!attr_set) {
+    DcrCtx* ctx = dcr_ctx();
+    if (!ctx) return -1;
+    if (!(ctx->attrs & DCR_ATTR_FBA)) {   // per device
         DCR_CUDA_OK(cudaFuncSetAttribute(fb_passA_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
-        attr_set = true;
+        ctx->attrs |= DCR_ATTR_FBA;
     }
     const int nsm = dcr_num_sms();
     DCR_CUDA_OK(cudaMemsetAsync(w.ghist, 0, (size_t)FB_WORDS * sizeof(unsigned), s));
@@ -1152,17 +1153,19 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
     // concurrently -- the slope median right after the front kernel, and the strided-subsample chain (scan, stride,
     // compress, dz median) right after the mask update -- so that their latency-bound small kernels hide behind the
     // bandwidth-bound passes of the main stream.  Joined before the result copy.
-    static thread_local cudaStream_t s2 = nullptr, s3 = nullptr;
-    static thread_local cudaEvent_t e_front = nullptr, e_mask = nullptr, e_join = nullptr, e_join3 = nullptr;
+    DcrCtx* ctx = dcr_ctx();   // side streams / events belong to the current device of this thread
+    if (!ctx) return -1;
     const bool side = use_bsel != 0;
-    if (side && !s2) {
-        DCR_CUDA_OK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
-        DCR_CUDA_OK(cudaEventCreateWithFlags(&e_front, cudaEventDisableTiming));
-        DCR_CUDA_OK(cudaEventCreateWithFlags(&e_mask, cudaEventDisableTiming));
-        DCR_CUDA_OK(cudaEventCreateWithFlags(&e_join, cudaEventDisableTiming));
-        DCR_CUDA_OK(cudaStreamCreateWithFlags(&s3, cudaStreamNonBlocking));
-        DCR_CUDA_OK(cudaEventCreateWithFlags(&e_join3, cudaEventDisableTiming));
+    if (side && !ctx->s2) {
+        DCR_CUDA_OK(cudaStreamCreateWithFlags(&ctx->s2, cudaStreamNonBlocking));
+        DCR_CUDA_OK(cudaEventCreateWithFlags(&ctx->e_front, cudaEventDisableTiming));
+        DCR_CUDA_OK(cudaEventCreateWithFlags(&ctx->e_mask, cudaEventDisableTiming));
+        DCR_CUDA_OK(cudaEventCreateWithFlags(&ctx->e_join, cudaEventDisableTiming));
+        DCR_CUDA_OK(cudaStreamCreateWithFlags(&ctx->s3, cudaStreamNonBlocking));
+        DCR_CUDA_OK(cudaEventCreateWithFlags(&ctx->e_join3, cudaEventDisableTiming));
     }
+    const cudaStream_t s2 = ctx->s2, s3 = ctx->s3;
+    const cudaEvent_t e_front = ctx->e_front, e_mask = ctx->e_mask, e_join = ctx->e_join, e_join3 = ctx->e_join3;
     cudaStream_t sb = side ? s2 : s;      // stream of the side work
     IterWs wb = w;                        // side selections use their own scratch
     if (side) wb.bsel_scratch = w.bsel_scratch2;
@@ -1242,8 +1245,9 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
 }
 
 // host part of an iteration: counts, guards, bin selection, fit, shift (coreglib.py:206-305, dem_align.py:150-172)
-static int iter_finalize(const IterDev* hd, int engine_used, dcr_iter_result* out) {
+static int iter_finalize(const IterDev* hd, int engine_used, dcr_iter_result* out, int bin_engine = 0) {
     out->select_engine = engine_used;
+    out->bin_engine = bin_engine;
     float selres[5];
     for (int k = 0; k < 5; ++k) selres[k] = engine_used ? hd->bsel[k].result : hd->sel[k].result;
     out->count_base = (int64_t)hd->counters[0];
@@ -1305,7 +1309,9 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_it
     DCR_ARG(front && out && workspace, "null pointer");
     const int remove_outliers = (flags & DCR_ITER_REMOVE_OUTLIERS) ? 1 : 0;
     const bool prof = (flags & DCR_ITER_PROFILE) != 0;
-    static thread_local cudaEvent_t ev[8] = {nullptr};
+    DcrCtx* ctx = dcr_ctx();
+    if (!ctx) return -1;
+    cudaEvent_t* ev = ctx->prof;
     if (prof && !ev[0])
         for (int k = 0; k < 8; ++k) DCR_CUDA_OK(cudaEventCreate(&ev[k]));
     const long long n = (long long)front->h * front->w;
@@ -1329,9 +1335,10 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_it
     w.nw.nd = &w.d->nuth;
     IterDev* d = w.d;
 
-    static thread_local IterDev* hd = nullptr;
-    if (!hd) DCR_CUDA_OK(cudaHostAlloc((void**)&hd, sizeof(IterDev), cudaHostAllocDefault));
+    IterDev* hd = (IterDev*)dcr_ctx_pinned(ctx, sizeof(IterDev));
+    if (!hd) { dcr_set_error("pinned host allocation failed"); return -1; }
     int engine_used = (flags & DCR_ITER_RADIX_ONLY) ? 0 : 1;
+    int bin_engine = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
         int rc = iteration_enqueue(front, remove_outliers, engine_used, w, grid, s, prof ? ev : nullptr,
                                    (flags & DCR_ITER_RADIX_ONLY) ? 0 : 1, (flags & DCR_ITER_APPLY_Z) ? 1 : 0);
@@ -1341,8 +1348,8 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_it
         if (flags & DCR_ITER_APPLY_Z) {
             // the result copy is already queued: wait for IT (event), not for the z-shift pass enqueued behind it --
             // the 0.1 ms read-modify-write of the source band then overlaps the host's fit and bookkeeping
-            static thread_local cudaEvent_t ev_copy = nullptr;
-            if (!ev_copy) DCR_CUDA_OK(cudaEventCreateWithFlags(&ev_copy, cudaEventDisableTiming));
+            if (!ctx->e_copy) DCR_CUDA_OK(cudaEventCreateWithFlags(&ctx->e_copy, cudaEventDisableTiming));
+            const cudaEvent_t ev_copy = ctx->e_copy;
             DCR_CUDA_OK(cudaEventRecord(ev_copy, s));
             const double zn = front->src_desc.ndv;
             zshift_dev_kernel<<<dcr_num_sms() * 8, 256, 0, s>>>(const_cast<float*>(front->src), front->src_desc.height,
@@ -1356,6 +1363,7 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_it
         if (hd->nuth.fast_fallback && getenv("DCR_DEBUG"))
             fprintf(stderr, "[dcr] fast bin path declined: ncand=%u scale=%g rmin=%g rmax=%g\n", hd->nuth.fast_ncand,
                     hd->nuth.fast_scale, hd->nuth.rmin, hd->nuth.rmax);
+        bin_engine = ((flags & DCR_ITER_RADIX_ONLY) || hd->nuth.fast_fallback) ? 0 : 1;
         if (hd->nuth.fast_fallback) {
             // fast bin path declined (heavy ties / degenerate 3-sigma range): exact 3-pass radix bins, same inputs
             if ((rc = nuth_bins_radix_enqueue(n, w.nw, grid, s))) return rc;
@@ -1384,7 +1392,7 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_it
     if (prof)
         for (int k = 0; k < 7; ++k) DCR_CUDA_OK(cudaEventElapsedTime(&out->stage_ms[k], ev[k], ev[k + 1]));
     {
-        const int rcf = iter_finalize(hd, engine_used, out);
+        const int rcf = iter_finalize(hd, engine_used, out, bin_engine);
         out->z_applied = ((flags & DCR_ITER_APPLY_Z) && !isnan(out->dz_med)) ? 1 : 0;
         return rcf;
     }
@@ -1407,7 +1415,7 @@ extern "C" int dcr_align_flush_z(dcr_align_state* st, void* stream) {
 extern "C" int dcr_align_nuth(dcr_align_state* st, int max_steps, int flags, dcr_align_iter* iters, int iters_cap,
                               int* n_iters, void* workspace, size_t workspace_bytes, void* stream) {
     DCR_ARG(st && workspace, "null pointer");
-    DCR_ARG(st->ref && st->src && st->dh && st->slope && st->aspect && st->maskbits, "null raster pointer");
+    DCR_ARG(st->ref && st->src && st->dh && st->slope && st->maskbits, "null raster pointer");
     DCR_ARG(st->src_ndz >= 0 && st->src_ndz <= 16, "0 <= src_ndz <= 16");
     int done_here = 0;
     if (n_iters) *n_iters = 0;
@@ -1447,6 +1455,7 @@ extern "C" int dcr_align_nuth(dcr_align_state* st, int max_steps, int flags, dcr
             dcr_align_iter& it = iters[done_here];
             it.dx = r.dx; it.dy = r.dy; it.dz = r.dz; it.status = r.status; it.select_engine = r.select_engine;
             it.h = grid.height; it.w = grid.width;
+            it.bin_engine = r.bin_engine; it._pad = 0;
             it.fit[0] = r.fit[0]; it.fit[1] = r.fit[1]; it.fit[2] = r.fit[2];
             it.dz_med = r.dz_med; it.med_slope = r.med_slope;
         }
@@ -1694,8 +1703,10 @@ extern "C" int dcr_band_result(const dcr_front_args* front, void* workspace, siz
     IterWs w;
     if (band_carve(workspace, workspace_bytes, n, grid, &w)) return -1;
     cudaStream_t s = (cudaStream_t)stream;
-    static thread_local IterDev* hd = nullptr;
-    if (!hd) DCR_CUDA_OK(cudaHostAlloc((void**)&hd, sizeof(IterDev), cudaHostAllocDefault));
+    DcrCtx* ctx = dcr_ctx();
+    if (!ctx) return -1;
+    IterDev* hd = (IterDev*)dcr_ctx_pinned(ctx, sizeof(IterDev));
+    if (!hd) { dcr_set_error("pinned host allocation failed"); return -1; }
     DCR_CUDA_OK(cudaMemcpyAsync(hd, w.d, sizeof(IterDev), cudaMemcpyDeviceToHost, s));
     DCR_CUDA_OK(cudaStreamSynchronize(s));
     memset(out, 0, sizeof(*out));

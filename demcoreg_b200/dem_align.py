@@ -127,6 +127,18 @@ def compute_offset(ref_dem_ds, src_dem_ds, src_dem_fn, mode='nuth', remove_outli
     raise ValueError(mode)
 
 
+def _looks_geographic(ds):
+    """True when the dataset is evidently in geographic coordinates (degrees): GEOGCS / longlat projection string, or
+    pixels smaller than 0.05 units on an origin inside +-360 / +-90."""
+    pr = (ds.proj or '').strip().upper()
+    if pr.startswith('GEOGCS') or pr.startswith('GEOGCRS') or '+PROJ=LONGLAT' in pr:
+        return True
+    if pr.startswith('PROJCS') or pr.startswith('PROJCRS') or pr.startswith('LOCAL_CS'):
+        return False
+    gt = ds.gt
+    return abs(gt[1]) < 0.05 and abs(gt[0]) <= 360.0 and abs(gt[3]) <= 90.0
+
+
 def getparser():
     """Reference ``dem_align.py:174-201``: same options, names and defaults."""
     parser = argparse.ArgumentParser(description="Perform DEM co-registration using multiple algorithms",
@@ -332,6 +344,15 @@ def main(argv=None):
 
     ref = rio.read_raster(ref_dem_fn)
     src = rio.read_raster(src_dem_fn)
+    # dem_align.py:270-289: inputs must be in a projected CRS with linear units of metres.  There is no PROJ here; the
+    # projection string and the geotransform decide (degrees-sized pixels inside +-360 / +-90)
+    for fn, ds in ((ref_dem_fn, ref), (src_dem_fn, src)):
+        if _looks_geographic(ds):
+            print("%s CRS: '%s'" % (fn, ds.proj))
+            print("Input DEMs must have projected CRS with linear units of meters (not WGS84 geographic, units of degrees)")
+            print("For relatively limited DEM extents (<100-300 km), you can consider reprojecting using the appropriate UTM projection")
+            print("Then rerun the dem_align.py command with the projected DEM(s)\n")
+            sys.exit()
     mask_source = None
     if args.mask_fn:
         m = rio.read_array(args.mask_fn)
@@ -339,6 +360,18 @@ def main(argv=None):
     elif args.mask_list:
         get_mask(None, args.mask_list)
 
+    if mode == 'none':
+        # dem_align.py:166-170 (its names outprefix / src_dem_orig are undefined inside compute_offset, so the reference itself
+        # dies with a NameError here): what it announces -- the source with the median bias over static surfaces removed
+        res0, _, _ = engine.nuth_iteration(ref, src, mask_source, True, args.max_dz, slope_lim)
+        if res0.status in _EXIT_MSG:
+            sys.exit(_EXIT_MSG[res0.status])
+        dz = np.float32(res0.dz_med)
+        print("Skipping alignment, writing out DEM with median bias over static surfaces removed")
+        dst_fn = outprefix + '_med%0.1f.tif' % dz
+        sa = coreglib.apply_z_shift(src, -dz, createcopy=True)
+        rio.write_raster(dst_fn, sa.numpy(), sa.gt, sa.ndv, sa.proj)
+        sys.exit()
     out = align(ref, src, mode=mode, mask_source=mask_source, tol=args.tol, max_offset=args.max_offset,
                 max_dz=args.max_dz, slope_lim=slope_lim, max_iter=args.max_iter, tiltcorr=tiltcorr, polyorder=polyorder)
     dx_total, dy_total, dz_total = out['dx'], out['dy'], out['dz']

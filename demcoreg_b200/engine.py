@@ -20,12 +20,14 @@ def _stream_ptr(torch):
 
 def workspace(nbytes, device=None):
     """A cached uint8 device tensor of at least ``nbytes`` (grown on demand) for the C-ABI scratch."""
+    import threading
     torch = _lib.require_cuda()
     dev = torch.cuda.current_device() if device is None else device
-    t = _ws_cache.get(dev)
+    key = (threading.get_ident(), dev)   # one scratch per (host thread, device): calls on it are stream-ordered
+    t = _ws_cache.get(key)
     if t is None or t.numel() < nbytes:
-        t = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda")
-        _ws_cache[dev] = t
+        t = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda:%d" % dev)
+        _ws_cache[key] = t
     return t
 
 
@@ -125,13 +127,26 @@ class NuthAligner(object):
     per loop -- or per iteration (``step``) -- through ``dcr_align_nuth``.
 
     ``src`` is shifted IN PLACE: its geotransform after every iteration, its band through deferred z shifts that the
-    front kernel applies while loading (``Raster.pending_dz``; ``Raster.data`` / ``finish()`` fold them into the band).
+    front kernel applies while loading.  The native state (``dcr_align_state.src_dz``) is the ONLY owner of those pending
+    shifts: ``run()`` / ``step()`` fold them into the band before they return, so that ``src`` is always consistent
+    (band, geotransform, no ``Raster.pending_dz``) when the interpreter looks at it.
+
+    One aligner can serve a whole batch of pairs (``reset``): the iteration outputs, the workspace and the record
+    array are allocated once and reused.
     """
 
     def __init__(self, ref, src, mask_source=None, tol=0.02, max_offset=100, max_dz=100, slope_lim=(0.1, 40), max_iter=30,
                  remove_outliers=True):
-        torch = _lib.require_cuda()
         self.L = _lib.lib()
+        self.cap = 0
+        self._iters = (_lib.AlignIter * 64)()
+        self._n = C.c_int(0)
+        self.reset(ref, src, mask_source, tol, max_offset, max_dz, slope_lim, max_iter, remove_outliers)
+
+    def reset(self, ref, src, mask_source=None, tol=0.02, max_offset=100, max_dz=100, slope_lim=(0.1, 40), max_iter=30,
+              remove_outliers=True):
+        """Point the loop at a new pair (fresh loop state); device buffers are kept when they are large enough."""
+        torch = _lib.require_cuda()
         self.ref, self.src, self.mask_source = ref, src, mask_source
         st = self.st = _lib.AlignState()
         st.ref = ref.data.data_ptr()
@@ -147,58 +162,67 @@ class NuthAligner(object):
             st.smask_desc = mask_source.desc()
         h = min(ref.RasterYSize, src.RasterYSize) + 2
         w = min(ref.RasterXSize, src.RasterXSize) + 2
-        self.cap = h * w
-        self._dh = torch.empty(self.cap, dtype=torch.float32, device="cuda")
-        self._slope = torch.empty(self.cap, dtype=torch.float32, device="cuda")
-        self._aspect = torch.empty(self.cap, dtype=torch.float32, device="cuda")
-        self._maskbits = torch.empty(self.cap, dtype=torch.uint8, device="cuda")
-        st.dh, st.slope, st.aspect, st.maskbits = (self._dh.data_ptr(), self._slope.data_ptr(), self._aspect.data_ptr(),
-                                                   self._maskbits.data_ptr())
+        if h * w > self.cap:
+            self.cap = h * w
+            self._dh = torch.empty(self.cap, dtype=torch.float32, device="cuda")
+            self._slope = torch.empty(self.cap, dtype=torch.float32, device="cuda")
+            self._maskbits = torch.empty(self.cap, dtype=torch.uint8, device="cuda")
+            self.ws = workspace(self.L.dcr_iteration_workspace_bytes(self.cap))
+        # (no aspect raster: nothing in the loop reads it -- the aspect-bin codes travel in the workspace)
+        st.dh, st.slope, st.aspect, st.maskbits = self._dh.data_ptr(), self._slope.data_ptr(), None, self._maskbits.data_ptr()
         st.out_capacity = self.cap
         st.tol, st.max_offset = float(tol), float(max_offset)
         st.max_dz, st.slope_lo, st.slope_hi = float(max_dz), float(slope_lim[0]), float(slope_lim[1])
         st.max_iter = int(max_iter)
         st.remove_outliers = 1 if remove_outliers else 0
-        self.ws = workspace(self.L.dcr_iteration_workspace_bytes(self.cap))
-        self._iters = (_lib.AlignIter * (min(max(1, int(max_iter)), 1024) + 2))()
         self.grid_hw = (0, 0)
-        self._n = C.c_int(0)
         self.iters = []
+        return self
 
-    def _sync_src(self):
-        st = self.st
-        self.src.gt = tuple(st.src_desc.gt[k] for k in range(6))
-        self.src.pending_dz = [st.src_dz[k] for k in range(st.src_ndz)]
+    def _publish(self):
+        """Fold the pending z shifts into the band and publish the geotransform: ``src`` is consistent again."""
+        torch = _lib.require_cuda()
+        _lib.check(self.L.dcr_align_flush_z(C.byref(self.st), _stream_ptr(torch)))
+        self.src.gt = tuple(self.st.src_desc.gt[k] for k in range(6))
+        self.src.pending_dz = []
 
     def run(self, max_steps=0, profile=False, radix_only=False):
-        """Run the loop to the end (``max_steps=0``) or at most ``max_steps`` iterations; returns the records of the
-        iterations this call ran (``_lib.AlignIter``: dx, dy, dz, status, grid size)."""
+        """Run the loop to the end (``max_steps=0``) or exactly ``max_steps`` further iterations (fewer if it stops);
+        returns the records of the iterations this call ran (dx, dy, dz, status, grid size, engines)."""
         torch = _lib.require_cuda()
         flags = (_lib.ITER_PROFILE if profile else 0) | (_lib.ITER_RADIX_ONLY if radix_only else 0)
-        _lib.check(self.L.dcr_align_nuth(C.byref(self.st), int(max_steps), flags, self._iters, len(self._iters),
-                                         C.byref(self._n), C.c_void_p(self.ws.data_ptr()), self.ws.numel(),
-                                         _stream_ptr(torch)))
-        self._sync_src()
-        out = [dict(n=len(self.iters) + k + 1, dx=it.dx, dy=it.dy, dz=it.dz, status=it.status, h=it.h, w=it.w,
-                    select_engine=it.select_engine, fit=(it.fit[0], it.fit[1], it.fit[2]), dz_med=it.dz_med,
-                    med_slope=it.med_slope) for k, it in enumerate(self._iters[:self._n.value])]
+        out = []
+        left = int(max_steps)
+        cap = len(self._iters)
+        while True:
+            chunk = cap if left <= 0 else min(left, cap)   # the record array bounds one native call, not the loop
+            _lib.check(self.L.dcr_align_nuth(C.byref(self.st), chunk, flags, self._iters, cap, C.byref(self._n),
+                                             C.c_void_p(self.ws.data_ptr()), self.ws.numel(), _stream_ptr(torch)))
+            n = self._n.value
+            for it in self._iters[:n]:
+                out.append(dict(n=len(self.iters) + len(out) + 1, dx=it.dx, dy=it.dy, dz=it.dz, status=it.status, h=it.h,
+                                w=it.w, select_engine=it.select_engine, bin_engine=it.bin_engine,
+                                fit=(it.fit[0], it.fit[1], it.fit[2]), dz_med=it.dz_med, med_slope=it.med_slope))
+            if left > 0:
+                left -= n
+                if left <= 0:
+                    break
+            if n < chunk or self.st.finished or self.st.exit_code:
+                break
+        if out:
+            self.grid_hw = (out[-1]['h'], out[-1]['w'])
+        self._publish()
         self.iters.extend(out)
         return out
 
     def step(self, profile=False):
         """Exactly one iteration (compute_offset + apply_xy_shift + apply_z_shift); returns the last ``IterResult``."""
-        torch = _lib.require_cuda()
-        flags = _lib.ITER_PROFILE if profile else 0
-        _lib.check(self.L.dcr_align_nuth(C.byref(self.st), 1, flags, self._iters, 1, None, C.c_void_p(self.ws.data_ptr()),
-                                         self.ws.numel(), _stream_ptr(torch)))
-        self.grid_hw = (self._iters[0].h, self._iters[0].w)
+        self.run(max_steps=1, profile=profile)
         return self.st.last
 
     def finish(self):
-        """Fold the pending z shifts into the band and publish the geotransform on ``src``."""
-        torch = _lib.require_cuda()
-        _lib.check(self.L.dcr_align_flush_z(C.byref(self.st), _stream_ptr(torch)))
-        self._sync_src()
+        """``src`` with every shift applied (``run`` / ``step`` already publish; kept for callers of the old protocol)."""
+        self._publish()
         return self.src
 
     @property
@@ -387,8 +411,11 @@ def ncc_corr(ref, ref_mask, src, src_mask, pad, ref_noise=None, kernel_noise=Non
     return np.array(m[:], dtype=np.float64).reshape(J, J), tuple(stats[:])
 
 
-def sad_search(ref, ref_mask, src, src_mask, pad):
-    """``dcr_sad_search``: IQR-trimmed mean absolute difference for every offset (float64, (2p+1)^2)."""
+def sad_search(ref, ref_mask, src, src_mask, pad, per_offset=False, info=None):
+    """``dcr_sad_search_ex``: IQR-trimmed mean absolute difference for every offset (float64, (2p+1)^2).
+
+    ``per_offset=True`` forces the exact per-offset path (the fallback of the batched kernels) for every offset;
+    ``info`` (dict) receives ``n_per_offset`` and the CUDA-event ``stage_ms`` of the batched stages."""
     torch = _lib.require_cuda()
     L = _lib.lib()
     h, w = int(ref.shape[0]), int(ref.shape[1])
@@ -398,9 +425,16 @@ def sad_search(ref, ref_mask, src, src_mask, pad):
     ws = workspace(L.dcr_sad_workspace_bytes(h, w, pad))
     rm = ref_mask.to(torch.uint8).contiguous() if ref_mask is not None else None
     sm = src_mask.to(torch.uint8).contiguous() if src_mask is not None else None
+    nfb = C.c_int(0)
+    stage = (C.c_float * 6)()
 
     def ptr(t):
         return C.c_void_p(t.data_ptr()) if t is not None else None
-    _lib.check(L.dcr_sad_search(ptr(ref), ptr(rm), ptr(src), ptr(sm), h, w, w, int(pad), m,
-                                C.c_void_p(ws.data_ptr()), ws.numel(), _stream_ptr(torch)))
+    _lib.check(L.dcr_sad_search_ex(ptr(ref), ptr(rm), ptr(src), ptr(sm), h, w, w, int(pad),
+                                   _lib.SAD_PER_OFFSET if per_offset else 0, m, C.byref(nfb),
+                                   stage if (info is not None and not per_offset) else None,
+                                   C.c_void_p(ws.data_ptr()), ws.numel(), _stream_ptr(torch)))
+    if info is not None:
+        info['n_per_offset'] = int(nfb.value)
+        info['stage_ms'] = dict(zip(("prep", "sample", "pass1", "find", "pass2", "final"), [float(v) for v in stage]))
     return np.array(m[:], dtype=np.float64).reshape(J, J)

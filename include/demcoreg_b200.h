@@ -182,10 +182,19 @@ int dcr_ncc_corr(const float* ref, const uint8_t* ref_mask, const float* src, co
 /* ---- K7b: SAD offset search -------------------------------------------------------------------
  * coreglib.compute_offset_sad <- coreglib.py:65-115: for every offset, diff = ref window - kernel (float32),
  * trim outside its [P25, P75] (exact percentiles, malib.calcperc), m = sum|diff| / count.
- * m_out (host): (2p+1)^2 float64 of the mean absolute difference (the caller negates it, coreglib.py:100). */
+ * m_out (host): (2p+1)^2 float64 of the mean absolute difference (the caller negates it, coreglib.py:100).
+ * All (2p+1)^2 offsets go through the same few passes over the rasters (batched; see dcr_sad.cu); an offset whose
+ * on-device verification fails (heavy ties, degenerate distribution) is redone by the exact per-offset path. */
 size_t dcr_sad_workspace_bytes(int h, int w, int pad);
 int dcr_sad_search(const float* ref, const uint8_t* ref_mask, const float* src, const uint8_t* src_mask, int h, int w,
                    int64_t stride, int pad, double* m_out, void* workspace, size_t workspace_bytes, void* stream);
+/* The same with flags (DCR_SAD_PER_OFFSET: every offset through the exact per-offset path -- materialised diff + two K3
+ * selections, the fallback of the batched path), the number of offsets that took the per-offset path (n_per_offset, may be
+ * NULL) and, when stage_ms != NULL, the CUDA-event times of the 6 batched stages: prep, sample, pass 1, find, pass 2, final. */
+#define DCR_SAD_PER_OFFSET 1
+int dcr_sad_search_ex(const float* ref, const uint8_t* ref_mask, const float* src, const uint8_t* src_mask, int h, int w,
+                      int64_t stride, int pad, int flags, double* m_out, int* n_per_offset, float* stage_ms /* [6] or NULL */,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- fit (host) -----------------------------------------------------------------------------
  * scipy.optimize.curve_fit(nuth_func, bin_centers, bin_med, x0) <- coreglib.py:305 with
@@ -227,6 +236,8 @@ typedef struct dcr_iter_result {
                                     5 bin count+median passes, 6 device->host copy */
     int32_t select_engine;       /* 1: one-pass sample-bracket selects verified ok; 0: 3-pass radix selects (fallback) */
     int32_t z_applied;           /* DCR_ITER_APPLY_Z: the source band has already been shifted by `dz` on the device */
+    int32_t bin_engine;          /* 1: two-pass shared-memory bin statistics; 0: 3-pass radix bins (heavy ties / degenerate range) */
+    int32_t _pad;
 } dcr_iter_result;
 #define DCR_ITER_REMOVE_OUTLIERS 1 /* flags of dcr_nuth_iteration: dem_align.py:91 remove_outliers */
 #define DCR_ITER_PROFILE 2         /* record per-stage CUDA events into stage_ms */
@@ -251,6 +262,7 @@ typedef struct dcr_align_iter {
     int32_t status;              /* dcr_iter_result.status */
     int32_t select_engine;
     int32_t h, w;                /* common grid of the iteration */
+    int32_t bin_engine, _pad;    /* dcr_iter_result.bin_engine */
     double fit[3];               /* a, b (deg), c of the iteration (NaN when status == 4) */
     float dz_med, med_slope;     /* for the reference's per-iteration 'Median dz / Nuth dz' message (dem_align.py:157-159) */
 } dcr_align_iter;
@@ -259,7 +271,8 @@ typedef struct dcr_align_state {
     const float* ref; int64_t ref_stride; dcr_raster_desc ref_desc;
     float* src; int64_t src_stride; dcr_raster_desc src_desc;                 /* shifted in place */
     const uint8_t* smask; int64_t smask_stride; dcr_raster_desc smask_desc;   /* world-fixed static mask or NULL */
-    float* dh; float* slope; float* aspect; uint8_t* maskbits;                /* iteration outputs, out_capacity pixels each */
+    float* dh; float* slope; float* aspect; uint8_t* maskbits;                /* iteration outputs, out_capacity pixels each;
+                                                                                 aspect may be NULL (nothing in the loop reads it) */
     int64_t out_capacity;
     double tol, max_offset;      /* dem_align.py -tol, -max_offset */
     float max_dz, slope_lo, slope_hi;

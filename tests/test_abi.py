@@ -147,3 +147,15 @@ def test_cli_parser_matches_reference_options():
             a.max_iter, a.outdir) == ('nuth', [], False, 1, 0.02, 100, 100, 'mean', (0.1, 40), 30, None)
     a = p.parse_args(["r", "s", "-mode", "ncc", "-max_offset", "200", "-res", "min", "-slope_lim", "1", "30"])
     assert a.mode == 'ncc' and a.max_offset == 200 and a.res == 'min' and a.slope_lim == [1.0, 30.0]
+
+
+def test_reference_import_name_resolves():
+    """``from demcoreg import coreglib`` (reference ``demcoreg/__init__.py:3``, ``dem_align.py:19``) resolves to the shim."""
+    import demcoreg
+    from demcoreg import coreglib
+    import demcoreg.dem_align as da
+    from demcoreg_b200 import coreglib as c2
+    assert coreglib is c2 and da.getparser().parse_args(['a.tif', 'b.tif']).mode == 'nuth'
+    for name in ('compute_offset_nuth', 'compute_offset_ncc', 'compute_offset_sad', 'apply_xy_shift', 'apply_z_shift',
+                 'nuth_func', 'find_subpixel_peak_position'):
+        assert callable(getattr(coreglib, name))

@@ -393,6 +393,55 @@ def test_sad_matches_oracle(cuda, masked):
     np.testing.assert_allclose(so, soo, atol=1e-4)
 
 
+@pytest.mark.parametrize("masked", [False, True])
+def test_sad_batched_equals_per_offset(cuda, masked):
+    """The batched SAD kernels (sample brackets, two passes over all offsets) vs the exact per-offset path (materialised
+    diff + two radix selections per offset) on a raster larger than the sample, ragged tile edges."""
+    from demcoreg_b200 import coreglib, engine
+    p = 5
+    ref, src = _ncc_pair(n=731, p=p, masked=masked)
+    d1, m1 = coreglib._to_device_masked(ref)
+    d2, m2 = coreglib._to_device_masked(src)
+    info = {}
+    mb = engine.sad_search(d1, m1, d2, m2, p, info=info)
+    mo = engine.sad_search(d1, m1, d2, m2, p, per_offset=True)
+    assert info['n_per_offset'] == 0
+    np.testing.assert_allclose(mb, mo, rtol=1e-6)
+
+
+def test_sad_heavy_ties_take_the_per_offset_path(cuda):
+    """Quantised rasters: thousands of equal differences around the quartiles -> the batched path declines those offsets
+    (candidate overflow / degenerate bracket) and the exact per-offset path answers; the map still equals the oracle's."""
+    from demcoreg_b200 import coreglib, engine
+    from oracle import coreglib as ocl
+    p = 2
+    ref, src = _ncc_pair(n=300, p=p, masked=True)
+    ref = np.ma.array(np.round(ref.data / 4) * 4, mask=ref.mask).astype(np.float32)
+    src = np.ma.array(np.round(src.data / 4) * 4, mask=src.mask).astype(np.float32)
+    d1, m1 = coreglib._to_device_masked(ref)
+    d2, m2 = coreglib._to_device_masked(src)
+    info = {}
+    mb = engine.sad_search(d1, m1, d2, m2, p, info=info)
+    assert info['n_per_offset'] > 0
+    mo, _, _ = ocl.compute_offset_sad(ref, src, pad=(p, p))
+    np.testing.assert_allclose(-mb, mo, rtol=2e-6)
+
+
+@pytest.mark.parametrize("p,n", [(30, 340), (51, 420)])
+def test_ncc_large_search_window(cuda, p, n):
+    """Search radii beyond one CTA's offset rows (dem_align -max_offset 100 at 2 m needs pad 51): blocks of offset rows."""
+    from demcoreg_b200 import coreglib
+    from oracle import coreglib as ocl
+    ref, src = _ncc_pair(n=n, p=p, masked=True)
+    rng = np.random.default_rng(3)
+    noise = (rng.standard_normal(ref.shape), rng.standard_normal((ref.shape[0] - 2 * p, ref.shape[1] - 2 * p)))
+    m, io, so, _ = coreglib.compute_offset_ncc(ref, src, pad=(p, p), noise=noise)
+    mo, ioo, soo, _ = ocl.compute_offset_ncc(ref, src, pad=(p, p), noise=noise)
+    np.testing.assert_allclose(m, mo, rtol=0, atol=2e-6 * np.abs(mo).max())
+    assert tuple(io) == tuple(ioo)
+    np.testing.assert_allclose(so, soo, atol=1e-4)
+
+
 @pytest.mark.parametrize("mode", ["ncc", "sad"])
 def test_dem_align_corr_modes(cuda, mode):
     """dem_align.compute_offset(mode='ncc'|'sad') vs the oracle's (noise injected for NCC)."""
