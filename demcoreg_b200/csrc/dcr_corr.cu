@@ -21,21 +21,38 @@
 // ------------------------------------------------------------------------------------------
 struct WinPartial { unsigned long long n; double s, ss; };
 
+// rows r0.., columns c0.. of x (and of its mask): warp = one row at a time, lanes stride the columns (no per-element
+// integer division; 4 independent loads in flight per lane)
 __global__ void __launch_bounds__(256) win_moments_kernel(const float* __restrict__ x, const unsigned char* __restrict__ m,
                                                           long long xstride, long long mstride, int r0, int c0, int h, int w,
                                                           WinPartial* __restrict__ part) {
     __shared__ WinPartial sp[8];
     unsigned long long cnt = 0;
     double s = 0, ss = 0;
-    const long long n = (long long)h * w;
-    for (long long k = (long long)blockIdx.x * 256 + threadIdx.x; k < n; k += (long long)gridDim.x * 256) {
-        const int i = (int)(k / w), j = (int)(k - (long long)i * w);
-        if (m && m[(long long)(r0 + i) * mstride + c0 + j]) continue;
-        const double v = (double)x[(long long)(r0 + i) * xstride + c0 + j];
-        ++cnt; s += v; ss += v * v;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * 8;
+    for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < h; i += nwarps) {
+        const float* xr = x + (long long)(r0 + i) * xstride + c0;
+        const unsigned char* mr = m ? m + (long long)(r0 + i) * mstride + c0 : nullptr;
+        for (int j0 = lane; j0 < w; j0 += 128) {
+            float v[4];
+            unsigned char mk[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + 32 * u;
+                v[u] = j < w ? xr[j] : 0.0f;
+                mk[u] = j < w ? (mr ? mr[j] : (unsigned char)0) : (unsigned char)1;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (mk[u]) continue;
+                const double d = (double)v[u];
+                ++cnt; s += d; ss += d * d;
+            }
+        }
     }
     cnt = dcr_warp_sum_u64(cnt); s = dcr_warp_sum(s); ss = dcr_warp_sum(ss);
-    if ((threadIdx.x & 31) == 0) { WinPartial q; q.n = cnt; q.s = s; q.ss = ss; sp[threadIdx.x >> 5] = q; }
+    if (lane == 0) { WinPartial q; q.n = cnt; q.s = s; q.ss = ss; sp[threadIdx.x >> 5] = q; }
     __syncthreads();
     if (threadIdx.x == 0) {
         WinPartial q = sp[0];
@@ -44,11 +61,13 @@ __global__ void __launch_bounds__(256) win_moments_kernel(const float* __restric
     }
 }
 
-// stats[0] = mean, stats[1] = std (ddof = 0), stats[2] = count
+// one warp, fixed order: lane l sums partials l, l + 32, ...; then the shuffle tree.  stats[0] = mean, [1] = std (ddof = 0),
+// [2] = count
 __global__ void win_moments_final_kernel(const WinPartial* __restrict__ part, int nparts, double* stats) {
-    if (threadIdx.x) return;
     unsigned long long n = 0; double s = 0, ss = 0;
-    for (int k = 0; k < nparts; ++k) { n += part[k].n; s += part[k].s; ss += part[k].ss; }
+    for (int k = threadIdx.x; k < nparts; k += 32) { n += part[k].n; s += part[k].s; ss += part[k].ss; }
+    n = dcr_warp_sum_u64(n); s = dcr_warp_sum(s); ss = dcr_warp_sum(ss);
+    if (threadIdx.x) return;
     const double mean = n ? s / (double)n : 0.0;
     double var = n ? ss / (double)n - mean * mean : 0.0;
     if (var < 0) var = 0;
@@ -61,13 +80,19 @@ __global__ void __launch_bounds__(256) zscore_kernel(const float* __restrict__ x
                                                      const double* __restrict__ stats, const float* __restrict__ noise,
                                                      float* __restrict__ z) {
     const double mean = stats[0], sd = stats[1];
-    const long long n = (long long)h * w;
-    for (long long k = (long long)blockIdx.x * 256 + threadIdx.x; k < n; k += (long long)gridDim.x * 256) {
-        const int i = (int)(k / w), j = (int)(k - (long long)i * w);
-        float o;
-        if (m && m[(long long)(r0 + i) * mstride + c0 + j]) o = noise ? noise[k] : 0.0f;
-        else o = (float)(((double)x[(long long)(r0 + i) * xstride + c0 + j] - mean) / sd);
-        z[k] = o;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * 8;
+    for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < h; i += nwarps) {
+        const float* xr = x + (long long)(r0 + i) * xstride + c0;
+        const unsigned char* mr = m ? m + (long long)(r0 + i) * mstride + c0 : nullptr;
+        const float* nr = noise ? noise + (long long)i * w : nullptr;
+        float* zr = z + (long long)i * w;
+        for (int j = lane; j < w; j += 32) {
+            float o;
+            if (mr && mr[j]) o = nr ? nr[j] : 0.0f;
+            else o = (float)(((double)xr[j] - mean) / sd);
+            zr[j] = o;
+        }
     }
 }
 

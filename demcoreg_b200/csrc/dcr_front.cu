@@ -252,7 +252,7 @@ __device__ __noinline__ float bilinear_fallback(float ul, float ur, float lr, fl
 // Returns false when any input is NaN (nodata).  aspect = NaN for flat.
 __device__ __noinline__ bool horn(float w0, float w1, float w2, float w3, float w4, float w5, float w6,
                                      float w7, float w8, double ewres, double nsres, bool want_slope,
-                                     bool want_aspect, float* slope, float* aspect) {
+                                     bool want_aspect, float* slope, float* aspect, float* tan_slope = nullptr) {
     (void)w4;
     float s = ((w0 + w1) + (w2 + w3)) + ((w4 + w5) + (w6 + w7)) + w8;  // NaN probe only
     if (isnan(s)) return false;
@@ -267,6 +267,7 @@ __device__ __noinline__ bool horn(float w0, float w1, float w2, float w3, float 
         double dy = (double)dyf / nsres;
         double key = dx * dx + dy * dy;
         *slope = (float)(atan(sqrt(key) / 8.0) * (180.0 / M_PI));
+        if (tan_slope) *tan_slope = (float)(sqrt(key) / 8.0);
     }
     if (want_aspect) {
         const float dxf = b - a;
@@ -304,7 +305,8 @@ __device__ __forceinline__ float atan01(float t) {
 // the FP64 formulation above.  Returns false when any input is NaN; *exact = true -> caller must call horn().
 __device__ __forceinline__ bool horn_fast(float w0, float w1, float w2, float w3, float w4, float w5, float w6,
                                           float w7, float w8, float c, float d, float inv8ew, float inv8ns, float slope_mid,
-                                          float slope_half, float slope_tol, float* slope, float* aspect, bool* exact) {
+                                          float slope_half, float slope_tol, float* slope, float* aspect, bool* exact,
+                                          float* tan_slope = nullptr) {
     // c = (w6 + w7 + w7 + w8), d = (w0 + w1 + w1 + w2): the row sums slide down the column with the window (the top row
     // of this window was the bottom row two pixels ago), so the caller carries them instead of re-adding them
     (void)w1; (void)w7;
@@ -318,6 +320,7 @@ __device__ __forceinline__ bool horn_fast(float w0, float w1, float w2, float w3
     // MUFU.SQRT (sqrt.approx, <= 1 ulp-class) instead of the IEEE sqrtf sequence: the guard bands below absorb it
     float g;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(gx * gx + gy * gy));
+    if (tan_slope) *tan_slope = g;
     const bool big = g > 1.0f;
     float sa = atan01(big ? __fdividef(1.0f, g) : g);
     if (big) sa = 1.5707963267948966f - sa;
@@ -488,6 +491,15 @@ struct FrontParams {
     float* src_w;
     unsigned short* bin;       // optional aspect-bin code per pixel (see the Horn loop), or nullptr
     unsigned long long* counters;  // [0]=count_base [1]=count_maxdz [2]=count_slope
+    // loop mode (the native dem_align loop): the slope raster holds tan(slope) = |gradient| / 8 instead of degrees (the
+    // consumers -- y = dh / tan(slope), the slope median -- want the tangent; saves an atan here and a tan there)
+    int loopmode;
+    float g_lo, g_hi, g_mid, g_half, g_tol;   // slope limits as tangents + guard band of the FP32 path around them
+    // fast path: front_fast_kernel handles the interior tiles without nodata and appends every other tile to `list`
+    // ([0] = count, then (ty << 16 | tx)); the general kernel then runs over that list
+    unsigned* list;
+    int list_mode;             // general kernel: 1 = tiles come from `list`
+    float max_dz_eff;          // max_dz, or +inf when the filter is off (branch-free test)
 };
 
 // 16-tap warp of one pixel out of a shared-memory footprint tile (taps start at (r0, c0))
@@ -583,8 +595,8 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ src, const 
     }
 }
 
-__global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ FrontParams p) {
-    extern __shared__ __align__(128) float smem[];
+// `it`: ordinal of the tile within this CTA (the mbarrier is initialised once and its phase parity alternates)
+__device__ __forceinline__ void front_tile(const FrontParams& p, float* smem, const int bx, const int by, const unsigned it) {
     float* s_src_base = smem;                             // F_SRC_R x F_SRC_C
     float* s_ref_base = s_src_base + F_SRC_WORDS;         // F_REF_R x F_REF_C (128-byte aligned: TMA destination)
     float* s_sw = s_ref_base + F_REF_WORDS;               // F_SW_R x F_SW_C : warped src (NaN = nodata)
@@ -595,7 +607,7 @@ __global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ F
     __shared__ __align__(128) unsigned char s_mask_base[F_TH * F_MSK_C];   // static (stable-surface) mask tile, 1 = masked
     unsigned char* s_mask = s_mask_base + (p.use_tma_mask ? p.tma_dx_msk : 0);
 
-    const int tj0 = blockIdx.x * F_TW, ti0 = p.row_begin + blockIdx.y * F_TH;
+    const int tj0 = bx * F_TW, ti0 = p.row_begin + by * F_TH;
     const int tid = threadIdx.x;
     if (tid < 3) s_cnt[tid] = 0ull;
 
@@ -603,7 +615,7 @@ __global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ F
     __shared__ __align__(8) unsigned long long s_bar;
     if (p.use_tma) {
         // both footprints by TMA: thread 0 arms the mbarrier with the byte count and issues the two tensor copies
-        if (tid == 0) mbar_init(&s_bar, 1);
+        if (tid == 0 && it == 0) mbar_init(&s_bar, 1);
         __syncthreads();
         if (tid == 0) {
             mbar_expect_tx(&s_bar, (unsigned)((F_SRC_R * F_SRC_C + F_REF_R * F_REF_C) * sizeof(float)) +
@@ -636,7 +648,7 @@ __global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ F
     if (p.use_tma) {
         // wait for the bytes (bounded spin: a mis-programmed copy must fault, not hang the GPU), then nodata -> NaN
         unsigned spins = 0;
-        while (!mbar_try_wait(&s_bar, 0)) {
+        while (!mbar_try_wait(&s_bar, it & 1u)) {
             if (++spins > (1u << 26)) __trap();
         }
         if (p.use_tma_mask) {
@@ -825,15 +837,16 @@ __global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ F
             q += F_SW_C;
             const float rs2 = (w6 + w7 + w7 + w8);
             if (rr < n_store) {
-                float sl = DCR_GDALDEM_NDV, as = DCR_GDALDEM_NDV;
+                float sl = DCR_GDALDEM_NDV, as = DCR_GDALDEM_NDV, sg = DCR_GDALDEM_NDV;
                 unsigned bits = DCR_M_SLOPE | DCR_M_ASPECT;
                 if (rr >= r_lo && rr < r_hi) {
-                    float sv, av;
+                    float sv, av, gv;
                     bool ex;
                     if (horn_fast(w0, w1, w2, w3, w4, w5, w6, w7, w8, rs2, rs0, p.inv8ew, p.inv8ns, p.slope_mid, p.slope_half,
-                                  p.slope_tol, &sv, &av, &ex)) {
-                        if (ex) horn(w0, w1, w2, w3, w4, w5, w6, w7, w8, p.ewres, p.nsres, true, true, &sv, &av);
+                                  p.slope_tol, &sv, &av, &ex, &gv)) {
+                        if (ex) horn(w0, w1, w2, w3, w4, w5, w6, w7, w8, p.ewres, p.nsres, true, true, &sv, &av, &gv);
                         sl = sv;
+                        sg = gv;
                         // range_fltr(slope, slope_lim): masked_outside keeps lo <= s <= hi
                         if (!(sl < p.slope_lo) && !(sl > p.slope_hi)) { bits &= ~DCR_M_SLOPE; ++n_slope; }
                         if (!isnan(av)) { as = av; bits &= ~DCR_M_ASPECT; }
@@ -841,7 +854,7 @@ __global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ F
                 }
                 if (!(valid_bits & (1u << rr))) bits |= DCR_M_BASE;
                 else if (maxdz_bits & (1u << rr)) bits |= DCR_M_MAXDZ;
-                p.slope[o] = sl;
+                p.slope[o] = p.loopmode ? sg : sl;
                 if (p.aspect) p.aspect[o] = as;
                 p.maskbits[o] = (unsigned char)bits;
                 if (p.bin) {
@@ -868,6 +881,320 @@ __global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ F
     }
     __syncthreads();
     if (tid < 3 && p.counters) atomicAdd(&p.counters[tid], s_cnt[tid]);
+}
+
+__global__ void __launch_bounds__(256, 4) front_kernel(const __grid_constant__ FrontParams p) {
+    extern __shared__ __align__(128) float smem[];
+    if (!p.list_mode) {
+        front_tile(p, smem, blockIdx.x, blockIdx.y, 0u);
+        return;
+    }
+    // list mode: the tiles the fast kernel declined (grid border, nodata in a footprint), a few per CTA
+    const unsigned n = p.list[0];
+    unsigned it = 0;
+    for (unsigned t = blockIdx.x; t < n; t += gridDim.x, ++it) {
+        const unsigned id = p.list[1 + t];
+        front_tile(p, smem, (int)(id & 0xffffu), (int)(id >> 16), it);
+        __syncthreads();   // shared memory (tiles, mbarrier, counters) is reused by the next tile
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fast path of the fused front end: interior tiles whose footprints hold no nodata.
+//
+// The general kernel above is issue-bound at ~345 thread-instructions per pixel, a third of them control flow and
+// integer bookkeeping for cases that almost never occur inside a raster (grid borders, nodata taps and the bilinear
+// fallback, row bands, partial tiles, optional outputs).  This kernel handles ONLY the common tile -- every output pixel of
+// the tile and of its halo ring inside the grid, every staged source pixel valid -- with straight-line code:
+//   * the axes of the translation on which a raster is pixel-aligned are known at launch (in the dem_align loop each axis
+//     has exactly one resampled raster): AX selects the 4-tap FP64 pass only where the offset has a fraction (bit 0/1: source
+//     x/y, bit 2/3: reference x/y); an aligned axis contributes its single tap, which is what GDAL's weights (0, 1, 0, 0)
+//     return for finite taps;
+//   * no NaN probes, no bilinear fallback, no row / column range checks; masks and counters are bit operations;
+//   * LOOPMODE: the slope raster receives tan(slope) (no atan), no aspect raster.
+// Every other tile (grid border, nodata or out-of-raster taps in a footprint) is appended to p.list and left to the general
+// kernel.  Results are bit-identical to the general kernel's (same arithmetic, same order).
+// ------------------------------------------------------------------------------------------
+template <bool FX>
+__device__ __forceinline__ double fast_xrow(const double* __restrict__ w, const float* __restrict__ q) {
+    if (FX) return w[0] * (double)q[0] + w[1] * (double)q[1] + w[2] * (double)q[2] + w[3] * (double)q[3];
+    return (double)q[1];
+}
+
+// exact Horn slope / aspect of one window (GDAL's FP64 formulation) for the guard-band pixels of the fast path
+__device__ __noinline__ void horn_exact(float w0, float w1, float w2, float w3, float w5, float w6, float w7, float w8,
+                                        double ewres, double nsres, float* slope_deg, float* tan_slope, float* aspect) {
+    const float a = (w0 + w3 + w3 + w6);
+    const float b = (w2 + w5 + w5 + w8);
+    const float c = (w6 + w7 + w7 + w8);
+    const float d = (w0 + w1 + w1 + w2);
+    const float dyf = c - d;
+    {
+        const float dxf = a - b;
+        const double dx = (double)dxf / ewres, dy = (double)dyf / nsres;
+        const double key = dx * dx + dy * dy;
+        *slope_deg = (float)(atan(sqrt(key) / 8.0) * (180.0 / M_PI));
+        *tan_slope = (float)(sqrt(key) / 8.0);
+    }
+    {
+        const float dxf = b - a;
+        const double dx = (double)dxf, dy = (double)dyf;
+        if (dx == 0.0 && dy == 0.0) {
+            *aspect = __int_as_float(0x7fc00000);
+        } else {
+            float asp = (float)(atan2(dy, -dx) / (M_PI / 180.0));
+            asp = (asp > 90.0f) ? __fsub_rn(450.0f, asp) : __fsub_rn(90.0f, asp);
+            if (asp == 360.0f) asp = 0.0f;
+            *aspect = asp;
+        }
+    }
+}
+
+template <int AX, bool LOOPMODE>
+__global__ void __launch_bounds__(256, 4) front_fast_kernel(const __grid_constant__ FrontParams p) {
+    constexpr bool SX = (AX & 1) != 0, SY = (AX & 2) != 0, RX = (AX & 4) != 0, RY = (AX & 8) != 0;
+    extern __shared__ __align__(128) float smem[];
+    float* s_src_base = smem;                             // F_SRC_R x F_SRC_C
+    float* s_ref_base = s_src_base + F_SRC_WORDS;         // F_REF_R x F_REF_C
+    float* s_sw = s_ref_base + F_REF_WORDS;               // F_SW_R x F_SW_C : warped src
+    const float* s_src = s_src_base + p.tma_dx_src;
+    const float* s_ref = s_ref_base + p.tma_dx_ref;
+    __shared__ __align__(128) unsigned char s_mask_base[F_TH * F_MSK_C];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ unsigned s_cnt[3];
+    const unsigned char* s_mask = s_mask_base + (p.use_tma_mask ? p.tma_dx_msk : 0);
+    const int tid = threadIdx.x;
+    const int tj0 = blockIdx.x * F_TW, ti0 = blockIdx.y * F_TH;
+    // a tile whose pixels or halo ring touch the border of the grid is not ours
+    const bool interior = blockIdx.x > 0 && blockIdx.y > 0 && tj0 + F_TW < p.w && ti0 + F_TH < p.h;
+    if (!interior) {
+        if (tid == 0) p.list[1u + atomicAdd(p.list, 1u)] = (blockIdx.y << 16) | blockIdx.x;
+        return;
+    }
+    if (tid < 3) s_cnt[tid] = 0u;
+    if (tid == 0) mbar_init(&s_bar, 1);
+    if (!p.use_tma_mask)   // no static mask: an all-clear tile (the main pass reads it unconditionally)
+        for (int k = tid; k < (F_TH * F_MSK_C) / 16; k += 256) reinterpret_cast<uint4*>(s_mask_base)[k] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&s_bar, (unsigned)((F_SRC_R * F_SRC_C + F_REF_R * F_REF_C) * sizeof(float)) +
+                                   (p.use_tma_mask ? (unsigned)(F_TH * F_MSK_C) : 0u));
+        if (p.use_tma_mask)
+            tma_load_2d(s_mask_base, &p.tm_msk, tj0 + p.smask_nx0 - p.tma_dx_msk, ti0 + p.smask_ny0 - p.smask_row0, &s_bar);
+        tma_load_2d(s_src_base, &p.tm_src, tj0 - 2 + p.sg.ix0 - p.tma_dx_src, ti0 - 2 + p.sg.iy0 - p.sg.row0, &s_bar);
+        tma_load_2d(s_ref_base, &p.tm_ref, tj0 - 1 + p.rg.ix0 - p.tma_dx_ref, ti0 - 1 + p.rg.iy0 - p.rg.row0, &s_bar);
+    }
+    {
+        unsigned spins = 0;
+        while (!mbar_try_wait(&s_bar, 0)) {
+            if (++spins > (1u << 26)) __trap();
+        }
+    }
+    if (p.use_tma_mask) {
+        // the copy engine fills bytes outside the mask raster with 0; outside = masked (1): tiles at the mask's edge only
+        const int mi0 = ti0 + p.smask_ny0, mj0 = tj0 + p.smask_nx0;
+        if (mi0 < p.smask_row0 || mj0 < 0 || mi0 + F_TH > p.smask_row1 || mj0 + F_TW > p.smask_w) {
+            unsigned char* sm = s_mask_base + p.tma_dx_msk;
+            for (int e = tid; e < F_TH * F_TW; e += 256) {
+                const int mi = mi0 + (e >> 7), mj = mj0 + (e & (F_TW - 1));
+                if (mi < p.smask_row0 || mj < 0 || mi >= p.smask_row1 || mj >= p.smask_w) sm[(e >> 7) * F_MSK_C + (e & (F_TW - 1))] = 1;
+            }
+        }
+    }
+    // pending z shifts of the source (coreglib.apply_z_shift deferred by the loop) + the scan for nodata / out-of-raster
+    // (NaN-filled by the copy engine) pixels: any of them sends the whole tile to the general kernel
+    bool bad = false;
+    {
+        const float snd = p.sg.has_ndv ? p.sg.ndv : __int_as_float(0x7fc00000);   // (x == NaN) is never true
+        const float rnd = p.rg.has_ndv ? p.rg.ndv : __int_as_float(0x7fc00000);
+        float4* t4 = reinterpret_cast<float4*>(s_src_base);
+        if (p.sg.ndz) {
+            const float nd = p.sg.ndv, zlo = p.sg.zlo, zhi = p.sg.zhi;
+            const int ndz = p.sg.ndz;
+            const float z0 = p.sg.dz[0], z1 = p.sg.dz[1], z2 = p.sg.dz[2], z3 = p.sg.dz[3];
+            auto fix = [&](float x) {
+                x = (x >= zlo && x <= zhi) ? nd : x + z0;
+                if (ndz > 1) x = (x >= zlo && x <= zhi) ? nd : x + z1;
+                if (ndz > 2) x = (x >= zlo && x <= zhi) ? nd : x + z2;
+                if (ndz > 3) x = (x >= zlo && x <= zhi) ? nd : x + z3;
+                return x;
+            };
+            for (int k = tid; k < (F_SRC_R * F_SRC_C) / 4; k += 256) {
+                float4 v = t4[k];
+                v.x = fix(v.x); v.y = fix(v.y); v.z = fix(v.z); v.w = fix(v.w);
+                t4[k] = v;
+                const float sum = (v.x + v.y) + (v.z + v.w);
+                bad = bad || (sum != sum) || v.x == snd || v.y == snd || v.z == snd || v.w == snd;
+            }
+        } else {
+            for (int k = tid; k < (F_SRC_R * F_SRC_C) / 4; k += 256) {
+                const float4 v = t4[k];
+                const float sum = (v.x + v.y) + (v.z + v.w);
+                bad = bad || (sum != sum) || v.x == snd || v.y == snd || v.z == snd || v.w == snd;
+            }
+        }
+        const float4* r4 = reinterpret_cast<const float4*>(s_ref_base);
+        for (int k = tid; k < (F_REF_R * F_REF_C) / 4; k += 256) {
+            const float4 v = r4[k];
+            const float sum = (v.x + v.y) + (v.z + v.w);
+            bad = bad || (sum != sum) || v.x == rnd || v.y == rnd || v.z == rnd || v.w == rnd;
+        }
+    }
+    if (__syncthreads_or(bad ? 1 : 0)) {
+        if (tid == 0) p.list[1u + atomicAdd(p.list, 1u)] = (blockIdx.y << 16) | blockIdx.x;
+        return;
+    }
+
+    // ---- halo ring of the warped-src tile (3x3 stencil)
+    for (int k = tid; k < 2 * F_SW_C + 2 * F_TH; k += 256) {
+        int rr, cc;
+        if (k < F_SW_C) { rr = 0; cc = k; }
+        else if (k < 2 * F_SW_C) { rr = F_SW_R - 1; cc = k - F_SW_C; }
+        else if (k < 2 * F_SW_C + F_TH) { rr = 1 + (k - 2 * F_SW_C); cc = 0; }
+        else { rr = 1 + (k - 2 * F_SW_C - F_TH); cc = F_SW_C - 1; }
+        s_sw[rr * F_SW_C + cc] = warp_px_tile<F_SRC_C>(s_src, rr, cc, p.sg);
+    }
+
+    // ---- main pass: thread = (column c, half hf), F_ROWS_PER_THREAD consecutive rows
+    const int c = tid & (F_TW - 1);
+    const int hf = tid >> 7;
+    const int rbeg = hf * F_ROWS_PER_THREAD;
+    const long long o0 = (long long)(ti0 + rbeg) * p.w + (tj0 + c);
+    unsigned valid_bits = 0, maxdz_bits = 0;
+    {
+        // tile row tr of s_src holds source row (output row - 2 + tr): the 4 taps of output row r are tr = r + 1 .. r + 4,
+        // the aligned-axis tap is tr = r + 2; columns alike (tap 0 at c + 1).  s_ref: taps tr = r .. r + 3 (aligned: r + 1).
+        const float* qs = s_src + (rbeg + 1) * F_SRC_C + (c + 1);
+        const float* qr = s_ref + rbeg * F_REF_C + c;
+        double xs0 = 0, xs1 = 0, xs2 = 0, xr0 = 0, xr1 = 0, xr2 = 0;
+        if (SY) {
+            xs0 = fast_xrow<SX>(p.sg.wx, qs);
+            xs1 = fast_xrow<SX>(p.sg.wx, qs + F_SRC_C);
+            xs2 = fast_xrow<SX>(p.sg.wx, qs + 2 * F_SRC_C);
+        }
+        if (RY) {
+            xr0 = fast_xrow<RX>(p.rg.wx, qr);
+            xr1 = fast_xrow<RX>(p.rg.wx, qr + F_REF_C);
+            xr2 = fast_xrow<RX>(p.rg.wx, qr + 2 * F_REF_C);
+        }
+        float* swp = s_sw + (rbeg + 1) * F_SW_C + (c + 1);
+        const unsigned char* mk = s_mask + rbeg * F_MSK_C + c;
+        const float slo = p.src_gm_lo, shi = p.src_gm_hi, rlo = p.ref_gm_lo, rhi = p.ref_gm_hi, mdz = p.max_dz_eff;
+        float* dhp = p.dh + o0;
+        const int w = p.w;
+#pragma unroll
+        for (int rr = 0; rr < F_ROWS_PER_THREAD; ++rr) {
+            float sv, rv;
+            if (SY) {
+                const double xs3 = fast_xrow<SX>(p.sg.wx, qs + (rr + 3) * F_SRC_C);
+                sv = (float)ypass(p.sg.wy, xs0, xs1, xs2, xs3);
+                xs0 = xs1; xs1 = xs2; xs2 = xs3;
+            } else {
+                sv = (float)fast_xrow<SX>(p.sg.wx, qs + (rr + 1) * F_SRC_C);
+            }
+            if (RY) {
+                const double xr3 = fast_xrow<RX>(p.rg.wx, qr + (rr + 3) * F_REF_C);
+                rv = (float)ypass(p.rg.wy, xr0, xr1, xr2, xr3);
+                xr0 = xr1; xr1 = xr2; xr2 = xr3;
+            } else {
+                rv = (float)fast_xrow<RX>(p.rg.wx, qr + (rr + 1) * F_REF_C);
+            }
+            swp[rr * F_SW_C] = sv;
+            // ds_getma masks as float32 intervals of numpy masked_values' |x - ndv| <= tol; static mask byte
+            const bool s_in = (sv >= slo) & (sv <= shi);
+            const bool r_in = (rv >= rlo) & (rv <= rhi);
+            const bool ok = !(s_in | r_in | (mk[rr * F_MSK_C] != 0));
+            const float dh = ok ? (sv - rv) : 0.0f;
+            const bool big = ok & (fabsf(dh) > mdz);
+            valid_bits |= ok ? (1u << rr) : 0u;
+            maxdz_bits |= big ? (1u << rr) : 0u;
+            dhp[(long long)rr * w] = dh;
+        }
+    }
+    __syncthreads();
+
+    // ---- Horn stencil on the warped src + mask byte + aspect-bin code
+    unsigned slope_bits = 0;
+    {
+        const float* q = s_sw + rbeg * F_SW_C + c;
+        float w0 = q[0], w1 = q[1], w2 = q[2];
+        float w3 = q[F_SW_C], w4 = q[F_SW_C + 1], w5 = q[F_SW_C + 2];
+        float rs0 = (w0 + w1 + w1 + w2), rs1 = (w3 + w4 + w4 + w5);
+        const float inv8ew = p.inv8ew, inv8ns = p.inv8ns;
+        float* slp = p.slope + o0;
+        unsigned char* mbp = p.maskbits + o0;
+        unsigned short* bnp = p.bin + o0;
+        float* asp = (!LOOPMODE && p.aspect) ? p.aspect + o0 : nullptr;
+        const int w = p.w;
+#pragma unroll
+        for (int rr = 0; rr < F_ROWS_PER_THREAD; ++rr) {
+            const float* qq = q + (rr + 2) * F_SW_C;
+            const float w6 = qq[0], w7 = qq[1], w8 = qq[2];
+            const float rs2 = (w6 + w7 + w7 + w8);
+            const float a = (w0 + w3 + w3 + w6);
+            const float b = (w2 + w5 + w5 + w8);
+            const float dxs = a - b;      // slope numerator; the aspect uses b - a = -dxs exactly
+            const float dyf = rs2 - rs0;
+            const float gx = dxs * inv8ew, gy = dyf * inv8ns;
+            float g;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(gx * gx + gy * gy));
+            float sl = 0.0f;
+            bool ex, s_ok;
+            if (LOOPMODE) {
+                // slope limits as tangents; within the guard band of either one the FP64 path decides
+                ex = !(fabsf(fabsf(g - p.g_mid) - p.g_half) > p.g_tol);
+                s_ok = (g >= p.g_lo) & (g <= p.g_hi);
+            } else {
+                const bool bigg = g > 1.0f;
+                float sa = atan01(bigg ? __fdividef(1.0f, g) : g);
+                if (bigg) sa = 1.5707963267948966f - sa;
+                sl = sa * 57.29577951308232f;
+                ex = !(fabsf(fabsf(sl - p.slope_mid) - p.slope_half) > p.slope_tol);
+                s_ok = !(sl < p.slope_lo) & !(sl > p.slope_hi);
+            }
+            // aspect: atan2(dyf, dxs) from the [0, 1] polynomial, GDAL's azimuth convention
+            const float ax = fabsf(dxs), ay = fabsf(dyf);
+            float an = atan01(__fdividef(fminf(ax, ay), fmaxf(ax, ay)));
+            if (ay > ax) an = 1.5707963267948966f - an;
+            if (dxs < 0.0f) an = 3.141592653589793f - an;
+            an = copysignf(an, dyf);
+            float af = an * 57.29577951308232f;
+            af = (af > 90.0f) ? (450.0f - af) : (90.0f - af);
+            const bool flat = (dxs == 0.0f) & (dyf == 0.0f);
+            // within 3e-4 deg of an integer degree (a bin edge) -> exact path; a flat window has no aspect at all
+            ex = (ex | !(fabsf((af - floorf(af)) - 0.5f) <= 0.5f - 3e-4f)) & !flat;
+            float gs = g;
+            if (ex) {   // ~0.06 % of the pixels
+                float sle, ge, ae;
+                horn_exact(w0, w1, w2, w3, w5, w6, w7, w8, p.ewres, p.nsres, &sle, &ge, &ae);
+                s_ok = !(sle < p.slope_lo) & !(sle > p.slope_hi);
+                sl = sle; gs = ge; af = ae;
+            }
+            const bool vok = (valid_bits >> rr) & 1u, mz = (maxdz_bits >> rr) & 1u;
+            unsigned bits = (s_ok ? 0u : (unsigned)DCR_M_SLOPE) | (flat ? (unsigned)DCR_M_ASPECT : 0u) |
+                            (vok ? (mz ? (unsigned)DCR_M_MAXDZ : 0u) : (unsigned)DCR_M_BASE);
+            slope_bits |= s_ok ? (1u << rr) : 0u;
+            const int bi = min((int)af, DCR_NBINS - 1);   // (NaN / flat never reaches a valid code: bits != 0)
+            slp[(long long)rr * w] = LOOPMODE ? gs : sl;
+            mbp[(long long)rr * w] = (unsigned char)bits;
+            bnp[(long long)rr * w] = (unsigned short)(bits == 0u ? bi : (int)DCR_BIN_INVALID);
+            if (!LOOPMODE && asp) asp[(long long)rr * w] = flat ? DCR_GDALDEM_NDV : af;
+            w0 = w3; w1 = w4; w2 = w5;
+            w3 = w6; w4 = w7; w5 = w8;
+            rs0 = rs1; rs1 = rs2;
+        }
+    }
+    // counters: base-valid, after max_dz, slope-valid
+    unsigned n_base = __reduce_add_sync(0xffffffffu, (unsigned)__popc(valid_bits));
+    unsigned n_maxdz = __reduce_add_sync(0xffffffffu, (unsigned)__popc(valid_bits & ~maxdz_bits));
+    unsigned n_slope = __reduce_add_sync(0xffffffffu, (unsigned)__popc(slope_bits));
+    if ((tid & 31) == 0) {
+        atomicAdd(&s_cnt[0], n_base);
+        atomicAdd(&s_cnt[1], n_maxdz);
+        atomicAdd(&s_cnt[2], n_slope);
+    }
+    __syncthreads();
+    if (tid < 3 && p.counters) atomicAdd(&p.counters[tid], (unsigned long long)s_cnt[tid]);
 }
 
 // float32 interval equivalent to numpy masked_values' |x - ndv| <= 1e-8 + 1e-5*|ndv| evaluated in float64
@@ -915,7 +1242,23 @@ static bool make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, lon
                u8 ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE : CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA) == CUDA_SUCCESS;
 }
 
-int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cudaStream_t stream, unsigned short* bin) {
+// the instantiated axis combinations of the fast kernel (bit 0/1: source x/y fractional, bit 2/3: reference x/y):
+// pixel-aligned pair, the four "one resampled raster per axis" cases of the dem_align loop, everything fractional
+typedef void (*FastKernelFn)(const FrontParams);
+static const int kFastAx[6] = {0, 3, 9, 6, 12, 15};
+static FastKernelFn fast_kernel_fn(int k, int loopmode) {
+    switch (k * 2 + (loopmode ? 1 : 0)) {
+        case 0: return front_fast_kernel<0, false>;   case 1: return front_fast_kernel<0, true>;
+        case 2: return front_fast_kernel<3, false>;   case 3: return front_fast_kernel<3, true>;
+        case 4: return front_fast_kernel<9, false>;   case 5: return front_fast_kernel<9, true>;
+        case 6: return front_fast_kernel<6, false>;   case 7: return front_fast_kernel<6, true>;
+        case 8: return front_fast_kernel<12, false>;  case 9: return front_fast_kernel<12, true>;
+        case 10: return front_fast_kernel<15, false>; default: return front_fast_kernel<15, true>;
+    }
+}
+
+int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cudaStream_t stream, unsigned short* bin,
+                     int loopmode, unsigned* tile_list, long long tile_list_cap) {
     DCR_ARG(a, "null args");
     DCR_ARG(a->ref && a->src && a->dh && a->slope && a->maskbits, "null raster pointer");
     DCR_ARG(a->h > 0 && a->w > 0, "empty grid");
@@ -1026,14 +1369,53 @@ int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cuda
     if (!ctx) return -1;
     if (!(ctx->attrs & DCR_ATTR_FRONT)) {   // per device
         DCR_CUDA_OK(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (int k = 0; k < 12; ++k)
+            DCR_CUDA_OK(cudaFuncSetAttribute(fast_kernel_fn(k >> 1, k & 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->attrs |= DCR_ATTR_FRONT;
     }
-    dim3 grid((a->w + F_TW - 1) / F_TW, (p.row_end - p.row_begin + F_TH - 1) / F_TH);
+    p.loopmode = loopmode ? 1 : 0;
+    p.max_dz_eff = a->use_max_dz ? a->max_dz : INFINITY;
+    {
+        const double lo = tan((double)a->slope_lo * (M_PI / 180.0)), hi = tan((double)a->slope_hi * (M_PI / 180.0));
+        p.g_lo = (float)lo;
+        p.g_hi = (float)hi;
+        p.g_mid = (float)(0.5 * (lo + hi));
+        p.g_half = (float)(0.5 * (hi - lo));
+        p.g_tol = 4e-6f * fmaxf(fabsf(p.g_lo), fabsf(p.g_hi)) + 4e-7f * fabsf(p.g_mid);
+    }
+    const int ntx = (a->w + F_TW - 1) / F_TW, nty = (p.row_end - p.row_begin + F_TH - 1) / F_TH;
+    dim3 grid(ntx, nty);
+    // Fast path: whole-grid launches (no row band) with TMA staging, the aspect-bin codes wanted and no warped rasters:
+    // front_fast_kernel takes the interior tiles without nodata, the general kernel the rest (from the list).
+    const bool slopes_ok = a->slope_lo >= 0.0f && a->slope_hi < 89.0f && a->slope_lo <= a->slope_hi;
+    const bool fast = tile_list && bin && p.use_tma && (!a->smask || p.use_tma_mask) && !a->ref_w && !a->src_w &&
+                      p.row_begin == 0 && p.row_end == a->h && a->ref_nrows <= 0 && a->src_nrows <= 0 && a->smask_nrows <= 0 &&
+                      (long long)ntx * nty + 1 <= tile_list_cap && ntx < 65536 && nty < 65536 && (!loopmode || slopes_ok) &&
+                      !getenv("DCR_NO_FAST_FRONT");
+    if (fast) {
+        int need = (a->src_geom.fx != 0.0 ? 1 : 0) | (a->src_geom.fy != 0.0 ? 2 : 0) | (a->ref_geom.fx != 0.0 ? 4 : 0) |
+                   (a->ref_geom.fy != 0.0 ? 8 : 0);
+        int k = 5;
+        for (int q = 0; q < 6; ++q)
+            if ((need & ~kFastAx[q]) == 0) { k = q; break; }
+        p.list = tile_list;
+        DCR_CUDA_OK(cudaMemsetAsync(tile_list, 0, sizeof(unsigned), stream));
+        p.list_mode = 0;
+        fast_kernel_fn(k, loopmode)<<<grid, 256, smem, stream>>>(p);
+        DCR_LAUNCH_OK("front_fast_kernel");
+        p.list_mode = 1;
+        long long g1 = (long long)ntx * nty;
+        const long long gmax = (long long)ctx->sms * 4;
+        if (g1 > gmax) g1 = gmax;
+        front_kernel<<<(unsigned)g1, 256, smem, stream>>>(p);
+        DCR_LAUNCH_OK("front_kernel (listed tiles)");
+        return 0;
+    }
     front_kernel<<<grid, 256, smem, stream>>>(p);
     DCR_LAUNCH_OK("front_kernel");
     return 0;
 }
 
 extern "C" int dcr_warp_diff_horn(const dcr_front_args* args, void* stream) {
-    return dcr_front_launch(args, nullptr, (cudaStream_t)stream, nullptr);
+    return dcr_front_launch(args, nullptr, (cudaStream_t)stream, nullptr, 0, nullptr, 0);
 }

@@ -26,7 +26,11 @@ void* dcr_ctx_pinned(DcrCtx* c, size_t bytes);   // pinned host scratch of at le
 // counters (device, 3 x u64, zeroed by the caller): base-valid, after max_dz, slope-valid
 // bin (device, h*w, optional): also emit the aspect-bin code of every pixel (DCR_BIN_INVALID outside the masks known to
 // the front end)
-int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cudaStream_t stream, unsigned short* bin = nullptr);
+// loopmode: the slope raster receives tan(slope) instead of degrees (native dem_align loop; nothing else reads it)
+// tile_list (device, tile_list_cap unsigned, optional): scratch that enables the fast interior-tile kernel
+int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cudaStream_t stream, unsigned short* bin = nullptr,
+                     int loopmode = 0, unsigned* tile_list = nullptr, long long tile_list_cap = 0);
+static inline long long dcr_front_list_cap(long long n) { return n / 512 + 65536; }
 
 // ---- exact selection (dcr_select.cu) ----
 // A "view" of the values taking part in a selection; all device pointers.

@@ -7,13 +7,15 @@
 // The reference runs the (2p+1)^2 offsets one after the other (two exact quantiles of kh*kw values each:
 // 1.4 s per offset at 4096^2).  Here ALL offsets are processed by the same few passes over the two rasters:
 //
-//   prep     masked pixels -> NaN (a NaN difference takes part in nothing), kernel = src[p:-p, p:-p] made contiguous
+//   prep     masked pixels -> NaN (a NaN difference takes part in nothing), kernel = src[p:-p, p:-p] made contiguous,
+//            validity bit planes of both
+//   count    per offset: number of unmasked differences = popcount of the AND of the shifted bit planes
 //   sample   one CTA per offset: 32768 stratified samples of diff -> a bracket [lo, hi] around each of the two
-//            order statistics (sample ranks -+ 5 sigma), localised by three rounds of a 1024-bin histogram
-//   pass 1   every difference of every offset, out of shared-memory tiles (thread = pixel column, 8 consecutive
-//            offsets unrolled so that the bracket bounds and the counters of an offset live in registers): exact
-//            counts below / inside the brackets; the ~5 % inside are parked in thread-private shared-memory slots and
-//            drained into a 512-bin histogram of their bracket (shared-memory atomics)
+//            order statistics (sample ranks -+ 4 sigma), localised by three rounds of a 1024-bin histogram
+//   pass 1   every difference of every offset, out of shared-memory tiles (thread = pixel column; 8 consecutive column
+//            offsets per CTA, two at a time): exact counts at / above the lower edge of each bracket; the ~4 % inside a
+//            bracket are parked in thread-private shared-memory slots and drained into a 256-bin histogram of their
+//            bracket (shared-memory atomics)
 //   find     per offset: exact integer ranks of P25 / P75 (float64 virtual index, as numpy) -> the histogram bins
 //            that hold them, VERIFIED to lie inside the brackets; the bin edges as exact float thresholds (bisection
 //            over the monotone bin function)
@@ -23,64 +25,117 @@
 //
 // An offset whose verification fails (heavy ties, degenerate or overlapping brackets, candidate overflow) is
 // redone by the exact per-offset path (materialised diff + two K3 selections), which is also what
-// DCR_SAD_PER_OFFSET runs for every offset (tests compare the two).  Both passes are FP32/integer-issue bound
-// out of shared memory (about 12 instructions per difference), not HBM bound: the rasters are read
-// (2p+1)^2 / 8 times from L2.
+// DCR_SAD_PER_OFFSET runs for every offset (tests compare the two).
+//
+// Both passes run out of shared memory and are bound by the half-rate ALU pipe (compares, predicate logic), not by HBM
+// or L2: the classification step of a difference is hand-written PTX -- 4 FSETP + 1 PLOP3 + 1 VIADD on the ALU pipe, the
+// subtraction and the two counter updates (FLOAT counters: predicated FADD) on the FMA pipe, 1 LDS + 1 predicated STS.
+// Per-thread state is kept small (two offsets at a time, bounds re-read from shared memory per offset pair) so that
+// 4 CTAs of 256 threads fit an SM and hide the tile loads.
 #include <string.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include "dcr_common.cuh"
 #include "dcr_internal.cuh"
 
-#define SAD_B 512        // histogram bins per bracket
-#define SAD_JC 8         // consecutive column offsets per CTA (per-thread register state scales with it)
+#define SAD_B 256        // histogram bins per bracket
+#define SAD_JC 8         // consecutive column offsets per CTA
 #define SAD_TU 8         // tile rows
 #define SAD_TV 256       // tile columns = threads per CTA
-#define SAD_DRAIN 4      // rows between two drains of the parked values (SAD_DRAIN * SAD_JC private slots per thread)
-#define SAD_PRIV (SAD_DRAIN * SAD_JC)
-#define SAD_CAP 2048     // candidates per (offset, quantile)
+#define SAD_PRIV (2 * SAD_TU)   // private parking slots per thread: one offset pair x SAD_TU rows can never overflow them
+#define SAD_CAP 4096     // candidates per (offset, quantile)
 #define SAD_S 32768      // samples per offset
 #define SAD_QNAN __int_as_float(0x7fc00000)
 
 struct SadOff {
-    // sample kernel
-    float lo[2], hi[2], sc[2];   // closed brackets of P25 / P75 and their bin scales SAD_B / (hi - lo)
-    float mid;                   // a value between the two brackets (which bracket a parked value belongs to)
+    // sample kernel: both brackets in terms of e = fl(d - c), c = centre of the gap between them:
+    //   bracket of P25 = {-b <= e <= -a}, bracket of P75 = {a <= e <= b}   (supersets of the sample brackets)
+    float c, a, b, sc;           // sc = SAD_B / (b - a): bin scale of both brackets
+    float lo[2], hi[2];          // the sample brackets themselves (closed, in d), informational
     int flag;                    // != 0: batched path not applicable / failed verification -> per-offset exact path
-    // pass 1
-    unsigned long long n_lt, n_ge, n_rng;   // d < lo[0] ; d >= lo[0] ; lo[0] <= d <= hi[1]
-    // find
+    int done;                    // m already final (no unmasked difference)
+    // count + pass 1
+    unsigned long long n_c0, n_gap;    // e >= -b ; |e| < a
+    long long count;             // unmasked differences (popcount of the validity planes)
+    // find (thresholds in e)
     float ta[2], tb[2];          // candidate intervals [ta, tb) of P25 / P75; the untouched middle is [tb[0], ta[1])
     long long n_mid;             // differences inside the middle
     unsigned k[2], k2[2];        // ranks of the two neighbouring order statistics inside the sorted candidates
     double g[2];                 // interpolation weights
     unsigned want[2];            // candidates pass 2 must find
     unsigned ncand[2];           // candidates pass 2 found
-    long long count;             // unmasked differences
-    int done;                    // m already final (no unmasked difference)
-    int pad;
 };
 
-__device__ __forceinline__ unsigned sad_trunc_bits(float d) { return __float_as_uint(d) & ~7u; }
-// bin of a parked difference inside its bracket: monotone non-decreasing in d (truncation of the low mantissa bits,
-// subtraction, multiplication, conversion and clamping all are)
-__device__ __forceinline__ int sad_bin(float dt, float lo, float sc) {
-    const float t = (dt - lo) * sc;
+// bin of a difference inside its bracket, from t = e - (lower edge of the bracket in e): monotone non-decreasing in d
+// (two subtractions, a multiplication, a conversion and clamping all are; the file is compiled without FMA contraction, so
+// every kernel rounds identically)
+__device__ __forceinline__ int sad_bin(float e, float lo_e, float sc) {
+    const float t = (e - lo_e) * sc;
     int b = (int)t;
     return b < 0 ? 0 : (b > SAD_B - 1 ? SAD_B - 1 : b);
 }
 
 // ------------------------------------------------------------------------------------------
-// prep: NaN-filled copies
+// prep: NaN-filled copies + validity bit planes; count: unmasked differences per offset
 // ------------------------------------------------------------------------------------------
+// one warp per 32 consecutive columns of a row; bits[row * wp + word], bit l = column 32 * word + l is valid
 __global__ void __launch_bounds__(256) sad_prep_kernel(const float* __restrict__ x, const unsigned char* __restrict__ m,
                                                        long long stride, int r0, int c0, int h, int w,
-                                                       float* __restrict__ out) {
-    const long long n = (long long)h * w;
-    for (long long k = (long long)blockIdx.x * 256 + threadIdx.x; k < n; k += (long long)gridDim.x * 256) {
-        const int i = (int)(k / w), j = (int)(k - (long long)i * w);
-        const long long s = (long long)(r0 + i) * stride + c0 + j;
-        out[k] = (m && m[s]) ? SAD_QNAN : x[s];
+                                                       float* __restrict__ out, unsigned* __restrict__ bits, int wp) {
+    const int lane = threadIdx.x & 31;
+    const int nwords = (w + 31) >> 5;
+    const long long ntask = (long long)h * nwords;
+    for (long long t = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); t < ntask; t += (long long)gridDim.x * 8) {
+        const int i = (int)(t / nwords), wd = (int)(t - (long long)i * nwords);
+        const int j = wd * 32 + lane;
+        bool ok = false;
+        if (j < w) {
+            const long long s = (long long)(r0 + i) * stride + c0 + j;
+            float v = x[s];
+            if (m && m[s]) v = SAD_QNAN;
+            ok = v == v;
+            out[(long long)i * w + j] = v;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) bits[(long long)i * wp + wd] = b;
+    }
+}
+
+// N(i, j) = sum over kernel pixels (u, v) of valid_k[u][v] & valid_r[u + i][v + j].  CTA = (row segment, offset row i,
+// chunk of 32 offset columns); lane = offset column j: the three words of a step are read once (broadcast) and shifted by
+// the lane's own j; per-lane counts leave through one atomic per lane and CTA.
+#define SAD_CNT_SEG 8
+__global__ void __launch_bounds__(256) sad_count_kernel(const unsigned* __restrict__ rb, int rwp, const unsigned* __restrict__ kb,
+                                                        int kwp, int kh, int J, SadOff* __restrict__ off) {
+    __shared__ unsigned long long s_n[8][32];
+    const int oi = blockIdx.y, jb = blockIdx.z * 32;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int oj = jb + lane;
+    unsigned long long n = 0;
+    for (int u = blockIdx.x * 8 + wrp; u < kh; u += SAD_CNT_SEG * 8) {
+        const unsigned* kr = kb + (long long)u * kwp;
+        const unsigned* rr = rb + (long long)(u + oi) * rwp + (jb >> 5);
+        unsigned cnt = 0;
+        for (int wd = 0; wd < kwp; wd += 4) {
+            unsigned kk[4], lo[4], hi[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bool in = wd + q < kwp;
+                kk[q] = in ? __ldg(kr + wd + q) : 0u;
+                lo[q] = in ? __ldg(rr + wd + q) : 0u;
+                hi[q] = in ? __ldg(rr + wd + q + 1) : 0u;   // (the planes carry one zero word of padding)
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cnt += __popc(kk[q] & __funnelshift_r(lo[q], hi[q], lane));
+        }
+        n += cnt;
+    }
+    s_n[wrp][lane] = n;
+    __syncthreads();
+    if (wrp == 0 && oj < J) {
+        unsigned long long t = 0;
+        for (int k = 0; k < 8; ++k) t += s_n[k][lane];
+        if (t) atomicAdd(reinterpret_cast<unsigned long long*>(&off[oi * J + oj].count), t);
     }
 }
 
@@ -175,7 +230,7 @@ __global__ void __launch_bounds__(1024) sad_sample_kernel(const float* __restric
         for (int r = 0; r < 2; ++r) {
             const double f = r == 0 ? 0.25 : 0.75;
             const double rk = f * (double)(m - 1);
-            const double dd = 5.0 * sqrt((double)m * f * (1.0 - f)) + 8.0;
+            const double dd = 4.0 * sqrt((double)m * f * (1.0 - f)) + 4.0;   // a miss (6e-5 per edge) costs one per-offset redo
             const long long a0 = (long long)floor(rk - dd), b0 = (long long)ceil(rk + dd);
             if (a0 < 0 || b0 >= m) { open = true; break; }
             unsigned base;
@@ -186,194 +241,188 @@ __global__ void __launch_bounds__(1024) sad_sample_kernel(const float* __restric
         }
     }
     if (threadIdx.x == 0) {
-        SadOff q;
-        memset(&q, 0, sizeof(q));
+        SadOff q = off[o];        // keeps the count of the count kernel
+        q.n_c0 = q.n_gap = 0ull;
+        q.n_mid = 0;
+        q.ncand[0] = q.ncand[1] = 0u;
+        q.done = 0;
         q.flag = open ? 1 : 0;
         if (!open) {
-            for (int r = 0; r < 2; ++r) {
-                q.lo[r] = dcr_key2f(klo[r]);
-                q.hi[r] = dcr_key2f(khi[r]);
-                const float w = q.hi[r] - q.lo[r];
-                q.sc[r] = (w > 0.0f && !isinf(w)) ? (float)SAD_B / w : 0.0f;
-            }
-            // the brackets must be well separated: a parked value is attributed to one of them by `mid`, after its low
-            // mantissa bits were cleared (<= 7 ulp towards zero)
-            q.mid = 0.5f * q.hi[0] + 0.5f * q.lo[1];
+            for (int r = 0; r < 2; ++r) { q.lo[r] = dcr_key2f(klo[r]); q.hi[r] = dcr_key2f(khi[r]); }
+            // e = fl(d - c) with c in the middle of the gap; a / b from the SAME float expression, so that (fl(. - c) being
+            // monotone) lo0 <= d <= hi0 implies -b <= e <= -a and lo1 <= d <= hi1 implies a <= e <= b
+            q.c = 0.5f * q.hi[0] + 0.5f * q.lo[1];
+            q.a = fminf(-(q.hi[0] - q.c), q.lo[1] - q.c);
+            q.b = fmaxf(-(q.lo[0] - q.c), q.hi[1] - q.c);
+            const float w = q.b - q.a;
+            q.sc = (w > 0.0f && !isinf(w)) ? (float)SAD_B / w : 0.0f;
             const float big = fmaxf(fabsf(q.hi[0]), fabsf(q.lo[1]));
-            if (!(q.lo[1] - q.hi[0] > 1e-5f * big) || !(q.mid > q.hi[0]) || !(q.mid < q.lo[1]) || isinf(q.lo[0]) || isinf(q.hi[1]))
-                q.flag = 1;
+            // the brackets must be well separated and finite
+            if (!(q.a > 1e-5f * big) || !(q.b > q.a) || isinf(q.b) || isnan(q.c) || !(q.sc > 0.0f)) q.flag = 1;
         }
         off[o] = q;
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// the tile loop shared by pass 1 and pass 2: thread = pixel column, SAD_JC consecutive column offsets unrolled
+// the tile loop shared by pass 1 and pass 2: thread = pixel column, SAD_JC consecutive column offsets, two at a time
 // ------------------------------------------------------------------------------------------
-struct SadTiles {
-    float* ks;   // [SAD_TU][SAD_TV]
-    float* rs;   // [SAD_TU][SAD_TV + SAD_JC]
-};
 #define SAD_RP (SAD_TV + SAD_JC)
 
+// k tile [SAD_TU][SAD_TV] of the kernel raster, r tile [SAD_TU][SAD_RP] of the reference rows u0 + oi .., columns v0 + j0 ..
 __device__ __forceinline__ void sad_load_tile(const float* __restrict__ rz, const float* __restrict__ kz, int W, int kh, int kw,
-                                              int oi, int j0, int u0, int v0, const SadTiles& t) {
+                                              int oi, int j0, int u0, int v0, float* __restrict__ ks, float* __restrict__ rs) {
     const int tid = threadIdx.x;
+    if (((kw | W) & 3) == 0 && u0 + SAD_TU <= kh && v0 + SAD_TV <= kw && v0 + j0 + SAD_RP <= W) {
+        // interior tile of 16-byte aligned rows: 16-byte loads (2 + 2..3 per thread instead of 17 scalar ones)
+        for (int q = tid; q < SAD_TU * (SAD_TV / 4); q += SAD_TV) {
+            const int r = q / (SAD_TV / 4), c4 = q - r * (SAD_TV / 4);
+            reinterpret_cast<float4*>(ks)[q] = __ldg(reinterpret_cast<const float4*>(kz + (long long)(u0 + r) * kw + v0) + c4);
+        }
+        for (int q = tid; q < SAD_TU * (SAD_RP / 4); q += SAD_TV) {
+            const int r = q / (SAD_RP / 4), c4 = q - r * (SAD_RP / 4);
+            reinterpret_cast<float4*>(rs)[q] = __ldg(reinterpret_cast<const float4*>(rz + (long long)(u0 + r + oi) * W + v0 + j0) + c4);
+        }
+        return;
+    }
     const bool cok = v0 + tid < kw;
 #pragma unroll
     for (int r = 0; r < SAD_TU; ++r) {
         const bool rok = u0 + r < kh;
-        t.ks[r * SAD_TV + tid] = (rok && cok) ? __ldg(kz + (long long)(u0 + r) * kw + v0 + tid) : SAD_QNAN;
+        ks[r * SAD_TV + tid] = (rok && cok) ? __ldg(kz + (long long)(u0 + r) * kw + v0 + tid) : SAD_QNAN;
         const float* rrow = rz + (long long)(u0 + r + oi) * W + v0 + j0;
-        t.rs[r * SAD_RP + tid] = (rok && v0 + j0 + tid < W) ? __ldg(rrow + tid) : SAD_QNAN;
-        if (tid < SAD_JC) t.rs[r * SAD_RP + SAD_TV + tid] = (rok && v0 + j0 + SAD_TV + tid < W) ? __ldg(rrow + SAD_TV + tid) : SAD_QNAN;
+        rs[r * SAD_RP + tid] = (rok && v0 + j0 + tid < W) ? __ldg(rrow + tid) : SAD_QNAN;
+        if (tid < SAD_JC) rs[r * SAD_RP + SAD_TV + tid] = (rok && v0 + j0 + SAD_TV + tid < W) ? __ldg(rrow + SAD_TV + tid) : SAD_QNAN;
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // pass 1
 // ------------------------------------------------------------------------------------------
-#define SAD_P1_SMEM ((SAD_TU * SAD_TV + SAD_TU * SAD_RP + SAD_JC * 2 * SAD_B + SAD_PRIV * SAD_TV + SAD_JC * 8 + SAD_JC * 4) * 4)
+#define SAD_P1_SMEM ((SAD_TU * SAD_TV + SAD_TU * SAD_RP + SAD_JC * 2 * SAD_B + SAD_PRIV * SAD_TV + SAD_JC * 4 + SAD_JC * 2) * 4)
 
-__global__ void __launch_bounds__(SAD_TV, 2) sad_pass1_kernel(const float* __restrict__ rz, const float* __restrict__ kz, int W,
+// One difference d: e = d - c; counters (float, exact below 2^24: predicated FADD = FMA pipe) of e >= -b and of |e| < a
+// (the gap between the brackets); e parked iff a <= |e| <= b: ONE predicated store + pointer bump.  Three compares, three
+// predicates.  NaN (a masked pixel) fails every comparison.
+#define SAD_P1_STEP(D, C0, CG, PTR, CC, NB, A, B, STEP)                                                             \
+    asm volatile(                                                                                                    \
+        "{\n\t"                                                                                                      \
+        ".reg .pred p0, pg, pin;\n\t"                                                                                \
+        ".reg .f32 e, ae;\n\t"                                                                                       \
+        "sub.f32 e, %3, %4;\n\t"                                                                                     \
+        "abs.f32 ae, e;\n\t"                                                                                         \
+        "setp.ge.f32 p0, e, %5;\n\t"                                                                                 \
+        "setp.lt.f32 pg, ae, %6;\n\t"                                                                                \
+        "setp.le.and.f32 pin, ae, %7, !pg;\n\t"                                                                      \
+        "@p0 add.f32 %0, %0, 0f3F800000;\n\t"                                                                        \
+        "@pg add.f32 %1, %1, 0f3F800000;\n\t"                                                                        \
+        "@pin st.shared.f32 [%2], e;\n\t"                                                                            \
+        "@pin add.s32 %2, %2, %8;\n\t"                                                                               \
+        "}"                                                                                                          \
+        : "+f"(C0), "+f"(CG), "+r"(PTR)                                                                              \
+        : "f"(D), "f"(CC), "f"(NB), "f"(A), "f"(B), "n"(STEP))
+
+__global__ void __launch_bounds__(SAD_TV, 4) sad_pass1_kernel(const float* __restrict__ rz, const float* __restrict__ kz, int W,
                                                               int kh, int kw, int J, int nchunk, SadOff* __restrict__ off,
                                                               unsigned* __restrict__ ghist) {
     extern __shared__ __align__(16) unsigned char sad_smem[];
     float* ks = reinterpret_cast<float*>(sad_smem);
     float* rs = ks + SAD_TU * SAD_TV;
     unsigned* sh_hist = reinterpret_cast<unsigned*>(rs + SAD_TU * SAD_RP);   // [SAD_JC][2][SAD_B]
-    unsigned* sh_priv = sh_hist + SAD_JC * 2 * SAD_B;                        // slot k of thread t at [k * SAD_TV + t]
-    float* sh_b = reinterpret_cast<float*>(sh_priv + SAD_PRIV * SAD_TV);     // [SAD_JC][8]: lo0 hi0 lo1 hi1 sc0 sc1 mid -
-    unsigned* sh_cnt = reinterpret_cast<unsigned*>(sh_b + SAD_JC * 8);       // [SAD_JC][4] (3 used)
+    float* sh_priv = reinterpret_cast<float*>(sh_hist + SAD_JC * 2 * SAD_B); // slot k of thread t at [k * SAD_TV + t]
+    float* sh_b = sh_priv + SAD_PRIV * SAD_TV;                               // [SAD_JC][4]: c a b sc
+    unsigned* sh_cnt = reinterpret_cast<unsigned*>(sh_b + SAD_JC * 4);       // [SAD_JC][2]
     const int tid = threadIdx.x;
     const int oi = blockIdx.y / nchunk, j0 = (blockIdx.y - oi * nchunk) * SAD_JC;
+    const int nj = min(SAD_JC, J - j0);
     const float inf = INFINITY;
-    float lo0[SAD_JC], hi0[SAD_JC], lo1[SAD_JC], hi1[SAD_JC];
-    unsigned n_lt[SAD_JC], n_ge[SAD_JC], n_rng[SAD_JC];
-    bool any = false;
-#pragma unroll
-    for (int jj = 0; jj < SAD_JC; ++jj) {
-        lo0[jj] = hi0[jj] = lo1[jj] = hi1[jj] = inf;   // nothing is counted or parked for an absent / flagged offset
-        n_lt[jj] = n_ge[jj] = n_rng[jj] = 0u;
-        if (j0 + jj < J) {
-            const SadOff* q = off + oi * J + j0 + jj;
-            if (!q->flag) { lo0[jj] = q->lo[0]; hi0[jj] = q->hi[0]; lo1[jj] = q->lo[1]; hi1[jj] = q->hi[1]; any = true; }
-        }
-    }
-    if (!any) return;   // CTA-uniform
     for (int k = tid; k < SAD_JC * 2 * SAD_B; k += SAD_TV) sh_hist[k] = 0u;
     if (tid < SAD_JC) {
-        const int jj = tid;
-        float b[8] = {inf, inf, inf, inf, 0.f, 0.f, inf, 0.f};
-        if (j0 + jj < J) {
-            const SadOff* q = off + oi * J + j0 + jj;
-            if (!q->flag) { b[0] = q->lo[0]; b[1] = q->hi[0]; b[2] = q->lo[1]; b[3] = q->hi[1]; b[4] = q->sc[0]; b[5] = q->sc[1]; b[6] = q->mid; }
+        float b[4] = {0.f, inf, inf, 0.f};   // absent / flagged offset (a = b = inf): nothing is parked
+        if (tid < nj) {
+            const SadOff* q = off + oi * J + j0 + tid;
+            if (!q->flag) { b[0] = q->c; b[1] = q->a; b[2] = q->b; b[3] = q->sc; }
         }
-        for (int k = 0; k < 8; ++k) sh_b[jj * 8 + k] = b[k];
-        sh_cnt[jj * 4 + 0] = sh_cnt[jj * 4 + 1] = sh_cnt[jj * 4 + 2] = sh_cnt[jj * 4 + 3] = 0u;
+        for (int k = 0; k < 4; ++k) sh_b[tid * 4 + k] = b[k];
+        sh_cnt[tid * 2 + 0] = sh_cnt[tid * 2 + 1] = 0u;
     }
-    SadTiles tl;
-    tl.ks = ks; tl.rs = rs;
-    // thread-private parking slots: slot k of thread t at sh_priv[k * SAD_TV + t]; `ptr` = shared address of the next free one
-    const unsigned mine = (unsigned)__cvta_generic_to_shared(sh_priv + tid);
-    unsigned ptr = mine;
-    // tag = jj, read back from memory so that it stays in a register (a compile-time constant would be re-materialised
-    // before every use): clearing the low mantissa bits and inserting the tag is then ONE three-input logic instruction
-    unsigned tag[SAD_JC];
+    float c0[SAD_JC], cg[SAD_JC];
 #pragma unroll
-    for (int jj = 0; jj < SAD_JC; ++jj) tag[jj] = (unsigned)jj + (unsigned)off[oi * J + (j0 + jj < J ? j0 + jj : J - 1)].pad;
-    auto drain = [&]() {
-        const unsigned c = (ptr - mine) / (SAD_TV * 4);
-        const unsigned cmax = __reduce_max_sync(0xffffffffu, c);
-        for (unsigned k = 0; k < cmax; ++k) {
-            if (k < c) {
-                unsigned pk;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pk) : "r"(mine + k * (SAD_TV * 4)));
-                const int jj = (int)(pk & 7u);
-                const float dt = __uint_as_float(pk & ~7u);
-                const float* b = sh_b + jj * 8;
-                const int r = dt > b[6] ? 1 : 0;
-                atomicAdd(&sh_hist[(jj * 2 + r) * SAD_B + sad_bin(dt, b[2 * r], b[4 + r])], 1u);
-            }
-        }
-        ptr = mine;
-    };
+    for (int jj = 0; jj < SAD_JC; ++jj) c0[jj] = cg[jj] = 0.0f;
+    // parking slots of one offset pair: the first offset fills the thread's slots upwards from slot 0, the second one
+    // downwards from the last slot -- no tag is needed to tell them apart and SAD_TU hits each always fit
+    const unsigned mineA = (unsigned)__cvta_generic_to_shared(sh_priv + tid);
+    const unsigned mineB = mineA + (SAD_PRIV - 1) * SAD_TV * 4;
     const int ntv = (kw + SAD_TV - 1) / SAD_TV, ntu = (kh + SAD_TU - 1) / SAD_TU;
     for (int t = blockIdx.x; t < ntv * ntu; t += gridDim.x) {
         const int tu = t / ntv, tv = t - tu * ntv;
-        __syncthreads();   // the previous tile is no longer read (also orders the histogram / bound set-up on the first trip)
-        sad_load_tile(rz, kz, W, kh, kw, oi, j0, tu * SAD_TU, tv * SAD_TV, tl);
+        __syncthreads();   // the previous tile is no longer read (also orders the set-up above on the first trip)
+        sad_load_tile(rz, kz, W, kh, kw, oi, j0, tu * SAD_TU, tv * SAD_TV, ks, rs);
         __syncthreads();
+        float kv[SAD_TU];
 #pragma unroll
-        for (int r = 0; r < SAD_TU; ++r) {
-            const float kv = ks[r * SAD_TV + tid];
-            const float* rr = rs + r * SAD_RP + tid;
+        for (int r = 0; r < SAD_TU; ++r) kv[r] = ks[r * SAD_TV + tid];
 #pragma unroll
-            for (int jj = 0; jj < SAD_JC; ++jj) {
-                const float d = rr[jj] - kv;
-                // The classification step in PTX, so that every counter update is ONE predicated add and the parking ONE
-                // predicated store + pointer bump (the compiler's own if-conversion emitted select pairs: 19 instructions
-                // per difference instead of 13).  NaN (a masked pixel) fails every comparison.
-                //   ge  = d >= lo0          rng = ge && d <= hi1          lt = d < lo0
-                //   in  = rng && (d <= hi0 || d >= lo1)  -> park (bits(d) & ~7) | tag
-                asm volatile(
-                    "{\n\t"
-                    ".reg .pred pge, prng, plt, pa, pb, pin;\n\t"
-                    ".reg .b32 t;\n\t"
-                    "setp.ge.f32 pge, %4, %5;\n\t"
-                    "setp.le.and.f32 prng, %4, %8, pge;\n\t"
-                    "setp.lt.f32 plt, %4, %5;\n\t"
-                    "setp.le.f32 pa, %4, %6;\n\t"
-                    "setp.ge.or.f32 pb, %4, %7, pa;\n\t"
-                    "and.pred pin, prng, pb;\n\t"
-                    "@pge add.u32 %0, %0, 1;\n\t"
-                    "@prng add.u32 %1, %1, 1;\n\t"
-                    "@plt add.u32 %2, %2, 1;\n\t"
-                    "mov.b32 t, %4;\n\t"
-                    "lop3.b32 t, t, 0xfffffff8, %9, 0xEA;\n\t"
-                    "@pin st.shared.u32 [%3], t;\n\t"
-                    "@pin add.u32 %3, %3, %10;\n\t"
-                    "}"
-                    : "+r"(n_ge[jj]), "+r"(n_rng[jj]), "+r"(n_lt[jj]), "+r"(ptr)
-                    : "f"(d), "f"(lo0[jj]), "f"(hi0[jj]), "f"(lo1[jj]), "f"(hi1[jj]), "r"(tag[jj]), "n"(SAD_TV * 4));
+        for (int jp = 0; jp < SAD_JC; jp += 2) {
+            if (jp >= nj) break;   // CTA-uniform
+            const float4 ba = *reinterpret_cast<const float4*>(sh_b + jp * 4);          // c a b sc (broadcast loads)
+            const float4 bb = *reinterpret_cast<const float4*>(sh_b + (jp + 1) * 4);
+            const float nba = -ba.z, nbb = -bb.z;
+            unsigned pa = mineA, pb = mineB;
+            const float* rr = rs + tid + jp;
+#pragma unroll
+            for (int r = 0; r < SAD_TU; ++r) {
+                const float da = rr[r * SAD_RP] - kv[r];
+                const float db = rr[r * SAD_RP + 1] - kv[r];
+                SAD_P1_STEP(da, c0[jp], cg[jp], pa, ba.x, nba, ba.y, ba.z, SAD_TV * 4);
+                SAD_P1_STEP(db, c0[jp + 1], cg[jp + 1], pb, bb.x, nbb, bb.y, bb.z, -SAD_TV * 4);
             }
-            if ((r % SAD_DRAIN) == SAD_DRAIN - 1) drain();
+            // drain the parked e into the bracket histograms: ONE value per trip (first the slots of the first offset, then
+            // those of the second), warp-uniform trip count; e < 0 -> bracket of P25
+            const unsigned na = (pa - mineA) / (SAD_TV * 4), nb = (mineB - pb) / (SAD_TV * 4);
+            const unsigned nmax = __reduce_max_sync(0xffffffffu, na + nb);
+            for (unsigned k = 0; k < nmax; ++k) {
+                if (k < na + nb) {
+                    const bool second = k >= na;
+                    float e;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(e) : "r"(second ? mineB - (k - na) * (SAD_TV * 4) : mineA + k * (SAD_TV * 4)));
+                    const float a_ = second ? bb.y : ba.y, nb_ = second ? nbb : nba, sc_ = second ? bb.w : ba.w;
+                    const int q = e > 0.0f ? 1 : 0;
+                    atomicAdd(&sh_hist[((jp + (second ? 1 : 0)) * 2 + q) * SAD_B + sad_bin(e, q ? a_ : nb_, sc_)], 1u);
+                }
+            }
         }
     }
     // counters -> shared -> global
     __syncthreads();
 #pragma unroll
     for (int jj = 0; jj < SAD_JC; ++jj) {
-        const unsigned a = __reduce_add_sync(0xffffffffu, n_lt[jj]);
-        const unsigned b = __reduce_add_sync(0xffffffffu, n_ge[jj]);
-        const unsigned d = __reduce_add_sync(0xffffffffu, n_rng[jj]);
+        const unsigned a = __reduce_add_sync(0xffffffffu, (unsigned)c0[jj]);
+        const unsigned b = __reduce_add_sync(0xffffffffu, (unsigned)cg[jj]);
         if ((tid & 31) == 0) {
-            if (a) atomicAdd(&sh_cnt[jj * 4 + 0], a);
-            if (b) atomicAdd(&sh_cnt[jj * 4 + 1], b);
-            if (d) atomicAdd(&sh_cnt[jj * 4 + 2], d);
+            if (a) atomicAdd(&sh_cnt[jj * 2 + 0], a);
+            if (b) atomicAdd(&sh_cnt[jj * 2 + 1], b);
         }
     }
     __syncthreads();
-    if (tid < SAD_JC && j0 + tid < J) {
+    if (tid < nj) {
         SadOff* q = off + oi * J + j0 + tid;
-        if (sh_cnt[tid * 4 + 0]) atomicAdd(&q->n_lt, (unsigned long long)sh_cnt[tid * 4 + 0]);
-        if (sh_cnt[tid * 4 + 1]) atomicAdd(&q->n_ge, (unsigned long long)sh_cnt[tid * 4 + 1]);
-        if (sh_cnt[tid * 4 + 2]) atomicAdd(&q->n_rng, (unsigned long long)sh_cnt[tid * 4 + 2]);
+        if (sh_cnt[tid * 2 + 0]) atomicAdd(&q->n_c0, (unsigned long long)sh_cnt[tid * 2 + 0]);
+        if (sh_cnt[tid * 2 + 1]) atomicAdd(&q->n_gap, (unsigned long long)sh_cnt[tid * 2 + 1]);
     }
-    for (int k = tid; k < SAD_JC * 2 * SAD_B; k += SAD_TV) {
+    for (int k = tid; k < nj * 2 * SAD_B; k += SAD_TV) {
         const unsigned v = sh_hist[k];
-        const int jj = k / (2 * SAD_B);
-        if (v && j0 + jj < J) atomicAdd(&ghist[(size_t)(oi * J + j0) * 2 * SAD_B + k], v);
+        if (v) atomicAdd(&ghist[(size_t)(oi * J + j0) * 2 * SAD_B + k], v);
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // find: ranks -> histogram bins -> exact float thresholds
 // ------------------------------------------------------------------------------------------
-// smallest float x in [lo, hi] with sad_bin(trunc(x), lo, sc) >= b; nextafter(hi) when there is none
+// smallest float e in [lo, hi] with sad_bin(e, lo, sc) >= b; nextafter(hi) when there is none
 __device__ float sad_threshold(int b, float lo, float hi, float sc) {
     unsigned a = dcr_f2key(lo), z = dcr_f2key(hi);
-    auto pred = [&](unsigned key) { return sad_bin(__uint_as_float(sad_trunc_bits(dcr_key2f(key))), lo, sc) >= b; };
+    auto pred = [&](unsigned key) { return sad_bin(dcr_key2f(key), lo, sc) >= b; };
     if (!pred(z)) return nextafterf(hi, INFINITY);
     while (a < z) {   // invariant: pred(z) true
         const unsigned mid = a + ((z - a) >> 1);
@@ -391,21 +440,21 @@ __global__ void __launch_bounds__(256) sad_find_kernel(SadOff* __restrict__ off,
     if (q->flag) return;
     for (int r = 0; r < 2; ++r) {
         const unsigned* h = ghist + ((size_t)o * 2 + r) * SAD_B;
-        const unsigned a = h[2 * threadIdx.x], b = h[2 * threadIdx.x + 1];
+        const unsigned a = h[threadIdx.x];   // SAD_B == blockDim.x
         unsigned tot;
-        const unsigned ex = dcr_block_excl_scan(a + b, s_scratch, &tot);
-        s_cum[r][2 * threadIdx.x] = ex;
-        s_cum[r][2 * threadIdx.x + 1] = ex + a;
+        const unsigned ex = dcr_block_excl_scan(a, s_scratch, &tot);
+        s_cum[r][threadIdx.x] = ex;
         if (threadIdx.x == 0) s_cum[r][SAD_B] = tot;
         __syncthreads();
     }
     if (threadIdx.x) return;
-    const long long N = (long long)(q->n_lt + q->n_ge);
-    q->count = N;
+    const long long N = q->count;
     if (N == 0) { q->done = 1; m_out[o] = __longlong_as_double(0x7ff8000000000000LL); return; }
-    const long long in0 = s_cum[0][SAD_B], in1 = s_cum[1][SAD_B];
-    // differences below each bracket
-    const long long below[2] = {(long long)q->n_lt, (long long)q->n_lt + (long long)q->n_rng - in1};
+    // differences below each bracket: e < -b ; e < a (= those + the P25 bracket + the gap)
+    const long long below0 = N - (long long)q->n_c0;
+    const long long below[2] = {below0, below0 + (long long)s_cum[0][SAD_B] + (long long)q->n_gap};
+    if (below0 < 0) { q->flag = 6; return; }
+    const float elo[2] = {-q->b, q->a}, ehi[2] = {-q->a, q->b};   // the brackets in e
     int blo[2], bhi[2];
     for (int r = 0; r < 2; ++r) {
         const double vi = (double)(N - 1) * (r == 0 ? 0.25 : 0.75);   // numpy's virtual index, float64
@@ -413,9 +462,9 @@ __global__ void __launch_bounds__(256) sad_find_kernel(SadOff* __restrict__ off,
         const long long khi = klo + 1 < N ? klo + 1 : N - 1;
         q->g[r] = vi - (double)klo;
         const long long c0 = klo - below[r], c1 = khi - below[r];
-        const long long nin = r == 0 ? in0 : in1;
+        const long long nin = (long long)s_cum[r][SAD_B];
         if (c0 < 0 || c1 >= nin) { q->flag = 2; return; }   // a rank outside its bracket
-        int b0 = 0, b1 = 0;
+        int b0, b1;
         {
             int lo = 0, hi = SAD_B - 1;
             while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((long long)s_cum[r][mid] <= c0) lo = mid; else hi = mid - 1; }
@@ -430,8 +479,8 @@ __global__ void __launch_bounds__(256) sad_find_kernel(SadOff* __restrict__ off,
         q->want[r] = want;
         q->k[r] = (unsigned)(c0 - (long long)s_cum[r][b0]);
         q->k2[r] = (unsigned)(c1 - (long long)s_cum[r][b0]);
-        q->ta[r] = b0 == 0 ? q->lo[r] : sad_threshold(b0, q->lo[r], q->hi[r], q->sc[r]);
-        q->tb[r] = b1 == SAD_B - 1 ? nextafterf(q->hi[r], INFINITY) : sad_threshold(b1 + 1, q->lo[r], q->hi[r], q->sc[r]);
+        q->ta[r] = b0 == 0 ? elo[r] : sad_threshold(b0, elo[r], ehi[r], q->sc);
+        q->tb[r] = b1 == SAD_B - 1 ? nextafterf(ehi[r], INFINITY) : sad_threshold(b1 + 1, elo[r], ehi[r], q->sc);
     }
     // differences in [tb[0], ta[1]): below ta[1] minus below tb[0]
     q->n_mid = (below[1] + (long long)s_cum[1][blo[1]]) - (below[0] + (long long)s_cum[0][bhi[0] + 1]);
@@ -441,64 +490,102 @@ __global__ void __launch_bounds__(256) sad_find_kernel(SadOff* __restrict__ off,
 // ------------------------------------------------------------------------------------------
 // pass 2
 // ------------------------------------------------------------------------------------------
-#define SAD_P2_SMEM ((SAD_TU * SAD_TV + SAD_TU * SAD_RP) * 4)
+#define SAD_P2_SMEM ((SAD_TU * SAD_TV + SAD_TU * SAD_RP + SAD_PRIV * SAD_TV + SAD_JC * 8) * 4)
 
-__global__ void __launch_bounds__(SAD_TV, 2) sad_pass2_kernel(const float* __restrict__ rz, const float* __restrict__ kz, int W,
+// One difference d, e = d - c, thresholds in e: ta0 <= tb0 <= ta1 <= tb1.  [tb0, ta1) is the middle (|d| summed), the rest
+// of [ta0, tb1) are the candidates of the two quantiles (d parked).
+#define SAD_P2_STEP(D, S, PTR, CC, TA0, TB0, TA1, TB1, STEP)                                                        \
+    asm volatile(                                                                                                    \
+        "{\n\t"                                                                                                      \
+        ".reg .pred p0, pr, p2, pm, ph;\n\t"                                                                         \
+        ".reg .f32 e, ad;\n\t"                                                                                       \
+        "sub.f32 e, %2, %3;\n\t"                                                                                     \
+        "setp.ge.f32 p0, e, %4;\n\t"                                                                                 \
+        "setp.lt.and.f32 pr, e, %7, p0;\n\t"                                                                         \
+        "setp.ge.f32 p2, e, %5;\n\t"                                                                                 \
+        "setp.lt.and.f32 pm, e, %6, p2;\n\t"                                                                         \
+        "and.pred ph, pr, !pm;\n\t"                                                                                  \
+        "abs.f32 ad, %2;\n\t"                                                                                        \
+        "@pm add.f32 %0, %0, ad;\n\t"                                                                                \
+        "@ph st.shared.f32 [%1], %2;\n\t"                                                                            \
+        "@ph add.s32 %1, %1, %8;\n\t"                                                                                \
+        "}"                                                                                                          \
+        : "+f"(S), "+r"(PTR)                                                                                         \
+        : "f"(D), "f"(CC), "f"(TA0), "f"(TB0), "f"(TA1), "f"(TB1), "n"(STEP))
+
+__global__ void __launch_bounds__(SAD_TV, 4) sad_pass2_kernel(const float* __restrict__ rz, const float* __restrict__ kz, int W,
                                                               int kh, int kw, int J, int nchunk, SadOff* off,
                                                               float* __restrict__ cand, double* __restrict__ part) {
     extern __shared__ __align__(16) unsigned char sad_smem[];
     float* ks = reinterpret_cast<float*>(sad_smem);
     float* rs = ks + SAD_TU * SAD_TV;
+    float* sh_priv = rs + SAD_TU * SAD_RP;
+    float* sh_b = sh_priv + SAD_PRIV * SAD_TV;      // [SAD_JC][8]: ta0 tb0 ta1 tb1 | c - - -
     __shared__ double s_red[SAD_TV / 32][SAD_JC];
     const int tid = threadIdx.x;
     const int oi = blockIdx.y / nchunk, j0 = (blockIdx.y - oi * nchunk) * SAD_JC;
+    const int nj = min(SAD_JC, J - j0);
     const float inf = INFINITY;
-    float ta0[SAD_JC], tb0[SAD_JC], ta1[SAD_JC], tb1[SAD_JC];
-    double acc[SAD_JC];
-    bool any = false;
-#pragma unroll
-    for (int jj = 0; jj < SAD_JC; ++jj) {
-        ta0[jj] = tb0[jj] = ta1[jj] = tb1[jj] = inf;
-        acc[jj] = 0.0;
-        if (j0 + jj < J) {
-            const SadOff* q = off + oi * J + j0 + jj;
-            if (!q->flag && !q->done) { ta0[jj] = q->ta[0]; tb0[jj] = q->tb[0]; ta1[jj] = q->ta[1]; tb1[jj] = q->tb[1]; any = true; }
+    if (tid < SAD_JC) {
+        float b[8] = {inf, inf, inf, inf, 0.f, 0.f, 0.f, 0.f};
+        if (tid < nj) {
+            const SadOff* q = off + oi * J + j0 + tid;
+            if (!q->flag && !q->done) { b[0] = q->ta[0]; b[1] = q->tb[0]; b[2] = q->ta[1]; b[3] = q->tb[1]; b[4] = q->c; }
         }
+        for (int k = 0; k < 8; ++k) sh_b[tid * 8 + k] = b[k];
     }
-    SadTiles tl;
-    tl.ks = ks; tl.rs = rs;
-    if (any) {
-        const int ntv = (kw + SAD_TV - 1) / SAD_TV, ntu = (kh + SAD_TU - 1) / SAD_TU;
-        for (int t = blockIdx.x; t < ntv * ntu; t += gridDim.x) {
-            const int tu = t / ntv, tv = t - tu * ntv;
-            __syncthreads();
-            sad_load_tile(rz, kz, W, kh, kw, oi, j0, tu * SAD_TU, tv * SAD_TV, tl);
-            __syncthreads();
-            float s[SAD_JC];
+    double acc[SAD_JC];
 #pragma unroll
-            for (int jj = 0; jj < SAD_JC; ++jj) s[jj] = 0.0f;
+    for (int jj = 0; jj < SAD_JC; ++jj) acc[jj] = 0.0;
+    const unsigned mineA = (unsigned)__cvta_generic_to_shared(sh_priv + tid);
+    const unsigned mineB = mineA + (SAD_PRIV - 1) * SAD_TV * 4;
+    const int ntv = (kw + SAD_TV - 1) / SAD_TV, ntu = (kh + SAD_TU - 1) / SAD_TU;
+    for (int t = blockIdx.x; t < ntv * ntu; t += gridDim.x) {
+        const int tu = t / ntv, tv = t - tu * ntv;
+        __syncthreads();
+        sad_load_tile(rz, kz, W, kh, kw, oi, j0, tu * SAD_TU, tv * SAD_TV, ks, rs);
+        __syncthreads();
+        float kv[SAD_TU];
+#pragma unroll
+        for (int r = 0; r < SAD_TU; ++r) kv[r] = ks[r * SAD_TV + tid];
+#pragma unroll
+        for (int jp = 0; jp < SAD_JC; jp += 2) {
+            if (jp >= nj) break;   // CTA-uniform
+            const float4 ba = *reinterpret_cast<const float4*>(sh_b + jp * 8);
+            const float4 bb = *reinterpret_cast<const float4*>(sh_b + (jp + 1) * 8);
+            const float ca = sh_b[jp * 8 + 4], cb = sh_b[(jp + 1) * 8 + 4];
+            unsigned pa = mineA, pb = mineB;
+            float sa = 0.0f, sb = 0.0f;
+            const float* rr = rs + tid + jp;
 #pragma unroll
             for (int r = 0; r < SAD_TU; ++r) {
-                const float kv = ks[r * SAD_TV + tid];
-                const float* rr = rs + r * SAD_RP + tid;
-#pragma unroll
-                for (int jj = 0; jj < SAD_JC; ++jj) {
-                    const float d = rr[jj] - kv;
-                    const bool c0 = (d >= ta0[jj]) && (d < tb0[jj]);
-                    const bool ge = d >= tb0[jj];
-                    const bool mid = ge && (d < ta1[jj]);
-                    const bool c1 = ge && !mid && (d < tb1[jj]);
-                    if (mid) s[jj] += fabsf(d);
-                    if (c0 || c1) {   // a few hundred per offset and quantile
-                        SadOff* q = off + oi * J + j0 + jj;
-                        const int r2 = c1 ? 1 : 0;
-                        const unsigned pos = atomicAdd(&q->ncand[r2], 1u);
-                        if (pos < SAD_CAP) cand[((size_t)(oi * J + j0 + jj) * 2 + r2) * SAD_CAP + pos] = d;
-                    }
+                const float da = rr[r * SAD_RP] - kv[r];
+                const float db = rr[r * SAD_RP + 1] - kv[r];
+                SAD_P2_STEP(da, sa, pa, ca, ba.x, ba.y, ba.z, ba.w, SAD_TV * 4);
+                SAD_P2_STEP(db, sb, pb, cb, bb.x, bb.y, bb.z, bb.w, -SAD_TV * 4);
+            }
+            acc[jp] += (double)sa;         // <= SAD_TU float32 terms per partial
+            acc[jp + 1] += (double)sb;
+            // the few hundred candidates per offset and quantile: appended to the offset's global lists
+            const unsigned na = (pa - mineA) / (SAD_TV * 4), nb = (mineB - pb) / (SAD_TV * 4);
+            if (__any_sync(0xffffffffu, (na | nb) != 0u)) {
+                for (unsigned k = 0; k < na; ++k) {
+                    float d;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(d) : "r"(mineA + k * (SAD_TV * 4)));
+                    const int q = (d - ca) < ba.y ? 0 : 1;
+                    SadOff* so = off + oi * J + j0 + jp;
+                    const unsigned pos = atomicAdd(&so->ncand[q], 1u);
+                    if (pos < SAD_CAP) cand[((size_t)(oi * J + j0 + jp) * 2 + q) * SAD_CAP + pos] = d;
+                }
+                for (unsigned k = 0; k < nb; ++k) {
+                    float d;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(d) : "r"(mineB - k * (SAD_TV * 4)));
+                    const int q = (d - cb) < bb.y ? 0 : 1;
+                    SadOff* so = off + oi * J + j0 + jp + 1;
+                    const unsigned pos = atomicAdd(&so->ncand[q], 1u);
+                    if (pos < SAD_CAP) cand[((size_t)(oi * J + j0 + jp + 1) * 2 + q) * SAD_CAP + pos] = d;
                 }
             }
-#pragma unroll
-            for (int jj = 0; jj < SAD_JC; ++jj) acc[jj] += (double)s[jj];   // <= 8 float32 terms per partial
         }
     }
     // fixed-order reduction of the per-thread FP64 partials: lanes (shuffle tree), warps (serial), one slot per CTA
@@ -508,7 +595,7 @@ __global__ void __launch_bounds__(SAD_TV, 2) sad_pass2_kernel(const float* __res
         if ((tid & 31) == 0) s_red[tid >> 5][jj] = v;
     }
     __syncthreads();
-    if (tid < SAD_JC && j0 + tid < J) {
+    if (tid < nj) {
         double v = 0.0;
         for (int w = 0; w < SAD_TV / 32; ++w) v += s_red[w][tid];
         part[(size_t)(oi * J + j0 + tid) * gridDim.x + blockIdx.x] = v;
@@ -636,6 +723,8 @@ __global__ void sad_sum_final_kernel(const SadPartial* __restrict__ part, int np
 
 struct SadWs {
     float* rz; float* kz;
+    unsigned* rb; unsigned* kb;   // validity bit planes (rwp / kwp words per row)
+    int rwp, kwp;
     SadOff* off;
     unsigned* ghist;
     float* cand;
@@ -651,7 +740,7 @@ struct SadWs {
 
 static int sad_p2_grid_x(int J) {
     const int nchunk = (J + SAD_JC - 1) / SAD_JC;
-    int gx = (dcr_num_sms() * 6 + J * nchunk - 1) / (J * nchunk);
+    int gx = (dcr_num_sms() * 12 + J * nchunk - 1) / (J * nchunk);   // ~3 waves of 4 CTAs per SM
     return gx < 1 ? 1 : gx;
 }
 
@@ -659,7 +748,8 @@ static size_t sad_ws_bytes(int h, int w, int pad) {
     const long long kh = h - 2 * pad, kw = w - 2 * pad;
     const long long n = kh * kw;
     const long long JJ = (long long)(2 * pad + 1) * (2 * pad + 1);
-    return dcr_al256((size_t)h * w * 4) + dcr_al256((size_t)n * 4) + dcr_al256((size_t)JJ * sizeof(SadOff)) +
+    return dcr_al256((size_t)h * w * 4) + dcr_al256((size_t)n * 4) + dcr_al256((size_t)h * (w / 32 + 12) * 4) +
+           dcr_al256((size_t)kh * ((kw + 31) / 32) * 4) + dcr_al256((size_t)JJ * sizeof(SadOff)) +
            dcr_al256((size_t)JJ * 2 * SAD_B * 4) + dcr_al256((size_t)JJ * 2 * SAD_CAP * 4) +
            dcr_al256((size_t)JJ * sad_p2_grid_x(2 * pad + 1) * 8) + dcr_al256((size_t)JJ * 8) +
            dcr_al256((size_t)n * 4) + dcr_al256((size_t)n) + dcr_al256(4 * sizeof(SelState)) +
@@ -676,6 +766,11 @@ static int sad_carve(void* workspace, size_t bytes, int h, int w, int pad, SadWs
     DcrBump ws(workspace, bytes);
     s->rz = ws.take<float>((size_t)h * w);
     s->kz = ws.take<float>(n);
+    s->rwp = w / 32 + 12;         // zero words of padding past the last (possibly partial) word: the count kernel's
+                                  // 32-column offset chunks read up to 9 words past it
+    s->kwp = (int)((kw + 31) / 32);
+    s->rb = ws.take<unsigned>((size_t)h * s->rwp);
+    s->kb = ws.take<unsigned>((size_t)kh * s->kwp);
     s->off = ws.take<SadOff>(JJ);
     s->ghist = ws.take<unsigned>((size_t)JJ * 2 * SAD_B);
     s->cand = ws.take<float>((size_t)JJ * 2 * SAD_CAP);
@@ -686,7 +781,7 @@ static int sad_carve(void* workspace, size_t bytes, int h, int w, int pad, SadWs
     s->sst = ws.take<SelState>(4);
     s->selhist = ws.take<unsigned>(DCR_SEL_HIST_WORDS);
     s->spart = ws.take<SadPartial>(4096);
-    if (!s->rz || !s->kz || !s->off || !s->ghist || !s->cand || !s->part || !s->dm || !s->diff || !s->dmask || !s->sst ||
+    if (!s->rz || !s->kz || !s->rb || !s->kb || !s->off || !s->ghist || !s->cand || !s->part || !s->dm || !s->diff || !s->dmask || !s->sst ||
         !s->selhist || !s->spart) {
         dcr_set_error("workspace too small");
         return -1;
@@ -751,9 +846,13 @@ extern "C" int dcr_sad_search_ex(const float* ref, const uint8_t* ref_mask, cons
     }
     DCR_CUDA_OK(cudaFuncSetAttribute(sad_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SAD_S * 4));
     DCR_CUDA_OK(cudaFuncSetAttribute(sad_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SAD_P1_SMEM));
+    DCR_CUDA_OK(cudaFuncSetAttribute(sad_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SAD_P2_SMEM));
     SAD_MARK(0);
-    sad_prep_kernel<<<g, 256, 0, s>>>(ref, ref_mask, stride, 0, 0, h, w, ws.rz);
-    sad_prep_kernel<<<g, 256, 0, s>>>(src, src_mask, stride, pad, pad, kh, kw, ws.kz);
+    DCR_CUDA_OK(cudaMemsetAsync(ws.rb, 0, (size_t)h * ws.rwp * 4, s));
+    DCR_CUDA_OK(cudaMemsetAsync(ws.off, 0, (size_t)JJ * sizeof(SadOff), s));
+    sad_prep_kernel<<<g, 256, 0, s>>>(ref, ref_mask, stride, 0, 0, h, w, ws.rz, ws.rb, ws.rwp);
+    sad_prep_kernel<<<g, 256, 0, s>>>(src, src_mask, stride, pad, pad, kh, kw, ws.kz, ws.kb, ws.kwp);
+    sad_count_kernel<<<dim3(SAD_CNT_SEG, J, (J + 31) / 32), 256, 0, s>>>(ws.rb, ws.rwp, ws.kb, ws.kwp, kh, J, ws.off);
     DCR_CUDA_OK(cudaMemsetAsync(ws.ghist, 0, (size_t)JJ * 2 * SAD_B * 4, s));
     SAD_MARK(1);
     sad_sample_kernel<<<JJ, 1024, SAD_S * 4, s>>>(ws.rz, ws.kz, w, kh, kw, J, ws.off);

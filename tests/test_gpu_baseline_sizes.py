@@ -101,8 +101,9 @@ def test_config3_4096_ncc(cuda):
     np.testing.assert_allclose(m, mo, rtol=0, atol=2e-6 * np.abs(mo).max())
     assert tuple(io) == tuple(ioo)
     np.testing.assert_allclose(so, soo, atol=1e-4)
-    # the injected displacement, in pixels (row, col): src[i, j] = T(x_j + 5.3 px, y_i - 3.6 px)
-    assert abs(so[1] - 5.3) < 0.2 and abs(so[0] - 3.6) < 0.2, so
+    # (the correlation peak of z-scored fractal terrain is broad: NCC lands within a pixel of the injected (3.6, 5.3) px
+    # displacement -- exactly where scipy's correlate2d puts it; the sharper SAD minimum recovers it to 0.05 px, below)
+    assert abs(so[1] - 5.3) < 1.5 and abs(so[0] - 3.6) < 1.5, so
 
 
 def test_config3_4096_sad(cuda):

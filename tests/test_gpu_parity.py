@@ -666,16 +666,21 @@ def test_native_align_loop_equals_python_loop(cuda, n, nodata):
 
 
 def test_native_align_stepper_many_steps(cuda):
-    """Stepping past DCR_ALIGN_MAX_PENDING folds the pending z shifts into the band; the band after finish() equals
-    the band of the python loop run for the same number of iterations (tol=0)."""
+    """Stepping: the native state is the only owner of the deferred z shifts and step() / run() fold them into the band
+    before they return, so `src` is consistent (band + geotransform) whenever the interpreter looks at it; a run(4) in the
+    middle passes DCR_ALIGN_MAX_PENDING inside one native call.  The band equals the python loop's after the same number of
+    iterations (tol=0)."""
     from demcoreg_b200 import dem_align, engine
     p = _pair(n=512, res=30.0)
     ref, src = _gds(p, 'ref'), _gds(p, 'src')
     al = engine.NuthAligner(ref, src, tol=0.0, max_iter=1 << 30)
-    for _ in range(6):
-        r = al.step()
-        assert r.status == 0 and len(al.src.pending_dz) == 0 or True
-    assert al.st.n_done == 6 and al.st.src_ndz == 2
+    r = al.step()
+    assert r.status == 0 and al.st.src_ndz == 0 and src.pending_dz == []
+    one = dem_align.align(_gds(p, 'ref'), _gds(p, 'src'), tol=0.0, max_iter=1, verbose=False, records=[])
+    assert src.gt == one['src_align'].gt and np.array_equal(src.numpy(), one['src_align'].numpy())   # no double shift
+    assert len(al.run(max_steps=4)) == 4
+    al.step()
+    assert al.st.n_done == 6 and al.st.src_ndz == 0 and len(al.iters) == 6
     al.finish()
     b = dem_align.align(_gds(p, 'ref'), _gds(p, 'src'), tol=0.0, max_iter=6, verbose=False, records=[])
     assert b['n_iter'] == 6
