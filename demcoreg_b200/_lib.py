@@ -7,12 +7,13 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdemcoreg_b200.so")
+# DCR_LIB: another build of the SAME library (A/B timing of kernel variants, profiles/experiments); never a fallback
+LIB_PATH = os.environ.get("DCR_LIB") or os.path.join(_HERE, "csrc", "libdemcoreg_b200.so")
 
 NBINS = 360
 M_BASE, M_MAXDZ, M_MAD, M_SLOPE, M_ASPECT = 0x01, 0x02, 0x04, 0x08, 0x10
 M_DIFF = M_BASE | M_MAXDZ | M_MAD | M_SLOPE
-ITER_REMOVE_OUTLIERS, ITER_PROFILE, ITER_RADIX_ONLY, ITER_APPLY_Z = 1, 2, 4, 8
+ITER_REMOVE_OUTLIERS, ITER_PROFILE, ITER_RADIX_ONLY, ITER_APPLY_Z, ITER_TAN_SLOPE = 1, 2, 4, 8, 16
 SAD_PER_OFFSET = 1
 
 

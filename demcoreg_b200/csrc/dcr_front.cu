@@ -921,6 +921,18 @@ __device__ __forceinline__ double fast_xrow(const double* __restrict__ w, const 
     return (double)q[1];
 }
 
+// warped value of the pixel whose 4x4 taps start at (r0, c0) of the source footprint tile, all taps finite
+template <bool FX, bool FY>
+__device__ __forceinline__ float fast_px(const float* __restrict__ t, int r0, int c0, const DevGeom& g) {
+    const float* q = t + r0 * F_SRC_C + c0;
+    if (FY) {
+        const double v0 = fast_xrow<FX>(g.wx, q), v1 = fast_xrow<FX>(g.wx, q + F_SRC_C),
+                     v2 = fast_xrow<FX>(g.wx, q + 2 * F_SRC_C), v3 = fast_xrow<FX>(g.wx, q + 3 * F_SRC_C);
+        return (float)ypass(g.wy, v0, v1, v2, v3);
+    }
+    return (float)fast_xrow<FX>(g.wx, q + F_SRC_C);
+}
+
 // exact Horn slope / aspect of one window (GDAL's FP64 formulation) for the guard-band pixels of the fast path
 __device__ __noinline__ void horn_exact(float w0, float w1, float w2, float w3, float w5, float w6, float w7, float w8,
                                         double ewres, double nsres, float* slope_deg, float* tan_slope, float* aspect) {
@@ -950,7 +962,17 @@ __device__ __noinline__ void horn_exact(float w0, float w1, float w2, float w3, 
     }
 }
 
-template <int AX, bool LOOPMODE>
+// Unroll factors of the two row loops: fully unrolled the kernel is 61 KB of SASS, twice the 32 KB instruction cache of an
+// SM, and 36 % of the warp-stall samples were instruction fetches (profiles/r2/front_fast_r2c_sass.txt)
+#ifndef DCR_FF_UNROLL_MAIN
+#define DCR_FF_UNROLL_MAIN 7
+#endif
+#ifndef DCR_FF_UNROLL_HORN
+#define DCR_FF_UNROLL_HORN 2
+#endif
+constexpr int FF_UNROLL_MAIN = DCR_FF_UNROLL_MAIN, FF_UNROLL_HORN = DCR_FF_UNROLL_HORN;
+// MODE: 0 = slope in degrees + aspect raster, 1 = slope in degrees, no aspect raster, 2 = tan(slope), no aspect raster
+template <int AX, int MODE>
 __global__ void __launch_bounds__(256, 4) front_fast_kernel(const __grid_constant__ FrontParams p) {
     constexpr bool SX = (AX & 1) != 0, SY = (AX & 2) != 0, RX = (AX & 4) != 0, RY = (AX & 8) != 0;
     extern __shared__ __align__(128) float smem[];
@@ -962,7 +984,7 @@ __global__ void __launch_bounds__(256, 4) front_fast_kernel(const __grid_constan
     __shared__ __align__(128) unsigned char s_mask_base[F_TH * F_MSK_C];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ unsigned s_cnt[3];
-    const unsigned char* s_mask = s_mask_base + (p.use_tma_mask ? p.tma_dx_msk : 0);
+    unsigned char* s_mask = s_mask_base + (p.use_tma_mask ? p.tma_dx_msk : 0);
     const int tid = threadIdx.x;
     const int tj0 = blockIdx.x * F_TW, ti0 = blockIdx.y * F_TH;
     // a tile whose pixels or halo ring touch the border of the grid is not ours
@@ -1045,14 +1067,14 @@ __global__ void __launch_bounds__(256, 4) front_fast_kernel(const __grid_constan
         return;
     }
 
-    // ---- halo ring of the warped-src tile (3x3 stencil)
+    // ---- halo ring of the warped-src tile (3x3 stencil); every tap is finite here, so the lean warp applies
     for (int k = tid; k < 2 * F_SW_C + 2 * F_TH; k += 256) {
         int rr, cc;
         if (k < F_SW_C) { rr = 0; cc = k; }
         else if (k < 2 * F_SW_C) { rr = F_SW_R - 1; cc = k - F_SW_C; }
         else if (k < 2 * F_SW_C + F_TH) { rr = 1 + (k - 2 * F_SW_C); cc = 0; }
         else { rr = 1 + (k - 2 * F_SW_C - F_TH); cc = F_SW_C - 1; }
-        s_sw[rr * F_SW_C + cc] = warp_px_tile<F_SRC_C>(s_src, rr, cc, p.sg);
+        s_sw[rr * F_SW_C + cc] = fast_px<SX, SY>(s_src, rr, cc, p.sg);
     }
 
     // ---- main pass: thread = (column c, half hf), F_ROWS_PER_THREAD consecutive rows
@@ -1060,7 +1082,11 @@ __global__ void __launch_bounds__(256, 4) front_fast_kernel(const __grid_constan
     const int hf = tid >> 7;
     const int rbeg = hf * F_ROWS_PER_THREAD;
     const long long o0 = (long long)(ti0 + rbeg) * p.w + (tj0 + c);
-    unsigned valid_bits = 0, maxdz_bits = 0;
+    const int w = p.w;
+    unsigned n_base = 0, n_big = 0, n_slope = 0;
+    // the thread's column of the mask tile: static-mask byte in, DCR_M_BASE / DCR_M_MAXDZ byte out (read back by the same
+    // thread in the Horn pass: no bit bookkeeping in registers)
+    unsigned char* const mk0 = s_mask + rbeg * F_MSK_C + c;
     {
         // tile row tr of s_src holds source row (output row - 2 + tr): the 4 taps of output row r are tr = r + 1 .. r + 4,
         // the aligned-axis tap is tr = r + 2; columns alike (tap 0 at c + 1).  s_ref: taps tr = r .. r + 3 (aligned: r + 1).
@@ -1077,59 +1103,64 @@ __global__ void __launch_bounds__(256, 4) front_fast_kernel(const __grid_constan
             xr1 = fast_xrow<RX>(p.rg.wx, qr + F_REF_C);
             xr2 = fast_xrow<RX>(p.rg.wx, qr + 2 * F_REF_C);
         }
+        qs += (SY ? 3 : 1) * F_SRC_C;
+        qr += (RY ? 3 : 1) * F_REF_C;
         float* swp = s_sw + (rbeg + 1) * F_SW_C + (c + 1);
-        const unsigned char* mk = s_mask + rbeg * F_MSK_C + c;
+        unsigned char* mk = mk0;
         const float slo = p.src_gm_lo, shi = p.src_gm_hi, rlo = p.ref_gm_lo, rhi = p.ref_gm_hi, mdz = p.max_dz_eff;
         float* dhp = p.dh + o0;
-        const int w = p.w;
-#pragma unroll
+#pragma unroll FF_UNROLL_MAIN
         for (int rr = 0; rr < F_ROWS_PER_THREAD; ++rr) {
             float sv, rv;
             if (SY) {
-                const double xs3 = fast_xrow<SX>(p.sg.wx, qs + (rr + 3) * F_SRC_C);
+                const double xs3 = fast_xrow<SX>(p.sg.wx, qs);
                 sv = (float)ypass(p.sg.wy, xs0, xs1, xs2, xs3);
                 xs0 = xs1; xs1 = xs2; xs2 = xs3;
             } else {
-                sv = (float)fast_xrow<SX>(p.sg.wx, qs + (rr + 1) * F_SRC_C);
+                sv = (float)fast_xrow<SX>(p.sg.wx, qs);
             }
             if (RY) {
-                const double xr3 = fast_xrow<RX>(p.rg.wx, qr + (rr + 3) * F_REF_C);
+                const double xr3 = fast_xrow<RX>(p.rg.wx, qr);
                 rv = (float)ypass(p.rg.wy, xr0, xr1, xr2, xr3);
                 xr0 = xr1; xr1 = xr2; xr2 = xr3;
             } else {
-                rv = (float)fast_xrow<RX>(p.rg.wx, qr + (rr + 1) * F_REF_C);
+                rv = (float)fast_xrow<RX>(p.rg.wx, qr);
             }
-            swp[rr * F_SW_C] = sv;
+            *swp = sv;
             // ds_getma masks as float32 intervals of numpy masked_values' |x - ndv| <= tol; static mask byte
             const bool s_in = (sv >= slo) & (sv <= shi);
             const bool r_in = (rv >= rlo) & (rv <= rhi);
-            const bool ok = !(s_in | r_in | (mk[rr * F_MSK_C] != 0));
+            const bool ok = !(s_in | r_in | (*mk != 0));
             const float dh = ok ? (sv - rv) : 0.0f;
-            const bool big = ok & (fabsf(dh) > mdz);
-            valid_bits |= ok ? (1u << rr) : 0u;
-            maxdz_bits |= big ? (1u << rr) : 0u;
-            dhp[(long long)rr * w] = dh;
+            const bool big = fabsf(dh) > mdz;          // (dh = 0 where not ok)
+            n_base += ok ? 1u : 0u;
+            n_big += big ? 1u : 0u;
+            *mk = (unsigned char)(ok ? (big ? DCR_M_MAXDZ : 0u) : DCR_M_BASE);
+            *dhp = dh;
+            qs += F_SRC_C; qr += F_REF_C; swp += F_SW_C; mk += F_MSK_C; dhp += w;
         }
     }
     __syncthreads();
 
     // ---- Horn stencil on the warped src + mask byte + aspect-bin code
-    unsigned slope_bits = 0;
     {
         const float* q = s_sw + rbeg * F_SW_C + c;
         float w0 = q[0], w1 = q[1], w2 = q[2];
         float w3 = q[F_SW_C], w4 = q[F_SW_C + 1], w5 = q[F_SW_C + 2];
         float rs0 = (w0 + w1 + w1 + w2), rs1 = (w3 + w4 + w4 + w5);
+        q += 2 * F_SW_C;
         const float inv8ew = p.inv8ew, inv8ns = p.inv8ns;
+        const float lim_mid = MODE == 2 ? p.g_mid : p.slope_mid, lim_half = MODE == 2 ? p.g_half : p.slope_half,
+                    lim_tol = MODE == 2 ? p.g_tol : p.slope_tol, lim_lo = MODE == 2 ? p.g_lo : p.slope_lo,
+                    lim_hi = MODE == 2 ? p.g_hi : p.slope_hi;
         float* slp = p.slope + o0;
         unsigned char* mbp = p.maskbits + o0;
         unsigned short* bnp = p.bin + o0;
-        float* asp = (!LOOPMODE && p.aspect) ? p.aspect + o0 : nullptr;
-        const int w = p.w;
-#pragma unroll
+        float* asp = MODE == 0 ? p.aspect + o0 : nullptr;
+        const unsigned char* mk = mk0;
+#pragma unroll FF_UNROLL_HORN
         for (int rr = 0; rr < F_ROWS_PER_THREAD; ++rr) {
-            const float* qq = q + (rr + 2) * F_SW_C;
-            const float w6 = qq[0], w7 = qq[1], w8 = qq[2];
+            const float w6 = q[0], w7 = q[1], w8 = q[2];
             const float rs2 = (w6 + w7 + w7 + w8);
             const float a = (w0 + w3 + w3 + w6);
             const float b = (w2 + w5 + w5 + w8);
@@ -1138,20 +1169,17 @@ __global__ void __launch_bounds__(256, 4) front_fast_kernel(const __grid_constan
             const float gx = dxs * inv8ew, gy = dyf * inv8ns;
             float g;
             asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(gx * gx + gy * gy));
-            float sl = 0.0f;
-            bool ex, s_ok;
-            if (LOOPMODE) {
-                // slope limits as tangents; within the guard band of either one the FP64 path decides
-                ex = !(fabsf(fabsf(g - p.g_mid) - p.g_half) > p.g_tol);
-                s_ok = (g >= p.g_lo) & (g <= p.g_hi);
-            } else {
+            // sl: the slope as this mode stores it -- tan(slope) (MODE 2) or degrees; the limits are in the same unit and
+            // within the guard band of either one the FP64 path decides
+            float sl = g;
+            if (MODE != 2) {
                 const bool bigg = g > 1.0f;
                 float sa = atan01(bigg ? __fdividef(1.0f, g) : g);
                 if (bigg) sa = 1.5707963267948966f - sa;
                 sl = sa * 57.29577951308232f;
-                ex = !(fabsf(fabsf(sl - p.slope_mid) - p.slope_half) > p.slope_tol);
-                s_ok = !(sl < p.slope_lo) & !(sl > p.slope_hi);
             }
+            bool ex = !(fabsf(fabsf(sl - lim_mid) - lim_half) > lim_tol);
+            bool s_ok = !(sl < lim_lo) & !(sl > lim_hi);
             // aspect: atan2(dyf, dxs) from the [0, 1] polynomial, GDAL's azimuth convention
             const float ax = fabsf(dxs), ay = fabsf(dyf);
             float an = atan01(__fdividef(fminf(ax, ay), fmaxf(ax, ay)));
@@ -1163,34 +1191,33 @@ __global__ void __launch_bounds__(256, 4) front_fast_kernel(const __grid_constan
             const bool flat = (dxs == 0.0f) & (dyf == 0.0f);
             // within 3e-4 deg of an integer degree (a bin edge) -> exact path; a flat window has no aspect at all
             ex = (ex | !(fabsf((af - floorf(af)) - 0.5f) <= 0.5f - 3e-4f)) & !flat;
-            float gs = g;
             if (ex) {   // ~0.06 % of the pixels
                 float sle, ge, ae;
                 horn_exact(w0, w1, w2, w3, w5, w6, w7, w8, p.ewres, p.nsres, &sle, &ge, &ae);
                 s_ok = !(sle < p.slope_lo) & !(sle > p.slope_hi);
-                sl = sle; gs = ge; af = ae;
+                sl = MODE == 2 ? ge : sle;
+                af = ae;
             }
-            const bool vok = (valid_bits >> rr) & 1u, mz = (maxdz_bits >> rr) & 1u;
-            unsigned bits = (s_ok ? 0u : (unsigned)DCR_M_SLOPE) | (flat ? (unsigned)DCR_M_ASPECT : 0u) |
-                            (vok ? (mz ? (unsigned)DCR_M_MAXDZ : 0u) : (unsigned)DCR_M_BASE);
-            slope_bits |= s_ok ? (1u << rr) : 0u;
+            const unsigned bits = (unsigned)*mk | (s_ok ? 0u : (unsigned)DCR_M_SLOPE) | (flat ? (unsigned)DCR_M_ASPECT : 0u);
+            n_slope += s_ok ? 1u : 0u;
             const int bi = min((int)af, DCR_NBINS - 1);   // (NaN / flat never reaches a valid code: bits != 0)
-            slp[(long long)rr * w] = LOOPMODE ? gs : sl;
-            mbp[(long long)rr * w] = (unsigned char)bits;
-            bnp[(long long)rr * w] = (unsigned short)(bits == 0u ? bi : (int)DCR_BIN_INVALID);
-            if (!LOOPMODE && asp) asp[(long long)rr * w] = flat ? DCR_GDALDEM_NDV : af;
+            *slp = sl;
+            *mbp = (unsigned char)bits;
+            *bnp = (unsigned short)(bits == 0u ? bi : (int)DCR_BIN_INVALID);
+            if (MODE == 0) { *asp = flat ? DCR_GDALDEM_NDV : af; asp += w; }
+            slp += w; mbp += w; bnp += w; mk += F_MSK_C; q += F_SW_C;
             w0 = w3; w1 = w4; w2 = w5;
             w3 = w6; w4 = w7; w5 = w8;
             rs0 = rs1; rs1 = rs2;
         }
     }
     // counters: base-valid, after max_dz, slope-valid
-    unsigned n_base = __reduce_add_sync(0xffffffffu, (unsigned)__popc(valid_bits));
-    unsigned n_maxdz = __reduce_add_sync(0xffffffffu, (unsigned)__popc(valid_bits & ~maxdz_bits));
-    unsigned n_slope = __reduce_add_sync(0xffffffffu, (unsigned)__popc(slope_bits));
+    n_base = __reduce_add_sync(0xffffffffu, n_base);
+    n_big = __reduce_add_sync(0xffffffffu, n_big);
+    n_slope = __reduce_add_sync(0xffffffffu, n_slope);
     if ((tid & 31) == 0) {
         atomicAdd(&s_cnt[0], n_base);
-        atomicAdd(&s_cnt[1], n_maxdz);
+        atomicAdd(&s_cnt[1], n_base - n_big);
         atomicAdd(&s_cnt[2], n_slope);
     }
     __syncthreads();
@@ -1246,16 +1273,10 @@ static bool make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, lon
 // pixel-aligned pair, the four "one resampled raster per axis" cases of the dem_align loop, everything fractional
 typedef void (*FastKernelFn)(const FrontParams);
 static const int kFastAx[6] = {0, 3, 9, 6, 12, 15};
-static FastKernelFn fast_kernel_fn(int k, int loopmode) {
-    switch (k * 2 + (loopmode ? 1 : 0)) {
-        case 0: return front_fast_kernel<0, false>;   case 1: return front_fast_kernel<0, true>;
-        case 2: return front_fast_kernel<3, false>;   case 3: return front_fast_kernel<3, true>;
-        case 4: return front_fast_kernel<9, false>;   case 5: return front_fast_kernel<9, true>;
-        case 6: return front_fast_kernel<6, false>;   case 7: return front_fast_kernel<6, true>;
-        case 8: return front_fast_kernel<12, false>;  case 9: return front_fast_kernel<12, true>;
-        case 10: return front_fast_kernel<15, false>; default: return front_fast_kernel<15, true>;
-    }
-}
+#define DCR_FAST_ROW(AX) {front_fast_kernel<AX, 0>, front_fast_kernel<AX, 1>, front_fast_kernel<AX, 2>}
+static FastKernelFn const kFastFn[6][3] = {DCR_FAST_ROW(0), DCR_FAST_ROW(3), DCR_FAST_ROW(9),
+                                           DCR_FAST_ROW(6), DCR_FAST_ROW(12), DCR_FAST_ROW(15)};
+static FastKernelFn fast_kernel_fn(int k, int mode) { return kFastFn[k][mode]; }
 
 int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cudaStream_t stream, unsigned short* bin,
                      int loopmode, unsigned* tile_list, long long tile_list_cap) {
@@ -1369,8 +1390,8 @@ int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cuda
     if (!ctx) return -1;
     if (!(ctx->attrs & DCR_ATTR_FRONT)) {   // per device
         DCR_CUDA_OK(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        for (int k = 0; k < 12; ++k)
-            DCR_CUDA_OK(cudaFuncSetAttribute(fast_kernel_fn(k >> 1, k & 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (int k = 0; k < 18; ++k)
+            DCR_CUDA_OK(cudaFuncSetAttribute(fast_kernel_fn(k / 3, k % 3), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->attrs |= DCR_ATTR_FRONT;
     }
     p.loopmode = loopmode ? 1 : 0;
@@ -1401,7 +1422,7 @@ int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cuda
         p.list = tile_list;
         DCR_CUDA_OK(cudaMemsetAsync(tile_list, 0, sizeof(unsigned), stream));
         p.list_mode = 0;
-        fast_kernel_fn(k, loopmode)<<<grid, 256, smem, stream>>>(p);
+        fast_kernel_fn(k, loopmode ? 2 : (a->aspect ? 0 : 1))<<<grid, 256, smem, stream>>>(p);
         DCR_LAUNCH_OK("front_fast_kernel");
         p.list_mode = 1;
         long long g1 = (long long)ntx * nty;

@@ -931,7 +931,8 @@ __global__ void __launch_bounds__(256) mask_update_kernel(const float* __restric
                                                           long long n, IterDev* d, unsigned* __restrict__ chunk_cnt,
                                                           const float* __restrict__ slope, float* __restrict__ y,
                                                           unsigned short* __restrict__ bin, NuthPartial* __restrict__ part,
-                                                          int thr_mode /* 0: thresholds in d; 1: compute; 2: no filter */) {
+                                                          int thr_mode /* 0: thresholds in d; 1: compute; 2: no filter */,
+                                                          int tan_slope /* `slope` holds tan(slope), not degrees */) {
     __shared__ unsigned s_a[8], s_b[8];
     __shared__ NuthPartial sp[8];
     float lo, hi;
@@ -991,7 +992,7 @@ __global__ void __launch_bounds__(256) mask_update_kernel(const float* __restric
             mb[k] = bits;
             if (!(bits & DCR_M_DIFF)) ++n_fin;
             if (NUTH && bits == 0u) {   // common mask of compute_offset_nuth: dh, slope and aspect all unmasked
-                const float t = nuth_y(v[k], sl[k]);
+                const float t = tan_slope ? __fdiv_rn(v[k], sl[k]) : nuth_y(v[k], sl[k]);
                 yv[k] = t;
                 ++cnt;
                 s += (double)t;
@@ -1063,7 +1064,8 @@ static size_t iter_ws_bytes(long long n, int grid) {
     const long long nch = (n + MU_CHUNK - 1) / MU_CHUNK;
     return nuth_ws_bytes(n, grid) + dcr_al256(sizeof(IterDev)) + dcr_al256(DCR_SEL_HIST_WORDS * sizeof(unsigned)) +
            dcr_al256(nch * sizeof(unsigned)) + dcr_al256(nch * sizeof(long long)) +
-           dcr_al256((size_t)(n < 6000016 ? n : 6000016) * sizeof(float)) + 3 * dcr_bsel_scratch_bytes(n) + 4096;
+           dcr_al256((size_t)(n < 6000016 ? n : 6000016) * sizeof(float)) + 3 * dcr_bsel_scratch_bytes(n) +
+           dcr_al256((size_t)dcr_front_list_cap(n) * sizeof(unsigned)) + 4096;
 }
 extern "C" size_t dcr_iteration_workspace_bytes(int64_t n) { return iter_ws_bytes(n, dcr_num_sms() * 8); }
 
@@ -1123,6 +1125,8 @@ struct IterWs {
     void* bsel_scratch;
     void* bsel_scratch2;   // selections running on the side stream
     void* bsel_scratch3;   // med_dh on its own side stream
+    unsigned* tile_list = nullptr;   // front end: tiles left to the general kernel by the fast interior-tile kernel
+    long long tile_cap = 0;
     NuthWs nw;
 };
 
@@ -1137,7 +1141,7 @@ static int iter_select(const SelView& v, int k, const IterWs& w, long long n, in
 }
 
 static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, int use_bsel, const IterWs& w, int grid,
-                             cudaStream_t s, cudaEvent_t* ev, int fast_bins, int apply_z) {
+                             cudaStream_t s, cudaEvent_t* ev, int fast_bins, int tan_slope) {
     const long long n = (long long)front->h * front->w;
     const long long nch = (n + MU_CHUNK - 1) / MU_CHUNK;
     IterDev* d = w.d;
@@ -1147,7 +1151,7 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
     DCR_CUDA_OK(cudaMemsetAsync(d, 0, sizeof(IterDev), s));
     dcr_front_args fa = *front;
     if (!remove_outliers) fa.use_max_dz = 0;
-    if ((rc = dcr_front_launch(&fa, d->counters, s, w.nw.bin))) return rc;   // + aspect-bin codes
+    if ((rc = dcr_front_launch(&fa, d->counters, s, w.nw.bin, tan_slope, w.tile_list, w.tile_cap))) return rc;   // + bin codes
 
     // Side stream (one-pass-select path): work that does not sit on the dependency chain of the MAD filter runs
     // concurrently -- the slope median right after the front kernel, and the strided-subsample chain (scan, stride,
@@ -1189,7 +1193,8 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
     }
     STAGE_MARK(2);
     mask_update_kernel<true><<<(unsigned)((nch + MU_KCH - 1) / MU_KCH), 256, 0, s>>>(
-        front->dh, front->maskbits, n, d, w.chunk_cnt, front->slope, w.nw.y, w.nw.bin, w.nw.part, remove_outliers ? 1 : 2);
+        front->dh, front->maskbits, n, d, w.chunk_cnt, front->slope, w.nw.y, w.nw.bin, w.nw.part, remove_outliers ? 1 : 2,
+        tan_slope);
     if (side) {
         DCR_CUDA_OK(cudaEventRecord(e_mask, s));
         DCR_CUDA_OK(cudaStreamWaitEvent(s2, e_mask, 0));
@@ -1239,13 +1244,12 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
     }
     DCR_LAUNCH_OK("iteration kernels");
     STAGE_MARK(6);
-    (void)apply_z;
 #undef STAGE_MARK
     return 0;
 }
 
 // host part of an iteration: counts, guards, bin selection, fit, shift (coreglib.py:206-305, dem_align.py:150-172)
-static int iter_finalize(const IterDev* hd, int engine_used, dcr_iter_result* out, int bin_engine = 0) {
+static int iter_finalize(const IterDev* hd, int engine_used, dcr_iter_result* out, int bin_engine = 0, int tan_slope = 0) {
     out->select_engine = engine_used;
     out->bin_engine = bin_engine;
     float selres[5];
@@ -1262,7 +1266,8 @@ static int iter_finalize(const IterDev* hd, int engine_used, dcr_iter_result* ou
     out->mad_hi = hd->mad_hi;
     out->med_dh = selres[2];
     out->dz_med = hd->stride > 1 ? selres[3] : selres[2];
-    out->med_slope = selres[4];
+    // DCR_ITER_TAN_SLOPE: the selection ran on tan(slope), a monotone map of the slope
+    out->med_slope = tan_slope ? (float)(atan((double)selres[4]) * (180.0 / M_PI)) : selres[4];
     nuth_dev_to_stats(hd->nuth, &out->nuth);
     out->dz = -(double)out->dz_med;
     if (out->count_base == 0) { out->status = 1; return 0; }
@@ -1309,6 +1314,7 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_it
     DCR_ARG(front && out && workspace, "null pointer");
     const int remove_outliers = (flags & DCR_ITER_REMOVE_OUTLIERS) ? 1 : 0;
     const bool prof = (flags & DCR_ITER_PROFILE) != 0;
+    const int tan_slope = (flags & DCR_ITER_TAN_SLOPE) ? 1 : 0;
     DcrCtx* ctx = dcr_ctx();
     if (!ctx) return -1;
     cudaEvent_t* ev = ctx->prof;
@@ -1331,6 +1337,8 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_it
     w.bsel_scratch = ws.take<char>(dcr_bsel_scratch_bytes(n));
     w.bsel_scratch2 = ws.take<char>(dcr_bsel_scratch_bytes(n));
     w.bsel_scratch3 = ws.take<char>(dcr_bsel_scratch_bytes(n));
+    w.tile_cap = dcr_front_list_cap(n);
+    w.tile_list = ws.take<unsigned>(w.tile_cap);
     if (nuth_ws_carve(ws, n, grid, &w.nw)) return -1;
     w.nw.nd = &w.d->nuth;
     IterDev* d = w.d;
@@ -1341,7 +1349,7 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_it
     int bin_engine = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
         int rc = iteration_enqueue(front, remove_outliers, engine_used, w, grid, s, prof ? ev : nullptr,
-                                   (flags & DCR_ITER_RADIX_ONLY) ? 0 : 1, (flags & DCR_ITER_APPLY_Z) ? 1 : 0);
+                                   (flags & DCR_ITER_RADIX_ONLY) ? 0 : 1, tan_slope);
         if (rc) return rc;
         DCR_CUDA_OK(cudaMemcpyAsync(hd, d, sizeof(IterDev), cudaMemcpyDeviceToHost, s));
         if (prof) DCR_CUDA_OK(cudaEventRecord(ev[7], s));
@@ -1392,7 +1400,7 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_it
     if (prof)
         for (int k = 0; k < 7; ++k) DCR_CUDA_OK(cudaEventElapsedTime(&out->stage_ms[k], ev[k], ev[k + 1]));
     {
-        const int rcf = iter_finalize(hd, engine_used, out, bin_engine);
+        const int rcf = iter_finalize(hd, engine_used, out, bin_engine, tan_slope);
         out->z_applied = ((flags & DCR_ITER_APPLY_Z) && !isnan(out->dz_med)) ? 1 : 0;
         return rcf;
     }
@@ -1448,7 +1456,8 @@ extern "C" int dcr_align_nuth(dcr_align_state* st, int max_steps, int flags, dcr
         a.dh = st->dh; a.slope = st->slope; a.aspect = st->aspect; a.maskbits = st->maskbits;
         a.src_ndz = st->src_ndz;
         for (int k = 0; k < st->src_ndz; ++k) a.src_dz[k] = st->src_dz[k];
-        const int f = (st->remove_outliers ? DCR_ITER_REMOVE_OUTLIERS : 0) | (flags & (DCR_ITER_PROFILE | DCR_ITER_RADIX_ONLY));
+        const int f = (st->remove_outliers ? DCR_ITER_REMOVE_OUTLIERS : 0) |
+                      (flags & (DCR_ITER_PROFILE | DCR_ITER_RADIX_ONLY | DCR_ITER_TAN_SLOPE));
         if ((rc = dcr_nuth_iteration(&a, f, &st->last, workspace, workspace_bytes, stream))) return rc;
         const dcr_iter_result& r = st->last;
         if (iters && done_here < iters_cap) {
@@ -1572,6 +1581,7 @@ static int band_carve(void* workspace, size_t workspace_bytes, long long n, int 
     w->bsel_scratch = ws.take<char>(dcr_bsel_scratch_bytes(n));
     w->bsel_scratch2 = ws.take<char>(dcr_bsel_scratch_bytes(n));
     w->bsel_scratch3 = ws.take<char>(dcr_bsel_scratch_bytes(n));
+    (void)ws.take<unsigned>(dcr_front_list_cap(n));   // same layout as dcr_nuth_iteration (band launches use the general kernel)
     if (nuth_ws_carve(ws, n, grid, &w->nw)) return -1;
     w->nw.nd = &w->d->nuth;
     return 0;
@@ -1646,7 +1656,7 @@ extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, 
     } else if (phase == BP_MASK) {
         mad_thresholds_kernel<<<1, 32, 0, s>>>(d, remove_outliers);
         mask_update_kernel<false><<<(unsigned)((nch + MU_KCH - 1) / MU_KCH), 256, 0, s>>>(front->dh, front->maskbits, n, d, w.chunk_cnt, nullptr, nullptr,
-                                                                nullptr, nullptr, 0);
+                                                                nullptr, nullptr, 0, 0);
         band_rank_count_kernel<<<1, 32, 0, s>>>(d, rank);
         want(&d->count_mad, 2 + 8, 1);  // count_mad, count_final, rank_counts[8] are contiguous
     } else if (phase == BP_COMPRESS) {

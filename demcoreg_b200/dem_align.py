@@ -93,8 +93,9 @@ def compute_offset(ref_dem_ds, src_dem_ds, src_dem_fn, mode='nuth', remove_outli
         get_mask(None, mask_list)
     fig = None
     if mode == 'nuth':
+        # (the slope raster stays on the device and is not returned: tan(slope) mode, like the native loop)
         res, grid, bufs = engine.nuth_iteration(ref_dem_ds, src_dem_ds, mask_source, remove_outliers, max_dz, slope_lim,
-                                                apply_z=_apply_z)
+                                                apply_z=_apply_z, tan_slope=True)
         if res.status in _EXIT_MSG:
             sys.exit(_EXIT_MSG[res.status])
         if _details is not None:

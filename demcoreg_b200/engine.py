@@ -98,13 +98,14 @@ def make_front_args(ref, src, mask_source, max_dz, use_max_dz, slope_lim, keep_w
 
 
 def nuth_iteration(ref, src, mask_source=None, remove_outliers=True, max_dz=100, slope_lim=(0.1, 40),
-                   keep_warped=False, bufs=None, profile=False, radix_only=False, apply_z=False):
+                   keep_warped=False, bufs=None, profile=False, radix_only=False, apply_z=False, tan_slope=False):
     """One full Nuth-Kaab iteration on the device (``dcr_nuth_iteration``).
 
     Returns ``(IterResult, Grid, IterBuffers)``; ``IterResult.dx/dy/dz`` is what
     ``dem_align.compute_offset`` returns (reference ``dem_align.py:172``).  ``apply_z=True`` additionally runs
     ``coreglib.apply_z_shift(src, dz)`` on the device before returning (``IterResult.z_applied``); the caller must
-    then not apply ``dz`` again.
+    then not apply ``dz`` again.  ``tan_slope=True`` (``DCR_ITER_TAN_SLOPE``): ``bufs.slope`` receives ``tan(slope)``
+    instead of degrees -- what the ``dem_align`` loop runs with, since nothing there reads the slope raster back.
     """
     torch = _lib.require_cuda()
     L = _lib.lib()
@@ -116,7 +117,8 @@ def nuth_iteration(ref, src, mask_source=None, remove_outliers=True, max_dz=100,
     ws = workspace(nbytes)
     res = _lib.IterResult()
     flags = (_lib.ITER_REMOVE_OUTLIERS if remove_outliers else 0) | (_lib.ITER_PROFILE if profile else 0) \
-        | (_lib.ITER_RADIX_ONLY if radix_only else 0) | (_lib.ITER_APPLY_Z if apply_z else 0)
+        | (_lib.ITER_RADIX_ONLY if radix_only else 0) | (_lib.ITER_APPLY_Z if apply_z else 0) \
+        | (_lib.ITER_TAN_SLOPE if tan_slope else 0)
     _lib.check(L.dcr_nuth_iteration(C.byref(a), flags, C.byref(res),
                                     C.c_void_p(ws.data_ptr()), ws.numel(), _stream_ptr(torch)))
     return res, grid, bufs
@@ -190,7 +192,7 @@ class NuthAligner(object):
         """Run the loop to the end (``max_steps=0``) or exactly ``max_steps`` further iterations (fewer if it stops);
         returns the records of the iterations this call ran (dx, dy, dz, status, grid size, engines)."""
         torch = _lib.require_cuda()
-        flags = (_lib.ITER_PROFILE if profile else 0) | (_lib.ITER_RADIX_ONLY if radix_only else 0)
+        flags = (_lib.ITER_PROFILE if profile else 0) | (_lib.ITER_RADIX_ONLY if radix_only else 0) | _lib.ITER_TAN_SLOPE
         out = []
         left = int(max_steps)
         cap = len(self._iters)

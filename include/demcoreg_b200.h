@@ -244,6 +244,10 @@ typedef struct dcr_iter_result {
 #define DCR_ITER_RADIX_ONLY 4      /* skip the one-pass sample-bracket selects (tests / profiling) */
 #define DCR_ITER_APPLY_Z 8         /* also run coreglib.apply_z_shift(src, dz) on the device (front->src must be writable,
                                       whole raster); the host must then NOT apply dz again (see z_applied) */
+#define DCR_ITER_TAN_SLOPE 16      /* front->slope receives tan(slope) = |gradient|/8 instead of degrees (the consumers of the
+                                    * iteration want the tangent: y = dh / tan(slope), coreglib.py:224-225; the slope median,
+                                    * coreglib.py:215, is taken on the tangent and converted).  Masks are still decided on the
+                                    * float32 slope in degrees.  Used by dcr_align_nuth, whose slope raster is scratch. */
 size_t dcr_iteration_workspace_bytes(int64_t n);
 int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_iter_result* out /* host */,
                        void* workspace, size_t workspace_bytes, void* stream);
@@ -291,7 +295,7 @@ typedef struct dcr_align_state {
 } dcr_align_state;
 /* Runs iterations until the loop finishes or max_steps (> 0) iterations were done in this call; appends one record per
  * iteration to iters[0..iters_cap) (may be NULL); *n_iters = iterations run by this call.  flags: DCR_ITER_PROFILE,
- * DCR_ITER_RADIX_ONLY.  Workspace: dcr_iteration_workspace_bytes(out_capacity). */
+ * DCR_ITER_RADIX_ONLY, DCR_ITER_TAN_SLOPE (st->slope is then scratch holding tan(slope)).  Workspace: dcr_iteration_workspace_bytes(out_capacity). */
 int dcr_align_nuth(dcr_align_state* st, int max_steps, int flags, dcr_align_iter* iters, int iters_cap, int* n_iters,
                    void* workspace, size_t workspace_bytes, void* stream);
 /* Writes the pending z shifts into the source band (call before reading the aligned band). */

@@ -50,30 +50,37 @@ def test_config2_8192_iteration(cuda):
     g[0] += 3.4
     g[3] += -1.8
     gt_s = tuple(g)
-    res, grid, bufs = engine.nuth_iteration(_gds(p, 'ref'), _gds(p, 'src', gt_s), MaskSource(p['mask'], p['gt']))
-    assert res.select_engine == 1, "the one-pass selects fell back to the radix select"
-    gmask = ((bufs.maskbits & _lib.M_DIFF) != 0).cpu().numpy()
     det = {}
     odx, ody, odz, omask, _ = oda.compute_offset(_ods(p, 'ref'), _ods(p, 'src', gt_s),
                                                  mask_source=oda.MaskSource(p['mask'], p['gt']), details=det)
-    assert np.array_equal(gmask, omask)
-    assert res.count_base == det['count_base'] and res.count_final == det['count_final']
     nd = det['nuth']
-    assert res.stats_stride == int(np.around(det['count_final'] / 4e6))
-    assert res.dz_med == det['dz_med'] and res.med_dh == nd['med_dh']
-    assert res.nuth.n_common == nd['n_common']
-    # 3-sigma trim of y: float32 comparisons against float32 thresholds; numpy's float32 tan is not correctly rounded, so a
-    # pixel within ~1 ulp of a threshold may legitimately differ (~1 pixel in 4e7) -- report it exactly
-    gc = np.array(res.nuth.bin_count[:])
     oc = nd['bin_count'].astype(np.int64)
-    ndiff = int(np.abs(gc - oc).sum())
-    assert abs(res.nuth.n_final - nd['n_final']) <= 2 and ndiff <= 2, (res.nuth.n_final, nd['n_final'], ndiff)
-    if ndiff == 0:
-        assert res.nuth.n_final == nd['n_final']
-    gm = np.array(res.nuth.bin_med[:], dtype=np.float64)
-    np.testing.assert_allclose(gm, nd['bin_med'], rtol=1e-4, atol=1e-4)
-    assert abs(res.dx - odx) < OFFTOL and abs(res.dy - ody) < OFFTOL and abs(res.dz - odz) < OFFTOL
-    print("config2 parity: bin-count differences %d, n_final %d vs %d" % (ndiff, res.nuth.n_final, nd['n_final']))
+    # both flavours of the slope raster: degrees (the standalone iteration) and tan(slope) (what the dem_align loop runs)
+    for tan_slope in (False, True):
+        res, grid, bufs = engine.nuth_iteration(_gds(p, 'ref'), _gds(p, 'src', gt_s), MaskSource(p['mask'], p['gt']),
+                                                tan_slope=tan_slope)
+        assert res.select_engine == 1, "the one-pass selects fell back to the radix select"
+        gmask = ((bufs.maskbits & _lib.M_DIFF) != 0).cpu().numpy()
+        assert np.array_equal(gmask, omask)
+        assert res.count_base == det['count_base'] and res.count_final == det['count_final']
+        assert res.count_slope == int(np.ma.count(det['slope']))
+        assert res.stats_stride == int(np.around(det['count_final'] / 4e6))
+        assert res.dz_med == det['dz_med'] and res.med_dh == nd['med_dh']
+        assert abs(res.med_slope - nd['med_slope']) <= 1e-5 * nd['med_slope']
+        assert res.nuth.n_common == nd['n_common']
+        # 3-sigma trim of y: float32 comparisons against float32 thresholds; numpy's float32 tan is not correctly rounded, so
+        # a pixel within ~1 ulp of a threshold may legitimately differ (~1 pixel in 4e7) -- report it
+        gc = np.array(res.nuth.bin_count[:])
+        ndiff = int(np.abs(gc - oc).sum())
+        assert abs(res.nuth.n_final - nd['n_final']) <= 2 and ndiff <= 2, (res.nuth.n_final, nd['n_final'], ndiff)
+        if ndiff == 0:
+            assert res.nuth.n_final == nd['n_final']
+        gm = np.array(res.nuth.bin_med[:], dtype=np.float64)
+        np.testing.assert_allclose(gm, nd['bin_med'], rtol=1e-4, atol=1e-4)
+        assert abs(res.dx - odx) < OFFTOL and abs(res.dy - ody) < OFFTOL and abs(res.dz - odz) < OFFTOL
+        print("config2 parity (tan_slope=%s): bin-count differences %d, n_final %d vs %d" %
+              (tan_slope, ndiff, res.nuth.n_final, nd['n_final']))
+        del bufs
 
 
 def _config3_pair():

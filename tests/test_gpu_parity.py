@@ -199,6 +199,14 @@ def test_nuth_iteration_matches_oracle(cuda, cfg):
     gmask = ((bufs.maskbits & _lib.M_DIFF) != 0).cpu().numpy()
     assert np.array_equal(gmask, omask)
     _compare_iteration(res, det, odx, ody, odz)
+    # DCR_ITER_TAN_SLOPE (what the dem_align loop runs): the slope raster holds tan(slope); same masks, counts and bins
+    res_t, _, bufs_t = engine.nuth_iteration(_gds(p, 'ref'), _gds(p, 'src', gt_s), ms_g, tan_slope=True)
+    assert np.array_equal(bufs_t.maskbits.cpu().numpy(), bufs.maskbits.cpu().numpy())
+    assert np.array_equal(bufs_t.dh.cpu().numpy(), bufs.dh.cpu().numpy())
+    _compare_iteration(res_t, det, odx, ody, odz)
+    ok = ((bufs.maskbits & _lib.M_SLOPE) == 0).cpu().numpy()
+    np.testing.assert_allclose(bufs_t.slope.cpu().numpy()[ok], np.tan(np.deg2rad(det['slope'].data[ok].astype(np.float64))),
+                               rtol=2e-6)
 
 
 def test_strided_stats_branch(cuda):
