@@ -965,10 +965,10 @@ __device__ __noinline__ void horn_exact(float w0, float w1, float w2, float w3, 
 // Unroll factors of the two row loops: fully unrolled the kernel is 61 KB of SASS, twice the 32 KB instruction cache of an
 // SM, and 36 % of the warp-stall samples were instruction fetches (profiles/r2/front_fast_r2c_sass.txt)
 #ifndef DCR_FF_UNROLL_MAIN
-#define DCR_FF_UNROLL_MAIN 7
+#define DCR_FF_UNROLL_MAIN 14
 #endif
 #ifndef DCR_FF_UNROLL_HORN
-#define DCR_FF_UNROLL_HORN 2
+#define DCR_FF_UNROLL_HORN 7
 #endif
 constexpr int FF_UNROLL_MAIN = DCR_FF_UNROLL_MAIN, FF_UNROLL_HORN = DCR_FF_UNROLL_HORN;
 // MODE: 0 = slope in degrees + aspect raster, 1 = slope in degrees, no aspect raster, 2 = tan(slope), no aspect raster
@@ -1253,8 +1253,17 @@ static EncodeTiledFn get_encode_tiled() {
     return fn;
 }
 // 2-D tensor map (float32, OOB -> NaN; or uint8, OOB -> 0) over the rows held in memory; box = (box_w x box_h)
+// (the descriptors of the last few rasters are kept per thread: the iterations of a loop stage the same three arrays, and
+// an encode costs microseconds of host time between two iterations)
+struct TmapKey { const void* base; int rows, cols, box_w, box_h, u8; long long stride; };
+struct TmapSlot { TmapKey k; CUtensorMap tm; bool used; };
 static bool make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, long long stride_elems, int box_w, int box_h,
                       bool u8 = false) {
+    static thread_local TmapSlot cache[8];
+    static thread_local unsigned next = 0;
+    const TmapKey key = {base, rows, cols, box_w, box_h, u8 ? 1 : 0, stride_elems};
+    for (int q = 0; q < 8; ++q)
+        if (cache[q].used && memcmp(&cache[q].k, &key, sizeof(key)) == 0) { *tm = cache[q].tm; return true; }
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) return false;
     const size_t esz = u8 ? 1 : sizeof(float);
@@ -1263,10 +1272,15 @@ static bool make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, lon
     const cuuint64_t strides[1] = {(cuuint64_t)stride_elems * esz};
     const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
     const cuuint32_t estr[2] = {1, 1};
-    return enc(tm, u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box,
-               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-               CU_TENSOR_MAP_L2_PROMOTION_NONE,  // (L2_128B promotion faults with this 544-byte box)
-               u8 ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE : CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA) == CUDA_SUCCESS;
+    if (enc(tm, u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box,
+            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_NONE,  // (L2_128B promotion faults with this 544-byte box)
+            u8 ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE : CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA) != CUDA_SUCCESS)
+        return false;
+    TmapSlot& sl = cache[next++ & 7u];
+    memset(&sl.k, 0, sizeof(sl.k));
+    sl.k = key; sl.tm = *tm; sl.used = true;
+    return true;
 }
 
 // the instantiated axis combinations of the fast kernel (bit 0/1: source x/y fractional, bit 2/3: reference x/y):

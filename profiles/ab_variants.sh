@@ -4,7 +4,7 @@ TAG=${1:-x}; shift
 mkdir -p gpurun_out
 for v in default "$@"; do
   if [ "$v" = default ]; then unset DCR_LIB; else export DCR_LIB=$PWD/demcoreg_b200/csrc/variants/$v.so; fi
-  python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-config3 --no-batch --no-band > gpurun_out/ab_${TAG}_$v.json 2> gpurun_out/ab_${TAG}_$v.err
+  python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-config3 --no-batch --no-band > gpurun_out/ab_${TAG}_$v.json 2> gpurun_out/ab_${TAG}_$v.err
   python - gpurun_out/ab_${TAG}_$v.json $v <<'PY'
 import json, sys
 try:
