@@ -140,6 +140,14 @@ SYMBOLS = {
     "dcr_band_phase": (C.c_int, [C.POINTER(FrontArgs), C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_size_t,
                                  C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
     "dcr_band_result": (C.c_int, [C.POINTER(FrontArgs), _P, C.c_size_t, C.POINTER(IterResult), _P]),
+    "dcr_comm_unique_id": (C.c_int, [_P, C.c_size_t]),
+    "dcr_comm_init": (C.c_int, [_P, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "dcr_comm_set": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "dcr_comm_destroy": (C.c_int, [_P]),
+    "dcr_comm_rank": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "dcr_band_exchange_halos": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, _P]),
+    "dcr_band_iteration": (C.c_int, [C.POINTER(FrontArgs), C.c_int, _P, C.POINTER(IterResult), _P, C.c_size_t, _P]),
     "dcr_nuth_iteration": (C.c_int, [C.POINTER(FrontArgs), C.c_int, C.POINTER(IterResult), _P, C.c_size_t, _P]),
     "dcr_align_nuth": (C.c_int, [C.POINTER(AlignState), C.c_int, C.c_int, C.POINTER(AlignIter), C.c_int,
                                  C.POINTER(C.c_int), _P, C.c_size_t, _P]),

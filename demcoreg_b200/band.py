@@ -231,13 +231,71 @@ class BandAligner(object):
 
 
 def iteration_distributed(al, group=None, **kw):
-    """One row-band iteration under ``torch.distributed`` (NCCL): phases + all-reduces.  Returns IterResult."""
+    """One row-band iteration under ``torch.distributed`` (NCCL): phases + all-reduces driven from the interpreter (28 phase
+    boundaries per iteration).  Returns IterResult.  ``iteration_native`` is the production path."""
     import torch.distributed as dist
     nph = al.begin_iteration(**kw)
     for ph in range(nph):
         for t in al.run_phase(ph):
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return al.result()
+
+
+class Comm(object):
+    """The library's own NCCL communicator (``dcr_comm``): rank 0 makes the ncclUniqueId, ``torch.distributed`` carries it to
+    the other ranks (any transport would do), every rank joins with ``dcr_comm_init``."""
+
+    def __init__(self, rank=None, world=None, group=None):
+        import torch.distributed as dist
+        torch = _lib.require_cuda()
+        L = _lib.lib()
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_ubyte * 128)()
+            _lib.check(L.dcr_comm_unique_id(buf, 128))
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        if self.world > 1:
+            dev = ident.cuda() if dist.get_backend(group) == "nccl" else ident
+            dist.broadcast(dev, src=0, group=group)
+            ident = dev.cpu()
+        raw = (C.c_ubyte * 128)(*[int(v) for v in ident.tolist()])
+        h = C.c_void_p()
+        _lib.check(L.dcr_comm_init(raw, 128, self.rank, self.world, C.byref(h)))
+        self.handle = h
+
+    def close(self):
+        if self.handle:
+            _lib.lib().dcr_comm_destroy(self.handle)
+            self.handle = None
+
+
+def iteration_native(al, comm, **kw):
+    """One row-band iteration as ONE native call (``dcr_band_iteration``): every phase and its ncclAllReduce enqueued back to
+    back on the current stream, no interpreter work in between.  Collective over ``comm``.  Returns IterResult."""
+    torch = al.torch
+    L = _lib.lib()
+    al.begin_iteration(**kw)
+    res = _lib.IterResult()
+    _lib.check(L.dcr_band_iteration(C.byref(al.args), al.flags, comm.handle, C.byref(res), C.c_void_p(al.ws.data_ptr()),
+                                    al.ws.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return res
+
+
+def exchange_halos_native(al, comm):
+    """Halo exchange of the three band rasters through the library's communicator (grouped ncclSend / ncclRecv)."""
+    torch = al.torch
+    L = _lib.lib()
+    a, b = al.owned
+    for band in al.bands():
+        nrows = int(band.data.shape[0])
+        up = _halo_of_neighbour(band, al.rank - 1, al.world, below=True) if al.rank > 0 else 0
+        dn = _halo_of_neighbour(band, al.rank + 1, al.world, below=False) if al.rank < al.world - 1 else 0
+        row_bytes = band.data.stride(0) * band.data.element_size()
+        _lib.check(L.dcr_band_exchange_halos(comm.handle, C.c_void_p(band.data.data_ptr()), row_bytes,
+                                             a, up, 0, a, b - dn, dn, b, nrows - b,
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
 
 class VirtualGroup(object):

@@ -986,9 +986,9 @@ __global__ void __launch_bounds__(256, 4) front_fast_kernel(const __grid_constan
     __shared__ unsigned s_cnt[3];
     unsigned char* s_mask = s_mask_base + (p.use_tma_mask ? p.tma_dx_msk : 0);
     const int tid = threadIdx.x;
-    const int tj0 = blockIdx.x * F_TW, ti0 = blockIdx.y * F_TH;
-    // a tile whose pixels or halo ring touch the border of the grid is not ours
-    const bool interior = blockIdx.x > 0 && blockIdx.y > 0 && tj0 + F_TW < p.w && ti0 + F_TH < p.h;
+    const int tj0 = blockIdx.x * F_TW, ti0 = p.row_begin + blockIdx.y * F_TH;   // (row band: rows [row_begin, row_end) of the grid)
+    // a tile whose pixels or halo ring touch the border of the grid, or that is cut by the end of the row band, is not ours
+    const bool interior = blockIdx.x > 0 && ti0 > 0 && tj0 + F_TW < p.w && ti0 + F_TH < p.h && ti0 + F_TH <= p.row_end;
     if (!interior) {
         if (tid == 0) p.list[1u + atomicAdd(p.list, 1u)] = (blockIdx.y << 16) | blockIdx.x;
         return;
@@ -1081,7 +1081,7 @@ __global__ void __launch_bounds__(256, 4) front_fast_kernel(const __grid_constan
     const int c = tid & (F_TW - 1);
     const int hf = tid >> 7;
     const int rbeg = hf * F_ROWS_PER_THREAD;
-    const long long o0 = (long long)(ti0 + rbeg) * p.w + (tj0 + c);
+    const long long o0 = (long long)(ti0 - p.row_begin + rbeg) * p.w + (tj0 + c);   // outputs hold the band's rows only
     const int w = p.w;
     unsigned n_base = 0, n_big = 0, n_slope = 0;
     // the thread's column of the mask tile: static-mask byte in, DCR_M_BASE / DCR_M_MAXDZ byte out (read back by the same
@@ -1424,7 +1424,6 @@ int dcr_front_launch(const dcr_front_args* a, unsigned long long* counters, cuda
     // front_fast_kernel takes the interior tiles without nodata, the general kernel the rest (from the list).
     const bool slopes_ok = a->slope_lo >= 0.0f && a->slope_hi < 89.0f && a->slope_lo <= a->slope_hi;
     const bool fast = tile_list && bin && p.use_tma && (!a->smask || p.use_tma_mask) && !a->ref_w && !a->src_w &&
-                      p.row_begin == 0 && p.row_end == a->h && a->ref_nrows <= 0 && a->src_nrows <= 0 && a->smask_nrows <= 0 &&
                       (long long)ntx * nty + 1 <= tile_list_cap && ntx < 65536 && nty < 65536 && (!loopmode || slopes_ok) &&
                       !getenv("DCR_NO_FAST_FRONT");
     if (fast) {

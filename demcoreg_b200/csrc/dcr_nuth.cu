@@ -1597,7 +1597,8 @@ static int band_carve(void* workspace, size_t workspace_bytes, long long n, int 
     w->bsel_scratch = ws.take<char>(dcr_bsel_scratch_bytes(n));
     w->bsel_scratch2 = ws.take<char>(dcr_bsel_scratch_bytes(n));
     w->bsel_scratch3 = ws.take<char>(dcr_bsel_scratch_bytes(n));
-    (void)ws.take<unsigned>(dcr_front_list_cap(n));   // same layout as dcr_nuth_iteration (band launches use the general kernel)
+    w->tile_cap = dcr_front_list_cap(n);
+    w->tile_list = ws.take<unsigned>(w->tile_cap);
     if (nuth_ws_carve(ws, n, grid, &w->nw)) return -1;
     w->nw.nd = &w->d->nuth;
     return 0;
@@ -1663,7 +1664,9 @@ extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, 
         DCR_CUDA_OK(cudaMemsetAsync(d, 0, sizeof(IterDev), s));
         dcr_front_args fa = *front;
         if (!remove_outliers) fa.use_max_dz = 0;
-        if ((rc = dcr_front_launch(&fa, d->counters, s))) return rc;
+        // like the single-GPU iteration: the front kernel emits the aspect-bin codes (so the aspect raster is optional)
+        // and may use the fast interior-tile kernel on the band
+        if ((rc = dcr_front_launch(&fa, d->counters, s, w.nw.bin, 0, w.tile_list, w.tile_cap))) return rc;
         want(d->counters, 4, 1);
     } else if (phase >= BP_SEL0 && phase < BP_SEL1) {
         rc = sel_phase(0, phase - BP_SEL0);
@@ -1671,8 +1674,9 @@ extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, 
         rc = sel_phase(1, phase - BP_SEL1);
     } else if (phase == BP_MASK) {
         mad_thresholds_kernel<<<1, 32, 0, s>>>(d, remove_outliers);
-        mask_update_kernel<false><<<(unsigned)((nch + MU_KCH - 1) / MU_KCH), 256, 0, s>>>(front->dh, front->maskbits, n, d, w.chunk_cnt, nullptr, nullptr,
-                                                                nullptr, nullptr, 0, 0);
+        // MAD filter + the Nuth-Kaab samples (y, partial moments, bin codes of the removed pixels) in one pass
+        mask_update_kernel<true><<<(unsigned)((nch + MU_KCH - 1) / MU_KCH), 256, 0, s>>>(
+            front->dh, front->maskbits, n, d, w.chunk_cnt, front->slope, w.nw.y, w.nw.bin, w.nw.part, 0, 0);
         band_rank_count_kernel<<<1, 32, 0, s>>>(d, rank);
         want(&d->count_mad, 2 + 8, 1);  // count_mad, count_final, rank_counts[8] are contiguous
     } else if (phase == BP_COMPRESS) {
@@ -1693,9 +1697,7 @@ extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, 
         rc = sel_phase(4, phase - BP_SEL4);
     } else if (phase == BP_PREPARE) {
         DCR_CUDA_OK(cudaMemsetAsync(w.nw.ghist, 0, (size_t)2 * NB * 2048 * sizeof(unsigned), s));
-        nuth_prepare_kernel<<<grid, 256, 0, s>>>(front->dh, front->slope, front->aspect, front->maskbits,
-                                                 DCR_M_DIFF | DCR_M_ASPECT, n, w.nw.y, w.nw.bin, w.nw.part);
-        band_mom_reduce_kernel<<<1, 256, 0, s>>>(w.nw.part, grid, d);
+        band_mom_reduce_kernel<<<1, 256, 0, s>>>(w.nw.part, (int)((nch + MU_KCH - 1) / MU_KCH), d);   // partials of the mask update
         want(d->mom3, 4, 2);
     } else if (phase == BP_BIN0) {
         band_moments_final_kernel<<<1, 256, 0, s>>>(d, 1);   // trim of y always on (dem_align.py:147)

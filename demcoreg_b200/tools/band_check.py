@@ -19,6 +19,9 @@ def main():
     ap.add_argument("--size", type=int, default=2048)
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--halo", type=int, default=16)
+    ap.add_argument("--native", action="store_true",
+                    help="the library's own NCCL communicator: dcr_band_exchange_halos + dcr_band_iteration (one native call "
+                         "per iteration) instead of interpreter-driven phases over torch.distributed")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -34,7 +37,12 @@ def main():
     r0, r1 = band.band_rows(n, rank, world)
     al = band.BandAligner(torch.from_numpy(p['ref'][r0:r1]).cuda(), torch.from_numpy(p['src'][r0:r1]).cuda(),
                           torch.from_numpy(p['mask'][r0:r1]).cuda(), n, p['gt'], p['ndv'], rank, world, halo=args.halo)
-    al.exchange_halos()
+    comm = None
+    if args.native:
+        comm = band.Comm()
+        band.exchange_halos_native(al, comm)
+    else:
+        al.exchange_halos()
     ok = True
     msgs = []
     if rank == 0:
@@ -42,7 +50,7 @@ def main():
         src = Raster(p['src'], p['gt'], p['ndv'])
         ms = MaskSource(p['mask'], p['gt'])
     for it in range(args.iters):
-        res = band.iteration_distributed(al)
+        res = band.iteration_native(al, comm) if args.native else band.iteration_distributed(al)
         if rank == 0:
             r1g, _, _ = engine.nuth_iteration(ref, src, ms, radix_only=True)
             same = (list(res.nuth.bin_count) == list(r1g.nuth.bin_count) and res.count_final == r1g.count_final
@@ -57,7 +65,10 @@ def main():
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     if rank == 0:
-        print(json.dumps(dict(world=world, size=n, ok=bool(ok), iterations=msgs)))
+        print(json.dumps(dict(world=world, size=n, native=bool(args.native), ok=bool(ok), iterations=msgs)))
+    if comm is not None:
+        torch.cuda.synchronize()
+        comm.close()
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) else 1)
 

@@ -341,6 +341,27 @@ int dcr_band_phase(const dcr_front_args* front, int flags, int rank, int nranks,
 int dcr_band_result(const dcr_front_args* front, void* workspace, size_t workspace_bytes, dcr_iter_result* out,
                     void* stream);
 
+/* The collective side in the library (one communicator per handle, injected or created here).  NCCL is resolved
+ * with dlopen("libnccl.so.2") on first use -- inside a PyTorch process that is the copy torch has loaded.
+ *   dcr_comm_unique_id: rank 0 makes the 128-byte ncclUniqueId and hands it to the other ranks by any means;
+ *   dcr_comm_init:      ncclCommInitRank (collective over the nranks callers);  dcr_comm_set: wrap an ncclComm_t the
+ *                       caller owns;  dcr_comm_destroy: frees the handle (and the communicator it created).
+ *   dcr_band_exchange_halos: grouped ncclSend/ncclRecv of the halo rows of one band raster with rank-1 / rank+1
+ *                       (row indices are stored-row indices of `band`, row_bytes its pitch in bytes).
+ *   dcr_band_iteration: ONE row-band iteration -- every phase of dcr_band_phase followed by the ncclAllReduce (sum) of the
+ *                       buffers it declares, back to back on `stream` (no host work or synchronisation in between), then
+ *                       dcr_band_result.  Collective.  Returns 100 + ncclResult_t on NCCL errors, -7 without libnccl. */
+typedef struct dcr_comm dcr_comm;
+int dcr_comm_unique_id(void* id, size_t id_bytes);
+int dcr_comm_init(const void* id, size_t id_bytes, int rank, int nranks, dcr_comm** comm);
+int dcr_comm_set(void* nccl_comm, int rank, int nranks, dcr_comm** comm);
+int dcr_comm_destroy(dcr_comm* comm);
+int dcr_comm_rank(const dcr_comm* comm, int* rank, int* nranks);
+int dcr_band_exchange_halos(dcr_comm* comm, void* band, int64_t row_bytes, int send_up_row, int n_send_up, int recv_up_row,
+                            int n_recv_up, int send_dn_row, int n_send_dn, int recv_dn_row, int n_recv_dn, void* stream);
+int dcr_band_iteration(const dcr_front_args* front, int flags, dcr_comm* comm, dcr_iter_result* out, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

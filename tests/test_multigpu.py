@@ -10,14 +10,17 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_row_band_nccl_matches_single_gpu(cuda):
+@pytest.mark.parametrize("native", [False, True])
+def test_row_band_nccl_matches_single_gpu(cuda, native):
+    """Row bands under real NCCL against the single-GPU iteration: interpreter-driven phases over torch.distributed, and the
+    native path (the library's own communicator, dcr_band_exchange_halos + dcr_band_iteration)."""
     n = cuda.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 2 if n < 4 else 4
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-           "--master-addr", "127.0.0.1", "--master-port", "29611", "-m", "demcoreg_b200.tools.band_check",
-           "--size", "2048", "--iters", "3"]
+           "--master-addr", "127.0.0.1", "--master-port", "29612" if native else "29611", "-m",
+           "demcoreg_b200.tools.band_check", "--size", "2048", "--iters", "3"] + (["--native"] if native else [])
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
