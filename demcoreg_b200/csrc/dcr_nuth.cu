@@ -8,6 +8,7 @@
 #include <string.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <nvtx3/nvToolsExt.h>
 #include "dcr_common.cuh"
 #include "dcr_internal.cuh"
 
@@ -1162,7 +1163,15 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
     const long long nch = (n + MU_CHUNK - 1) / MU_CHUNK;
     IterDev* d = w.d;
     int rc;
-#define STAGE_MARK(k) do { if (ev) DCR_CUDA_OK(cudaEventRecord(ev[k], s)); } while (0)
+    // stage boundaries: CUDA events for DCR_ITER_PROFILE and an NVTX range per stage (header-only nvtx3: free unless a tool
+    // is attached) -- 0 front, 1 median + MAD, 2 mask update, 3 subsample chain, 4 med_dh / med_slope, 5-6 bin statistics
+    static const char* const stage_name[7] = {"dcr:front (warp+dh+masks+Horn+bins)", "dcr:median+MAD selects",
+                                              "dcr:mask update (+y, moments)", "dcr:subsample scan/compress/dz",
+                                              "dcr:med_dh/med_slope selects + bin statistics", "dcr:bin statistics", "dcr:join+copy"};
+    int nvtx_open = 0;
+#define STAGE_MARK(k) do { if (ev) DCR_CUDA_OK(cudaEventRecord(ev[k], s)); \
+                           if (nvtx_open) { nvtxRangePop(); nvtx_open = 0; } \
+                           if ((k) < 6) { nvtxRangePushA(stage_name[(k) == 5 ? 5 : (k)]); nvtx_open = 1; } } while (0)
     STAGE_MARK(0);
     DCR_CUDA_OK(cudaMemsetAsync(d, 0, sizeof(IterDev), s));
     dcr_front_args fa = *front;

@@ -171,8 +171,9 @@ def getparser():
 
 
 def align(ref_dem_ds, src_dem_ds, mode='nuth', mask_source=None, tol=0.02, max_offset=100, max_dz=100,
-          slope_lim=(0.1, 40), max_iter=30, verbose=True, records=None, tiltcorr=False, polyorder=1):
-    """The iteration loop of reference ``dem_align.py:291-357`` on device-resident rasters.
+          slope_lim=(0.1, 40), max_iter=30, verbose=True, records=None, tiltcorr=False, polyorder=1, res='max'):
+    """The iteration loop of reference ``dem_align.py:291-357`` on device-resident rasters.  ``res``: the resolution of the
+    one-time ``memwarp_multi`` before the loop (``-res``; only matters for inputs of different pixel size).
 
     ``src_dem_ds`` is copied; the copy is shifted in place each iteration (geotransform + band) exactly
     as the reference does.  Returns ``dict(dx, dy, dz, n_iter, iters, src_align)``.
@@ -182,7 +183,7 @@ def align(ref_dem_ds, src_dem_ds, mode='nuth', mask_source=None, tol=0.02, max_o
     src_dem_ds_align = src_dem_ds.copy()
     # dem_align.py:294-299: both rasters are clipped / resampled ONCE to their intersection before the loop (rasters that
     # already share extent and lattice pass through untouched); the loop then works on these
-    ref_dem_ds, src_dem_ds_align = engine.memwarp_multi([ref_dem_ds, src_dem_ds_align])
+    ref_dem_ds, src_dem_ds_align = engine.memwarp_multi([ref_dem_ds, src_dem_ds_align], res=res)
     if mode == 'nuth' and records is None:
         return _align_nuth_native(ref_dem_ds, src_dem_ds_align, mask_source, tol, max_offset, max_dz, slope_lim, max_iter,
                                   verbose, tiltcorr, polyorder)
@@ -305,6 +306,9 @@ def diff_stats(ref_dem_ds, src_dem_ds, mask_source=None, max_dz=100):
     Returns ``dict(stats, stats_filt, diff, diff_filt, gt)`` with the rasters as masked arrays.
     """
     from . import robust_stats
+    if abs(ref_dem_ds.gt[1] - src_dem_ds.gt[1]) >= 1e-3:
+        # (dem_align.py:368-369, 506-507: memwarp_multi(res='max') -- rasters of different pixel size are resampled first)
+        ref_dem_ds, src_dem_ds = engine.memwarp_multi([ref_dem_ds, src_dem_ds], res='max')
     res, grid, bufs = engine.nuth_iteration(ref_dem_ds, src_dem_ds, mask_source, True, max_dz, (0.1, 40))
     base = (bufs.maskbits & _lib.M_BASE) != 0
     filt = (bufs.maskbits & _lib.M_DIFF) != 0
@@ -374,7 +378,8 @@ def main(argv=None):
         rio.write_raster(dst_fn, sa.numpy(), sa.gt, sa.ndv, sa.proj)
         sys.exit()
     out = align(ref, src, mode=mode, mask_source=mask_source, tol=args.tol, max_offset=args.max_offset,
-                max_dz=args.max_dz, slope_lim=slope_lim, max_iter=args.max_iter, tiltcorr=tiltcorr, polyorder=polyorder)
+                max_dz=args.max_dz, slope_lim=slope_lim, max_iter=args.max_iter, tiltcorr=tiltcorr, polyorder=polyorder,
+                res=args.res)
     dx_total, dy_total, dz_total = out['dx'], out['dy'], out['dz']
     xyz_shift_str_cum_fn = '_%s_x%+0.2f_y%+0.2f_z%+0.2f' % (mode, dx_total, dy_total, dz_total)
     align_fn = outprefix + xyz_shift_str_cum_fn + '_align.tif'

@@ -335,17 +335,87 @@ def warp_cubic(src, grid, geom, dst_ndv=0.0):
     return Raster(dst, tuple(grid.gt), dst_ndv, src.proj)
 
 
-def memwarp_multi(ds_list, extent='intersection'):
-    """``warplib.memwarp_multi([a, b], res=..., extent=..., r='cubic')`` for two rasters of equal resolution: a raster whose
-    extent already equals the target grid is returned unchanged (same object); the other one is resampled with the GDAL
-    cubic kernel onto the grid, band nodata 0 (pygeotools' ``dst_ndv``).  Reference ``dem_align.py:294-299`` does this
-    once before the loop (both rasters clipped to their intersection)."""
+def resample_cubic(src, grid, dst_ndv=0.0):
+    """GDAL cubic warp of a Raster onto a grid of ANOTHER resolution (``dcr_resample_cubic``) -> Raster."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    h, w = grid.height, grid.width
+    dst = torch.empty((h, w), dtype=torch.float32, device="cuda")
+    d = src.desc()
+    _lib.check(L.dcr_resample_cubic(C.c_void_p(src.data.data_ptr()), C.byref(d), src.data.stride(0), C.byref(grid),
+                                    C.c_void_p(dst.data_ptr()), w, float(dst_ndv), _stream_ptr(torch)))
+    return Raster(dst, tuple(grid.gt), dst_ndv, src.proj)
+
+
+def target_res(ds_list, res='max'):
+    """``warplib.parse_res``: 'max' | 'min' | 'mean' of the inputs' (square) pixel sizes, or a number."""
+    rl = [(ds.gt[1] + abs(ds.gt[5])) / 2.0 for ds in ds_list]
+    if isinstance(res, str):
+        if res == 'max':
+            return max(rl)
+        if res == 'min':
+            return min(rl)
+        if res == 'mean':
+            return float(np.mean(rl))
+        try:
+            return float(res)
+        except ValueError:
+            raise NotImplementedError("res=%r: only min / max / mean / a number are built (reference dem_align.py:150 also "
+                                      "lists common_scale_factor)" % res)
+    return float(res)
+
+
+def memwarp_multi(ds_list, extent='intersection', res='max'):
+    """``warplib.memwarp_multi([a, b], res=res, extent=extent, r='cubic')`` (reference ``dem_align.py:294-299``: once before the
+    loop, both rasters clipped / resampled to their intersection; ``compute_diff.py:97``).  A raster whose extent and
+    resolution already equal the target grid is returned unchanged (same object); one of the target resolution is
+    resampled by the translation-only GDAL cubic kernel; one of another resolution by the general kernel
+    (``dcr_resample_cubic``: scaled footprint when down-sampling).  Band nodata 0 (pygeotools' ``dst_ndv``)."""
     from .raster import plan_extent
     a, b = ds_list
-    grid, ga, gb = plan_extent(a, b, extent)
+    tres = target_res(ds_list, res)
+    rl = [(ds.gt[1] + abs(ds.gt[5])) / 2.0 for ds in ds_list]
+    if all(abs(r - tres) < 1e-3 for r in rl):
+        grid, ga, gb = plan_extent(a, b, extent)
+        out = []
+        for ds, g in ((a, ga), (b, gb)):
+            out.append(ds if g.identity else warp_cubic(ds, grid, g, 0.0))
+        return out
+    # unequal resolutions: target extent in map coordinates, grid = int(round(extent / res)) (Python round, like pygeotools)
+    L = _lib.lib()
+
+    def ext(r):
+        gt = r.gt
+        return [gt[0], gt[3] + gt[5] * r.RasterYSize, gt[0] + gt[1] * r.RasterXSize, gt[3]]
+    ea, eb = ext(a), ext(b)
+    if extent == 'intersection':
+        te = [max(ea[0], eb[0]), max(ea[1], eb[1]), min(ea[2], eb[2]), min(ea[3], eb[3])]
+        if te[2] <= te[0] or te[3] <= te[1]:
+            raise _lib.DcrError("no intersection between input extents")
+    elif extent == 'union':
+        te = [min(ea[0], eb[0]), min(ea[1], eb[1]), max(ea[2], eb[2]), max(ea[3], eb[3])]
+    elif extent == 'first':
+        te = ea
+    elif extent == 'last':
+        te = eb
+    else:
+        raise ValueError("extent must be one of intersection, union, first, last")
+    grid = _lib.Grid()
+    for k, v in enumerate((te[0], tres, 0.0, te[3], 0.0, -tres)):
+        grid.gt[k] = v
+    grid.width = int(round((te[2] - te[0]) / tres))
+    grid.height = int(round((te[3] - te[1]) / tres))
     out = []
-    for ds, g in ((a, ga), (b, gb)):
-        out.append(ds if g.identity else warp_cubic(ds, grid, g, 0.0))
+    for ds, e, r in ((a, ea, rl[0]), (b, eb, rl[1])):
+        if abs(r - tres) < 1e-3 and all(abs(x - y) < 1e-3 for x, y in zip(e, te)):
+            out.append(ds)
+        elif abs(r - tres) < 1e-3:
+            g = _lib.WarpGeom()
+            d = ds.desc()
+            _lib.check(L.dcr_plan_onto_grid(C.byref(d), C.byref(grid), C.byref(g)))
+            out.append(warp_cubic(ds, grid, g, 0.0))
+        else:
+            out.append(resample_cubic(ds, grid, 0.0))
     return out
 
 

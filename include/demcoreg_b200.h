@@ -83,6 +83,14 @@ int dcr_warp_cubic(const float* src, int src_h, int src_w, int64_t src_stride, d
                    const dcr_warp_geom* geom, float* dst, int h, int w, int64_t dst_stride, float dst_ndv,
                    void* stream);
 
+/* GDAL cubic warp between north-up grids of the same SRS but different pixel size: the one-time
+ * warplib.memwarp_multi(ds_list, res=args.res, extent='intersection') of dem_align.py:298-299 / compute_diff.py:97 when the
+ * inputs do not share a resolution (-res min|max|mean, -tr).  scale = source res / grid res: >= 0.95 -> the 4x4 Catmull-Rom
+ * at per-pixel fractions (bilinear near nodata / edges), < 0.95 -> GDAL's scaled-footprint GWKResample (radius ceil(2/scale),
+ * weight-normalised, nodata pixels skipped).  dst: grid->height x grid->width, nodata `dst_ndv`. */
+int dcr_resample_cubic(const float* src, const dcr_raster_desc* src_desc, int64_t src_stride, const dcr_grid* grid,
+                       float* dst, int64_t dst_stride, double dst_ndv, void* stream);
+
 /* ---- K2: Horn slope / aspect ----------------------------------------------------------
  * gdal.DEMProcessing('slope'|'aspect', computeEdges=False) as reached through
  * geolib.gdaldem_mem_ds <- dem_align.py:54, 100.  Outputs use nodata -9999.  Either output may be NULL. */

@@ -214,6 +214,104 @@ def gdal_cubic_warp(src, src_ndv, geom, H, W, dst_ndv=0.0):
     return out32
 
 
+def gwk_cubic(x):
+    """GDAL ``GWKCubic`` (bicubic convolution, a = -0.5) evaluated at the (scaled) tap distance, double.  [RECALLED]"""
+    ax = np.abs(x)
+    x2 = x * x
+    inner = x2 * (1.5 * ax - 2.5) + 1.0
+    outer = x2 * (-0.5 * ax + 2.5) - 4.0 * ax + 2.0
+    return np.where(ax <= 1.0, inner, np.where(ax <= 2.0, outer, 0.0))
+
+
+def gdal_cubic_resample(src, src_ndv, src_gt, xmin, ymax, tres, H, W, dst_ndv=0.0):
+    """GDAL cubic warp between north-up grids of the same SRS but different resolution (``memwarp_multi(res=...)`` with
+    inputs of unequal pixel size, reference ``dem_align.py:298-299`` / ``compute_diff.py:97``).  [RECALLED] from
+    gdalwarpkernel.cpp, GWKGeneralCase:
+
+    * source position of an output pixel centre in source pixel units: ``sx = (x - X0)/sres``, ``sy = (Y0 - y)/sres``;
+      scale = sres / tres (< 1 when down-sampling; GDAL derives it from the window sizes -- the exact ratio is used here);
+    * the nearest source pixel ``(floor(sy), floor(sx))`` must be inside the raster and valid, else dst nodata;
+    * scale >= 0.95 ("bUse4SamplesFormula"): the 4x4 Catmull-Rom of ``gdal_cubic_warp`` with per-pixel fractions (all 16
+      taps valid, else the bilinear fallback);
+    * scale < 0.95 (``GWKResample``): radius R = ceil(2 / scale), taps i, j in [1 - R, R] around
+      ``(floor(sx - 0.5), floor(sy - 0.5))`` clipped to the raster, invalid pixels skipped, weights
+      ``GWKCubic((i - dx) * scale)``, per-row accumulation in double, result = acc / weight unless the weight sum is within
+      1e-5 of 1; nodata when the weight sum < 1e-6.
+    """
+    src = np.asarray(src, dtype=np.float32)
+    Hs, Ws = src.shape
+    sres = float(src_gt[1])
+    scale = sres / float(tres)
+    valid = ~np.isnan(src)
+    if src_ndv is not None:
+        valid &= (src != np.float32(src_ndv))
+    jj = np.arange(W, dtype=np.float64)
+    ii = np.arange(H, dtype=np.float64)
+    sx = ((xmin + (jj + 0.5) * tres) - src_gt[0]) / sres
+    sy = (src_gt[3] - (ymax - (ii + 0.5) * tres)) / sres
+    nx = np.floor(sx).astype(np.int64)
+    ny = np.floor(sy).astype(np.int64)
+    ix = np.floor(sx - 0.5).astype(np.int64)
+    iy = np.floor(sy - 0.5).astype(np.int64)
+    dx = sx - 0.5 - ix
+    dy = sy - 0.5 - iy
+
+    def take(A, r, c, fill):
+        """A[r, c] over the outer product of row / column index vectors; `fill` outside the raster."""
+        rin = (r >= 0) & (r < Hs)
+        cin = (c >= 0) & (c < Ws)
+        out = A[np.clip(r, 0, Hs - 1)[:, None], np.clip(c, 0, Ws - 1)[None, :]]
+        return np.where(rin[:, None] & cin[None, :], out, fill)
+    near_ok = take(valid, ny, nx, False)
+    P = src.astype(np.float64)
+    if scale >= 0.95:
+        cx = cubic_weights(dx)          # tuples of (W,) arrays
+        cy = cubic_weights(dy)
+        all16 = np.ones((H, W), dtype=bool)
+        for r in range(4):
+            for c in range(4):
+                all16 &= take(valid, iy - 1 + r, ix - 1 + c, False)
+        v = []
+        for r in range(4):
+            p = [take(P, iy - 1 + r, ix - 1 + c, 0.0) for c in range(4)]
+            v.append(cx[0][None, :] * p[0] + cx[1][None, :] * p[1] + cx[2][None, :] * p[2] + cx[3][None, :] * p[3])
+        cubic = cy[0][:, None] * v[0] + cy[1][:, None] * v[1] + cy[2][:, None] * v[2] + cy[3][:, None] * v[3]
+        acc = np.zeros((H, W))
+        div = np.zeros((H, W))
+        for (r, c, w) in ((0, 0, (1.0 - dx)[None, :] * (1.0 - dy)[:, None]), (0, 1, dx[None, :] * (1.0 - dy)[:, None]),
+                          (1, 1, dx[None, :] * dy[:, None]), (1, 0, (1.0 - dx)[None, :] * dy[:, None])):
+            ok = take(valid, iy + r, ix + c, False)
+            val = take(P, iy + r, ix + c, 0.0)
+            div = div + np.where(ok, w, 0.0)
+            acc = acc + np.where(ok, val * w, 0.0)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            bil = np.where(div == 1.0, acc, acc / div)
+        out = np.where(all16, cubic, bil)
+        ok = near_ok & (all16 | (div >= 0.00001))
+    else:
+        R = int(math.ceil(2.0 / scale))
+        acc = np.zeros((H, W))
+        wsum = np.zeros((H, W))
+        for j in range(1 - R, R + 1):
+            w1 = gwk_cubic((j - dy) * scale)                 # (H,)
+            accl = np.zeros((H, W))
+            wl = np.zeros((H, W))
+            for i in range(1 - R, R + 1):
+                w2 = gwk_cubic((i - dx) * scale)             # (W,)
+                ok = take(valid, iy + j, ix + i, False)
+                val = take(P, iy + j, ix + i, 0.0)
+                accl = accl + np.where(ok, val * w2[None, :], 0.0)
+                wl = wl + np.where(ok, w2[None, :], 0.0)
+            acc = acc + accl * w1[:, None]
+            wsum = wsum + wl * w1[:, None]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            out = np.where((wsum < 0.99999) | (wsum > 1.00001), acc / wsum, acc)
+        ok = near_ok & ~(wsum < 0.000001)
+    out32 = out.astype(np.float32)
+    out32[~ok] = np.float32(dst_ndv)
+    return out32
+
+
 def memwarp_multi(ds_list, res="max", extent="intersection", t_srs=None, r="cubic", dst_ndv=0):
     """``warplib.memwarp_multi`` for same-SRS inputs.
 
@@ -236,9 +334,6 @@ def memwarp_multi(ds_list, res="max", extent="intersection", t_srs=None, r="cubi
             raise NotImplementedError(res)
     else:
         tres = float(res)
-    for rr in res_list:
-        if abs(rr - tres) > 1e-3 * tres:
-            raise NotImplementedError("oracle restates the equal-resolution (no down-sampling) case only")
     if extent == "intersection":
         xmin, ymax, W, H, text = intersection_grid(ds_list, tres)
     else:
@@ -258,8 +353,11 @@ def memwarp_multi(ds_list, res="max", extent="intersection", t_srs=None, r="cubi
         if same:
             out.append(ds)
             continue
-        geom = warp_geometry(ds, xmin, ymax, tres)
-        a = gdal_cubic_warp(ds.array, ds.ndv, geom, H, W, dst_ndv=dst_ndv)
+        if abs(get_res(ds)[0] - tres) < 1e-3:
+            geom = warp_geometry(ds, xmin, ymax, tres)
+            a = gdal_cubic_warp(ds.array, ds.ndv, geom, H, W, dst_ndv=dst_ndv)
+        else:   # unequal resolution: per-pixel fractions / scaled footprint
+            a = gdal_cubic_resample(ds.array, ds.ndv, ds.GetGeoTransform(), xmin, ymax, tres, H, W, dst_ndv=dst_ndv)
         out.append(MemDataset(a, (xmin, tres, 0.0, ymax, 0.0, -tres), dst_ndv, ds.proj))
     return out
 

@@ -1030,3 +1030,118 @@ def test_align_loop_ragged_inputs(cuda, case):
     assert np.array_equal(out['src_align'].numpy(), oo['src_align'].array)
     np.testing.assert_allclose(out['src_align'].gt, oo['src_align'].gt, rtol=0, atol=OFFTOL)   # origin + cumulative shift
     assert np.array_equal(out['ref'].numpy(), oo['ref'].array)
+
+
+@pytest.mark.parametrize("shape", [(333, 517), (768, 768), (57, 1031)])
+def test_guard_zones_stay_intact(cuda, shape, monkeypatch):
+    """Out-of-bounds writes (compute-sanitizer is not available on the GPU pool, so the check is our own): every output
+    raster and the workspace of an iteration sit between 64 KB guard zones filled with a pattern; after a one-pass and a
+    radix iteration -- ragged sizes, partial tiles, sub-pixel shift, nodata, static mask -- the guards are untouched and the
+    results equal those of the ordinary allocation."""
+    from demcoreg_b200 import engine
+    from demcoreg_b200.raster import MaskSource
+    h, w = shape
+    n = max(h, w)
+    p = _pair(n=((n + 127) // 128) * 128, res=30.0, nodata_frac=0.01, static_mask_frac=0.2)
+    q = {k: (np.ascontiguousarray(v[:h, :w]) if isinstance(v, np.ndarray) else v) for k, v in p.items()}
+    gt_s = _shifted_gt(q['gt'], 13.7, -21.3)
+    ms = MaskSource(q['mask'], q['gt'])
+    want, _, wb = engine.nuth_iteration(_gds(q, 'ref'), _gds(q, 'src', gt_s), ms)
+    G = 65536
+    PAT = 0xA5
+
+    class Arena(object):
+        def __init__(self):
+            self.guards = []
+
+        def alloc(self, nbytes):
+            nb = (int(nbytes) + 255) // 256 * 256
+            t = cuda.full((G + nb + G,), PAT, dtype=cuda.uint8, device="cuda")
+            self.guards.append((t, nb))
+            return t[G:G + nb]
+
+        def check(self):
+            for t, nb in self.guards:
+                assert bool((t[:G] == PAT).all()) and bool((t[G + nb:] == PAT).all()), "guard zone overwritten"
+    ar = Arena()
+    gh, gw = wb.h, wb.w
+    bufs = engine.IterBuffers.__new__(engine.IterBuffers)
+    bufs.h, bufs.w = gh, gw
+    bufs.dh = ar.alloc(gh * gw * 4).view(cuda.float32)[:gh * gw].view(gh, gw)
+    bufs.slope = ar.alloc(gh * gw * 4).view(cuda.float32)[:gh * gw].view(gh, gw)
+    bufs.aspect = ar.alloc(gh * gw * 4).view(cuda.float32)[:gh * gw].view(gh, gw)
+    bufs.maskbits = ar.alloc(gh * gw)[:gh * gw].view(gh, gw)
+    bufs.ref_w = bufs.src_w = None
+    monkeypatch.setattr(engine, "workspace", lambda nbytes, device=None: ar.alloc(nbytes))
+    for radix in (False, True):
+        res, _, _ = engine.nuth_iteration(_gds(q, 'ref'), _gds(q, 'src', gt_s), ms, bufs=bufs, radix_only=radix)
+        cuda.cuda.synchronize()
+        ar.check()
+        assert (res.dx, res.dy, res.dz, res.count_final) == (want.dx, want.dy, want.dz, want.count_final) or radix
+        assert res.count_final == want.count_final and list(res.nuth.bin_count) == list(want.nuth.bin_count)
+        assert np.array_equal(bufs.maskbits.cpu().numpy(), wb.maskbits.cpu().numpy())
+        assert np.array_equal(bufs.dh.cpu().numpy(), wb.dh.cpu().numpy())
+
+
+@pytest.mark.parametrize("res", ["max", "min", "mean"])
+def test_memwarp_multi_unequal_resolution_matches_oracle(cuda, res):
+    """f3: the general GDAL cubic (dcr_resample_cubic) through engine.memwarp_multi on a 2:1 pair with nodata holes and a
+    source origin off the reference lattice: same grid as the oracle, same untouched pass-through, identical rasters
+    (down-sampled footprint for res='max', 4-sample up-sampling for 'min', both for 'mean')."""
+    from demcoreg_b200 import engine, synth
+    from demcoreg_b200.raster import Raster
+    from oracle import pygeotools_restated as pg
+    p = synth.make_pair(n=256, res=8.0, seed=12, nodata_frac=0.01)
+    q = synth.make_pair(n=512, res=4.0, seed=12, nodata_frac=0.01)
+    gt_s = _shifted_gt(q['gt'], 13.7, -21.3)
+    ga = engine.memwarp_multi([Raster(p['ref'], p['gt'], p['ndv']), Raster(q['src'], gt_s, q['ndv'])], res=res)
+    oa = pg.memwarp_multi([pg.MemDataset(p['ref'], p['gt'], p['ndv']), pg.MemDataset(q['src'], gt_s, q['ndv'])], res=res)
+    for g, o in zip(ga, oa):
+        assert g.RasterYSize == o.RasterYSize and g.RasterXSize == o.RasterXSize
+        np.testing.assert_allclose(g.gt, o.GetGeoTransform(), rtol=0, atol=1e-9)
+        assert (g.ndv if g.ndv is not None else None) == o.ndv
+        assert np.array_equal(g.numpy(), o.array)
+
+
+def test_dem_align_unequal_resolution(cuda):
+    """dem_align on a pair of different pixel size (ref 8 m, src 4 m; -res max): the one-time memwarp_multi brings both to
+    the 8 m intersection grid, then the loop runs as usual -- same iterations and offsets as the oracle."""
+    from demcoreg_b200 import dem_align, synth
+    from demcoreg_b200.raster import Raster
+    from oracle import dem_align as oda, pygeotools_restated as pg
+    p = synth.make_pair(n=384, res=8.0, seed=13)
+    q = synth.make_pair(n=768, res=4.0, seed=13)          # (another realisation of the terrain: only the plumbing matters)
+    src4 = np.repeat(np.repeat(p['src'], 2, axis=0), 2, axis=1)
+    gt4 = (p['gt'][0], 4.0, 0.0, p['gt'][3], 0.0, -4.0)
+    del q
+    out = dem_align.align(Raster(p['ref'], p['gt'], p['ndv']), Raster(src4, gt4, p['ndv']), verbose=False, res='max')
+    ra, sa = pg.memwarp_multi([pg.MemDataset(p['ref'], p['gt'], p['ndv']), pg.MemDataset(src4, gt4, p['ndv'])], res='max')
+    oo = oda.align(ra, sa, final_stats=False)
+    assert out['n_iter'] == oo['n_iter']
+    for k in ('dx', 'dy', 'dz'):
+        assert abs(out[k] - oo[k]) < OFFTOL, (k, out[k], oo[k])
+
+
+def test_compute_diff_tr_and_rate(cuda, tmp_path):
+    """compute_diff -tr on rasters of different pixel size and -rate from the dates in the file names
+    (compute_diff.py:81-93, 132-136)."""
+    from demcoreg_b200 import compute_diff, rasterio_lite as rio, synth
+    from oracle import pygeotools_restated as pg
+    p = synth.make_pair(n=256, res=8.0, seed=14)
+    src4 = np.repeat(np.repeat(p['src'], 2, axis=0), 2, axis=1)
+    gt4 = (p['gt'][0], 4.0, 0.0, p['gt'][3], 0.0, -4.0)
+    f1 = str(tmp_path / "20150101_ref-DEM.npz")
+    f2 = str(tmp_path / "20170101_src-DEM.npz")
+    rio.write_raster(f1, p['ref'], p['gt'], p['ndv'])
+    rio.write_raster(f2, src4, gt4, p['ndv'])
+    dst = compute_diff.main([f1, f2, "-tr", "max", "-rate", "-outdir", str(tmp_path)])
+    d = rio.read_array(dst)
+    ra, sa = pg.memwarp_multi([pg.MemDataset(p['ref'], p['gt'], p['ndv']), pg.MemDataset(src4, gt4, p['ndv'])], res='max')
+    want = pg.ds_getma(sa) - pg.ds_getma(ra)
+    got = np.ma.masked_values(d['array'], -9999.0)
+    assert np.array_equal(np.ma.getmaskarray(got), np.ma.getmaskarray(want))
+    assert np.array_equal(got.compressed(), want.compressed())
+    r = rio.read_array(dst.replace("_diff.", "_diff_rate."))
+    years = (731 * 86400.0) / (365.25 * 86400.0)          # 2015-01-01 -> 2017-01-01
+    rate = np.ma.masked_values(r['array'], -9999.0)
+    np.testing.assert_allclose(rate.compressed(), (want / np.float32(years)).compressed(), rtol=1e-6)
