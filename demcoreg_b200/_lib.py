@@ -133,6 +133,12 @@ SYMBOLS = {
     "dcr_sad_search_ex": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_double),
                                     C.POINTER(C.c_int), C.POINTER(C.c_float), _P, C.c_size_t, _P]),
     "dcr_resample_cubic": (C.c_int, [_P, C.POINTER(RasterDesc), C.c_int64, C.POINTER(Grid), _P, C.c_int64, C.c_double, _P]),
+    "dcr_axis_median_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "dcr_axis_median": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, _P, _P, _P, C.c_size_t, _P]),
+    "dcr_axis_subtract": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, _P, C.c_int, _P]),
+    "dcr_binary_dilate": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "dcr_mask_from_classes": (C.c_int, [_P, C.c_int64, _P, _P, _P]),
+    "dcr_mask_threshold": (C.c_int, [_P, C.c_int64, C.c_float, C.c_int, _P, _P]),
     "dcr_fit_nuth": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]),
     "dcr_apply_z_shift": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_float, _P, _P]),
     "dcr_apply_z_shift_seq": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.c_double, C.POINTER(C.c_float), C.c_int, _P]),

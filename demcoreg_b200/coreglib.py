@@ -204,3 +204,61 @@ def find_subpixel_peak_position(corr, subpixel_method='gaussian'):
     except IndexError:
         subp_peak_position = default_peak_position
     return subp_peak_position[0], subp_peak_position[1]
+
+
+def successive_med(a, first_axis=1, first_axis_only=False, sav_filter=False, sg_window=101, sg_poly=2, min_axes_count=350):
+    """Reference ``coreglib.py:490-584``: subtract the per-row / per-column medians of a difference map (along-track /
+    cross-track correction).  Same arguments and return list ``[b, med_first, med_second, first_correction_surface,
+    second_correction_surface(, med_first_smooth, med_second_smooth)]``.
+
+    The line medians and counts (``np.ma.median`` / ``np.ma.count`` along an axis) and the two subtractions run on the
+    device (``dcr_axis_median``, ``dcr_axis_subtract``); the Savitzky-Golay smoothing of the two 1-D profiles stays on the
+    host (``scipy.signal.savgol_filter``).  Deviation: with ``sav_filter=False`` the reference dies at ``coreglib.py:576``
+    (it uses ``med_second_smooth``, which only exists when ``sav_filter=True``); this function uses ``med_second`` there,
+    which is what the line evidently means.
+    """
+    torch = _lib.require_cuda()
+    second_axis = 0 if first_axis == 1 else 1
+    am = np.ma.asarray(a)
+    mask_np = np.ma.getmaskarray(am)
+    d = torch.from_numpy(np.ascontiguousarray(am.filled(0).astype(np.float32))).cuda()
+    m = torch.from_numpy(np.ascontiguousarray(mask_np.astype(np.uint8))).cuda()
+
+    def profile(x, axis):
+        med, cnt = engine.axis_median(x, m, axis)
+        med = med.cpu().numpy()
+        cnt = cnt.cpu().numpy()
+        # np.ma.median masks a fully masked line; the reference then overwrites every line with too few samples by 0
+        med = np.ma.array(med, mask=np.isnan(med))
+        med[cnt < min_axes_count] = 0
+        return med
+    med_first = profile(d, first_axis)
+    if sav_filter:
+        import scipy.signal
+        med_first_smooth = scipy.signal.savgol_filter(med_first, window_length=sg_window, polyorder=sg_poly, mode='nearest')
+        corr1 = med_first_smooth
+    else:
+        corr1 = med_first
+    first_correction_surface = np.expand_dims(corr1, axis=first_axis)
+    engine.axis_subtract(d, torch.from_numpy(np.ascontiguousarray(np.ma.filled(corr1, 0).astype(np.float32))).cuda(),
+                         1 if first_axis == 1 else 0)
+    if first_axis_only:
+        med_second = np.zeros(am.shape[0 if second_axis == 1 else 1])
+    else:
+        med_second = profile(d, second_axis)
+    if sav_filter:
+        import scipy.signal
+        med_second_smooth = scipy.signal.savgol_filter(med_second, window_length=sg_window, polyorder=sg_poly, mode='nearest')
+        corr2 = med_second_smooth
+    else:
+        corr2 = med_second
+    second_correction_surface = np.expand_dims(corr2, axis=second_axis)
+    engine.axis_subtract(d, torch.from_numpy(np.ascontiguousarray(np.ma.filled(corr2, 0).astype(np.float32))).cuda(),
+                         1 if second_axis == 1 else 0)
+    b = np.ma.array(d.cpu().numpy(), mask=mask_np)
+    if first_axis_only:
+        b = b.astype(np.float64)   # (the reference subtracts a float64 np.zeros profile there: its b becomes float64)
+    out = [b, med_first, med_second, first_correction_surface, second_correction_surface]
+    if sav_filter:
+        out.extend([med_first_smooth, med_second_smooth])
+    return out

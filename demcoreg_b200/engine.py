@@ -510,3 +510,42 @@ def sad_search(ref, ref_mask, src, src_mask, pad, per_offset=False, info=None):
         info['n_per_offset'] = int(nfb.value)
         info['stage_ms'] = dict(zip(("prep", "sample", "pass1", "find", "pass2", "final"), [float(v) for v in stage]))
     return np.array(m[:], dtype=np.float64).reshape(J, J)
+
+
+def axis_median(a, mask, axis):
+    """``np.ma.median(a, axis)`` / ``np.ma.count(a, axis)`` of a device raster (``dcr_axis_median``): float32 tensor of the
+    line medians (NaN for a fully masked line) and an int64 tensor of the unmasked counts."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    h, w = int(a.shape[0]), int(a.shape[1])
+    nl = h if axis == 1 else w
+    med = torch.empty(nl, dtype=torch.float32, device="cuda")
+    cnt = torch.empty(nl, dtype=torch.int64, device="cuda")
+    nb = L.dcr_axis_median_workspace_bytes(h, w, axis)
+    ws = workspace(nb)
+    m = mask.to(torch.uint8).contiguous() if mask is not None else None
+    _lib.check(L.dcr_axis_median(C.c_void_p(a.data_ptr()), C.c_void_p(m.data_ptr()) if m is not None else None, h, w,
+                                 a.stride(0), w, axis, C.c_void_p(med.data_ptr()), C.c_void_p(cnt.data_ptr()),
+                                 C.c_void_p(ws.data_ptr()), ws.numel(), _stream_ptr(torch)))
+    return med, cnt
+
+
+def axis_subtract(a, corr, axis):
+    """``a -= np.expand_dims(corr, axis)`` in place on the device (``dcr_axis_subtract``)."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    c = corr.to(torch.float32).contiguous()
+    _lib.check(L.dcr_axis_subtract(C.c_void_p(a.data_ptr()), int(a.shape[0]), int(a.shape[1]), a.stride(0),
+                                   C.c_void_p(c.data_ptr()), axis, _stream_ptr(torch)))
+    return a
+
+
+def binary_dilate(mask, iterations):
+    """``scipy.ndimage.binary_dilation(mask, iterations=n)`` (cross structure) on a device uint8 0/1 mask -> new tensor."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    m = mask.to(torch.uint8).contiguous().clone()
+    scratch = torch.empty_like(m)
+    _lib.check(L.dcr_binary_dilate(C.c_void_p(m.data_ptr()), int(m.shape[0]), int(m.shape[1]), int(iterations),
+                                   C.c_void_p(scratch.data_ptr()), _stream_ptr(torch)))
+    return m

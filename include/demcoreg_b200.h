@@ -334,6 +334,25 @@ int dcr_polyval2d(const dcr_poly2d* model, const double gt[6], int h, int w, flo
 int dcr_polyval2d_apply(float* band, int h, int w, int64_t stride, const double gt[6], double ndv, int has_ndv,
                         const dcr_poly2d* model, double sign, void* stream);
 
+/* ---- raster pieces next to the hot path ------------------------------------------------------
+ * dcr_axis_median: np.ma.median(a, axis) and np.ma.count(a, axis) of coreglib.successive_med (coreglib.py:537-538,
+ *   562-563): exact median of the unmasked, non-NaN elements of every row (axis = 1) or column (axis = 0); even counts give
+ *   the float32 mean of the two middle values; a fully masked line gives NaN and count 0.  mask: uint8, != 0 = masked, or NULL.
+ *   Workspace only for lines longer than 40960 elements (dcr_axis_median_workspace_bytes).
+ * dcr_axis_subtract: a -= expand_dims(corr, axis) (coreglib.py:553, 580).
+ * dcr_binary_dilate: scipy.ndimage.binary_dilation(mask, iterations = n), default cross structure, border 0
+ *   (dem_mask.py:561-565); mask is 0/1 uint8, updated in place; scratch h*w bytes.
+ * dcr_mask_from_classes: out = lut[classes] (the NLCD class filters of dem_mask.py:111-139);
+ * dcr_mask_threshold: out = x > thresh (greater = 1; bare ground, dem_mask.py:141-157) or x <= thresh (greater = 0; TOA
+ *   reflectance, dem_mask.py:403-409). */
+size_t dcr_axis_median_workspace_bytes(int h, int w, int axis);
+int dcr_axis_median(const float* a, const uint8_t* mask, int h, int w, int64_t stride, int64_t mask_stride, int axis,
+                    float* med, int64_t* count, void* workspace, size_t workspace_bytes, void* stream);
+int dcr_axis_subtract(float* a, int h, int w, int64_t stride, const float* corr, int axis, void* stream);
+int dcr_binary_dilate(uint8_t* mask, int h, int w, int iterations, uint8_t* scratch, void* stream);
+int dcr_mask_from_classes(const uint8_t* classes, int64_t n, const uint8_t lut[256], uint8_t* out, void* stream);
+int dcr_mask_threshold(const float* x, int64_t n, float thresh, int greater, uint8_t* out, void* stream);
+
 /* ---- row-band mode: one very large raster split into bands of output rows, one band per GPU ----------------
  * (BASELINE.json configs[4]; the reference does not tile -- it loads whole arrays, dem_align.py:79-80.)
  * The iteration of dcr_nuth_iteration is cut into dcr_band_nphases() phases.  Each rank calls dcr_band_phase for

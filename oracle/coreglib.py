@@ -208,3 +208,37 @@ def compute_offset_nuth(dh, slope, aspect, min_count=100, remove_outliers=True, 
                        bin_count=full_count, bin_med=full_med, n_final=ydata.size, **info)
         return fit, fit_fig, details
     return fit, fit_fig
+
+
+def successive_med(a, first_axis=1, first_axis_only=False, sav_filter=False, sg_window=101, sg_poly=2, min_axes_count=350):
+    """Reference ``coreglib.py:490-584`` with numpy / scipy.  (``:576`` uses ``med_second_smooth`` when ``sav_filter`` is
+    False -- undefined there, the reference raises; restated with ``med_second``, the evident intent.)"""
+    import scipy.signal
+    second_axis = 0
+    if first_axis == 0:
+        second_axis = 1
+    med_first = np.ma.median(a, axis=first_axis)
+    count_first = np.ma.count(a, axis=first_axis)
+    med_first[count_first < min_axes_count] = 0
+    if sav_filter:
+        med_first_smooth = scipy.signal.savgol_filter(med_first, window_length=sg_window, polyorder=sg_poly, mode='nearest')
+        first_correction_surface = np.expand_dims(med_first_smooth, axis=first_axis)
+    else:
+        first_correction_surface = np.expand_dims(med_first, axis=first_axis)
+    b = a - first_correction_surface
+    if first_axis_only:
+        med_second = np.zeros(a.shape[0 if second_axis == 1 else 1])
+    else:
+        med_second = np.ma.median(b, axis=second_axis)
+        count_second = np.ma.count(a, axis=second_axis)
+        med_second[count_second < min_axes_count] = 0
+    if sav_filter:
+        med_second_smooth = scipy.signal.savgol_filter(med_second, window_length=sg_window, polyorder=sg_poly, mode='nearest')
+        second_correction_surface = np.expand_dims(med_second_smooth, axis=second_axis)
+    else:
+        second_correction_surface = np.expand_dims(med_second, axis=second_axis)
+    b = b - second_correction_surface
+    out = [b, med_first, med_second, first_correction_surface, second_correction_surface]
+    if sav_filter:
+        out.extend([med_first_smooth, med_second_smooth])
+    return out

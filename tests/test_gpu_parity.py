@@ -1145,3 +1145,77 @@ def test_compute_diff_tr_and_rate(cuda, tmp_path):
     years = (731 * 86400.0) / (365.25 * 86400.0)          # 2015-01-01 -> 2017-01-01
     rate = np.ma.masked_values(r['array'], -9999.0)
     np.testing.assert_allclose(rate.compressed(), (want / np.float32(years)).compressed(), rtol=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(257, 1031), (8, 41000), (300, 300)])
+def test_axis_median_matches_numpy(cuda, shape):
+    """dcr_axis_median = np.ma.median / np.ma.count along an axis: odd and even counts, duplicates, fully masked lines,
+    lines longer than the shared-memory staging (global spill)."""
+    from demcoreg_b200 import engine
+    rng = np.random.default_rng(5)
+    h, w = shape
+    a = np.round(rng.normal(size=shape) * 4).astype(np.float32) / 4          # many duplicates
+    m = rng.random(shape) < 0.3
+    m[3, :] = True
+    m[:, 7] = True
+    a[5, ::2] = 1.25
+    ma = np.ma.array(a, mask=m)
+    for axis in (1, 0):
+        med, cnt = engine.axis_median(cuda.from_numpy(a).cuda(), cuda.from_numpy(m.astype(np.uint8)).cuda(), axis)
+        want = np.ma.median(ma, axis=axis)
+        got = med.cpu().numpy()
+        assert np.array_equal(cnt.cpu().numpy(), np.ma.count(ma, axis=axis))
+        assert np.array_equal(np.isnan(got), np.ma.getmaskarray(want))
+        ok = ~np.isnan(got)
+        assert np.array_equal(got[ok], np.asarray(want[ok], dtype=np.float32))
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(first_axis=0), dict(first_axis_only=True), dict(sav_filter=True, sg_window=31)])
+def test_successive_med_matches_oracle(cuda, kw):
+    """coreglib.successive_med (coreglib.py:490-584) against the numpy/scipy restatement."""
+    from demcoreg_b200 import coreglib
+    from oracle import coreglib as ocl
+    rng = np.random.default_rng(6)
+    h, w = 420, 530
+    yy, xx = np.mgrid[0:h, 0:w]
+    a = (rng.normal(size=(h, w)) + 0.5 * np.sin(yy / 40.0) + 0.3 * np.cos(xx / 25.0)).astype(np.float32)
+    m = rng.random((h, w)) < 0.2
+    m[:, :30] |= rng.random((h, 30)) < 0.9          # columns with too few samples -> correction 0
+    ma = np.ma.array(a, mask=m)
+    got = coreglib.successive_med(ma, **kw)
+    want = ocl.successive_med(ma, **kw)
+    assert len(got) == len(want)
+    exact = not kw.get('sav_filter')
+    for g, o in zip(got, want):
+        assert np.shape(g) == np.shape(o)
+        assert np.array_equal(np.ma.getmaskarray(g), np.ma.getmaskarray(o))
+        if exact:
+            assert np.array_equal(np.ma.filled(g, 0), np.ma.filled(o, 0))
+        else:
+            np.testing.assert_allclose(np.ma.filled(g, 0), np.ma.filled(o, 0), rtol=0, atol=2e-6)
+    assert got[0].dtype == want[0].dtype
+
+
+def test_dem_mask_raster_pieces(cuda):
+    """dem_mask.py:111-161, 403-409, 448-565 (raster parts): class / threshold masks and the dilated final mask."""
+    from scipy import ndimage
+    from demcoreg_b200 import dem_mask
+    rng = np.random.default_rng(8)
+    l = rng.choice(np.array([11, 12, 31, 41, 42, 43, 52, 71], dtype=np.uint8), size=(300, 411))
+    for f in ('rock', 'rock+ice', 'rock+ice+water', 'not_forest', 'not_forest+not_water'):
+        want = {'rock': l == 31, 'rock+ice': (l == 31) | (l == 12), 'rock+ice+water': (l == 31) | (l == 12) | (l == 11),
+                'not_forest': ~((l == 41) | (l == 42) | (l == 43)),
+                'not_forest+not_water': ~((l == 41) | (l == 42) | (l == 43) | (l == 11))}[f]
+        assert np.array_equal(dem_mask.get_nlcd_mask(l, f), want)
+    assert dem_mask.get_nlcd_mask(l, 'bogus') is None
+    bg = (rng.random((300, 411)) * 100).astype(np.float32)
+    assert np.array_equal(dem_mask.get_bareground_mask(bg, 60), bg > 60)
+    toa = np.ma.array(rng.random((300, 411)).astype(np.float32), mask=rng.random((300, 411)) < 0.1)
+    assert np.array_equal(dem_mask.get_toa_mask(toa, 0.4), ~np.ma.getmaskarray(np.ma.masked_greater(toa, 0.4)))
+    valid = [dem_mask.get_nlcd_mask(l, 'not_forest'), bg > 60]
+    for nit in (None, 1, 3):
+        got = dem_mask.combine_masks(l.shape, valid, dilate=nit)
+        newmask = ~(valid[0] & valid[1])
+        if nit is not None:
+            newmask = ~(ndimage.binary_dilation(~newmask, iterations=nit))
+        assert np.array_equal(got, newmask)
