@@ -440,7 +440,8 @@ def bench_band(args, torch, rank, world, local, dist):
     src_b[hole] = synth.NDV
     del base, hole, nz
     torch.cuda.empty_cache()
-    al = band.BandAligner(ref_b, src_b, msk_b, n, (500000.0, res, 0.0, 4100000.0, 0.0, -res), synth.NDV, rank, world, halo=64)
+    al = band.BandAligner(ref_b, src_b, msk_b, n, (500000.0, res, 0.0, 4100000.0, 0.0, -res), synth.NDV, rank, world, halo=64,
+                          keep_aspect=False)
     del ref_b, src_b, msk_b
     torch.cuda.empty_cache()
     comm = band.Comm()
@@ -479,8 +480,9 @@ def bench_band(args, torch, rank, world, local, dist):
                         "mask, 1 %% nodata) split into %d row bands; NCCL halo exchange + histogram all-reduces" % (n, n, res, world),
             "ms_per_iteration": ms_step, "gpix_per_s": pix / nst / (ms_step * 1e-3) / 1e9, "steps": nst,
             "roofline_frac_of_n_x_peak": ach / (peak * world), "halo_rows": 64,
-            "path": "dcr_band_iteration: 28 phases + their ncclAllReduce enqueued natively on one stream (library-owned "
-                    "communicator), fast front kernel on the band, bins from the front kernel",
+            "path": "dcr_band_iteration: 33 phases + their ncclAllReduce enqueued natively on one stream (library-owned "
+                    "communicator); fast front kernel on the band, bins from the front kernel, one-pass sample-bracket selects "
+                    "(sample keys / counts / histograms all-reduced), deferred z shifts",
             "ms_per_iteration_interpreter_phases": ms_py,
             "last_step_shift_m": [r.dx, r.dy, r.dz], "select_engine": int(r.select_engine), "bin_engine": int(r.bin_engine)}
 

@@ -106,7 +106,7 @@ def _halo_of_neighbour(band, nrank, world, below):
 class BandAligner(object):
     """One rank's state of the row-band iteration."""
 
-    def __init__(self, ref_rows, src_rows, mask_rows, height, gt, ndv, rank, world, halo=16):
+    def __init__(self, ref_rows, src_rows, mask_rows, height, gt, ndv, rank, world, halo=16, keep_aspect=True):
         torch = _lib.require_cuda()
         self.torch = torch
         self.rank, self.world, self.halo = rank, world, halo
@@ -122,12 +122,15 @@ class BandAligner(object):
                 b.halo = halo
         self.ws = None
         self.bufs = None
+        self.pending_dz = []        # z shifts of the source not yet written into the band (applied by the front kernel)
+        self.keep_aspect = keep_aspect
 
     def bands(self):
         return [b for b in (self.ref, self.src, self.mask) if b is not None]
 
     def exchange_halos(self, group=None):
         """NCCL halo exchange of all three rasters with the neighbouring ranks."""
+        self.flush_z()
         for b in self.bands():
             exchange_halos(b, self.owned, self.rank, self.world, group)
 
@@ -181,6 +184,11 @@ class BandAligner(object):
         a.use_max_dz = 1 if remove_outliers else 0
         a.slope_lo, a.slope_hi = float(slope_lim[0]), float(slope_lim[1])
         a.dh, a.slope, a.aspect, a.maskbits = (t.data_ptr() for t in self.bufs)
+        if not self.keep_aspect:
+            a.aspect = None             # the bin codes come out of the front kernel: the aspect raster is optional
+        a.src_ndz = len(self.pending_dz)
+        for k, z in enumerate(self.pending_dz):
+            a.src_dz[k] = z
         self.args = a
         self.grid = grid
         self.flags = _lib.ITER_REMOVE_OUTLIERS if remove_outliers else 0
@@ -216,18 +224,30 @@ class BandAligner(object):
                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return res
 
-    def apply_shift(self, dx, dy, dz):
-        """``apply_xy_shift`` + ``apply_z_shift`` on this rank's band (halo rows included: they stay consistent)."""
-        L = _lib.lib()
-        torch = self.torch
+    def apply_shift(self, dx, dy, dz, defer=True):
+        """``apply_xy_shift`` + ``apply_z_shift`` on this rank's band (halo rows included: they stay consistent).  The z
+        shift is deferred like in the native single-GPU loop: the next front kernels add the pending float32 shifts, in
+        order, while they load the source tile; every third one is written into the band (``flush_z``)."""
         g = list(self.src.gt)
         g[0] += dx
         g[3] += dy
         self.src.gt = tuple(g)
+        self.pending_dz.append(float(np.float32(dz)))
+        if not defer or len(self.pending_dz) >= 3:
+            self.flush_z()
+
+    def flush_z(self):
+        """Write the pending z shifts into the source band (same ordered float32 adds as one apply_z_shift per iteration)."""
+        if not self.pending_dz:
+            return
+        L = _lib.lib()
+        torch = self.torch
         b = self.src
-        _lib.check(L.dcr_apply_z_shift(C.c_void_p(b.data.data_ptr()), int(b.data.shape[0]), b.width, b.data.stride(0),
-                                       b.ndv if b.ndv is not None else 0.0, float(np.float32(dz)), None,
-                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        dz = (C.c_float * len(self.pending_dz))(*self.pending_dz)
+        _lib.check(L.dcr_apply_z_shift_seq(C.c_void_p(b.data.data_ptr()), int(b.data.shape[0]), b.width, b.data.stride(0),
+                                           b.ndv if b.ndv is not None else 0.0, dz, len(self.pending_dz),
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        self.pending_dz = []
 
 
 def iteration_distributed(al, group=None, **kw):
@@ -235,10 +255,15 @@ def iteration_distributed(al, group=None, **kw):
     boundaries per iteration).  Returns IterResult.  ``iteration_native`` is the production path."""
     import torch.distributed as dist
     nph = al.begin_iteration(**kw)
-    for ph in range(nph):
-        for t in al.run_phase(ph):
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-    return al.result()
+    for attempt in range(2):
+        for ph in range(nph):
+            for t in al.run_phase(ph):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        res = al.result()
+        if res.status != _lib.STATUS_RERUN_RADIX:
+            break
+        al.flags |= _lib.ITER_RADIX_ONLY     # a one-pass selection declined (on every rank alike): radix selects
+    return res
 
 
 class Comm(object):
@@ -287,6 +312,7 @@ def exchange_halos_native(al, comm):
     """Halo exchange of the three band rasters through the library's communicator (grouped ncclSend / ncclRecv)."""
     torch = al.torch
     L = _lib.lib()
+    al.flush_z()
     a, b = al.owned
     for band in al.bands():
         nrows = int(band.data.shape[0])
@@ -332,19 +358,26 @@ class VirtualGroup(object):
                     na, ne = self.ranks[r + 1].owned
                     b.data[e:nrows] = nb.data[na:na + (nrows - e)]
 
-    def iteration(self, **kw):
+    def iteration(self, radix_only=False, **kw):
         nph = 0
         for al in self.ranks:
             nph = al.begin_iteration(**kw)
-        for ph in range(nph):
-            outs = [al.run_phase(ph) for al in self.ranks]
-            for k in range(len(outs[0])):
-                tot = outs[0][k].clone()
-                for o in outs[1:]:
-                    tot += o[k]
-                for o in outs:
-                    o[k].copy_(tot)
-        res = [al.result() for al in self.ranks]
+            if radix_only:
+                al.flags |= _lib.ITER_RADIX_ONLY
+        for attempt in range(2):
+            for ph in range(nph):
+                outs = [al.run_phase(ph) for al in self.ranks]
+                for k in range(len(outs[0])):
+                    tot = outs[0][k].clone()
+                    for o in outs[1:]:
+                        tot += o[k]
+                    for o in outs:
+                        o[k].copy_(tot)
+            res = [al.result() for al in self.ranks]
+            if res[0].status != _lib.STATUS_RERUN_RADIX:
+                break
+            for al in self.ranks:
+                al.flags |= _lib.ITER_RADIX_ONLY
         return res
 
     def apply_shift(self, dx, dy, dz):

@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(1024) bsel_sample_kernel(const SelView v, doub
 typedef BselCollector<16, 4096> MainCollector;
 template <int TRANSFORM>
 __global__ void __launch_bounds__(BS_THREADS) bsel_main_kernel(const SelView v, BselState* st, unsigned* ghist,
-                                                               unsigned* __restrict__ cand, unsigned cap, double q_percent) {
+                                                               unsigned* __restrict__ cand, unsigned cap, double q_percent,
+                                                               int band) {
     extern __shared__ __align__(16) unsigned char bsel_smem[];
     MainCollector::Shared* sh = reinterpret_cast<MainCollector::Shared*>(bsel_smem);
     __shared__ unsigned s_scr[33];
@@ -220,14 +221,16 @@ __global__ void __launch_bounds__(BS_THREADS) bsel_main_kernel(const SelView v, 
             col.add(x, !(mb & reject));
         },
         [&]() { col.drain(); });
-    col.finish(ghist, q_percent, gridDim.x, s_scr);
+    col.finish(ghist, q_percent, gridDim.x, s_scr, band);
 }
 
 // Refinement over the candidate buffer only (a few per cent of the data): histogram the next <= 11 bits of
 // the candidates sharing the resolved prefix of each rank; the last CTA to finish locates the sub-bins.
 // Ties of any multiplicity are handled (the final level has one bin per distinct key).
+// mode 0: histogram + find by the last CTA (single GPU); row-band mode splits the two around the all-reduce of ghist:
+// mode 1 = histogram of this rank's candidates only, mode 2 = find only (one CTA, on the summed histogram)
 __global__ void __launch_bounds__(BS_THREADS) bsel_refine_kernel(BselState* st, const unsigned* __restrict__ cand,
-                                                                 unsigned* ghist /* [2][2048] */) {
+                                                                 unsigned* ghist /* [2][2048] */, int mode) {
     __shared__ bool s_last;
     if (st->done) return;
     const unsigned ncand = st->ncand;
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(BS_THREADS) bsel_refine_kernel(BselState* st, 
     const int ns = cs > 11 ? cs - 11 : 0;
     const unsigned smask = (1u << (cs - ns)) - 1u;
     const unsigned p0 = st->prefix[0] >> cs, p1 = st->prefix[1] >> cs;
-    {
+    if (mode != 2) {
         const unsigned step = gridDim.x * BS_THREADS;
         for (unsigned i0 = blockIdx.x * BS_THREADS + threadIdx.x; i0 < ncand; i0 += 4 * step) {
             unsigned kv[4];
@@ -252,12 +255,15 @@ __global__ void __launch_bounds__(BS_THREADS) bsel_refine_kernel(BselState* st, 
             }
         }
     }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
+    if (mode == 1) return;
+    if (mode == 0) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+    }
     {
         __shared__ unsigned s_scratch[33];
         __shared__ unsigned s_sel[2];
@@ -330,8 +336,8 @@ int dcr_bsel_sample_enqueue(const SelView& v, double q_percent, BselState* st, v
 int dcr_bsel_refine_enqueue(BselState* st, void* scratch, long long n_max, cudaStream_t s) {
     unsigned *hist, *cand, cap;
     dcr_bsel_buffers(scratch, n_max, &hist, &cand, &cap);
-    bsel_refine_kernel<<<dcr_num_sms() * 4, BS_THREADS, 0, s>>>(st, cand, hist);  // shift -> max(shift-11, 0)
-    bsel_refine_kernel<<<dcr_num_sms() * 4, BS_THREADS, 0, s>>>(st, cand, hist);  // -> 0 (returns at once if done)
+    bsel_refine_kernel<<<dcr_num_sms() * 4, BS_THREADS, 0, s>>>(st, cand, hist, 0);  // shift -> max(shift-11, 0)
+    bsel_refine_kernel<<<dcr_num_sms() * 4, BS_THREADS, 0, s>>>(st, cand, hist, 0);  // -> 0 (returns at once if done)
     DCR_LAUNCH_OK("bsel_refine_kernel");
     return 0;
 }
@@ -357,9 +363,193 @@ int dcr_bsel_enqueue(const SelView& v, double q_percent, BselState* st, void* sc
     if (grid < grid0) grid = grid0;
     if (grid > (1 << 20)) grid = 1 << 20;
     if (v.transform == 1)
-        bsel_main_kernel<1><<<(unsigned)grid, BS_THREADS, sizeof(MainCollector::Shared), s>>>(v, st, hist, cand, cap, q_percent);
+        bsel_main_kernel<1><<<(unsigned)grid, BS_THREADS, sizeof(MainCollector::Shared), s>>>(v, st, hist, cand, cap, q_percent, 0);
     else
-        bsel_main_kernel<0><<<(unsigned)grid, BS_THREADS, sizeof(MainCollector::Shared), s>>>(v, st, hist, cand, cap, q_percent);
+        bsel_main_kernel<0><<<(unsigned)grid, BS_THREADS, sizeof(MainCollector::Shared), s>>>(v, st, hist, cand, cap, q_percent, 0);
     DCR_LAUNCH_OK("bsel_main_kernel");
     return dcr_bsel_refine_enqueue(st, scratch, n_max, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// Row-band mode: the same selection over a view that is split across ranks.  The one streaming pass stays; what the single
+// GPU does with last-CTA hand-offs is cut at the points where the ranks must agree, and the small buffers in between are
+// summed over the ranks by the caller (ncclAllReduce / in-process sum):
+//   sub 0  sample     this rank gathers its share of the S = 8192 stratified sample keys (strata k in [S r / R, S (r+1) / R)
+//                     over its own elements) into a zeroed key array                              -> all-reduce keys[8192]
+//   sub 1  bracket    every rank localises the SAME bracket from the complete sample; main pass over its own elements:
+//                     below / total counts, bracket histogram, candidates (kept local)   -> all-reduce {below, total}, ghist[2049]
+//   sub 2  find       ranks located + bracket verified on the summed histogram (identical on every rank), then the histogram
+//                     of the local candidates under the resolved prefix                           -> all-reduce ghist[4096]
+//   sub 3  refine     sub-bins located; next 11 bits histogrammed                                 -> all-reduce ghist[4096]
+//   sub 4  refine     final value (published); a declined selection leaves st->fallback = 1 on every rank.
+// Exactness: the counts, histograms and candidate keys are integers, so every rank computes the same order statistic as the
+// single-GPU selection does.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) bsel_band_sample_kernel(const SelView v, BselState* st, float* publish,
+                                                                unsigned* __restrict__ keys, int rank, int nranks) {
+    const long long n = v.n_ptr ? *v.n_ptr : v.n;
+    const float center = v.center_ptr ? *v.center_ptr : v.center_imm;
+    const int k0 = (int)(((long long)BS_S * rank) / nranks), k1 = (int)(((long long)BS_S * (rank + 1)) / nranks);
+    const int ns = k1 - k0;   // this rank's strata
+    if (threadIdx.x == 0) {
+        st->fallback = 0; st->done = 0; st->empty = 0;
+        st->below = 0; st->total = 0; st->ncand = 0; st->nsmall = 0; st->ticket = 0;
+        st->publish = publish;
+    }
+    for (int j = threadIdx.x; j < ns; j += 1024) {
+        unsigned key = 0xFFFFFFFFu;
+        if (n > 0) {
+            // hashed position inside stratum j of this rank's elements (a plain stride aliases with the raster width)
+            const unsigned long long lo = ((unsigned long long)j * (unsigned long long)n) / (unsigned long long)ns;
+            unsigned long long hi = ((unsigned long long)(j + 1) * (unsigned long long)n) / (unsigned long long)ns;
+            if (hi <= lo) hi = lo + 1;
+            const unsigned long long hsh = ((unsigned long long)(k0 + j) * 0x9E3779B97F4A7C15ull) >> 20;
+            const long long i = (long long)(lo + hsh % (hi - lo));
+            if (i < n) {
+                const unsigned mb = v.m ? (unsigned)v.m[i] : 0u;
+                unsigned kk;
+                if (bsel_key(v, center, v.x[i], mb, &kk)) key = kk;
+            }
+        }
+        keys[k0 + j] = key;   // (the other ranks' slots stay 0: the sum over ranks assembles the sample)
+    }
+}
+
+// the localisation half of bsel_sample_kernel on a complete key array (identical input and result on every rank)
+__global__ void __launch_bounds__(1024) bsel_band_bracket_kernel(const unsigned* __restrict__ keys, double q_percent, BselState* st) {
+    __shared__ unsigned s[BS_S];
+    __shared__ unsigned hist[1024];
+    __shared__ unsigned s_scratch[33];
+    __shared__ unsigned s_kmin, s_kmax, s_valid;
+    __shared__ unsigned s_bin[2], s_ex[2];
+    if (threadIdx.x == 0) { s_kmin = 0xFFFFFFFFu; s_kmax = 0u; s_valid = 0u; }
+    __syncthreads();
+    {
+        unsigned kmn = 0xFFFFFFFFu, kmx = 0u, nv = 0;
+#pragma unroll
+        for (int q = 0; q < BS_S / 1024; ++q) {
+            const unsigned k = keys[q * 1024 + threadIdx.x];
+            s[q * 1024 + threadIdx.x] = k;
+            if (k != 0xFFFFFFFFu) { kmn = min(kmn, k); kmx = max(kmx, k); ++nv; }
+        }
+        kmn = __reduce_min_sync(0xffffffffu, kmn);
+        kmx = __reduce_max_sync(0xffffffffu, kmx);
+        nv = __reduce_add_sync(0xffffffffu, nv);
+        if ((threadIdx.x & 31) == 0) { atomicMin(&s_kmin, kmn); atomicMax(&s_kmax, kmx); atomicAdd(&s_valid, nv); }
+    }
+    __syncthreads();
+    const long long m = s_valid;
+    bool open_lo = true, open_hi = true;
+    long long ra = 0, rb = 0;
+    if (m > 0) {
+        const double f = q_percent / 100.0;
+        const double r = f * (double)(m - 1);
+        const double d = 5.0 * sqrt((double)m * f * (1.0 - f)) + 8.0;
+        const long long a0 = (long long)floor(r - d), b0 = (long long)ceil(r + d);
+        open_lo = a0 < 0;
+        open_hi = b0 >= m;
+        ra = open_lo ? 0 : a0;
+        rb = open_hi ? m - 1 : b0;
+    }
+    unsigned base = s_kmin;
+    unsigned long long span = m > 0 ? (unsigned long long)s_kmax - s_kmin + 1ull : 1ull;
+    for (int round = 0; round < 3 && m > 0; ++round) {
+        int shift = 0;
+        while ((span >> shift) > 1024ull) ++shift;
+        hist[threadIdx.x] = 0u;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < BS_S / 1024; ++q) {
+            const unsigned k = s[q * 1024 + threadIdx.x];
+            if (k != 0xFFFFFFFFu && k >= base && (unsigned long long)(k - base) < span) atomicAdd(&hist[(k - base) >> shift], 1u);
+        }
+        __syncthreads();
+        const unsigned hv = hist[threadIdx.x];
+        unsigned tot;
+        const unsigned ex = dcr_block_excl_scan(hv, s_scratch, &tot);
+        if ((long long)ex <= ra && ra < (long long)ex + hv) { s_bin[0] = threadIdx.x; s_ex[0] = ex; }
+        if ((long long)ex <= rb && rb < (long long)ex + hv) { s_bin[1] = threadIdx.x; s_ex[1] = ex; }
+        __syncthreads();
+        const unsigned long long nb = (unsigned long long)base + ((unsigned long long)s_bin[0] << shift);
+        unsigned long long nt = (unsigned long long)base + (((unsigned long long)s_bin[1] + 1ull) << shift);  // exclusive
+        if (nt > (unsigned long long)base + span) nt = (unsigned long long)base + span;
+        ra -= s_ex[0];
+        rb -= s_ex[0];
+        base = (unsigned)nb;
+        span = nt - nb;
+        __syncthreads();
+        if (shift == 0) break;
+    }
+    if (threadIdx.x == 0) {
+        unsigned klo = dcr_f2key(-INFINITY), khi = dcr_f2key(INFINITY);
+        if (m > 0) {
+            if (!open_lo) klo = base;
+            if (!open_hi) khi = (unsigned)((unsigned long long)base + span - 1ull);
+        }
+        st->klo = klo; st->khi = khi;
+        st->flo = dcr_key2f(klo); st->fhi = dcr_key2f(khi);
+        const unsigned long long bspan = (unsigned long long)khi - klo + 1ull;
+        int shift = 0;
+        while ((bspan >> shift) > 2048ull) ++shift;
+        st->shift = shift;
+    }
+}
+
+__global__ void __launch_bounds__(BS_THREADS) bsel_band_find_kernel(BselState* st, unsigned* ghist, double q_percent, unsigned cap) {
+    __shared__ unsigned s_cum[2049];
+    __shared__ unsigned s_scr[33];
+    if (st->done) return;
+    bsel_find_block(st, ghist, q_percent, cap, s_cum, s_scr, 1);
+}
+
+int dcr_bsel_band_nsub(void) { return 5; }
+
+// Sub-phase `sub` of a band selection; red_ptr / red_count / red_kind / *nred describe what the caller sums over the ranks
+// before the next sub-phase (kind 0 = uint32, 1 = int64).
+int dcr_bsel_band_phase(const SelView& v, double q_percent, BselState* st, void* scratch, long long n_max, int rank, int nranks,
+                        int sub, cudaStream_t s, float* publish, void** red_ptr, int64_t* red_count, int* red_kind, int* nred) {
+    unsigned *hist, *cand, cap;
+    dcr_bsel_buffers(scratch, n_max, &hist, &cand, &cap);
+    DcrCtx* ctx = dcr_ctx();
+    if (!ctx) return -1;
+    // the sample keys live at the END of the candidate buffer's first 64 K words (cap >= 65536): candidates are appended
+    // from the front only after the bracket kernel has consumed the sample
+    unsigned* keys = cand + (65536 - BS_S);
+    auto want = [&](void* p, int64_t cnt, int kind) { red_ptr[*nred] = p; red_count[*nred] = cnt; red_kind[*nred] = kind; ++*nred; };
+    if (sub == 0) {
+        DCR_CUDA_OK(cudaMemsetAsync(keys, 0, BS_S * sizeof(unsigned), s));
+        DCR_CUDA_OK(cudaMemsetAsync(hist, 0, 4096 * sizeof(unsigned), s));
+        bsel_band_sample_kernel<<<1, 1024, 0, s>>>(v, st, publish, keys, rank, nranks);
+        want(keys, BS_S, 0);
+    } else if (sub == 1) {
+        bsel_band_bracket_kernel<<<1, 1024, 0, s>>>(keys, q_percent, st);
+        if (!(ctx->attrs & DCR_ATTR_BSEL)) {   // per device
+            DCR_CUDA_OK(cudaFuncSetAttribute(bsel_main_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(MainCollector::Shared)));
+            DCR_CUDA_OK(cudaFuncSetAttribute(bsel_main_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(MainCollector::Shared)));
+            ctx->attrs |= DCR_ATTR_BSEL;
+        }
+        long long grid = (n_max + 57343) / 57344;
+        if (grid < ctx->sms * 8) grid = ctx->sms * 8;
+        if (grid > (1 << 20)) grid = 1 << 20;
+        if (v.transform == 1)
+            bsel_main_kernel<1><<<(unsigned)grid, BS_THREADS, sizeof(MainCollector::Shared), s>>>(v, st, hist, cand, cap, q_percent, 1);
+        else
+            bsel_main_kernel<0><<<(unsigned)grid, BS_THREADS, sizeof(MainCollector::Shared), s>>>(v, st, hist, cand, cap, q_percent, 1);
+        want(&st->below, 2, 1);
+        want(hist, 2049, 0);
+    } else if (sub == 2) {
+        bsel_band_find_kernel<<<1, BS_THREADS, 0, s>>>(st, hist, q_percent, cap);
+        bsel_refine_kernel<<<dcr_num_sms() * 4, BS_THREADS, 0, s>>>(st, cand, hist, 1);
+        want(hist, 4096, 0);
+    } else if (sub == 3) {
+        bsel_refine_kernel<<<1, BS_THREADS, 0, s>>>(st, cand, hist, 2);
+        bsel_refine_kernel<<<dcr_num_sms() * 4, BS_THREADS, 0, s>>>(st, cand, hist, 1);
+        want(hist, 4096, 0);
+    } else {
+        bsel_refine_kernel<<<1, BS_THREADS, 0, s>>>(st, cand, hist, 2);
+    }
+    DCR_LAUNCH_OK("band selection kernels");
+    return 0;
 }

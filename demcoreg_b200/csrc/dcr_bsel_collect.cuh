@@ -31,8 +31,10 @@ __device__ __forceinline__ void bsel_publish(BselState* st) {
 // Level-0 find (run by the LAST CTA of bsel_main_kernel): the bracket-histogram bin of each of the two ranks,
 // after VERIFYING that both ranks fall inside the bracket and that no candidate was dropped.
 // off = key - klo; bin0 = off >> shift.  256 threads, 8 bins each.
+// band != 0 (row-band mode): below / total / ghist have been summed over all ranks, the candidates stay on their ranks --
+// the per-rank "no candidate dropped" checks were folded into the all-reduced overflow word ghist[2048] by the main pass.
 __device__ __forceinline__ void bsel_find_block(BselState* st, unsigned* ghist, double q_percent, unsigned cap, unsigned* s_cum /*[2049]*/,
-                                unsigned* s_scratch /*[33]*/) {
+                                unsigned* s_scratch /*[33]*/, int band = 0) {
     const int t = threadIdx.x;
     unsigned v[8], sum = 0;
 #pragma unroll
@@ -42,9 +44,11 @@ __device__ __forceinline__ void bsel_find_block(BselState* st, unsigned* ghist, 
 #pragma unroll
     for (int q = 0; q < 8; ++q) { s_cum[t * 8 + q] = ex; ex += v[q]; }
     if (t == 0) s_cum[2048] = total;
+    const unsigned overflow = band ? __ldcg(ghist + 2048) : 0u;
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < 8; ++q) ghist[t * 8 + q] = 0u;
+    if (band && t == 0) ghist[2048] = 0u;
     if (t == 0) {
         const long long count = (long long)st->total;
         st->count = count;
@@ -58,7 +62,8 @@ __device__ __forceinline__ void bsel_find_block(BselState* st, unsigned* ghist, 
             st->gamma = g;
             const long long c[2] = {klo - (long long)st->below, khi - (long long)st->below};
             const long long nin = (long long)total;
-            const bool ok = (c[0] >= 0) && (c[1] < nin) && (st->ncand <= cap) && ((long long)st->ncand == nin);
+            const bool ok = band ? ((c[0] >= 0) && (c[1] < nin) && overflow == 0u)
+                                 : ((c[0] >= 0) && (c[1] < nin) && (st->ncand <= cap) && ((long long)st->ncand == nin));
             if (!ok) { st->fallback = 1; st->done = 1; }
             else {
                 for (int r = 0; r < 2; ++r) {
@@ -168,7 +173,9 @@ struct BselCollector {
 
     // all threads of the CTA, once, after the stream (contains barriers).  nctas = CTAs taking part in this selection.
     // s_scr: 33 words of shared scratch (used by the last CTA only).
-    __device__ __forceinline__ void finish(unsigned* ghist, double q_percent, unsigned nctas, unsigned* s_scr) {
+    // band != 0: no find here -- the caller all-reduces below / total / ghist[0..2048] over the ranks first; the last CTA
+    // only records whether this rank dropped candidates (ghist[2048], summed with the rest)
+    __device__ __forceinline__ void finish(unsigned* ghist, double q_percent, unsigned nctas, unsigned* s_scr, int band = 0) {
         if (!on) return;
         const int lane = threadIdx.x & 31;
         drain();
@@ -198,6 +205,14 @@ struct BselCollector {
         __syncthreads();
         if (!sh->last) return;
         __threadfence();
+        if (band) {
+            if (threadIdx.x == 0) {
+                const unsigned nc = *((volatile unsigned*)&st->ncand);
+                ghist[2048] = (nc > cap) ? 1u : 0u;
+                st->ticket = 0;
+            }
+            return;
+        }
         bsel_find_block(st, ghist, q_percent, cap, sh->buf, s_scr);
     }
 };

@@ -135,18 +135,25 @@ extern "C" int dcr_band_iteration(const dcr_front_args* front, int flags, dcr_co
     cudaStream_t s = (cudaStream_t)stream;
     static const ncclDataType_t kind_type[3] = {ncclUint32, ncclInt64, ncclFloat64};
     const int nph = dcr_band_nphases();
-    for (int ph = 0; ph < nph; ++ph) {
-        void* ptrs[2];
-        int64_t counts[2];
-        int kinds[2], nred = 0;
-        int rc = dcr_band_phase(front, flags, h->rank, h->nranks, ph, workspace, workspace_bytes, ptrs, counts, kinds, &nred, stream);
-        if (rc) return rc;
-        if (h->nranks > 1 && nred > 0) {
-            if (nred > 1) DCR_NCCL_OK(api->GroupStart());
-            for (int k = 0; k < nred; ++k)
-                DCR_NCCL_OK(api->AllReduce(ptrs[k], ptrs[k], (size_t)counts[k], kind_type[kinds[k]], ncclSum, h->comm, s));
-            if (nred > 1) DCR_NCCL_OK(api->GroupEnd());
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const int f = flags | (attempt ? DCR_ITER_RADIX_ONLY : 0);
+        for (int ph = 0; ph < nph; ++ph) {
+            void* ptrs[2];
+            int64_t counts[2];
+            int kinds[2], nred = 0;
+            int rc = dcr_band_phase(front, f, h->rank, h->nranks, ph, workspace, workspace_bytes, ptrs, counts, kinds, &nred, stream);
+            if (rc) return rc;
+            if (h->nranks > 1 && nred > 0) {
+                if (nred > 1) DCR_NCCL_OK(api->GroupStart());
+                for (int k = 0; k < nred; ++k)
+                    DCR_NCCL_OK(api->AllReduce(ptrs[k], ptrs[k], (size_t)counts[k], kind_type[kinds[k]], ncclSum, h->comm, s));
+                if (nred > 1) DCR_NCCL_OK(api->GroupEnd());
+            }
         }
+        int rc = dcr_band_result(front, workspace, workspace_bytes, out, stream);
+        if (rc) return rc;
+        // a declined one-pass selection (seen by every rank alike): once more with the radix selects
+        if (out->status != DCR_STATUS_RERUN_RADIX) break;
     }
-    return dcr_band_result(front, workspace, workspace_bytes, out, stream);
+    return 0;
 }

@@ -88,6 +88,10 @@ void dcr_bsel_buffers(void* scratch, long long n_max, unsigned** hist, unsigned*
 int dcr_bsel_sample_enqueue(const SelView& v, double q_percent, BselState* st, void* scratch, long long n_max, cudaStream_t s,
                             float* publish = nullptr);
 int dcr_bsel_refine_enqueue(BselState* st, void* scratch, long long n_max, cudaStream_t s);
+// row-band mode: the selection cut into dcr_bsel_band_nsub() sub-phases with all-reduced hand-offs (see dcr_bsel.cu)
+int dcr_bsel_band_nsub(void);
+int dcr_bsel_band_phase(const SelView& v, double q_percent, BselState* st, void* scratch, long long n_max, int rank, int nranks,
+                        int sub, cudaStream_t s, float* publish, void** red_ptr, int64_t* red_count, int* red_kind, int* nred);
 
 // ---- nuth (dcr_nuth.cu) ----
 struct NuthDev;  // device block

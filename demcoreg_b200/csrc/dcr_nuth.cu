@@ -1525,20 +1525,27 @@ extern "C" int dcr_align_nuth(dcr_align_state* st, int max_steps, int flags, dcr
 // ------------------------------------------------------------------------------------------
 enum {
     BP_FRONT = 0,
-    BP_SEL0 = 1,       // 4 phases per selection: H0 | F0+H1 | F1+H2 | F2+publish
-    BP_SEL1 = 5,
-    BP_MASK = 9,
-    BP_COMPRESS = 10,
-    BP_SEL2 = 11,
-    BP_SEL3 = 15,
-    BP_SEL4 = 19,
-    BP_PREPARE = 23,
-    BP_BIN0 = 24,
-    BP_BIN1 = 25,
-    BP_BIN2 = 26,
-    BP_FINAL = 27,
-    BP_COUNT = 28
+    // 5 phases per selection.  One-pass sample-bracket select (dcr_bsel_band_phase): sample | bracket + main pass | find +
+    // refine | refine | final.  Radix select (DCR_ITER_RADIX_ONLY, and the rerun after a declined bracket): H0 | F0+H1 |
+    // F1+H2 | F2+publish | -.
+    BP_SEL0 = 1,
+    BP_SEL1 = 6,
+    BP_MASK = 11,
+    BP_COMPRESS = 12,
+    BP_SEL2 = 13,
+    BP_SEL3 = 18,
+    BP_SEL4 = 23,
+    BP_PREPARE = 28,
+    BP_BIN0 = 29,
+    BP_BIN1 = 30,
+    BP_BIN2 = 31,
+    BP_FINAL = 32,
+    BP_COUNT = 33
 };
+
+__global__ void band_set_engine_kernel(IterDev* d, int use_bsel) {
+    if (threadIdx.x == 0) d->selpad = use_bsel;
+}
 
 __global__ void band_rank_count_kernel(IterDev* d, int rank) {
     if (threadIdx.x == 0) d->rank_counts[rank] = (long long)d->count_final;
@@ -1651,10 +1658,15 @@ extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, 
         else { v.x = front->slope; v.reject = DCR_M_SLOPE; }
         return v;
     };
+    const int use_bsel = (flags & DCR_ITER_RADIX_ONLY) ? 0 : 1;
     auto sel_phase = [&](int k, int sub) -> int {
-        // sub 0: H0 | 1: F0+H1 | 2: F1+H2 | 3: F2 + publish
         if ((k == 0 || k == 1) && !remove_outliers) return 0;
         SelView v = view_of(k);
+        if (use_bsel)
+            return dcr_bsel_band_phase(v, 50.0, &d->bsel[k], w.bsel_scratch, k == 3 ? w.dense_cap : n, rank, nranks, sub, s,
+                                       &d->selres[k], reduce_ptr, reduce_count, reduce_kind, nreduce);
+        // radix: sub 0: H0 | 1: F0+H1 | 2: F1+H2 | 3: F2 + publish | 4: -
+        if (sub > 3) return 0;
         int r2 = 0;
         if (sub == 0) DCR_CUDA_OK(cudaMemsetAsync(w.hist, 0, DCR_SEL_HIST_WORDS * sizeof(unsigned), s));
         if (sub > 0) r2 = dcr_sel_find_pass(&d->sel[k], w.hist, 50.0, sub - 1, s);
@@ -1671,6 +1683,7 @@ extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, 
 
     if (phase == BP_FRONT) {
         DCR_CUDA_OK(cudaMemsetAsync(d, 0, sizeof(IterDev), s));
+        band_set_engine_kernel<<<1, 32, 0, s>>>(d, use_bsel);
         dcr_front_args fa = *front;
         if (!remove_outliers) fa.use_max_dz = 0;
         // like the single-GPU iteration: the front kernel emits the aspect-bin codes (so the aspect raster is optional)
@@ -1747,5 +1760,12 @@ extern "C" int dcr_band_result(const dcr_front_args* front, void* workspace, siz
     DCR_CUDA_OK(cudaMemcpyAsync(hd, w.d, sizeof(IterDev), cudaMemcpyDeviceToHost, s));
     DCR_CUDA_OK(cudaStreamSynchronize(s));
     memset(out, 0, sizeof(*out));
-    return iter_finalize(hd, 0, out);
+    const int engine = hd->selpad ? 1 : 0;
+    if (engine) {
+        // a one-pass selection declined (bracket missed / heavy ties / overflow; the decision was taken on all-reduced data,
+        // so every rank sees it): the caller reruns the iteration with DCR_ITER_RADIX_ONLY
+        for (int k = 0; k < 5; ++k)
+            if (hd->bsel[k].fallback) { out->status = DCR_STATUS_RERUN_RADIX; out->select_engine = 0; return 0; }
+    }
+    return iter_finalize(hd, engine, out);
 }

@@ -361,6 +361,8 @@ int dcr_mask_threshold(const float* x, int64_t n, float thresh, int greater, uin
  * all ranks (ncclAllReduce / torch.distributed.all_reduce on `stream`) and calls the next phase.  Halo rows of the
  * rasters are exchanged by the caller (ncclSend/Recv).  After the last phase dcr_band_result() returns the same
  * dcr_iter_result on every rank.  Workspace: dcr_iteration_workspace_bytes(rows_in_band * w). */
+#define DCR_STATUS_RERUN_RADIX 100   /* dcr_iter_result.status of dcr_band_result: a one-pass selection declined on every rank
+                                      * alike; run the iteration again with DCR_ITER_RADIX_ONLY (dcr_band_iteration does) */
 int dcr_band_nphases(void);
 int dcr_band_phase(const dcr_front_args* front, int flags, int rank, int nranks, int phase, void* workspace,
                    size_t workspace_bytes, void** reduce_ptr, int64_t* reduce_count, int* reduce_kind, int* nreduce,

@@ -1219,3 +1219,31 @@ def test_dem_mask_raster_pieces(cuda):
         if nit is not None:
             newmask = ~(ndimage.binary_dilation(~newmask, iterations=nit))
         assert np.array_equal(got, newmask)
+
+
+def test_row_band_one_pass_selects_and_radix_rerun(cuda):
+    """Row bands use the one-pass sample-bracket selects (sample keys, counts and histograms summed over the ranks); heavy
+    ties make a bracket decline on every rank alike and the iteration reruns with the radix selects.  Both ways the integer
+    results equal the single-GPU iteration's."""
+    from demcoreg_b200 import engine, band
+    from demcoreg_b200.raster import MaskSource
+    p = _pair(n=1024, res=8.0, nodata_frac=0.01, static_mask_frac=0.3)
+    for quant in (False, True):
+        ref, src = p['ref'], p['src']
+        if quant:   # quantised elevations: thousands of equal dh values around the median
+            ref = np.where(ref == p['ndv'], p['ndv'], np.round(ref)).astype(np.float32)
+            src = np.where(src == p['ndv'], p['ndv'], np.round(src)).astype(np.float32)
+        q = dict(p, ref=ref, src=src)
+        ms = MaskSource(p['mask'], p['gt'])
+        r1, _, _ = engine.nuth_iteration(_gds(q, 'ref'), _gds(q, 'src'), ms, radix_only=True)
+        vg = band.VirtualGroup(ref, src, p['mask'], p['gt'], p['ndv'], 3, halo=8)
+        res = vg.iteration()
+        for r in res:
+            assert r.status == r1.status
+            for f in ("count_base", "count_maxdz", "count_mad", "count_final", "count_slope", "med1", "nmad1", "dz_med", "med_dh",
+                      "med_slope"):
+                assert getattr(r, f) == getattr(r1, f), (quant, f, getattr(r, f), getattr(r1, f))
+            assert list(r.nuth.bin_count) == list(r1.nuth.bin_count)
+        if not quant:
+            assert res[0].select_engine == 1, "the one-pass selects should have run on the bands"
+        print("band selects: quantised=%s engine=%d" % (quant, res[0].select_engine))
