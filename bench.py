@@ -463,6 +463,7 @@ def bench_band(args, torch, rank, world, local, dist):
         for _ in range(nst):
             r = step(native)
             pix += al.grid.height * al.grid.width
+            engines.append((int(r.select_engine), int(r.bin_engine)))
         e1.record()
         dist.barrier()
         torch.cuda.synchronize()
@@ -470,6 +471,7 @@ def bench_band(args, torch, rank, world, local, dist):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / nst, pix, r
     nst = 4
+    engines = []
     ms_py, _, _ = timed(False, 2)     # interpreter-driven phases over torch.distributed (round 1's path), for comparison
     ms_step, pix, r = timed(True, nst)
     peak, _ = peaks()
@@ -484,7 +486,8 @@ def bench_band(args, torch, rank, world, local, dist):
                     "communicator); fast front kernel on the band, bins from the front kernel, one-pass sample-bracket selects "
                     "(sample keys / counts / histograms all-reduced), deferred z shifts",
             "ms_per_iteration_interpreter_phases": ms_py,
-            "last_step_shift_m": [r.dx, r.dy, r.dz], "select_engine": int(r.select_engine), "bin_engine": int(r.bin_engine)}
+            "last_step_shift_m": [r.dx, r.dy, r.dz], "select_engine": int(r.select_engine), "bin_engine": int(r.bin_engine),
+            "radix_reruns": sum(1 for e in engines if e != (1, 1)), "steps_counted": len(engines)}
 
 
 def main():

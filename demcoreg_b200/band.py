@@ -123,6 +123,7 @@ class BandAligner(object):
         self.ws = None
         self.bufs = None
         self.pending_dz = []        # z shifts of the source not yet written into the band (applied by the front kernel)
+        self.sticky_flags = 0       # engines that declined for this raster stay switched off (ITER_RADIX_BINS / _ONLY)
         self.keep_aspect = keep_aspect
 
     def bands(self):
@@ -191,7 +192,7 @@ class BandAligner(object):
             a.src_dz[k] = z
         self.args = a
         self.grid = grid
-        self.flags = _lib.ITER_REMOVE_OUTLIERS if remove_outliers else 0
+        self.flags = (_lib.ITER_REMOVE_OUTLIERS if remove_outliers else 0) | self.sticky_flags
         nbytes = L.dcr_iteration_workspace_bytes(nrows * W)
         if self.ws is None or self.ws.numel() < nbytes:
             self.ws = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda")
@@ -215,6 +216,12 @@ class BandAligner(object):
             off = ptrs[k] - self.ws.data_ptr()
             out.append(self.ws[off:off + counts[k] * sz].view(dtype))
         return out
+
+    def note_declined(self, res):
+        """A one-pass selection / the fast bins declined (on every rank alike): switch that engine off for this raster."""
+        add = _lib.ITER_RADIX_BINS if res.select_engine else _lib.ITER_RADIX_ONLY
+        self.flags |= add
+        self.sticky_flags |= add
 
     def result(self):
         torch = self.torch
@@ -255,14 +262,14 @@ def iteration_distributed(al, group=None, **kw):
     boundaries per iteration).  Returns IterResult.  ``iteration_native`` is the production path."""
     import torch.distributed as dist
     nph = al.begin_iteration(**kw)
-    for attempt in range(2):
+    for attempt in range(3):
         for ph in range(nph):
             for t in al.run_phase(ph):
                 dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         res = al.result()
         if res.status != _lib.STATUS_RERUN_RADIX:
             break
-        al.flags |= _lib.ITER_RADIX_ONLY     # a one-pass selection declined (on every rank alike): radix selects
+        al.note_declined(res)
     return res
 
 
@@ -305,6 +312,11 @@ def iteration_native(al, comm, **kw):
     res = _lib.IterResult()
     _lib.check(L.dcr_band_iteration(C.byref(al.args), al.flags, comm.handle, C.byref(res), C.c_void_p(al.ws.data_ptr()),
                                     al.ws.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    # an engine that declined inside the call (and was rerun natively) stays off for the next iterations of this raster
+    if not res.select_engine:
+        al.sticky_flags |= _lib.ITER_RADIX_ONLY
+    elif not res.bin_engine:
+        al.sticky_flags |= _lib.ITER_RADIX_BINS
     return res
 
 
@@ -364,7 +376,7 @@ class VirtualGroup(object):
             nph = al.begin_iteration(**kw)
             if radix_only:
                 al.flags |= _lib.ITER_RADIX_ONLY
-        for attempt in range(2):
+        for attempt in range(3):
             for ph in range(nph):
                 outs = [al.run_phase(ph) for al in self.ranks]
                 for k in range(len(outs[0])):
@@ -376,8 +388,8 @@ class VirtualGroup(object):
             res = [al.result() for al in self.ranks]
             if res[0].status != _lib.STATUS_RERUN_RADIX:
                 break
-            for al in self.ranks:
-                al.flags |= _lib.ITER_RADIX_ONLY
+            for al, r in zip(self.ranks, res):
+                al.note_declined(r)
         return res
 
     def apply_shift(self, dx, dy, dz):

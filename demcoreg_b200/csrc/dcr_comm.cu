@@ -135,8 +135,8 @@ extern "C" int dcr_band_iteration(const dcr_front_args* front, int flags, dcr_co
     cudaStream_t s = (cudaStream_t)stream;
     static const ncclDataType_t kind_type[3] = {ncclUint32, ncclInt64, ncclFloat64};
     const int nph = dcr_band_nphases();
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        const int f = flags | (attempt ? DCR_ITER_RADIX_ONLY : 0);
+    int f = flags;
+    for (int attempt = 0; attempt < 3; ++attempt) {
         for (int ph = 0; ph < nph; ++ph) {
             void* ptrs[2];
             int64_t counts[2];
@@ -152,8 +152,9 @@ extern "C" int dcr_band_iteration(const dcr_front_args* front, int flags, dcr_co
         }
         int rc = dcr_band_result(front, workspace, workspace_bytes, out, stream);
         if (rc) return rc;
-        // a declined one-pass selection (seen by every rank alike): once more with the radix selects
+        // a declined one-pass selection / fast bin path (seen by every rank alike): once more with the radix engine for it
         if (out->status != DCR_STATUS_RERUN_RADIX) break;
+        f |= out->select_engine ? DCR_ITER_RADIX_BINS : DCR_ITER_RADIX_ONLY;
     }
     return 0;
 }

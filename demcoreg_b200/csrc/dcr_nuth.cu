@@ -339,12 +339,21 @@ __global__ void nuth_count_final_kernel(NuthDev* nd) {
 // ------------------------------------------------------------------------------------------
 #define FB_COARSE 64
 #define FB_FINE 1024
-#define FB_SLOT 128
+#define FB_SLOT 512    // keys of one final fine cell that pass D ranks exactly (more -> heavy ties -> radix bins)
+#define NUTH_GHIST_WORDS (2 * NB * 2048 + 65536)   // radix histogram [2][NB][2048]; the fast path's scratch lives in it too
 #define FB_HB_WORDS (2 * NB * FB_FINE)              // histB [2][NB][1024]
 #define FB_HA_OFF FB_HB_WORDS                       // histA [NB][64]
 #define FB_SLOT_OFF (FB_HA_OFF + NB * FB_COARSE)    // slots [NB][2][FB_SLOT]
 #define FB_SLOTN_OFF (FB_SLOT_OFF + NB * 2 * FB_SLOT)  // slot counters [NB][2]
 #define FB_WORDS (FB_SLOTN_OFF + NB * 2)
+// row-band mode (the candidates of a fine cell are spread over the ranks): one overflow word, this rank's own slots and slot
+// counts, and the table of every rank's slot counts -- all inside the same [2][NB][2048] histogram allocation
+#define FB_FLAG_OFF FB_WORDS
+#define FB_LSLOT_OFF (FB_WORDS + 16)
+#define FB_LSLOTN_OFF (FB_LSLOT_OFF + NB * 2 * FB_SLOT)
+#define FB_RCNT_OFF (FB_LSLOTN_OFF + NB * 2)
+#define FB_BAND_WORDS (FB_RCNT_OFF + 8 * NB * 2)
+static_assert(FB_BAND_WORDS <= NUTH_GHIST_WORDS, "band-mode scratch must fit the histogram allocation");
 
 __device__ __forceinline__ unsigned fb_fine(float y, float rmin, float scale) {
     const float t = (y - rmin) * scale;
@@ -493,11 +502,13 @@ __global__ void __launch_bounds__(256) fb_passB_kernel(const float* __restrict__
 }
 
 // one warp per bin: fine cells of the two median elements (scan of 1024 fine cells)
-__global__ void __launch_bounds__(256) fb_findB_kernel(NuthDev* nd, unsigned* __restrict__ ghist, unsigned cap) {
+// band_flag (row-band mode): all-reduced "some rank ran out of candidate space" word instead of this rank's own count
+__global__ void __launch_bounds__(256) fb_findB_kernel(NuthDev* nd, unsigned* __restrict__ ghist, unsigned cap,
+                                                       const unsigned* __restrict__ band_flag) {
     const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (b >= NB || nd->fast_fallback) return;
-    if (b == 0 && lane == 0 && nd->fast_ncand > cap) nd->fast_fallback = 1;
+    if (b == 0 && lane == 0 && (band_flag ? (*band_flag != 0u) : (nd->fast_ncand > cap))) nd->fast_fallback = 1;
     if (nd->bin_count[b] == 0) return;
     const unsigned c0 = nd->fa_cell[0][b], c1 = nd->fa_cell[1][b];
     for (int r = 0; r < 2; ++r) {
@@ -526,14 +537,12 @@ __global__ void __launch_bounds__(256) fb_findB_kernel(NuthDev* nd, unsigned* __
 }
 
 __global__ void __launch_bounds__(256) fb_passC_kernel(NuthDev* nd, const unsigned long long* __restrict__ cand,
-                                                       unsigned* __restrict__ ghist) {
+                                                       unsigned* __restrict__ slots, unsigned* __restrict__ slotn) {
     __shared__ unsigned short s_f0[NB], s_f1[NB];
     if (nd->fast_fallback) return;
     for (int k = threadIdx.x; k < NB; k += 256) { s_f0[k] = nd->fb_cell[0][k]; s_f1[k] = nd->fb_cell[1][k]; }
     __syncthreads();
     const unsigned ncand = nd->fast_ncand;
-    unsigned* slots = ghist + FB_SLOT_OFF;
-    unsigned* slotn = ghist + FB_SLOTN_OFF;
     const unsigned step = gridDim.x * 256;
     for (unsigned i0 = blockIdx.x * 256 + threadIdx.x; i0 < ncand; i0 += 4 * step) {
         unsigned long long rec[4];
@@ -591,6 +600,35 @@ __global__ void __launch_bounds__(256) fb_passD_kernel(NuthDev* nd, const unsign
     }
 }
 
+// ---- row-band mode glue of the fast bins -----------------------------------------------------------------------------
+__global__ void fb_band_flag_kernel(const NuthDev* nd, unsigned cap, unsigned* flag) {
+    if (threadIdx.x == 0) *flag = (nd->fast_ncand > cap) ? 1u : 0u;
+}
+// this rank's row of the slot-count table (the other rows stay zero: the sum over ranks assembles the table)
+__global__ void fb_band_counts_kernel(const unsigned* __restrict__ lslotn, unsigned* __restrict__ rcnt, int rank) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < NB * 2) rcnt[rank * NB * 2 + k] = lslotn[k];
+}
+// this rank's keys of every final fine cell go behind those of the lower ranks in the (zeroed) common slot array; the total
+// per cell is known to every rank from the table
+__global__ void __launch_bounds__(256) fb_band_scatter_kernel(const unsigned* __restrict__ lslots, const unsigned* __restrict__ rcnt,
+                                                              int rank, int nranks, unsigned* __restrict__ slots,
+                                                              unsigned* __restrict__ slotn, NuthDev* nd) {
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5);   // one warp per (bin, cell)
+    const int lane = threadIdx.x & 31;
+    if (k >= NB * 2 || nd->fast_fallback) return;
+    unsigned off = 0, tot = 0;
+    for (int r = 0; r < nranks; ++r) {
+        const unsigned c = rcnt[r * NB * 2 + k];
+        if (r < rank) off += c;
+        tot += c;
+    }
+    const unsigned mine = rcnt[rank * NB * 2 + k];
+    if (lane == 0) slotn[k] = tot;
+    if (tot > FB_SLOT) return;                        // (pass D declines: heavy ties)
+    for (unsigned i = lane; i < mine; i += 32) slots[k * FB_SLOT + off + i] = lslots[k * FB_SLOT + i];
+}
+
 struct NuthWs {
     float* y;
     unsigned short* bin;
@@ -613,14 +651,14 @@ static unsigned nuth_cand_cap(long long n) {
 }
 static size_t nuth_ws_bytes(long long n, int grid) {
     return dcr_al256(n * sizeof(float)) + dcr_al256(n * sizeof(unsigned short)) + dcr_al256((size_t)nuth_nparts(n, grid) * sizeof(NuthPartial)) +
-           dcr_al256((size_t)2 * NB * 2048 * sizeof(unsigned)) + dcr_al256(sizeof(NuthDev)) +
+           dcr_al256((size_t)NUTH_GHIST_WORDS * sizeof(unsigned)) + dcr_al256(sizeof(NuthDev)) +
            dcr_al256((size_t)nuth_cand_cap(n) * sizeof(unsigned long long));
 }
 static int nuth_ws_carve(DcrBump& ws, long long n, int grid, NuthWs* w) {
     w->y = ws.take<float>(n);
     w->bin = ws.take<unsigned short>(n);
     w->part = ws.take<NuthPartial>(nuth_nparts(n, grid));
-    w->ghist = ws.take<unsigned>((size_t)2 * NB * 2048);
+    w->ghist = ws.take<unsigned>((size_t)NUTH_GHIST_WORDS);
     w->nd = ws.take<NuthDev>(1);
     w->cand_cap = nuth_cand_cap(n);
     w->cand = ws.take<unsigned long long>(w->cand_cap);
@@ -656,8 +694,8 @@ static int nuth_bins_fast_enqueue(long long n, const NuthWs& w, cudaStream_t s) 
     fb_passA_kernel<<<nsm * 2, 512, smemA, s>>>(w.y, w.bin, n, w.nd, w.ghist);
     fb_findA_kernel<<<(NB + 127) / 128, 128, 0, s>>>(w.nd, w.ghist);
     fb_passB_kernel<<<nsm * 16, 256, 0, s>>>(w.y, w.bin, n, w.nd, w.ghist, w.cand, w.cand_cap);  // small CTAs: the 4 % candidates of a CTA must fit its staging buffer
-    fb_findB_kernel<<<(NB + 7) / 8, 256, 0, s>>>(w.nd, w.ghist, w.cand_cap);
-    fb_passC_kernel<<<nsm * 8, 256, 0, s>>>(w.nd, w.cand, w.ghist);
+    fb_findB_kernel<<<(NB + 7) / 8, 256, 0, s>>>(w.nd, w.ghist, w.cand_cap, nullptr);
+    fb_passC_kernel<<<nsm * 8, 256, 0, s>>>(w.nd, w.cand, w.ghist + FB_SLOT_OFF, w.ghist + FB_SLOTN_OFF);
     fb_passD_kernel<<<(NB + 7) / 8, 256, 0, s>>>(w.nd, w.ghist);
     DCR_LAUNCH_OK("fast bin kernels");   // (n_final = sum of the bin counts: nuth_dev_to_stats, on the host)
     return 0;
@@ -1536,11 +1574,14 @@ enum {
     BP_SEL3 = 18,
     BP_SEL4 = 23,
     BP_PREPARE = 28,
+    // bins.  Fast path (shared-memory coarse cells, then the fine cells of the median cells): A | findA + B | findB + C |
+    // scatter of the per-rank slots | D.  Radix bins (DCR_ITER_RADIX_ONLY / rerun): H0 | F0+H1 | F1+H2 | F2 + counts | -.
     BP_BIN0 = 29,
     BP_BIN1 = 30,
     BP_BIN2 = 31,
-    BP_FINAL = 32,
-    BP_COUNT = 33
+    BP_BIN3 = 32,
+    BP_BIN4 = 33,
+    BP_COUNT = 34
 };
 
 __global__ void band_set_engine_kernel(IterDev* d, int use_bsel) {
@@ -1592,6 +1633,13 @@ __global__ void band_moments_final_kernel(IterDev* d, int remove_outliers) {
         nd->mean_y = mean; nd->std_y = sd;
         if (remove_outliers) { const float fs = 3.0f * sd; nd->rmin = mean - fs; nd->rmax = mean + fs; }
         else { nd->rmin = -INFINITY; nd->rmax = INFINITY; }
+        // set-up of the fast bin path, as nuth_moments_final_kernel does
+        const float span = nd->rmax - nd->rmin;
+        nd->fast_ncand = 0;
+        nd->fast_fallback = 0;
+        nd->fast_scale = 0.f;
+        if (!(span > 0.0f) || isinf(span) || isnan(span)) nd->fast_fallback = 1;
+        else nd->fast_scale = 65536.0f / span;
     }
     for (int k = threadIdx.x; k < NB; k += blockDim.x) {
         nd->bin_count[k] = 0ull;
@@ -1659,6 +1707,7 @@ extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, 
         return v;
     };
     const int use_bsel = (flags & DCR_ITER_RADIX_ONLY) ? 0 : 1;
+    const int use_fast_bins = (use_bsel && !(flags & DCR_ITER_RADIX_BINS)) ? 1 : 0;
     auto sel_phase = [&](int k, int sub) -> int {
         if ((k == 0 || k == 1) && !remove_outliers) return 0;
         SelView v = view_of(k);
@@ -1683,7 +1732,7 @@ extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, 
 
     if (phase == BP_FRONT) {
         DCR_CUDA_OK(cudaMemsetAsync(d, 0, sizeof(IterDev), s));
-        band_set_engine_kernel<<<1, 32, 0, s>>>(d, use_bsel);
+        band_set_engine_kernel<<<1, 32, 0, s>>>(d, use_bsel | (use_fast_bins << 1));
         dcr_front_args fa = *front;
         if (!remove_outliers) fa.use_max_dz = 0;
         // like the single-GPU iteration: the front kernel emits the aspect-bin codes (so the aspect raster is optional)
@@ -1718,11 +1767,46 @@ extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, 
     } else if (phase >= BP_SEL4 && phase < BP_PREPARE) {
         rc = sel_phase(4, phase - BP_SEL4);
     } else if (phase == BP_PREPARE) {
-        DCR_CUDA_OK(cudaMemsetAsync(w.nw.ghist, 0, (size_t)2 * NB * 2048 * sizeof(unsigned), s));
         band_mom_reduce_kernel<<<1, 256, 0, s>>>(w.nw.part, (int)((nch + MU_KCH - 1) / MU_KCH), d);   // partials of the mask update
         want(d->mom3, 4, 2);
+    } else if (phase >= BP_BIN0 && use_fast_bins) {
+        // fast bins across ranks (the same engine switch as the selections: DCR_ITER_RADIX_ONLY takes the radix bins)
+        NuthDev* nd = &d->nuth;
+        unsigned* gh = w.nw.ghist;
+        const int nsm = dcr_num_sms();
+        if (phase == BP_BIN0) {
+            band_moments_final_kernel<<<1, 256, 0, s>>>(d, 1);   // trim of y always on (dem_align.py:147)
+            DcrCtx* ctx = dcr_ctx();
+            if (!ctx) return -1;
+            const size_t smemA = (size_t)NB * FB_COARSE * sizeof(unsigned);
+            if (!(ctx->attrs & DCR_ATTR_FBA)) {   // per device
+                DCR_CUDA_OK(cudaFuncSetAttribute(fb_passA_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+                ctx->attrs |= DCR_ATTR_FBA;
+            }
+            DCR_CUDA_OK(cudaMemsetAsync(gh, 0, (size_t)FB_BAND_WORDS * sizeof(unsigned), s));
+            fb_passA_kernel<<<nsm * 2, 512, smemA, s>>>(w.nw.y, w.nw.bin, n, nd, gh);
+            want(gh + FB_HA_OFF, NB * FB_COARSE, 0);
+        } else if (phase == BP_BIN1) {
+            fb_findA_kernel<<<(NB + 127) / 128, 128, 0, s>>>(nd, gh);     // global counts + coarse cells, same on every rank
+            fb_passB_kernel<<<nsm * 16, 256, 0, s>>>(w.nw.y, w.nw.bin, n, nd, gh, w.nw.cand, w.nw.cand_cap);
+            fb_band_flag_kernel<<<1, 32, 0, s>>>(nd, w.nw.cand_cap, gh + FB_FLAG_OFF);
+            want(gh, FB_HB_WORDS, 0);
+            want(gh + FB_FLAG_OFF, 1, 0);
+        } else if (phase == BP_BIN2) {
+            fb_findB_kernel<<<(NB + 7) / 8, 256, 0, s>>>(nd, gh, w.nw.cand_cap, gh + FB_FLAG_OFF);
+            fb_passC_kernel<<<nsm * 8, 256, 0, s>>>(nd, w.nw.cand, gh + FB_LSLOT_OFF, gh + FB_LSLOTN_OFF);
+            fb_band_counts_kernel<<<(NB * 2 + 255) / 256, 256, 0, s>>>(gh + FB_LSLOTN_OFF, gh + FB_RCNT_OFF, rank);
+            want(gh + FB_RCNT_OFF, (int64_t)nranks * NB * 2, 0);
+        } else if (phase == BP_BIN3) {
+            fb_band_scatter_kernel<<<(NB * 2 + 7) / 8, 256, 0, s>>>(gh + FB_LSLOT_OFF, gh + FB_RCNT_OFF, rank, nranks,
+                                                                    gh + FB_SLOT_OFF, gh + FB_SLOTN_OFF, nd);
+            want(gh + FB_SLOT_OFF, (int64_t)NB * 2 * FB_SLOT, 0);
+        } else {
+            fb_passD_kernel<<<(NB + 7) / 8, 256, 0, s>>>(nd, gh);
+        }
     } else if (phase == BP_BIN0) {
         band_moments_final_kernel<<<1, 256, 0, s>>>(d, 1);   // trim of y always on (dem_align.py:147)
+        DCR_CUDA_OK(cudaMemsetAsync(w.nw.ghist, 0, (size_t)2 * NB * 2048 * sizeof(unsigned), s));
         bin_hist_kernel<0><<<grid, 256, 0, s>>>(w.nw.y, w.nw.bin, n, &d->nuth, w.nw.ghist);
         want(w.nw.ghist, (int64_t)2 * NB * 2048, 0);
         want(d->nuth.bin_count, NB, 1);
@@ -1734,7 +1818,7 @@ extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, 
         bin_find_kernel<1><<<NB, 256, 0, s>>>(&d->nuth, w.nw.ghist);
         bin_hist_kernel<2><<<grid, 256, 0, s>>>(w.nw.y, w.nw.bin, n, &d->nuth, w.nw.ghist);
         want(w.nw.ghist, (int64_t)2 * NB * 2048, 0);
-    } else if (phase == BP_FINAL) {
+    } else if (phase == BP_BIN3) {
         bin_find_kernel<2><<<NB, 256, 0, s>>>(&d->nuth, w.nw.ghist);
         nuth_count_final_kernel<<<1, 32, 0, s>>>(&d->nuth);
     }
@@ -1760,12 +1844,20 @@ extern "C" int dcr_band_result(const dcr_front_args* front, void* workspace, siz
     DCR_CUDA_OK(cudaMemcpyAsync(hd, w.d, sizeof(IterDev), cudaMemcpyDeviceToHost, s));
     DCR_CUDA_OK(cudaStreamSynchronize(s));
     memset(out, 0, sizeof(*out));
-    const int engine = hd->selpad ? 1 : 0;
-    if (engine) {
-        // a one-pass selection declined (bracket missed / heavy ties / overflow; the decision was taken on all-reduced data,
-        // so every rank sees it): the caller reruns the iteration with DCR_ITER_RADIX_ONLY
-        for (int k = 0; k < 5; ++k)
-            if (hd->bsel[k].fallback) { out->status = DCR_STATUS_RERUN_RADIX; out->select_engine = 0; return 0; }
+    const int engine = (hd->selpad & 1) ? 1 : 0, fast_bins = (hd->selpad & 2) ? 1 : 0;
+    {
+        // a one-pass selection (bracket missed / heavy ties / overflow) or the fast bins (heavy ties / degenerate 3-sigma
+        // range) declined -- on all-reduced data, so on every rank alike: the caller reruns the iteration with
+        // DCR_ITER_RADIX_ONLY resp. DCR_ITER_RADIX_BINS; select_engine / bin_engine say which one it was
+        bool sfb = false;
+        for (int k = 0; engine && k < 5; ++k) sfb = sfb || (hd->bsel[k].fallback != 0);
+        const bool bfb = fast_bins && hd->nuth.fast_fallback != 0;
+        if (sfb || bfb) {
+            out->status = DCR_STATUS_RERUN_RADIX;
+            out->select_engine = sfb ? 0 : engine;
+            out->bin_engine = bfb ? 0 : fast_bins;
+            return 0;
+        }
     }
-    return iter_finalize(hd, engine, out);
+    return iter_finalize(hd, engine, out, fast_bins);
 }

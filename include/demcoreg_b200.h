@@ -256,6 +256,8 @@ typedef struct dcr_iter_result {
                                     * iteration want the tangent: y = dh / tan(slope), coreglib.py:224-225; the slope median,
                                     * coreglib.py:215, is taken on the tangent and converted).  Masks are still decided on the
                                     * float32 slope in degrees.  Used by dcr_align_nuth, whose slope raster is scratch. */
+#define DCR_ITER_RADIX_BINS 64     /* row-band mode: radix bin statistics (the fast bins declined for this raster), one-pass
+                                      selections kept */
 size_t dcr_iteration_workspace_bytes(int64_t n);
 int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_iter_result* out /* host */,
                        void* workspace, size_t workspace_bytes, void* stream);
@@ -361,8 +363,10 @@ int dcr_mask_threshold(const float* x, int64_t n, float thresh, int greater, uin
  * all ranks (ncclAllReduce / torch.distributed.all_reduce on `stream`) and calls the next phase.  Halo rows of the
  * rasters are exchanged by the caller (ncclSend/Recv).  After the last phase dcr_band_result() returns the same
  * dcr_iter_result on every rank.  Workspace: dcr_iteration_workspace_bytes(rows_in_band * w). */
-#define DCR_STATUS_RERUN_RADIX 100   /* dcr_iter_result.status of dcr_band_result: a one-pass selection declined on every rank
-                                      * alike; run the iteration again with DCR_ITER_RADIX_ONLY (dcr_band_iteration does) */
+#define DCR_STATUS_RERUN_RADIX 100   /* dcr_iter_result.status of dcr_band_result: a one-pass selection (select_engine = 0) or the
+                                      * fast bins (bin_engine = 0) declined, on every rank alike; run the iteration again with
+                                      * DCR_ITER_RADIX_ONLY resp. DCR_ITER_RADIX_BINS (dcr_band_iteration does, and reports the
+                                      * engines that finally ran so that the caller can keep the flag for the next iterations) */
 int dcr_band_nphases(void);
 int dcr_band_phase(const dcr_front_args* front, int flags, int rank, int nranks, int phase, void* workspace,
                    size_t workspace_bytes, void** reduce_ptr, int64_t* reduce_count, int* reduce_kind, int* nreduce,
