@@ -1671,7 +1671,7 @@ static int band_carve(void* workspace, size_t workspace_bytes, long long n, int 
 extern "C" int dcr_band_nphases(void) { return BP_COUNT; }
 
 // Runs phase `phase` of the iteration on this rank's band (front->row_begin/row_end).  On return reduce_ptr[k] /
-// reduce_count[k] / reduce_kind[k] (k < *nreduce <= 2) describe device buffers inside `workspace` that must be
+// reduce_count[k] / reduce_kind[k] (k < *nreduce <= 4) describe device buffers inside `workspace` that must be
 // summed over all ranks before the next phase: kind 0 = int32 (histograms), 1 = int64 (counters), 2 = float64.
 extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, int nranks, int phase, void* workspace,
                               size_t workspace_bytes, void** reduce_ptr, int64_t* reduce_count, int* reduce_kind,
@@ -1711,9 +1711,12 @@ extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, 
     auto sel_phase = [&](int k, int sub) -> int {
         if ((k == 0 || k == 1) && !remove_outliers) return 0;
         SelView v = view_of(k);
-        if (use_bsel)
-            return dcr_bsel_band_phase(v, 50.0, &d->bsel[k], w.bsel_scratch, k == 3 ? w.dense_cap : n, rank, nranks, sub, s,
+        if (use_bsel) {
+            // (selections that run in lockstep -- 0 with 4, 2 with 3 -- need scratch of their own)
+            void* scr = (k == 4) ? w.bsel_scratch2 : (k == 3) ? w.bsel_scratch3 : w.bsel_scratch;
+            return dcr_bsel_band_phase(v, 50.0, &d->bsel[k], scr, k == 3 ? w.dense_cap : n, rank, nranks, sub, s,
                                        &d->selres[k], reduce_ptr, reduce_count, reduce_kind, nreduce);
+        }
         // radix: sub 0: H0 | 1: F0+H1 | 2: F1+H2 | 3: F2 + publish | 4: -
         if (sub > 3) return 0;
         int r2 = 0;
@@ -1740,7 +1743,10 @@ extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, 
         if ((rc = dcr_front_launch(&fa, d->counters, s, w.nw.bin, 0, w.tile_list, w.tile_cap))) return rc;
         want(d->counters, 4, 1);
     } else if (phase >= BP_SEL0 && phase < BP_SEL1) {
+        // one-pass engine: the slope median (independent of the MAD chain) advances in lockstep with the first dh median --
+        // the same sub-phases, their all-reduces issued together (5 collective latencies less per iteration)
         rc = sel_phase(0, phase - BP_SEL0);
+        if (!rc && use_bsel) rc = sel_phase(4, phase - BP_SEL0);
     } else if (phase >= BP_SEL1 && phase < BP_MASK) {
         rc = sel_phase(1, phase - BP_SEL1);
     } else if (phase == BP_MASK) {
@@ -1761,11 +1767,12 @@ extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, 
                                        w.dense_cap, s, &d->band_base, MU_KCH)))
             return rc;
     } else if (phase >= BP_SEL2 && phase < BP_SEL3) {
-        rc = sel_phase(2, phase - BP_SEL2);
+        rc = sel_phase(2, phase - BP_SEL2);                          // med_dh over the final mask ...
+        if (!rc && use_bsel) rc = sel_phase(3, phase - BP_SEL2);     // ... in lockstep with the subsample median
     } else if (phase >= BP_SEL3 && phase < BP_SEL4) {
-        rc = sel_phase(3, phase - BP_SEL3);
+        if (!use_bsel) rc = sel_phase(3, phase - BP_SEL3);
     } else if (phase >= BP_SEL4 && phase < BP_PREPARE) {
-        rc = sel_phase(4, phase - BP_SEL4);
+        if (!use_bsel) rc = sel_phase(4, phase - BP_SEL4);
     } else if (phase == BP_PREPARE) {
         band_mom_reduce_kernel<<<1, 256, 0, s>>>(w.nw.part, (int)((nch + MU_KCH - 1) / MU_KCH), d);   // partials of the mask update
         want(d->mom3, 4, 2);

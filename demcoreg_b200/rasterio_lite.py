@@ -28,8 +28,9 @@ def _read_tiff(fn):
         off = struct.unpack_from("<I", buf, 4)[0]
         n = struct.unpack_from("<H", buf, off)[0]
         esz, base = 12, off + 2
-    tsz = {1: 1, 2: 1, 3: 2, 4: 4, 5: 8, 11: 4, 12: 8, 16: 8}
-    tfmt = {1: "B", 2: "c", 3: "H", 4: "I", 11: "f", 12: "d", 16: "Q"}
+    tsz = {1: 1, 2: 1, 3: 2, 4: 4, 5: 8, 6: 1, 7: 1, 8: 2, 9: 4, 10: 8, 11: 4, 12: 8, 13: 4, 16: 8, 17: 8, 18: 8}
+    tfmt = {1: "B", 2: "c", 3: "H", 4: "I", 6: "b", 7: "B", 8: "h", 9: "i", 11: "f", 12: "d", 13: "I", 16: "Q", 17: "q",
+            18: "Q"}
     tags = {}
     for k in range(n):
         e = base + k * esz
@@ -40,9 +41,10 @@ def _read_tiff(fn):
         if nbytes > (8 if big else 4):
             voff = struct.unpack_from("<Q" if big else "<I", buf, voff)[0]
         if typ == 2:
-            tags[tag] = buf[voff:voff + cnt].split(b"\0")[0].decode()
-        else:
+            tags[tag] = buf[voff:voff + cnt].split(b"\0")[0].decode(errors="replace")
+        elif typ in tfmt:
             tags[tag] = struct.unpack_from("<%d%s" % (cnt, tfmt[typ]), buf, voff)
+        # (RATIONAL / unknown field types -- XResolution and friends -- carry nothing this codec needs: skipped)
     w, h = tags[256][0], tags[257][0]
     if tags.get(259, (1,))[0] != 1:
         raise ValueError("compressed TIFF needs GDAL (not installed); write uncompressed strips")
@@ -57,13 +59,41 @@ def _read_tiff(fn):
         sx, sy = tags[33550][0], tags[33550][1]
         tp = tags[33922]
         gt = (tp[3] - tp[0] * sx, sx, 0.0, tp[4] + tp[1] * sy, 0.0, -sy)
+        gk = tags.get(34735, ())
+        for q in range(4, len(gk) - 3, 4):
+            if gk[q] == 1025 and gk[q + 1] == 0 and gk[q + 3] == 2:   # GTRasterTypeGeoKey = RasterPixelIsPoint:
+                gt = (gt[0] - 0.5 * sx, sx, 0.0, gt[3] + 0.5 * sy, 0.0, -sy)   # the tiepoint is a pixel CENTRE
     ndv = None
     if 42113 in tags:
         try:
             ndv = float(tags[42113])
         except ValueError:
             ndv = None
-    return dict(array=a, gt=gt, ndv=ndv, proj=tags.get(34737, ""))
+    return dict(array=a, gt=gt, ndv=ndv, proj=_pack_geokeys(tags))
+
+
+_GK = "GEOKEYS:"
+
+
+def _pack_geokeys(tags):
+    """The CRS of a GeoTIFF as this codec carries it: the three GeoKey tags verbatim (34735 directory, 34736 doubles, 34737
+    ASCII), packed into the ``proj`` string so that every product written from this raster gets them back."""
+    import json
+    if 34735 not in tags:
+        return ""
+    return _GK + json.dumps({"34735": list(tags[34735]), "34736": list(tags.get(34736, ())), "34737": tags.get(34737, "")})
+
+
+def _unpack_geokeys(proj):
+    import json
+    if not proj or not proj.startswith(_GK):
+        return None
+    d = json.loads(proj[len(_GK):])
+    gk = list(d["34735"])
+    for q in range(4, len(gk) - 3, 4):      # products are written PixelIsArea (the geotransform is corner-based)
+        if gk[q] == 1025 and gk[q + 1] == 0:
+            gk[q + 3] = 1
+    return gk, list(d["34736"]), d["34737"]
 
 
 def _write_tiff(fn, a, gt, ndv, proj=""):
@@ -79,7 +109,8 @@ def _write_tiff(fn, a, gt, ndv, proj=""):
     entries = []
     extra = b""
     hdr = 16
-    n_entries = 12 + (1 if nd else 0)
+    geo = _unpack_geokeys(proj)
+    n_entries = 12 + (1 if nd else 0) + ((1 + (1 if geo[1] else 0) + (1 if geo[2] else 0)) if geo else 0)
     ifd_size = 8 + n_entries * 20 + 8
     extra_off = hdr + ifd_size
     data_off = None
@@ -104,6 +135,13 @@ def _write_tiff(fn, a, gt, ndv, proj=""):
     add(339, 3, 1, struct.pack("<H", fmt))
     add(33550, 12, 3, scale)
     add(33922, 12, 6, tie)
+    if geo:
+        add(34735, 3, len(geo[0]), struct.pack("<%dH" % len(geo[0]), *geo[0]))
+        if geo[1]:
+            add(34736, 12, len(geo[1]), struct.pack("<%dd" % len(geo[1]), *geo[1]))
+        if geo[2]:
+            asc = (geo[2] + "\0").encode()
+            add(34737, 2, len(asc), asc)
     if nd:
         add(42113, 2, len(nd), nd)
     n_entries = len(entries)
