@@ -32,12 +32,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALG_BYTES_ITER = 90.0      # algorithmic bytes per pixel per iteration
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of front_kernel on the default 8192^2 workload, from the
-# `ncu --set full` capture summarised in profiles/front_kernel_r1_final_raw.csv
-FRONT_KERNEL_DRAM_BYTES_8192 = 1559338240   # 604.63 MB read + 954.70 MB written
+# dram__bytes_read.sum + dram__bytes_write.sum of the front end (front_fast_kernel + front_kernel over the listed tiles) on
+# the default 8192^2 workload, from the `ncu --set full` capture summarised in profiles/r2/front_r2_raw.csv:
+# 591.41 + 43.73 MB read, 653.27 + 7.87 MB written
+FRONT_KERNEL_DRAM_BYTES_8192 = 1296272640
 # algorithmic bytes per pixel of each profiled stage
 STAGE_INFO = [
-    ("front_kernel (TMA-staged warp + dh + masks + Horn + aspect-bin codes)", 9.0 + 15.0),
+    # R ref 4 + src 4 + mask 1, W dh 4 + slope 4 + aspect 4 = 21 B/px (the kernels really write dh 4 + tan(slope) 4
+    # + mask bits 1 + bin code 2 = 11 B/px: the aspect raster is replaced by its 1-degree bin code)
+    ("front end: front_fast_kernel (interior tiles) + front_kernel (listed tiles): TMA-staged warp + dh + masks + Horn + bin codes",
+     21.0),
     ("bsel_* x2 on the main stream: median + MAD of dh (slope median on a side stream)", 10.0),
     ("mask_update_kernel (MAD filter + y + moments of y, fused)", 9.0 + 4.0),
     ("(side streams only: scan/compress/dz median, med_dh)", 0.0),
@@ -45,9 +49,9 @@ STAGE_INFO = [
     ("fb_pass* (bin count + exact bin medians; shares bandwidth with the side streams)", 12.0),
     ("result copy", 0.0),
 ]
-# front 1 + 5 selections x (sample, main, 2 refine) 20 + mask update 1 + scan/stride/compress 3 + moments 2 + bins 6 = 33
-# (+ one z-shift fold every 4th step)
-KERNELS_PER_STEP = 1 + 5 * 4 + 1 + 3 + 2 + 6
+# front 2 (fast + listed tiles) + 5 selections x (sample, main, 2 refine) 20 + mask update 1 + scan/stride/compress 3 +
+# moments 2 + bins 6 = 34 (+ one z-shift fold every 4th step)
+KERNELS_PER_STEP = 2 + 5 * 4 + 1 + 3 + 2 + 6
 
 
 def peaks():
