@@ -709,8 +709,13 @@ def main():
                                                                   "note": "dem_align.align to convergence (tol 0.02 m), device-resident pair, incl. the src copy"}},
             "clocks": clocks, "gpu_launches": KERNELS_PER_STEP * args.steps,
             "e2e": {"value": e2e_val, "unit": "Gpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    # the ceiling the upload path allows: measured H2D rate per GPU with all ranks copying at once
+                    "h2d_gbs_per_gpu_all_ranks_copying": (batch_obj or {}).get("h2d_gbs_per_gpu_measured_all_ranks_copying"),
+                    "upload_bound_value": (world * (batch_obj["h2d_gbs_per_gpu_measured_all_ranks_copying"] * 1e9 / h2d) * npx / 1e9
+                                           if batch_obj else None),
                     "note": "engine.nuth_iteration on host-resident pinned rasters through batch.stream_pairs: uploads double-"
-                            "buffered on a copy stream (step k+1's H2D overlaps step k's kernels); PCIe-bound"},
+                            "buffered on a copy stream (step k+1's H2D overlaps step k's kernels); bound by the host->device "
+                            "copies (PCIe at N=1, the host side of the box when all ranks copy at once)"},
             "roofline": roofline, "roofline_iteration": roofline_iter, "cpu_baseline": cpu,
             "config3": config3_obj, "batch": batch_obj, "band": band_obj}
     print(json.dumps(line))

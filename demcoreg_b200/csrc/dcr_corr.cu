@@ -87,11 +87,23 @@ __global__ void __launch_bounds__(256) zscore_kernel(const float* __restrict__ x
         const unsigned char* mr = m ? m + (long long)(r0 + i) * mstride + c0 : nullptr;
         const float* nr = noise ? noise + (long long)i * w : nullptr;
         float* zr = z + (long long)i * w;
-        for (int j = lane; j < w; j += 32) {
-            float o;
-            if (mr && mr[j]) o = nr ? nr[j] : 0.0f;
-            else o = (float)(((double)xr[j] - mean) / sd);
-            zr[j] = o;
+        // 4 independent column groups per trip: all their loads are in flight before the first divide
+        for (int j0 = lane; j0 < w; j0 += 128) {
+            float xv[4], nv[4];
+            unsigned char mk[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + 32 * u;
+                const bool in = j < w;
+                xv[u] = in ? xr[j] : 0.0f;
+                mk[u] = (in && mr) ? mr[j] : (unsigned char)0;
+                nv[u] = (in && nr) ? nr[j] : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + 32 * u;
+                if (j < w) zr[j] = mk[u] ? nv[u] : (float)(((double)xv[u] - mean) / sd);
+            }
         }
     }
 }
