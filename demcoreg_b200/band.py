@@ -202,9 +202,9 @@ class BandAligner(object):
         """Run one phase; returns the tensors (views into the workspace) that must be sum-all-reduced."""
         torch = self.torch
         L = _lib.lib()
-        ptrs = (C.c_void_p * 4)()
-        counts = (C.c_int64 * 4)()
-        kinds = (C.c_int * 4)()
+        ptrs = (C.c_void_p * 8)()
+        counts = (C.c_int64 * 8)()
+        kinds = (C.c_int * 8)()
         nred = C.c_int(0)
         _lib.check(L.dcr_band_phase(C.byref(self.args), self.flags, self.rank, self.world, phase,
                                     C.c_void_p(self.ws.data_ptr()), self.ws.numel(), ptrs, counts, kinds, C.byref(nred),

@@ -138,9 +138,9 @@ extern "C" int dcr_band_iteration(const dcr_front_args* front, int flags, dcr_co
     int f = flags;
     for (int attempt = 0; attempt < 3; ++attempt) {
         for (int ph = 0; ph < nph; ++ph) {
-            void* ptrs[4];
-            int64_t counts[4];
-            int kinds[4], nred = 0;
+            void* ptrs[8];
+            int64_t counts[8];
+            int kinds[8], nred = 0;
             int rc = dcr_band_phase(front, f, h->rank, h->nranks, ph, workspace, workspace_bytes, ptrs, counts, kinds, &nred, stream);
             if (rc) return rc;
             if (h->nranks > 1 && nred > 0) {

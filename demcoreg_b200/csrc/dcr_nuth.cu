@@ -1670,15 +1670,10 @@ static int band_carve(void* workspace, size_t workspace_bytes, long long n, int 
 
 extern "C" int dcr_band_nphases(void) { return BP_COUNT; }
 
-// Runs phase `phase` of the iteration on this rank's band (front->row_begin/row_end).  On return reduce_ptr[k] /
-// reduce_count[k] / reduce_kind[k] (k < *nreduce <= 4) describe device buffers inside `workspace` that must be
-// summed over all ranks before the next phase: kind 0 = int32 (histograms), 1 = int64 (counters), 2 = float64.
-extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, int nranks, int phase, void* workspace,
-                              size_t workspace_bytes, void** reduce_ptr, int64_t* reduce_count, int* reduce_kind,
-                              int* nreduce, void* stream) {
-    DCR_ARG(front && workspace && reduce_ptr && reduce_count && reduce_kind && nreduce, "null pointer");
-    DCR_ARG(nranks >= 1 && nranks <= 8 && rank >= 0 && rank < nranks, "1 <= nranks <= 8");
-    DCR_ARG(phase >= 0 && phase < BP_COUNT, "bad phase");
+// One elementary phase (BP_*); appends what must be summed over the ranks to reduce_ptr / reduce_count / reduce_kind.
+static int band_phase_one(const dcr_front_args* front, int flags, int rank, int nranks, int phase, void* workspace,
+                          size_t workspace_bytes, void** reduce_ptr, int64_t* reduce_count, int* reduce_kind,
+                          int* nreduce, void* stream) {
     const int remove_outliers = (flags & DCR_ITER_REMOVE_OUTLIERS) ? 1 : 0;
     const int rb = front->row_end > 0 ? front->row_begin : 0, re = front->row_end > 0 ? front->row_end : front->h;
     const long long n = (long long)(re - rb) * front->w;
@@ -1690,7 +1685,6 @@ extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, 
     if (band_carve(workspace, workspace_bytes, n, grid, &w)) return -1;
     IterDev* d = w.d;
     const long long nch = (n + MU_CHUNK - 1) / MU_CHUNK;
-    *nreduce = 0;
     auto want = [&](void* p, int64_t cnt, int kind) { reduce_ptr[*nreduce] = p; reduce_count[*nreduce] = cnt; reduce_kind[*nreduce] = kind; ++*nreduce; };
     int rc = 0;
 
@@ -1831,6 +1825,41 @@ extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, 
     }
     if (rc) return rc;
     DCR_LAUNCH_OK("band phase kernels");
+    return 0;
+}
+
+// Runs phase `phase` of the iteration on this rank's band (front->row_begin/row_end).  On return reduce_ptr[k] /
+// reduce_count[k] / reduce_kind[k] (k < *nreduce <= 8) describe device buffers inside `workspace` that must be
+// summed over all ranks before the next phase: kind 0 = int32 (histograms), 1 = int64 (counters), 2 = float64.
+//
+// With the one-pass selections (no DCR_ITER_RADIX_ONLY) the elementary phases that do not depend on each other share a
+// phase boundary, so that their collectives are issued together -- 16 boundaries instead of 34: the front end with the
+// sample of the first selections; the moment sums with the mask update; the compress step, the selections over the final
+// mask and the bin statistics in lockstep.  The remaining phase numbers are empty then.
+extern "C" int dcr_band_phase(const dcr_front_args* front, int flags, int rank, int nranks, int phase, void* workspace,
+                              size_t workspace_bytes, void** reduce_ptr, int64_t* reduce_count, int* reduce_kind,
+                              int* nreduce, void* stream) {
+    DCR_ARG(front && workspace && reduce_ptr && reduce_count && reduce_kind && nreduce, "null pointer");
+    DCR_ARG(nranks >= 1 && nranks <= 8 && rank >= 0 && rank < nranks, "1 <= nranks <= 8");
+    DCR_ARG(phase >= 0 && phase < BP_COUNT, "bad phase");
+    *nreduce = 0;
+    if (flags & DCR_ITER_RADIX_ONLY)
+        return band_phase_one(front, flags, rank, nranks, phase, workspace, workspace_bytes, reduce_ptr, reduce_count,
+                              reduce_kind, nreduce, stream);
+    static const signed char plan[16][3] = {
+        {BP_FRONT, BP_SEL0 + 0, -1},
+        {BP_SEL0 + 1, -1, -1}, {BP_SEL0 + 2, -1, -1}, {BP_SEL0 + 3, -1, -1}, {BP_SEL0 + 4, -1, -1},
+        {BP_SEL1 + 0, -1, -1}, {BP_SEL1 + 1, -1, -1}, {BP_SEL1 + 2, -1, -1}, {BP_SEL1 + 3, -1, -1}, {BP_SEL1 + 4, -1, -1},
+        {BP_MASK, BP_PREPARE, -1},
+        {BP_COMPRESS, BP_SEL2 + 0, BP_BIN0},
+        {BP_SEL2 + 1, BP_BIN1, -1}, {BP_SEL2 + 2, BP_BIN2, -1}, {BP_SEL2 + 3, BP_BIN3, -1}, {BP_SEL2 + 4, BP_BIN4, -1}};
+    if (phase >= 16) return 0;
+    for (int q = 0; q < 3; ++q) {
+        if (plan[phase][q] < 0) break;
+        const int rc = band_phase_one(front, flags, rank, nranks, plan[phase][q], workspace, workspace_bytes, reduce_ptr,
+                                      reduce_count, reduce_kind, nreduce, stream);
+        if (rc) return rc;
+    }
     return 0;
 }
 

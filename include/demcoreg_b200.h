@@ -359,7 +359,7 @@ int dcr_mask_threshold(const float* x, int64_t n, float thresh, int greater, uin
  * (BASELINE.json configs[4]; the reference does not tile -- it loads whole arrays, dem_align.py:79-80.)
  * The iteration of dcr_nuth_iteration is cut into dcr_band_nphases() phases.  Each rank calls dcr_band_phase for
  * its band (front->row_begin/row_end, rasters held as band + halo, see dcr_front_args), then all-reduces (sum)
- * the (up to 4) device buffers the phase declares -- kind 0 = int32 histograms, 1 = int64 counters, 2 = float64 sums -- over
+ * the (up to 8) device buffers the phase declares -- kind 0 = int32 histograms, 1 = int64 counters, 2 = float64 sums -- over
  * all ranks (ncclAllReduce / torch.distributed.all_reduce on `stream`) and calls the next phase.  Halo rows of the
  * rasters are exchanged by the caller (ncclSend/Recv).  After the last phase dcr_band_result() returns the same
  * dcr_iter_result on every rank.  Workspace: dcr_iteration_workspace_bytes(rows_in_band * w). */
