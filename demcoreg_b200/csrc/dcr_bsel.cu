@@ -49,6 +49,11 @@ __device__ __forceinline__ bool bsel_key(const SelView& v, float center, float x
     return true;
 }
 
+// (defined with the row-band code below: the gather half and the localisation half of the sampling step as two kernels)
+__global__ void bsel_band_sample_kernel(const SelView v, BselState* st, float* publish, unsigned* __restrict__ keys, int rank,
+                                        int nranks);
+__global__ void bsel_band_bracket_kernel(const unsigned* __restrict__ keys, double q_percent, BselState* st);
+
 __global__ void __launch_bounds__(1024) bsel_sample_kernel(const SelView v, double q_percent, BselState* st, float* publish) {
     __shared__ unsigned s[BS_S];
     __shared__ unsigned s_valid;
@@ -328,6 +333,15 @@ int dcr_bsel_sample_enqueue(const SelView& v, double q_percent, BselState* st, v
     unsigned *hist, *cand, cap;
     dcr_bsel_buffers(scratch, n_max, &hist, &cand, &cap);
     DCR_CUDA_OK(cudaMemsetAsync(hist, 0, 4096 * sizeof(unsigned), s));
+    if (n_max > BS_S) {
+        // gather spread over 8 CTAs (one scattered load per thread) + the localisation kernel: 4 + 11 us instead of 23 us for
+        // the fused single-CTA kernel, which stays for views that may fit the sample buffer whole (exact by sorting)
+        unsigned* keys = cand + (65536 - BS_S);     // (cap >= 65536; candidates are appended from the front, later)
+        bsel_band_sample_kernel<<<BS_S / 1024, 1024, 0, s>>>(v, st, publish, keys, 0, 1);
+        bsel_band_bracket_kernel<<<1, 1024, 0, s>>>(keys, q_percent, st);
+        DCR_LAUNCH_OK("bsel sample kernels");
+        return 0;
+    }
     bsel_sample_kernel<<<1, 1024, 0, s>>>(v, q_percent, st, publish);
     DCR_LAUNCH_OK("bsel_sample_kernel");
     return 0;
@@ -391,12 +405,14 @@ __global__ void __launch_bounds__(1024) bsel_band_sample_kernel(const SelView v,
     const float center = v.center_ptr ? *v.center_ptr : v.center_imm;
     const int k0 = (int)(((long long)BS_S * rank) / nranks), k1 = (int)(((long long)BS_S * (rank + 1)) / nranks);
     const int ns = k1 - k0;   // this rank's strata
-    if (threadIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->fallback = 0; st->done = 0; st->empty = 0;
         st->below = 0; st->total = 0; st->ncand = 0; st->nsmall = 0; st->ticket = 0;
         st->publish = publish;
     }
-    for (int j = threadIdx.x; j < ns; j += 1024) {
+    // one gather per thread, spread over several CTAs: the positions are scattered over the whole array (TLB + DRAM latency
+    // ~2 us each), and a single CTA walking its strata eight deep took 23 us
+    for (int j = blockIdx.x * 1024 + threadIdx.x; j < ns; j += gridDim.x * 1024) {
         unsigned key = 0xFFFFFFFFu;
         if (n > 0) {
             // hashed position inside stratum j of this rank's elements (a plain stride aliases with the raster width)
@@ -519,7 +535,7 @@ int dcr_bsel_band_phase(const SelView& v, double q_percent, BselState* st, void*
     if (sub == 0) {
         DCR_CUDA_OK(cudaMemsetAsync(keys, 0, BS_S * sizeof(unsigned), s));
         DCR_CUDA_OK(cudaMemsetAsync(hist, 0, 4096 * sizeof(unsigned), s));
-        bsel_band_sample_kernel<<<1, 1024, 0, s>>>(v, st, publish, keys, rank, nranks);
+        bsel_band_sample_kernel<<<BS_S / 1024, 1024, 0, s>>>(v, st, publish, keys, rank, nranks);
         want(keys, BS_S, 0);
     } else if (sub == 1) {
         bsel_band_bracket_kernel<<<1, 1024, 0, s>>>(keys, q_percent, st);
