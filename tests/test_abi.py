@@ -159,3 +159,42 @@ def test_reference_import_name_resolves():
     for name in ('compute_offset_nuth', 'compute_offset_ncc', 'compute_offset_sad', 'apply_xy_shift', 'apply_z_shift',
                  'nuth_func', 'find_subpixel_peak_position'):
         assert callable(getattr(coreglib, name))
+
+
+def test_flag_constants_match_the_header():
+    """The Python mirror of the C-ABI's #define constants (iteration flags, mask bits, statuses) equals include/*.h."""
+    import re
+    from demcoreg_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "demcoreg_b200.h")).read()
+    defs = {m.group(1): int(m.group(2).rstrip("u"), 0) for m in re.finditer(r"#define\s+(DCR_\w+)\s+(0x[0-9a-fA-F]+u?|\d+u?)\b", hdr)}
+    pairs = {"DCR_ITER_REMOVE_OUTLIERS": _lib.ITER_REMOVE_OUTLIERS, "DCR_ITER_PROFILE": _lib.ITER_PROFILE,
+             "DCR_ITER_RADIX_ONLY": _lib.ITER_RADIX_ONLY, "DCR_ITER_APPLY_Z": _lib.ITER_APPLY_Z,
+             "DCR_ITER_TAN_SLOPE": _lib.ITER_TAN_SLOPE, "DCR_ITER_RADIX_BINS": _lib.ITER_RADIX_BINS,
+             "DCR_STATUS_RERUN_RADIX": _lib.STATUS_RERUN_RADIX, "DCR_M_BASE": _lib.M_BASE, "DCR_M_SLOPE": _lib.M_SLOPE}
+    for name, val in pairs.items():
+        assert defs[name] == val, (name, defs[name], val)
+    flags = [defs[k] for k in defs if k.startswith("DCR_ITER_")]
+    assert len(set(flags)) == len(flags) and all(f & (f - 1) == 0 for f in flags), "iteration flags must be distinct bits"
+
+
+def test_host_helpers_of_the_cli():
+    """Pure host logic next to the kernels: dates in file names (compute_diff -rate), memwarp_multi's target resolution,
+    band row split, phase count of the row-band iteration."""
+    import datetime
+    from demcoreg_b200 import band, compute_diff, engine
+    from demcoreg_b200._lib import lib
+    f = compute_diff.fn_getdatetime
+    assert f("/x/20150203_1234_1020_abc-DEM_8m.tif") == datetime.datetime(2015, 2, 3, 12, 34)
+    assert f("WV01_20190712_102001008A_x.tif") == datetime.datetime(2019, 7, 12)
+    assert f("SETSM_WV02_20121301_bad_20120131T101112.tif") == datetime.datetime(2012, 1, 31, 10, 11, 12)
+    assert f("nodate_1234567.tif") is None
+
+    class R(object):
+        def __init__(self, res):
+            self.gt = (0.0, res, 0.0, 0.0, 0.0, -res)
+    rs = [R(2.0), R(8.0)]
+    assert engine.target_res(rs, 'max') == 8.0 and engine.target_res(rs, 'min') == 2.0
+    assert engine.target_res(rs, 'mean') == 5.0 and engine.target_res(rs, '4') == 4.0 and engine.target_res(rs, 3) == 3.0
+    rows = [band.band_rows(32768, r, 8) for r in range(8)]
+    assert rows[0][0] == 0 and rows[-1][1] == 32768 and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+    assert lib().dcr_band_nphases() == 34
