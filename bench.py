@@ -49,9 +49,9 @@ STAGE_INFO = [
     ("fb_pass* (bin count + exact bin medians; shares bandwidth with the side streams)", 12.0),
     ("result copy", 0.0),
 ]
-# front 2 (fast + listed tiles) + 5 selections x (sample, main, 2 refine) 20 + mask update 1 + scan/stride/compress 3 +
-# moments 2 + bins 6 = 34 (+ one z-shift fold every 4th step)
-KERNELS_PER_STEP = 2 + 5 * 4 + 1 + 3 + 2 + 6
+# front 2 (fast + listed tiles) + 5 selections x (sample gather, bracket, main, 2 refine) 25 + mask update 1 +
+# scan/stride/compress 3 + moments 2 + bins 6 = 39 (+ one z-shift fold every 4th step)
+KERNELS_PER_STEP = 2 + 5 * 5 + 1 + 3 + 2 + 6
 
 
 def peaks():

@@ -15,6 +15,7 @@ M_BASE, M_MAXDZ, M_MAD, M_SLOPE, M_ASPECT = 0x01, 0x02, 0x04, 0x08, 0x10
 M_DIFF = M_BASE | M_MAXDZ | M_MAD | M_SLOPE
 ITER_REMOVE_OUTLIERS, ITER_PROFILE, ITER_RADIX_ONLY, ITER_APPLY_Z, ITER_TAN_SLOPE = 1, 2, 4, 8, 16
 ITER_RADIX_BINS = 64
+ITER_NO_BINS = 128
 STATUS_RERUN_RADIX = 100
 SAD_PER_OFFSET = 1
 

@@ -10,8 +10,9 @@ def compute_offset_corr(ref_dem_ds, src_dem_ds, mode, remove_outliers, max_offse
                         ncc_noise=None, _details=None):
     """Front end identical to the Nuth path (warp, dh, outlier / slope masks, dz = median), then the NCC or SAD
     search on the warped rasters re-masked with the final ``static_mask`` -> ``(dx, dy, dz, static_mask, fig)``."""
+    # (masks, counts and dz only: the aspect-bin statistics and the fit of the Nuth branch are skipped)
     res, grid, bufs = engine.nuth_iteration(ref_dem_ds, src_dem_ds, mask_source, remove_outliers, max_dz, slope_lim,
-                                            keep_warped=True)
+                                            keep_warped=True, no_bins=True)
     if res.status == 1:
         sys.exit("No overlapping, unmasked pixels shared between input DEMs")
     r = float(grid.gt[1])

@@ -1196,7 +1196,7 @@ static int iter_select(const SelView& v, int k, const IterWs& w, long long n, in
 }
 
 static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, int use_bsel, const IterWs& w, int grid,
-                             cudaStream_t s, cudaEvent_t* ev, int fast_bins, int tan_slope) {
+                             cudaStream_t s, cudaEvent_t* ev, int fast_bins, int tan_slope, int no_bins = 0) {
     const long long n = (long long)front->h * front->w;
     const long long nch = (n + MU_CHUNK - 1) / MU_CHUNK;
     IterDev* d = w.d;
@@ -1298,8 +1298,11 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
     STAGE_MARK(4);
     // (dem_align.py:147 calls coreglib.compute_offset_nuth WITHOUT forwarding remove_outliers: the 3-sigma trim of y is
     //  always on -- its default -- whatever dem_align's own flag says)
-    if ((rc = nuth_enqueue_prepared(n, (nch + MU_KCH - 1) / MU_KCH, 1, w.nw, grid, s, ev ? ev[5] : nullptr,
-                                    fast_bins)))
+    if (no_bins) {
+        // DCR_ITER_NO_BINS: the caller only wants the masks, the counts and the medians (-mode ncc / sad, dem_align.py:126-143)
+        if (ev) DCR_CUDA_OK(cudaEventRecord(ev[5], s));
+    } else if ((rc = nuth_enqueue_prepared(n, (nch + MU_KCH - 1) / MU_KCH, 1, w.nw, grid, s, ev ? ev[5] : nullptr,
+                                           fast_bins)))
         return rc;
     if (side) {
         DCR_CUDA_OK(cudaStreamWaitEvent(s, e_join, 0));
@@ -1412,7 +1415,7 @@ extern "C" int dcr_nuth_iteration(const dcr_front_args* front, int flags, dcr_it
     int bin_engine = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
         int rc = iteration_enqueue(front, remove_outliers, engine_used, w, grid, s, prof ? ev : nullptr,
-                                   (flags & DCR_ITER_RADIX_ONLY) ? 0 : 1, tan_slope);
+                                   (flags & DCR_ITER_RADIX_ONLY) ? 0 : 1, tan_slope, (flags & DCR_ITER_NO_BINS) ? 1 : 0);
         if (rc) return rc;
         DCR_CUDA_OK(cudaMemcpyAsync(hd, d, sizeof(IterDev), cudaMemcpyDeviceToHost, s));
         if (prof) DCR_CUDA_OK(cudaEventRecord(ev[7], s));

@@ -98,7 +98,7 @@ def make_front_args(ref, src, mask_source, max_dz, use_max_dz, slope_lim, keep_w
 
 
 def nuth_iteration(ref, src, mask_source=None, remove_outliers=True, max_dz=100, slope_lim=(0.1, 40),
-                   keep_warped=False, bufs=None, profile=False, radix_only=False, apply_z=False, tan_slope=False):
+                   keep_warped=False, bufs=None, profile=False, radix_only=False, apply_z=False, tan_slope=False, no_bins=False):
     """One full Nuth-Kaab iteration on the device (``dcr_nuth_iteration``).
 
     Returns ``(IterResult, Grid, IterBuffers)``; ``IterResult.dx/dy/dz`` is what
@@ -118,7 +118,7 @@ def nuth_iteration(ref, src, mask_source=None, remove_outliers=True, max_dz=100,
     res = _lib.IterResult()
     flags = (_lib.ITER_REMOVE_OUTLIERS if remove_outliers else 0) | (_lib.ITER_PROFILE if profile else 0) \
         | (_lib.ITER_RADIX_ONLY if radix_only else 0) | (_lib.ITER_APPLY_Z if apply_z else 0) \
-        | (_lib.ITER_TAN_SLOPE if tan_slope else 0)
+        | (_lib.ITER_TAN_SLOPE if tan_slope else 0) | (_lib.ITER_NO_BINS if no_bins else 0)
     _lib.check(L.dcr_nuth_iteration(C.byref(a), flags, C.byref(res),
                                     C.c_void_p(ws.data_ptr()), ws.numel(), _stream_ptr(torch)))
     return res, grid, bufs

@@ -256,6 +256,8 @@ typedef struct dcr_iter_result {
                                     * iteration want the tangent: y = dh / tan(slope), coreglib.py:224-225; the slope median,
                                     * coreglib.py:215, is taken on the tangent and converted).  Masks are still decided on the
                                     * float32 slope in degrees.  Used by dcr_align_nuth, whose slope raster is scratch. */
+#define DCR_ITER_NO_BINS 128       /* skip the aspect-bin statistics and the fit (status 4, dx = dy = 0): the masks, counts and
+                                      medians are all the caller wants -- the -mode ncc / sad branch, dem_align.py:126-143 */
 #define DCR_ITER_RADIX_BINS 64     /* row-band mode: radix bin statistics (the fast bins declined for this raster), one-pass
                                       selections kept */
 size_t dcr_iteration_workspace_bytes(int64_t n);
