@@ -137,39 +137,64 @@ def oracle_iteration_seconds(p, crop, shift_gt):
 
 
 def _ref_worker(args):
-    """One worker = one DEM pair processed by one single-threaded process (the reference's execution model)."""
-    size, res, crop, rank, nrep = args
-    p = make_workload(size, res, rank)
-    return [oracle_iteration_seconds(p, crop, (3.4, -1.8)) for _ in range(nrep)]
+    """One worker = one single-threaded process (the reference's execution model) on ONE crop of the bench workload: the
+    size x size pair of rank 0 is cut into g x g crops, worker (ci, cj) takes its crop of both rasters and of the mask."""
+    size, res, gy, gx, ci, cj, nrep = args
+    p = make_workload(size, res, 0)
+    ch, cw = size // gy, size // gx
+    q = dict(p)
+    for k in ('ref', 'src', 'mask'):
+        q[k] = np.ascontiguousarray(p[k][ci * ch:(ci + 1) * ch, cj * cw:(cj + 1) * cw]) if p[k] is not None else None
+    gt = p['gt']
+    q['gt'] = (gt[0] + cj * cw * gt[1], gt[1], 0.0, gt[3] + ci * ch * gt[5], 0.0, gt[5])
+    del p
+    out = []
+    for _ in range(nrep):
+        sec, _px = oracle_iteration_seconds(q, max(ch, cw), (3.4, -1.8))   # (the crop slices of that helper are no-ops here)
+        out.append((sec, ch * cw))
+    return out
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU path.  The reference itself cannot be imported (pygeotools / GDAL are
-    absent), so this times the oracle restatement: one single-threaded process per DEM pair, as many
-    concurrent pairs as host cores (the reference's only parallelism, `parallel -j`, dem_align_parallel.pbs:122)."""
+    absent), so this times the oracle restatement on the SAME workload as the GPU arm: the size x size pair is cut
+    into g x g crops and every crop is one single-threaded process (the reference's only parallelism is one process per
+    raster, `parallel -j`, dem_align_parallel.pbs:122) -- all host cores busy, a step = one iteration over every pixel of
+    the pair."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     cores = min(len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1), 128)
     nrep = args.warmup + args.steps
-    crop = min(args.size, 2048 if nrep <= 16 else 1024)
-    with mp.get_context("spawn").Pool(cores) as pool:
-        out = pool.map(_ref_worker, [(crop, args.res, crop, r, nrep) for r in range(cores)])
+    g = max(1, min(int(np.floor(np.sqrt(cores))), args.size // 1024))
+    while args.size % g:
+        g -= 1
+    gy = gx = g
+    while gy * gx * 2 <= cores and args.size % (gx * 2) == 0 and args.size // (gx * 2) >= 512:
+        gx *= 2                     # more cores than square crops: split the crops' columns once more
+    crop = args.size // gy
+    cropw = args.size // gx
+    nw = gy * gx
+    with mp.get_context("spawn").Pool(nw) as pool:
+        out = pool.map(_ref_worker, [(args.size, args.res, gy, gx, k // gx, k % gx, nrep) for k in range(nw)])
     # per step: all workers run concurrently; the step time is the slowest worker's
-    step_s = [max(out[w][k][0] for w in range(cores)) for k in range(args.warmup, nrep)]
-    px = cores * crop * crop
+    step_s = [max(out[w][k][0] for w in range(nw)) for k in range(args.warmup, nrep)]
+    px = nw * crop * cropw
     val = px * len(step_s) / sum(step_s) / 1e9
     line = {"metric": "nuth_kaab_iteration_throughput", "value": val, "unit": "Gpix/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(step_s) / len(step_s),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
-            "config": {"workload": "dem_align -mode nuth, one iteration per step on %d concurrent synthetic %dx%d pairs at %g m "
-                                   "(bounded sample of the %dx%d workload) with a 30%% stable-surface mask"
-                                   % (cores, crop, crop, args.res, args.size, args.size)},
-            "cpu_baseline": {"value": val, "unit": "Gpix/s", "cores": cores, "kind": "port",
-                             "sample": "%d concurrent single-thread oracle iterations (numpy/scipy restatement of the "
-                                       "reference, plot path off) on %dx%d pairs" % (cores, crop, crop)},
+            "config": {"workload": "dem_align -mode nuth, one iteration per step on a synthetic %dx%d fractal-terrain pair "
+                                   "at %g m with a 30%% stable-surface mask, 1%% nodata (the GPU arm's pair), processed as "
+                                   "%d crops of %dx%d by %d concurrent single-thread processes"
+                                   % (args.size, args.size, args.res, nw, crop, cropw, nw),
+                       "pixels_per_step": px},
+            "cpu_baseline": {"value": val, "unit": "Gpix/s", "cores": nw, "kind": "port",
+                             "sample": "every pixel of the %dx%d workload per step: %d concurrent single-thread oracle "
+                                       "iterations (numpy/scipy restatement of the reference, plot path off) on its %dx%d "
+                                       "crops; %d host cores available" % (args.size, args.size, nw, crop, cropw, cores)},
             "e2e": {"value": val, "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
