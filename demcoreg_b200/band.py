@@ -125,6 +125,42 @@ class BandAligner(object):
         self.pending_dz = []        # z shifts of the source not yet written into the band (applied by the front kernel)
         self.sticky_flags = 0       # engines that declined for this raster stay switched off (ITER_RADIX_BINS / _ONLY)
         self.keep_aspect = keep_aspect
+        # how the halos were last filled: grow_halo() repeats it with the deeper halo.  Set by whoever exchanges
+        # (exchange_halos -> torch.distributed, exchange_halos_native -> the library's communicator, VirtualGroup)
+        self._exchange = None
+        self.halo_regrown = 0
+
+    def needed_halo(self, gr, gs):
+        """Halo rows the current geometry needs: output row i reads source rows i + iy0 - 2 .. i + iy0 + 3 of each raster
+        (4-tap cubic footprint + one Horn ring), and the bands are laid out on the raster row numbers -- the relative row
+        offset of the two rasters (the cumulative y shift in pixels) comes on top.  Same value on every rank."""
+        return abs(int(gs.iy0) - int(gr.iy0)) + 4
+
+    def grow_halo(self, new_halo):
+        """Re-lay the three band rasters with a deeper halo and fetch the new halo rows from the neighbours (collective: every
+        rank sees the same geometry and grows in the same iteration).  The owned rows are kept as they are (with every z
+        shift applied so far)."""
+        torch = self.torch
+        if self._exchange is None:
+            raise _lib.DcrError("row-band halo of %d rows too small for the current shift and no exchange registered" % self.halo)
+        own = self.r1 - self.r0
+        if self.world > 1 and new_halo > min(band_rows(self.height, r, self.world)[1] - band_rows(self.height, r, self.world)[0]
+                                             for r in range(self.world)):
+            raise _lib.DcrError("shift of %d rows exceeds a whole band (%d rows): use fewer ranks" % (new_halo, own))
+        self.flush_z()
+        a, b = self.owned
+        for name in ("ref", "src", "mask"):
+            old = getattr(self, name)
+            if old is None:
+                continue
+            nb, owned = make_band(old.data[a:b], self.r0, self.r1, self.height, new_halo, old.gt, old.ndv, torch)
+            nb.halo = new_halo
+            setattr(self, name, nb)
+            new_owned = owned
+        self.owned = new_owned
+        self.halo = new_halo
+        self.halo_regrown += 1
+        self._exchange(self)
 
     def bands(self):
         return [b for b in (self.ref, self.src, self.mask) if b is not None]
@@ -134,6 +170,7 @@ class BandAligner(object):
         self.flush_z()
         for b in self.bands():
             exchange_halos(b, self.owned, self.rank, self.world, group)
+        self._exchange = lambda al: al.exchange_halos(group)
 
     # ---- one iteration, phase by phase -------------------------------------------------------
     def begin_iteration(self, remove_outliers=True, max_dz=100, slope_lim=(0.1, 40)):
@@ -142,6 +179,11 @@ class BandAligner(object):
         grid, gr, gs = _lib.Grid(), _lib.WarpGeom(), _lib.WarpGeom()
         dr, dsrc = self.ref.desc(), self.src.desc()
         _lib.check(L.dcr_plan_intersection(C.byref(dr), C.byref(dsrc), 0.0, C.byref(grid), C.byref(gr), C.byref(gs)))
+        need = self.needed_halo(gr, gs)
+        if need > self.halo and self.world > 1:
+            # the cumulative shift has outgrown the halo: deeper halo, rows re-exchanged with the neighbours
+            self.grow_halo(max(2 * self.halo, need + 8))
+            dr, dsrc = self.ref.desc(), self.src.desc()
         H, W = grid.height, grid.width
         rb = min(max(self.r0 - gr.iy0, 0), H)
         re = min(max(self.r1 - gr.iy0, 0), H)
@@ -325,6 +367,7 @@ def exchange_halos_native(al, comm):
     torch = al.torch
     L = _lib.lib()
     al.flush_z()
+    al._exchange = lambda x: exchange_halos_native(x, comm)
     a, b = al.owned
     for band in al.bands():
         nrows = int(band.data.shape[0])
@@ -352,9 +395,14 @@ class VirtualGroup(object):
                                           H, gt, ndv, r, world, halo))
         self.exchange_halos()
 
-    def exchange_halos(self):
+    def exchange_halos(self, only=None):
         """In-process stand-in for the NCCL halo exchange: copy the neighbours' owned rows into the halos."""
+        for al in self.ranks:
+            al.flush_z()             # (under NCCL every rank flushes inside the collective exchange)
         for r, al in enumerate(self.ranks):
+            if only is not None and al is not only:
+                continue
+            al._exchange = lambda x: self.exchange_halos(only=x)
             for name in ("ref", "src", "mask"):
                 b = getattr(al, name)
                 if b is None:

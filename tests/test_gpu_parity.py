@@ -1247,3 +1247,30 @@ def test_row_band_one_pass_selects_and_radix_rerun(cuda):
         if not quant:
             assert res[0].select_engine == 1, "the one-pass selects should have run on the bands"
         print("band selects: quantised=%s engine=%d" % (quant, res[0].select_engine))
+
+
+def test_row_band_halo_grows_with_the_shift(cuda):
+    """A cumulative y shift larger than the halo: the bands are re-laid with a deeper halo and the new rows fetched from the
+    neighbours (round 1 returned -5 "re-exchange halos" and nothing re-exchanged); results equal the single-GPU iteration."""
+    from demcoreg_b200 import engine, band
+    from demcoreg_b200.raster import MaskSource
+    p = _pair(n=1024, res=8.0, nodata_frac=0.01, static_mask_frac=0.3)
+    gt_s = _shifted_gt(p['gt'], 13.7, -101.3)      # 12.7 rows: beyond the 8-row halo
+    ms = MaskSource(p['mask'], p['gt'])
+    r1, grid, bufs = engine.nuth_iteration(_gds(p, 'ref'), _gds(p, 'src', gt_s), ms, radix_only=True)
+    vg = band.VirtualGroup(p['ref'], p['src'], p['mask'], p['gt'], p['ndv'], 3, halo=8)
+    for al in vg.ranks:
+        al.src.gt = gt_s
+    res = vg.iteration()
+    assert all(al.halo_regrown == 1 and al.halo >= 16 for al in vg.ranks)
+    for r in res:
+        for f in ("count_base", "count_final", "count_slope", "med1", "nmad1", "dz_med", "med_dh", "med_slope"):
+            assert getattr(r, f) == getattr(r1, f), (f, getattr(r, f), getattr(r1, f))
+        assert list(r.nuth.bin_count) == list(r1.nuth.bin_count)
+        assert abs(r.dx - r1.dx) < 1e-9 and abs(r.dy - r1.dy) < 1e-9
+    rows = 0
+    for al in vg.ranks:
+        rb, re = al.args.row_begin, al.args.row_end
+        assert np.array_equal(al.bufs[0].cpu().numpy(), bufs.dh[rb:re].cpu().numpy())
+        rows += re - rb
+    assert rows == grid.height
