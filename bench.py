@@ -42,16 +42,17 @@ STAGE_INFO = [
     # + mask bits 1 + bin code 2 = 11 B/px: the aspect raster is replaced by its 1-degree bin code)
     ("front end: front_fast_kernel (interior tiles) + front_kernel (listed tiles): TMA-staged warp + dh + masks + Horn + bin codes",
      21.0),
-    ("bsel_* x2 on the main stream: median + MAD of dh (slope median on a side stream)", 10.0),
+    ("msel_*: median + MAD of dh in ONE pass with two brackets (slope median on a side stream)", 10.0),
     ("mask_update_kernel (MAD filter + y + moments of y, fused)", 9.0 + 4.0),
     ("(side streams only: scan/compress/dz median, med_dh)", 0.0),
     ("nuth_moments_reduce/final", 0.0),
     ("fb_pass* (bin count + exact bin medians; shares bandwidth with the side streams)", 12.0),
     ("result copy", 0.0),
 ]
-# front 2 (fast + listed tiles) + 5 selections x (sample gather, bracket, main, 2 refine) 25 + mask update 1 +
-# scan/stride/compress 3 + moments 2 + bins 6 = 39 (+ one z-shift fold every 4th step)
-KERNELS_PER_STEP = 2 + 5 * 5 + 1 + 3 + 2 + 6
+# front 2 (fast + listed tiles) + median & MAD in one pass 10 (2 sample, bracket, main, 2 refine, rekey, find, 2 refine) +
+# 3 selections x (sample gather, bracket, main, 2 refine) 15 + mask update 1 + scan/stride/compress 3 + moments 2 + bins 6 = 39
+# (+ one z-shift fold every 4th step)
+KERNELS_PER_STEP = 2 + 10 + 3 * 5 + 1 + 3 + 2 + 6
 
 
 def peaks():

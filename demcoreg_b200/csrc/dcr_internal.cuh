@@ -76,7 +76,7 @@ struct BselState {
     long long count;
     double gamma;
     float v_lo, v_hi, result;
-    int pad;
+    float chat;                      // dual median + MAD select: the centre estimate the streaming pass measures |x - chat| from
     float* publish;                  // optional device scalar that receives `result` as soon as it is final
 };
 unsigned dcr_bsel_cap(long long n);
@@ -88,6 +88,10 @@ void dcr_bsel_buffers(void* scratch, long long n_max, unsigned** hist, unsigned*
 int dcr_bsel_sample_enqueue(const SelView& v, double q_percent, BselState* st, void* scratch, long long n_max, cudaStream_t s,
                             float* publish = nullptr);
 int dcr_bsel_refine_enqueue(BselState* st, void* scratch, long long n_max, cudaStream_t s);
+// median of v AND median of |v - that median| (filtlib.mad_fltr <- dem_align.py:46) with ONE streaming pass over the data:
+// results into st0->result / st1->result (published to publish0 / publish1); a declined bracket sets st?->fallback
+int dcr_msel_enqueue(const SelView& v, BselState* st0, BselState* st1, void* scratch0, void* scratch1, long long n_max,
+                     cudaStream_t s, float* publish0, float* publish1);
 // row-band mode: the selection cut into dcr_bsel_band_nsub() sub-phases with all-reduced hand-offs (see dcr_bsel.cu)
 int dcr_bsel_band_nsub(void);
 int dcr_bsel_band_phase(const SelView& v, double q_percent, BselState* st, void* scratch, long long n_max, int rank, int nranks,

@@ -1250,9 +1250,17 @@ static int iteration_enqueue(const dcr_front_args* front, int remove_outliers, i
     v.x = front->dh; v.m = front->maskbits; v.n = n;
     if (remove_outliers) {
         v.reject = DCR_M_BASE | DCR_M_MAXDZ; v.transform = 0;
-        if ((rc = iter_select(v, 0, w, n, use_bsel, s))) return rc;
-        v.transform = 1; v.center_ptr = &d->selres[0];
-        if ((rc = iter_select(v, 1, w, n, use_bsel, s))) return rc;
+        static const bool msel_on = getenv("DCR_NO_MSEL") == nullptr;   // (DCR_NO_MSEL: the two dependent selections, for A/B)
+        if (use_bsel && msel_on && n > 262144) {
+            // median and MAD of dh (filtlib.mad_fltr) with ONE pass over the data: dcr_msel_enqueue
+            if ((rc = dcr_msel_enqueue(v, &d->bsel[0], &d->bsel[1], w.bsel_scratch, w.bsel_scratch3, n, s, &d->selres[0],
+                                       &d->selres[1])))
+                return rc;
+        } else {
+            if ((rc = iter_select(v, 0, w, n, use_bsel, s))) return rc;
+            v.transform = 1; v.center_ptr = &d->selres[0];
+            if ((rc = iter_select(v, 1, w, n, use_bsel, s))) return rc;
+        }
     }
     STAGE_MARK(2);
     mask_update_kernel<true><<<(unsigned)((nch + MU_KCH - 1) / MU_KCH), 256, 0, s>>>(
