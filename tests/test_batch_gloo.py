@@ -102,3 +102,28 @@ def test_band_rows_partition():
         rows = [band.band_rows(H, r, G) for r in range(G)]
         assert rows[0][0] == 0 and rows[-1][1] == H
         assert all(rows[k][1] == rows[k + 1][0] for k in range(G - 1))
+
+
+def test_band_halo_bookkeeping_is_consistent_between_neighbours():
+    """Row bands, host logic only: what rank r sends to a neighbour is exactly what that neighbour's halo holds, for every
+    split (the native exchange, dcr_band_exchange_halos, pairs one ncclSend with one ncclRecv of the same size)."""
+    from demcoreg_b200 import band
+
+    class FakeBand(object):
+        def __init__(self, height, halo):
+            self.height, self.halo = height, halo
+    for height, world, halo in ((1000, 2, 16), (1001, 3, 8), (32768, 8, 64), (257, 4, 100), (64, 8, 3)):
+        rows = [band.band_rows(height, r, world) for r in range(world)]
+        assert rows[0][0] == 0 and rows[-1][1] == height and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+        b = FakeBand(height, halo)
+        for r in range(world):
+            r0, r1 = rows[r]
+            top = r0 - max(0, r0 - halo)                    # rows this rank stores above / below its own
+            bot = min(height, r1 + halo) - r1
+            if r > 0:        # the neighbour above sends its bottom rows: as many as our top halo holds
+                assert band._halo_of_neighbour(b, r, world, below=False) == top
+                # and we send it our top rows: as many as ITS bottom halo holds
+                pr0, pr1 = rows[r - 1]
+                assert band._halo_of_neighbour(b, r - 1, world, below=True) == min(height, pr1 + halo) - pr1
+            if r < world - 1:
+                assert band._halo_of_neighbour(b, r, world, below=True) == bot
