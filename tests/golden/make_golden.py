@@ -61,6 +61,31 @@ def horn_and_loop(n=96, name="horn_loop_96.npz"):
     print(name, "loop", out['dx'], out['dy'], out['dz'], out['n_iter'], "tilt ptp", float(np.ptp(out['tiltcorr']['vals'])))
 
 
+def resample_and_successive(name="resample_successive_64.npz"):
+    """Unequal-resolution memwarp_multi (2:1 pair, nodata, source origin off the reference lattice; res = max and min) and
+    successive_med of a masked difference map with row / column biases."""
+    from oracle import coreglib as ocl
+    p = synth.make_pair(n=64, res=8.0, seed=20260999, nodata_frac=0.02)
+    q = synth.make_pair(n=128, res=4.0, seed=20260999, nodata_frac=0.02)
+    gt8 = p['gt']
+    gt4 = (q['gt'][0] + 5.3, 4.0, 0.0, q['gt'][3] - 9.1, 0.0, -4.0)
+    a, b = pg.MemDataset(p['ref'], gt8, p['ndv']), pg.MemDataset(q['src'], gt4, q['ndv'])
+    mx = pg.memwarp_multi([a, b], res='max')
+    mn = pg.memwarp_multi([a, b], res='min')
+    rng = np.random.default_rng(5)
+    yy, xx = np.mgrid[0:90, 0:110]
+    d = (rng.normal(size=(90, 110)) + 0.5 * np.sin(yy / 9.0) + 0.3 * np.cos(xx / 7.0)).astype(np.float32)
+    m = rng.random((90, 110)) < 0.2
+    sm = ocl.successive_med(np.ma.array(d, mask=m), min_axes_count=40)
+    np.savez_compressed(os.path.join(HERE, name), ref=p['ref'], src=q['src'], gt_ref=np.array(gt8), gt_src=np.array(gt4),
+                        max_ref=mx[0].array, max_src=mx[1].array, max_gt=np.array(mx[1].GetGeoTransform()),
+                        min_ref=mn[0].array, min_src=mn[1].array, min_gt=np.array(mn[0].GetGeoTransform()),
+                        sm_in=d, sm_mask=m, sm_out=sm[0].filled(0).astype(np.float32), sm_first=np.ma.filled(sm[1], 0).astype(np.float32),
+                        sm_second=np.ma.filled(sm[2], 0).astype(np.float32))
+    print(name, mx[1].array.shape, mn[0].array.shape)
+
+
 if __name__ == "__main__":
+    resample_and_successive()
     nuth_iter()
     horn_and_loop()

@@ -1274,3 +1274,24 @@ def test_row_band_halo_grows_with_the_shift(cuda):
         assert np.array_equal(al.bufs[0].cpu().numpy(), bufs.dh[rb:re].cpu().numpy())
         rows += re - rb
     assert rows == grid.height
+
+
+def test_golden_resample_and_successive_med(cuda):
+    """The CUDA path against the third regression fixture: unequal-resolution memwarp_multi (res = max and min) and
+    coreglib.successive_med, bit for bit."""
+    import os
+    from demcoreg_b200 import coreglib, engine
+    from demcoreg_b200.raster import Raster
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resample_successive_64.npz"))
+
+    def pair():
+        return [Raster(z['ref'], tuple(z['gt_ref']), -9999.0), Raster(z['src'], tuple(z['gt_src']), -9999.0)]
+    mx = engine.memwarp_multi(pair(), res='max')
+    mn = engine.memwarp_multi(pair(), res='min')
+    assert np.array_equal(mx[0].numpy(), z['max_ref']) and np.array_equal(mx[1].numpy(), z['max_src'])
+    assert np.array_equal(mn[0].numpy(), z['min_ref']) and np.array_equal(mn[1].numpy(), z['min_src'])
+    np.testing.assert_allclose(mx[1].gt, z['max_gt'], rtol=0, atol=1e-9)
+    sm = coreglib.successive_med(np.ma.array(z['sm_in'], mask=z['sm_mask']), min_axes_count=40)
+    assert np.array_equal(sm[0].filled(0).astype(np.float32), z['sm_out'])
+    assert np.array_equal(np.ma.filled(sm[1], 0).astype(np.float32), z['sm_first'])
+    assert np.array_equal(np.ma.filled(sm[2], 0).astype(np.float32), z['sm_second'])
